@@ -1,0 +1,86 @@
+"""ctypes binding of ``libhoc_b200.so`` (C ABI declared in ``include/hoc_b200.h``).
+
+The library is the product: there is no CPU or PyTorch fallback.  If it has not been built
+(``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C handobjectconsist_b200/csrc``)
+every operator of this package raises ``HocLibraryError``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhoc_b200.so")
+
+HOC_LAYOUT_RAW = 0
+HOC_LAYOUT_IMAGE = 1
+
+_c_float_p = ctypes.c_void_p  # device pointers travel as integers
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_sz = ctypes.c_size_t
+
+
+class HocLibraryError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/hoc_b200.h one to one
+SIGNATURES = {
+    "hoc_abi_version": (_i, []),
+    "hoc_last_error": (ctypes.c_char_p, []),
+    "hoc_raster_forward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _vp,
+                                 _vp, _sz, _vp]),
+    "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hoc_warp_photo_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "hoc_warp": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
+    "hoc_warp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
+    "hoc_occlusion_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+}
+
+_LIB = None
+
+
+def lib():
+    """Load the shared library once; raise loudly when it is missing."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise HocLibraryError(
+                f"{LIB_PATH} not found: the sm_100a kernels are not built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+                "There is no CPU / PyTorch fallback for this path.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = L
+    return _LIB
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().hoc_last_error().decode("utf-8", "replace")
+        raise HocLibraryError(f"{what} failed with code {code}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors, what="operator"):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise TypeError(f"{what} supports only cuda Tensors (got a {t.device} tensor); "
+                            "this package has no CPU path")

@@ -1,0 +1,53 @@
+/* hoc_common.cuh -- small helpers shared by the sm_100a kernels of libhoc_b200.so. */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hoc_b200.h"
+
+#define HOC_FULL_MASK 0xffffffffu
+
+/* Raised by the C-ABI entry points; text is fetched with hoc_last_error(). */
+void hoc_set_error(const char *fmt, ...);
+
+#define HOC_CHECK_ARG(cond, ...)        \
+    do {                                \
+        if (!(cond)) {                  \
+            hoc_set_error(__VA_ARGS__); \
+            return HOC_ERR_INVALID_ARG; \
+        }                               \
+    } while (0)
+
+#define HOC_CHECK_LAUNCH(name)                                                    \
+    do {                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                     \
+        if (e__ != cudaSuccess) {                                                 \
+            hoc_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+            return HOC_ERR_CUDA;                                                  \
+        }                                                                         \
+    } while (0)
+
+/* Address helpers for the two output layouts (see include/hoc_b200.h):
+ *   HOC_LAYOUT_RAW      rgb [B,S,S,3], planes [B,S,S], raster row order (row 0 = bottom)
+ *   HOC_LAYOUT_IMAGE    rgb [B,3,S,S], planes [B,S,S], rows flipped (row 0 = top)            */
+__device__ __forceinline__ long hoc_plane_off(int layout, int S, int b, int yi, int xi)
+{
+    const int row = (layout == HOC_LAYOUT_IMAGE) ? (S - 1 - yi) : yi;
+    return ((long)b * S + row) * S + xi;
+}
+
+__device__ __forceinline__ long hoc_rgb_off(int layout, int S, int b, int yi, int xi, int c)
+{
+    if (layout == HOC_LAYOUT_IMAGE)
+        return (((long)b * 3 + c) * S + (S - 1 - yi)) * S + xi;
+    return (((long)b * S + yi) * S + xi) * 3 + c;
+}
+
+__device__ __forceinline__ float hoc_warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(HOC_FULL_MASK, v, o);
+    return v;
+}

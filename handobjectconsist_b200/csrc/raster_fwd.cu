@@ -1,0 +1,300 @@
+/*
+ * raster_fwd.cu -- rasterizer forward for sm_100a.
+ *
+ * Replaces forward_face_index_map + forward_texture_sampling of `neural_renderer.cuda.rasterize`
+ * (bound at /root/reference/meshreg/neurender/rasterize.py:202-215,232-243) and the wrapper ops
+ * around them (buffer fills :58-85, background :252-260, alpha :246-249, clones :118-124, and
+ * the permute + row-flip gathers of rasterize_rgbad :417-428).
+ *
+ * The reference walks ALL faces from every pixel (B*S*S*F triangle tests).  Here the work is
+ * proportional to what is actually covered:
+ *
+ *   pass 1  hoc_raster_zbuf_kernel      face-parallel.  A warp owns 32 faces: each lane sets up
+ *           its own face (cull, barycentric matrix, clipped pixel bounding box), the records
+ *           are staged in shared memory and the warp then sweeps the bounding box of one face
+ *           at a time with 32 pixels in flight.  Every pixel that passes the three edge tests
+ *           and the near/far test does ONE 64-bit atomicMin on a packed (depth, face) key:
+ *           the minimum is the nearest depth and, among exact ties, the lowest face index --
+ *           the result of the reference's in-order strict `<` loop.  The key buffer (8 B/px)
+ *           stays in L2.
+ *   pass 2  hoc_raster_resolve_kernel   pixel-parallel, one thread per pixel, streaming: reads
+ *           the key, recomputes weights/depth of the winning face with the same functions
+ *           (bit-identical), samples the texture cube, blends the background and writes every
+ *           requested map once, coalesced, directly in the layout the caller returns.
+ */
+#include "hoc_common.cuh"
+#include "raster_math.h"
+
+#define ZB_WARPS 8
+#define ZB_THREADS (ZB_WARPS * 32)
+#define ZB_REC 24 /* floats per staged face record: 9 face + 9 inverse + 4 bbox (+2 pad) */
+
+__global__ void __launch_bounds__(ZB_THREADS)
+hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__restrict__ zbuf, int F, int S,
+                       float near_, float far_)
+{
+    extern __shared__ float s_centre[]; /* [S] pixel-centre NDC coordinate of index i */
+    __shared__ float s_rec[ZB_WARPS][32][ZB_REC];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+
+    for (int i = threadIdx.x; i < S; i += ZB_THREADS)
+        s_centre[i] = hoc_pix_centre(i, S);
+
+    const int fi = blockIdx.x * ZB_THREADS + warp * 32 + lane;
+    bool active = false;
+    if (fi < F) {
+        float f[9];
+        const float *src = faces + ((long)b * F + fi) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            f[k] = __ldg(src + k);
+        if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
+            /* pixel bounding box: inside  =>  pmin <= xi <= pmax in exact arithmetic;
+             * half a pixel of slack absorbs fp32 rounding of the edge tests. */
+            const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
+            const float pxmax = hoc_ndc_to_pix(fmaxf(f[0], fmaxf(f[3], f[6])), S);
+            const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
+            const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
+            const float fS1 = (float)(S - 1);
+            const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
+            const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
+            const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
+            const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
+            if (x_lo <= x_hi && y_lo <= y_hi) {
+                active = true;
+                float inv[9];
+                hoc_face_inv(f, S, inv);
+                float *rec = s_rec[warp][lane];
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    rec[k] = f[k];
+                    rec[9 + k] = inv[k];
+                }
+                rec[18] = x_lo;
+                rec[19] = y_lo;
+                rec[20] = x_hi - x_lo + 1.0f;
+                rec[21] = y_hi - y_lo + 1.0f;
+            }
+        }
+    }
+    __syncthreads(); /* s_centre ready; also orders s_rec writes */
+
+    unsigned todo = __ballot_sync(HOC_FULL_MASK, active);
+    unsigned long long *zb = zbuf + (long)b * S * S;
+    const int f_base = blockIdx.x * ZB_THREADS + warp * 32;
+    while (todo) {
+        const int j = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float *rec = s_rec[warp][j];
+        float f[9], inv[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            f[k] = rec[k];
+            inv[k] = rec[9 + k];
+        }
+        const int x0 = (int)rec[18], y0 = (int)rec[19];
+        const int bw = (int)rec[20], bh = (int)rec[21];
+        const int n = bw * bh;
+        const unsigned fidx = (unsigned)(f_base + j);
+        for (int p = lane; p < n; p += 32) {
+            const int yy = p / bw;
+            const int xi = x0 + (p - yy * bw);
+            const int yi = y0 + yy;
+            if (!hoc_pixel_inside(f, s_centre[xi], s_centre[yi]))
+                continue;
+            float w[3], zp;
+            if (!hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp))
+                continue;
+            if (!(zp < far_)) /* NaN depth never wins a `<` comparison in the reference */
+                continue;
+            const unsigned long long key = ((unsigned long long)hoc_float_order(zp) << 32) | fidx;
+            atomicMin(zb + (long)yi * S + xi, key);
+        }
+    }
+}
+
+#define RS_THREADS 256
+
+/* Stage `n_per` floats per thread in shared memory and store them as one contiguous, coalesced
+ * run of RS_THREADS*n_per floats starting at dst (bounded by `limit` floats). */
+template <int N_PER>
+__device__ __forceinline__ void hoc_store_interleaved(float *smem, const float *vals, float *dst, long limit)
+{
+#pragma unroll
+    for (int k = 0; k < N_PER; k++)
+        smem[threadIdx.x * N_PER + k] = vals[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N_PER; k++) {
+        const int o = k * RS_THREADS + threadIdx.x;
+        if (o < limit)
+            dst[o] = smem[o];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
+                          const unsigned long long *__restrict__ zbuf, int F, int S, int ts, float near_, float far_,
+                          float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int layout,
+                          float *__restrict__ rgb, float *__restrict__ alpha, float *__restrict__ depth,
+                          int32_t *__restrict__ face_index_map, float *__restrict__ weight_map,
+                          float *__restrict__ face_inv_map)
+{
+    __shared__ float s_stage[RS_THREADS * 9];
+
+    const int b = blockIdx.y;
+    const long npix = (long)S * S;
+    const long pix0 = (long)blockIdx.x * RS_THREADS;
+    const long pix = pix0 + threadIdx.x;
+    const bool in_range = pix < npix;
+
+    int fidx = -1;
+    int yi = 0, xi = 0;
+    float w[3] = {0.f, 0.f, 0.f};
+    float inv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float zp = far_;
+    float col[3];
+    if (bg_dev != nullptr) {
+        col[0] = __ldg(bg_dev + b * 3 + 0);
+        col[1] = __ldg(bg_dev + b * 3 + 1);
+        col[2] = __ldg(bg_dev + b * 3 + 2);
+    } else {
+        col[0] = bg0;
+        col[1] = bg1;
+        col[2] = bg2;
+    }
+
+    if (in_range) {
+        yi = (int)(pix / S);
+        xi = (int)(pix - (long)yi * S);
+        const unsigned long long key = zbuf[(long)b * npix + pix];
+        fidx = (int)(unsigned)(key & 0xffffffffull);
+        if (fidx >= 0) {
+            float f[9];
+            const float *src = faces + ((long)b * F + fidx) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                f[k] = __ldg(src + k);
+            hoc_face_inv(f, S, inv);
+            hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+            if (rgb != nullptr) {
+                const float *tex = textures + ((long)b * F + fidx) * ts * ts * ts * 3;
+                float tf[3];
+                int ti[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
+                    ti[k] = hoc_tex_cell(t, ts);
+                    tf[k] = t - (float)ti[k];
+                }
+                float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int pn = 0; pn < 8; pn++) {
+                    float ww = 1.0f;
+                    int isc = 0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (((pn >> k) & 1) == 0) {
+                            ww *= 1.0f - tf[k];
+                            isc = isc * ts + ti[k];
+                        } else {
+                            ww *= tf[k];
+                            isc = isc * ts + ti[k] + 1;
+                        }
+                    }
+                    /* a tap with zero weight may point one past the cube when ts == 1 */
+                    if (ts == 1)
+                        isc = 0;
+#pragma unroll
+                    for (int c = 0; c < 3; c++)
+                        acc[c] += ww * __ldg(tex + isc * 3 + c);
+                }
+                col[0] = acc[0];
+                col[1] = acc[1];
+                col[2] = acc[2];
+            }
+        }
+    }
+
+    /* ---- stores ---- */
+    if (in_range) {
+        face_index_map[(long)b * npix + pix] = fidx;
+        const long po = hoc_plane_off(layout, S, b, yi, xi);
+        if (alpha != nullptr)
+            alpha[po] = (fidx >= 0) ? 1.0f : 0.0f;
+        if (depth != nullptr)
+            depth[po] = zp;
+        if (rgb != nullptr && layout == HOC_LAYOUT_IMAGE) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                rgb[hoc_rgb_off(layout, S, b, yi, xi, c)] = col[c];
+        }
+    }
+    const long left = npix - pix0; /* pixels of this block that exist */
+    if (rgb != nullptr && layout == HOC_LAYOUT_RAW)
+        hoc_store_interleaved<3>(s_stage, col, rgb + ((long)b * npix + pix0) * 3, left * 3);
+    if (weight_map != nullptr)
+        hoc_store_interleaved<3>(s_stage, w, weight_map + ((long)b * npix + pix0) * 3, left * 3);
+    if (face_inv_map != nullptr)
+        hoc_store_interleaved<9>(s_stage, inv, face_inv_map + ((long)b * npix + pix0) * 9, left * 9);
+}
+
+extern "C" size_t hoc_raster_forward_workspace_bytes(int B, int F, int S)
+{
+    (void)F;
+    if (B <= 0 || S <= 0)
+        return 0;
+    return (size_t)B * S * S * sizeof(unsigned long long);
+}
+
+extern "C" int hoc_raster_forward(const float *faces, const float *textures, int B, int F, int S, int ts,
+                                  float near_, float far_, float eps, const float *background_host,
+                                  const float *background_dev, int layout, float *rgb, float *alpha, float *depth,
+                                  int32_t *face_index_map, float *weight_map, float *face_inv_map, void *workspace,
+                                  size_t workspace_bytes, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && F >= 0, "hoc_raster_forward: negative batch (%d) or face count (%d)", B, F);
+    HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_forward: image_size %d outside [1, 2048]", S);
+    HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_forward: bad layout %d", layout);
+    HOC_CHECK_ARG(face_index_map != nullptr, "hoc_raster_forward: face_index_map is required");
+    HOC_CHECK_ARG(rgb == nullptr || (textures != nullptr && ts >= 1),
+                  "hoc_raster_forward: rgb requested without textures / texture_size");
+    HOC_CHECK_ARG(B == 0 || F == 0 || faces != nullptr, "hoc_raster_forward: faces is NULL");
+    HOC_CHECK_ARG(B <= 65535, "hoc_raster_forward: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    const size_t need = hoc_raster_forward_workspace_bytes(B, F, S);
+    if (workspace == nullptr || workspace_bytes < need) {
+        hoc_set_error("hoc_raster_forward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+        return HOC_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long *zbuf = (unsigned long long *)workspace;
+    cudaError_t e = cudaMemsetAsync(zbuf, 0xff, need, st);
+    if (e != cudaSuccess) {
+        hoc_set_error("hoc_raster_forward: memset failed: %s", cudaGetErrorString(e));
+        return HOC_ERR_CUDA;
+    }
+    if (F > 0) {
+        dim3 grid((F + ZB_THREADS - 1) / ZB_THREADS, B);
+        hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_);
+        HOC_CHECK_LAUNCH("hoc_raster_zbuf_kernel");
+    }
+    float bg[3] = {0.f, 0.f, 0.f};
+    if (background_host != nullptr) {
+        bg[0] = background_host[0];
+        bg[1] = background_host[1];
+        bg[2] = background_host[2];
+    }
+    const long npix = (long)S * S;
+    dim3 grid2((unsigned)((npix + RS_THREADS - 1) / RS_THREADS), B);
+    hoc_raster_resolve_kernel<<<grid2, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps, bg[0],
+                                                           bg[1], bg[2], background_dev, layout, rgb, alpha, depth,
+                                                           face_index_map, weight_map, face_inv_map);
+    HOC_CHECK_LAUNCH("hoc_raster_resolve_kernel");
+    return HOC_OK;
+}

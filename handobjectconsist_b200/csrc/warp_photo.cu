@@ -1,0 +1,502 @@
+/*
+ * warp_photo.cu -- flow-guided image warp, masked photometric L1 and the forward-backward
+ * occlusion check for sm_100a.
+ *
+ * Replaces, for the reference's meshreg/warping/imgflowarp.py:
+ *   warp()                 :31-55   (meshgrid + flow -> normalise -> grid_sample x2 -> threshold)
+ *   pair_consist()         :58-115  (4 warps, valid-mask algebra, 2x criterion)
+ *   get_occlusion_mask()   :118-146 + occlusion_mask_from_warped_grid() :149-172
+ * and meshreg/optim/pyramidloss.py:56-58 + lossutils.py:1-8 (|a-b|, masked mean per sample).
+ *
+ * The reference runs ~60 ATen launches per frame pair here (CPU-built meshgrids, eight
+ * grid_sample calls, ~40 element-wise kernels).  One direction of pair_consist is ONE kernel:
+ * flow -> sampling position -> 4 taps of the image and of the jitter mask -> in-bounds mask ->
+ * valid mask -> |warp - target| -> per-sample (sum, count), block-reduced with warp shuffles.
+ *
+ * Bit compatibility.  The reference's masks contain two exact floating-point tests
+ * (`mask >= 0.99999` and `warped_jitter == 1`) on sums of four bilinear weights, so the kernel
+ * reproduces the arithmetic of the ATen CUDA kernels the reference runs on, operation by
+ * operation (this file is compiled with -fmad=false; the FMAs ATen's nvcc build contracts are
+ * written explicitly as __fmaf_rn):
+ *   x_norm  = ((x + flow) * 2) * (1 / (W-1)) - 1          torch mul / div-by-scalar / sub kernels
+ *   ix      = fma(x_norm + 1, W, -1) * 0.5                grid_sampler_unnormalize, align_corners=False (F6 quirk)
+ *   weights = (ix_se - ix) * (iy_se - iy) ...             in tap order nw, ne, sw, se
+ *   value   = fma(v_se, se, fma(v_sw, sw, fma(v_ne, ne, v_nw * nw)))  over the in-bounds taps
+ */
+#include "hoc_common.cuh"
+
+struct HocTaps {
+    float ix, iy;
+    int x0, y0;          /* north-west tap */
+    float nw, ne, sw, se;
+    bool b_nw, b_ne, b_sw, b_se; /* tap inside the image */
+};
+
+__device__ __forceinline__ float hoc_norm_coord(int p, float flow, int size)
+{
+    const float inv = __fdiv_rn(1.0f, (float)max(size - 1, 1));
+    const float v = __fadd_rn((float)p, flow);
+    return __fadd_rn(__fmul_rn(__fmul_rn(2.0f, v), inv), -1.0f);
+}
+
+__device__ __forceinline__ float hoc_unnormalize(float coord, int size)
+{
+    /* ((coord + 1.f) * size - 1) / 2 with the multiply-subtract contracted */
+    return __fmul_rn(__fmaf_rn(__fadd_rn(coord, 1.0f), (float)size, -1.0f), 0.5f);
+}
+
+__device__ __forceinline__ void hoc_bilinear_taps(int x, int y, float fx, float fy, int H, int W, HocTaps &T)
+{
+    const float ix = hoc_unnormalize(hoc_norm_coord(x, fx, W), W);
+    const float iy = hoc_unnormalize(hoc_norm_coord(y, fy, H), H);
+    T.ix = ix;
+    T.iy = iy;
+    /* clamp before the conversion only to keep it defined; far-away taps are out of bounds anyway */
+    const float fxn = floorf(fminf(fmaxf(ix, -4.0f), (float)W + 4.0f));
+    const float fyn = floorf(fminf(fmaxf(iy, -4.0f), (float)H + 4.0f));
+    const int x0 = (int)fxn, y0 = (int)fyn;
+    T.x0 = x0;
+    T.y0 = y0;
+    const float x_nw = (float)x0, y_nw = (float)y0;
+    const float x_se = (float)(x0 + 1), y_se = (float)(y0 + 1);
+    T.nw = __fmul_rn(__fsub_rn(x_se, ix), __fsub_rn(y_se, iy));
+    T.ne = __fmul_rn(__fsub_rn(ix, x_nw), __fsub_rn(y_se, iy));
+    T.sw = __fmul_rn(__fsub_rn(x_se, ix), __fsub_rn(iy, y_nw));
+    T.se = __fmul_rn(__fsub_rn(ix, x_nw), __fsub_rn(iy, y_nw));
+    const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
+    const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
+    /* NaN coordinates: every comparison above is false in ATen as well -> no tap */
+    const bool ok = (ix == ix) && (iy == iy);
+    T.b_nw = ok && xin0 && yin0;
+    T.b_ne = ok && xin1 && yin0;
+    T.b_sw = ok && xin0 && yin1;
+    T.b_se = ok && xin1 && yin1;
+}
+
+/* grid_sample of an all-ones image: sum of the in-bounds weights in tap order. */
+__device__ __forceinline__ float hoc_ones_sample(const HocTaps &T)
+{
+    float acc = 0.0f;
+    if (T.b_nw) acc = __fmaf_rn(1.0f, T.nw, acc);
+    if (T.b_ne) acc = __fmaf_rn(1.0f, T.ne, acc);
+    if (T.b_sw) acc = __fmaf_rn(1.0f, T.sw, acc);
+    if (T.b_se) acc = __fmaf_rn(1.0f, T.se, acc);
+    return acc;
+}
+
+/* grid_sample of one channel plane (zeros padding). */
+__device__ __forceinline__ float hoc_plane_sample(const float *__restrict__ plane, int W, const HocTaps &T)
+{
+    float acc = 0.0f;
+    const float *p = plane + (long)T.y0 * W + T.x0;
+    if (T.b_nw) acc = __fmaf_rn(__ldg(p), T.nw, acc);
+    if (T.b_ne) acc = __fmaf_rn(__ldg(p + 1), T.ne, acc);
+    if (T.b_sw) acc = __fmaf_rn(__ldg(p + W), T.sw, acc);
+    if (T.b_se) acc = __fmaf_rn(__ldg(p + W + 1), T.se, acc);
+    return acc;
+}
+
+/* mask[mask < thresh] = 0; mask[mask > 0] = 1 */
+__device__ __forceinline__ float hoc_threshold_mask(float m, float thresh)
+{
+    if (m < thresh)
+        m = 0.0f;
+    if (m > 0.0f)
+        m = 1.0f;
+    return m;
+}
+
+#define WP_THREADS 256
+#define WP_MAXC 4
+
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__restrict__ target,
+                              const float *__restrict__ flow, const float *__restrict__ jitter, int C, int Cj, int H,
+                              int W, float thresh, float *__restrict__ warped, float *__restrict__ warp_mask,
+                              uint8_t *__restrict__ valid_mask, float *__restrict__ diff, double *__restrict__ sums)
+{
+    __shared__ float s_sum[WP_THREADS / 32];
+    __shared__ float s_cnt[WP_THREADS / 32];
+    const int b = blockIdx.y;
+    const long npix = (long)H * W;
+    const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
+    float my_sum = 0.0f, my_cnt = 0.0f;
+    if (pix < npix) {
+        const int y = (int)(pix / W);
+        const int x = (int)(pix - (long)y * W);
+        const float2 fl = *reinterpret_cast<const float2 *>(flow + ((long)b * npix + pix) * 2);
+        HocTaps T;
+        hoc_bilinear_taps(x, y, fl.x, fl.y, H, W, T);
+        const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
+        /* jitter mask: warped with the same flow, tested for == 1; plus == 1 at the pixel itself */
+        bool valid = false;
+        float wm[WP_MAXC];
+#pragma unroll
+        for (int c = 0; c < WP_MAXC; c++)
+            wm[c] = m;
+        if (jitter != nullptr) {
+            for (int c = 0; c < Cj && c < WP_MAXC; c++) {
+                const float wj = __fmul_rn(hoc_plane_sample(jitter + ((long)b * Cj + c) * npix, W, T), m);
+                wm[c] = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
+            }
+            if (Cj == 1) {
+#pragma unroll
+                for (int c = 1; c < WP_MAXC; c++)
+                    wm[c] = wm[0];
+            }
+            valid = (wm[0] != 0.0f) && !(fl.x == 0.0f) && (__ldg(jitter + (long)b * Cj * npix + pix) == 1.0f);
+        } else {
+            valid = (m != 0.0f) && !(fl.x == 0.0f);
+        }
+        if (valid_mask != nullptr)
+            valid_mask[(long)b * npix + pix] = valid ? 1 : 0;
+        for (int c = 0; c < C; c++) {
+            const long o = ((long)b * C + c) * npix + pix;
+            const float v = __fmul_rn(hoc_plane_sample(src + ((long)b * C + c) * npix, W, T), m);
+            const float d = fabsf(__fsub_rn(v, target[o]));
+            if (warped != nullptr)
+                warped[o] = v;
+            if (diff != nullptr)
+                diff[o] = d;
+            if (warp_mask != nullptr)
+                warp_mask[o] = wm[c < WP_MAXC ? c : 0];
+            if (valid) {
+                my_sum += d;
+                my_cnt += 1.0f;
+            }
+        }
+    }
+    my_sum = hoc_warp_sum(my_sum);
+    my_cnt = hoc_warp_sum(my_cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_sum[warp] = my_sum;
+        s_cnt[warp] = my_cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float a = (lane < WP_THREADS / 32) ? s_sum[lane] : 0.0f;
+        float n = (lane < WP_THREADS / 32) ? s_cnt[lane] : 0.0f;
+        a = hoc_warp_sum(a);
+        n = hoc_warp_sum(n);
+        if (lane == 0 && n > 0.0f) {
+            atomicAdd(&sums[2 * b + 0], (double)a);
+            atomicAdd(&sums[2 * b + 1], (double)n);
+        }
+    }
+}
+
+/* d loss[b] / d flow.  loss[b] = sum_valid |warp - target| / max(count, 1); the thresholded masks
+ * carry no gradient, so only the bilinear taps of `src` depend on the flow. */
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_warp_photo_backward_kernel(const float *__restrict__ src, const float *__restrict__ target,
+                               const float *__restrict__ flow, const uint8_t *__restrict__ valid_mask,
+                               const double *__restrict__ sums, const float *__restrict__ grad_loss, int C, int H,
+                               int W, float thresh, float *__restrict__ grad_flow)
+{
+    const int b = blockIdx.y;
+    const long npix = (long)H * W;
+    const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
+    if (pix >= npix)
+        return;
+    float2 g = make_float2(0.0f, 0.0f);
+    if (valid_mask[(long)b * npix + pix]) {
+        const int y = (int)(pix / W);
+        const int x = (int)(pix - (long)y * W);
+        const float2 fl = *reinterpret_cast<const float2 *>(flow + ((long)b * npix + pix) * 2);
+        HocTaps T;
+        hoc_bilinear_taps(x, y, fl.x, fl.y, H, W, T);
+        const float cnt = (float)sums[2 * b + 1];
+        const float scale = grad_loss[b] / fmaxf(cnt, 1.0f);
+        const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
+        float gix = 0.0f, giy = 0.0f;
+        for (int c = 0; c < C; c++) {
+            const float *plane = src + ((long)b * C + c) * npix;
+            const float v = hoc_plane_sample(plane, W, T); /* valid => in-bounds mask is 1 */
+            const float d = v - target[((long)b * C + c) * npix + pix];
+            const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+            const float go = scale * sgn;
+            const float *p = plane + (long)T.y0 * W + T.x0;
+            if (T.b_nw) {
+                const float v0 = __ldg(p);
+                gix -= v0 * (y_se - T.iy) * go;
+                giy -= v0 * (x_se - T.ix) * go;
+            }
+            if (T.b_ne) {
+                const float v1 = __ldg(p + 1);
+                gix += v1 * (y_se - T.iy) * go;
+                giy -= v1 * (T.ix - x_nw) * go;
+            }
+            if (T.b_sw) {
+                const float v2 = __ldg(p + W);
+                gix -= v2 * (T.iy - y_nw) * go;
+                giy += v2 * (x_se - T.ix) * go;
+            }
+            if (T.b_se) {
+                const float v3 = __ldg(p + W + 1);
+                gix += v3 * (T.iy - y_nw) * go;
+                giy += v3 * (T.ix - x_nw) * go;
+            }
+        }
+        /* d ix / d x_norm = W / 2 ; d x_norm / d flow = 2 / (W - 1) */
+        g.x = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
+        g.y = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
+    }
+    *reinterpret_cast<float2 *>(grad_flow + ((long)b * npix + pix) * 2) = g;
+}
+
+/* Plain warp(): out = grid_sample(x, grid(flow)) * mask.  flow is NCHW [B,2,H,W] like the
+ * reference's argument.  mode 0 = bilinear, 1 = nearest. */
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, int C, int H, int W, float thresh,
+                int mode, float *__restrict__ out, float *__restrict__ mask)
+{
+    const int b = blockIdx.y;
+    const long npix = (long)H * W;
+    const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
+    if (pix >= npix)
+        return;
+    const int py = (int)(pix / W);
+    const int px = (int)(pix - (long)py * W);
+    const float fx = flow[((long)b * 2 + 0) * npix + pix];
+    const float fy = flow[((long)b * 2 + 1) * npix + pix];
+    if (mode == 0) {
+        HocTaps T;
+        hoc_bilinear_taps(px, py, fx, fy, H, W, T);
+        const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
+        for (int c = 0; c < C; c++) {
+            const long o = ((long)b * C + c) * npix + pix;
+            out[o] = __fmul_rn(hoc_plane_sample(x + ((long)b * C + c) * npix, W, T), m);
+            if (mask != nullptr)
+                mask[o] = m;
+        }
+    } else {
+        const float ix = hoc_unnormalize(hoc_norm_coord(px, fx, W), W);
+        const float iy = hoc_unnormalize(hoc_norm_coord(py, fy, H), H);
+        const float rx = nearbyintf(fminf(fmaxf(ix, -4.0f), (float)W + 4.0f));
+        const float ry = nearbyintf(fminf(fmaxf(iy, -4.0f), (float)H + 4.0f));
+        const int sx = (int)rx, sy = (int)ry;
+        const bool inb = (ix == ix) && (iy == iy) && sx >= 0 && sx < W && sy >= 0 && sy < H;
+        const float m = hoc_threshold_mask(inb ? 1.0f : 0.0f, thresh);
+        for (int c = 0; c < C; c++) {
+            const long o = ((long)b * C + c) * npix + pix;
+            const float v = inb ? __ldg(x + ((long)b * C + c) * npix + (long)sy * W + sx) : 0.0f;
+            out[o] = __fmul_rn(v, m);
+            if (mask != nullptr)
+                mask[o] = m;
+        }
+    }
+}
+
+
+/* Gradient of warp() (bilinear) w.r.t. its NCHW flow: grad_out is the gradient of `out * mask`. */
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_warp_backward_kernel(const float *__restrict__ x, const float *__restrict__ flow,
+                         const float *__restrict__ grad_out, int C, int H, int W, float thresh,
+                         float *__restrict__ grad_flow)
+{
+    const int b = blockIdx.y;
+    const long npix = (long)H * W;
+    const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
+    if (pix >= npix)
+        return;
+    const int py = (int)(pix / W);
+    const int px = (int)(pix - (long)py * W);
+    HocTaps T;
+    hoc_bilinear_taps(px, py, flow[((long)b * 2 + 0) * npix + pix], flow[((long)b * 2 + 1) * npix + pix], H, W, T);
+    const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
+    float gix = 0.0f, giy = 0.0f;
+    if (m != 0.0f) {
+        const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
+        for (int c = 0; c < C; c++) {
+            const float go = grad_out[((long)b * C + c) * npix + pix] * m;
+            const float *p = x + ((long)b * C + c) * npix + (long)T.y0 * W + T.x0;
+            if (T.b_nw) {
+                const float v0 = __ldg(p);
+                gix -= v0 * (y_se - T.iy) * go;
+                giy -= v0 * (x_se - T.ix) * go;
+            }
+            if (T.b_ne) {
+                const float v1 = __ldg(p + 1);
+                gix += v1 * (y_se - T.iy) * go;
+                giy -= v1 * (T.ix - x_nw) * go;
+            }
+            if (T.b_sw) {
+                const float v2 = __ldg(p + W);
+                gix -= v2 * (T.iy - y_nw) * go;
+                giy += v2 * (x_se - T.ix) * go;
+            }
+            if (T.b_se) {
+                const float v3 = __ldg(p + W + 1);
+                gix += v3 * (T.iy - y_nw) * go;
+                giy += v3 * (T.ix - x_nw) * go;
+            }
+        }
+    }
+    grad_flow[((long)b * 2 + 0) * npix + pix] = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
+    grad_flow[((long)b * 2 + 1) * npix + pix] = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
+}
+
+/* Nearest-mode source pixel of warp(., flow) at (px, py); false when it falls outside. */
+__device__ __forceinline__ bool hoc_nearest_src(int px, int py, float fx, float fy, int H, int W, int *sx, int *sy)
+{
+    const float ix = hoc_unnormalize(hoc_norm_coord(px, fx, W), W);
+    const float iy = hoc_unnormalize(hoc_norm_coord(py, fy, H), H);
+    const float rx = nearbyintf(fminf(fmaxf(ix, -4.0f), (float)W + 4.0f));
+    const float ry = nearbyintf(fminf(fmaxf(iy, -4.0f), (float)H + 4.0f));
+    *sx = (int)rx;
+    *sy = (int)ry;
+    return (ix == ix) && (iy == iy) && *sx >= 0 && *sx < W && *sy >= 0 && *sy < H;
+}
+
+/* Forward-backward consistency check.  The reference warps a 4-channel tensor
+ * [x/W, y/H, mask, mask] there and back with nearest sampling; the grid values are just
+ * coordinates, so the double warp is two dependent gathers per pixel:
+ *   r --flow_a(r)--> s --flow_b(s)--> q,   occl(r) = M * [ |(q/WH * k - r/WH) * M| < thresh ]
+ * with k = m_a(r) in(s) m_b(s) in(q) and M = m_a(r) * (k * m_a(q)).  blockIdx.z selects the
+ * direction (0: a = frame 1, 1: a = frame 2). */
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_occlusion_kernel(const float *__restrict__ mask1, const float *__restrict__ mask2,
+                     const float *__restrict__ flow12, const float *__restrict__ flow21, int Cf, int H, int W,
+                     float distance_thresh, float *__restrict__ occl1, float *__restrict__ occl2)
+{
+    const int b = blockIdx.y;
+    const long npix = (long)H * W;
+    const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
+    if (pix >= npix)
+        return;
+    const bool second = blockIdx.z != 0;
+    const float *ma = (second ? mask2 : mask1) + (long)b * npix;
+    const float *mb = (second ? mask1 : mask2) + (long)b * npix;
+    const float *fa = (second ? flow21 : flow12) + (long)b * Cf * npix;
+    const float *fb = (second ? flow12 : flow21) + (long)b * Cf * npix;
+    float *out = (second ? occl2 : occl1) + (long)b * npix;
+
+    const int ry = (int)(pix / W);
+    const int rx = (int)(pix - (long)ry * W);
+    const float inv_w = __fdiv_rn(1.0f, (float)W), inv_h = __fdiv_rn(1.0f, (float)H);
+    const float m_r = ma[pix];
+    /* second warp (evaluated at r): source s in the once-warped grid */
+    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f;
+    int sx, sy;
+    if (hoc_nearest_src(rx, ry, fa[pix], fa[npix + pix], H, W, &sx, &sy)) {
+        const long sp = (long)sy * W + sx;
+        /* first warp (evaluated at s): source q in the coordinate grid of frame a */
+        float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+        int qx, qy;
+        if (hoc_nearest_src(sx, sy, fb[sp], fb[npix + sp], H, W, &qx, &qy)) {
+            g0 = __fmul_rn((float)qx, inv_w);
+            g1 = __fmul_rn((float)qy, inv_h);
+            g2 = ma[(long)qy * W + qx];
+        }
+        const float m_s = mb[sp];
+        w0 = __fmul_rn(g0, m_s);
+        w1 = __fmul_rn(g1, m_s);
+        w2 = __fmul_rn(g2, m_s);
+    }
+    w0 = __fmul_rn(w0, m_r);
+    w1 = __fmul_rn(w1, m_r);
+    w2 = __fmul_rn(w2, m_r);
+    const float M = __fmul_rn(m_r, w2);
+    const float dx = __fmul_rn(__fsub_rn(w0, __fmul_rn((float)rx, inv_w)), M);
+    const float dy = __fmul_rn(__fsub_rn(w1, __fmul_rn((float)ry, inv_h)), M);
+    const float displ = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    out[pix] = __fmul_rn(M, (displ < distance_thresh) ? 1.0f : 0.0f);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" int hoc_warp_photo_forward(const float *src, const float *target, const float *flow, const float *jitter,
+                                      int B, int C, int Cj, int H, int W, float thresh, float *warped,
+                                      float *warp_mask, uint8_t *valid_mask, float *diff, double *sums, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp_photo_forward: bad shape B=%d C=%d H=%d W=%d", B, C,
+                  H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_warp_photo_forward: batch %d exceeds 65535", B);
+    HOC_CHECK_ARG(jitter == nullptr || Cj == 1 || Cj == C, "hoc_warp_photo_forward: jitter channels %d vs %d", Cj, C);
+    HOC_CHECK_ARG(warp_mask == nullptr || C <= WP_MAXC, "hoc_warp_photo_forward: warp_mask supports C <= %d", WP_MAXC);
+    HOC_CHECK_ARG(sums != nullptr, "hoc_warp_photo_forward: sums is required");
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(src && target && flow, "hoc_warp_photo_forward: NULL input");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, st);
+    if (e != cudaSuccess) {
+        hoc_set_error("hoc_warp_photo_forward: memset failed: %s", cudaGetErrorString(e));
+        return HOC_ERR_CUDA;
+    }
+    const long npix = (long)H * W;
+    dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
+    hoc_warp_photo_forward_kernel<<<grid, WP_THREADS, 0, st>>>(src, target, flow, jitter, C, Cj, H, W, thresh, warped,
+                                                               warp_mask, valid_mask, diff, sums);
+    HOC_CHECK_LAUNCH("hoc_warp_photo_forward_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_warp_photo_backward(const float *src, const float *target, const float *flow,
+                                       const uint8_t *valid_mask, const double *sums, const float *grad_loss, int B,
+                                       int C, int H, int W, float thresh, float *grad_flow, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp_photo_backward: bad shape B=%d C=%d H=%d W=%d", B,
+                  C, H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_warp_photo_backward: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(src && target && flow && valid_mask && sums && grad_loss && grad_flow,
+                  "hoc_warp_photo_backward: NULL argument");
+    const long npix = (long)H * W;
+    dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
+    hoc_warp_photo_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
+        src, target, flow, valid_mask, sums, grad_loss, C, H, W, thresh, grad_flow);
+    HOC_CHECK_LAUNCH("hoc_warp_photo_backward_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_warp(const float *x, const float *flow_nchw, int B, int C, int H, int W, float thresh, int mode,
+                        float *out, float *mask, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    HOC_CHECK_ARG(mode == 0 || mode == 1, "hoc_warp: mode %d (0 bilinear, 1 nearest)", mode);
+    HOC_CHECK_ARG(B <= 65535, "hoc_warp: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(x && flow_nchw && out, "hoc_warp: NULL argument");
+    const long npix = (long)H * W;
+    dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
+    hoc_warp_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, C, H, W, thresh, mode, out, mask);
+    HOC_CHECK_LAUNCH("hoc_warp_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_warp_backward(const float *x, const float *flow_nchw, const float *grad_out, int B, int C, int H,
+                                 int W, float thresh, float *grad_flow_nchw, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp_backward: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_warp_backward: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(x && flow_nchw && grad_out && grad_flow_nchw, "hoc_warp_backward: NULL argument");
+    const long npix = (long)H * W;
+    dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
+    hoc_warp_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, grad_out, C, H, W, thresh,
+                                                                            grad_flow_nchw);
+    HOC_CHECK_LAUNCH("hoc_warp_backward_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow12, const float *flow21,
+                                  int B, int Cf, int H, int W, float distance_thresh, float *occl1, float *occl2,
+                                  void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && Cf >= 2 && H >= 1 && W >= 1, "hoc_occlusion_mask: bad shape B=%d Cf=%d H=%d W=%d", B, Cf,
+                  H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_occlusion_mask: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(mask1 && mask2 && flow12 && flow21 && occl1 && occl2, "hoc_occlusion_mask: NULL argument");
+    const long npix = (long)H * W;
+    dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B, 2);
+    hoc_occlusion_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(mask1, mask2, flow12, flow21, Cf, H, W,
+                                                                        distance_thresh, occl1, occl2);
+    HOC_CHECK_LAUNCH("hoc_occlusion_kernel");
+    return HOC_OK;
+}

@@ -1,0 +1,138 @@
+/*
+ * hoc_b200.h -- C ABI of libhoc_b200.so: the sm_100a (B200) kernels behind the
+ * differentiable-render + photometric-consistency path of hassony2/handobjectconsist.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes, no torch / C++ types; every pointer is a DEVICE pointer to a
+ *     contiguous buffer owned by the caller unless the parameter name ends in `_host`;
+ *   - fp32 data, int32 index maps, int64 not used;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); launches
+ *     are asynchronous and allocate nothing -- scratch memory is caller-provided, its size
+ *     comes from the matching `*_workspace_bytes` query;
+ *   - return value: HOC_OK (0) or a negative HOC_ERR_* code; `hoc_last_error()` returns a
+ *     thread-local human-readable message.  No exception crosses the boundary.
+ *
+ * Each entry point names the reference interface it replaces.  The reference's rasterizer
+ * kernels live in the third-party extension `neural_renderer.cuda.rasterize` and are bound at
+ * /root/reference/meshreg/neurender/rasterize.py:202,232,269,290,306; the warp / loss path is
+ * /root/reference/meshreg/warping/imgflowarp.py and meshreg/optim/{pyramidloss,lossutils}.py;
+ * MANO skinning is `manopth.manolayer.ManoLayer.forward`, bound at
+ * /root/reference/meshreg/models/manobranch.py:70-85,101-145.
+ */
+#ifndef HOC_B200_H
+#define HOC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOC_ABI_VERSION 1
+
+#define HOC_OK 0
+#define HOC_ERR_INVALID_ARG (-1)
+#define HOC_ERR_CUDA (-2)
+#define HOC_ERR_WORKSPACE (-3)
+
+/* Output layouts of the rasterizer.
+ * RAW   = what RasterizeFunction.forward returns (rasterize.py:118-125): rgb [B,S,S,3],
+ *         alpha/depth [B,S,S], raster row order (row 0 is the image BOTTOM).
+ * IMAGE = what rasterize_rgbad returns after its permute + row flip (rasterize.py:417-428):
+ *         rgb [B,3,S,S], alpha/depth [B,S,S] with row 0 at the image TOP.  Writing this layout
+ *         directly removes the three gather kernels of the reference.
+ * face_index_map / weight_map / face_inv_map are never flipped (rasterize.py:443-445). */
+#define HOC_LAYOUT_RAW 0
+#define HOC_LAYOUT_IMAGE 1
+
+int hoc_abi_version(void);
+const char *hoc_last_error(void);
+
+/* ---- rasterizer forward -------------------------------------------------------------------
+ * Replaces forward_face_index_map + forward_texture_sampling (rasterize.py:202-215,232-243)
+ * plus the wrapper's fill_/background/alpha/clone/flip ops (rasterize.py:58-125,246-260,417-428).
+ *   faces      [B,F,3,3]  x,y in NDC (y up), z metric
+ *   textures   [B,F,ts,ts,ts,3] or NULL (then rgb must be NULL)
+ *   background_host  3 floats (host), used when background_dev is NULL
+ *   background_dev   [B,3] per-sample background or NULL
+ *   rgb / alpha / depth            outputs in `layout`, any of them may be NULL (not produced)
+ *   face_index_map [B,S,S] int32   (-1 = background)                        never NULL
+ *   weight_map     [B,S,S,3]       may be NULL
+ *   face_inv_map   [B,S,S,3,3]     may be NULL (the reference fills it only when return_depth)
+ *   workspace      hoc_raster_forward_workspace_bytes(B,F,S) bytes
+ */
+size_t hoc_raster_forward_workspace_bytes(int B, int F, int S);
+int hoc_raster_forward(const float *faces, const float *textures, int B, int F, int S, int ts, float near_,
+                       float far_, float eps, const float *background_host, const float *background_dev,
+                       int layout, float *rgb, float *alpha, float *depth, int32_t *face_index_map,
+                       float *weight_map, float *face_inv_map, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* ---- rasterizer backward ------------------------------------------------------------------
+ * Replaces backward_pixel_map + backward_textures + backward_depth_map
+ * (rasterize.py:269-281,290-297,306-315) and the zero-fills around them (rasterize.py:151-181).
+ * One launch; every face's gradient is produced by exactly one warp (no float atomics, results
+ * are deterministic run to run).
+ *   faces, textures, face_index_map   forward inputs / output
+ *   rgb              forward output in `layout` (NULL when the forward had no rgb)
+ *   grad_rgb / grad_alpha / grad_depth  incoming gradients in `layout`; NULL = all zeros / that
+ *                    output was not requested in the forward
+ *   use_alpha        1 when the forward produced alpha (return_alpha), else 0
+ *   grad_faces       [B,F,3,3] out (fully overwritten) or NULL to skip the geometry gradient
+ *   grad_textures    [B,F,ts,ts,ts,3] out (fully overwritten) or NULL to skip it
+ */
+size_t hoc_raster_backward_workspace_bytes(int B, int F, int S);
+int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
+                        const float *rgb, const float *grad_rgb, const float *grad_alpha,
+                        const float *grad_depth, int B, int F, int S, int ts, float near_, float far_,
+                        float eps, int layout, int use_alpha, float *grad_faces, float *grad_textures,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- flow-guided warp + masked photometric L1 ---------------------------------------------
+ * ONE direction of pair_consist (imgflowarp.py:80-107) in one launch: warp(src, flow),
+ * warp(jitter, flow), the valid-mask algebra and criterion.compute / batch_masked_mean_loss
+ * (pyramidloss.py:56-58, lossutils.py:1-8).  For the reference's direction 1 the caller passes
+ * src = image_ref, target = image, flow = recons_flow[1], jitter = jitter_mask; for direction 2
+ * src = image, target = image_ref, flow = recons_flow[0], jitter = jitter_mask_ref.
+ *   src, target [B,C,H,W];  flow [B,H,W,2] pixel offsets;  jitter [B,Cj,H,W] (Cj == 1 or C) or NULL
+ * outputs (any may be NULL except sums):
+ *   warped     [B,C,H,W]  warp(src, flow), already multiplied by its in-bounds mask
+ *   warp_mask  [B,C,H,W]  in-bounds mask * (warp(jitter, flow) == 1)
+ *   valid_mask [B,H,W] uint8   warp_mask[:,0] & (flow[...,0] != 0) & (jitter[:,0] == 1)
+ *   diff       [B,C,H,W]  |warped - target|
+ *   sums       [B,2] DOUBLE (sum of diff over valid elements, number of valid elements);
+ *              zero-filled by the call;  loss[b] = sums[b,0] / max(sums[b,1], 1)
+ */
+int hoc_warp_photo_forward(const float *src, const float *target, const float *flow, const float *jitter, int B,
+                           int C, int Cj, int H, int W, float thresh, float *warped, float *warp_mask,
+                           uint8_t *valid_mask, float *diff, double *sums, void *stream);
+
+/* Gradient of loss[b] w.r.t. flow, the only differentiable input (imgflowarp.py:52-53: the
+ * thresholded masks carry no gradient).  grad_loss [B]; valid_mask / sums from the forward;
+ * grad_flow [B,H,W,2] out (fully overwritten). */
+int hoc_warp_photo_backward(const float *src, const float *target, const float *flow, const uint8_t *valid_mask,
+                            const double *sums, const float *grad_loss, int B, int C, int H, int W, float thresh,
+                            float *grad_flow, void *stream);
+
+/* Plain warp (imgflowarp.py:31-55).  flow_nchw [B,2,H,W]; mode 0 bilinear, 1 nearest.
+ *   out [B,C,H,W] = grid_sample(x) * mask;  mask [B,C,H,W] or NULL. */
+int hoc_warp(const float *x, const float *flow_nchw, int B, int C, int H, int W, float thresh, int mode,
+             float *out, float *mask, void *stream);
+
+/* Gradient of hoc_warp (bilinear) w.r.t. the flow: grad_out [B,C,H,W] is the gradient of the masked
+ * output; grad_flow_nchw [B,2,H,W] out (fully overwritten).  The sampled image gets no gradient. */
+int hoc_warp_backward(const float *x, const float *flow_nchw, const float *grad_out, int B, int C, int H, int W,
+                      float thresh, float *grad_flow_nchw, void *stream);
+
+/* Forward-backward occlusion check on rendered flows (get_occlusion_mask +
+ * occlusion_mask_from_warped_grid, imgflowarp.py:118-172), both directions in one launch.
+ *   mask1, mask2 [B,H,W];  flow12, flow21 [B,Cf,H,W] (first two channels used);
+ *   occl1, occl2 [B,H,W] out. */
+int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow12, const float *flow21, int B,
+                       int Cf, int H, int W, float distance_thresh, float *occl1, float *occl2, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOC_B200_H */

@@ -1,0 +1,330 @@
+/*
+ * tests/emul/raster_emul.cpp -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Serial host emulation of the ALGORITHM of csrc/raster_fwd.cu and csrc/raster_bwd.cu: same
+ * per-face / per-pixel functions (it includes the product header raster_math.h), same work
+ * decomposition (face-parallel z-buffer with a packed (depth, face) min key, pixel resolve,
+ * face-owned gradient gather, clipped outward scans), with loops where the kernels have lanes.
+ * It lets the CPU test-suite check the restructured algorithm against the oracle's literal
+ * restatement of the reference without a GPU.  It is never loaded by the product.
+ * Build: g++ -O2 -ffp-contract=off -shared -fPIC (tests/test_host_emulation.py).
+ */
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../handobjectconsist_b200/csrc/raster_math.h"
+
+static bool face_bbox(const float *f, int S, int *x0, int *y0, int *bw, int *bh)
+{
+    const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
+    const float pxmax = hoc_ndc_to_pix(fmaxf(f[0], fmaxf(f[3], f[6])), S);
+    const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
+    const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
+    const float fS1 = (float)(S - 1);
+    const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
+    const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
+    const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
+    const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
+    if (!(x_lo <= x_hi && y_lo <= y_hi))
+        return false;
+    *x0 = (int)x_lo;
+    *y0 = (int)y_lo;
+    *bw = (int)(x_hi - x_lo + 1.0f);
+    *bh = (int)(y_hi - y_lo + 1.0f);
+    return true;
+}
+
+static inline long plane_off(int layout, int S, int b, int yi, int xi)
+{
+    const int row = layout ? (S - 1 - yi) : yi;
+    return ((long)b * S + row) * S + xi;
+}
+static inline long rgb_off(int layout, int S, int b, int yi, int xi, int c)
+{
+    if (layout)
+        return (((long)b * 3 + c) * S + (S - 1 - yi)) * S + xi;
+    return (((long)b * S + yi) * S + xi) * 3 + c;
+}
+
+extern "C" void emul_raster_forward(const float *faces, const float *textures, int B, int F, int S, int ts, float near_,
+                                    float far_, float eps, const float *bg, int layout, float *rgb, float *alpha,
+                                    float *depth, int32_t *face_index_map, float *weight_map, float *face_inv_map)
+{
+    std::vector<uint64_t> zbuf((size_t)B * S * S, ~0ull);
+    std::vector<float> centre(S);
+    for (int i = 0; i < S; i++)
+        centre[i] = hoc_pix_centre(i, S);
+    for (int b = 0; b < B; b++)
+        for (int fi = 0; fi < F; fi++) {
+            const float *f = faces + ((long)b * F + fi) * 9;
+            if (!hoc_face_xy_finite(f) || hoc_face_back(f))
+                continue;
+            int x0, y0, bw, bh;
+            if (!face_bbox(f, S, &x0, &y0, &bw, &bh))
+                continue;
+            float inv[9];
+            hoc_face_inv(f, S, inv);
+            for (int p = 0; p < bw * bh; p++) {
+                const int yy = p / bw, xi = x0 + (p - yy * bw), yi = y0 + yy;
+                if (!hoc_pixel_inside(f, centre[xi], centre[yi]))
+                    continue;
+                float w[3], zp;
+                if (!hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp))
+                    continue;
+                if (!(zp < far_))
+                    continue;
+                const uint64_t key = ((uint64_t)hoc_float_order(zp) << 32) | (uint32_t)fi;
+                uint64_t &z = zbuf[((size_t)b * S + yi) * S + xi];
+                z = std::min(z, key);
+            }
+        }
+    for (int b = 0; b < B; b++)
+        for (int yi = 0; yi < S; yi++)
+            for (int xi = 0; xi < S; xi++) {
+                const long pix = ((long)b * S + yi) * S + xi;
+                const int fidx = (int)(uint32_t)(zbuf[pix] & 0xffffffffull);
+                float w[3] = {0, 0, 0}, inv[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, zp = far_;
+                float col[3] = {bg[0], bg[1], bg[2]};
+                if (fidx >= 0) {
+                    const float *f = faces + ((long)b * F + fidx) * 9;
+                    hoc_face_inv(f, S, inv);
+                    hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+                    if (rgb) {
+                        const float *tex = textures + ((long)b * F + fidx) * ts * ts * ts * 3;
+                        float tf[3];
+                        int ti[3];
+                        for (int k = 0; k < 3; k++) {
+                            const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
+                            ti[k] = hoc_tex_cell(t, ts);
+                            tf[k] = t - (float)ti[k];
+                        }
+                        float acc[3] = {0, 0, 0};
+                        for (int pn = 0; pn < 8; pn++) {
+                            float ww = 1.0f;
+                            int isc = 0;
+                            for (int k = 0; k < 3; k++) {
+                                if (((pn >> k) & 1) == 0) {
+                                    ww *= 1.0f - tf[k];
+                                    isc = isc * ts + ti[k];
+                                } else {
+                                    ww *= tf[k];
+                                    isc = isc * ts + ti[k] + 1;
+                                }
+                            }
+                            if (ts == 1)
+                                isc = 0;
+                            for (int c = 0; c < 3; c++)
+                                acc[c] += ww * tex[isc * 3 + c];
+                        }
+                        for (int c = 0; c < 3; c++)
+                            col[c] = acc[c];
+                    }
+                }
+                face_index_map[pix] = fidx;
+                if (alpha)
+                    alpha[plane_off(layout, S, b, yi, xi)] = fidx >= 0 ? 1.0f : 0.0f;
+                if (depth)
+                    depth[plane_off(layout, S, b, yi, xi)] = zp;
+                if (rgb)
+                    for (int c = 0; c < 3; c++)
+                        rgb[rgb_off(layout, S, b, yi, xi, c)] = col[c];
+                if (weight_map)
+                    for (int k = 0; k < 3; k++)
+                        weight_map[pix * 3 + k] = w[k];
+                if (face_inv_map)
+                    for (int k = 0; k < 9; k++)
+                        face_inv_map[pix * 9 + k] = inv[k];
+            }
+}
+
+struct Maps {
+    const int32_t *idx;
+    const float *rgb, *g_rgb, *g_alpha;
+    int S, layout, b;
+    bool use_alpha, use_rgb;
+};
+
+static void load_I(const Maps &M, int xi, int yi, float *I)
+{
+    I[0] = I[1] = I[2] = I[3] = 0.0f;
+    if (M.use_alpha)
+        I[0] = M.idx[(long)yi * M.S + xi] >= 0 ? 1.0f : 0.0f;
+    if (M.use_rgb)
+        for (int k = 0; k < 3; k++)
+            I[1 + k] = M.rgb[rgb_off(M.layout, M.S, M.b, yi, xi, k)];
+}
+
+static float delta_at(const Maps &M, int xi, int yi, const float *Iref)
+{
+    float d = 0.0f;
+    if (M.use_alpha) {
+        const float a = M.idx[(long)yi * M.S + xi] >= 0 ? 1.0f : 0.0f;
+        d += (a - Iref[0]) * M.g_alpha[plane_off(M.layout, M.S, M.b, yi, xi)];
+    }
+    if (M.use_rgb)
+        for (int k = 0; k < 3; k++) {
+            const long o = rgb_off(M.layout, M.S, M.b, yi, xi, k);
+            d += (M.rgb[o] - Iref[1 + k]) * M.g_rgb[o];
+        }
+    return d;
+}
+
+extern "C" void emul_raster_backward(const float *faces, const int32_t *face_index_map, const float *rgb,
+                                     const float *g_rgb, const float *g_alpha, const float *g_depth, int B, int F,
+                                     int S, int ts, float near_, float far_, float eps, int layout, int use_alpha,
+                                     float *grad_faces, float *grad_textures)
+{
+    const int tex_n = ts * ts * ts * 3;
+    /* extent pre-pass */
+    std::vector<int> ext((size_t)B * 4 * S);
+    for (int b = 0; b < B; b++) {
+        int *e = ext.data() + (size_t)b * 4 * S;
+        for (int i = 0; i < S; i++) {
+            e[0 * S + i] = e[2 * S + i] = 0x7f7f7f7f;
+            e[1 * S + i] = e[3 * S + i] = -1;
+        }
+        for (int yi = 0; yi < S; yi++)
+            for (int xi = 0; xi < S; xi++) {
+                bool nz = false;
+                if (g_rgb)
+                    for (int c = 0; c < 3; c++)
+                        nz = nz || !(g_rgb[rgb_off(layout, S, b, yi, xi, c)] == 0.0f);
+                if (g_alpha && use_alpha)
+                    nz = nz || !(g_alpha[plane_off(layout, S, b, yi, xi)] == 0.0f);
+                if (nz) {
+                    e[0 * S + yi] = std::min(e[0 * S + yi], xi);
+                    e[1 * S + yi] = std::max(e[1 * S + yi], xi);
+                    e[2 * S + xi] = std::min(e[2 * S + xi], yi);
+                    e[3 * S + xi] = std::max(e[3 * S + xi], yi);
+                }
+            }
+    }
+    for (int b = 0; b < B; b++)
+        for (int fi = 0; fi < F; fi++) {
+            const float *f = faces + ((long)b * F + fi) * 9;
+            float *gt = grad_textures ? grad_textures + ((long)b * F + fi) * tex_n : nullptr;
+            float *gf = grad_faces ? grad_faces + ((long)b * F + fi) * 9 : nullptr;
+            if (gf)
+                for (int k = 0; k < 9; k++)
+                    gf[k] = 0.0f;
+            if (gt)
+                for (int k = 0; k < tex_n; k++)
+                    gt[k] = 0.0f;
+            if (!hoc_face_xy_finite(f) || hoc_face_back(f))
+                continue;
+            const int32_t *idx = face_index_map + (long)b * S * S;
+            float inv[9];
+            hoc_face_inv(f, S, inv);
+            const bool want_tex = gt && g_rgb, want_depth = gf && g_depth;
+            float acc_d[3] = {0, 0, 0};
+            bool any_hit = false;
+            int x0, y0, bw, bh;
+            if ((want_tex || want_depth) && face_bbox(f, S, &x0, &y0, &bw, &bh)) {
+                for (int p = 0; p < bw * bh; p++) {
+                    const int yy = p / bw, xi = x0 + (p - yy * bw), yi = y0 + yy;
+                    if (idx[(long)yi * S + xi] != fi)
+                        continue;
+                    any_hit = true;
+                    float w[3], zp;
+                    hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+                    if (want_depth) {
+                        const float gz = g_depth[plane_off(layout, S, b, yi, xi)] * zp * zp;
+                        for (int k = 0; k < 3; k++)
+                            acc_d[k] += gz * w[k];
+                    }
+                    if (want_tex) {
+                        float tf[3];
+                        int ti[3];
+                        for (int k = 0; k < 3; k++) {
+                            const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
+                            ti[k] = hoc_tex_cell(t, ts);
+                            tf[k] = t - (float)ti[k];
+                        }
+                        for (int pn = 0; pn < 8; pn++) {
+                            float ww = 1.0f;
+                            int isc = 0;
+                            for (int k = 0; k < 3; k++) {
+                                if (((pn >> k) & 1) == 0) {
+                                    ww *= 1.0f - tf[k];
+                                    isc = isc * ts + ti[k];
+                                } else {
+                                    ww *= tf[k];
+                                    isc = isc * ts + ti[k] + 1;
+                                }
+                            }
+                            if (ts == 1)
+                                isc = 0;
+                            for (int c = 0; c < 3; c++)
+                                gt[isc * 3 + c] += ww * g_rgb[rgb_off(layout, S, b, yi, xi, c)];
+                        }
+                    }
+                }
+            }
+            if (!gf)
+                continue;
+            if (want_depth && any_hit) {
+                float tmp[2];
+                for (int l = 0; l < 2; l++)
+                    tmp[l] = inv[l] / f[2] + inv[3 + l] / f[5] + inv[6 + l] / f[8];
+                for (int k = 0; k < 3; k++) {
+                    const float zk = f[3 * k + 2];
+                    gf[3 * k + 2] = acc_d[k] / (zk * zk);
+                    gf[3 * k + 0] = acc_d[k] * tmp[0] * (float)S / 2.0f;
+                    gf[3 * k + 1] = acc_d[k] * tmp[1] * (float)S / 2.0f;
+                }
+            }
+            Maps M = {idx, rgb, g_rgb, g_alpha, S, layout, b, use_alpha && g_alpha, rgb && g_rgb};
+            if (!(M.use_alpha || M.use_rgb))
+                continue;
+            const int *e = ext.data() + (size_t)b * 4 * S;
+            for (int combo = 0; combo < 6; combo++) {
+                const int edge = combo >> 1, axis = combo & 1;
+                HocK4Edge E;
+                hoc_k4_edge(f, S, edge, axis, &E);
+                float gA = 0.0f, gB = 0.0f;
+                for (int d0 = E.d0_from; d0 <= E.d0_to; d0++) {
+                    float d1_cross;
+                    int d1_in, d1_out;
+                    if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out))
+                        continue;
+                    const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+                    const int xout = axis == 0 ? d0 : d1_out, yout = axis == 0 ? d1_out : d0;
+                    float I_in[4], I_out[4];
+                    load_I(M, xin, yin, I_in);
+                    load_I(M, xout, yout, I_out);
+                    if (idx[(long)yin * S + xin] == fi) {
+                        const int d1_limit = (0 < E.dir) ? S - 1 : 0;
+                        int d1_from = std::max(std::min(d1_out, d1_limit), 0);
+                        int d1_to = std::min(std::max(d1_out, d1_limit), S - 1);
+                        const int lo = axis == 0 ? e[2 * S + d0] : e[0 * S + d0];
+                        const int hi = axis == 0 ? e[3 * S + d0] : e[1 * S + d0];
+                        d1_from = std::max(d1_from, lo);
+                        d1_to = std::min(d1_to, hi);
+                        for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+                            const float delta = delta_at(M, xi, yi, I_in);
+                            if (delta <= 0.0f)
+                                continue;
+                            hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+                        }
+                    }
+                    const int lim = hoc_k4_inward_limit(&E, d0);
+                    const int d1_from = std::max(std::min(d1_in, lim), 0);
+                    const int d1_to = std::min(std::max(d1_in, lim), S - 1);
+                    for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+                        if (idx[(long)yi * S + xi] != fi)
+                            continue;
+                        const float delta = delta_at(M, xi, yi, I_out);
+                        if (delta <= 0.0f)
+                            continue;
+                        hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+                    }
+                }
+                gf[edge * 3 + (1 - axis)] += gA;
+                gf[((edge + 1) % 3) * 3 + (1 - axis)] += gB;
+            }
+        }
+}
