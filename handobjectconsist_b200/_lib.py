@@ -28,6 +28,9 @@ class HocLibraryError(RuntimeError):
 SIGNATURES = {
     "hoc_abi_version": (_i, []),
     "hoc_last_error": (ctypes.c_char_p, []),
+    "hoc_launch_count": (ctypes.c_ulonglong, [_i]),
+    "hoc_timer_begin": (_i, [_i]),
+    "hoc_timer_end": (_i, [ctypes.POINTER(ctypes.c_float), _i]),
     "hoc_raster_forward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -40,6 +43,9 @@ SIGNATURES = {
     "hoc_warp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "hoc_occlusion_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
 }
+
+KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_backward": 3, "warp_photo_fwd": 4,
+              "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8}
 
 _LIB = None
 

@@ -1,4 +1,4 @@
-/* hoc_abi.cu -- version / error reporting of the C ABI (include/hoc_b200.h). */
+/* hoc_abi.cu -- version / error reporting / launch accounting of the C ABI (include/hoc_b200.h). */
 #include <stdarg.h>
 #include <stdio.h>
 
@@ -17,3 +17,62 @@ void hoc_set_error(const char *fmt, ...)
 extern "C" int hoc_abi_version(void) { return HOC_ABI_VERSION; }
 
 extern "C" const char *hoc_last_error(void) { return g_hoc_error; }
+
+/* ---- launch accounting + per-kernel device timing (used by bench.py) ---------------------- */
+#define HOC_TIMER_CAP 4096
+static unsigned long long g_launches[HOC_KERNEL_COUNT];
+static int g_timer_kernel = -1;
+static int g_timer_n = 0;
+static cudaEvent_t g_timer_ev[HOC_TIMER_CAP][2];
+static int g_timer_created = 0;
+
+void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
+{
+    if (phase == 0)
+        g_launches[kernel_id]++;
+    if (kernel_id != g_timer_kernel || g_timer_n >= HOC_TIMER_CAP)
+        return;
+    if (phase == 0) {
+        if (g_timer_n >= g_timer_created) {
+            cudaEventCreate(&g_timer_ev[g_timer_n][0]);
+            cudaEventCreate(&g_timer_ev[g_timer_n][1]);
+            g_timer_created = g_timer_n + 1;
+        }
+        cudaEventRecord(g_timer_ev[g_timer_n][0], st);
+    } else {
+        cudaEventRecord(g_timer_ev[g_timer_n][1], st);
+        g_timer_n++;
+    }
+}
+
+extern "C" unsigned long long hoc_launch_count(int kernel_id)
+{
+    if (kernel_id < 0) {
+        unsigned long long t = 0;
+        for (int k = 0; k < HOC_KERNEL_COUNT; k++)
+            t += g_launches[k];
+        return t;
+    }
+    return kernel_id < HOC_KERNEL_COUNT ? g_launches[kernel_id] : 0;
+}
+
+extern "C" int hoc_timer_begin(int kernel_id)
+{
+    HOC_CHECK_ARG(kernel_id >= -1 && kernel_id < HOC_KERNEL_COUNT, "hoc_timer_begin: kernel id %d", kernel_id);
+    g_timer_kernel = kernel_id;
+    g_timer_n = 0;
+    return HOC_OK;
+}
+
+extern "C" int hoc_timer_end(float *ms_host, int capacity)
+{
+    const int n = g_timer_n < capacity ? g_timer_n : capacity;
+    for (int i = 0; i < n; i++) {
+        cudaEventSynchronize(g_timer_ev[i][1]);
+        if (cudaEventElapsedTime(&ms_host[i], g_timer_ev[i][0], g_timer_ev[i][1]) != cudaSuccess)
+            ms_host[i] = -1.0f;
+    }
+    g_timer_kernel = -1;
+    g_timer_n = 0;
+    return n;
+}

@@ -11,6 +11,17 @@
 /* Raised by the C-ABI entry points; text is fetched with hoc_last_error(). */
 void hoc_set_error(const char *fmt, ...);
 
+/* Counts the launch and, when bench.py armed the timer for this kernel, brackets it with events
+ * on the launching stream (phase 0 before the launch, 1 after). */
+void hoc_note_launch(int kernel_id, cudaStream_t st, int phase);
+
+#define HOC_LAUNCH(kernel_id, st, ...)    \
+    do {                                  \
+        hoc_note_launch(kernel_id, st, 0); \
+        __VA_ARGS__;                      \
+        hoc_note_launch(kernel_id, st, 1); \
+    } while (0)
+
 #define HOC_CHECK_ARG(cond, ...)        \
     do {                                \
         if (!(cond)) {                  \

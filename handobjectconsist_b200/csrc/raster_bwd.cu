@@ -453,18 +453,22 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
             return HOC_ERR_CUDA;
         }
         dim3 eg((S + 31) / 32, (S + 31) / 32, B);
-        hoc_grad_extent_kernel<<<eg, dim3(32, 8), 0, st>>>(grad_rgb, (use_alpha ? grad_alpha : nullptr), S, layout, ext);
+        HOC_LAUNCH(HOC_K_GRAD_EXTENT, st,
+                   (hoc_grad_extent_kernel<<<eg, dim3(32, 8), 0, st>>>(grad_rgb, (use_alpha ? grad_alpha : nullptr), S,
+                                                                      layout, ext)));
         HOC_CHECK_LAUNCH("hoc_grad_extent_kernel");
     }
     dim3 grid((F + BW_WARPS - 1) / BW_WARPS, B);
     if (ts == 2)
-        hoc_raster_backward_kernel<true><<<grid, BW_THREADS, 0, st>>>(
-            faces, textures, face_index_map, rgb, grad_rgb, grad_alpha, grad_depth, F, S, ts, near_, far_, eps, layout,
-            use_alpha, ext, grad_faces, grad_textures);
+        HOC_LAUNCH(HOC_K_RASTER_BACKWARD, st,
+                   (hoc_raster_backward_kernel<true><<<grid, BW_THREADS, 0, st>>>(
+                       faces, textures, face_index_map, rgb, grad_rgb, grad_alpha, grad_depth, F, S, ts, near_, far_, eps,
+                       layout, use_alpha, ext, grad_faces, grad_textures)));
     else
-        hoc_raster_backward_kernel<false><<<grid, BW_THREADS, 0, st>>>(
-            faces, textures, face_index_map, rgb, grad_rgb, grad_alpha, grad_depth, F, S, ts, near_, far_, eps, layout,
-            use_alpha, ext, grad_faces, grad_textures);
+        HOC_LAUNCH(HOC_K_RASTER_BACKWARD, st,
+                   (hoc_raster_backward_kernel<false><<<grid, BW_THREADS, 0, st>>>(
+                       faces, textures, face_index_map, rgb, grad_rgb, grad_alpha, grad_depth, F, S, ts, near_, far_, eps,
+                       layout, use_alpha, ext, grad_faces, grad_textures)));
     HOC_CHECK_LAUNCH("hoc_raster_backward_kernel");
     return HOC_OK;
 }

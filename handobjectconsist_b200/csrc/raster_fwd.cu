@@ -281,7 +281,8 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     }
     if (F > 0) {
         dim3 grid((F + ZB_THREADS - 1) / ZB_THREADS, B);
-        hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_);
+        HOC_LAUNCH(HOC_K_RASTER_ZBUF, st,
+                   (hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_)));
         HOC_CHECK_LAUNCH("hoc_raster_zbuf_kernel");
     }
     float bg[3] = {0.f, 0.f, 0.f};
@@ -292,9 +293,11 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     }
     const long npix = (long)S * S;
     dim3 grid2((unsigned)((npix + RS_THREADS - 1) / RS_THREADS), B);
-    hoc_raster_resolve_kernel<<<grid2, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps, bg[0],
-                                                           bg[1], bg[2], background_dev, layout, rgb, alpha, depth,
-                                                           face_index_map, weight_map, face_inv_map);
+    HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
+               (hoc_raster_resolve_kernel<<<grid2, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
+                                                                        bg[0], bg[1], bg[2], background_dev, layout, rgb,
+                                                                        alpha, depth, face_index_map, weight_map,
+                                                                        face_inv_map)));
     HOC_CHECK_LAUNCH("hoc_raster_resolve_kernel");
     return HOC_OK;
 }

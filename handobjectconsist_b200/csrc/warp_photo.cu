@@ -426,8 +426,9 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
     }
     const long npix = (long)H * W;
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
-    hoc_warp_photo_forward_kernel<<<grid, WP_THREADS, 0, st>>>(src, target, flow, jitter, C, Cj, H, W, thresh, warped,
-                                                               warp_mask, valid_mask, diff, sums);
+    HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
+               (hoc_warp_photo_forward_kernel<<<grid, WP_THREADS, 0, st>>>(src, target, flow, jitter, C, Cj, H, W, thresh,
+                                                                           warped, warp_mask, valid_mask, diff, sums)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_forward_kernel");
     return HOC_OK;
 }
@@ -445,8 +446,9 @@ extern "C" int hoc_warp_photo_backward(const float *src, const float *target, co
                   "hoc_warp_photo_backward: NULL argument");
     const long npix = (long)H * W;
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
-    hoc_warp_photo_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
-        src, target, flow, valid_mask, sums, grad_loss, C, H, W, thresh, grad_flow);
+    HOC_LAUNCH(HOC_K_WARP_PHOTO_BWD, (cudaStream_t)stream,
+               (hoc_warp_photo_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
+                   src, target, flow, valid_mask, sums, grad_loss, C, H, W, thresh, grad_flow)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_backward_kernel");
     return HOC_OK;
 }
@@ -462,7 +464,9 @@ extern "C" int hoc_warp(const float *x, const float *flow_nchw, int B, int C, in
     HOC_CHECK_ARG(x && flow_nchw && out, "hoc_warp: NULL argument");
     const long npix = (long)H * W;
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
-    hoc_warp_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, C, H, W, thresh, mode, out, mask);
+    HOC_LAUNCH(HOC_K_WARP, (cudaStream_t)stream,
+               (hoc_warp_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, C, H, W, thresh, mode, out,
+                                                                               mask)));
     HOC_CHECK_LAUNCH("hoc_warp_kernel");
     return HOC_OK;
 }
@@ -477,8 +481,9 @@ extern "C" int hoc_warp_backward(const float *x, const float *flow_nchw, const f
     HOC_CHECK_ARG(x && flow_nchw && grad_out && grad_flow_nchw, "hoc_warp_backward: NULL argument");
     const long npix = (long)H * W;
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
-    hoc_warp_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, grad_out, C, H, W, thresh,
-                                                                            grad_flow_nchw);
+    HOC_LAUNCH(HOC_K_WARP_BWD, (cudaStream_t)stream,
+               (hoc_warp_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, grad_out, C, H, W,
+                                                                                        thresh, grad_flow_nchw)));
     HOC_CHECK_LAUNCH("hoc_warp_backward_kernel");
     return HOC_OK;
 }
@@ -495,8 +500,9 @@ extern "C" int hoc_occlusion_mask(const float *mask1, const float *mask2, const 
     HOC_CHECK_ARG(mask1 && mask2 && flow12 && flow21 && occl1 && occl2, "hoc_occlusion_mask: NULL argument");
     const long npix = (long)H * W;
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B, 2);
-    hoc_occlusion_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(mask1, mask2, flow12, flow21, Cf, H, W,
-                                                                        distance_thresh, occl1, occl2);
+    HOC_LAUNCH(HOC_K_OCCLUSION, (cudaStream_t)stream,
+               (hoc_occlusion_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(mask1, mask2, flow12, flow21, Cf, H, W,
+                                                                                    distance_thresh, occl1, occl2)));
     HOC_CHECK_LAUNCH("hoc_occlusion_kernel");
     return HOC_OK;
 }

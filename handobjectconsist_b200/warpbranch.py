@@ -1,0 +1,96 @@
+"""Photometric-consistency branch -- same surface as /root/reference/meshreg/models/warpbranch.py:9-96.
+
+``forward(samples, all_results, hand_face, renderer, image_size, criterion, ...)`` gathers the hand and
+object vertices of every frame, swaps in ground truth for the reference frames (``gt_refs``), detaches
+all but the first frame (``first_only``), renders the mesh-induced flows and returns the mean pair loss.
+Samples may be keyed by the reference's own ``TransQueries`` / ``BaseQueries`` enums or by ours -- the
+lookup goes by member NAME.
+"""
+import torch
+
+from .meshutils import batch_cat_meshes
+from .warping import imgflowarp, opticalflow
+
+
+def _get(sample, name):
+    for key, val in sample.items():
+        if getattr(key, "name", key) == name:
+            return val
+    raise KeyError(name)
+
+
+def _trans(sample, name):
+    # TransQueries and BaseQueries share member names; the reference reads IMAGE / JITTERMASK / CAMINTR
+    # from the transformed queries and faces / GT vertices from the base ones.
+    for key, val in sample.items():
+        if getattr(key, "name", key) == name and type(key).__name__ == "TransQueries":
+            return val
+    return _get(sample, name)
+
+
+def _base(sample, name):
+    for key, val in sample.items():
+        if getattr(key, "name", key) == name and type(key).__name__ == "BaseQueries":
+            return val
+    return _get(sample, name)
+
+
+def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt_refs=True, first_only=True,
+            hand_ignore_faces=None, use_backward=True, detach_renders=True):
+    """
+    Args:
+        use_backward: also compare the warp from the first to the other frame (warpbranch.py:21-25)
+        detach_renders: extension -- the reference hard-codes True (warpbranch.py:66); False lets the
+            NMR geometry gradient flow as well
+    Returns (full_loss, pair_results) like the reference.
+    """
+    images = [_trans(sample, "IMAGE").cuda() for sample in samples]
+    jitter_masks = [_trans(sample, "JITTERMASK").cuda() for sample in samples]
+    camintrs = [_trans(sample, "CAMINTR").cuda() for sample in samples]
+
+    obj_verts = [result["recov_objverts3d"] for result in all_results]
+    obj_faces = [_base(sample, "OBJFACES").long().cuda() for sample in samples]
+    hand_verts = [result["recov_handverts3d"] for result in all_results]
+    hand_faces_b = hand_face.repeat(obj_verts[0].shape[0], 1, 1).long()
+    hand_faces = [hand_faces_b for _ in range(len(samples))]
+    if gt_refs:
+        for sample_idx in range(1, len(samples)):
+            obj_verts[sample_idx] = _base(samples[sample_idx], "OBJVERTS3D").cuda()
+            hand_verts[sample_idx] = _base(samples[sample_idx], "HANDVERTS3D").cuda()
+    verts_world = []
+    for seq_idx in range(len(samples)):
+        all_verts, all_faces, _ = batch_cat_meshes([hand_verts[seq_idx], obj_verts[seq_idx]],
+                                                   [hand_faces[seq_idx], obj_faces[seq_idx]])
+        if first_only and seq_idx > 0:
+            all_verts = all_verts.detach()
+        verts_world.append(all_verts)
+
+    recons_flows = opticalflow.get_opticalflows(verts_world, all_faces, camintrs, renderer, image_size,
+                                                detach_textures=False, detach_renders=detach_renders,
+                                                ignore_face_idxs=hand_ignore_faces)
+    all_masks, all_warps, all_diffs, full_losses = [], [], [], []
+    for recons_flow, image, jitter_mask in zip(recons_flows, images[1:], jitter_masks[1:]):
+        warp_loss, masks, warps, diffs = imgflowarp.pair_consist(
+            recons_flow, image_ref=images[0], image=image, jitter_mask_ref=jitter_masks[0], jitter_mask=jitter_mask,
+            criterion=criterion, use_backward=use_backward)
+        all_masks.append(masks)
+        full_losses.append(warp_loss)
+        all_warps.append(warps)
+        all_diffs.append(diffs)
+    stack_losses = torch.stack(full_losses)
+    full_loss = stack_losses.mean()
+    pair_results = {"masks": all_masks, "warps": all_warps, "recons_flows": recons_flows, "diffs": all_diffs,
+                    "diff_losses": stack_losses}
+    return full_loss, pair_results
+
+
+def consist_step(verts1, verts2, faces, K, image_ref, image, jitter_mask_ref, jitter_mask, renderer, criterion,
+                 orig_img_size, ignore_face_idxs=None, detach_renders=True, use_backward=True):
+    """One frame pair given already-concatenated meshes: flows -> pair_consist -> batch mean.
+    (What ``forward`` does after its gather / concat glue; used by bench.py and the tests.)"""
+    flows = opticalflow.get_opticalflow([verts1, verts2], faces, [K, K], renderer, orig_img_size,
+                                        detach_textures=False, detach_renders=detach_renders,
+                                        ignore_face_idxs=ignore_face_idxs)
+    loss, masks, warps, diffs = imgflowarp.pair_consist(flows, image_ref, image, jitter_mask_ref, jitter_mask,
+                                                        criterion, use_backward)
+    return loss.mean(), dict(flows=flows, loss=loss, masks=masks, warps=warps, diffs=diffs)

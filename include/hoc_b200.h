@@ -49,6 +49,26 @@ extern "C" {
 int hoc_abi_version(void);
 const char *hoc_last_error(void);
 
+/* Kernel ids for launch accounting / device timing (bench.py's `gpu_launches` and `roofline`). */
+#define HOC_K_RASTER_ZBUF 0
+#define HOC_K_RASTER_RESOLVE 1
+#define HOC_K_GRAD_EXTENT 2
+#define HOC_K_RASTER_BACKWARD 3
+#define HOC_K_WARP_PHOTO_FWD 4
+#define HOC_K_WARP_PHOTO_BWD 5
+#define HOC_K_WARP 6
+#define HOC_K_WARP_BWD 7
+#define HOC_K_OCCLUSION 8
+#define HOC_KERNEL_COUNT 16
+
+/* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
+unsigned long long hoc_launch_count(int kernel_id);
+/* Arm / read the device timer: between begin and end every launch of `kernel_id` is bracketed by CUDA
+ * events on its stream; end synchronises them and writes up to `capacity` durations (ms) to host memory,
+ * returning how many were recorded.  Not thread-safe; meant for benchmarking. */
+int hoc_timer_begin(int kernel_id);
+int hoc_timer_end(float *ms_host, int capacity);
+
 /* ---- rasterizer forward -------------------------------------------------------------------
  * Replaces forward_face_index_map + forward_texture_sampling (rasterize.py:202-215,232-243)
  * plus the wrapper's fill_/background/alpha/clone/flip ops (rasterize.py:58-125,246-260,417-428).

@@ -1,0 +1,187 @@
+"""GPU parity: the CUDA rasterizer (through the reference-shaped python surface, i.e. through the
+C ABI of libhoc_b200.so) against the CPU oracle on the same seeded inputs.
+Bar (BASELINE.json north_star): forward maps bit-exact (integer index map exact, fp32 maps 1e-4 abs --
+they are in fact identical), gradients within 1e-3 relative of the oracle's float64 accumulation."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import onmr
+
+pytestmark = pytest.mark.gpu
+
+ABS_TOL = 1e-4   # pixels (north_star)
+REL_TOL = 1e-3   # gradients (north_star)
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _run_function(faces, tex, S, bg=(0, 0, 0), eps=1e-3, rr=True, ra=True, rd=True):
+    from handobjectconsist_b200.neurender.rasterize import RasterizeFunction
+    f = _cuda(faces).requires_grad_(True)
+    t = _cuda(tex).requires_grad_(True) if tex is not None else None
+    out = RasterizeFunction.apply(f, t, S, 0.1, 100.0, eps, bg, rr, ra, rd)
+    return f, t, out
+
+
+@pytest.mark.parametrize("S,B,seed", [(64, 2, 0), (48, 3, 3), (33, 1, 5), (128, 2, 7)])
+def test_forward_matches_oracle(S, B, seed):
+    faces, tex, _ = helpers.scene_faces(B, S, seed=seed)
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0.1, 0.2, 0.3), True, True, True)
+    _, _, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, tex, S, bg=(0.1, 0.2, 0.3))
+    assert (ora["face_index_map"] >= 0).mean() > 0.02
+    np.testing.assert_array_equal(idx.cpu().numpy(), ora["face_index_map"])
+    np.testing.assert_array_equal(depth.detach().cpu().numpy(), ora["depth_map"])
+    np.testing.assert_array_equal(wmap.detach().cpu().numpy(), ora["weight_map"])
+    np.testing.assert_array_equal(alpha.detach().cpu().numpy(), ora["alpha_map"])
+    np.testing.assert_array_equal(inv.detach().cpu().numpy(), ora["face_inv_map"])
+    assert np.abs(rgb.detach().cpu().numpy() - ora["rgb_map"]).max() <= ABS_TOL
+    np.testing.assert_array_equal(rgb.detach().cpu().numpy(), ora["rgb_map"])
+
+
+def test_forward_flags_and_disabled_outputs():
+    S = 32
+    faces, tex, _ = helpers.scene_faces(1, S, seed=2)
+    _, _, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, None, S, rr=False, ra=True, rd=False)
+    assert rgb.numel() == 0 and depth.numel() == 0 and inv.numel() == 1
+    ora = onmr.rasterize_forward(faces, None, S, 0.1, 100.0, 1e-3, (0, 0, 0), False, True, False)
+    np.testing.assert_array_equal(alpha.cpu().numpy(), ora["alpha_map"])
+    np.testing.assert_array_equal(idx.cpu().numpy(), ora["face_index_map"])
+
+
+def test_forward_edge_cases():
+    from handobjectconsist_b200.neurender.rasterize import RasterizeFunction
+    S = 16
+    # empty batch of faces: everything is background
+    f = torch.zeros(2, 0, 3, 3, device="cuda")
+    t = torch.zeros(2, 0, 2, 2, 2, 3, device="cuda")
+    rgb, alpha, depth, idx, inv, w = RasterizeFunction.apply(f, t, S, 0.1, 100.0, 1e-3, (0.5, 0.25, 0.125), True, True, True)
+    assert (idx == -1).all() and (alpha == 0).all() and (depth == 100.0).all()
+    assert torch.equal(rgb[0, 0, 0].cpu(), torch.tensor([0.5, 0.25, 0.125]))
+    # full-screen triangle, a degenerate one, one with NaN, one behind `near`, one beyond `far`
+    faces = np.array([[[[-3, -3, 1.0], [3, -3, 1.0], [0, 3, 2.0]],
+                       [[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]],
+                       [[np.nan, 0, 1.0], [1, 0, 1.0], [0, 1, 1.0]],
+                       [[-1, -1, 0.05], [1, -1, 0.05], [0, 1, 0.05]],
+                       [[-1, -1, 200.0], [1, -1, 200.0], [0, 1, 200.0]]]], dtype=np.float32)
+    tex = np.random.default_rng(0).uniform(size=(1, 5, 2, 2, 2, 3)).astype(np.float32)
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    _, _, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, tex, S)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ora["face_index_map"])
+    np.testing.assert_array_equal(depth.detach().cpu().numpy(), ora["depth_map"])
+    np.testing.assert_array_equal(rgb.detach().cpu().numpy(), ora["rgb_map"])
+    # CPU tensors are rejected like the reference (rasterize.py:346-347)
+    from handobjectconsist_b200.neurender.rasterize import Rasterize
+    with pytest.raises(TypeError):
+        Rasterize(S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)(torch.zeros(1, 1, 3, 3), torch.zeros(1, 1, 2, 2, 2, 3))
+
+
+def test_z_ties_lowest_face_index_wins():
+    S = 24
+    tri = [[-0.8, -0.8, 1.0], [0.8, -0.8, 1.0], [0.0, 0.9, 1.0]]
+    faces = np.array([[tri, tri, tri]], dtype=np.float32)  # three coplanar copies -> exact ties
+    tex = np.zeros((1, 3, 2, 2, 2, 3), np.float32)
+    for i in range(3):
+        tex[0, i] = i + 1
+    _, _, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, tex, S)
+    covered = idx.cpu().numpy() >= 0
+    assert covered.any()
+    assert (idx.cpu().numpy()[covered] == 0).all()
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ora["face_index_map"])
+
+
+@pytest.mark.parametrize("dense,S,B", [(True, 48, 2), (False, 48, 2), (False, 96, 2), (True, 64, 1)])
+def test_backward_matches_oracle(dense, S, B):
+    faces, tex, _ = helpers.scene_faces(B, S, seed=1)
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    rng = np.random.default_rng(0)
+    g_rgb = rng.normal(size=ora["rgb_map"].shape).astype(np.float32)
+    g_alpha = rng.normal(size=ora["alpha_map"].shape).astype(np.float32)
+    g_depth = rng.normal(size=ora["depth_map"].shape).astype(np.float32)
+    if not dense:
+        cov = (ora["face_index_map"] >= 0).astype(np.float32)
+        g_rgb *= cov[..., None]
+        g_alpha *= cov
+    gf64, gt64 = onmr.rasterize_backward(ora, g_rgb, g_alpha, g_depth, dtype=np.float64)
+    f, t, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, tex, S)
+    loss = (rgb * _cuda(g_rgb)).sum() + (alpha * _cuda(g_alpha)).sum() + (depth * _cuda(g_depth)).sum()
+    loss.backward()
+    gf, gt = f.grad.cpu().numpy(), t.grad.cpu().numpy()
+    assert np.isfinite(gf).all() and np.isfinite(gt).all()
+    assert helpers.rel_err(gt, gt64) < REL_TOL
+    assert helpers.rel_err(gf, gf64) < REL_TOL
+    # deterministic: a second run gives bit-identical gradients (no float atomics)
+    f2, t2, (rgb2, alpha2, depth2, _, _, _) = _run_function(faces, tex, S)
+    ((rgb2 * _cuda(g_rgb)).sum() + (alpha2 * _cuda(g_alpha)).sum() + (depth2 * _cuda(g_depth)).sum()).backward()
+    assert torch.equal(f2.grad, f.grad) and torch.equal(t2.grad, t.grad)
+
+
+def test_backward_partial_outputs():
+    """Only some outputs carry gradient (None for the others), silhouette-only mode, texture size 3."""
+    S = 40
+    faces, tex, _ = helpers.scene_faces(1, S, seed=4)
+    rng = np.random.default_rng(1)
+    # rgb only
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    g_rgb = rng.normal(size=ora["rgb_map"].shape).astype(np.float32)
+    gf64, gt64 = onmr.rasterize_backward(ora, g_rgb, None, None, dtype=np.float64)
+    f, t, out = _run_function(faces, tex, S)
+    (out[0] * _cuda(g_rgb)).sum().backward()
+    assert helpers.rel_err(f.grad.cpu().numpy(), gf64) < REL_TOL
+    assert helpers.rel_err(t.grad.cpu().numpy(), gt64) < REL_TOL
+    # alpha only, no textures at all
+    ora = onmr.rasterize_forward(faces, None, S, 0.1, 100.0, 1e-3, (0, 0, 0), False, True, False)
+    g_alpha = rng.normal(size=ora["alpha_map"].shape).astype(np.float32)
+    gf64, _ = onmr.rasterize_backward(ora, None, g_alpha, None, dtype=np.float64)
+    f, _, out = _run_function(faces, None, S, rr=False, ra=True, rd=False)
+    (out[1] * _cuda(g_alpha)).sum().backward()
+    assert helpers.rel_err(f.grad.cpu().numpy(), gf64) < REL_TOL
+    # texture size 3 (generic path)
+    tex3 = rng.uniform(size=(1, faces.shape[1], 3, 3, 3, 3)).astype(np.float32)
+    ora = onmr.rasterize_forward(faces, tex3, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    g_rgb = rng.normal(size=ora["rgb_map"].shape).astype(np.float32)
+    gf64, gt64 = onmr.rasterize_backward(ora, g_rgb, None, None, dtype=np.float64)
+    f, t, out = _run_function(faces, tex3, S)
+    np.testing.assert_array_equal(out[0].detach().cpu().numpy(), ora["rgb_map"])
+    (out[0] * _cuda(g_rgb)).sum().backward()
+    assert helpers.rel_err(t.grad.cpu().numpy(), gt64) < REL_TOL
+    assert helpers.rel_err(f.grad.cpu().numpy(), gf64) < REL_TOL
+
+
+@pytest.mark.parametrize("aa", [False, True])
+def test_rasterize_rgbad_matches_oracle(aa):
+    from handobjectconsist_b200.neurender.rasterize import rasterize_rgbad
+    S = 32
+    faces, tex, _ = helpers.scene_faces(2, S * (2 if aa else 1), seed=6)
+    ora = onmr.rasterize_rgbad(faces, tex, S, aa, 0.1, 100.0, 1e-3, (0, 0, 0))
+    out = rasterize_rgbad(_cuda(faces), _cuda(tex), S, aa, 0.1, 100.0, 1e-3, (0, 0, 0))
+    for k in ("rgb", "alpha", "depth"):
+        assert np.abs(out[k].cpu().numpy() - ora[k]).max() <= ABS_TOL, k
+    np.testing.assert_array_equal(out["face_index_map"].cpu().numpy(), ora["face_index_map"])
+    np.testing.assert_array_equal(out["weight_map"].cpu().numpy(), ora["weight_map"])
+    np.testing.assert_array_equal(out["face_inv_map"].cpu().numpy(), ora["face_inv_map"])
+
+
+def test_image_layout_backward_matches_raw_layout():
+    """The fused NCHW/flipped output path gives the same gradients as the reference-shaped path
+    followed by permute + flip."""
+    from handobjectconsist_b200.neurender.rasterize import rasterize_rgbad
+    S = 48
+    faces, tex, _ = helpers.scene_faces(2, S, seed=8)
+    rng = np.random.default_rng(3)
+    g_rgb = _cuda(rng.normal(size=(2, 3, S, S)).astype(np.float32))
+    g_a = _cuda(rng.normal(size=(2, S, S)).astype(np.float32))
+    g_d = _cuda(rng.normal(size=(2, S, S)).astype(np.float32))
+    f1 = _cuda(faces).requires_grad_(True)
+    t1 = _cuda(tex).requires_grad_(True)
+    o = rasterize_rgbad(f1, t1, S, False, 0.1, 100.0, 1e-3, (0, 0, 0))
+    ((o["rgb"] * g_rgb).sum() + (o["alpha"] * g_a).sum() + (o["depth"] * g_d).sum()).backward()
+    f2, t2, (rgb, alpha, depth, _, _, _) = _run_function(faces, tex, S)
+    rgb = rgb.permute(0, 3, 1, 2).flip(2)
+    assert torch.equal(rgb, o["rgb"])
+    ((rgb * g_rgb).sum() + (alpha.flip(1) * g_a).sum() + (depth.flip(1) * g_d).sum()).backward()
+    assert torch.equal(f1.grad, f2.grad) and torch.equal(t1.grad, t2.grad)
