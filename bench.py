@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- render + warp + photometric forward+backward frames/s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+One step = one pass of the hot path over one batch of synthetic frame pairs (BASELINE.json configs[2],
+which contains configs[1] -- 32 hand+object mesh renders of 9 104 triangles at 256x256 -- as its
+rasterizer part): per rank 16 pairs -> 2 x 16 mesh renders (fill_back, 2F = 9104 faces), occlusion
+check, 2 x 16 image warps + masked L1, and the full backward (texture AND geometry gradients, i.e.
+detach_renders=False so that nothing the reference computes is skipped) down to the camera-space
+vertices.  frames/s = 2 * pairs * ranks * steps / time.  Weak scaling: every rank gets its own 16 pairs
+and there is no data-path collective.
+
+The JSON line follows the driver contract; `roofline` is for hoc_raster_backward_kernel (the kernel
+BASELINE.json's north_star names), timed live with CUDA events around each of its launches in the timed
+region; `cpu_baseline` / `--impl reference` time the CPU oracle (the reference has no CPU renderer and
+its CUDA extension is not installable here -- DESIGN.md) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PAIRS = 16          # frame pairs per rank and step (configs[2])
+SIZE = 256          # raster / image side
+N_SETS = 3          # distinct input sets cycled between steps (> L2 between reuse)
+METRIC = "render+warp+photometric fwd+bwd frames/sec @256x256"
+UNIT = "frames/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def _make_sets(n_sets, pairs, size, device, pin=False, rank=0):
+    import torch
+    from handobjectconsist_b200 import synth
+
+    sets = []
+    for i in range(n_sets):
+        sc = synth.make_scene(pairs, size, size, seed=1000 * rank + i)
+        if device is not None:
+            sc = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in sc.items()}
+        elif pin:
+            sc = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in sc.items()}
+        sets.append(sc)
+    return sets
+
+
+def _samples_from_scene(sc, hand_v=778):
+    """The reference's batch layout: two sample dicts + two result dicts (warpbranch.py:27-44)."""
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+
+    import torch
+
+    def own(t):  # contiguous (and pinned, for host sets) tensors: slices of pinned storage are not DMA-able as is
+        t = t.contiguous()
+        return t.pin_memory() if (not t.is_cuda and sc["verts1"].is_pinned()) else t
+
+    obj_faces = own(sc["faces"][:, 1552:] - hand_v)
+    samples, results = [], []
+    for verts, img, jit in ((sc["verts1"], sc["image_ref"], sc["jitter_mask_ref"]),
+                            (sc["verts2"], sc["image"], sc["jitter_mask"])):
+        samples.append({TransQueries.IMAGE: img, TransQueries.JITTERMASK: jit, TransQueries.CAMINTR: sc["K"],
+                        BaseQueries.OBJFACES: obj_faces, BaseQueries.OBJVERTS3D: own(verts[:, hand_v:]),
+                        BaseQueries.HANDVERTS3D: own(verts[:, :hand_v])})
+        results.append({"recov_handverts3d": own(verts[:, :hand_v]), "recov_objverts3d": own(verts[:, hand_v:])})
+    return samples, results
+
+
+def run_native(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from handobjectconsist_b200 import _lib, warpbranch
+    from handobjectconsist_b200.neurender.renderer import Renderer
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: the product path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    renderer = Renderer(image_size=SIZE, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                        K=torch.ones(1, 3, 3, device=dev), orig_size=SIZE, anti_aliasing=False, fill_back=True,
+                        near=0.1, no_light=True)
+    criterion = PyramidCriterion("l1")
+    hand_face = None
+
+    def step(samples, results, hand_face, ignore):
+        hv = results[0]["recov_handverts3d"].detach().requires_grad_(True)
+        ov = results[0]["recov_objverts3d"].detach().requires_grad_(True)
+        res = [{"recov_handverts3d": hv, "recov_objverts3d": ov}, results[1]]
+        loss, _ = warpbranch.forward(samples, res, hand_face, renderer, (SIZE, SIZE), criterion, gt_refs=True,
+                                     first_only=True, hand_ignore_faces=ignore, use_backward=True,
+                                     detach_renders=False)
+        loss.backward()
+        return loss, hv.grad, ov.grad
+
+    # ---- device-resident arm ----------------------------------------------------------------
+    dsets = _make_sets(N_SETS, PAIRS, SIZE, dev, rank=rank)
+    hand_face = dsets[0]["faces"][0, :1552].clone()
+    ignore = dsets[0]["hand_ignore_faces"]
+    dbatches = [_samples_from_scene(sc) for sc in dsets]
+    for i in range(args.warmup):
+        step(*dbatches[i % N_SETS], hand_face, ignore)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.hoc_launch_count(-1)
+    L.hoc_timer_begin(_lib.KERNEL_IDS["raster_backward"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(args.steps):
+        step(*dbatches[i % N_SETS], hand_face, ignore)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    buf = (ctypes.c_float * 4096)()
+    n_k = L.hoc_timer_end(buf, 4096)
+    kernel_ms = [buf[i] for i in range(n_k)]
+    launches = int(L.hoc_launch_count(-1) - launches0)
+    clocks = sampler.finish()
+
+    # ---- end-to-end arm: host (pinned) buffers through the reference-facing call ------------
+    hsets = _make_sets(N_SETS, PAIRS, SIZE, None, pin=True, rank=rank)
+    hbatches = [_samples_from_scene(sc) for sc in hsets]
+    grad_host = [torch.empty(PAIRS, 778, 3).pin_memory(), torch.empty(PAIRS, 1502, 3).pin_memory()]
+    loss_host = torch.empty(()).pin_memory()
+
+    def e2e_step(i):
+        samples, results = hbatches[i % N_SETS]
+        dres = [{k: v.to(dev, non_blocking=True) for k, v in r.items()} for r in results]
+        loss, gh, go = step(samples, dres, hand_face, ignore)  # warpbranch.forward does the .cuda() of the samples
+        grad_host[0].copy_(gh, non_blocking=True)
+        grad_host[1].copy_(go, non_blocking=True)
+        loss_host.copy_(loss.detach(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
+
+    h2d = sum(v.numel() * v.element_size() for s in hbatches[0][0] for v in s.values() if torch.is_tensor(v))
+    h2d += sum(v.numel() * v.element_size() for v in hbatches[0][1][0].values())
+    d2h = grad_host[0].numel() * 4 + grad_host[1].numel() * 4 + 4
+    for i in range(args.warmup):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        e2e_step(i)
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e2e_ms = t0.elapsed_time(t1)
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = t.tolist()
+    if rank != 0:
+        return None
+
+    frames = 2 * PAIRS * world * args.steps
+    value = frames / (ms / 1e3)
+    peak, peak_src = _peaks()
+    F2 = 2 * 4552
+    algo_bytes = PAIRS * SIZE * SIZE * 36 + PAIRS * F2 * (36 + 36 + 96)
+    k_ms = sum(kernel_ms) / max(len(kernel_ms), 1)
+    achieved = algo_bytes / (k_ms * 1e-3) / 1e9 if kernel_ms else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "raster_backward_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[2]: {PAIRS} frame pairs/rank (= {2 * PAIRS} mesh renders of configs[1] shape, "
+                               f"9104 faces after fill_back) render->flow->occlusion->warp->masked L1 fwd+bwd at "
+                               f"{SIZE}x{SIZE}, full geometry+texture backward (detach_renders=False), use_backward=True",
+                   "pairs_per_rank": PAIRS, "image_size": SIZE, "faces_per_mesh": F2, "parallelism": f"dp{world}",
+                   "l2": f"{N_SETS} input sets rotate; one step touches >300 MB (> 126 MB L2)"},
+        "e2e": {"value": frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "hoc_raster_backward_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": (achieved / peak if achieved else None), "traffic": traffic,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                     "avg_launch_ms": k_ms, "launches_timed": len(kernel_ms),
+                     "share_of_step": (sum(kernel_ms) / ms if kernel_ms else None)},
+    }
+    return out
+
+
+def _reference_pairs_per_second(pairs, steps, warmup, threads):
+    """Oracle (CPU restatement of the reference algorithm) on `pairs` frame pairs per step."""
+    import numpy as np
+    import torch
+
+    from handobjectconsist_b200 import synth
+    from oracle import pipeline as opipe  # the ONE place bench.py executes oracle/: the CPU baseline
+
+    from oracle import nmr as onmr
+
+    torch.set_num_threads(threads)
+    onmr.set_threads(threads)
+    times = []
+    for i in range(warmup + steps):
+        sc = synth.make_scene(pairs, SIZE, SIZE, seed=i)
+        t0 = time.perf_counter()
+        v1 = sc["verts1"].clone().requires_grad_(True)
+        loss, _ = opipe.consist_step(v1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                     sc["jitter_mask_ref"], sc["jitter_mask"], SIZE, (SIZE, SIZE),
+                                     sc["hand_ignore_faces"], detach_renders=False, use_backward=True,
+                                     grad_dtype=np.float32)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times), len(times)
+
+
+def cpu_baseline(sample_pairs=2, steps=1, warmup=0):
+    threads = os.cpu_count() or 1
+    total, n = _reference_pairs_per_second(sample_pairs, steps, warmup, threads)
+    return {"value": 2 * sample_pairs * n / total, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} step(s) of {sample_pairs} frame pairs (of the {PAIRS}-pair workload) at {SIZE}x{SIZE}, "
+                      f"oracle/ C restatement (pthreads over pixels/faces) + torch CPU warp/loss"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return None
+    threads = os.cpu_count() or 1
+    pairs = 2
+    steps = max(1, min(args.steps, 3))
+    warmup = min(args.warmup, 1)
+    total, n = _reference_pairs_per_second(pairs, steps, warmup, threads)
+    value = 2 * pairs * n / total
+    return {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": warmup, "ms_per_step": total / n * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[2] on host cores: bounded sample of {pairs} frame pairs/step at {SIZE}x{SIZE} "
+                               f"(same scene generator, full backward, use_backward=True)",
+                   "pairs_per_step": pairs, "image_size": SIZE, "faces_per_mesh": 2 * 4552},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} timed step(s) of {pairs} frame pairs; the reference has no CPU renderer and "
+                                   f"its CUDA extension is absent, so this is the oracle/ restatement"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        out = run_reference(args, rank)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+
+    import torch.distributed as dist
+
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        import torch
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    args.warmup = max(args.warmup, 3)
+    out = run_native(args, rank, world, local_rank)
+    if out is not None:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

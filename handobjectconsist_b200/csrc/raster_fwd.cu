@@ -261,7 +261,7 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_forward: image_size %d outside [1, 2048]", S);
     HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_forward: bad layout %d", layout);
     HOC_CHECK_ARG(face_index_map != nullptr, "hoc_raster_forward: face_index_map is required");
-    HOC_CHECK_ARG(rgb == nullptr || (textures != nullptr && ts >= 1),
+    HOC_CHECK_ARG(rgb == nullptr || ((textures != nullptr || F == 0) && ts >= 1),
                   "hoc_raster_forward: rgb requested without textures / texture_size");
     HOC_CHECK_ARG(B == 0 || F == 0 || faces != nullptr, "hoc_raster_forward: faces is NULL");
     HOC_CHECK_ARG(B <= 65535, "hoc_raster_forward: batch %d exceeds 65535", B);

@@ -105,9 +105,10 @@ def _forward_impl(ctx, faces, textures, image_size, near, far, eps, background_c
     ctx.mark_non_differentiable(face_index_map)
     ctx.set_materialize_grads(False)
 
-    empty = torch.tensor([])
-    return (rgb if return_rgb else empty, alpha if return_alpha else empty, depth if return_depth else empty,
-            face_index_map, face_inv_map, weight_map if want_weight else torch.zeros(1, device=dev))
+    # disabled outputs are empty CPU tensors like the reference's (rasterize.py:118); one object per output
+    return (rgb if return_rgb else torch.tensor([]), alpha if return_alpha else torch.tensor([]),
+            depth if return_depth else torch.tensor([]), face_index_map, face_inv_map,
+            weight_map if want_weight else torch.zeros(1, device=dev))
 
 
 def _backward_impl(ctx, grad_rgb, grad_alpha, grad_depth):

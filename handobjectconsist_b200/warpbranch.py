@@ -44,19 +44,20 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
             NMR geometry gradient flow as well
     Returns (full_loss, pair_results) like the reference.
     """
-    images = [_trans(sample, "IMAGE").cuda() for sample in samples]
-    jitter_masks = [_trans(sample, "JITTERMASK").cuda() for sample in samples]
-    camintrs = [_trans(sample, "CAMINTR").cuda() for sample in samples]
+    # Put inputs on GPU (stream-ordered copies when the host tensors are pinned)
+    images = [_trans(sample, "IMAGE").cuda(non_blocking=True) for sample in samples]
+    jitter_masks = [_trans(sample, "JITTERMASK").cuda(non_blocking=True) for sample in samples]
+    camintrs = [_trans(sample, "CAMINTR").cuda(non_blocking=True) for sample in samples]
 
     obj_verts = [result["recov_objverts3d"] for result in all_results]
-    obj_faces = [_base(sample, "OBJFACES").long().cuda() for sample in samples]
+    obj_faces = [_base(sample, "OBJFACES").cuda(non_blocking=True).long() for sample in samples]
     hand_verts = [result["recov_handverts3d"] for result in all_results]
     hand_faces_b = hand_face.repeat(obj_verts[0].shape[0], 1, 1).long()
     hand_faces = [hand_faces_b for _ in range(len(samples))]
     if gt_refs:
         for sample_idx in range(1, len(samples)):
-            obj_verts[sample_idx] = _base(samples[sample_idx], "OBJVERTS3D").cuda()
-            hand_verts[sample_idx] = _base(samples[sample_idx], "HANDVERTS3D").cuda()
+            obj_verts[sample_idx] = _base(samples[sample_idx], "OBJVERTS3D").cuda(non_blocking=True)
+            hand_verts[sample_idx] = _base(samples[sample_idx], "HANDVERTS3D").cuda(non_blocking=True)
     verts_world = []
     for seq_idx in range(len(samples)):
         all_verts, all_faces, _ = batch_cat_meshes([hand_verts[seq_idx], obj_verts[seq_idx]],

@@ -42,6 +42,11 @@ def lib():
     return _LIB
 
 
+def set_threads(n):
+    """Host threads used by the forward pixel loop and the pseudo-gradient face loop (default 1)."""
+    lib().nmr_oracle_set_threads(int(n))
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 

@@ -45,18 +45,24 @@ static int FN(face_inv)(const REAL *face, int is, REAL *face_inv)
 
 /* K1 + K2: rasterizer forward, rasterize.py:199-215.  Buffers must be pre-initialised by the
  * caller exactly as rasterize.py:58-85 does (face_index_map=-1, weight_map=0, depth_map=far,
- * face_inv_map=0). */
-void FN(forward_face_index_map)(const REAL *faces, int32_t *face_index_map, REAL *weight_map, REAL *depth_map,
-                                REAL *face_inv_map, REAL *faces_inv, int batch_size, int num_faces, int image_size,
-                                REAL near, REAL far, int return_depth)
-{
-    const int is = image_size, nf = num_faces;
-    memset(faces_inv, 0, sizeof(REAL) * (size_t)batch_size * nf * 9);
-    for (long i = 0; i < (long)batch_size * nf; i++)
-        FN(face_inv)(&faces[i * 9], is, &faces_inv[i * 9]);
+ * face_inv_map=0).  The per-pixel loop over ALL faces is split over host threads by pixel range. */
+struct FN(fwd_ctx) {
+    const REAL *faces;
+    int32_t *face_index_map;
+    REAL *weight_map, *depth_map, *face_inv_map;
+    const REAL *faces_inv;
+    int nf, is;
+    REAL near, far;
+    int return_depth;
+};
 
-#pragma omp parallel for schedule(dynamic, 64)
-    for (long i = 0; i < (long)batch_size * is * is; i++) {
+static void FN(fwd_range)(void *vc, long begin, long end)
+{
+    struct FN(fwd_ctx) *c = (struct FN(fwd_ctx) *)vc;
+    const REAL *faces = c->faces, *faces_inv = c->faces_inv;
+    const int is = c->is, nf = c->nf;
+    const REAL near = c->near, far = c->far;
+    for (long i = begin; i < end; i++) {
         const int bn = (int)(i / (is * is));
         const int pn = (int)(i % (is * is));
         const int yi = pn / is;
@@ -100,15 +106,28 @@ void FN(forward_face_index_map)(const REAL *faces, int32_t *face_index_map, REAL
             }
         }
         if (0 <= face_index_min) {
-            depth_map[i] = depth_min;
-            face_index_map[i] = face_index_min;
+            c->depth_map[i] = depth_min;
+            c->face_index_map[i] = face_index_min;
             for (int k = 0; k < 3; k++)
-                weight_map[3 * i + k] = weight_min[k];
-            if (return_depth)
+                c->weight_map[3 * i + k] = weight_min[k];
+            if (c->return_depth)
                 for (int k = 0; k < 9; k++)
-                    face_inv_map[9 * i + k] = face_inv_min[k];
+                    c->face_inv_map[9 * i + k] = face_inv_min[k];
         }
     }
+}
+
+void FN(forward_face_index_map)(const REAL *faces, int32_t *face_index_map, REAL *weight_map, REAL *depth_map,
+                                REAL *face_inv_map, REAL *faces_inv, int batch_size, int num_faces, int image_size,
+                                REAL near, REAL far, int return_depth)
+{
+    const int is = image_size, nf = num_faces;
+    memset(faces_inv, 0, sizeof(REAL) * (size_t)batch_size * nf * 9);
+    for (long i = 0; i < (long)batch_size * nf; i++)
+        FN(face_inv)(&faces[i * 9], is, &faces_inv[i * 9]);
+    struct FN(fwd_ctx) c = {faces, face_index_map, weight_map, depth_map, face_inv_map, faces_inv, nf, is, near, far,
+                            return_depth};
+    ora_parallel_for((long)batch_size * is * is, FN(fwd_range), &c);
 }
 
 /* K3: trilinear sampling of the per-face texture cube, rasterize.py:218-243 (Appendix C3). */
@@ -118,7 +137,6 @@ void FN(forward_texture_sampling)(const REAL *faces, const REAL *textures, const
                                   int num_faces, int image_size, int texture_size, REAL eps)
 {
     const int is = image_size, nf = num_faces, ts = texture_size;
-#pragma omp parallel for schedule(static)
     for (long i = 0; i < (long)batch_size * is * is; i++) {
         const int face_index = face_index_map[i];
         if (face_index < 0)
@@ -163,14 +181,28 @@ void FN(forward_texture_sampling)(const REAL *faces, const REAL *textures, const
 
 /* K4: NMR pseudo-gradient of rgb/alpha w.r.t. the xy of the face vertices, rasterize.py:263-281
  * (Appendix C4).  One serial scan per face; grad_faces[b,f] is OVERWRITTEN for front faces. */
-void FN(backward_pixel_map)(const REAL *faces, const int32_t *face_index_map, const REAL *rgb_map,
-                            const REAL *alpha_map, const REAL *grad_rgb_map, const REAL *grad_alpha_map,
-                            REAL *grad_faces, int batch_size, int num_faces, int image_size, REAL eps,
-                            int return_rgb, int return_alpha)
+struct FN(k4_ctx) {
+    const REAL *faces;
+    const int32_t *face_index_map;
+    const REAL *rgb_map, *alpha_map, *grad_rgb_map, *grad_alpha_map;
+    REAL *grad_faces;
+    int num_faces, image_size;
+    REAL eps;
+    int return_rgb, return_alpha;
+};
+
+static void FN(k4_range)(void *vc, long begin, long end)
 {
-    const int is = image_size;
-#pragma omp parallel for schedule(dynamic, 16)
-    for (long i = 0; i < (long)batch_size * num_faces; i++) {
+    struct FN(k4_ctx) *c = (struct FN(k4_ctx) *)vc;
+    const REAL *faces = c->faces;
+    const int32_t *face_index_map = c->face_index_map;
+    const REAL *rgb_map = c->rgb_map, *alpha_map = c->alpha_map;
+    const REAL *grad_rgb_map = c->grad_rgb_map, *grad_alpha_map = c->grad_alpha_map;
+    REAL *grad_faces = c->grad_faces;
+    const int num_faces = c->num_faces, is = c->image_size;
+    const REAL eps = c->eps;
+    const int return_rgb = c->return_rgb, return_alpha = c->return_alpha;
+    for (long i = begin; i < end; i++) {
         const int bn = (int)(i / num_faces);
         const int fn = (int)(i % num_faces);
         const REAL *face = &faces[i * 9];
@@ -301,6 +333,16 @@ void FN(backward_pixel_map)(const REAL *faces, const int32_t *face_index_map, co
         for (int k = 0; k < 9; k++)
             grad_faces[i * 9 + k] = grad_face[k];
     }
+}
+
+void FN(backward_pixel_map)(const REAL *faces, const int32_t *face_index_map, const REAL *rgb_map,
+                            const REAL *alpha_map, const REAL *grad_rgb_map, const REAL *grad_alpha_map,
+                            REAL *grad_faces, int batch_size, int num_faces, int image_size, REAL eps,
+                            int return_rgb, int return_alpha)
+{
+    struct FN(k4_ctx) c = {faces, face_index_map, rgb_map, alpha_map, grad_rgb_map, grad_alpha_map, grad_faces,
+                           num_faces, image_size, eps, return_rgb, return_alpha};
+    ora_parallel_for((long)batch_size * num_faces, FN(k4_range), &c);
 }
 
 /* K5: exact gradient w.r.t. the texture cubes, rasterize.py:284-297 (Appendix C5).  Accumulates

@@ -94,7 +94,8 @@ def _ignore_mask(face_index_map, ignore_face_idxs):
 
 
 def get_opticalflow(verts_cam, faces, camintrs, image_size, orig_img_size=None, mask_occlusions=True,
-                    detach_textures=False, detach_renders=True, ignore_face_idxs=None, grad_dtype=np.float32):
+                    detach_textures=False, detach_renders=True, ignore_face_idxs=None, grad_dtype=np.float32,
+                    warp_device=None):
     loc1 = nrfuncs.batch_proj2d(verts_cam[0], camintrs[0])
     loc2 = nrfuncs.batch_proj2d(verts_cam[1], camintrs[1])
     d12 = loc2 - loc1
@@ -116,7 +117,12 @@ def get_opticalflow(verts_cam, faces, camintrs, image_size, orig_img_size=None, 
     if mask_occlusions:
         with torch.no_grad():
             mask2 = out["alpha"].unsqueeze(1)  # sic, opticalflow.py:139
-            o1, o2 = owarp.get_occlusion_mask(mask1, mask2, flow12, flow21)
+            if warp_device is not None:  # the reference runs these ATen ops on CUDA
+                o1, o2 = owarp.get_occlusion_mask(mask1.to(warp_device), mask2.to(warp_device),
+                                                  flow12.to(warp_device), flow21.to(warp_device))
+                o1, o2 = o1.cpu(), o2.cpu()
+            else:
+                o1, o2 = owarp.get_occlusion_mask(mask1, mask2, flow12, flow21)
         mask1 = mask1 * o1.unsqueeze(1)
         mask2 = mask2 * o2.unsqueeze(1)
         flow12 = flow12 * mask1
@@ -130,9 +136,18 @@ def get_opticalflow(verts_cam, faces, camintrs, image_size, orig_img_size=None, 
 
 
 def consist_step(verts1, verts2, faces, K, image_ref, image, jitter_mask_ref, jitter_mask, image_size, orig_img_size,
-                 ignore_face_idxs=None, detach_renders=True, use_backward=True, grad_dtype=np.float32):
-    """flows -> pair_consist -> mean over the batch (warpbranch.py:57-88 for one pair)."""
+                 ignore_face_idxs=None, detach_renders=True, use_backward=True, grad_dtype=np.float32,
+                 warp_device=None):
+    """flows -> pair_consist -> mean over the batch (warpbranch.py:57-88 for one pair).
+
+    ``warp_device``: run the warp / mask / loss ATen ops there (autograd crosses devices).  The
+    reference's masks hold exact float tests (== 1, >= 0.99999) whose outcome depends on the rounding
+    of ATen's CPU vs CUDA grid_sampler; the reference runs them on CUDA, so the GPU tests pass "cuda"."""
     flows = get_opticalflow([verts1, verts2], faces, [K, K], image_size, orig_img_size, True, False, detach_renders,
-                            ignore_face_idxs, grad_dtype)
+                            ignore_face_idxs, grad_dtype, warp_device)
+    if warp_device is not None:
+        mv = lambda t: t.to(warp_device)
+        flows = [mv(f) for f in flows]
+        image_ref, image, jitter_mask_ref, jitter_mask = mv(image_ref), mv(image), mv(jitter_mask_ref), mv(jitter_mask)
     loss, masks, warps, diffs = owarp.pair_consist(flows, image_ref, image, jitter_mask_ref, jitter_mask, use_backward)
     return loss.mean(), dict(flows=flows, loss=loss, masks=masks, warps=warps, diffs=diffs)

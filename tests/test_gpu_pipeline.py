@@ -1,0 +1,92 @@
+"""GPU end-to-end parity: vertices -> rendered flows -> occlusion -> warp -> masked L1 -> backward, through
+the reference-shaped surface (Renderer, get_opticalflow, pair_consist, warpbranch.forward), against the
+oracle pipeline (C restatement of the rasterizer on the CPU + the reference's warp ops run by ATen on
+CUDA, where the reference runs them).  Bar: flows / loss 1e-4 abs, vertex gradients 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from handobjectconsist_b200 import synth
+from oracle import pipeline as opipe
+
+pytestmark = pytest.mark.gpu
+
+
+def _renderer(S, dev):
+    from handobjectconsist_b200.neurender.renderer import Renderer
+    return Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                    K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True, near=0.1,
+                    no_light=True)
+
+
+@pytest.mark.parametrize("S,crop,detach,use_bwd,seed", [
+    (64, (64, 64), False, True, 0),
+    (64, (64, 64), True, False, 1),     # the reference's training setting (warpbranch.py:59-68, CLI default)
+    (96, (96, 54), True, True, 2),      # rectangular image inside a square raster
+    (128, (128, 128), False, True, 3),
+])
+def test_consist_step_matches_oracle(S, crop, detach, use_bwd, seed):
+    from handobjectconsist_b200 import warpbranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    B = 2
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, crop[0], crop[1], seed=seed)
+    sc["K"] = synth.camera_intrinsics(B, S, S)  # camera of the square raster
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    v1 = g["verts1"].clone().requires_grad_(True)
+    loss, res = warpbranch.consist_step(v1, g["verts2"], g["faces"], g["K"], g["image_ref"], g["image"],
+                                        g["jitter_mask_ref"], g["jitter_mask"], _renderer(S, dev),
+                                        PyramidCriterion("l1"), crop, sc["hand_ignore_faces"], detach_renders=detach,
+                                        use_backward=use_bwd)
+    loss.backward()
+    c1 = sc["verts1"].clone().requires_grad_(True)
+    loss_o, res_o = opipe.consist_step(c1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                       sc["jitter_mask_ref"], sc["jitter_mask"], S, crop, sc["hand_ignore_faces"],
+                                       detach_renders=detach, use_backward=use_bwd, warp_device=dev)
+    loss_o.backward()
+    for i in range(2):
+        assert res["flows"][i].shape == (B, crop[1], crop[0], 2)
+        assert (res["flows"][i].detach() - res_o["flows"][i].detach()).abs().max().item() <= 1e-4
+        assert torch.equal(res["masks"][i]["full_mask"], res_o["masks"][i]["full_mask"])
+    assert res_o["masks"][0]["full_mask"].float().mean().item() > 0.005
+    assert abs(loss.item() - loss_o.item()) <= 1e-4
+    go = c1.grad.numpy()
+    assert np.abs(go).max() > 0
+    assert helpers.rel_err(v1.grad.cpu().numpy(), go) < 1e-3
+
+
+def test_warpbranch_forward_batch_dicts():
+    """The reference's calling convention: sample dicts keyed by TransQueries/BaseQueries + result dicts."""
+    from handobjectconsist_b200 import warpbranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+    S, B = 64, 2
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, S, seed=5)
+    hv = 778
+    obj_faces = sc["faces"][:, 1552:] - hv
+    samples, results = [], []
+    for verts, img, jit in ((sc["verts1"], sc["image_ref"], sc["jitter_mask_ref"]),
+                            (sc["verts2"], sc["image"], sc["jitter_mask"])):
+        samples.append({TransQueries.IMAGE: img, TransQueries.JITTERMASK: jit, TransQueries.CAMINTR: sc["K"],
+                        BaseQueries.OBJFACES: obj_faces, BaseQueries.OBJVERTS3D: verts[:, hv:],
+                        BaseQueries.HANDVERTS3D: verts[:, :hv]})
+        results.append({"recov_handverts3d": verts[:, :hv].to(dev), "recov_objverts3d": verts[:, hv:].to(dev)})
+    h = results[0]["recov_handverts3d"].requires_grad_(True)
+    o = results[0]["recov_objverts3d"].requires_grad_(True)
+    # second frame prediction is garbage on purpose: gt_refs must replace it by the sample's GT vertices
+    results[1] = {k: torch.zeros_like(v) for k, v in results[1].items()}
+    loss, pair = warpbranch.forward(samples, results, sc["faces"][0, :1552].to(dev), _renderer(S, dev), (S, S),
+                                    PyramidCriterion("l1"), gt_refs=True, first_only=True,
+                                    hand_ignore_faces=sc["hand_ignore_faces"], use_backward=True)
+    loss.backward()
+    c1 = sc["verts1"].clone().requires_grad_(True)
+    loss_o, _ = opipe.consist_step(c1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                   sc["jitter_mask_ref"], sc["jitter_mask"], S, (S, S), sc["hand_ignore_faces"],
+                                   detach_renders=True, use_backward=True, warp_device=dev)
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) <= 1e-4
+    g = torch.cat([h.grad, o.grad], 1).cpu().numpy()
+    assert helpers.rel_err(g, c1.grad.numpy()) < 1e-3
+    assert set(pair.keys()) == {"masks", "warps", "recons_flows", "diffs", "diff_losses"}

@@ -82,9 +82,8 @@ def test_forward_image_layout_is_flipped_nchw():
     np.testing.assert_array_equal(img["idx"], raw["idx"])
 
 
-@pytest.mark.parametrize("dense", [True, False])
-def test_backward_matches_oracle(dense):
-    S = 48
+@pytest.mark.parametrize("dense,S", [(True, 48), (False, 48), (False, 96)])
+def test_backward_matches_oracle(dense, S):
     faces, tex, _ = helpers.scene_faces(2, S, seed=1)
     ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
     rng = np.random.default_rng(0)
@@ -95,12 +94,17 @@ def test_backward_matches_oracle(dense):
         cov = (ora["face_index_map"] >= 0).astype(np.float32)
         g_rgb *= cov[..., None]
         g_alpha *= cov
+    gf32, gt32 = onmr.rasterize_backward(ora, g_rgb, g_alpha, g_depth)
     gf64, gt64 = onmr.rasterize_backward(ora, g_rgb, g_alpha, g_depth, dtype=np.float64)
     gf, gt = emul_backward(faces, ora["face_index_map"], ora["rgb_map"], g_rgb, g_alpha, g_depth, S)
     assert np.isfinite(gf).all() and np.isfinite(gt).all()
-    assert np.abs(gf64).max() > 0 and np.abs(gt64).max() > 0
-    assert helpers.rel_err(gt, gt64) < 1e-3
-    assert helpers.rel_err(gf, gf64) < 1e-3
+    assert np.abs(gf32).max() > 0 and np.abs(gt32).max() > 0
+    # same fp32 decisions as the reference restatement -> element-wise 1e-3
+    assert helpers.rel_err(gt, gt32) < 1e-3
+    assert helpers.rel_err(gf, gf32) < 1e-3
+    # fp64 re-evaluation flips a few floor/ceil / sign gates: norm-wise bound only
+    assert np.linalg.norm(gf - gf64) / np.linalg.norm(gf64) < 2e-2
+    assert np.linalg.norm(gt - gt64) / np.linalg.norm(gt64) < 2e-2
 
 
 def test_backward_float_oracle_agrees_with_double():
