@@ -18,9 +18,9 @@ def batch_vertex_textures(faces, vertex_colors):
     barycentric coordinates (b0,b1,b2) is b0*c0 + b1*c1 + b2*c2, i.e. T[i,j,k] = i*c0 + j*c1 + k*c2
     (the multilinear extension)."""
     B, Fn = faces.shape[:2]
-    idx = faces.long()
-    cols = torch.gather(vertex_colors.unsqueeze(1).expand(B, Fn, -1, 3), 2,
-                        idx.unsqueeze(-1).expand(B, Fn, 3, 3))  # [B,F,vertex,channel]
+    V = vertex_colors.shape[1]
+    idx = faces.long() + (torch.arange(B, device=faces.device) * V)[:, None, None]
+    cols = vertex_colors.reshape(B * V, 3)[idx]  # [B,F,vertex,channel]
     basis = vertex_colors.new_zeros(2, 2, 2, 3)
     basis[1, :, :, 0] = 1
     basis[:, 1, :, 1] = 1

@@ -61,7 +61,7 @@ def test_forward_flags_and_disabled_outputs():
     _, _, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, None, S, rr=False, ra=True, rd=False)
     assert rgb.numel() == 0 and depth.numel() == 0 and inv.numel() == 1
     ora = onmr.rasterize_forward(faces, None, S, 0.1, 100.0, 1e-3, (0, 0, 0), False, True, False)
-    np.testing.assert_array_equal(alpha.cpu().numpy(), ora["alpha_map"])
+    np.testing.assert_array_equal(alpha.detach().cpu().numpy(), ora["alpha_map"])
     np.testing.assert_array_equal(idx.cpu().numpy(), ora["face_index_map"])
 
 
