@@ -42,10 +42,16 @@ SIGNATURES = {
     "hoc_warp": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "hoc_warp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "hoc_occlusion_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "hoc_mesh_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hoc_mesh_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hoc_flow_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp,
+                               _vp]),
+    "hoc_flow_finalize_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
 }
 
 KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_backward": 3, "warp_photo_fwd": 4,
-              "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8}
+              "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8, "mesh_gather": 9, "mesh_scatter": 10,
+              "flow_finalize": 11, "flow_finalize_bwd": 12}
 
 _LIB = None
 

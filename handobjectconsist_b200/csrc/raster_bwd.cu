@@ -6,21 +6,15 @@
  * 269-281, 290-297, 306-315) and the zero-fills of rasterize.py:151-181.
  *
  * The reference scatters texture / depth gradients from every pixel with float atomics and runs
- * the pseudo-gradient as one serial thread per face.  Here ONE WARP owns ONE FACE and produces
- * all of that face's gradients, so nothing is accumulated atomically, the result is
- * deterministic and the output buffers need no zero-fill:
- *
- *   part A (textures + depth)  the warp sweeps the face's clipped pixel bounding box, keeps the
- *           pixels whose face_index_map entry is this face, recomputes weights / depth / the
- *           eight trilinear taps with the forward's functions (bit-identical, so neither
- *           weight_map, face_inv_map nor the two sampling maps are ever stored or read) and
- *           reduces the per-lane partial sums with shuffles.
- *   part B (pseudo-gradient)   lanes take the integer columns (rows) crossed by the three
- *           edges; each lane does its short inward scan itself; the long outward scans (to the
- *           image border) are executed cooperatively, 32 pixels per step, coalesced along rows,
- *           and clipped to the span of the line where the incoming gradient is non-zero (a
- *           pixel with zero incoming gradient contributes exactly nothing).  That span table is
- *           built by hoc_grad_extent_kernel, a streaming pre-pass over the incoming gradients.
+ * the pseudo-gradient as one serial thread per face over whole image rows / columns.  Here a CTA owns
+ * 256 faces: a thread sweeps the few pixels of its own face for the texture / depth terms (registers,
+ * no atomics, no zero-fill of the outputs), the faces that own pixels are compacted and their
+ * (face, edge, axis) scan tasks are spread over the CTA, and the long outward scans are clipped to the
+ * span of the line where the incoming gradient is non-zero (a pixel with zero incoming gradient
+ * contributes exactly nothing).  That span table is built by hoc_grad_extent_kernel, a streaming
+ * pre-pass over the incoming gradients.  Weights, depth and texture taps are recomputed with the
+ * forward's functions (bit-identical), so neither weight_map, face_inv_map nor the two sampling maps
+ * of the reference are ever stored or read.
  */
 #include "hoc_common.cuh"
 #include "raster_math.h"
@@ -126,9 +120,142 @@ __device__ __forceinline__ float hoc_delta(const HocBwdMaps &M, int xi, int yi, 
     return d;
 }
 
-#define BW_WARPS 8
-#define BW_THREADS (BW_WARPS * 32)
+#define BW_THREADS 256
+#define BW_WARPS (BW_THREADS / 32)
+#define BW_BIG 128 /* bounding boxes with more pixels than this are swept by the whole CTA */
 
+/* Per-pixel contribution of an owned pixel to the texture (ts == 2: 8 cube corners x 3 channels) and
+ * depth accumulators of its face. */
+template <bool TS2>
+__device__ __forceinline__ void hoc_bwd_pixel(const float *f, const float *inv, int xi, int yi, int b, int S, int ts,
+                                              float near_, float far_, float eps, int layout, bool want_tex,
+                                              bool want_depth, const float *__restrict__ g_rgb,
+                                              const float *__restrict__ g_depth, float *acc_t, float *acc_d,
+                                              float *gt, bool gt_shared)
+{
+    float w[3], zp;
+    hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+    if (want_depth) {
+        const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            acc_d[k] += gz * w[k];
+    }
+    if (want_tex) {
+        float gr[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            gr[c] = g_rgb[hoc_rgb_off(layout, S, b, yi, xi, c)];
+        float tf[3];
+        int ti[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
+            ti[k] = hoc_tex_cell(t, ts);
+            tf[k] = t - (float)ti[k];
+        }
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            float ww = 1.0f;
+            int isc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (((pn >> k) & 1) == 0) {
+                    ww *= 1.0f - tf[k];
+                    isc = isc * ts + ti[k];
+                } else {
+                    ww *= tf[k];
+                    isc = isc * ts + ti[k] + 1;
+                }
+            }
+            if (TS2) {
+                /* ts == 2: floor(t) == 0, tap pn is cube corner (b0,b1,b2) */
+                const int corner = ((pn & 1) << 2) | (pn & 2) | ((pn >> 2) & 1);
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    acc_t[corner * 3 + c] += ww * gr[c];
+            } else {
+                if (ts == 1)
+                    isc = 0;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    if (gt_shared)
+                        atomicAdd(gt + isc * 3 + c, ww * gr[c]); /* CTA-cooperative sweep of a big face */
+                    else
+                        gt[isc * 3 + c] += ww * gr[c];           /* the face is private to this thread */
+                }
+            }
+        }
+    }
+}
+
+/* One (face, edge, axis) task of the pseudo-gradient: every integer column crossed by the edge, its
+ * inward scan and (when the inside pixel is owned by the face) its outward scan clipped to the span of
+ * non-zero incoming gradient.  Contributions to vertex A = edge and B = edge+1. */
+__device__ __forceinline__ void hoc_k4_task(const float *f, int fi, int edge, int axis, const HocBwdMaps &M,
+                                            const int *__restrict__ e, float eps, float *gA_out, float *gB_out)
+{
+    const int S = M.S;
+    HocK4Edge E;
+    hoc_k4_edge(f, S, edge, axis, &E);
+    float gA = 0.0f, gB = 0.0f;
+    for (int d0 = E.d0_from; d0 <= E.d0_to; d0++) {
+        float d1_cross;
+        int d1_in, d1_out;
+        if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out))
+            continue;
+        const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+        const int xout = axis == 0 ? d0 : d1_out, yout = axis == 0 ? d1_out : d0;
+        if (M.idx[(long)yin * S + xin] == fi) {
+            float I_in[4];
+            hoc_load_I(M, xin, yin, I_in);
+            const int d1_limit = (0 < E.dir) ? S - 1 : 0;
+            int d1_from = max(min(d1_out, d1_limit), 0);
+            int d1_to = min(max(d1_out, d1_limit), S - 1);
+            /* clip to where the incoming gradient of this line is non-zero */
+            d1_from = max(d1_from, (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0]);
+            d1_to = min(d1_to, (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0]);
+            for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+                const float delta = hoc_delta(M, xi, yi, I_in);
+                if (delta <= 0.0f)
+                    continue;
+                hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+            }
+        }
+        const int lim = hoc_k4_inward_limit(&E, d0);
+        const int d1_from = max(min(d1_in, lim), 0);
+        const int d1_to = min(max(d1_in, lim), S - 1);
+        bool have_out = false;
+        float I_out[4];
+        for (int d1 = d1_from; d1 <= d1_to; d1++) {
+            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+            if (M.idx[(long)yi * S + xi] != fi)
+                continue;
+            if (!have_out) {
+                hoc_load_I(M, xout, yout, I_out);
+                have_out = true;
+            }
+            const float delta = hoc_delta(M, xi, yi, I_out);
+            if (delta <= 0.0f)
+                continue;
+            hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+        }
+    }
+    *gA_out = gA;
+    *gB_out = gB;
+}
+
+/*
+ * One CTA owns 256 consecutive faces of one sample.
+ *   phase 1  thread = face: cull, then a serial sweep of the face's own clipped bounding box (faces are a
+ *            few pixels large); owned pixels feed the texture / depth accumulators held in registers.
+ *            Rare large faces are deferred and swept by the whole CTA.
+ *   phase 2  the faces that own at least one pixel are compacted; thread = (face, edge, axis) task of the
+ *            pseudo-gradient (faces that own no pixel cannot contribute: both scans require ownership).
+ *   phase 3  thread = face again: sums the six task results in a fixed order, adds the depth term, stores.
+ * No gradient is accumulated atomically in global memory (ts == 2); results are deterministic.
+ */
 template <bool TS2>
 __global__ void __launch_bounds__(BW_THREADS)
 hoc_raster_backward_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
@@ -138,169 +265,47 @@ hoc_raster_backward_kernel(const float *__restrict__ faces, const float *__restr
                            int layout, int use_alpha, const int *__restrict__ ext, float *__restrict__ grad_faces,
                            float *__restrict__ grad_textures)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int b = blockIdx.y;
-    const int fi = blockIdx.x * BW_WARPS + warp;
-    if (fi >= F)
-        return;
+    __shared__ float s_face[BW_THREADS][9];
+    __shared__ float s_k4[BW_THREADS][6][2];
+    __shared__ unsigned short s_vis[BW_THREADS];
+    __shared__ unsigned short s_big[BW_THREADS];
+    __shared__ float s_red[BW_WARPS][28];
+    __shared__ int s_nvis, s_nbig;
 
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int f_base = blockIdx.x * BW_THREADS;
+    const int fi = f_base + tid;
+    const bool valid = fi < F;
+    const int tex_n = ts * ts * ts * 3;
+    const int32_t *idx = face_index_map + (long)b * S * S;
+
+    if (tid == 0) {
+        s_nvis = 0;
+        s_nbig = 0;
+    }
     float f[9];
-    {
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+        f[k] = 0.0f;
+    if (valid) {
         const float *src = faces + ((long)b * F + fi) * 9;
 #pragma unroll
         for (int k = 0; k < 9; k++)
             f[k] = __ldg(src + k);
     }
-    const int tex_n = ts * ts * ts * 3;
-    float *gt = (grad_textures != nullptr) ? grad_textures + ((long)b * F + fi) * tex_n : nullptr;
-    float *gf = (grad_faces != nullptr) ? grad_faces + ((long)b * F + fi) * 9 : nullptr;
-
-    const bool front = hoc_face_xy_finite(f) && !hoc_face_back(f);
-    if (!front) {
-        if (gf != nullptr && lane < 9)
-            gf[lane] = 0.0f;
-        if (gt != nullptr)
-            for (int i = lane; i < tex_n; i += 32)
-                gt[i] = 0.0f;
-        return;
-    }
-
-    const int32_t *idx = face_index_map + (long)b * S * S;
-
-    /* ---------------- part A: texture + depth gradients over the bounding box -------------- */
-    float acc_t[24];
-    float acc_d[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int k = 0; k < 24; k++)
-        acc_t[k] = 0.0f;
-    float inv[9];
-    hoc_face_inv(f, S, inv);
-    const bool want_tex = (gt != nullptr) && (g_rgb != nullptr);
-    const bool want_depth = (gf != nullptr) && (g_depth != nullptr);
-    if (gt != nullptr && (!TS2 || !want_tex)) {
-        for (int i = lane; i < tex_n; i += 32)
-            gt[i] = 0.0f;
-        __syncwarp();
-    }
-    bool any_hit = false;
-    if (want_tex || want_depth) {
-        const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
-        const float pxmax = hoc_ndc_to_pix(fmaxf(f[0], fmaxf(f[3], f[6])), S);
-        const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
-        const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
-        const float fS1 = (float)(S - 1);
-        const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
-        const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
-        const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
-        const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
-        if (x_lo <= x_hi && y_lo <= y_hi) {
-            const int x0 = (int)x_lo, y0 = (int)y_lo;
-            const int bw = (int)(x_hi - x_lo + 1.0f), bh = (int)(y_hi - y_lo + 1.0f);
-            const int n = bw * bh;
-            for (int p = lane; p < n; p += 32) {
-                const int yy = p / bw;
-                const int xi = x0 + (p - yy * bw);
-                const int yi = y0 + yy;
-                if (idx[(long)yi * S + xi] != fi)
-                    continue;
-                any_hit = true;
-                float w[3], zp;
-                hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
-                if (want_depth) {
-                    const float gd = g_depth[hoc_plane_off(layout, S, b, yi, xi)];
-                    const float gz = gd * zp * zp;
-#pragma unroll
-                    for (int k = 0; k < 3; k++)
-                        acc_d[k] += gz * w[k];
-                }
-                if (want_tex) {
-                    float gr[3];
-#pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        gr[c] = g_rgb[hoc_rgb_off(layout, S, b, yi, xi, c)];
-                    float tf[3];
-                    int ti[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
-                        ti[k] = hoc_tex_cell(t, ts);
-                        tf[k] = t - (float)ti[k];
-                    }
-#pragma unroll
-                    for (int pn = 0; pn < 8; pn++) {
-                        float ww = 1.0f;
-                        int isc = 0;
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            if (((pn >> k) & 1) == 0) {
-                                ww *= 1.0f - tf[k];
-                                isc = isc * ts + ti[k];
-                            } else {
-                                ww *= tf[k];
-                                isc = isc * ts + ti[k] + 1;
-                            }
-                        }
-                        if (TS2) {
-                            /* ts == 2: floor(t) == 0, tap pn is cube corner (b0,b1,b2) */
-                            const int corner = ((pn & 1) << 2) | (pn & 2) | ((pn >> 2) & 1);
-#pragma unroll
-                            for (int c = 0; c < 3; c++)
-                                acc_t[corner * 3 + c] += ww * gr[c];
-                        } else {
-                            if (ts == 1)
-                                isc = 0;
-#pragma unroll
-                            for (int c = 0; c < 3; c++)
-                                atomicAdd(gt + isc * 3 + c, ww * gr[c]);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    any_hit = __any_sync(HOC_FULL_MASK, any_hit);
-    if (any_hit) {
-        if (want_depth) {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                acc_d[k] = hoc_warp_sum(acc_d[k]);
-        }
-        if (TS2 && want_tex) {
-#pragma unroll
-            for (int k = 0; k < 24; k++)
-                acc_t[k] = hoc_warp_sum(acc_t[k]);
-        }
-    }
-    if (TS2 && want_tex && lane == 0) {
-        float4 *dst = reinterpret_cast<float4 *>(gt); /* 96 B per face, 16 B aligned */
-#pragma unroll
-        for (int q = 0; q < 6; q++)
-            dst[q] = make_float4(acc_t[4 * q], acc_t[4 * q + 1], acc_t[4 * q + 2], acc_t[4 * q + 3]);
-    }
-    if (gf == nullptr)
-        return;
-
-    /* depth gradient of the face (backward_depth_map), from A_k = sum gd * zp^2 * w_k */
-    float gface[9];
 #pragma unroll
     for (int k = 0; k < 9; k++)
-        gface[k] = 0.0f;
-    if (want_depth && any_hit) {
-        float tmp[2];
+        s_face[tid][k] = f[k];
 #pragma unroll
-        for (int l = 0; l < 2; l++)
-            tmp[l] = inv[l] / f[2] + inv[3 + l] / f[5] + inv[6 + l] / f[8];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const float zk = f[3 * k + 2];
-            gface[3 * k + 2] = acc_d[k] / (zk * zk);
-            gface[3 * k + 0] = acc_d[k] * tmp[0] * (float)S / 2.0f;
-            gface[3 * k + 1] = acc_d[k] * tmp[1] * (float)S / 2.0f;
-        }
-    }
+    for (int k = 0; k < 12; k++)
+        (&s_k4[tid][0][0])[k] = 0.0f;
 
-    /* ---------------- part B: pseudo-gradient of rgb / alpha w.r.t. vertex xy -------------- */
+    float *gt = (grad_textures != nullptr && valid) ? grad_textures + ((long)b * F + fi) * tex_n : nullptr;
+    float *gf = (grad_faces != nullptr && valid) ? grad_faces + ((long)b * F + fi) * 9 : nullptr;
+    const bool front = valid && hoc_face_xy_finite(f) && !hoc_face_back(f);
+
     HocBwdMaps M;
     M.idx = idx;
     M.rgb = rgb;
@@ -311,98 +316,167 @@ hoc_raster_backward_kernel(const float *__restrict__ faces, const float *__restr
     M.b = b;
     M.use_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     M.use_rgb = (rgb != nullptr) && (g_rgb != nullptr);
+    const bool want_tex = (grad_textures != nullptr) && (g_rgb != nullptr);
+    const bool want_depth = (grad_faces != nullptr) && (g_depth != nullptr);
+    const bool want_k4 = (grad_faces != nullptr) && (M.use_alpha || M.use_rgb);
 
-    float gsum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}; /* slot = vertex * 2 + (0: x, 1: y) */
-    if (M.use_alpha || M.use_rgb) {
-        const int *e = ext + (long)b * 4 * S;
-        for (int combo = 0; combo < 6; combo++) {
-            const int edge = combo >> 1, axis = combo & 1;
-            HocK4Edge E;
-            hoc_k4_edge(f, S, edge, axis, &E);
-            const int n = E.d0_to - E.d0_from + 1;
-            if (n <= 0)
-                continue;
-            float gA = 0.0f, gB = 0.0f;
-            for (int base = 0; base < n; base += 32) {
-                const int t = base + lane;
-                const int d0 = E.d0_from + t;
-                bool pending = false;
-                float d1_cross = 0.0f;
-                int d1_in = 0, d1_out = 0;
-                float I_in[4] = {0.f, 0.f, 0.f, 0.f};
-                if (t < n && hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out)) {
-                    const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
-                    const int xout = axis == 0 ? d0 : d1_out, yout = axis == 0 ? d1_out : d0;
-                    float I_out[4];
-                    hoc_load_I(M, xin, yin, I_in);
-                    hoc_load_I(M, xout, yout, I_out);
-                    pending = (idx[(long)yin * S + xin] == fi);
-                    /* inward scan, lane-serial (bounded by the face's own extent) */
-                    const int lim = hoc_k4_inward_limit(&E, d0);
-                    const int d1_from = max(min(d1_in, lim), 0);
-                    const int d1_to = min(max(d1_in, lim), S - 1);
-                    for (int d1 = d1_from; d1 <= d1_to; d1++) {
-                        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+    /* generic texture size: the texture gradient block is accumulated in place, zero it first */
+    if (gt != nullptr && (!TS2 || !want_tex || !front))
+        for (int i = 0; i < tex_n; i++)
+            gt[i] = 0.0f;
+    __syncthreads(); /* counters + (for big faces) zero-fills visible CTA-wide */
+
+    /* ---------------- phase 1: texture + depth gradients, ownership ---------------- */
+    float acc_t[24];
+    float acc_d[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 24; k++)
+        acc_t[k] = 0.0f;
+    float inv[9];
+    bool hit = false;
+    if (front) {
+        hoc_face_inv(f, S, inv);
+        const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
+        const float pxmax = hoc_ndc_to_pix(fmaxf(f[0], fmaxf(f[3], f[6])), S);
+        const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
+        const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
+        const float fS1 = (float)(S - 1);
+        const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
+        const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
+        const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
+        const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
+        if (x_lo <= x_hi && y_lo <= y_hi) {
+            const int x0 = (int)x_lo, y0 = (int)y_lo, x1 = (int)x_hi, y1 = (int)y_hi;
+            if ((x1 - x0 + 1) * (y1 - y0 + 1) > BW_BIG) {
+                s_big[atomicAdd(&s_nbig, 1)] = (unsigned short)tid;
+            } else {
+                for (int yi = y0; yi <= y1; yi++)
+                    for (int xi = x0; xi <= x1; xi++) {
                         if (idx[(long)yi * S + xi] != fi)
                             continue;
-                        const float delta = hoc_delta(M, xi, yi, I_out);
-                        if (delta <= 0.0f)
-                            continue;
-                        hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+                        hit = true;
+                        hoc_bwd_pixel<TS2>(f, inv, xi, yi, b, S, ts, near_, far_, eps, layout, want_tex, want_depth,
+                                           g_rgb, g_depth, acc_t, acc_d, gt, false);
                     }
-                }
-                /* outward scans, cooperative: 32 pixels of one scan per step */
-                unsigned m = __ballot_sync(HOC_FULL_MASK, pending);
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int s_d0 = __shfl_sync(HOC_FULL_MASK, d0, j);
-                    const int s_out = __shfl_sync(HOC_FULL_MASK, d1_out, j);
-                    const float s_cross = __shfl_sync(HOC_FULL_MASK, d1_cross, j);
-                    float s_I[4];
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        s_I[k] = __shfl_sync(HOC_FULL_MASK, I_in[k], j);
-                    const int d1_limit = (0 < E.dir) ? S - 1 : 0;
-                    int d1_from = max(min(s_out, d1_limit), 0);
-                    int d1_to = min(max(s_out, d1_limit), S - 1);
-                    /* clip to where the incoming gradient of this line is non-zero */
-                    const int lo = (axis == 0) ? e[EXT_COL_LO * S + s_d0] : e[EXT_ROW_LO * S + s_d0];
-                    const int hi = (axis == 0) ? e[EXT_COL_HI * S + s_d0] : e[EXT_ROW_HI * S + s_d0];
-                    d1_from = max(d1_from, lo);
-                    d1_to = min(d1_to, hi);
-                    for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
-                        const int xi = axis == 0 ? s_d0 : d1, yi = axis == 0 ? d1 : s_d0;
-                        const float delta = hoc_delta(M, xi, yi, s_I);
-                        if (delta <= 0.0f)
-                            continue;
-                        hoc_k4_accum(&E, S, s_d0, d1, s_cross, eps, delta, &gA, &gB);
-                    }
-                }
-            }
-            /* A = edge, B = edge+1; the walk along axis updates the perpendicular coordinate */
-            const int slotA = edge * 2 + (1 - axis);
-            const int slotB = ((edge + 1) % 3) * 2 + (1 - axis);
-#pragma unroll
-            for (int s = 0; s < 6; s++) {
-                if (s == slotA)
-                    gsum[s] += gA;
-                if (s == slotB)
-                    gsum[s] += gB;
             }
         }
-#pragma unroll
-        for (int s = 0; s < 6; s++)
-            gsum[s] = hoc_warp_sum(gsum[s]);
     }
-    if (lane == 0) {
+    __syncthreads();
+    /* large faces: the whole CTA sweeps the bounding box, block reduction, owner thread keeps the sums */
+    const int nbig = s_nbig;
+    for (int q = 0; q < nbig; q++) {
+        const int owner = s_big[q];
+        float bf[9], binv[9];
 #pragma unroll
-        for (int v = 0; v < 3; v++) {
-            gf[3 * v + 0] = gsum[2 * v + 0] + gface[3 * v + 0];
-            gf[3 * v + 1] = gsum[2 * v + 1] + gface[3 * v + 1];
-            gf[3 * v + 2] = gface[3 * v + 2];
+        for (int k = 0; k < 9; k++)
+            bf[k] = s_face[owner][k];
+        hoc_face_inv(bf, S, binv);
+        const float fS1 = (float)(S - 1);
+        const int x0 = (int)fmaxf(ceilf(hoc_ndc_to_pix(fminf(bf[0], fminf(bf[3], bf[6])), S) - 0.5f), 0.0f);
+        const int x1 = (int)fminf(floorf(hoc_ndc_to_pix(fmaxf(bf[0], fmaxf(bf[3], bf[6])), S) + 0.5f), fS1);
+        const int y0 = (int)fmaxf(ceilf(hoc_ndc_to_pix(fminf(bf[1], fminf(bf[4], bf[7])), S) - 0.5f), 0.0f);
+        const int y1 = (int)fminf(floorf(hoc_ndc_to_pix(fmaxf(bf[1], fmaxf(bf[4], bf[7])), S) + 0.5f), fS1);
+        const int bw = x1 - x0 + 1, n = bw * (y1 - y0 + 1);
+        const int bfi = f_base + owner;
+        float part[28];
+#pragma unroll
+        for (int k = 0; k < 28; k++)
+            part[k] = 0.0f;
+        float *bgt = (grad_textures != nullptr) ? grad_textures + ((long)b * F + bfi) * tex_n : nullptr;
+        for (int p = tid; p < n; p += BW_THREADS) {
+            const int yy = p / bw, xi = x0 + (p - yy * bw), yi = y0 + yy;
+            if (idx[(long)yi * S + xi] != bfi)
+                continue;
+            part[27] = 1.0f;
+            hoc_bwd_pixel<TS2>(bf, binv, xi, yi, b, S, ts, near_, far_, eps, layout, want_tex, want_depth, g_rgb,
+                               g_depth, part, part + 24, bgt, true);
+        }
+#pragma unroll
+        for (int k = 0; k < 28; k++) {
+            const float v = hoc_warp_sum(part[k]);
+            if (lane == 0)
+                s_red[warp][k] = v;
+        }
+        __syncthreads();
+        if (tid == owner) {
+            float any = 0.0f;
+            for (int wq = 0; wq < BW_WARPS; wq++) {
+#pragma unroll
+                for (int k = 0; k < 24; k++)
+                    acc_t[k] += s_red[wq][k];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    acc_d[k] += s_red[wq][24 + k];
+                any += s_red[wq][27];
+            }
+            hit = any > 0.0f;
+        }
+        __syncthreads();
+    }
+    if (TS2 && want_tex && front) {
+        float4 *dst = reinterpret_cast<float4 *>(gt); /* 96 B per face, 16 B aligned */
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            dst[q] = make_float4(acc_t[4 * q], acc_t[4 * q + 1], acc_t[4 * q + 2], acc_t[4 * q + 3]);
+    }
+    if (grad_faces == nullptr)
+        return;
+
+    /* ---------------- phase 2: pseudo-gradient tasks of the faces that own pixels ---------------- */
+    if (want_k4) {
+        if (hit)
+            s_vis[atomicAdd(&s_nvis, 1)] = (unsigned short)tid;
+        __syncthreads();
+        const int ntask = s_nvis * 6;
+        const int *e = ext + (long)b * 4 * S;
+        for (int task = tid; task < ntask; task += BW_THREADS) {
+            const int lf = s_vis[task / 6];
+            const int combo = task - (task / 6) * 6;
+            float tf[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                tf[k] = s_face[lf][k];
+            float gA, gB;
+            hoc_k4_task(tf, f_base + lf, combo >> 1, combo & 1, M, e, eps, &gA, &gB);
+            s_k4[lf][combo][0] = gA;
+            s_k4[lf][combo][1] = gB;
+        }
+        __syncthreads();
+    }
+
+    /* ---------------- phase 3: assemble grad_faces ---------------- */
+    if (gf == nullptr)
+        return;
+    float gface[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+        gface[k] = 0.0f;
+    if (front) {
+        if (want_depth && hit) {
+            float tmp[2];
+#pragma unroll
+            for (int l = 0; l < 2; l++)
+                tmp[l] = inv[l] / f[2] + inv[3 + l] / f[5] + inv[6 + l] / f[8];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float zk = f[3 * k + 2];
+                gface[3 * k + 2] = acc_d[k] / (zk * zk);
+                gface[3 * k + 0] = acc_d[k] * tmp[0] * (float)S / 2.0f;
+                gface[3 * k + 1] = acc_d[k] * tmp[1] * (float)S / 2.0f;
+            }
+        }
+        if (want_k4 && hit) {
+#pragma unroll
+            for (int combo = 0; combo < 6; combo++) {
+                const int edge = combo >> 1, axis = combo & 1;
+                gface[edge * 3 + (1 - axis)] += s_k4[tid][combo][0];
+                gface[((edge + 1) % 3) * 3 + (1 - axis)] += s_k4[tid][combo][1];
+            }
         }
     }
+#pragma unroll
+    for (int k = 0; k < 9; k++)
+        gf[k] = gface[k];
 }
 
 extern "C" size_t hoc_raster_backward_workspace_bytes(int B, int F, int S)
@@ -458,7 +532,7 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                                                       layout, ext)));
         HOC_CHECK_LAUNCH("hoc_grad_extent_kernel");
     }
-    dim3 grid((F + BW_WARPS - 1) / BW_WARPS, B);
+    dim3 grid((F + BW_THREADS - 1) / BW_THREADS, B);
     if (ts == 2)
         HOC_LAUNCH(HOC_K_RASTER_BACKWARD, st,
                    (hoc_raster_backward_kernel<true><<<grid, BW_THREADS, 0, st>>>(

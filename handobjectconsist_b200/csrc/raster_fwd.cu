@@ -10,8 +10,9 @@
  * proportional to what is actually covered:
  *
  *   pass 1  hoc_raster_zbuf_kernel      face-parallel.  A warp owns 32 faces: each lane sets up
- *           its own face (cull, barycentric matrix, clipped pixel bounding box), the records
- *           are staged in shared memory and the warp then sweeps the bounding box of one face
+ *           its own face (cull, barycentric matrix, clipped pixel bounding box).  Faces of a few
+ *           pixels (the common case for a 9k-triangle mesh at 256x256) are swept by their own lane;
+ *           larger ones are staged in shared memory and swept by the whole warp, one face
  *           at a time with 32 pixels in flight.  Every pixel that passes the three edge tests
  *           and the near/far test does ONE 64-bit atomicMin on a packed (depth, face) key:
  *           the minimum is the nearest depth and, among exact ties, the lowest face index --
@@ -28,6 +29,7 @@
 #define ZB_WARPS 8
 #define ZB_THREADS (ZB_WARPS * 32)
 #define ZB_REC 24 /* floats per staged face record: 9 face + 9 inverse + 4 bbox (+2 pad) */
+#define ZB_SMALL 48 /* bounding boxes up to this many pixels are swept by one lane */
 
 __global__ void __launch_bounds__(ZB_THREADS)
 hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__restrict__ zbuf, int F, int S,
@@ -44,7 +46,10 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
         s_centre[i] = hoc_pix_centre(i, S);
 
     const int fi = blockIdx.x * ZB_THREADS + warp * 32 + lane;
-    bool active = false;
+    bool active = false; /* large face: swept by the whole warp below */
+    bool small = false;  /* few-pixel face (the common case): swept by its own lane */
+    int sx0 = 0, sy0 = 0, sx1 = -1, sy1 = -1;
+    float sf[9], sinv[9];
     if (fi < F) {
         float f[9];
         const float *src = faces + ((long)b * F + fi) * 9;
@@ -64,27 +69,55 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
             const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
             const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
             if (x_lo <= x_hi && y_lo <= y_hi) {
-                active = true;
                 float inv[9];
                 hoc_face_inv(f, S, inv);
-                float *rec = s_rec[warp][lane];
+                const int x0 = (int)x_lo, y0 = (int)y_lo, x1 = (int)x_hi, y1 = (int)y_hi;
+                if ((x1 - x0 + 1) * (y1 - y0 + 1) <= ZB_SMALL) {
+                    small = true;
+                    sx0 = x0; sy0 = y0; sx1 = x1; sy1 = y1;
 #pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    rec[k] = f[k];
-                    rec[9 + k] = inv[k];
+                    for (int k = 0; k < 9; k++) {
+                        sf[k] = f[k];
+                        sinv[k] = inv[k];
+                    }
+                } else {
+                    active = true;
+                    float *rec = s_rec[warp][lane];
+#pragma unroll
+                    for (int k = 0; k < 9; k++) {
+                        rec[k] = f[k];
+                        rec[9 + k] = inv[k];
+                    }
+                    rec[18] = x_lo;
+                    rec[19] = y_lo;
+                    rec[20] = x_hi - x_lo + 1.0f;
+                    rec[21] = y_hi - y_lo + 1.0f;
                 }
-                rec[18] = x_lo;
-                rec[19] = y_lo;
-                rec[20] = x_hi - x_lo + 1.0f;
-                rec[21] = y_hi - y_lo + 1.0f;
             }
         }
     }
     __syncthreads(); /* s_centre ready; also orders s_rec writes */
 
-    unsigned todo = __ballot_sync(HOC_FULL_MASK, active);
     unsigned long long *zb = zbuf + (long)b * S * S;
     const int f_base = blockIdx.x * ZB_THREADS + warp * 32;
+    if (small) {
+        for (int yi = sy0; yi <= sy1; yi++) {
+            const float yp = s_centre[yi];
+            for (int xi = sx0; xi <= sx1; xi++) {
+                if (!hoc_pixel_inside(sf, s_centre[xi], yp))
+                    continue;
+                float w[3], zp;
+                if (!hoc_pixel_weights_depth(sf, sinv, xi, yi, near_, far_, w, &zp))
+                    continue;
+                if (!(zp < far_))
+                    continue;
+                const unsigned long long key = ((unsigned long long)hoc_float_order(zp) << 32) | (unsigned)fi;
+                atomicMin(zb + (long)yi * S + xi, key);
+            }
+        }
+    }
+    __syncwarp();
+    unsigned todo = __ballot_sync(HOC_FULL_MASK, active);
     while (todo) {
         const int j = __ffs(todo) - 1;
         todo &= todo - 1;

@@ -59,6 +59,10 @@ const char *hoc_last_error(void);
 #define HOC_K_WARP 6
 #define HOC_K_WARP_BWD 7
 #define HOC_K_OCCLUSION 8
+#define HOC_K_MESH_GATHER 9
+#define HOC_K_MESH_SCATTER 10
+#define HOC_K_FLOW_FINALIZE 11
+#define HOC_K_FLOW_FINALIZE_BWD 12
 #define HOC_KERNEL_COUNT 16
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
@@ -151,6 +155,30 @@ int hoc_warp_backward(const float *x, const float *flow_nchw, const float *grad_
  *   occl1, occl2 [B,H,W] out. */
 int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow12, const float *flow21, int B,
                        int Cf, int H, int W, float distance_thresh, float *occl1, float *occl2, void *stream);
+
+/* ---- mesh-flow glue (opticalflow.py:98-154, renderer.py:250-252,282) as kernels ---------------
+ * hoc_mesh_gather: what batch_vertex_textures + fill_back + vertices_to_faces build with ~15 tensor ops.
+ *   verts [B,V,3] (NDC x,y + metric z), attrs [B,V,3] per-vertex values (NULL: no textures),
+ *   faces_idx [B,F,3] int64 -> faces_out [B,F',3,3], textures_out [B,F',2,2,2,3] (F' = 2F when fill_back:
+ *   faces F..2F-1 are the reversed windings, their cubes the permute(0,1,4,3,2,5) of the originals). */
+int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
+                    int fill_back, float *faces_out, float *textures_out, void *stream);
+/* Adjoint: grad_faces [B,F',3,3] / grad_textures [B,F',2,2,2,3] (either may be NULL together with its output)
+ * -> grad_verts [B,V,3], grad_attrs [B,V,3] (zero-filled by the call, accumulated with atomics). */
+int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B, int V,
+                     int F, int fill_back, float *grad_verts, float *grad_attrs, void *stream);
+/* hoc_flow_finalize: everything get_opticalflow does after its two renders (opticalflow.py:109-154): alpha
+ * threshold, ignore-face mask, flow = rgb * mask, forward-backward occlusion check, mask products, channel
+ * slice, crop.  rgb [B,3,S,S] / alpha [B,S,S] in HOC_LAYOUT_IMAGE, idx [B,S,S] raster order;
+ * ignore_faces: device int[n_ignore] (n_ignore <= 64);  outputs flow12 / flow21 [B,H,W,2] and
+ * mult1 / mult2 [B,H,W] = d flow / d rgb (kept for the backward). */
+int hoc_flow_finalize(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
+                      const float *alpha2, const int32_t *idx2, int B, int S, int H, int W, const int *ignore_faces,
+                      int n_ignore, int mask_occlusions, float distance_thresh, float *flow12, float *flow21,
+                      float *mult1, float *mult2, void *stream);
+/* grad_flow [B,H,W,2], mult [B,H,W] -> grad_rgb [B,3,S,S] (fully overwritten; zero outside the crop). */
+int hoc_flow_finalize_backward(const float *grad_flow, const float *mult, int B, int S, int H, int W,
+                               float *grad_rgb, void *stream);
 
 #ifdef __cplusplus
 }
