@@ -29,8 +29,8 @@ SIGNATURES = {
     "hoc_abi_version": (_i, []),
     "hoc_last_error": (ctypes.c_char_p, []),
     "hoc_launch_count": (ctypes.c_ulonglong, [_i]),
-    "hoc_timer_begin": (_i, [_i]),
-    "hoc_timer_end": (_i, [ctypes.POINTER(ctypes.c_float), _i]),
+    "hoc_timer_begin": (_i, [ctypes.c_ulonglong]),
+    "hoc_timer_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), _i]),
     "hoc_raster_forward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
@@ -47,11 +47,15 @@ SIGNATURES = {
     "hoc_flow_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp,
                                _vp]),
     "hoc_flow_finalize_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "hoc_flow_vertices": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp,
+                               _vp]),
+    "hoc_flow_vertices_backward": (_i, [_vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _f, _i, _i, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp]),
 }
 
 KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_backward": 3, "warp_photo_fwd": 4,
               "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8, "mesh_gather": 9, "mesh_scatter": 10,
-              "flow_finalize": 11, "flow_finalize_bwd": 12}
+              "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16}
 
 _LIB = None
 

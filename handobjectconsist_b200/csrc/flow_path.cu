@@ -294,6 +294,172 @@ hoc_flow_finalize_backward_kernel(const float *__restrict__ grad_flow, const flo
     dst[2 * npix] = 0.0f;
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* Per-vertex front end of get_opticalflow for one frame pair (opticalflow.py:98-102,121-122 and
+ * nr.projection as called from renderer.py:187): pixel locations of both frames (batch_proj2d),
+ * their displacements as vertex attributes [dx, dy, 1], and the NDC coordinates of both meshes.
+ * Camera tensors may be shared by the batch (leading dimension 1): *_bs is their batch stride. */
+struct HocCam {
+    const float *K1, *K2, *R, *t, *dist;
+    int K1_bs, K2_bs, R_bs, t_bs, dist_bs; /* 0 when broadcast over the batch */
+    float orig_size;
+};
+
+__device__ __forceinline__ void hoc_proj2d(const float *K, const float *v, float *u, float *w, float *hz)
+{
+    /* accumulate like a GEMM k-loop (the reference's bmm): acc = fma(a_k, b_k, acc) */
+    const float h0 = fmaf(K[2], v[2], fmaf(K[1], v[1], K[0] * v[0]));
+    const float h1 = fmaf(K[5], v[2], fmaf(K[4], v[1], K[3] * v[0]));
+    const float h2 = fmaf(K[8], v[2], fmaf(K[7], v[1], K[6] * v[0]));
+    *u = h0 / h2;
+    *w = h1 / h2;
+    *hz = h2;
+}
+
+/* nr.projection of one vertex; also returns the intermediates the backward needs. */
+struct HocProj {
+    float xc, yc, zc;   /* camera space after R, t */
+    float x_, y_;       /* divided by z + eps */
+    float ndc[3];
+};
+__device__ __forceinline__ void hoc_ndc_project(const float *K, const float *R, const float *t, const float *d,
+                                                float orig, const float *v, HocProj *P)
+{
+    const float xc = fmaf(v[2], R[2], fmaf(v[1], R[1], v[0] * R[0])) + t[0];
+    const float yc = fmaf(v[2], R[5], fmaf(v[1], R[4], v[0] * R[3])) + t[1];
+    const float zc = fmaf(v[2], R[8], fmaf(v[1], R[7], v[0] * R[6])) + t[2];
+    const float x_ = xc / (zc + 1e-9f), y_ = yc / (zc + 1e-9f);
+    const float r = sqrtf(x_ * x_ + y_ * y_);
+    const float r2 = r * r;
+    const float radial = 1.0f + d[0] * r2 + d[1] * (r2 * r2) + d[4] * (r2 * r2 * r2);
+    const float x__ = x_ * radial + 2.0f * d[2] * x_ * y_ + d[3] * (r2 + 2.0f * x_ * x_);
+    const float y__ = y_ * radial + d[2] * (r2 + 2.0f * y_ * y_) + 2.0f * d[3] * x_ * y_;
+    float u = fmaf(1.0f, K[2], fmaf(y__, K[1], x__ * K[0]));
+    float w = fmaf(1.0f, K[5], fmaf(y__, K[4], x__ * K[3]));
+    w = orig - w;
+    u = 2.0f * (u - orig / 2.0f) / orig;
+    w = 2.0f * (w - orig / 2.0f) / orig;
+    P->xc = xc; P->yc = yc; P->zc = zc; P->x_ = x_; P->y_ = y_;
+    P->ndc[0] = u; P->ndc[1] = w; P->ndc[2] = zc;
+}
+
+__global__ void __launch_bounds__(FP_THREADS)
+hoc_flow_vertices_kernel(const float *__restrict__ verts1, const float *__restrict__ verts2, HocCam C, int V,
+                         float *__restrict__ ndc1, float *__restrict__ ndc2, float *__restrict__ attrs12,
+                         float *__restrict__ attrs21)
+{
+    const int b = blockIdx.y;
+    const int vi = blockIdx.x * FP_THREADS + threadIdx.x;
+    if (vi >= V)
+        return;
+    const long o = ((long)b * V + vi) * 3;
+    const float v1[3] = {verts1[o], verts1[o + 1], verts1[o + 2]};
+    const float v2[3] = {verts2[o], verts2[o + 1], verts2[o + 2]};
+    const float *K1 = C.K1 + (long)b * C.K1_bs, *K2 = C.K2 + (long)b * C.K2_bs;
+    const float *R = C.R + (long)b * C.R_bs, *t = C.t + (long)b * C.t_bs, *d = C.dist + (long)b * C.dist_bs;
+    float u1, w1, u2, w2, hz;
+    hoc_proj2d(K1, v1, &u1, &w1, &hz);
+    hoc_proj2d(K2, v2, &u2, &w2, &hz);
+    attrs12[o] = u2 - u1;
+    attrs12[o + 1] = w2 - w1;
+    attrs12[o + 2] = 1.0f;
+    attrs21[o] = u1 - u2;
+    attrs21[o + 1] = w1 - w2;
+    attrs21[o + 2] = 1.0f;
+    HocProj P;
+    hoc_ndc_project(K1, R, t, d, C.orig_size, v1, &P);
+    ndc1[o] = P.ndc[0]; ndc1[o + 1] = P.ndc[1]; ndc1[o + 2] = P.ndc[2];
+    hoc_ndc_project(K2, R, t, d, C.orig_size, v2, &P);
+    ndc2[o] = P.ndc[0]; ndc2[o + 1] = P.ndc[1]; ndc2[o + 2] = P.ndc[2];
+}
+
+/* adjoint of batch_proj2d: (gu, gw) -> grad v (accumulated) */
+__device__ __forceinline__ void hoc_proj2d_bwd(const float *K, const float *v, float gu, float gw, float *gv)
+{
+    float u, w, h2;
+    hoc_proj2d(K, v, &u, &w, &h2);
+    const float gh0 = gu / h2, gh1 = gw / h2;
+    const float gh2 = -(gu * u + gw * w) / h2;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        gv[j] += gh0 * K[j] + gh1 * K[3 + j] + gh2 * K[6 + j];
+}
+
+/* adjoint of nr.projection: grad ndc -> grad v (accumulated) */
+__device__ __forceinline__ void hoc_ndc_project_bwd(const float *K, const float *R, const float *t, const float *d,
+                                                    float orig, const float *v, const float *g, float *gv)
+{
+    HocProj P;
+    hoc_ndc_project(K, R, t, d, orig, v, &P);
+    const float x_ = P.x_, y_ = P.y_;
+    const float r2 = x_ * x_ + y_ * y_;
+    const float radial = 1.0f + d[0] * r2 + d[1] * r2 * r2 + d[4] * r2 * r2 * r2;
+    const float dradial = d[0] + 2.0f * d[1] * r2 + 3.0f * d[4] * r2 * r2; /* d radial / d r2 */
+    /* u_ndc = 2 (u_px - o/2) / o ; w_ndc = 2 ((o - w_px) - o/2) / o */
+    const float gu = g[0] * 2.0f / orig, gw = -g[1] * 2.0f / orig;
+    const float gx__ = gu * K[0] + gw * K[3];
+    const float gy__ = gu * K[1] + gw * K[4];
+    /* x__ = x_ radial + 2 p1 x_ y_ + p2 (r2 + 2 x_^2);  y__ = y_ radial + p1 (r2 + 2 y_^2) + 2 p2 x_ y_ */
+    const float p1 = d[2], p2 = d[3];
+    const float dxx = radial + x_ * dradial * 2.0f * x_ + 2.0f * p1 * y_ + p2 * (2.0f * x_ + 4.0f * x_);
+    const float dxy = x_ * dradial * 2.0f * y_ + 2.0f * p1 * x_ + p2 * 2.0f * y_;
+    const float dyx = y_ * dradial * 2.0f * x_ + p1 * 2.0f * x_ + 2.0f * p2 * y_;
+    const float dyy = radial + y_ * dradial * 2.0f * y_ + p1 * (2.0f * y_ + 4.0f * y_) + 2.0f * p2 * x_;
+    const float gx_ = gx__ * dxx + gy__ * dyx;
+    const float gy_ = gx__ * dxy + gy__ * dyy;
+    const float zi = 1.0f / (P.zc + 1e-9f);
+    const float gxc = gx_ * zi, gyc = gy_ * zi;
+    const float gzc = g[2] - (gx_ * x_ + gy_ * y_) * zi;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        gv[j] += gxc * R[j] + gyc * R[3 + j] + gzc * R[6 + j];
+}
+
+__global__ void __launch_bounds__(FP_THREADS)
+hoc_flow_vertices_backward_kernel(const float *__restrict__ verts1, const float *__restrict__ verts2, HocCam C, int V,
+                                  const float *__restrict__ g_ndc1, const float *__restrict__ g_ndc2,
+                                  const float *__restrict__ g_a12, const float *__restrict__ g_a21,
+                                  float *__restrict__ grad_v1, float *__restrict__ grad_v2)
+{
+    const int b = blockIdx.y;
+    const int vi = blockIdx.x * FP_THREADS + threadIdx.x;
+    if (vi >= V)
+        return;
+    const long o = ((long)b * V + vi) * 3;
+    const float v1[3] = {verts1[o], verts1[o + 1], verts1[o + 2]};
+    const float v2[3] = {verts2[o], verts2[o + 1], verts2[o + 2]};
+    const float *K1 = C.K1 + (long)b * C.K1_bs, *K2 = C.K2 + (long)b * C.K2_bs;
+    const float *R = C.R + (long)b * C.R_bs, *t = C.t + (long)b * C.t_bs, *d = C.dist + (long)b * C.dist_bs;
+    /* attrs12 = loc2 - loc1, attrs21 = loc1 - loc2 */
+    float gu1 = 0.f, gw1 = 0.f;
+    if (g_a12 != nullptr) {
+        gu1 -= g_a12[o];
+        gw1 -= g_a12[o + 1];
+    }
+    if (g_a21 != nullptr) {
+        gu1 += g_a21[o];
+        gw1 += g_a21[o + 1];
+    }
+    float gv1[3] = {0.f, 0.f, 0.f}, gv2[3] = {0.f, 0.f, 0.f};
+    if (grad_v1 != nullptr) {
+        hoc_proj2d_bwd(K1, v1, gu1, gw1, gv1);
+        if (g_ndc1 != nullptr) {
+            const float g[3] = {g_ndc1[o], g_ndc1[o + 1], g_ndc1[o + 2]};
+            hoc_ndc_project_bwd(K1, R, t, d, C.orig_size, v1, g, gv1);
+        }
+        grad_v1[o] = gv1[0]; grad_v1[o + 1] = gv1[1]; grad_v1[o + 2] = gv1[2];
+    }
+    if (grad_v2 != nullptr) {
+        hoc_proj2d_bwd(K2, v2, -gu1, -gw1, gv2);
+        if (g_ndc2 != nullptr) {
+            const float g[3] = {g_ndc2[o], g_ndc2[o + 1], g_ndc2[o + 2]};
+            hoc_ndc_project_bwd(K2, R, t, d, C.orig_size, v2, g, gv2);
+        }
+        grad_v2[o] = gv2[0]; grad_v2[o + 1] = gv2[1]; grad_v2[o + 2] = gv2[2];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 extern "C" int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                                int fill_back, float *faces_out, float *textures_out, void *stream)
@@ -383,5 +549,62 @@ extern "C" int hoc_flow_finalize_backward(const float *grad_flow, const float *m
                (hoc_flow_finalize_backward_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(grad_flow, mult, S, H,
                                                                                                 W, grad_rgb)));
     HOC_CHECK_LAUNCH("hoc_flow_finalize_backward_kernel");
+    return HOC_OK;
+}
+
+static HocCam hoc_make_cam(const float *K1, int K1_batched, const float *K2, int K2_batched, const float *R,
+                           int R_batched, const float *t, int t_batched, const float *dist, int dist_batched,
+                           float orig_size)
+{
+    HocCam C;
+    C.K1 = K1; C.K2 = K2; C.R = R; C.t = t; C.dist = dist;
+    C.K1_bs = K1_batched ? 9 : 0;
+    C.K2_bs = K2_batched ? 9 : 0;
+    C.R_bs = R_batched ? 9 : 0;
+    C.t_bs = t_batched ? 3 : 0;
+    C.dist_bs = dist_batched ? 5 : 0;
+    C.orig_size = orig_size;
+    return C;
+}
+
+extern "C" int hoc_flow_vertices(const float *verts1, const float *verts2, const float *K1, int K1_batched,
+                                 const float *K2, int K2_batched, const float *R, int R_batched, const float *t,
+                                 int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B,
+                                 int V, float *ndc1, float *ndc2, float *attrs12, float *attrs21, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && V >= 0 && B <= 65535, "hoc_flow_vertices: bad shape B=%d V=%d", B, V);
+    if (B == 0 || V == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(verts1 && verts2 && K1 && K2 && R && t && dist_coeffs && ndc1 && ndc2 && attrs12 && attrs21,
+                  "hoc_flow_vertices: NULL argument");
+    HocCam C = hoc_make_cam(K1, K1_batched, K2, K2_batched, R, R_batched, t, t_batched, dist_coeffs, dist_batched,
+                            orig_size);
+    dim3 grid((V + FP_THREADS - 1) / FP_THREADS, B);
+    HOC_LAUNCH(HOC_K_FLOW_VERTICES, (cudaStream_t)stream,
+               (hoc_flow_vertices_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(verts1, verts2, C, V, ndc1,
+                                                                                        ndc2, attrs12, attrs21)));
+    HOC_CHECK_LAUNCH("hoc_flow_vertices_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_flow_vertices_backward(const float *verts1, const float *verts2, const float *K1, int K1_batched,
+                                          const float *K2, int K2_batched, const float *R, int R_batched,
+                                          const float *t, int t_batched, const float *dist_coeffs, int dist_batched,
+                                          float orig_size, int B, int V, const float *grad_ndc1,
+                                          const float *grad_ndc2, const float *grad_attrs12,
+                                          const float *grad_attrs21, float *grad_verts1, float *grad_verts2,
+                                          void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && V >= 0 && B <= 65535, "hoc_flow_vertices_backward: bad shape B=%d V=%d", B, V);
+    if (B == 0 || V == 0 || (grad_verts1 == nullptr && grad_verts2 == nullptr))
+        return HOC_OK;
+    HOC_CHECK_ARG(verts1 && verts2 && K1 && K2 && R && t && dist_coeffs, "hoc_flow_vertices_backward: NULL argument");
+    HocCam C = hoc_make_cam(K1, K1_batched, K2, K2_batched, R, R_batched, t, t_batched, dist_coeffs, dist_batched,
+                            orig_size);
+    dim3 grid((V + FP_THREADS - 1) / FP_THREADS, B);
+    HOC_LAUNCH(HOC_K_FLOW_VERTICES_BWD, (cudaStream_t)stream,
+               (hoc_flow_vertices_backward_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   verts1, verts2, C, V, grad_ndc1, grad_ndc2, grad_attrs12, grad_attrs21, grad_verts1, grad_verts2)));
+    HOC_CHECK_LAUNCH("hoc_flow_vertices_backward_kernel");
     return HOC_OK;
 }

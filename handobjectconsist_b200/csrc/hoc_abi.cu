@@ -19,18 +19,19 @@ extern "C" int hoc_abi_version(void) { return HOC_ABI_VERSION; }
 extern "C" const char *hoc_last_error(void) { return g_hoc_error; }
 
 /* ---- launch accounting + per-kernel device timing (used by bench.py) ---------------------- */
-#define HOC_TIMER_CAP 4096
+#define HOC_TIMER_CAP 8192
 static unsigned long long g_launches[HOC_KERNEL_COUNT];
-static int g_timer_kernel = -1;
+static unsigned long long g_timer_mask = 0;
 static int g_timer_n = 0;
 static cudaEvent_t g_timer_ev[HOC_TIMER_CAP][2];
+static int g_timer_id[HOC_TIMER_CAP];
 static int g_timer_created = 0;
 
 void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
 {
     if (phase == 0)
         g_launches[kernel_id]++;
-    if (kernel_id != g_timer_kernel || g_timer_n >= HOC_TIMER_CAP)
+    if (!((g_timer_mask >> kernel_id) & 1ull) || g_timer_n >= HOC_TIMER_CAP)
         return;
     if (phase == 0) {
         if (g_timer_n >= g_timer_created) {
@@ -38,6 +39,7 @@ void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
             cudaEventCreate(&g_timer_ev[g_timer_n][1]);
             g_timer_created = g_timer_n + 1;
         }
+        g_timer_id[g_timer_n] = kernel_id;
         cudaEventRecord(g_timer_ev[g_timer_n][0], st);
     } else {
         cudaEventRecord(g_timer_ev[g_timer_n][1], st);
@@ -56,23 +58,24 @@ extern "C" unsigned long long hoc_launch_count(int kernel_id)
     return kernel_id < HOC_KERNEL_COUNT ? g_launches[kernel_id] : 0;
 }
 
-extern "C" int hoc_timer_begin(int kernel_id)
+extern "C" int hoc_timer_begin(unsigned long long kernel_mask)
 {
-    HOC_CHECK_ARG(kernel_id >= -1 && kernel_id < HOC_KERNEL_COUNT, "hoc_timer_begin: kernel id %d", kernel_id);
-    g_timer_kernel = kernel_id;
+    g_timer_mask = kernel_mask;
     g_timer_n = 0;
     return HOC_OK;
 }
 
-extern "C" int hoc_timer_end(float *ms_host, int capacity)
+extern "C" int hoc_timer_end(float *ms_host, int *kernel_ids_host, int capacity)
 {
     const int n = g_timer_n < capacity ? g_timer_n : capacity;
     for (int i = 0; i < n; i++) {
         cudaEventSynchronize(g_timer_ev[i][1]);
         if (cudaEventElapsedTime(&ms_host[i], g_timer_ev[i][0], g_timer_ev[i][1]) != cudaSuccess)
             ms_host[i] = -1.0f;
+        if (kernel_ids_host != nullptr)
+            kernel_ids_host[i] = g_timer_id[i];
     }
-    g_timer_kernel = -1;
+    g_timer_mask = 0;
     g_timer_n = 0;
     return n;
 }

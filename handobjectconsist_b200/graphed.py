@@ -1,0 +1,100 @@
+"""CUDA-graph capture of the consistency step.
+
+``warpbranch.forward`` + its backward is ~60 launches of which ~25 are this package's kernels and the rest
+small tensor ops; at 16 pairs of 256x256 the GPU work is well under a millisecond, so eager execution is
+bound by CPU launch overhead.  ``GraphedConsistStep`` captures forward AND backward (loss -> gradients of the
+first frame's hand / object vertices) once for fixed shapes and replays the graph; inputs are copied into
+static device buffers (straight from pinned host memory when they live there), outputs are read from
+static buffers.  ``GraphedConsistStep.apply`` is the autograd-friendly entry: it returns the loss as a
+differentiable function of the predicted vertices, so it drops into a training step in place of
+``WarpRegNet.warp_forward`` (/root/reference/meshreg/models/warpreg.py:66-79).
+"""
+import torch
+from torch.autograd import Function
+
+from . import warpbranch
+
+
+def _name(key):
+    return getattr(key, "name", key)
+
+
+class GraphedConsistStep:
+    def __init__(self, renderer, criterion, image_size, hand_face, samples, all_results, hand_ignore_faces=None,
+                 gt_refs=True, first_only=True, use_backward=True, detach_renders=True, warmup=3):
+        """``samples`` / ``all_results``: one example batch (reference layout, warpbranch.py:27-44) that fixes
+        shapes and dtypes; their values are only used for the warm-up iterations."""
+        if len(samples) != 2:
+            raise ValueError("GraphedConsistStep captures one frame pair (sample_nb == 2)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        dev = self.device
+        self.renderer, self.criterion, self.image_size = renderer, criterion, image_size
+        self.kw = dict(gt_refs=gt_refs, first_only=first_only, hand_ignore_faces=hand_ignore_faces,
+                       use_backward=use_backward, detach_renders=detach_renders)
+        self.hand_face = hand_face.to(dev)
+        # static inputs
+        self.samples = [{k: v.to(dev).clone() if torch.is_tensor(v) else v for k, v in s.items()} for s in samples]
+        self.results = [{k: v.detach().to(dev).clone() for k, v in r.items() if torch.is_tensor(v)}
+                        for r in all_results]
+        self.hand = self.results[0]["recov_handverts3d"].requires_grad_(True)
+        self.obj = self.results[0]["recov_objverts3d"].requires_grad_(True)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):
+                self._run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.grad_hand, self.grad_obj = self._run()
+
+    def _run(self):
+        loss, _ = warpbranch.forward(self.samples, self.results, self.hand_face, self.renderer, self.image_size,
+                                     self.criterion, **self.kw)
+        gh, go = torch.autograd.grad(loss, [self.hand, self.obj], allow_unused=True)
+        if gh is None:
+            gh = torch.zeros_like(self.hand)
+        if go is None:
+            go = torch.zeros_like(self.obj)
+        return loss.detach(), gh, go
+
+    def load(self, samples, all_results):
+        """Copy a new batch into the static buffers (stream-ordered; pinned host tensors copy asynchronously)."""
+        with torch.no_grad():
+            for dst, src in zip(self.samples, samples):
+                by_name = {(_name(k), type(k).__name__): v for k, v in src.items()}
+                for k, buf in dst.items():
+                    if torch.is_tensor(buf):
+                        buf.copy_(by_name[(_name(k), type(k).__name__)], non_blocking=True)
+            for dst, src in zip(self.results, all_results):
+                for k, buf in dst.items():
+                    buf.copy_(src[k].detach(), non_blocking=True)
+
+    def replay(self):
+        """Run the captured forward + backward; returns the static (loss, grad_hand, grad_obj) tensors."""
+        self.graph.replay()
+        return self.loss, self.grad_hand, self.grad_obj
+
+    def __call__(self, samples, all_results):
+        self.load(samples, all_results)
+        return self.replay()
+
+    def apply(self, samples, all_results):
+        """Differentiable entry: loss as a function of all_results[0]['recov_handverts3d' / 'recov_objverts3d']."""
+        return _GraphedConsistFunction.apply(all_results[0]["recov_handverts3d"], all_results[0]["recov_objverts3d"],
+                                             self, samples, all_results)
+
+
+class _GraphedConsistFunction(Function):
+    @staticmethod
+    def forward(ctx, hand, obj, step, samples, all_results):
+        loss, gh, go = step(samples, all_results)
+        ctx.save_for_backward(gh.clone(), go.clone())
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        gh, go = ctx.saved_tensors
+        return gh * grad_loss, go * grad_loss, None, None, None

@@ -140,6 +140,56 @@ class _FlowFinalizeFunction(Function):
         return outs[0], None, None, outs[1], None, None, None, None, None
 
 
+class _FlowVertexFunction(Function):
+    """batch_proj2d x2 + displacement attributes + nr.projection x2 in one launch each way
+    (hoc_flow_vertices / hoc_flow_vertices_backward)."""
+
+    @staticmethod
+    def forward(ctx, verts1, verts2, K1, K2, R, t, dist, orig_size):
+        _lib.require_cuda(verts1, verts2, K1, K2, what="get_opticalflow")
+        L = _lib.lib()
+        c = lambda x: x.detach().contiguous().float()
+        v1, v2, K1, K2, R, t, dist = c(verts1), c(verts2), c(K1), c(K2), c(R), c(t), c(dist)
+        B, V = v1.shape[:2]
+        cams = (K1.reshape(-1, 9), K2.reshape(-1, 9), R.reshape(-1, 9), t.reshape(-1, 3), dist.reshape(-1, 5))
+        for cam in cams:
+            if cam.shape[0] not in (1, B):
+                raise ValueError("camera tensors must have batch dimension 1 or B")
+        flags = [int(cam.shape[0] == B and B > 1) for cam in cams]
+        dev = v1.device
+        with torch.cuda.device(dev):
+            outs = [torch.empty((B, V, 3), dtype=torch.float32, device=dev) for _ in range(4)]
+            _lib.check(L.hoc_flow_vertices(_lib.ptr(v1), _lib.ptr(v2), _lib.ptr(cams[0]), flags[0], _lib.ptr(cams[1]),
+                                           flags[1], _lib.ptr(cams[2]), flags[2], _lib.ptr(cams[3]), flags[3],
+                                           _lib.ptr(cams[4]), flags[4], float(orig_size), B, V, *[_lib.ptr(o) for o in outs],
+                                           _lib.stream_ptr()), "hoc_flow_vertices")
+        ctx.save_for_backward(v1, v2, *cams)
+        ctx.cfg = (B, V, flags, float(orig_size))
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_ndc1, g_ndc2, g_a12, g_a21):
+        v1, v2, K1, K2, R, t, dist = ctx.saved_tensors
+        B, V, flags, orig_size = ctx.cfg
+        need1, need2 = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need1 or need2):
+            return (None,) * 8
+        L = _lib.lib()
+        c = lambda g: None if g is None else g.contiguous().float()
+        g_ndc1, g_ndc2, g_a12, g_a21 = c(g_ndc1), c(g_ndc2), c(g_a12), c(g_a21)
+        dev = v1.device
+        with torch.cuda.device(dev):
+            gv1 = torch.empty_like(v1) if need1 else None
+            gv2 = torch.empty_like(v2) if need2 else None
+            _lib.check(L.hoc_flow_vertices_backward(
+                _lib.ptr(v1), _lib.ptr(v2), _lib.ptr(K1), flags[0], _lib.ptr(K2), flags[1], _lib.ptr(R), flags[2],
+                _lib.ptr(t), flags[3], _lib.ptr(dist), flags[4], orig_size, B, V, _lib.ptr(g_ndc1), _lib.ptr(g_ndc2),
+                _lib.ptr(g_a12), _lib.ptr(g_a21), _lib.ptr(gv1), _lib.ptr(gv2), _lib.stream_ptr()),
+                "hoc_flow_vertices_backward")
+        return (gv1, gv2) + (None,) * 6
+
+
 def _fused_path_ok(neurenderer):
     from ..neurender.renderer import Renderer
     return (isinstance(neurenderer, Renderer) and neurenderer.camera_mode == "projection"
@@ -150,17 +200,16 @@ def _get_opticalflow_fused(verts_cam, faces, camintrs, neurenderer, orig_img_siz
                            detach_renders, ignore_face_idxs):
     """Same results as the op-by-op path below with ~10 launches instead of ~150."""
     S = neurenderer.image_size
-    locs1 = batch_proj2d(verts_cam[0], camintrs[0])
-    locs2 = batch_proj2d(verts_cam[1], camintrs[1])
-    displ_12 = locs2 - locs1
-    ones = torch.ones_like(displ_12[:, :, :1])
-    attrs12 = torch.cat([displ_12, ones], -1)
-    attrs21 = torch.cat([locs1 - locs2, ones], -1)
+    dev, dt = verts_cam[0].device, verts_cam[0].dtype
+    R = neurenderer.R if neurenderer.R is not None else torch.eye(3, dtype=dt, device=dev)[None]
+    t = neurenderer.t if neurenderer.t is not None else torch.zeros(1, 3, dtype=dt, device=dev)
+    dist = neurenderer.dist_coeffs if neurenderer.dist_coeffs is not None else torch.zeros(1, 5, dtype=dt, device=dev)
+    ndc1, ndc2, attrs12, attrs21 = _FlowVertexFunction.apply(verts_cam[0], verts_cam[1], camintrs[0], camintrs[1], R,
+                                                             t, dist, neurenderer.orig_size)
     if detach_textures:
         attrs12 = attrs12.detach()  # the reference detaches only the first set (opticalflow.py:104-105)
     renders = []
-    for verts, K, attrs in ((verts_cam[0], camintrs[0], attrs12), (verts_cam[1], camintrs[1], attrs21)):
-        ndc = neurenderer.project(verts, K=K)
+    for ndc, attrs in ((ndc1, attrs12), (ndc2, attrs21)):
         if detach_renders:
             ndc = ndc.detach()
         renders.append(_MeshRasterFunction.apply(ndc, attrs, faces, S, neurenderer.near, neurenderer.far,

@@ -52,8 +52,8 @@ const char *hoc_last_error(void);
 /* Kernel ids for launch accounting / device timing (bench.py's `gpu_launches` and `roofline`). */
 #define HOC_K_RASTER_ZBUF 0
 #define HOC_K_RASTER_RESOLVE 1
-#define HOC_K_GRAD_EXTENT 2
-#define HOC_K_RASTER_BACKWARD 3
+#define HOC_K_GRAD_EXTENT 2 /* retired: merged into HOC_K_RASTER_BWD_PIXEL */
+#define HOC_K_RASTER_BACKWARD 3 /* hoc_raster_bwd_face_kernel */
 #define HOC_K_WARP_PHOTO_FWD 4
 #define HOC_K_WARP_PHOTO_BWD 5
 #define HOC_K_WARP 6
@@ -63,15 +63,20 @@ const char *hoc_last_error(void);
 #define HOC_K_MESH_SCATTER 10
 #define HOC_K_FLOW_FINALIZE 11
 #define HOC_K_FLOW_FINALIZE_BWD 12
-#define HOC_KERNEL_COUNT 16
+#define HOC_K_RASTER_BWD_PIXEL 13
+#define HOC_K_RASTER_BWD_LINE 14
+#define HOC_K_FLOW_VERTICES 15
+#define HOC_K_FLOW_VERTICES_BWD 16
+#define HOC_KERNEL_COUNT 24
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
 unsigned long long hoc_launch_count(int kernel_id);
-/* Arm / read the device timer: between begin and end every launch of `kernel_id` is bracketed by CUDA
- * events on its stream; end synchronises them and writes up to `capacity` durations (ms) to host memory,
- * returning how many were recorded.  Not thread-safe; meant for benchmarking. */
-int hoc_timer_begin(int kernel_id);
-int hoc_timer_end(float *ms_host, int capacity);
+/* Arm / read the device timer: between begin and end every launch of a kernel whose bit is set in
+ * `kernel_mask` (1 << HOC_K_*) is bracketed by CUDA events on its stream; end synchronises them and writes
+ * up to `capacity` durations (ms) and kernel ids to host memory, returning how many were recorded.  Not
+ * thread-safe, not usable during stream capture; meant for benchmarking. */
+int hoc_timer_begin(unsigned long long kernel_mask);
+int hoc_timer_end(float *ms_host, int *kernel_ids_host, int capacity);
 
 /* ---- rasterizer forward -------------------------------------------------------------------
  * Replaces forward_face_index_map + forward_texture_sampling (rasterize.py:202-215,232-243)
@@ -96,8 +101,9 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
 /* ---- rasterizer backward ------------------------------------------------------------------
  * Replaces backward_pixel_map + backward_textures + backward_depth_map
  * (rasterize.py:269-281,290-297,306-315) and the zero-fills around them (rasterize.py:151-181).
- * One launch; every face's gradient is produced by exactly one warp (no float atomics, results
- * are deterministic run to run).
+ * Three launches (pixel pass, face pass, line pass -- csrc/raster_bwd.cu).  Texture / depth gradients and
+ * the outward-scan part of the pseudo-gradient are accumulated with float atomics, like the reference's
+ * backward_textures / backward_depth_map: results are reproducible to rounding, not bit for bit.
  *   faces, textures, face_index_map   forward inputs / output
  *   rgb              forward output in `layout` (NULL when the forward had no rgb)
  *   grad_rgb / grad_alpha / grad_depth  incoming gradients in `layout`; NULL = all zeros / that
@@ -105,6 +111,8 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
  *   use_alpha        1 when the forward produced alpha (return_alpha), else 0
  *   grad_faces       [B,F,3,3] out (fully overwritten) or NULL to skip the geometry gradient
  *   grad_textures    [B,F,ts,ts,ts,3] out (fully overwritten) or NULL to skip it
+ *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes (dominated by the outward-scan queue,
+ *                    24 S^2 B bytes worst case, of which only the used part is ever touched)
  */
 size_t hoc_raster_backward_workspace_bytes(int B, int F, int S);
 int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
@@ -179,6 +187,23 @@ int hoc_flow_finalize(const float *rgb1, const float *alpha1, const int32_t *idx
 /* grad_flow [B,H,W,2], mult [B,H,W] -> grad_rgb [B,3,S,S] (fully overwritten; zero outside the crop). */
 int hoc_flow_finalize_backward(const float *grad_flow, const float *mult, int B, int S, int H, int W,
                                float *grad_rgb, void *stream);
+
+/* Per-vertex front end of get_opticalflow for one frame pair: batch_proj2d of both frames, the displacement
+ * attributes [dx, dy, 1] of both directions (opticalflow.py:98-102,121-122) and nr.projection of both meshes
+ * to NDC (renderer.py:187; OpenCV distortion, y flip, [-1,1] scaling by orig_size) in ONE launch.
+ * verts1/verts2 [B,V,3]; K1/K2 [B or 1,3,3]; R [B or 1,3,3]; t [B or 1,3]; dist_coeffs [B or 1,5]
+ * (`*_batched` = 1 when the leading dimension is B);  outputs ndc1/ndc2/attrs12/attrs21 [B,V,3]. */
+int hoc_flow_vertices(const float *verts1, const float *verts2, const float *K1, int K1_batched, const float *K2,
+                      int K2_batched, const float *R, int R_batched, const float *t, int t_batched,
+                      const float *dist_coeffs, int dist_batched, float orig_size, int B, int V, float *ndc1,
+                      float *ndc2, float *attrs12, float *attrs21, void *stream);
+/* Adjoint: gradients of the four outputs (any may be NULL = zero) -> grad_verts1 / grad_verts2 [B,V,3]
+ * (either may be NULL; fully overwritten).  Cameras get no gradient. */
+int hoc_flow_vertices_backward(const float *verts1, const float *verts2, const float *K1, int K1_batched,
+                               const float *K2, int K2_batched, const float *R, int R_batched, const float *t,
+                               int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B, int V,
+                               const float *grad_ndc1, const float *grad_ndc2, const float *grad_attrs12,
+                               const float *grad_attrs21, float *grad_verts1, float *grad_verts2, void *stream);
 
 #ifdef __cplusplus
 }

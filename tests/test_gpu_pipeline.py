@@ -114,7 +114,54 @@ def test_fused_flow_path_equals_op_by_op_path(detach):
         outs.append((flows, v1.grad, v2.grad))
     for i in range(2):
         assert outs[0][0][i].shape == (B, 64, S, 2)
-        assert (outs[0][0][i] - outs[1][0][i]).abs().max().item() <= 1e-5
+        assert (outs[0][0][i] - outs[1][0][i]).abs().max().item() <= 1e-4  # north_star pixel tolerance
         assert torch.equal(outs[0][0][i] == 0, outs[1][0][i] == 0)
     for k in (1, 2):
         assert helpers.rel_err(outs[0][k].cpu().numpy(), outs[1][k].cpu().numpy()) < 1e-3
+
+
+def test_graphed_step_matches_eager():
+    """CUDA-graph capture of forward+backward (handobjectconsist_b200.graphed) reproduces the eager step,
+    also after loading a different batch into its static buffers, from pinned host memory."""
+    from handobjectconsist_b200 import warpbranch
+    from handobjectconsist_b200.graphed import GraphedConsistStep
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+    S, B, hv = 64, 2, 778
+    dev = torch.device("cuda:0")
+
+    def batch(seed, device):
+        sc = synth.make_scene(B, S, S, seed=seed)
+        mv = (lambda t: t.to(device)) if device is not None else (lambda t: t.contiguous().pin_memory())
+        obj_faces = mv(sc["faces"][:, 1552:] - hv)
+        samples, results = [], []
+        for verts, img, jit in ((sc["verts1"], sc["image_ref"], sc["jitter_mask_ref"]),
+                                (sc["verts2"], sc["image"], sc["jitter_mask"])):
+            samples.append({TransQueries.IMAGE: mv(img), TransQueries.JITTERMASK: mv(jit),
+                            TransQueries.CAMINTR: mv(sc["K"]), BaseQueries.OBJFACES: obj_faces,
+                            BaseQueries.OBJVERTS3D: mv(verts[:, hv:]), BaseQueries.HANDVERTS3D: mv(verts[:, :hv])})
+            results.append({"recov_handverts3d": mv(verts[:, :hv]), "recov_objverts3d": mv(verts[:, hv:])})
+        return sc, samples, results
+
+    sc, samples, results = batch(20, dev)
+    hand_face = sc["faces"][0, :1552].to(dev)
+    crit = PyramidCriterion("l1")
+    gstep = GraphedConsistStep(_renderer(S, dev), crit, (S, S), hand_face, samples, results,
+                               hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)
+    for seed, device in ((20, dev), (21, None), (22, dev)):
+        sc, samples, results = batch(seed, device)
+        loss_g, gh_g, go_g = [t.clone() for t in gstep(samples, results)]
+        dres = [{k: v.to(dev) for k, v in r.items()} for r in results]
+        h = dres[0]["recov_handverts3d"].requires_grad_(True)
+        o = dres[0]["recov_objverts3d"].requires_grad_(True)
+        loss_e, _ = warpbranch.forward(samples, dres, hand_face, _renderer(S, dev), (S, S), crit,
+                                       hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)
+        loss_e.backward()
+        assert abs(loss_g.item() - loss_e.item()) <= 1e-6
+        assert helpers.rel_err(gh_g.cpu().numpy(), h.grad.cpu().numpy()) < 1e-4
+        assert helpers.rel_err(go_g.cpu().numpy(), o.grad.cpu().numpy()) < 1e-4
+    # autograd entry: loss as a differentiable function of the predicted vertices
+    h2 = dres[0]["recov_handverts3d"].detach().clone().requires_grad_(True)
+    dres[0] = {"recov_handverts3d": h2, "recov_objverts3d": dres[0]["recov_objverts3d"].detach()}
+    (gstep.apply(samples, dres) * 3.0).backward()
+    assert helpers.rel_err(h2.grad.cpu().numpy(), 3.0 * h.grad.cpu().numpy()) < 1e-4
