@@ -26,46 +26,59 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
                        const long long *__restrict__ faces_idx, int V, int F, int fill_back,
                        float *__restrict__ faces_out, float *__restrict__ tex_out)
 {
+    /* per-face records are staged in shared memory and written out as contiguous, coalesced runs */
+    __shared__ __align__(16) float s_tex[FP_THREADS * 24];
+    __shared__ float s_face[FP_THREADS * 9];
     const int Fo = fill_back ? 2 * F : F;
-    const int fo = blockIdx.x * FP_THREADS + threadIdx.x;
+    const int fo0 = blockIdx.x * FP_THREADS;
+    const int fo = fo0 + threadIdx.x;
     const int b = blockIdx.y;
-    if (fo >= Fo)
-        return;
-    const int f = fo >= F ? fo - F : fo;
-    const long long *fi = faces_idx + ((long)b * F + f) * 3;
-    long long i0 = fi[0], i1 = fi[1], i2 = fi[2];
-    if (fo >= F) { /* reversed winding: (v2, v1, v0) */
-        const long long t = i0;
-        i0 = i2;
-        i2 = t;
-    }
-    const long long iv[3] = {i0, i1, i2};
-    float c[3][3];
-    float *fd = faces_out + ((long)b * Fo + fo) * 9;
+    if (fo < Fo) {
+        const int f = fo >= F ? fo - F : fo;
+        const long long *fi = faces_idx + ((long)b * F + f) * 3;
+        long long i0 = fi[0], i1 = fi[1], i2 = fi[2];
+        if (fo >= F) { /* reversed winding: (v2, v1, v0) */
+            const long long t = i0;
+            i0 = i2;
+            i2 = t;
+        }
+        const long long iv[3] = {i0, i1, i2};
+        float c[3][3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const float *vs = verts + ((long)b * V + iv[k]) * 3;
-        fd[3 * k + 0] = vs[0];
-        fd[3 * k + 1] = vs[1];
-        fd[3 * k + 2] = vs[2];
+        for (int k = 0; k < 3; k++) {
+            const float *vs = verts + ((long)b * V + iv[k]) * 3;
+            s_face[threadIdx.x * 9 + 3 * k + 0] = vs[0];
+            s_face[threadIdx.x * 9 + 3 * k + 1] = vs[1];
+            s_face[threadIdx.x * 9 + 3 * k + 2] = vs[2];
+            if (tex_out != nullptr) {
+                const float *as = attrs + ((long)b * V + iv[k]) * 3;
+                c[k][0] = as[0];
+                c[k][1] = as[1];
+                c[k][2] = as[2];
+            }
+        }
         if (tex_out != nullptr) {
-            const float *as = attrs + ((long)b * V + iv[k]) * 3;
-            c[k][0] = as[0];
-            c[k][1] = as[1];
-            c[k][2] = as[2];
+            /* cube whose trilinear sample at the barycentric coordinates is b0 c0 + b1 c1 + b2 c2:
+             * T[i,j,k] = i c0 + j c1 + k c2 (the reversed copy is the permute(0,1,4,3,2,5) of the original) */
+#pragma unroll
+            for (int corner = 0; corner < 8; corner++) {
+                const float wi = (float)((corner >> 2) & 1), wj = (float)((corner >> 1) & 1), wk = (float)(corner & 1);
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++)
+                    s_tex[threadIdx.x * 24 + corner * 3 + ch] = wi * c[0][ch] + wj * c[1][ch] + wk * c[2][ch];
+            }
         }
     }
+    __syncthreads();
+    const int nf = min(FP_THREADS, Fo - fo0);
+    float *fd = faces_out + ((long)b * Fo + fo0) * 9;
+    for (int i = threadIdx.x; i < nf * 9; i += FP_THREADS)
+        fd[i] = s_face[i];
     if (tex_out != nullptr) {
-        /* cube whose trilinear sample at the barycentric coordinates is b0 c0 + b1 c1 + b2 c2:
-         * T[i,j,k] = i c0 + j c1 + k c2 (the reversed copy is the permute(0,1,4,3,2,5) of the original) */
-        float *td = tex_out + ((long)b * Fo + fo) * 24;
-#pragma unroll
-        for (int corner = 0; corner < 8; corner++) {
-            const float wi = (float)((corner >> 2) & 1), wj = (float)((corner >> 1) & 1), wk = (float)(corner & 1);
-#pragma unroll
-            for (int ch = 0; ch < 3; ch++)
-                td[corner * 3 + ch] = wi * c[0][ch] + wj * c[1][ch] + wk * c[2][ch];
-        }
+        float4 *td = reinterpret_cast<float4 *>(tex_out + ((long)b * Fo + fo0) * 24);
+        const float4 *ts4 = reinterpret_cast<const float4 *>(s_tex);
+        for (int i = threadIdx.x; i < nf * 6; i += FP_THREADS)
+            td[i] = ts4[i];
     }
 }
 
@@ -225,6 +238,15 @@ hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const 
     float fx, fy;
     hoc_fp_flow(Ra, b, S, rx, ry, mt_r, &fx, &fy);
     float mfinal = mt_r;
+    float *flow = second ? flow21 : flow12;
+    float *mult = second ? mult2 : mult1;
+    const long o = ((long)b * H + ry) * W + rx;
+    if (mask_occlusions && (second ? alpha_r : mt_r) == 0.0f && fx == fx && fy == fy) {
+        /* the pixel's own mask is zero (93 % of a typical frame): every product below is zero */
+        *reinterpret_cast<float2 *>(flow + o * 2) = make_float2(0.0f, 0.0f);
+        mult[o] = 0.0f;
+        return;
+    }
     if (mask_occlusions) {
         /* masks that enter the check: render 1 -> thresholded*keep, render 2 -> raw alpha (sic) */
         const float m_r = second ? alpha_r : mt_r;
@@ -262,9 +284,6 @@ hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const 
         fx = __fmul_rn(fx, mfinal);
         fy = __fmul_rn(fy, mfinal);
     }
-    float *flow = second ? flow21 : flow12;
-    float *mult = second ? mult2 : mult1;
-    const long o = ((long)b * H + ry) * W + rx;
     *reinterpret_cast<float2 *>(flow + o * 2) = make_float2(fx, fy);
     mult[o] = mask_occlusions ? __fmul_rn(mt_r, mfinal) : mt_r;
 }

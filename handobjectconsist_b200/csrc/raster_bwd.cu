@@ -115,7 +115,7 @@ __device__ __forceinline__ float hoc_delta(const HocBwdMaps &M, int xi, int yi, 
     return d;
 }
 
-#define BW_THREADS 256
+#define BW_THREADS 128
 #define BW_WARPS (BW_THREADS / 32)
 
 /*
@@ -137,73 +137,83 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
     int *e = ext + (long)b * 4 * S;
     const int tex_n = ts * ts * ts * 3;
     int c_lo = 0x7f7f7f7f, c_hi = -1;
-#pragma unroll 1
+    /* issue the loads of all four rows first (memory-level parallelism), then do the per-pixel work */
+    float gr[4][3], ga[4];
+    int fis[4];
+#pragma unroll
     for (int r = 0; r < 4; r++) {
         const int yi = blockIdx.y * 32 + r * 8 + ty;
-        bool nz = false;
-        if (xi < S && yi < S) {
-            float gr[3] = {0.f, 0.f, 0.f};
+        const bool in = xi < S && yi < S;
+        gr[r][0] = gr[r][1] = gr[r][2] = 0.0f;
+        ga[r] = 0.0f;
+        fis[r] = -1;
+        if (in) {
             if (g_rgb != nullptr) {
 #pragma unroll
                 for (int c = 0; c < 3; c++)
-                    gr[c] = g_rgb[hoc_rgb_off(layout, S, b, yi, xi, c)];
-                nz = !(gr[0] == 0.0f) || !(gr[1] == 0.0f) || !(gr[2] == 0.0f);
+                    gr[r][c] = g_rgb[hoc_rgb_off(layout, S, b, yi, xi, c)];
             }
             if (g_alpha != nullptr)
-                nz = nz || !(g_alpha[hoc_plane_off(layout, S, b, yi, xi)] == 0.0f);
-            const int fi = face_index_map[((long)b * S + yi) * S + xi];
-            if (fi >= 0) {
-                atomicAdd(owned + (long)b * F + fi, 1);
-                const bool want_tex = (grad_textures != nullptr) && (g_rgb != nullptr);
-                const bool want_depth = (acc_d != nullptr) && (g_depth != nullptr);
-                if (want_tex || want_depth) {
-                    float f[9], inv[9], w[3], zp;
-                    const float *src = faces + ((long)b * F + fi) * 9;
+                ga[r] = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+            fis[r] = face_index_map[((long)b * S + yi) * S + xi];
+        }
+    }
+    const bool want_tex = (grad_textures != nullptr) && (g_rgb != nullptr);
+    const bool want_depth = (acc_d != nullptr) && (g_depth != nullptr);
 #pragma unroll
-                    for (int k = 0; k < 9; k++)
-                        f[k] = __ldg(src + k);
-                    hoc_face_inv(f, S, inv);
-                    hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
-                    if (want_depth) {
-                        const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
-                        if (gz != 0.0f) {
-                            float *ad = acc_d + ((long)b * F + fi) * 3;
+    for (int r = 0; r < 4; r++) {
+        const int yi = blockIdx.y * 32 + r * 8 + ty;
+        const bool nz = !(gr[r][0] == 0.0f) || !(gr[r][1] == 0.0f) || !(gr[r][2] == 0.0f) || !(ga[r] == 0.0f);
+        const int fi = fis[r];
+        if (fi >= 0) {
+            atomicAdd(owned + (long)b * F + fi, 1);
+            if ((want_tex && nz) || want_depth) {
+                float f[9], inv[9], w[3], zp;
+                const float *src = faces + ((long)b * F + fi) * 9;
 #pragma unroll
-                            for (int k = 0; k < 3; k++)
-                                atomicAdd(ad + k, gz * w[k]);
-                        }
+                for (int k = 0; k < 9; k++)
+                    f[k] = __ldg(src + k);
+                hoc_face_inv(f, S, inv);
+                hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+                if (want_depth) {
+                    const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
+                    if (gz != 0.0f) {
+                        float *ad = acc_d + ((long)b * F + fi) * 3;
+#pragma unroll
+                        for (int k = 0; k < 3; k++)
+                            atomicAdd(ad + k, gz * w[k]);
                     }
-                    if (want_tex && nz) {
-                        float *gt = grad_textures + ((long)b * F + fi) * tex_n;
-                        float tf[3];
-                        int ti[3];
+                }
+                if (want_tex && nz) {
+                    float *gt = grad_textures + ((long)b * F + fi) * tex_n;
+                    float tf[3];
+                    int ti[3];
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
+                        ti[k] = hoc_tex_cell(t, ts);
+                        tf[k] = t - (float)ti[k];
+                    }
+#pragma unroll
+                    for (int pn = 0; pn < 8; pn++) {
+                        float ww = 1.0f;
+                        int isc = 0;
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
-                            const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
-                            ti[k] = hoc_tex_cell(t, ts);
-                            tf[k] = t - (float)ti[k];
+                            if (((pn >> k) & 1) == 0) {
+                                ww *= 1.0f - tf[k];
+                                isc = isc * ts + ti[k];
+                            } else {
+                                ww *= tf[k];
+                                isc = isc * ts + ti[k] + 1;
+                            }
                         }
+                        if (!TS2 && ts == 1)
+                            isc = 0;
+                        if (ww != 0.0f) {
 #pragma unroll
-                        for (int pn = 0; pn < 8; pn++) {
-                            float ww = 1.0f;
-                            int isc = 0;
-#pragma unroll
-                            for (int k = 0; k < 3; k++) {
-                                if (((pn >> k) & 1) == 0) {
-                                    ww *= 1.0f - tf[k];
-                                    isc = isc * ts + ti[k];
-                                } else {
-                                    ww *= tf[k];
-                                    isc = isc * ts + ti[k] + 1;
-                                }
-                            }
-                            if (!TS2 && ts == 1)
-                                isc = 0;
-                            if (ww != 0.0f) {
-#pragma unroll
-                                for (int c = 0; c < 3; c++)
-                                    atomicAdd(gt + isc * 3 + c, ww * gr[c]);
-                            }
+                            for (int c = 0; c < 3; c++)
+                                atomicAdd(gt + isc * 3 + c, ww * gr[r][c]);
                         }
                     }
                 }
@@ -239,21 +249,17 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
     }
 }
 
-/* One (face, edge, axis) task: the inward scans of every column the edge crosses; columns whose inside
- * pixel is owned by the face queue an outward scan on their line. */
-__device__ __forceinline__ void hoc_k4_face_task(const float *f, int fi, int edge, int axis, const HocBwdMaps &M,
-                                                 float eps, int *__restrict__ line_count,
-                                                 int *__restrict__ emitters, float *gA_out, float *gB_out)
+/* One column d0 of a (face, edge, axis): queue the outward scan on the line it runs along when the inside
+ * pixel is owned by the face, and do the short inward scan (the face's own pixels) here. */
+__device__ __forceinline__ void hoc_k4_face_column(const HocK4Edge &E, int fi, int edge, int axis, int d0,
+                                                   const HocBwdMaps &M, float eps, int *__restrict__ line_count,
+                                                   int *__restrict__ emitters, float *gA_out, float *gB_out)
 {
     const int S = M.S;
-    HocK4Edge E;
-    hoc_k4_edge(f, S, edge, axis, &E);
     float gA = 0.0f, gB = 0.0f;
-    for (int d0 = E.d0_from; d0 <= E.d0_to; d0++) {
-        float d1_cross;
-        int d1_in, d1_out;
-        if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out))
-            continue;
+    float d1_cross;
+    int d1_in, d1_out;
+    if (hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out)) {
         const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
         if (M.idx[(long)yin * S + xin] == fi) {
             const long line = ((long)M.b * 2 + axis) * S + d0;
@@ -266,18 +272,19 @@ __device__ __forceinline__ void hoc_k4_face_task(const float *f, int fi, int edg
         const int d1_to = min(max(d1_in, lim), S - 1);
         bool have_out = false;
         float I_out[4];
+        HocK4Col C;
         for (int d1 = d1_from; d1 <= d1_to; d1++) {
             const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
             if (M.idx[(long)yi * S + xi] != fi)
                 continue;
             if (!have_out) {
                 hoc_load_I(M, axis == 0 ? d0 : d1_out, axis == 0 ? d1_out : d0, I_out);
+                hoc_k4_col(&E, S, d0, d1_cross, &C);
                 have_out = true;
             }
             const float delta = hoc_delta(M, xi, yi, I_out);
-            if (delta <= 0.0f)
-                continue;
-            hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+            if (!(delta <= 0.0f))
+                hoc_k4_accum_col(&C, d1, eps, delta, &gA, &gB);
         }
     }
     *gA_out = gA;
@@ -285,8 +292,10 @@ __device__ __forceinline__ void hoc_k4_face_task(const float *f, int fi, int edg
 }
 
 /*
- * Face pass.  One CTA owns 256 consecutive faces of one sample; writes grad_faces for all of them
- * (depth term + inward scans; zeros for culled / unowned faces).
+ * Face pass.  One CTA owns BW_THREADS consecutive faces of one sample; writes grad_faces for all of them
+ * (depth term + inward scans; zeros for culled / unowned faces).  The faces that own pixels are
+ * compacted and their work is flattened to one item per (face, edge, axis, column), so that every lane
+ * has a short, independent task (the columns of all edges of ~35 faces, ~600 items per CTA).
  */
 __global__ void __launch_bounds__(BW_THREADS)
 hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
@@ -298,12 +307,14 @@ hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__res
     __shared__ float s_face[BW_THREADS][9];
     __shared__ float s_k4[BW_THREADS][6][2];
     __shared__ unsigned short s_vis[BW_THREADS];
+    __shared__ int s_pre[BW_THREADS * 6 + 1];
     __shared__ int s_nvis;
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
-    const int f_base = blockIdx.x * BW_THREADS;
-    const int fi = f_base + tid;
+    /* faces are dealt to the CTAs round-robin (CTA c takes faces c, c + G, c + 2G, ...) so that every CTA
+     * gets the same mix of large / small / hidden faces */
+    const int fi = tid * gridDim.x + blockIdx.x;
     const bool valid = fi < F;
     if (tid == 0)
         s_nvis = 0;
@@ -343,18 +354,61 @@ hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__res
         if (hit)
             s_vis[atomicAdd(&s_nvis, 1)] = (unsigned short)tid;
         __syncthreads();
-        const int ntask = s_nvis * 6;
-        for (int task = tid; task < ntask; task += BW_THREADS) {
-            const int lf = s_vis[task / 6];
-            const int combo = task - (task / 6) * 6;
-            float tf[9];
+        const int nq = s_nvis * 6; /* (face, edge, axis) groups */
+        for (int q = tid; q < nq; q += BW_THREADS) {
+            const int lf = s_vis[q / 6];
+            const int combo = q - (q / 6) * 6;
+            HocK4Edge E;
+            hoc_k4_edge(s_face[lf], S, combo >> 1, combo & 1, &E);
+            s_pre[q] = max(E.d0_to - E.d0_from + 1, 0);
+        }
+        __syncthreads();
+        if (tid < 32) { /* exclusive prefix sum of the column counts: each lane scans a contiguous chunk */
+            const int per = (nq + 31) / 32;
+            const int lo = min(tid * per, nq), hi = min(lo + per, nq);
+            int sum = 0;
+            for (int q = lo; q < hi; q++)
+                sum += s_pre[q];
+            int incl = sum;
 #pragma unroll
-            for (int k = 0; k < 9; k++)
-                tf[k] = s_face[lf][k];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+                if (tid >= o)
+                    incl += v;
+            }
+            int run = incl - sum;
+            for (int q = lo; q < hi; q++) {
+                const int c = s_pre[q];
+                s_pre[q] = run;
+                run += c;
+            }
+            if (tid == 31)
+                s_pre[nq] = incl;
+        }
+        __syncthreads();
+        const int total = s_pre[nq];
+        for (int item = tid; item < total; item += BW_THREADS) {
+            int lo = 0, hi = nq; /* last q with s_pre[q] <= item */
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_pre[mid] <= item)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const int q = lo;
+            const int lf = s_vis[q / 6];
+            const int combo = q - (q / 6) * 6;
+            const int edge = combo >> 1, axis = combo & 1;
+            HocK4Edge E;
+            hoc_k4_edge(s_face[lf], S, edge, axis, &E);
             float gA, gB;
-            hoc_k4_face_task(tf, f_base + lf, combo >> 1, combo & 1, M, eps, line_count, emitters, &gA, &gB);
-            s_k4[lf][combo][0] = gA;
-            s_k4[lf][combo][1] = gB;
+            hoc_k4_face_column(E, lf * gridDim.x + blockIdx.x, edge, axis, E.d0_from + (item - s_pre[q]), M, eps, line_count, emitters,
+                               &gA, &gB);
+            if (gA != 0.0f)
+                atomicAdd(&s_k4[lf][combo][0], gA);
+            if (gB != 0.0f)
+                atomicAdd(&s_k4[lf][combo][1], gB);
         }
         __syncthreads();
     }
@@ -401,7 +455,7 @@ hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__res
  * where the incoming gradient is non-zero is staged in shared memory once (I = (alpha, r, g, b) and
  * dL/dI per pixel); every lane then runs one queued outward scan from shared memory.
  */
-#define LN_THREADS 128
+#define LN_THREADS 256
 __global__ void __launch_bounds__(LN_THREADS)
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
@@ -476,6 +530,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         const int d1_from = max(max(min(d1_out, d1_limit), 0), lo);
         const int d1_to = min(min(max(d1_out, d1_limit), S - 1), hi);
         float gA = 0.0f, gB = 0.0f;
+        HocK4Col C;
+        hoc_k4_col(&E, S, d0, d1_cross, &C);
         for (int d1 = d1_from; d1 <= d1_to; d1++) {
             const int i = d1 - lo;
             /* delta = sum_ch (I - I_in) * g in the reference's order: alpha first, then r, g, b */
@@ -487,9 +543,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 for (int k = 1; k < 4; k++)
                     delta += (s_line[k * len + i] - I_in[k]) * s_line[(4 + k) * len + i];
             }
-            if (delta <= 0.0f)
-                continue;
-            hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+            if (!(delta <= 0.0f))
+                hoc_k4_accum_col(&C, d1, eps, delta, &gA, &gB);
         }
         float *gf = grad_faces + ((long)b * F + fi) * 9;
         if (gA != 0.0f)

@@ -26,17 +26,47 @@
 #include "hoc_common.cuh"
 #include "raster_math.h"
 
-#define ZB_WARPS 8
+#define ZB_WARPS 4
 #define ZB_THREADS (ZB_WARPS * 32)
-#define ZB_REC 24 /* floats per staged face record: 9 face + 9 inverse + 4 bbox (+2 pad) */
-#define ZB_SMALL 48 /* bounding boxes up to this many pixels are swept by one lane */
+#define ZB_FACES_PER_WARP 64 /* two faces per lane before culling, ~one after */
+#define ZB_REC 24            /* floats per surviving face: 9 coordinates, 9 inverse, x0, y0, width, 1/width, id */
 
+/* clipped pixel bounding box of a face: inside => pmin <= xi <= pmax in exact arithmetic; half a
+ * pixel of slack absorbs fp32 rounding of the edge tests.  false when empty. */
+__device__ __forceinline__ bool hoc_face_bbox(const float *f, int S, int *x0, int *y0, int *x1, int *y1)
+{
+    const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
+    const float pxmax = hoc_ndc_to_pix(fmaxf(f[0], fmaxf(f[3], f[6])), S);
+    const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
+    const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
+    const float fS1 = (float)(S - 1);
+    const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
+    const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
+    const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
+    const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
+    if (!(x_lo <= x_hi && y_lo <= y_hi))
+        return false;
+    *x0 = (int)x_lo;
+    *y0 = (int)y_lo;
+    *x1 = (int)x_hi;
+    *y1 = (int)y_hi;
+    return true;
+}
+
+/*
+ * A warp culls 64 faces, compacts the survivors (about half of a closed, back-filled mesh) into shared
+ * memory together with their barycentric matrices and pixel bounding boxes, and then walks the
+ * CONCATENATION of all bounding boxes with one pixel per lane: every lane always has a pixel to test,
+ * whatever the sizes of the individual faces (a 9k-triangle mesh at 256x256 has faces of 2-30 pixels,
+ * a silhouette test has two triangles of 30 000).
+ */
 __global__ void __launch_bounds__(ZB_THREADS)
 hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__restrict__ zbuf, int F, int S,
                        float near_, float far_)
 {
     extern __shared__ float s_centre[]; /* [S] pixel-centre NDC coordinate of index i */
-    __shared__ float s_rec[ZB_WARPS][32][ZB_REC];
+    __shared__ float s_rec[ZB_WARPS][ZB_FACES_PER_WARP][ZB_REC];
+    __shared__ int s_pre[ZB_WARPS][ZB_FACES_PER_WARP + 1];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -45,107 +75,86 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
     for (int i = threadIdx.x; i < S; i += ZB_THREADS)
         s_centre[i] = hoc_pix_centre(i, S);
 
-    const int fi = blockIdx.x * ZB_THREADS + warp * 32 + lane;
-    bool active = false; /* large face: swept by the whole warp below */
-    bool small = false;  /* few-pixel face (the common case): swept by its own lane */
-    int sx0 = 0, sy0 = 0, sx1 = -1, sy1 = -1;
-    float sf[9], sinv[9];
-    if (fi < F) {
+    /* faces are dealt to the warps round-robin (warp w takes faces w, w + W, w + 2W, ...): neighbouring
+     * faces of a mesh have similar screen size, so contiguous chunks would give some warps (the hand, close
+     * to the camera) several times the pixels of others */
+    const int n_warps = gridDim.x * ZB_WARPS;
+    const int gw = blockIdx.x * ZB_WARPS + warp;
+    int n_surv = 0, n_pix = 0;
+#pragma unroll
+    for (int h = 0; h < ZB_FACES_PER_WARP / 32; h++) {
+        const int fi = (h * 32 + lane) * n_warps + gw;
         float f[9];
-        const float *src = faces + ((long)b * F + fi) * 9;
+        int x0 = 0, y0 = 0, x1 = -1, y1 = -1;
+        bool keep = false;
+        if (fi < F) {
+            const float *src = faces + ((long)b * F + fi) * 9;
 #pragma unroll
-        for (int k = 0; k < 9; k++)
-            f[k] = __ldg(src + k);
-        if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
-            /* pixel bounding box: inside  =>  pmin <= xi <= pmax in exact arithmetic;
-             * half a pixel of slack absorbs fp32 rounding of the edge tests. */
-            const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
-            const float pxmax = hoc_ndc_to_pix(fmaxf(f[0], fmaxf(f[3], f[6])), S);
-            const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
-            const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
-            const float fS1 = (float)(S - 1);
-            const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
-            const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
-            const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
-            const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
-            if (x_lo <= x_hi && y_lo <= y_hi) {
-                float inv[9];
-                hoc_face_inv(f, S, inv);
-                const int x0 = (int)x_lo, y0 = (int)y_lo, x1 = (int)x_hi, y1 = (int)y_hi;
-                if ((x1 - x0 + 1) * (y1 - y0 + 1) <= ZB_SMALL) {
-                    small = true;
-                    sx0 = x0; sy0 = y0; sx1 = x1; sy1 = y1;
-#pragma unroll
-                    for (int k = 0; k < 9; k++) {
-                        sf[k] = f[k];
-                        sinv[k] = inv[k];
-                    }
-                } else {
-                    active = true;
-                    float *rec = s_rec[warp][lane];
-#pragma unroll
-                    for (int k = 0; k < 9; k++) {
-                        rec[k] = f[k];
-                        rec[9 + k] = inv[k];
-                    }
-                    rec[18] = x_lo;
-                    rec[19] = y_lo;
-                    rec[20] = x_hi - x_lo + 1.0f;
-                    rec[21] = y_hi - y_lo + 1.0f;
-                }
-            }
+            for (int k = 0; k < 9; k++)
+                f[k] = __ldg(src + k);
+            keep = hoc_face_xy_finite(f) && !hoc_face_back(f) && hoc_face_bbox(f, S, &x0, &y0, &x1, &y1);
         }
+        const unsigned m = __ballot_sync(HOC_FULL_MASK, keep);
+        const int cnt = keep ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0;
+        /* inclusive scan of the pixel counts over the lanes */
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        if (keep) {
+            const int slot = n_surv + __popc(m & ((1u << lane) - 1u));
+            float *rec = s_rec[warp][slot];
+            float inv[9];
+            hoc_face_inv(f, S, inv);
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                rec[k] = f[k];
+                rec[9 + k] = inv[k];
+            }
+            rec[18] = __int_as_float(x0);
+            rec[19] = __int_as_float(y0);
+            rec[20] = __int_as_float(x1 - x0 + 1);
+            rec[21] = 1.0f / (float)(x1 - x0 + 1);
+            rec[22] = __int_as_float(fi);
+            s_pre[warp][slot] = n_pix + incl - cnt;
+        }
+        n_surv += __popc(m);
+        n_pix += __shfl_sync(HOC_FULL_MASK, incl, 31);
     }
-    __syncthreads(); /* s_centre ready; also orders s_rec writes */
+    if (lane == 0)
+        s_pre[warp][n_surv] = n_pix;
+    __syncthreads(); /* s_centre ready; orders the record writes */
 
     unsigned long long *zb = zbuf + (long)b * S * S;
-    const int f_base = blockIdx.x * ZB_THREADS + warp * 32;
-    if (small) {
-        for (int yi = sy0; yi <= sy1; yi++) {
-            const float yp = s_centre[yi];
-            for (int xi = sx0; xi <= sx1; xi++) {
-                if (!hoc_pixel_inside(sf, s_centre[xi], yp))
-                    continue;
-                float w[3], zp;
-                if (!hoc_pixel_weights_depth(sf, sinv, xi, yi, near_, far_, w, &zp))
-                    continue;
-                if (!(zp < far_))
-                    continue;
-                const unsigned long long key = ((unsigned long long)hoc_float_order(zp) << 32) | (unsigned)fi;
-                atomicMin(zb + (long)yi * S + xi, key);
-            }
+    const int *pre = s_pre[warp];
+    for (int item = lane; item < n_pix; item += 32) {
+        int lo = 0, hi = n_surv; /* last slot with pre[slot] <= item */
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pre[mid] <= item)
+                lo = mid;
+            else
+                hi = mid;
         }
-    }
-    __syncwarp();
-    unsigned todo = __ballot_sync(HOC_FULL_MASK, active);
-    while (todo) {
-        const int j = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const float *rec = s_rec[warp][j];
-        float f[9], inv[9];
-#pragma unroll
-        for (int k = 0; k < 9; k++) {
-            f[k] = rec[k];
-            inv[k] = rec[9 + k];
-        }
-        const int x0 = (int)rec[18], y0 = (int)rec[19];
-        const int bw = (int)rec[20], bh = (int)rec[21];
-        const int n = bw * bh;
-        const unsigned fidx = (unsigned)(f_base + j);
-        for (int p = lane; p < n; p += 32) {
-            const int yy = p / bw;
-            const int xi = x0 + (p - yy * bw);
-            const int yi = y0 + yy;
-            if (!hoc_pixel_inside(f, s_centre[xi], s_centre[yi]))
-                continue;
-            float w[3], zp;
-            if (!hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp))
-                continue;
-            if (!(zp < far_)) /* NaN depth never wins a `<` comparison in the reference */
-                continue;
-            const unsigned long long key = ((unsigned long long)hoc_float_order(zp) << 32) | fidx;
-            atomicMin(zb + (long)yi * S + xi, key);
-        }
+        const float *rec = s_rec[warp][lo];
+        const int p = item - pre[lo];
+        const int bw = __float_as_int(rec[20]);
+        int yy = (int)(((float)p + 0.5f) * rec[21]); /* p / bw for p < 2^22 */
+        const int xi = __float_as_int(rec[18]) + (p - yy * bw);
+        const int yi = __float_as_int(rec[19]) + yy;
+        if (!hoc_pixel_inside(rec, s_centre[xi], s_centre[yi]))
+            continue;
+        float w[3], zp;
+        if (!hoc_pixel_weights_depth(rec, rec + 9, xi, yi, near_, far_, w, &zp))
+            continue;
+        if (!(zp < far_)) /* NaN depth never wins a `<` comparison in the reference */
+            continue;
+        const unsigned long long key =
+            ((unsigned long long)hoc_float_order(zp) << 32) | (unsigned)__float_as_int(rec[22]);
+        atomicMin(zb + (long)yi * S + xi, key);
     }
 }
 
@@ -313,7 +322,8 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
         return HOC_ERR_CUDA;
     }
     if (F > 0) {
-        dim3 grid((F + ZB_THREADS - 1) / ZB_THREADS, B);
+        const int per_cta = ZB_WARPS * ZB_FACES_PER_WARP;
+        dim3 grid((F + per_cta - 1) / per_cta, B);
         HOC_LAUNCH(HOC_K_RASTER_ZBUF, st,
                    (hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_)));
         HOC_CHECK_LAUNCH("hoc_raster_zbuf_kernel");

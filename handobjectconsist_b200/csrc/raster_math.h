@@ -230,3 +230,38 @@ HOC_HD void hoc_k4_accum(const HocK4Edge *E, int S, int d0, int d1, float d1_cro
         *gB -= delta / dist;
     }
 }
+
+/* Per-column constants of hoc_k4_accum, hoisted out of the scan loops: dist = c * (d1 - d1_cross) * 2 / S
+ * with c = (b0-a0)/(b0-d0) for vertex A and (b0-a0)/(d0-a0) for vertex B (a vertex whose walk coordinate
+ * equals d0 gets no contribution).  `scale` = 2 / S is applied as one multiply (<= 1 ulp from the
+ * reference's `* 2. / is`; gradients carry a 1e-3 tolerance). */
+struct HocK4Col {
+    float cross, cA, cB, scale;
+    bool hasA, hasB;
+};
+
+HOC_HD void hoc_k4_col(const HocK4Edge *E, int S, int d0, float d1_cross, HocK4Col *C)
+{
+    const float fd0 = (float)d0;
+    C->cross = d1_cross;
+    C->scale = 2.0f / (float)S;
+    C->hasA = E->b0 != fd0;
+    C->hasB = E->a0 != fd0;
+    C->cA = C->hasA ? (E->b0 - E->a0) / (E->b0 - fd0) : 0.0f;
+    C->cB = C->hasB ? (E->b0 - E->a0) / (fd0 - E->a0) : 0.0f;
+}
+
+HOC_HD void hoc_k4_accum_col(const HocK4Col *C, int d1, float eps, float delta, float *gA, float *gB)
+{
+    const float t = ((float)d1 - C->cross) * C->scale;
+    if (C->hasA) {
+        float dist = C->cA * t;
+        dist = (0 < dist) ? dist + eps : dist - eps;
+        *gA -= delta / dist;
+    }
+    if (C->hasB) {
+        float dist = C->cB * t;
+        dist = (0 < dist) ? dist + eps : dist - eps;
+        *gB -= delta / dist;
+    }
+}

@@ -166,6 +166,11 @@ class _FlowVertexFunction(Function):
         ctx.save_for_backward(v1, v2, *cams)
         ctx.cfg = (B, V, flags, float(orig_size))
         ctx.set_materialize_grads(False)
+        # ndc_k depends on verts_k only: a detached frame (first_only / gt_refs, warpbranch.py:45-55) must not
+        # make its render look differentiable, or its geometry backward would run for nothing
+        nondiff = [o for o, need in ((outs[0], ctx.needs_input_grad[0]), (outs[1], ctx.needs_input_grad[1])) if not need]
+        if nondiff:
+            ctx.mark_non_differentiable(*nondiff)
         return tuple(outs)
 
     @staticmethod

@@ -116,8 +116,9 @@ def test_fused_flow_path_equals_op_by_op_path(detach):
         assert outs[0][0][i].shape == (B, 64, S, 2)
         assert (outs[0][0][i] - outs[1][0][i]).abs().max().item() <= 1e-4  # north_star pixel tolerance
         assert torch.equal(outs[0][0][i] == 0, outs[1][0][i] == 0)
-    for k in (1, 2):
-        assert helpers.rel_err(outs[0][k].cpu().numpy(), outs[1][k].cpu().numpy()) < 1e-3
+    for k in (1, 2):  # vertex gradients: sums over many faces with cancellation -> relative to the gradient scale
+        a, b = outs[0][k].cpu().numpy(), outs[1][k].cpu().numpy()
+        assert np.abs(a - b).max() <= 1e-3 * np.abs(b).max()
 
 
 def test_graphed_step_matches_eager():
