@@ -55,7 +55,21 @@ SIGNATURES = {
 
 KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_backward": 3, "warp_photo_fwd": 4,
               "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8, "mesh_gather": 9, "mesh_scatter": 10,
-              "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16}
+              "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16, "mano_fwd": 17,
+              "mano_bwd": 18}
+
+
+
+class ManoModelStruct(ctypes.Structure):
+    """``hoc_mano_model`` of include/hoc_b200.h."""
+    _fields_ = [("v_template", _vp), ("shapedirs", _vp), ("posedirs", _vp), ("j_regressor", _vp), ("weights", _vp),
+                ("hands_components", _vp), ("hands_mean", _vp), ("num_verts", _i), ("ncomps", _i), ("use_pca", _i),
+                ("center_idx", _i), ("tip_ids", _i * 5)]
+
+
+SIGNATURES["hoc_mano_forward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp, _vp, _i, _vp, _vp, _vp])
+SIGNATURES["hoc_mano_backward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
+                                        _vp])
 
 _LIB = None
 

@@ -166,3 +166,34 @@ def make_scene(batch, width=256, height=256, seed=0, device="cpu", with_object=T
         image_ref=t(img[0]), image=t(img[1]), jitter_mask_ref=t(jit[0]), jitter_mask=t(jit[1]),
         hand_ignore_faces=HAND_IGNORE_FACES,
     )
+
+
+def mano_model(seed=0, device="cpu"):
+    """Synthetic parameter set with MANO's shapes (the licensed MANO_RIGHT.pkl is not available): the hand
+    template, 16 joints on five three-link chains, softmax skinning weights, small shape / pose blend shapes,
+    an orthonormal PCA basis and a non-zero mean pose.  Returns a dict of float32 tensors + ``tip_ids`` /
+    ``faces`` (the 1538 non-closing faces)."""
+    rng = np.random.default_rng(seed + 100)
+    v, f = hand_template()
+    v = v.astype(np.float64)
+    # joints: root at the wrist end, five chains fanning out along +y
+    joints = [np.array([0.0, -0.08, 0.0])]
+    for finger in range(5):
+        x = (finger - 2) * 0.018
+        for link in range(3):
+            joints.append(np.array([x * (1 + 0.2 * link), -0.02 + 0.035 * link, 0.0]))
+    J = np.stack(joints)  # [16,3]
+    d2 = ((v[:, None, :] - J[None]) ** 2).sum(-1)
+    w = np.exp(-d2 / (0.02 ** 2))
+    w = w / w.sum(1, keepdims=True)
+    # J_regressor: rows that reproduce J from the template as well as a sparse, positive regressor can
+    jr = np.exp(-d2.T / (0.012 ** 2))
+    jr = jr / jr.sum(1, keepdims=True)
+    q, _ = np.linalg.qr(rng.normal(size=(45, 45)))
+    model = dict(
+        v_template=v, shapedirs=rng.normal(size=(778, 3, 10)) * 2e-3, posedirs=rng.normal(size=(778, 3, 135)) * 2e-4,
+        j_regressor=jr, weights=w, hands_components=q, hands_mean=rng.normal(size=45) * 0.15)
+    out = {k: torch.from_numpy(np.ascontiguousarray(a)).float().to(device) for k, a in model.items()}
+    out["tip_ids"] = (745, 317, 444, 556, 673)
+    out["faces"] = torch.from_numpy(f[:1538].copy()).to(device)
+    return out

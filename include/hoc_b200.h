@@ -67,6 +67,8 @@ const char *hoc_last_error(void);
 #define HOC_K_RASTER_BWD_LINE 14
 #define HOC_K_FLOW_VERTICES 15
 #define HOC_K_FLOW_VERTICES_BWD 16
+#define HOC_K_MANO_FWD 17
+#define HOC_K_MANO_BWD 18
 #define HOC_KERNEL_COUNT 24
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
@@ -204,6 +206,38 @@ int hoc_flow_vertices_backward(const float *verts1, const float *verts2, const f
                                int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B, int V,
                                const float *grad_ndc1, const float *grad_ndc2, const float *grad_attrs12,
                                const float *grad_attrs21, float *grad_verts1, float *grad_verts2, void *stream);
+
+/* ---- MANO linear-blend skinning ------------------------------------------------------------
+ * Replaces manopth ManoLayer.forward (absent dependency; called at manobranch.py:70-85,139-145 and built at
+ * warpreg.py:54-60) for PCA or axis-angle pose input with an axis-angle root.  One launch per direction.
+ * Model constants (device, fp32, MANO's own layouts): v_template [V,3], shapedirs [V,3,10],
+ * posedirs [V,3,135], j_regressor [16,V], weights [V,16], hands_components [ncomps,45] (PCA rows actually
+ * used; ignored when use_pca == 0), hands_mean [45] (zeros for flat_hand_mean).
+ *   pose  [B,3+ncomps] (use_pca) or [B,48] (axis-angle, ncomps = 45); betas [B,10] or NULL (zeros);
+ *   trans [B,3] or NULL (then the outputs are centred on reordered joint `center_idx`, -1 = no centring);
+ *   verts [B,V,3], joints [B,21,3] out, millimetres and joint order of manopth. */
+typedef struct hoc_mano_model {
+    const float *v_template;
+    const float *shapedirs;
+    const float *posedirs;
+    const float *j_regressor;
+    const float *weights;
+    const float *hands_components;
+    const float *hands_mean;
+    int num_verts;
+    int ncomps;
+    int use_pca;
+    int center_idx;
+    int tip_ids[5]; /* fingertip vertex ids (manopth: 745, 317, 444 (right) / 445 (left), 556, 673) */
+} hoc_mano_model;
+
+int hoc_mano_forward(const hoc_mano_model *model, const float *pose, const float *betas, const float *trans, int B,
+                     float *verts, float *joints, void *stream);
+/* grad_verts [B,V,3] / grad_joints [B,21,3] (either may be NULL) -> grad_pose [B,3+ncomps], grad_betas [B,10],
+ * grad_trans [B,3] (any may be NULL; fully overwritten). */
+int hoc_mano_backward(const hoc_mano_model *model, const float *pose, const float *betas, const float *trans,
+                      const float *grad_verts, const float *grad_joints, int B, float *grad_pose, float *grad_betas,
+                      float *grad_trans, void *stream);
 
 #ifdef __cplusplus
 }
