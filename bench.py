@@ -86,13 +86,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def _make_sets(n_sets, pairs, size, device, pin=False, rank=0):
+def _make_sets(n_sets, pairs, size, device, pin=False, rank=0, world=1):
+    """`n_sets` input sets for this rank: the GLOBAL batch of pairs*world frame pairs is generated identically on
+    every rank (same seed) and rank r keeps its shard [r*pairs, (r+1)*pairs) -- sharding.shard_range."""
     import torch
-    from handobjectconsist_b200 import synth
+    from handobjectconsist_b200 import sharding, synth
 
     sets = []
     for i in range(n_sets):
-        sc = synth.make_scene(pairs, size, size, seed=1000 * rank + i)
+        sc = synth.make_scene(pairs * world, size, size, seed=1000 + i)
+        lo, hi = sharding.shard_range(pairs * world, rank, world)
+        sc = {k: (v[lo:hi].contiguous() if torch.is_tensor(v) else v) for k, v in sc.items()}
         if device is not None:
             sc = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in sc.items()}
         elif pin:
@@ -169,7 +173,7 @@ def run_native(args, rank, world, local_rank):
         barrier()
         return t0.elapsed_time(t1)
 
-    dsets = _make_sets(N_SETS, PAIRS, SIZE, dev, rank=rank)
+    dsets = _make_sets(N_SETS, PAIRS, SIZE, dev, rank=rank, world=world)
     hand_face = dsets[0]["faces"][0, :1552].clone()
     ignore = dsets[0]["hand_ignore_faces"]
     dbatches = [_samples_from_scene(sc) for sc in dsets]
@@ -211,7 +215,7 @@ def run_native(args, rank, world, local_rank):
     launches = launches_per_step * args.steps
 
     # ---- end-to-end arm: pinned host buffers -> static device buffers -> graph -> host ----
-    hsets = _make_sets(N_SETS, PAIRS, SIZE, None, pin=True, rank=rank)
+    hsets = _make_sets(N_SETS, PAIRS, SIZE, None, pin=True, rank=rank, world=world)
     hbatches = [_samples_from_scene(sc) for sc in hsets]
     grad_host = [torch.empty(PAIRS, 778, 3).pin_memory(), torch.empty(PAIRS, 1502, 3).pin_memory()]
     loss_host = torch.empty(()).pin_memory()
@@ -255,10 +259,9 @@ def run_native(args, rank, world, local_rank):
         e2e_step(i)
     e2e_ms = timed(lambda i: e2e_step(i + args.warmup), args.steps)
 
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms, eager_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, eager_ms = t.tolist()
+    from handobjectconsist_b200 import sharding
+    ms, e2e_ms, eager_ms = sharding.max_over_ranks([ms, e2e_ms, eager_ms], device=dev)
+    global_loss = float(sharding.global_mean_loss(gstep.loss))  # the one scalar exchange of the path
     if rank != 0:
         return None
 
@@ -312,6 +315,7 @@ def run_native(args, rank, world, local_rank):
         "e2e": {"value": frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
+        "loss_global_mean": global_loss,
         "execution": "forward+backward captured once in a CUDA graph (handobjectconsist_b200.graphed), replayed per step",
         "eager": {"value": frames / (eager_ms / 1e3), "ms_per_step": eager_ms / args.steps,
                   "note": "same step with every launch issued from python; per-kernel times come from this arm"},
