@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libhoc_b200.so")
 
 HOC_LAYOUT_RAW = 0
 HOC_LAYOUT_IMAGE = 1
+HOC_TEX_GRAD_CUBE = 0
+HOC_TEX_GRAD_VERTEX = 1
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
 _vp = ctypes.c_void_p
@@ -35,7 +37,7 @@ SIGNATURES = {
     "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
-    "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _vp, _vp,
+    "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i, _vp, _vp,
                                  _vp, _sz, _vp]),
     "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hoc_warp_photo_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
@@ -43,7 +45,7 @@ SIGNATURES = {
     "hoc_warp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "hoc_occlusion_mask": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "hoc_mesh_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "hoc_mesh_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hoc_mesh_scatter": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hoc_flow_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _vp,
                                _vp]),
     "hoc_flow_finalize_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

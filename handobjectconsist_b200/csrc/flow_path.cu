@@ -84,7 +84,7 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
 
 __global__ void __launch_bounds__(FP_THREADS)
 hoc_mesh_scatter_kernel(const float *__restrict__ grad_faces, const float *__restrict__ grad_tex,
-                        const long long *__restrict__ faces_idx, int V, int F, int fill_back,
+                        const long long *__restrict__ faces_idx, int V, int F, int fill_back, int tex_grad_mode,
                         float *__restrict__ grad_verts, float *__restrict__ grad_attrs)
 {
     const int Fo = fill_back ? 2 * F : F;
@@ -104,7 +104,16 @@ hoc_mesh_scatter_kernel(const float *__restrict__ grad_faces, const float *__res
         }
     }
     bool any_t = false;
-    if (grad_tex != nullptr && grad_attrs != nullptr) {
+    if (grad_tex != nullptr && grad_attrs != nullptr && tex_grad_mode == HOC_TEX_GRAD_VERTEX) {
+        const float *src = grad_tex + ((long)b * Fo + fo) * 9;
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) {
+                gc[k][ch] = src[3 * k + ch];
+                any_t = any_t || (gc[k][ch] != 0.0f);
+            }
+    } else if (grad_tex != nullptr && grad_attrs != nullptr) {
         const float4 *src = reinterpret_cast<const float4 *>(grad_tex + ((long)b * Fo + fo) * 24);
         float g[24];
 #pragma unroll
@@ -190,7 +199,7 @@ __device__ __forceinline__ float hoc_fp_mask(const HocRender &R, int b, int S, i
     const float a = R.alpha[po];
     *alpha_out = a;
     float m = (a > 0.99999f) ? 1.0f : 0.0f;
-    if (n_ignore > 0) {
+    if (n_ignore > 0 && m != 0.0f) { /* the keep-mask only matters where alpha passed the threshold */
         const int fidx = R.idx[((long)b * S + (S - 1 - y)) * S + x];
         bool keep = true;
         for (int k = 0; k < n_ignore; k++)
@@ -500,7 +509,8 @@ extern "C" int hoc_mesh_gather(const float *verts, const float *attrs, const lon
 }
 
 extern "C" int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B,
-                                int V, int F, int fill_back, float *grad_verts, float *grad_attrs, void *stream)
+                                int V, int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs,
+                                void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && V >= 0 && F >= 0, "hoc_mesh_scatter: bad shape B=%d V=%d F=%d", B, V, F);
     HOC_CHECK_ARG(B <= 65535, "hoc_mesh_scatter: batch %d exceeds 65535", B);
@@ -523,7 +533,7 @@ extern "C" int hoc_mesh_scatter(const float *grad_faces, const float *grad_textu
     dim3 grid((Fo + FP_THREADS - 1) / FP_THREADS, B);
     HOC_LAUNCH(HOC_K_MESH_SCATTER, st,
                (hoc_mesh_scatter_kernel<<<grid, FP_THREADS, 0, st>>>(grad_faces, grad_textures, faces_idx, V, F,
-                                                                     fill_back, grad_verts, grad_attrs)));
+                                                                     fill_back, tex_grad_mode, grad_verts, grad_attrs)));
     HOC_CHECK_LAUNCH("hoc_mesh_scatter_kernel");
     return HOC_OK;
 }

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                             const float *__restrict__ g_rgb, const float *__restrict__ g_alpha,
                             const float *__restrict__ g_depth, int F, int S, int ts, float near_, float far_, float eps,
-                            int layout, int want_ext, int *__restrict__ ext, int *__restrict__ owned,
+                            int layout, int want_ext, int tex_mode, int *__restrict__ ext, int *__restrict__ owned,
                             float *__restrict__ acc_d, float *__restrict__ grad_textures)
 {
     __shared__ int s_lo[8][32];
@@ -184,7 +184,21 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
                             atomicAdd(ad + k, gz * w[k]);
                     }
                 }
-                if (want_tex && nz) {
+                if (want_tex && nz && tex_mode == HOC_TEX_GRAD_VERTEX) {
+                    /* textures are the multilinear extension of three vertex values (T[i,j,k] = i c0 + j c1 +
+                     * k c2, ts == 2): d rgb / d c_k = t_k, so nine sums per face instead of twenty-four */
+                    float *gt = grad_textures + ((long)b * F + fi) * 9;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, 2, eps);
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float v = t * gr[r][c];
+                            if (v != 0.0f)
+                                atomicAdd(gt + 3 * k + c, v);
+                        }
+                    }
+                } else if (want_tex && nz) {
                     float *gt = grad_textures + ((long)b * F + fi) * tex_n;
                     float tf[3];
                     int ti[3];
@@ -212,8 +226,11 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
                             isc = 0;
                         if (ww != 0.0f) {
 #pragma unroll
-                            for (int c = 0; c < 3; c++)
-                                atomicAdd(gt + isc * 3 + c, ww * gr[r][c]);
+                            for (int c = 0; c < 3; c++) {
+                                const float v = ww * gr[r][c];
+                                if (v != 0.0f)
+                                    atomicAdd(gt + isc * 3 + c, v);
+                            }
                         }
                     }
                 }
@@ -564,10 +581,12 @@ extern "C" size_t hoc_raster_backward_workspace_bytes(int B, int F, int S)
 extern "C" int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
                                    const float *rgb, const float *grad_rgb, const float *grad_alpha,
                                    const float *grad_depth, int B, int F, int S, int ts, float near_, float far_,
-                                   float eps, int layout, int use_alpha, float *grad_faces, float *grad_textures,
-                                   void *workspace, size_t workspace_bytes, void *stream)
+                                   float eps, int layout, int use_alpha, int tex_grad_mode, float *grad_faces,
+                                   float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
 {
     (void)textures;
+    HOC_CHECK_ARG(tex_grad_mode == HOC_TEX_GRAD_CUBE || (tex_grad_mode == HOC_TEX_GRAD_VERTEX && ts == 2),
+                  "hoc_raster_backward: tex_grad_mode %d (vertex mode needs texture_size 2, got %d)", tex_grad_mode, ts);
     HOC_CHECK_ARG(B >= 0 && F >= 0, "hoc_raster_backward: negative batch (%d) or face count (%d)", B, F);
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_backward: image_size %d outside [1, 2048]", S);
     HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_backward: bad layout %d",
@@ -590,7 +609,9 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     const float *g_alpha = use_alpha ? grad_alpha : nullptr;
     const bool k4 = grad_faces != nullptr && (grad_rgb != nullptr || g_alpha != nullptr);
     const bool want_depth = grad_faces != nullptr && grad_depth != nullptr;
-    const size_t tex_bytes = sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
+    const size_t tex_bytes = (tex_grad_mode == HOC_TEX_GRAD_VERTEX)
+                                 ? sizeof(float) * 9 * (size_t)B * F
+                                 : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
 
     cudaError_t e = cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, st);
     if (e == cudaSuccess && k4) { /* hi rows = -1, lo rows (every second row of S ints) = 0x7f7f7f7f */
@@ -611,12 +632,12 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_pixel_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
                            faces, face_index_map, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, eps, layout,
-                           k4 ? 1 : 0, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
+                           k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
         else
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_pixel_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
                            faces, face_index_map, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, eps, layout,
-                           k4 ? 1 : 0, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
+                           k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_pixel_kernel");
     }
     if (grad_faces == nullptr)

@@ -28,7 +28,7 @@
 
 #define ZB_WARPS 4
 #define ZB_THREADS (ZB_WARPS * 32)
-#define ZB_FACES_PER_WARP 64 /* two faces per lane before culling, ~one after */
+#define ZB_FACES_PER_WARP 32 /* one face per lane before culling */
 #define ZB_REC 24            /* floats per surviving face: 9 coordinates, 9 inverse, x0, y0, width, 1/width, id */
 
 /* clipped pixel bounding box of a face: inside => pmin <= xi <= pmax in exact arithmetic; half a

@@ -137,7 +137,8 @@ def _backward_impl(ctx, grad_rgb, grad_alpha, grad_depth):
         code = L.hoc_raster_backward(
             _lib.ptr(faces), _lib.ptr(textures), _lib.ptr(face_index_map), _lib.ptr(rgb), _lib.ptr(g_rgb),
             _lib.ptr(g_alpha), _lib.ptr(g_depth), B, Fn, S, ctx.texture_size, ctx.near, ctx.far, ctx.eps, ctx.layout,
-            int(ctx.return_alpha), _lib.ptr(grad_faces), _lib.ptr(grad_textures), _lib.ptr(ws), ws_bytes,
+            int(ctx.return_alpha), _lib.HOC_TEX_GRAD_CUBE, _lib.ptr(grad_faces), _lib.ptr(grad_textures), _lib.ptr(ws),
+            ws_bytes,
             _lib.stream_ptr())
         _lib.check(code, "hoc_raster_backward")
     return grad_faces, grad_textures

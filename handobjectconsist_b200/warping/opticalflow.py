@@ -81,17 +81,19 @@ class _MeshRasterFunction(Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
             grad_faces = torch.empty_like(faces) if need_v else None
-            grad_tex = torch.empty((B, Fo, 2, 2, 2, 3), dtype=torch.float32, device=dev) if need_a else None
+            # the cubes come from three vertex values per face: ask for d loss / d vertex value directly
+            grad_tex = torch.empty((B, Fo, 3, 3), dtype=torch.float32, device=dev) if need_a else None
             ws_bytes = L.hoc_raster_backward_workspace_bytes(B, Fo, S)
             ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
             _lib.check(L.hoc_raster_backward(_lib.ptr(faces), None, _lib.ptr(idx), _lib.ptr(rgb), _lib.ptr(g_rgb),
                                              _lib.ptr(g_alpha), _lib.ptr(g_depth), B, Fo, S, 2, near, far, eps,
-                                             _lib.HOC_LAYOUT_IMAGE, 1, _lib.ptr(grad_faces), _lib.ptr(grad_tex),
-                                             _lib.ptr(ws), ws_bytes, st), "hoc_raster_backward")
+                                             _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_faces),
+                                             _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st), "hoc_raster_backward")
             grad_verts = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_v else None
             grad_attrs = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_a else None
             _lib.check(L.hoc_mesh_scatter(_lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(fi), B, V, Fn,
-                                          int(fill_back), _lib.ptr(grad_verts), _lib.ptr(grad_attrs), st),
+                                          int(fill_back), _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_verts),
+                                          _lib.ptr(grad_attrs), st),
                        "hoc_mesh_scatter")
         return (grad_verts, grad_attrs) + (None,) * 7
 

@@ -116,12 +116,17 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
  *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes (dominated by the outward-scan queue,
  *                    24 S^2 B bytes worst case, of which only the used part is ever touched)
  */
+/* tex_grad_mode: CUBE = grad_textures is [B,F,ts,ts,ts,3] (the reference's backward_textures);
+ * VERTEX = the cubes were built by hoc_mesh_gather from three vertex values per face (ts == 2): grad_textures
+ * is [B,F,3,3] = d loss / d (vertex k of the face, channel c) -- nine sums per face instead of twenty-four. */
+#define HOC_TEX_GRAD_CUBE 0
+#define HOC_TEX_GRAD_VERTEX 1
 size_t hoc_raster_backward_workspace_bytes(int B, int F, int S);
 int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
                         const float *rgb, const float *grad_rgb, const float *grad_alpha,
                         const float *grad_depth, int B, int F, int S, int ts, float near_, float far_,
-                        float eps, int layout, int use_alpha, float *grad_faces, float *grad_textures,
-                        void *workspace, size_t workspace_bytes, void *stream);
+                        float eps, int layout, int use_alpha, int tex_grad_mode, float *grad_faces,
+                        float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- flow-guided warp + masked photometric L1 ---------------------------------------------
  * ONE direction of pair_consist (imgflowarp.py:80-107) in one launch: warp(src, flow),
@@ -173,10 +178,11 @@ int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow
  *   faces F..2F-1 are the reversed windings, their cubes the permute(0,1,4,3,2,5) of the originals). */
 int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                     int fill_back, float *faces_out, float *textures_out, void *stream);
-/* Adjoint: grad_faces [B,F',3,3] / grad_textures [B,F',2,2,2,3] (either may be NULL together with its output)
- * -> grad_verts [B,V,3], grad_attrs [B,V,3] (zero-filled by the call, accumulated with atomics). */
+/* Adjoint: grad_faces [B,F',3,3] / grad_textures (either may be NULL together with its output)
+ * -> grad_verts [B,V,3], grad_attrs [B,V,3] (zero-filled by the call, accumulated with atomics).
+ * tex_grad_mode as in hoc_raster_backward: CUBE = grad_textures [B,F',2,2,2,3], VERTEX = [B,F',3,3]. */
 int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B, int V,
-                     int F, int fill_back, float *grad_verts, float *grad_attrs, void *stream);
+                     int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs, void *stream);
 /* hoc_flow_finalize: everything get_opticalflow does after its two renders (opticalflow.py:109-154): alpha
  * threshold, ignore-face mask, flow = rgb * mask, forward-backward occlusion check, mask products, channel
  * slice, crop.  rgb [B,3,S,S] / alpha [B,S,S] in HOC_LAYOUT_IMAGE, idx [B,S,S] raster order;
