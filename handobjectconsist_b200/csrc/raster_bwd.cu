@@ -124,6 +124,7 @@ __device__ __forceinline__ float hoc_delta(const HocBwdMaps &M, int xi, int yi, 
 template <bool TS2>
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
+                            const float *__restrict__ weight_map, const float *__restrict__ depth_map,
                             const float *__restrict__ g_rgb, const float *__restrict__ g_alpha,
                             const float *__restrict__ g_depth, int F, int S, int ts, float near_, float far_, float eps,
                             int layout, int want_ext, int tex_mode, int *__restrict__ ext, int *__restrict__ owned,
@@ -168,13 +169,26 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
         if (fi >= 0) {
             atomicAdd(owned + (long)b * F + fi, 1);
             if ((want_tex && nz) || want_depth) {
-                float f[9], inv[9], w[3], zp;
+                float f[9], w[3], zp;
                 const float *src = faces + ((long)b * F + fi) * 9;
+                if (weight_map != nullptr && depth_map != nullptr) {
+                    /* the forward saved its weights and depth: only the three vertex depths are needed */
+                    const float *wm = weight_map + (((long)b * S + yi) * S + xi) * 3;
+                    w[0] = wm[0];
+                    w[1] = wm[1];
+                    w[2] = wm[2];
+                    zp = depth_map[hoc_plane_off(layout, S, b, yi, xi)];
+                    f[2] = __ldg(src + 2);
+                    f[5] = __ldg(src + 5);
+                    f[8] = __ldg(src + 8);
+                } else { /* recompute with the forward's functions (bit-identical) */
+                    float inv[9];
 #pragma unroll
-                for (int k = 0; k < 9; k++)
-                    f[k] = __ldg(src + k);
-                hoc_face_inv(f, S, inv);
-                hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+                    for (int k = 0; k < 9; k++)
+                        f[k] = __ldg(src + k);
+                    hoc_face_inv(f, S, inv);
+                    hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+                }
                 if (want_depth) {
                     const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
                     if (gz != 0.0f) {
@@ -579,7 +593,8 @@ extern "C" size_t hoc_raster_backward_workspace_bytes(int B, int F, int S)
 }
 
 extern "C" int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
-                                   const float *rgb, const float *grad_rgb, const float *grad_alpha,
+                                   const float *rgb, const float *weight_map, const float *depth,
+                                   const float *grad_rgb, const float *grad_alpha,
                                    const float *grad_depth, int B, int F, int S, int ts, float near_, float far_,
                                    float eps, int layout, int use_alpha, int tex_grad_mode, float *grad_faces,
                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
@@ -631,13 +646,13 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         if (ts == 2)
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_pixel_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
-                           faces, face_index_map, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, eps, layout,
-                           k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
+                           faces, face_index_map, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_,
+                           eps, layout, k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
         else
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_pixel_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
-                           faces, face_index_map, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, eps, layout,
-                           k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
+                           faces, face_index_map, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_,
+                           eps, layout, k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_pixel_kernel");
     }
     if (grad_faces == nullptr)

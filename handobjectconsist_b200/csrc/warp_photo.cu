@@ -89,6 +89,7 @@ __device__ __forceinline__ float hoc_plane_sample(const float *__restrict__ plan
 {
     float acc = 0.0f;
     const float *p = plane + (long)T.y0 * W + T.x0;
+
     if (T.b_nw) acc = __fmaf_rn(__ldg(p), T.nw, acc);
     if (T.b_ne) acc = __fmaf_rn(__ldg(p + 1), T.ne, acc);
     if (T.b_sw) acc = __fmaf_rn(__ldg(p + W), T.sw, acc);
@@ -109,12 +110,15 @@ __device__ __forceinline__ float hoc_threshold_mask(float m, float thresh)
 #define WP_THREADS 256
 #define WP_MAXC 4
 
+template <int CT, int CJT> /* compile-time channel counts (0 = use the run-time values) */
 __global__ void __launch_bounds__(WP_THREADS)
 hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__restrict__ target,
-                              const float *__restrict__ flow, const float *__restrict__ jitter, int C, int Cj, int H,
-                              int W, float thresh, float *__restrict__ warped, float *__restrict__ warp_mask,
+                              const float *__restrict__ flow, const float *__restrict__ jitter, int C_rt, int Cj_rt,
+                              int H, int W, float thresh, float *__restrict__ warped, float *__restrict__ warp_mask,
                               uint8_t *__restrict__ valid_mask, float *__restrict__ diff, double *__restrict__ sums)
 {
+    const int C = CT > 0 ? CT : C_rt;
+    const int Cj = CJT > 0 ? CJT : Cj_rt;
     __shared__ float s_sum[WP_THREADS / 32];
     __shared__ float s_cnt[WP_THREADS / 32];
     const int b = blockIdx.y;
@@ -135,7 +139,10 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
         for (int c = 0; c < WP_MAXC; c++)
             wm[c] = m;
         if (jitter != nullptr) {
-            for (int c = 0; c < Cj && c < WP_MAXC; c++) {
+#pragma unroll
+            for (int c = 0; c < WP_MAXC; c++) {
+                if (c >= Cj)
+                    break;
                 const float wj = __fmul_rn(hoc_plane_sample(jitter + ((long)b * Cj + c) * npix, W, T), m);
                 wm[c] = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
             }
@@ -150,6 +157,7 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
         }
         if (valid_mask != nullptr)
             valid_mask[(long)b * npix + pix] = valid ? 1 : 0;
+#pragma unroll 4
         for (int c = 0; c < C; c++) {
             const long o = ((long)b * C + c) * npix + pix;
             const float v = __fmul_rn(hoc_plane_sample(src + ((long)b * C + c) * npix, W, T), m);
@@ -426,9 +434,14 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
     }
     const long npix = (long)H * W;
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
-    HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
-               (hoc_warp_photo_forward_kernel<<<grid, WP_THREADS, 0, st>>>(src, target, flow, jitter, C, Cj, H, W, thresh,
-                                                                           warped, warp_mask, valid_mask, diff, sums)));
+    if (C == 3 && (jitter == nullptr || Cj == 3)) /* the reference's case: RGB images, 3-channel jitter masks */
+        HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
+                   (hoc_warp_photo_forward_kernel<3, 3><<<grid, WP_THREADS, 0, st>>>(
+                       src, target, flow, jitter, C, Cj, H, W, thresh, warped, warp_mask, valid_mask, diff, sums)));
+    else
+        HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
+                   (hoc_warp_photo_forward_kernel<0, 0><<<grid, WP_THREADS, 0, st>>>(
+                       src, target, flow, jitter, C, Cj, H, W, thresh, warped, warp_mask, valid_mask, diff, sums)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_forward_kernel");
     return HOC_OK;
 }

@@ -101,7 +101,9 @@ def _forward_impl(ctx, faces, textures, image_size, near, far, eps, background_c
     ctx.return_rgb, ctx.return_alpha, ctx.return_depth = return_rgb, return_alpha, return_depth
     ctx.layout, ctx.texture_size = layout, ts
     ctx.batch_size, ctx.num_faces = B, Fn
-    ctx.save_for_backward(faces_c, tex_c if return_rgb else None, face_index_map, rgb)
+    ctx.save_for_backward(faces_c, tex_c if return_rgb else None, face_index_map, rgb,
+                          weight_map if (want_weight and return_depth) else None,
+                          depth if (want_weight and return_depth) else None)
     ctx.mark_non_differentiable(face_index_map)
     ctx.set_materialize_grads(False)
 
@@ -112,7 +114,7 @@ def _forward_impl(ctx, faces, textures, image_size, near, far, eps, background_c
 
 
 def _backward_impl(ctx, grad_rgb, grad_alpha, grad_depth):
-    faces, textures, face_index_map, rgb = ctx.saved_tensors
+    faces, textures, face_index_map, rgb, weight_map, depth = ctx.saved_tensors
     L = _lib.lib()
     B, Fn, S = ctx.batch_size, ctx.num_faces, ctx.image_size
     dev = faces.device
@@ -135,8 +137,8 @@ def _backward_impl(ctx, grad_rgb, grad_alpha, grad_depth):
         ws_bytes = L.hoc_raster_backward_workspace_bytes(B, Fn, S)
         ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
         code = L.hoc_raster_backward(
-            _lib.ptr(faces), _lib.ptr(textures), _lib.ptr(face_index_map), _lib.ptr(rgb), _lib.ptr(g_rgb),
-            _lib.ptr(g_alpha), _lib.ptr(g_depth), B, Fn, S, ctx.texture_size, ctx.near, ctx.far, ctx.eps, ctx.layout,
+            _lib.ptr(faces), _lib.ptr(textures), _lib.ptr(face_index_map), _lib.ptr(rgb), _lib.ptr(weight_map),
+            _lib.ptr(depth), _lib.ptr(g_rgb), _lib.ptr(g_alpha), _lib.ptr(g_depth), B, Fn, S, ctx.texture_size, ctx.near, ctx.far, ctx.eps, ctx.layout,
             int(ctx.return_alpha), _lib.HOC_TEX_GRAD_CUBE, _lib.ptr(grad_faces), _lib.ptr(grad_textures), _lib.ptr(ws),
             ws_bytes,
             _lib.stream_ptr())

@@ -55,13 +55,14 @@ class _MeshRasterFunction(Function):
             alpha = torch.empty((B, S, S), dtype=torch.float32, device=dev)
             depth = torch.empty((B, S, S), dtype=torch.float32, device=dev)
             idx = torch.empty((B, S, S), dtype=torch.int32, device=dev)
+            wmap = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)  # saved for the backward
             ws_bytes = L.hoc_raster_forward_workspace_bytes(B, Fo, S)
             ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
             _lib.check(L.hoc_raster_forward(_lib.ptr(faces), _lib.ptr(tex), B, Fo, S, 2, float(near), float(far),
                                             float(eps), bg, None, _lib.HOC_LAYOUT_IMAGE, _lib.ptr(rgb),
-                                            _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx), None, None, _lib.ptr(ws),
-                                            ws_bytes, st), "hoc_raster_forward")
-        ctx.save_for_backward(faces, fi, idx, rgb)
+                                            _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx), _lib.ptr(wmap), None,
+                                            _lib.ptr(ws), ws_bytes, st), "hoc_raster_forward")
+        ctx.save_for_backward(faces, fi, idx, rgb, wmap, depth)
         ctx.cfg = (B, V, Fn, Fo, S, float(near), float(far), float(eps), bool(fill_back))
         ctx.mark_non_differentiable(idx)
         ctx.set_materialize_grads(False)
@@ -69,7 +70,7 @@ class _MeshRasterFunction(Function):
 
     @staticmethod
     def backward(ctx, g_rgb, g_alpha, g_depth, g_idx):
-        faces, fi, idx, rgb = ctx.saved_tensors
+        faces, fi, idx, rgb, wmap, depth = ctx.saved_tensors
         B, V, Fn, Fo, S, near, far, eps, fill_back = ctx.cfg
         need_v, need_a = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_v or need_a) or (g_rgb is None and g_alpha is None and g_depth is None):
@@ -85,7 +86,8 @@ class _MeshRasterFunction(Function):
             grad_tex = torch.empty((B, Fo, 3, 3), dtype=torch.float32, device=dev) if need_a else None
             ws_bytes = L.hoc_raster_backward_workspace_bytes(B, Fo, S)
             ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
-            _lib.check(L.hoc_raster_backward(_lib.ptr(faces), None, _lib.ptr(idx), _lib.ptr(rgb), _lib.ptr(g_rgb),
+            _lib.check(L.hoc_raster_backward(_lib.ptr(faces), None, _lib.ptr(idx), _lib.ptr(rgb), _lib.ptr(wmap),
+                                             _lib.ptr(depth), _lib.ptr(g_rgb),
                                              _lib.ptr(g_alpha), _lib.ptr(g_depth), B, Fo, S, 2, near, far, eps,
                                              _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_faces),
                                              _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st), "hoc_raster_backward")

@@ -108,6 +108,8 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
  * backward_textures / backward_depth_map: results are reproducible to rounding, not bit for bit.
  *   faces, textures, face_index_map   forward inputs / output
  *   rgb              forward output in `layout` (NULL when the forward had no rgb)
+ *   weight_map, depth  forward outputs ([B,S,S,3] raster order / [B,S,S] in `layout`) or NULL: when both are
+ *                    given the pixel pass reads them instead of recomputing weights and depth from the faces
  *   grad_rgb / grad_alpha / grad_depth  incoming gradients in `layout`; NULL = all zeros / that
  *                    output was not requested in the forward
  *   use_alpha        1 when the forward produced alpha (return_alpha), else 0
@@ -123,7 +125,8 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
 #define HOC_TEX_GRAD_VERTEX 1
 size_t hoc_raster_backward_workspace_bytes(int B, int F, int S);
 int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
-                        const float *rgb, const float *grad_rgb, const float *grad_alpha,
+                        const float *rgb, const float *weight_map, const float *depth, const float *grad_rgb,
+                        const float *grad_alpha,
                         const float *grad_depth, int B, int F, int S, int ts, float near_, float far_,
                         float eps, int layout, int use_alpha, int tex_grad_mode, float *grad_faces,
                         float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
