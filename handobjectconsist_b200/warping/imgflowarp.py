@@ -12,6 +12,16 @@ from torch.autograd import Function
 from .. import _lib
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def get_spatial_meshgrid(x: torch.Tensor, scale=False):
     """Grid of pixel coordinates [B,2,H,W] (imgflowarp.py:8-28), built on the device of ``x``."""
     batch_size, _, height, width = x.size()
@@ -167,12 +177,21 @@ def pair_consist(recons_flow, image_ref: torch.Tensor, image: torch.Tensor, jitt
     """
     image_ref, image = image_ref.cuda(), image.cuda()
     jitter_mask_ref, jitter_mask = jitter_mask_ref.cuda(), jitter_mask.cuda()
+    # the two directions are independent: the second runs on a side stream (its kernels overlap the first's)
+    dev = image.device
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        # direction 2: warp(image, flow12) against image_ref; jitter_mask_ref warped with flow12
+        dir2 = _one_direction(recons_flow[0], image, image_ref, jitter_mask_ref, criterion)
+        for t in dir2:
+            t.record_stream(main)
     # direction 1: warp(image_ref, flow21) against image; jitter_mask warped with flow21 (imgflowarp.py:80-95)
     losses_fwd, warp1, warp_mask1, valid_mask1, flow_mask1, diffs_fwd = _one_direction(
         recons_flow[1], image_ref, image, jitter_mask, criterion)
-    # direction 2: warp(image, flow12) against image_ref; jitter_mask_ref warped with flow12
-    losses_bwd, warp2, warp_mask2, valid_mask2, flow_mask2, diffs_bwd = _one_direction(
-        recons_flow[0], image, image_ref, jitter_mask_ref, criterion)
+    main.wait_stream(side)
+    losses_bwd, warp2, warp_mask2, valid_mask2, flow_mask2, diffs_bwd = dir2
     masks = [
         {"warp_mask": warp_mask1, "full_mask": valid_mask1, "flow_mask": flow_mask1},
         {"warp_mask": warp_mask2, "full_mask": valid_mask2, "flow_mask": flow_mask2},

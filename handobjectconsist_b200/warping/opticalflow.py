@@ -18,6 +18,14 @@ from ..meshutils import batch_proj2d, batch_vertex_textures
 from . import imgflowarp
 
 _IGNORE_CACHE = {}
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
 
 
 def _ignore_tensor(ignore_face_idxs, device):
@@ -217,13 +225,24 @@ def _get_opticalflow_fused(verts_cam, faces, camintrs, neurenderer, orig_img_siz
                                                              t, dist, neurenderer.orig_size)
     if detach_textures:
         attrs12 = attrs12.detach()  # the reference detaches only the first set (opticalflow.py:104-105)
-    renders = []
-    for ndc, attrs in ((ndc1, attrs12), (ndc2, attrs21)):
-        if detach_renders:
-            ndc = ndc.detach()
-        renders.append(_MeshRasterFunction.apply(ndc, attrs, faces, S, neurenderer.near, neurenderer.far,
-                                                 neurenderer.rasterizer_eps, neurenderer.background_color,
-                                                 neurenderer.fill_back))
+    # the two renders are independent: the second one runs on a side stream so that their (small, tail-heavy)
+    # kernels overlap; autograd replays the same stream assignment in the backward
+    main = torch.cuda.current_stream(dev)
+    side = _side_stream(dev)
+    renders = [None, None]
+    if detach_renders:
+        ndc1, ndc2 = ndc1.detach(), ndc2.detach()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        renders[1] = _MeshRasterFunction.apply(ndc2, attrs21, faces, S, neurenderer.near, neurenderer.far,
+                                               neurenderer.rasterizer_eps, neurenderer.background_color,
+                                               neurenderer.fill_back)
+        for t in renders[1]:
+            t.record_stream(main)
+    renders[0] = _MeshRasterFunction.apply(ndc1, attrs12, faces, S, neurenderer.near, neurenderer.far,
+                                           neurenderer.rasterizer_eps, neurenderer.background_color,
+                                           neurenderer.fill_back)
+    main.wait_stream(side)
     W, H = (S, S) if orig_img_size is None else (min(orig_img_size[0], S), min(orig_img_size[1], S))
     ignore = None if ignore_face_idxs is None else _ignore_tensor(ignore_face_idxs, verts_cam[0].device)
     (rgb1, alpha1, _, idx1), (rgb2, alpha2, _, idx2) = renders
