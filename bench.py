@@ -401,7 +401,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager-only", action="store_true", help="profiling aid: run only the eager arm (ncu)")
+    ap.add_argument("--pairs", type=int, default=PAIRS, help="frame pairs per rank and step (default: configs[2])")
+    ap.add_argument("--size", type=int, default=SIZE, help="raster / image side (default: configs[2])")
     args = ap.parse_args()
+    globals()["PAIRS"], globals()["SIZE"] = args.pairs, args.size
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -238,7 +238,7 @@ hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const 
     const long pix = (long)blockIdx.x * FP_THREADS + threadIdx.x;
     if (pix >= (long)H * W)
         return;
-    const int ry = (int)(pix / W), rx = (int)(pix - (long)ry * W);
+    const int ry = (int)((unsigned)pix / (unsigned)W), rx = (int)pix - ry * W;
     const HocRender &Ra = second ? R2 : R1;
     const HocRender &Rb = second ? R1 : R2;
 
@@ -307,7 +307,7 @@ hoc_flow_finalize_backward_kernel(const float *__restrict__ grad_flow, const flo
     const long npix = (long)S * S;
     if (pix >= npix)
         return;
-    const int y = (int)(pix / S), x = (int)(pix - (long)y * S);
+    const int y = (int)((unsigned)pix / (unsigned)S), x = (int)pix - y * S;
     float gx = 0.0f, gy = 0.0f;
     if (y < H && x < W) {
         const long o = ((long)b * H + y) * W + x;

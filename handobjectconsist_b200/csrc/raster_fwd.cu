@@ -211,8 +211,8 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
     }
 
     if (in_range) {
-        yi = (int)(pix / S);
-        xi = (int)(pix - (long)yi * S);
+        yi = (int)((unsigned)pix / (unsigned)S);
+        xi = (int)pix - yi * S;
         const unsigned long long key = zbuf[(long)b * npix + pix];
         fidx = (int)(unsigned)(key & 0xffffffffull);
         if (fidx >= 0) {

@@ -251,17 +251,25 @@ HOC_HD void hoc_k4_col(const HocK4Edge *E, int S, int d0, float d1_cross, HocK4C
     C->cB = C->hasB ? (E->b0 - E->a0) / (fd0 - E->a0) : 0.0f;
 }
 
+/* delta / dist: on the device the approximate (2 ulp) divide -- the pseudo-gradient carries a 1e-3 tolerance and
+ * this quotient is evaluated once per scanned pixel per vertex, which makes the IEEE divide the hot instruction. */
+#ifdef __CUDA_ARCH__
+#define HOC_FAST_DIV(a, b) __fdividef((a), (b))
+#else
+#define HOC_FAST_DIV(a, b) ((a) / (b))
+#endif
+
 HOC_HD void hoc_k4_accum_col(const HocK4Col *C, int d1, float eps, float delta, float *gA, float *gB)
 {
     const float t = ((float)d1 - C->cross) * C->scale;
     if (C->hasA) {
         float dist = C->cA * t;
         dist = (0 < dist) ? dist + eps : dist - eps;
-        *gA -= delta / dist;
+        *gA -= HOC_FAST_DIV(delta, dist);
     }
     if (C->hasB) {
         float dist = C->cB * t;
         dist = (0 < dist) ? dist + eps : dist - eps;
-        *gB -= delta / dist;
+        *gB -= HOC_FAST_DIV(delta, dist);
     }
 }

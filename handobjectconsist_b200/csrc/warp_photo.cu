@@ -126,8 +126,8 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
     const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
     float my_sum = 0.0f, my_cnt = 0.0f;
     if (pix < npix) {
-        const int y = (int)(pix / W);
-        const int x = (int)(pix - (long)y * W);
+        const int y = (int)((unsigned)pix / (unsigned)W);
+        const int x = (int)pix - y * W;
         const float2 fl = *reinterpret_cast<const float2 *>(flow + ((long)b * npix + pix) * 2);
         HocTaps T;
         hoc_bilinear_taps(x, y, fl.x, fl.y, H, W, T);
@@ -209,8 +209,8 @@ hoc_warp_photo_backward_kernel(const float *__restrict__ src, const float *__res
         return;
     float2 g = make_float2(0.0f, 0.0f);
     if (valid_mask[(long)b * npix + pix]) {
-        const int y = (int)(pix / W);
-        const int x = (int)(pix - (long)y * W);
+        const int y = (int)((unsigned)pix / (unsigned)W);
+        const int x = (int)pix - y * W;
         const float2 fl = *reinterpret_cast<const float2 *>(flow + ((long)b * npix + pix) * 2);
         HocTaps T;
         hoc_bilinear_taps(x, y, fl.x, fl.y, H, W, T);
@@ -264,8 +264,8 @@ hoc_warp_kernel(const float *__restrict__ x, const float *__restrict__ flow, int
     const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
     if (pix >= npix)
         return;
-    const int py = (int)(pix / W);
-    const int px = (int)(pix - (long)py * W);
+    const int py = (int)((unsigned)pix / (unsigned)W);
+    const int px = (int)pix - py * W;
     const float fx = flow[((long)b * 2 + 0) * npix + pix];
     const float fy = flow[((long)b * 2 + 1) * npix + pix];
     if (mode == 0) {
@@ -308,8 +308,8 @@ hoc_warp_backward_kernel(const float *__restrict__ x, const float *__restrict__ 
     const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
     if (pix >= npix)
         return;
-    const int py = (int)(pix / W);
-    const int px = (int)(pix - (long)py * W);
+    const int py = (int)((unsigned)pix / (unsigned)W);
+    const int px = (int)pix - py * W;
     HocTaps T;
     hoc_bilinear_taps(px, py, flow[((long)b * 2 + 0) * npix + pix], flow[((long)b * 2 + 1) * npix + pix], H, W, T);
     const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
@@ -380,8 +380,8 @@ hoc_occlusion_kernel(const float *__restrict__ mask1, const float *__restrict__ 
     const float *fb = (second ? flow12 : flow21) + (long)b * Cf * npix;
     float *out = (second ? occl2 : occl1) + (long)b * npix;
 
-    const int ry = (int)(pix / W);
-    const int rx = (int)(pix - (long)ry * W);
+    const int ry = (int)((unsigned)pix / (unsigned)W);
+    const int rx = (int)pix - ry * W;
     const float inv_w = __fdiv_rn(1.0f, (float)W), inv_h = __fdiv_rn(1.0f, (float)H);
     const float m_r = ma[pix];
     /* second warp (evaluated at r): source s in the once-warped grid */
@@ -417,8 +417,8 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
                                       int B, int C, int Cj, int H, int W, float thresh, float *warped,
                                       float *warp_mask, uint8_t *valid_mask, float *diff, double *sums, void *stream)
 {
-    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp_photo_forward: bad shape B=%d C=%d H=%d W=%d", B, C,
-                  H, W);
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (long)H * W < (1l << 31),
+                  "hoc_warp_photo_forward: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
     HOC_CHECK_ARG(B <= 65535, "hoc_warp_photo_forward: batch %d exceeds 65535", B);
     HOC_CHECK_ARG(jitter == nullptr || Cj == 1 || Cj == C, "hoc_warp_photo_forward: jitter channels %d vs %d", Cj, C);
     HOC_CHECK_ARG(warp_mask == nullptr || C <= WP_MAXC, "hoc_warp_photo_forward: warp_mask supports C <= %d", WP_MAXC);
@@ -450,7 +450,7 @@ extern "C" int hoc_warp_photo_backward(const float *src, const float *target, co
                                        const uint8_t *valid_mask, const double *sums, const float *grad_loss, int B,
                                        int C, int H, int W, float thresh, float *grad_flow, void *stream)
 {
-    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp_photo_backward: bad shape B=%d C=%d H=%d W=%d", B,
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (long)H * W < (1l << 31), "hoc_warp_photo_backward: bad shape B=%d C=%d H=%d W=%d", B,
                   C, H, W);
     HOC_CHECK_ARG(B <= 65535, "hoc_warp_photo_backward: batch %d exceeds 65535", B);
     if (B == 0)
@@ -469,7 +469,7 @@ extern "C" int hoc_warp_photo_backward(const float *src, const float *target, co
 extern "C" int hoc_warp(const float *x, const float *flow_nchw, int B, int C, int H, int W, float thresh, int mode,
                         float *out, float *mask, void *stream)
 {
-    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (long)H * W < (1l << 31), "hoc_warp: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
     HOC_CHECK_ARG(mode == 0 || mode == 1, "hoc_warp: mode %d (0 bilinear, 1 nearest)", mode);
     HOC_CHECK_ARG(B <= 65535, "hoc_warp: batch %d exceeds 65535", B);
     if (B == 0)
@@ -487,7 +487,7 @@ extern "C" int hoc_warp(const float *x, const float *flow_nchw, int B, int C, in
 extern "C" int hoc_warp_backward(const float *x, const float *flow_nchw, const float *grad_out, int B, int C, int H,
                                  int W, float thresh, float *grad_flow_nchw, void *stream)
 {
-    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1, "hoc_warp_backward: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+    HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (long)H * W < (1l << 31), "hoc_warp_backward: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
     HOC_CHECK_ARG(B <= 65535, "hoc_warp_backward: batch %d exceeds 65535", B);
     if (B == 0)
         return HOC_OK;
@@ -505,7 +505,7 @@ extern "C" int hoc_occlusion_mask(const float *mask1, const float *mask2, const 
                                   int B, int Cf, int H, int W, float distance_thresh, float *occl1, float *occl2,
                                   void *stream)
 {
-    HOC_CHECK_ARG(B >= 0 && Cf >= 2 && H >= 1 && W >= 1, "hoc_occlusion_mask: bad shape B=%d Cf=%d H=%d W=%d", B, Cf,
+    HOC_CHECK_ARG(B >= 0 && Cf >= 2 && H >= 1 && W >= 1 && (long)H * W < (1l << 31), "hoc_occlusion_mask: bad shape B=%d Cf=%d H=%d W=%d", B, Cf,
                   H, W);
     HOC_CHECK_ARG(B <= 65535, "hoc_occlusion_mask: batch %d exceeds 65535", B);
     if (B == 0)
