@@ -22,9 +22,18 @@
 #ifndef REAL
 #error "define REAL and FN(name) before including"
 #endif
+/* The per-pixel / per-face bodies are plain functions (FN(fwd_pixel), FN(tex_pixel), FN(k4_face), FN(bt_pixel),
+ * FN(bd_pixel)) -- one call = what ONE thread of the reference's kernels does -- driven here by host loops / a
+ * pthread pool.  ORA_HD / ORA_ATOMIC_ADD / ORA_NO_HOST_DRIVERS let another driver reuse the same bodies. */
+#ifndef ORA_HD
+#define ORA_HD static inline
+#endif
+#ifndef ORA_ATOMIC_ADD
+#define ORA_ATOMIC_ADD(ptr, val) (*(ptr) += (val))
+#endif
 
 /* K1: barycentric coefficient matrix of one face in pixel-index space (Appendix C1). */
-static int FN(face_inv)(const REAL *face, int is, REAL *face_inv)
+ORA_HD int FN(face_inv)(const REAL *face, int is, REAL *face_inv)
 {
     /* back-face rule, NDC y-up (Appendix A) */
     if ((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0]))
@@ -56,13 +65,12 @@ struct FN(fwd_ctx) {
     int return_depth;
 };
 
-static void FN(fwd_range)(void *vc, long begin, long end)
+ORA_HD void FN(fwd_pixel)(const struct FN(fwd_ctx) *c, long i)
 {
-    struct FN(fwd_ctx) *c = (struct FN(fwd_ctx) *)vc;
     const REAL *faces = c->faces, *faces_inv = c->faces_inv;
     const int is = c->is, nf = c->nf;
     const REAL near = c->near, far = c->far;
-    for (long i = begin; i < end; i++) {
+    {
         const int bn = (int)(i / (is * is));
         const int pn = (int)(i % (is * is));
         const int yi = pn / is;
@@ -117,6 +125,13 @@ static void FN(fwd_range)(void *vc, long begin, long end)
     }
 }
 
+#ifndef ORA_NO_HOST_DRIVERS
+static void FN(fwd_range)(void *vc, long begin, long end)
+{
+    for (long i = begin; i < end; i++)
+        FN(fwd_pixel)((const struct FN(fwd_ctx) *)vc, i);
+}
+
 void FN(forward_face_index_map)(const REAL *faces, int32_t *face_index_map, REAL *weight_map, REAL *depth_map,
                                 REAL *face_inv_map, REAL *faces_inv, int batch_size, int num_faces, int image_size,
                                 REAL near, REAL far, int return_depth)
@@ -129,18 +144,18 @@ void FN(forward_face_index_map)(const REAL *faces, int32_t *face_index_map, REAL
                             return_depth};
     ora_parallel_for((long)batch_size * is * is, FN(fwd_range), &c);
 }
+#endif
 
-/* K3: trilinear sampling of the per-face texture cube, rasterize.py:218-243 (Appendix C3). */
-void FN(forward_texture_sampling)(const REAL *faces, const REAL *textures, const int32_t *face_index_map,
-                                  const REAL *weight_map, const REAL *depth_map, REAL *rgb_map,
-                                  int32_t *sampling_index_map, REAL *sampling_weight_map, int batch_size,
-                                  int num_faces, int image_size, int texture_size, REAL eps)
+/* K3: trilinear sampling of the per-face texture cube, rasterize.py:218-243 (Appendix C3); one pixel. */
+ORA_HD void FN(tex_pixel)(const REAL *faces, const REAL *textures, const int32_t *face_index_map,
+                          const REAL *weight_map, const REAL *depth_map, REAL *rgb_map, int32_t *sampling_index_map,
+                          REAL *sampling_weight_map, int num_faces, int image_size, int texture_size, REAL eps, long i)
 {
     const int is = image_size, nf = num_faces, ts = texture_size;
-    for (long i = 0; i < (long)batch_size * is * is; i++) {
+    {
         const int face_index = face_index_map[i];
         if (face_index < 0)
-            continue;
+            return;
         const int bn = (int)(i / (is * is));
         const REAL *face = &faces[((long)bn * nf + face_index) * 9];
         const REAL *texture = &textures[((long)bn * nf + face_index) * ts * ts * ts * 3];
@@ -179,6 +194,18 @@ void FN(forward_texture_sampling)(const REAL *faces, const REAL *textures, const
     }
 }
 
+#ifndef ORA_NO_HOST_DRIVERS
+void FN(forward_texture_sampling)(const REAL *faces, const REAL *textures, const int32_t *face_index_map,
+                                  const REAL *weight_map, const REAL *depth_map, REAL *rgb_map,
+                                  int32_t *sampling_index_map, REAL *sampling_weight_map, int batch_size,
+                                  int num_faces, int image_size, int texture_size, REAL eps)
+{
+    for (long i = 0; i < (long)batch_size * image_size * image_size; i++)
+        FN(tex_pixel)(faces, textures, face_index_map, weight_map, depth_map, rgb_map, sampling_index_map,
+                      sampling_weight_map, num_faces, image_size, texture_size, eps, i);
+}
+#endif
+
 /* K4: NMR pseudo-gradient of rgb/alpha w.r.t. the xy of the face vertices, rasterize.py:263-281
  * (Appendix C4).  One serial scan per face; grad_faces[b,f] is OVERWRITTEN for front faces. */
 struct FN(k4_ctx) {
@@ -191,9 +218,8 @@ struct FN(k4_ctx) {
     int return_rgb, return_alpha;
 };
 
-static void FN(k4_range)(void *vc, long begin, long end)
+ORA_HD void FN(k4_face)(const struct FN(k4_ctx) *c, long i)
 {
-    struct FN(k4_ctx) *c = (struct FN(k4_ctx) *)vc;
     const REAL *faces = c->faces;
     const int32_t *face_index_map = c->face_index_map;
     const REAL *rgb_map = c->rgb_map, *alpha_map = c->alpha_map;
@@ -202,13 +228,13 @@ static void FN(k4_range)(void *vc, long begin, long end)
     const int num_faces = c->num_faces, is = c->image_size;
     const REAL eps = c->eps;
     const int return_rgb = c->return_rgb, return_alpha = c->return_alpha;
-    for (long i = begin; i < end; i++) {
+    {
         const int bn = (int)(i / num_faces);
         const int fn = (int)(i % num_faces);
         const REAL *face = &faces[i * 9];
         REAL grad_face[9] = {0};
         if ((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0]))
-            continue;
+            return;
         for (int edge_num = 0; edge_num < 3; edge_num++) {
             int pi[3];
             REAL pp[3][2];
@@ -335,6 +361,13 @@ static void FN(k4_range)(void *vc, long begin, long end)
     }
 }
 
+#ifndef ORA_NO_HOST_DRIVERS
+static void FN(k4_range)(void *vc, long begin, long end)
+{
+    for (long i = begin; i < end; i++)
+        FN(k4_face)((const struct FN(k4_ctx) *)vc, i);
+}
+
 void FN(backward_pixel_map)(const REAL *faces, const int32_t *face_index_map, const REAL *rgb_map,
                             const REAL *alpha_map, const REAL *grad_rgb_map, const REAL *grad_alpha_map,
                             REAL *grad_faces, int batch_size, int num_faces, int image_size, REAL eps,
@@ -345,57 +378,76 @@ void FN(backward_pixel_map)(const REAL *faces, const int32_t *face_index_map, co
     ora_parallel_for((long)batch_size * num_faces, FN(k4_range), &c);
 }
 
-/* K5: exact gradient w.r.t. the texture cubes, rasterize.py:284-297 (Appendix C5).  Accumulates
- * into grad_textures (caller zero-fills, rasterize.py:151).  Serial => deterministic. */
+#endif
+
+/* K5: exact gradient w.r.t. the texture cubes, rasterize.py:284-297 (Appendix C5); one pixel.  Accumulates
+ * into grad_textures (caller zero-fills, rasterize.py:151). */
+ORA_HD void FN(bt_pixel)(const int32_t *face_index_map, const REAL *sampling_weight_map,
+                         const int32_t *sampling_index_map, const REAL *grad_rgb_map, REAL *grad_textures,
+                         int num_faces, int image_size, int texture_size, long i)
+{
+    const int is = image_size, nf = num_faces, ts = texture_size;
+    const int face_index = face_index_map[i];
+    if (face_index < 0)
+        return;
+    const int bn = (int)(i / (is * is));
+    REAL *grad_texture = &grad_textures[((long)bn * nf + face_index) * ts * ts * ts * 3];
+    for (int pn = 0; pn < 8; pn++) {
+        const REAL w = sampling_weight_map[i * 8 + pn];
+        const int isc = sampling_index_map[i * 8 + pn];
+        for (int k = 0; k < 3; k++)
+            ORA_ATOMIC_ADD(&grad_texture[isc * 3 + k], w * grad_rgb_map[i * 3 + k]);
+    }
+}
+
+/* K6: analytic gradient of the interpolated depth, rasterize.py:300-315 (Appendix C6); one pixel.
+ * Accumulates into grad_faces AFTER K4 stored into it. */
+ORA_HD void FN(bd_pixel)(const REAL *faces, const REAL *depth_map, const int32_t *face_index_map,
+                         const REAL *face_inv_map, const REAL *weight_map, const REAL *grad_depth_map,
+                         REAL *grad_faces, int num_faces, int image_size, long i)
+{
+    const int is = image_size, nf = num_faces;
+    const int fn = face_index_map[i];
+    if (fn < 0)
+        return;
+    const int bn = (int)(i / (is * is));
+    const REAL *face = &faces[((long)bn * nf + fn) * 9];
+    const REAL depth = depth_map[i];
+    const REAL depth2 = depth * depth;
+    const REAL *face_inv = &face_inv_map[i * 9];
+    const REAL *weight = &weight_map[i * 3];
+    const REAL grad_depth = grad_depth_map[i];
+    REAL *grad_face = &grad_faces[((long)bn * nf + fn) * 9];
+    for (int k = 0; k < 3; k++) {
+        const REAL z_k = face[3 * k + 2];
+        ORA_ATOMIC_ADD(&grad_face[3 * k + 2], grad_depth * weight[k] * depth2 / (z_k * z_k));
+    }
+    REAL tmp[3] = {0, 0, 0};
+    for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++)
+            tmp[k] += -face_inv[3 * l + k] / face[3 * l + 2];
+    for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 2; l++)
+            ORA_ATOMIC_ADD(&grad_face[3 * k + l], -grad_depth * depth2 * weight[k] * tmp[l] * is / 2);
+}
+
+#ifndef ORA_NO_HOST_DRIVERS
+/* serial => deterministic */
 void FN(backward_textures)(const int32_t *face_index_map, const REAL *sampling_weight_map,
                            const int32_t *sampling_index_map, const REAL *grad_rgb_map, REAL *grad_textures,
                            int batch_size, int num_faces, int image_size, int texture_size)
 {
-    const int is = image_size, nf = num_faces, ts = texture_size;
-    for (long i = 0; i < (long)batch_size * is * is; i++) {
-        const int face_index = face_index_map[i];
-        if (face_index < 0)
-            continue;
-        const int bn = (int)(i / (is * is));
-        REAL *grad_texture = &grad_textures[((long)bn * nf + face_index) * ts * ts * ts * 3];
-        for (int pn = 0; pn < 8; pn++) {
-            const REAL w = sampling_weight_map[i * 8 + pn];
-            const int isc = sampling_index_map[i * 8 + pn];
-            for (int k = 0; k < 3; k++)
-                grad_texture[isc * 3 + k] += w * grad_rgb_map[i * 3 + k];
-        }
-    }
+    for (long i = 0; i < (long)batch_size * image_size * image_size; i++)
+        FN(bt_pixel)(face_index_map, sampling_weight_map, sampling_index_map, grad_rgb_map, grad_textures, num_faces,
+                     image_size, texture_size, i);
 }
 
-/* K6: analytic gradient of the interpolated depth, rasterize.py:300-315 (Appendix C6).
- * Accumulates into grad_faces AFTER K4 stored into it. */
 void FN(backward_depth_map)(const REAL *faces, const REAL *depth_map, const int32_t *face_index_map,
                             const REAL *face_inv_map, const REAL *weight_map, const REAL *grad_depth_map,
                             REAL *grad_faces, int batch_size, int num_faces, int image_size)
 {
-    const int is = image_size, nf = num_faces;
-    for (long i = 0; i < (long)batch_size * is * is; i++) {
-        const int fn = face_index_map[i];
-        if (fn < 0)
-            continue;
-        const int bn = (int)(i / (is * is));
-        const REAL *face = &faces[((long)bn * nf + fn) * 9];
-        const REAL depth = depth_map[i];
-        const REAL depth2 = depth * depth;
-        const REAL *face_inv = &face_inv_map[i * 9];
-        const REAL *weight = &weight_map[i * 3];
-        const REAL grad_depth = grad_depth_map[i];
-        REAL *grad_face = &grad_faces[((long)bn * nf + fn) * 9];
-        for (int k = 0; k < 3; k++) {
-            const REAL z_k = face[3 * k + 2];
-            grad_face[3 * k + 2] += grad_depth * weight[k] * depth2 / (z_k * z_k);
-        }
-        REAL tmp[3] = {0, 0, 0};
-        for (int k = 0; k < 3; k++)
-            for (int l = 0; l < 3; l++)
-                tmp[k] += -face_inv[3 * l + k] / face[3 * l + 2];
-        for (int k = 0; k < 3; k++)
-            for (int l = 0; l < 2; l++)
-                grad_face[3 * k + l] += -grad_depth * depth2 * weight[k] * tmp[l] * is / 2;
-    }
+    for (long i = 0; i < (long)batch_size * image_size * image_size; i++)
+        FN(bd_pixel)(faces, depth_map, face_index_map, face_inv_map, weight_map, grad_depth_map, grad_faces, num_faces,
+                     image_size, i);
 }
+#endif
