@@ -32,11 +32,19 @@ struct HocTaps {
     bool b_nw, b_ne, b_sw, b_se; /* tap inside the image */
 };
 
-__device__ __forceinline__ float hoc_norm_coord(int p, float flow, int size)
+/* 1 / max(size - 1, 1) as torch's div-by-scalar kernel computes it (IEEE float divide); evaluated once per
+ * thread by the kernels below and passed down, not once per coordinate */
+__device__ __forceinline__ float hoc_inv_extent(int size) { return __fdiv_rn(1.0f, (float)max(size - 1, 1)); }
+
+__device__ __forceinline__ float hoc_norm_coord_inv(int p, float flow, float inv)
 {
-    const float inv = __fdiv_rn(1.0f, (float)max(size - 1, 1));
     const float v = __fadd_rn((float)p, flow);
     return __fadd_rn(__fmul_rn(__fmul_rn(2.0f, v), inv), -1.0f);
+}
+
+__device__ __forceinline__ float hoc_norm_coord(int p, float flow, int size)
+{
+    return hoc_norm_coord_inv(p, flow, hoc_inv_extent(size));
 }
 
 __device__ __forceinline__ float hoc_unnormalize(float coord, int size)
@@ -45,10 +53,19 @@ __device__ __forceinline__ float hoc_unnormalize(float coord, int size)
     return __fmul_rn(__fmaf_rn(__fadd_rn(coord, 1.0f), (float)size, -1.0f), 0.5f);
 }
 
+__device__ __forceinline__ void hoc_bilinear_taps_inv(int x, int y, float fx, float fy, int H, int W, float inv_w,
+                                                      float inv_h, HocTaps &T);
+
 __device__ __forceinline__ void hoc_bilinear_taps(int x, int y, float fx, float fy, int H, int W, HocTaps &T)
 {
-    const float ix = hoc_unnormalize(hoc_norm_coord(x, fx, W), W);
-    const float iy = hoc_unnormalize(hoc_norm_coord(y, fy, H), H);
+    hoc_bilinear_taps_inv(x, y, fx, fy, H, W, hoc_inv_extent(W), hoc_inv_extent(H), T);
+}
+
+__device__ __forceinline__ void hoc_bilinear_taps_inv(int x, int y, float fx, float fy, int H, int W, float inv_w,
+                                                      float inv_h, HocTaps &T)
+{
+    const float ix = hoc_unnormalize(hoc_norm_coord_inv(x, fx, inv_w), W);
+    const float iy = hoc_unnormalize(hoc_norm_coord_inv(y, fy, inv_h), H);
     T.ix = ix;
     T.iy = iy;
     /* clamp before the conversion only to keep it defined; far-away taps are out of bounds anyway */
@@ -97,6 +114,33 @@ __device__ __forceinline__ float hoc_plane_sample(const float *__restrict__ plan
     return acc;
 }
 
+/* Branch-free form of hoc_plane_sample for the streaming kernels: out-of-bounds taps are read from a clamped
+ * (valid) address and enter the same FMA chain with weight 0 -- fma(v, 0, acc) == acc for every finite v -- so
+ * that all loads of all planes can be issued before the first one is consumed. */
+struct HocTapsFlat {
+    int o[4];   /* offsets of nw, ne, sw, se inside a plane (clamped into the image) */
+    float w[4]; /* their weights, 0 for taps outside the image */
+};
+
+__device__ __forceinline__ void hoc_flatten_taps(const HocTaps &T, int H, int W, HocTapsFlat &F)
+{
+    const int x0 = min(max(T.x0, 0), W - 1), x1 = min(max(T.x0 + 1, 0), W - 1);
+    const int y0 = min(max(T.y0, 0), H - 1), y1 = min(max(T.y0 + 1, 0), H - 1);
+    F.o[0] = y0 * W + x0;
+    F.o[1] = y0 * W + x1;
+    F.o[2] = y1 * W + x0;
+    F.o[3] = y1 * W + x1;
+    F.w[0] = T.b_nw ? T.nw : 0.0f;
+    F.w[1] = T.b_ne ? T.ne : 0.0f;
+    F.w[2] = T.b_sw ? T.sw : 0.0f;
+    F.w[3] = T.b_se ? T.se : 0.0f;
+}
+
+__device__ __forceinline__ float hoc_flat_combine(const float *v, const HocTapsFlat &F)
+{
+    return __fmaf_rn(v[3], F.w[3], __fmaf_rn(v[2], F.w[2], __fmaf_rn(v[1], F.w[1], __fmaf_rn(v[0], F.w[0], 0.0f))));
+}
+
 /* mask[mask < thresh] = 0; mask[mask > 0] = 1 */
 __device__ __forceinline__ float hoc_threshold_mask(float m, float thresh)
 {
@@ -110,69 +154,120 @@ __device__ __forceinline__ float hoc_threshold_mask(float m, float thresh)
 #define WP_THREADS 256
 #define WP_MAXC 4
 
-template <int CT, int CJT> /* compile-time channel counts (0 = use the run-time values) */
+template <int CT, int CJT> /* compile-time channel counts (0 = use the run-time values, any count) */
 __global__ void __launch_bounds__(WP_THREADS)
 hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__restrict__ target,
                               const float *__restrict__ flow, const float *__restrict__ jitter, int C_rt, int Cj_rt,
-                              int H, int W, float thresh, float *__restrict__ warped, float *__restrict__ warp_mask,
-                              uint8_t *__restrict__ valid_mask, float *__restrict__ diff, double *__restrict__ sums)
+                              int H, int W, float inv_w, float inv_h, float thresh, float *__restrict__ warped,
+                              float *__restrict__ warp_mask, uint8_t *__restrict__ valid_mask,
+                              float *__restrict__ diff, double *__restrict__ sums)
 {
     const int C = CT > 0 ? CT : C_rt;
     const int Cj = CJT > 0 ? CJT : Cj_rt;
     __shared__ float s_sum[WP_THREADS / 32];
     __shared__ float s_cnt[WP_THREADS / 32];
     const int b = blockIdx.y;
-    const long npix = (long)H * W;
-    const long pix = (long)blockIdx.x * WP_THREADS + threadIdx.x;
+    const int npix = H * W;
+    const int pix = blockIdx.x * WP_THREADS + threadIdx.x;
     float my_sum = 0.0f, my_cnt = 0.0f;
     if (pix < npix) {
-        const int y = (int)((unsigned)pix / (unsigned)W);
-        const int x = (int)pix - y * W;
-        const float2 fl = *reinterpret_cast<const float2 *>(flow + ((long)b * npix + pix) * 2);
+        const int y = pix / W;
+        const int x = pix - y * W;
+        const float2 fl = *reinterpret_cast<const float2 *>(flow + ((size_t)b * npix + pix) * 2);
         HocTaps T;
-        hoc_bilinear_taps(x, y, fl.x, fl.y, H, W, T);
+        hoc_bilinear_taps_inv(x, y, fl.x, fl.y, H, W, inv_w, inv_h, T);
         const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
-        /* jitter mask: warped with the same flow, tested for == 1; plus == 1 at the pixel itself */
-        bool valid = false;
+        const float *sb = src + (size_t)b * C * npix;
+        const float *tb = target + (size_t)b * C * npix + pix;
+        const float *jb = (jitter != nullptr) ? jitter + (size_t)b * Cj * npix : nullptr;
+        bool valid;
         float wm[WP_MAXC];
+        if (CT > 0) {
+            /* fixed channel counts: every load of every plane is issued before the first use */
+            HocTapsFlat F;
+            hoc_flatten_taps(T, H, W, F);
+            float sv[CT > 0 ? CT : 1][4], jv[CJT > 0 ? CJT : 1][4], tv[CT > 0 ? CT : 1];
+            float jc = 1.0f;
 #pragma unroll
-        for (int c = 0; c < WP_MAXC; c++)
-            wm[c] = m;
-        if (jitter != nullptr) {
+            for (int c = 0; c < CT; c++) {
 #pragma unroll
-            for (int c = 0; c < WP_MAXC; c++) {
-                if (c >= Cj)
-                    break;
-                const float wj = __fmul_rn(hoc_plane_sample(jitter + ((long)b * Cj + c) * npix, W, T), m);
-                wm[c] = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
+                for (int k = 0; k < 4; k++)
+                    sv[c][k] = __ldg(sb + (size_t)c * npix + F.o[k]);
+                tv[c] = __ldg(tb + (size_t)c * npix);
             }
-            if (Cj == 1) {
+            if (jb != nullptr) {
 #pragma unroll
-                for (int c = 1; c < WP_MAXC; c++)
-                    wm[c] = wm[0];
+                for (int c = 0; c < CJT; c++)
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        jv[c][k] = __ldg(jb + (size_t)c * npix + F.o[k]);
+                jc = __ldg(jb + pix);
             }
-            valid = (wm[0] != 0.0f) && !(fl.x == 0.0f) && (__ldg(jitter + (long)b * Cj * npix + pix) == 1.0f);
+#pragma unroll
+            for (int c = 0; c < WP_MAXC; c++)
+                wm[c] = m;
+            if (jb != nullptr) {
+#pragma unroll
+                for (int c = 0; c < CJT; c++) {
+                    const float wj = __fmul_rn(hoc_flat_combine(jv[c], F), m);
+                    wm[c] = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
+                }
+                valid = (wm[0] != 0.0f) && !(fl.x == 0.0f) && (jc == 1.0f);
+            } else {
+                valid = (m != 0.0f) && !(fl.x == 0.0f);
+            }
+#pragma unroll
+            for (int c = 0; c < CT; c++) {
+                const size_t o = ((size_t)b * C + c) * npix + pix;
+                const float v = __fmul_rn(hoc_flat_combine(sv[c], F), m);
+                const float d = fabsf(__fsub_rn(v, tv[c]));
+                if (warped != nullptr)
+                    warped[o] = v;
+                if (diff != nullptr)
+                    diff[o] = d;
+                if (warp_mask != nullptr)
+                    warp_mask[o] = wm[c < WP_MAXC ? c : 0];
+                if (valid) {
+                    my_sum += d;
+                    my_cnt += 1.0f;
+                }
+            }
         } else {
-            valid = (m != 0.0f) && !(fl.x == 0.0f);
+#pragma unroll
+            for (int c = 0; c < WP_MAXC; c++)
+                wm[c] = m;
+            if (jb != nullptr) {
+                for (int c = 0; c < Cj && c < WP_MAXC; c++) {
+                    const float wj = __fmul_rn(hoc_plane_sample(jb + (size_t)c * npix, W, T), m);
+                    wm[c] = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
+                }
+                if (Cj == 1) {
+#pragma unroll
+                    for (int c = 1; c < WP_MAXC; c++)
+                        wm[c] = wm[0];
+                }
+                valid = (wm[0] != 0.0f) && !(fl.x == 0.0f) && (__ldg(jb + pix) == 1.0f);
+            } else {
+                valid = (m != 0.0f) && !(fl.x == 0.0f);
+            }
+            for (int c = 0; c < C; c++) {
+                const size_t o = ((size_t)b * C + c) * npix + pix;
+                const float v = __fmul_rn(hoc_plane_sample(sb + (size_t)c * npix, W, T), m);
+                const float d = fabsf(__fsub_rn(v, tb[(size_t)c * npix]));
+                if (warped != nullptr)
+                    warped[o] = v;
+                if (diff != nullptr)
+                    diff[o] = d;
+                if (warp_mask != nullptr)
+                    warp_mask[o] = wm[c < WP_MAXC ? c : 0];
+                if (valid) {
+                    my_sum += d;
+                    my_cnt += 1.0f;
+                }
+            }
         }
         if (valid_mask != nullptr)
-            valid_mask[(long)b * npix + pix] = valid ? 1 : 0;
-#pragma unroll 4
-        for (int c = 0; c < C; c++) {
-            const long o = ((long)b * C + c) * npix + pix;
-            const float v = __fmul_rn(hoc_plane_sample(src + ((long)b * C + c) * npix, W, T), m);
-            const float d = fabsf(__fsub_rn(v, target[o]));
-            if (warped != nullptr)
-                warped[o] = v;
-            if (diff != nullptr)
-                diff[o] = d;
-            if (warp_mask != nullptr)
-                warp_mask[o] = wm[c < WP_MAXC ? c : 0];
-            if (valid) {
-                my_sum += d;
-                my_cnt += 1.0f;
-            }
-        }
+            valid_mask[(size_t)b * npix + pix] = valid ? 1 : 0;
     }
     my_sum = hoc_warp_sum(my_sum);
     my_cnt = hoc_warp_sum(my_cnt);
@@ -200,7 +295,7 @@ __global__ void __launch_bounds__(WP_THREADS)
 hoc_warp_photo_backward_kernel(const float *__restrict__ src, const float *__restrict__ target,
                                const float *__restrict__ flow, const uint8_t *__restrict__ valid_mask,
                                const double *__restrict__ sums, const float *__restrict__ grad_loss, int C, int H,
-                               int W, float thresh, float *__restrict__ grad_flow)
+                               int W, float inv_w, float inv_h, float thresh, float *__restrict__ grad_flow)
 {
     const int b = blockIdx.y;
     const long npix = (long)H * W;
@@ -213,7 +308,7 @@ hoc_warp_photo_backward_kernel(const float *__restrict__ src, const float *__res
         const int x = (int)pix - y * W;
         const float2 fl = *reinterpret_cast<const float2 *>(flow + ((long)b * npix + pix) * 2);
         HocTaps T;
-        hoc_bilinear_taps(x, y, fl.x, fl.y, H, W, T);
+        hoc_bilinear_taps_inv(x, y, fl.x, fl.y, H, W, inv_w, inv_h, T);
         const float cnt = (float)sums[2 * b + 1];
         const float scale = grad_loss[b] / fmaxf(cnt, 1.0f);
         const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
@@ -433,15 +528,17 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
         return HOC_ERR_CUDA;
     }
     const long npix = (long)H * W;
+    /* torch's `tensor / python_int` multiplies by this IEEE-float reciprocal */
+    const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1), inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
     if (C == 3 && (jitter == nullptr || Cj == 3)) /* the reference's case: RGB images, 3-channel jitter masks */
         HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
                    (hoc_warp_photo_forward_kernel<3, 3><<<grid, WP_THREADS, 0, st>>>(
-                       src, target, flow, jitter, C, Cj, H, W, thresh, warped, warp_mask, valid_mask, diff, sums)));
+                       src, target, flow, jitter, C, Cj, H, W, inv_w, inv_h, thresh, warped, warp_mask, valid_mask, diff, sums)));
     else
         HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
                    (hoc_warp_photo_forward_kernel<0, 0><<<grid, WP_THREADS, 0, st>>>(
-                       src, target, flow, jitter, C, Cj, H, W, thresh, warped, warp_mask, valid_mask, diff, sums)));
+                       src, target, flow, jitter, C, Cj, H, W, inv_w, inv_h, thresh, warped, warp_mask, valid_mask, diff, sums)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_forward_kernel");
     return HOC_OK;
 }
@@ -461,7 +558,8 @@ extern "C" int hoc_warp_photo_backward(const float *src, const float *target, co
     dim3 grid((unsigned)((npix + WP_THREADS - 1) / WP_THREADS), B);
     HOC_LAUNCH(HOC_K_WARP_PHOTO_BWD, (cudaStream_t)stream,
                (hoc_warp_photo_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
-                   src, target, flow, valid_mask, sums, grad_loss, C, H, W, thresh, grad_flow)));
+                   src, target, flow, valid_mask, sums, grad_loss, C, H, W,
+                   1.0f / (float)(W - 1 > 1 ? W - 1 : 1), 1.0f / (float)(H - 1 > 1 ? H - 1 : 1), thresh, grad_flow)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_backward_kernel");
     return HOC_OK;
 }

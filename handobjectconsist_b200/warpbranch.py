@@ -59,9 +59,15 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
             obj_verts[sample_idx] = _base(samples[sample_idx], "OBJVERTS3D").cuda(non_blocking=True)
             hand_verts[sample_idx] = _base(samples[sample_idx], "HANDVERTS3D").cuda(non_blocking=True)
     verts_world = []
+    last = len(samples) - 1
     for seq_idx in range(len(samples)):
-        all_verts, all_faces, _ = batch_cat_meshes([hand_verts[seq_idx], obj_verts[seq_idx]],
-                                                   [hand_faces[seq_idx], obj_faces[seq_idx]])
+        if seq_idx == last:
+            # the reference concatenates the faces of every frame but only the last frame's survive the loop
+            # (warpbranch.py:50-52,57-60): build that one
+            all_verts, all_faces, _ = batch_cat_meshes([hand_verts[seq_idx], obj_verts[seq_idx]],
+                                                       [hand_faces[seq_idx], obj_faces[seq_idx]])
+        else:
+            all_verts = torch.cat([hand_verts[seq_idx], obj_verts[seq_idx]], 1)
         if first_only and seq_idx > 0:
             all_verts = all_verts.detach()
         verts_world.append(all_verts)
