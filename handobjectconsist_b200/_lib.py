@@ -39,7 +39,8 @@ SIGNATURES = {
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
                                  _vp, _vp, _vp, _sz, _vp]),
-    "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp]),
     "hoc_warp_photo_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),
     "hoc_warp": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp]),
     "hoc_warp_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _vp, _vp]),

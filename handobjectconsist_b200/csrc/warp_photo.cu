@@ -160,7 +160,7 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
                               const float *__restrict__ flow, const float *__restrict__ jitter, int C_rt, int Cj_rt,
                               int H, int W, float inv_w, float inv_h, float thresh, float *__restrict__ warped,
                               float *__restrict__ warp_mask, uint8_t *__restrict__ valid_mask,
-                              float *__restrict__ diff, double *__restrict__ sums)
+                              uint8_t *__restrict__ flow_mask, float *__restrict__ diff, double *__restrict__ sums)
 {
     const int C = CT > 0 ? CT : C_rt;
     const int Cj = CJT > 0 ? CJT : Cj_rt;
@@ -268,6 +268,12 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
         }
         if (valid_mask != nullptr)
             valid_mask[(size_t)b * npix + pix] = valid ? 1 : 0;
+        if (flow_mask != nullptr) { /* ~(flow == 0), both components (imgflowarp.py:93,99) */
+            uchar2 fm;
+            fm.x = !(fl.x == 0.0f) ? 1 : 0;
+            fm.y = !(fl.y == 0.0f) ? 1 : 0;
+            *reinterpret_cast<uchar2 *>(flow_mask + ((size_t)b * npix + pix) * 2) = fm;
+        }
     }
     my_sum = hoc_warp_sum(my_sum);
     my_cnt = hoc_warp_sum(my_cnt);
@@ -287,6 +293,14 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
             atomicAdd(&sums[2 * b + 1], (double)n);
         }
     }
+}
+
+/* batch_masked_mean_loss (lossutils.py:1-8) from the per-sample (sum, count): loss = sum / max(count, 1) */
+__global__ void hoc_masked_mean_kernel(const double *__restrict__ sums, int B, float *__restrict__ loss)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B)
+        loss[b] = (float)(sums[2 * b] / fmax(sums[2 * b + 1], 1.0));
 }
 
 /* d loss[b] / d flow.  loss[b] = sum_valid |warp - target| / max(count, 1); the thresholded masks
@@ -510,7 +524,8 @@ hoc_occlusion_kernel(const float *__restrict__ mask1, const float *__restrict__ 
 /* ------------------------------------------------------------------------------------------ */
 extern "C" int hoc_warp_photo_forward(const float *src, const float *target, const float *flow, const float *jitter,
                                       int B, int C, int Cj, int H, int W, float thresh, float *warped,
-                                      float *warp_mask, uint8_t *valid_mask, float *diff, double *sums, void *stream)
+                                      float *warp_mask, uint8_t *valid_mask, uint8_t *flow_mask, float *diff,
+                                      double *sums, float *loss, void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (long)H * W < (1l << 31),
                   "hoc_warp_photo_forward: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
@@ -534,12 +549,16 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
     if (C == 3 && (jitter == nullptr || Cj == 3)) /* the reference's case: RGB images, 3-channel jitter masks */
         HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
                    (hoc_warp_photo_forward_kernel<3, 3><<<grid, WP_THREADS, 0, st>>>(
-                       src, target, flow, jitter, C, Cj, H, W, inv_w, inv_h, thresh, warped, warp_mask, valid_mask, diff, sums)));
+                       src, target, flow, jitter, C, Cj, H, W, inv_w, inv_h, thresh, warped, warp_mask, valid_mask, flow_mask, diff, sums)));
     else
         HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
                    (hoc_warp_photo_forward_kernel<0, 0><<<grid, WP_THREADS, 0, st>>>(
-                       src, target, flow, jitter, C, Cj, H, W, inv_w, inv_h, thresh, warped, warp_mask, valid_mask, diff, sums)));
+                       src, target, flow, jitter, C, Cj, H, W, inv_w, inv_h, thresh, warped, warp_mask, valid_mask, flow_mask, diff, sums)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_forward_kernel");
+    if (loss != nullptr) {
+        hoc_masked_mean_kernel<<<(B + 127) / 128, 128, 0, st>>>(sums, B, loss);
+        HOC_CHECK_LAUNCH("hoc_masked_mean_kernel");
+    }
     return HOC_OK;
 }
 

@@ -112,21 +112,22 @@ class _WarpPhotoFunction(Function):
             warped = torch.empty_like(sc)
             warp_mask = torch.empty_like(sc)
             diff = torch.empty_like(sc)
-            valid = torch.empty((B, H, W), dtype=torch.uint8, device=sc.device)
+            valid = torch.empty((B, H, W), dtype=torch.bool, device=sc.device)      # written as 0/1 bytes
+            flow_mask = torch.empty((B, H, W, 2), dtype=torch.bool, device=sc.device)
             sums = torch.empty((B, 2), dtype=torch.float64, device=sc.device)
+            loss = torch.empty((B,), dtype=torch.float32, device=sc.device)
             _lib.check(L.hoc_warp_photo_forward(_lib.ptr(sc), _lib.ptr(tc), _lib.ptr(fc), _lib.ptr(jc), B, C, Cj, H, W,
                                                 float(thresh), _lib.ptr(warped), _lib.ptr(warp_mask), _lib.ptr(valid),
-                                                _lib.ptr(diff), _lib.ptr(sums), _lib.stream_ptr()),
-                       "hoc_warp_photo_forward")
-            loss = (sums[:, 0] / sums[:, 1].clamp(min=1.0)).float()
+                                                _lib.ptr(flow_mask), _lib.ptr(diff), _lib.ptr(sums), _lib.ptr(loss),
+                                                _lib.stream_ptr()), "hoc_warp_photo_forward")
         ctx.save_for_backward(sc, tc, fc, valid, sums)
         ctx.thresh = float(thresh)
-        ctx.mark_non_differentiable(warp_mask, valid)
+        ctx.mark_non_differentiable(warp_mask, valid, flow_mask)
         ctx.set_materialize_grads(False)
-        return loss, warped, warp_mask, valid, diff
+        return loss, warped, warp_mask, valid, flow_mask, diff
 
     @staticmethod
-    def backward(ctx, grad_loss, grad_warped, grad_mask, grad_valid, grad_diff):
+    def backward(ctx, grad_loss, grad_warped, grad_mask, grad_valid, grad_flow_mask, grad_diff):
         if grad_warped is not None or grad_diff is not None:
             raise NotImplementedError("pair_consist: only the loss output is differentiable in the fused path")
         if not ctx.needs_input_grad[0] or grad_loss is None:
@@ -149,10 +150,10 @@ def _criterion_is_fused_l1(criterion):
 
 def _one_direction(flow, src, target, jitter, criterion, thresh=0.99999):
     """(loss [B], warp, warp_mask, valid_mask, flow_mask, diff) for one direction."""
-    flow_mask = ~(flow == 0)
     if _criterion_is_fused_l1(criterion):
-        loss, warped, warp_mask, valid, diff = _WarpPhotoFunction.apply(flow, src, target, jitter, thresh)
-        return loss, warped, warp_mask, valid.bool(), flow_mask, diff
+        loss, warped, warp_mask, valid, flow_mask, diff = _WarpPhotoFunction.apply(flow, src, target, jitter, thresh)
+        return loss, warped, warp_mask, valid, flow_mask, diff
+    flow_mask = ~(flow == 0)
     # other criteria (l2 / ssim / pyramids): warp kernels + the criterion's own torch ops
     flow_nchw = flow.permute(0, 3, 1, 2)
     warped, warp_mask = warp(src, flow_nchw, thresh)

@@ -141,14 +141,16 @@ int hoc_raster_backward(const float *faces, const float *textures, const int32_t
  * outputs (any may be NULL except sums):
  *   warped     [B,C,H,W]  warp(src, flow), already multiplied by its in-bounds mask
  *   warp_mask  [B,C,H,W]  in-bounds mask * (warp(jitter, flow) == 1)
- *   valid_mask [B,H,W] uint8   warp_mask[:,0] & (flow[...,0] != 0) & (jitter[:,0] == 1)
+ *   valid_mask [B,H,W] uint8 (0/1)   warp_mask[:,0] & (flow[...,0] != 0) & (jitter[:,0] == 1)
+ *   flow_mask  [B,H,W,2] uint8 (0/1) ~(flow == 0)
  *   diff       [B,C,H,W]  |warped - target|
- *   sums       [B,2] DOUBLE (sum of diff over valid elements, number of valid elements);
- *              zero-filled by the call;  loss[b] = sums[b,0] / max(sums[b,1], 1)
+ *   sums       [B,2] DOUBLE (sum of diff over valid elements, number of valid elements); zero-filled by the call
+ *   loss       [B] = sums[b,0] / max(sums[b,1], 1)  (batch_masked_mean_loss; second tiny launch; may be NULL)
  */
 int hoc_warp_photo_forward(const float *src, const float *target, const float *flow, const float *jitter, int B,
                            int C, int Cj, int H, int W, float thresh, float *warped, float *warp_mask,
-                           uint8_t *valid_mask, float *diff, double *sums, void *stream);
+                           uint8_t *valid_mask, uint8_t *flow_mask, float *diff, double *sums, float *loss,
+                           void *stream);
 
 /* Gradient of loss[b] w.r.t. flow, the only differentiable input (imgflowarp.py:52-53: the
  * thresholded masks carry no gradient).  grad_loss [B]; valid_mask / sums from the forward;
