@@ -67,6 +67,7 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
     extern __shared__ float s_centre[]; /* [S] pixel-centre NDC coordinate of index i */
     __shared__ float s_rec[ZB_WARPS][ZB_FACES_PER_WARP][ZB_REC];
     __shared__ int s_pre[ZB_WARPS][ZB_FACES_PER_WARP + 1];
+    __shared__ int s_queue[ZB_WARPS][64]; /* pixels that passed the edge tests: slot | x << 8 | y << 20 */
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -130,31 +131,57 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
 
     unsigned long long *zb = zbuf + (long)b * S * S;
     const int *pre = s_pre[warp];
-    for (int item = lane; item < n_pix; item += 32) {
-        int lo = 0, hi = n_surv; /* last slot with pre[slot] <= item */
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (pre[mid] <= item)
-                lo = mid;
-            else
-                hi = mid;
+    /* Two-stage loop.  Stage 1 (cheap, every lane busy): one bounding-box pixel per lane, three edge tests.
+     * Pixels that pass (~15 %) are queued in shared memory; stage 2 (the IEEE divisions of the clamped
+     * barycentric weights and of the perspective depth, then the atomicMin) runs whenever 32 of them are
+     * waiting, again with every lane busy. */
+    int *queue = s_queue[warp];
+    int qn = 0; /* warp-uniform */
+    for (int base = 0; base < n_pix || qn > 0; base += 32) {
+        const int item = base + lane;
+        bool hit = false;
+        int packed = 0;
+        if (item < n_pix) {
+            int lo = 0, hi = n_surv; /* last slot with pre[slot] <= item */
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pre[mid] <= item)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const float *rec = s_rec[warp][lo];
+            const int p = item - pre[lo];
+            const int bw = __float_as_int(rec[20]);
+            const int yy = (int)(((float)p + 0.5f) * rec[21]); /* p / bw for p < 2^22 */
+            const int xi = __float_as_int(rec[18]) + (p - yy * bw);
+            const int yi = __float_as_int(rec[19]) + yy;
+            hit = hoc_pixel_inside(rec, s_centre[xi], s_centre[yi]);
+            packed = lo | (xi << 8) | (yi << 20);
         }
-        const float *rec = s_rec[warp][lo];
-        const int p = item - pre[lo];
-        const int bw = __float_as_int(rec[20]);
-        int yy = (int)(((float)p + 0.5f) * rec[21]); /* p / bw for p < 2^22 */
-        const int xi = __float_as_int(rec[18]) + (p - yy * bw);
-        const int yi = __float_as_int(rec[19]) + yy;
-        if (!hoc_pixel_inside(rec, s_centre[xi], s_centre[yi]))
-            continue;
-        float w[3], zp;
-        if (!hoc_pixel_weights_depth(rec, rec + 9, xi, yi, near_, far_, w, &zp))
-            continue;
-        if (!(zp < far_)) /* NaN depth never wins a `<` comparison in the reference */
-            continue;
-        const unsigned long long key =
-            ((unsigned long long)hoc_float_order(zp) << 32) | (unsigned)__float_as_int(rec[22]);
-        atomicMin(zb + (long)yi * S + xi, key);
+        const unsigned m = __ballot_sync(HOC_FULL_MASK, hit);
+        if (hit)
+            queue[qn + __popc(m & ((1u << lane) - 1u))] = packed;
+        qn += __popc(m);
+        __syncwarp();
+        const bool flush = base + 32 >= n_pix; /* last pass over the boxes: drain what is left */
+        while (qn >= 32 || (flush && qn > 0)) {
+            const int take = min(qn, 32);
+            if (lane < take) {
+                const int pk = queue[qn - take + lane];
+                const float *rec = s_rec[warp][pk & 0xff];
+                const int xi = (pk >> 8) & 0xfff, yi = (pk >> 20) & 0xfff;
+                float w[3], zp;
+                if (hoc_pixel_weights_depth(rec, rec + 9, xi, yi, near_, far_, w, &zp) && zp < far_) {
+                    /* (a NaN depth fails `zp < far` and never wins a `<` comparison in the reference either) */
+                    const unsigned long long key =
+                        ((unsigned long long)hoc_float_order(zp) << 32) | (unsigned)__float_as_int(rec[22]);
+                    atomicMin(zb + (long)yi * S + xi, key);
+                }
+            }
+            qn -= take;
+            __syncwarp();
+        }
     }
 }
 
