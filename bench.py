@@ -367,7 +367,7 @@ def _reference_pairs_per_second(pairs, steps, warmup, threads):
     return sum(times), len(times)
 
 
-def cpu_baseline(sample_pairs=2, steps=1, warmup=0):
+def cpu_baseline(sample_pairs=4, steps=4, warmup=1):
     threads = os.cpu_count() or 1
     total, n = _reference_pairs_per_second(sample_pairs, steps, warmup, threads)
     return {"value": 2 * sample_pairs * n / total, "unit": UNIT, "cores": threads, "kind": "port",
@@ -379,8 +379,8 @@ def run_reference(args, rank):
     if rank != 0:
         return None
     threads = os.cpu_count() or 1
-    pairs = 2
-    steps = max(1, min(args.steps, 3))
+    pairs = 4
+    steps = max(1, min(args.steps, 6))
     warmup = min(args.warmup, 1)
     total, n = _reference_pairs_per_second(pairs, steps, warmup, threads)
     value = 2 * pairs * n / total
