@@ -33,6 +33,8 @@ SIGNATURES = {
     "hoc_launch_count": (ctypes.c_ulonglong, [_i]),
     "hoc_timer_begin": (_i, [ctypes.c_ulonglong]),
     "hoc_timer_end": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), _i]),
+    "hoc_timer_pause": (_i, []),
+    "hoc_timer_peek": (_i, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), _i]),
     "hoc_raster_forward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -27,6 +27,17 @@ static cudaEvent_t g_timer_ev[HOC_TIMER_CAP][2];
 static int g_timer_id[HOC_TIMER_CAP];
 static int g_timer_created = 0;
 
+/* Inside a stream capture the record becomes an EXTERNAL event node of the graph: it is re-recorded by every
+ * replay and cudaEventElapsedTime on it is valid, so kernels can be timed where they run in production. */
+static void hoc_timer_record(cudaEvent_t ev, cudaStream_t st)
+{
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive)
+        cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal);
+    else
+        cudaEventRecord(ev, st);
+}
+
 void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
 {
     if (phase == 0)
@@ -40,9 +51,9 @@ void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
             g_timer_created = g_timer_n + 1;
         }
         g_timer_id[g_timer_n] = kernel_id;
-        cudaEventRecord(g_timer_ev[g_timer_n][0], st);
+        hoc_timer_record(g_timer_ev[g_timer_n][0], st);
     } else {
-        cudaEventRecord(g_timer_ev[g_timer_n][1], st);
+        hoc_timer_record(g_timer_ev[g_timer_n][1], st);
         g_timer_n++;
     }
 }
@@ -63,6 +74,25 @@ extern "C" int hoc_timer_begin(unsigned long long kernel_mask)
     g_timer_mask = kernel_mask;
     g_timer_n = 0;
     return HOC_OK;
+}
+
+extern "C" int hoc_timer_pause(void)
+{
+    g_timer_mask = 0; /* stop bracketing new launches, keep the recorded event pairs */
+    return g_timer_n;
+}
+
+extern "C" int hoc_timer_peek(float *ms_host, int *kernel_ids_host, int capacity)
+{
+    const int n = g_timer_n < capacity ? g_timer_n : capacity;
+    for (int i = 0; i < n; i++) {
+        cudaEventSynchronize(g_timer_ev[i][1]);
+        if (cudaEventElapsedTime(&ms_host[i], g_timer_ev[i][0], g_timer_ev[i][1]) != cudaSuccess)
+            ms_host[i] = -1.0f;
+        if (kernel_ids_host != nullptr)
+            kernel_ids_host[i] = g_timer_id[i];
+    }
+    return n;
 }
 
 extern "C" int hoc_timer_end(float *ms_host, int *kernel_ids_host, int capacity)

@@ -21,7 +21,8 @@ def _name(key):
 
 class GraphedConsistStep:
     def __init__(self, renderer, criterion, image_size, hand_face, samples, all_results, hand_ignore_faces=None,
-                 gt_refs=True, first_only=True, use_backward=True, detach_renders=True, warmup=3):
+                 gt_refs=True, first_only=True, use_backward=True, detach_renders=True, warmup=3,
+                 before_capture=None):
         """``samples`` / ``all_results``: one example batch (reference layout, warpbranch.py:27-44) that fixes
         shapes and dtypes; their values are only used for the warm-up iterations."""
         if len(samples) != 2:
@@ -46,6 +47,8 @@ class GraphedConsistStep:
                 self._run()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if before_capture is not None:
+            before_capture()  # e.g. arm the library's device timer so that the capture is instrumented
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.grad_hand, self.grad_obj = self._run()

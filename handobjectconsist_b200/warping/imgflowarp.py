@@ -9,7 +9,7 @@ align_corners=True formula but sampled with align_corners=False, so a zero flow 
 import torch
 from torch.autograd import Function
 
-from .. import _lib
+from .. import _config, _lib
 
 
 _SIDE_STREAMS = {}
@@ -181,7 +181,7 @@ def pair_consist(recons_flow, image_ref: torch.Tensor, image: torch.Tensor, jitt
     # the two directions are independent: the second runs on a side stream (its kernels overlap the first's)
     dev = image.device
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
+    side = _side_stream(dev) if _config.overlap_streams else main
     side.wait_stream(main)
     with torch.cuda.stream(side):
         # direction 2: warp(image, flow12) against image_ref; jitter_mask_ref warped with flow12

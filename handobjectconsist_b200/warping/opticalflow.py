@@ -13,7 +13,7 @@ from typing import List
 import torch
 from torch.autograd import Function
 
-from .. import _lib
+from .. import _config, _lib
 from ..meshutils import batch_proj2d, batch_vertex_textures
 from . import imgflowarp
 
@@ -228,7 +228,7 @@ def _get_opticalflow_fused(verts_cam, faces, camintrs, neurenderer, orig_img_siz
     # the two renders are independent: the second one runs on a side stream so that their (small, tail-heavy)
     # kernels overlap; autograd replays the same stream assignment in the backward
     main = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
+    side = _side_stream(dev) if _config.overlap_streams else main
     renders = [None, None]
     if detach_renders:
         ndc1, ndc2 = ndc1.detach(), ndc2.detach()

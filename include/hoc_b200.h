@@ -76,9 +76,14 @@ unsigned long long hoc_launch_count(int kernel_id);
 /* Arm / read the device timer: between begin and end every launch of a kernel whose bit is set in
  * `kernel_mask` (1 << HOC_K_*) is bracketed by CUDA events on its stream; end synchronises them and writes
  * up to `capacity` durations (ms) and kernel ids to host memory, returning how many were recorded.  Not
- * thread-safe, not usable during stream capture; meant for benchmarking. */
+ * thread-safe; meant for benchmarking. */
 int hoc_timer_begin(unsigned long long kernel_mask);
 int hoc_timer_end(float *ms_host, int *kernel_ids_host, int capacity);
+/* Timing kernels INSIDE a CUDA graph: arm the timer, capture the graph (the brackets become external event
+ * nodes that every replay re-records), call hoc_timer_pause() (stops bracketing, keeps the event pairs; returns
+ * how many), replay, then hoc_timer_peek() reads the durations of the latest replay without resetting. */
+int hoc_timer_pause(void);
+int hoc_timer_peek(float *ms_host, int *kernel_ids_host, int capacity);
 
 /* ---- rasterizer forward -------------------------------------------------------------------
  * Replaces forward_face_index_map + forward_texture_sampling (rasterize.py:202-215,232-243)
