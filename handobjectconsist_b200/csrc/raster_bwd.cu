@@ -328,7 +328,7 @@ __device__ __forceinline__ void hoc_k4_face_column(const HocK4Edge &E, int fi, i
  * compacted and their work is flattened to one item per (face, edge, axis, column), so that every lane
  * has a short, independent task (the columns of all edges of ~35 faces, ~600 items per CTA).
  */
-__global__ void __launch_bounds__(BW_THREADS)
+__global__ void __launch_bounds__(BW_THREADS, 8) /* 8 CTAs/SM: the 1152 CTAs of 16 x 9104 faces fit in one wave */
 hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
