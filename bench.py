@@ -296,9 +296,12 @@ def run_native(args, rank, world, local_rank):
     algo = {
         "raster_zbuf": PAIRS * F2 * 36 + npx * 8,                       # faces in, 8-byte depth/face key per pixel
         "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 96) + npx * 24,   # key, faces+textures, rgb12+alpha4+depth4+idx4
-        "raster_bwd_pixel": npx * (4 + 12) + PAIRS * F2 * (36 + 96),     # idx + grad_rgb in, faces in, grad_textures out
-        "raster_backward": PAIRS * F2 * (36 + 4 + 36) + npx * (4 + 12 + 12),  # face pass: faces, owned, grad_faces; idx, rgb, grad_rgb
-        "raster_bwd_line": npx * (12 + 12 + 4) + PAIRS * F2 * 36,        # line pass: rgb, grad_rgb, idx once; grad_faces update
+        # pixel pass: idx, grad_rgb, weights, depth in; faces in; grad of the 9 vertex values out
+        "raster_bwd_pixel": npx * (4 + 12 + 12 + 4) + PAIRS * F2 * (36 + 36),
+        # ... with the pseudo-gradient: + rgb in, two flag bytes per pixel out, grad_faces (memset + update)
+        "raster_bwd_pixel_k4": npx * (4 + 12 + 12 + 4 + 12 + 2) + PAIRS * F2 * (36 + 36 + 36),
+        "raster_backward": PAIRS * F2 * (36 + 12 + 36),                  # depth epilogue (only with dL/ddepth)
+        "raster_bwd_line": npx * (12 + 12 + 4 + 2) + PAIRS * F2 * 36,    # line pass: rgb, grad_rgb, idx, flags once; grad_faces update
         "warp_photo_fwd": npx * (12 + 8 + 12 + 4 + 4 + 12 + 12 + 12 + 1),
         "warp_photo_bwd": npx * (12 + 8 + 12 + 1 + 8),
         "flow_finalize": 2 * npx * (2 * (8 + 4 + 4) + 8 + 4),
@@ -316,7 +319,7 @@ def run_native(args, rank, world, local_rank):
                       "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
     table.sort(key=lambda r: -r["share_of_step"])
     kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve_kernel",
-             "raster_bwd_pixel": "hoc_raster_bwd_pixel_kernel", "raster_backward": "hoc_raster_bwd_face_kernel",
+             "raster_bwd_pixel": "hoc_raster_bwd_pixel_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_pixel_kernel<K4>", "raster_backward": "hoc_raster_bwd_depth_kernel",
              "raster_bwd_line": "hoc_raster_bwd_line_kernel", "warp_photo_fwd": "hoc_warp_photo_forward_kernel",
              "warp_photo_bwd": "hoc_warp_photo_backward_kernel", "flow_finalize": "hoc_flow_finalize_kernel",
              "flow_finalize_bwd": "hoc_flow_finalize_backward_kernel", "mesh_gather": "hoc_mesh_gather_kernel",
@@ -328,14 +331,13 @@ def run_native(args, rank, world, local_rank):
         with open(tpath) as f:
             traffic_tab = json.load(f)
     # `roofline`: the kernel with the largest share of the step (table[0]); `roofline_raster_backward`: the kernel
-    # BASELINE.json's north_star names -- three launches here (pixel, face, line pass), reported together with the
+    # BASELINE.json's north_star names -- two launches here (pixel pass, line pass), reported together with the
     # bytes of the whole backward of one render counted once
     dom = next((r for r in table if r["algorithmic_bytes_per_launch"]), None)
-    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel", "raster_backward", "raster_bwd_line")]
+    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel_k4", "raster_backward", "raster_bwd_line")]
     bwd_bytes = npx * (4 + 12 + 12) + PAIRS * F2 * (36 + 36 + 36)
-    bwd_ms = sum(r["avg_ms"] for r in bwd if r["kernel"] != "raster_bwd_pixel") + \
-        sum(r["avg_ms"] for r in bwd if r["kernel"] == "raster_bwd_pixel")
-    traffic = traffic_tab.get(kname[dom["kernel"]]) if dom else None
+    bwd_ms = sum(r["avg_ms"] for r in bwd)
+    traffic = traffic_tab.get(kname[dom["kernel"]].split("<")[0]) if dom else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -369,8 +371,8 @@ def run_native(args, rank, world, local_rank):
             "algorithmic_bytes_per_render": bwd_bytes, "ms_per_render": bwd_ms if bwd else None,
             "achieved": (bwd_bytes / (bwd_ms * 1e-3) / 1e9) if bwd and bwd_ms > 0 else None, "peak": peak, "unit": "GB/s",
             "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak) if bwd and bwd_ms > 0 else None,
-            "traffic": sum(traffic_tab.get(kname[r["kernel"]], 0) for r in bwd) or None,
-            "note": "pixel + face + line pass of the render whose geometry gradient is needed"},
+            "traffic": sum(traffic_tab.get(kname[r["kernel"]].split("<")[0], 0) for r in bwd) or None,
+            "note": "pixel pass + line pass of the render whose geometry gradient is needed (the per-face pass of earlier builds is gone: the pseudo-gradient runs from the pixels)"},
         "kernels": table,
     }
     return out

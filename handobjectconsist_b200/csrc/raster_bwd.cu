@@ -10,20 +10,23 @@
  * passes over it) and scatters texture / depth gradients with one thread per pixel.  Here the work is
  * split by what it is parallel over:
  *
- *   hoc_raster_bwd_pixel_kernel   pixel-parallel, streaming (one pass over face_index_map and the
- *           incoming gradients): per-line spans of non-zero incoming gradient (a pixel with zero incoming
- *           gradient contributes exactly nothing to any scan, so scans are clipped to the span), and for
- *           covered pixels the texture / depth gradient of the owning face plus its owned-pixel count.
- *           Weights, depth and the eight trilinear taps are recomputed with the forward's functions
- *           (bit-identical), so weight_map, face_inv_map and the reference's two sampling maps (64 B/px)
- *           are never stored or read.
- *   hoc_raster_bwd_face_kernel    face-parallel: a CTA owns 256 faces; faces that own no pixel are done
- *           (both scans of the pseudo-gradient require ownership); the others are compacted and their
- *           (face, edge, axis) tasks spread over the CTA.  A task walks the integer columns its edge
- *           crosses, does the short INWARD scan itself and hands the long OUTWARD scan to the line it
- *           runs along by appending a 4-byte record (face, edge) to that line's bucket.
- *   hoc_raster_bwd_line_kernel    line-parallel: a CTA owns one image row or column, stages the span of
- *           that line (I and dL/dI of every pixel) in shared memory ONCE and lets every lane run one
+ *   hoc_raster_bwd_pixel_kernel   pixel-parallel.  Phase 1 streams face_index_map and the incoming gradients
+ *           once: per-line spans of non-zero incoming gradient (a pixel with zero incoming gradient
+ *           contributes exactly nothing to any scan, so scans are clipped to the span), and for covered
+ *           pixels the texture / depth gradient of the owning face.  Phase 2 runs the pseudo-gradient FROM
+ *           THE PIXELS: a pixel owned by face f lies on column x and row y of f; for each of the 3 edges x
+ *           2 axes it evaluates that column of the edge once and (a) adds its own term of the short INWARD
+ *           scan (the reference visits exactly the owned pixels between the edge and the opposite edge),
+ *           (b) if it is the pixel just inside the edge, flags the long OUTWARD scan that starts there:
+ *           one byte per pixel and axis (3 "edge e starts a scan here" bits + 3 direction bits), written
+ *           coalesced -- row-major for row scans, transposed for column scans.  No per-face pass, no
+ *           queues, no counters: a scan is identified by (line, position, edge), the face by
+ *           face_index_map at that position.
+ *   hoc_raster_bwd_depth_kernel   face-parallel epilogue of backward_depth_map (only when dL/ddepth exists).
+ *   hoc_raster_bwd_line_kernel    line-parallel: a CTA owns one image row or column, reads the line's flag
+ *           bytes, compacts them IN POSITION ORDER into two lists (scans towards +, scans towards -, so
+ *           that neighbouring lanes get scans of nearly equal length), stages the span of that line
+ *           (P = sum_ch I_ch g_ch and g of every pixel) in shared memory ONCE and lets every lane run one
  *           outward scan out of shared memory; each scan adds its two vertex contributions to grad_faces.
  */
 #include "hoc_common.cuh"
@@ -34,20 +37,18 @@
 #define EXT_COL_LO 2
 #define EXT_COL_HI 3
 
-/* Workspace carved by hoc_raster_backward (all int32 / float32, 16-byte aligned regions):
- *   ext        int [B][4][S]      {row_lo, row_hi, col_lo, col_hi}: span of non-zero incoming gradient
- *   owned      int [B][F]         pixels owned by each face
- *   acc_d      float [B][F][3]    sum over owned pixels of dL/ddepth * depth^2 * w_k
- *   line_count int [B][2][S]      outward scans queued on each line (axis 0: column x, axis 1: row y)
- *   emitters   int [B][2][S][3S]  the queue: face | edge << 29.  3S is a hard bound: a scan is keyed by its
- *                                 inside pixel on the line, which is owned by exactly one face with 3 edges */
+/* Workspace carved by hoc_raster_backward (16-byte aligned regions):
+ *   ext        int   [B][4][S]     {row_lo, row_hi, col_lo, col_hi}: span of non-zero incoming gradient
+ *   acc_d      float [B][F][3]     sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
+ *   flags      uint8 [B][2][S][S]  outward-scan flags; plane 0 (column scans) is stored [x][y], plane 1 (row
+ *                                  scans) [y][x], so a line's bytes are contiguous.  Bit e: edge e of the face
+ *                                  owning this pixel starts an outward scan here; bit 3+e: it runs towards +.
+ *                                  Every byte is written by the pixel pass (no zero-fill). */
 struct HocBwdWorkspace {
     int *ext;
-    int *owned;
     float *acc_d;
-    int *line_count;
-    int *emitters;
-    size_t zero_begin, zero_bytes; /* byte range (owned .. line_count) that must be zero-filled */
+    uint8_t *flags;
+    size_t acc_bytes;
     size_t total;
 };
 
@@ -59,16 +60,11 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     char *p = (char *)base;
     w.ext = (int *)(p + off);
     off = up(off + sizeof(int) * 4 * (size_t)B * S);
-    w.zero_begin = off;
-    w.owned = (int *)(p + off);
-    off = up(off + sizeof(int) * (size_t)B * F);
     w.acc_d = (float *)(p + off);
-    off = up(off + sizeof(float) * 3 * (size_t)B * F);
-    w.line_count = (int *)(p + off);
-    off = up(off + sizeof(int) * 2 * (size_t)B * S);
-    w.zero_bytes = off - w.zero_begin;
-    w.emitters = (int *)(p + off);
-    off = up(off + sizeof(int) * 2 * (size_t)B * S * 3 * (size_t)S);
+    w.acc_bytes = sizeof(float) * 3 * (size_t)B * F;
+    off = up(off + w.acc_bytes);
+    w.flags = (uint8_t *)(p + off);
+    off = up(off + 2 * (size_t)B * S * S);
     w.total = off;
     return w;
 }
@@ -97,47 +93,88 @@ __device__ __forceinline__ void hoc_load_I(const HocBwdMaps &M, int xi, int yi, 
     }
 }
 
-/* delta = sum_ch (I(pixel) - Iref) * g(pixel), in the reference's accumulation order. */
-__device__ __forceinline__ float hoc_delta(const HocBwdMaps &M, int xi, int yi, const float *Iref)
+/* One (edge, axis) of the face owning pixel (xi, yi): the pixel's term of the inward scan of the column it
+ * lies on (added to grad_faces) and, when it is the pixel just inside the edge, the outward-scan flag.
+ * (ax..cy) are the face's vertices in NDC rotated so that A is the first vertex of the edge; gfA / gfB point
+ * at the x component of vertex A / B in grad_faces.  I / g: (alpha, r, g, b) of the pixel and its incoming
+ * gradient. */
+__device__ __forceinline__ unsigned hoc_k4_pixel_combo(float ax, float ay, float bx, float by, float cx, float cy,
+                                                       int edge, int axis, int xi, int yi, const HocBwdMaps &M,
+                                                       const float *I, const float *g, float eps,
+                                                       float *__restrict__ gfA, float *__restrict__ gfB)
 {
-    float d = 0.0f;
-    if (M.use_alpha) {
-        const float a = (M.idx[(long)yi * M.S + xi] >= 0) ? 1.0f : 0.0f;
-        d += (a - Iref[0]) * M.g_alpha[hoc_plane_off(M.layout, M.S, M.b, yi, xi)];
-    }
-    if (M.use_rgb) {
+    HocK4Edge E;
+    hoc_k4_edge_pts(ax, ay, bx, by, cx, cy, M.S, axis, &E);
+    const int d0 = axis == 0 ? xi : yi, d1p = axis == 0 ? yi : xi;
+    if (d0 < E.d0_from || d0 > E.d0_to)
+        return 0u;
+    float d1_cross;
+    int d1_in, d1_out;
+    if (!hoc_k4_column(&E, M.S, d0, &d1_cross, &d1_in, &d1_out))
+        return 0u;
+    unsigned flag = 0u;
+    if (d1_in == d1p)
+        flag = (1u << edge) | ((0 < E.dir) ? (8u << edge) : 0u);
+    const int lim = hoc_k4_inward_limit(&E, d0);
+    const int d1_from = max(min(d1_in, lim), 0);
+    const int d1_to = min(max(d1_in, lim), M.S - 1);
+    if (d1_from <= d1p && d1p <= d1_to) {
+        float I_out[4];
+        hoc_load_I(M, axis == 0 ? d0 : d1_out, axis == 0 ? d1_out : d0, I_out);
+        float delta = 0.0f; /* the reference's accumulation order: alpha, r, g, b */
+        if (M.use_alpha)
+            delta += (I[0] - I_out[0]) * g[0];
+        if (M.use_rgb) {
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const long o = hoc_rgb_off(M.layout, M.S, M.b, yi, xi, k);
-            d += (M.rgb[o] - Iref[1 + k]) * M.g_rgb[o];
+            for (int k = 1; k < 4; k++)
+                delta += (I[k] - I_out[k]) * g[k];
+        }
+        if (!(delta <= 0.0f)) {
+            HocK4Col C;
+            hoc_k4_col(&E, M.S, d0, d1_cross, &C);
+            float gA = 0.0f, gB = 0.0f;
+            hoc_k4_accum_col(&C, d1p, eps, delta, &gA, &gB);
+            if (gA != 0.0f)
+                atomicAdd(gfA + (1 - axis), gA);
+            if (gB != 0.0f)
+                atomicAdd(gfB + (1 - axis), gB);
         }
     }
-    return d;
+    return flag;
 }
-
-#define BW_THREADS 128
-#define BW_WARPS (BW_THREADS / 32)
 
 /*
  * Pixel pass.  Block (32, 8) covers a 32 x 32 pixel tile (4 rows per thread).
  */
-template <bool TS2>
+template <bool TS2, bool K4>
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
-                            const float *__restrict__ weight_map, const float *__restrict__ depth_map,
-                            const float *__restrict__ g_rgb, const float *__restrict__ g_alpha,
-                            const float *__restrict__ g_depth, int F, int S, int ts, float near_, float far_, float eps,
-                            int layout, int want_ext, int tex_mode, int *__restrict__ ext, int *__restrict__ owned,
-                            float *__restrict__ acc_d, float *__restrict__ grad_textures)
+                            const float *__restrict__ rgb, const float *__restrict__ weight_map,
+                            const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
+                            const float *__restrict__ g_alpha, const float *__restrict__ g_depth, int F, int S, int ts,
+                            float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
+                            int *__restrict__ ext, float *__restrict__ acc_d, uint8_t *__restrict__ flags,
+                            float *__restrict__ grad_faces, float *__restrict__ grad_textures)
 {
     __shared__ int s_lo[8][32];
     __shared__ int s_hi[8][32];
+    __shared__ unsigned short s_cov[1024]; /* covered pixels of the tile: ly << 5 | lx */
+    __shared__ __align__(16) uint8_t s_flag[2][32][36];  /* [0][lx][ly] (transposed), [1][ly][lx] */
+    __shared__ int s_ncov;
     const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * 32 + tx;
     const int b = blockIdx.z;
     const int xi = blockIdx.x * 32 + tx;
     int *e = ext + (long)b * 4 * S;
     const int tex_n = ts * ts * ts * 3;
     int c_lo = 0x7f7f7f7f, c_hi = -1;
+    if (K4) {
+        if (tid == 0)
+            s_ncov = 0;
+        for (int i = tid; i < 2 * 32 * 36 / 4; i += 256)
+            reinterpret_cast<uint32_t *>(&s_flag[0][0][0])[i] = 0u;
+        __syncthreads();
+    }
     /* issue the loads of all four rows first (memory-level parallelism), then do the per-pixel work */
     float gr[4][3], ga[4];
     int fis[4];
@@ -166,8 +203,16 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
         const int yi = blockIdx.y * 32 + r * 8 + ty;
         const bool nz = !(gr[r][0] == 0.0f) || !(gr[r][1] == 0.0f) || !(gr[r][2] == 0.0f) || !(ga[r] == 0.0f);
         const int fi = fis[r];
+        if (K4) { /* ordered compaction of the covered pixels of this warp row */
+            const unsigned cm = __ballot_sync(HOC_FULL_MASK, fi >= 0);
+            int base = 0;
+            if (tx == 0 && cm != 0)
+                base = atomicAdd(&s_ncov, __popc(cm));
+            base = __shfl_sync(HOC_FULL_MASK, base, 0);
+            if (fi >= 0)
+                s_cov[base + __popc(cm & ((1u << tx) - 1u))] = (unsigned short)(((r * 8 + ty) << 5) | tx);
+        }
         if (fi >= 0) {
-            atomicAdd(owned + (long)b * F + fi, 1);
             if ((want_tex && nz) || want_depth) {
                 float f[9], w[3], zp;
                 const float *src = faces + ((long)b * F + fi) * 9;
@@ -250,7 +295,7 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
                 }
             }
         }
-        if (want_ext) {
+        if (K4) {
             const unsigned m = __ballot_sync(HOC_FULL_MASK, nz);
             if (m != 0 && tx == 0) {
                 atomicMin(&e[EXT_ROW_LO * S + yi], blockIdx.x * 32 + (__ffs(m) - 1));
@@ -262,7 +307,7 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
             }
         }
     }
-    if (!want_ext)
+    if (!K4)
         return;
     s_lo[ty][tx] = c_lo;
     s_hi[ty][tx] = c_hi;
@@ -278,96 +323,8 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
             atomicMax(&e[EXT_COL_HI * S + xi], c_hi);
         }
     }
-}
 
-/* One column d0 of a (face, edge, axis): queue the outward scan on the line it runs along when the inside
- * pixel is owned by the face, and do the short inward scan (the face's own pixels) here. */
-__device__ __forceinline__ void hoc_k4_face_column(const HocK4Edge &E, int fi, int edge, int axis, int d0,
-                                                   const HocBwdMaps &M, float eps, int *__restrict__ line_count,
-                                                   int *__restrict__ emitters, float *gA_out, float *gB_out)
-{
-    const int S = M.S;
-    float gA = 0.0f, gB = 0.0f;
-    float d1_cross;
-    int d1_in, d1_out;
-    if (hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out)) {
-        const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
-        if (M.idx[(long)yin * S + xin] == fi) {
-            const long line = ((long)M.b * 2 + axis) * S + d0;
-            const int pos = atomicAdd(line_count + line, 1);
-            if (pos < 3 * S) /* cannot fail (see HocBwdWorkspace); keeps a corrupted map from overrunning */
-                emitters[line * 3 * S + pos] = fi | (edge << 29);
-        }
-        const int lim = hoc_k4_inward_limit(&E, d0);
-        const int d1_from = max(min(d1_in, lim), 0);
-        const int d1_to = min(max(d1_in, lim), S - 1);
-        bool have_out = false;
-        float I_out[4];
-        HocK4Col C;
-        for (int d1 = d1_from; d1 <= d1_to; d1++) {
-            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-            if (M.idx[(long)yi * S + xi] != fi)
-                continue;
-            if (!have_out) {
-                hoc_load_I(M, axis == 0 ? d0 : d1_out, axis == 0 ? d1_out : d0, I_out);
-                hoc_k4_col(&E, S, d0, d1_cross, &C);
-                have_out = true;
-            }
-            const float delta = hoc_delta(M, xi, yi, I_out);
-            if (!(delta <= 0.0f))
-                hoc_k4_accum_col(&C, d1, eps, delta, &gA, &gB);
-        }
-    }
-    *gA_out = gA;
-    *gB_out = gB;
-}
-
-/*
- * Face pass.  One CTA owns BW_THREADS consecutive faces of one sample; writes grad_faces for all of them
- * (depth term + inward scans; zeros for culled / unowned faces).  The faces that own pixels are
- * compacted and their work is flattened to one item per (face, edge, axis, column), so that every lane
- * has a short, independent task (the columns of all edges of ~35 faces, ~600 items per CTA).
- */
-__global__ void __launch_bounds__(BW_THREADS, 8) /* 8 CTAs/SM: the 1152 CTAs of 16 x 9104 faces fit in one wave */
-hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
-                           const float *__restrict__ rgb, const float *__restrict__ g_rgb,
-                           const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
-                           int want_depth, const int *__restrict__ owned, const float *__restrict__ acc_d,
-                           int *__restrict__ line_count, int *__restrict__ emitters, float *__restrict__ grad_faces)
-{
-    __shared__ float s_face[BW_THREADS][9];
-    __shared__ float s_k4[BW_THREADS][6][2];
-    __shared__ unsigned short s_vis[BW_THREADS];
-    __shared__ int s_pre[BW_THREADS * 6 + 1];
-    __shared__ int s_nvis;
-
-    const int tid = threadIdx.x;
-    const int b = blockIdx.y;
-    /* faces are dealt to the CTAs round-robin (CTA c takes faces c, c + G, c + 2G, ...) so that every CTA
-     * gets the same mix of large / small / hidden faces */
-    const int fi = tid * gridDim.x + blockIdx.x;
-    const bool valid = fi < F;
-    if (tid == 0)
-        s_nvis = 0;
-    float f[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++)
-        f[k] = 0.0f;
-    if (valid) {
-        const float *src = faces + ((long)b * F + fi) * 9;
-#pragma unroll
-        for (int k = 0; k < 9; k++)
-            f[k] = __ldg(src + k);
-    }
-#pragma unroll
-    for (int k = 0; k < 9; k++)
-        s_face[tid][k] = f[k];
-#pragma unroll
-    for (int k = 0; k < 12; k++)
-        (&s_k4[tid][0][0])[k] = 0.0f;
-    const bool front = valid && hoc_face_xy_finite(f) && !hoc_face_back(f);
-    const bool hit = front && owned[(long)b * F + fi] > 0;
-
+    /* Phase 2: the pseudo-gradient from the covered pixels of the tile, one pixel per thread. */
     HocBwdMaps M;
     M.idx = face_index_map + (long)b * S * S;
     M.rgb = rgb;
@@ -378,137 +335,169 @@ hoc_raster_bwd_face_kernel(const float *__restrict__ faces, const int32_t *__res
     M.b = b;
     M.use_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     M.use_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    const bool want_k4 = M.use_alpha || M.use_rgb;
-    __syncthreads();
-
-    if (want_k4) {
-        if (hit)
-            s_vis[atomicAdd(&s_nvis, 1)] = (unsigned short)tid;
-        __syncthreads();
-        const int nq = s_nvis * 6; /* (face, edge, axis) groups */
-        for (int q = tid; q < nq; q += BW_THREADS) {
-            const int lf = s_vis[q / 6];
-            const int combo = q - (q / 6) * 6;
-            HocK4Edge E;
-            hoc_k4_edge(s_face[lf], S, combo >> 1, combo & 1, &E);
-            s_pre[q] = max(E.d0_to - E.d0_from + 1, 0);
-        }
-        __syncthreads();
-        if (tid < 32) { /* exclusive prefix sum of the column counts: each lane scans a contiguous chunk */
-            const int per = (nq + 31) / 32;
-            const int lo = min(tid * per, nq), hi = min(lo + per, nq);
-            int sum = 0;
-            for (int q = lo; q < hi; q++)
-                sum += s_pre[q];
-            int incl = sum;
+    const int ncov = s_ncov;
+    for (int i = tid; i < ncov; i += 256) {
+        const int l = s_cov[i];
+        const int lx = l & 31, ly = l >> 5;
+        const int px = blockIdx.x * 32 + lx, py = blockIdx.y * 32 + ly;
+        const int fi = M.idx[(long)py * S + px];
+        float f[9];
+        const float *src = faces + ((long)b * F + fi) * 9;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(HOC_FULL_MASK, incl, o);
-                if (tid >= o)
-                    incl += v;
-            }
-            int run = incl - sum;
-            for (int q = lo; q < hi; q++) {
-                const int c = s_pre[q];
-                s_pre[q] = run;
-                run += c;
-            }
-            if (tid == 31)
-                s_pre[nq] = incl;
-        }
-        __syncthreads();
-        const int total = s_pre[nq];
-        for (int item = tid; item < total; item += BW_THREADS) {
-            int lo = 0, hi = nq; /* last q with s_pre[q] <= item */
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_pre[mid] <= item)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-            const int q = lo;
-            const int lf = s_vis[q / 6];
-            const int combo = q - (q / 6) * 6;
-            const int edge = combo >> 1, axis = combo & 1;
-            HocK4Edge E;
-            hoc_k4_edge(s_face[lf], S, edge, axis, &E);
-            float gA, gB;
-            hoc_k4_face_column(E, lf * gridDim.x + blockIdx.x, edge, axis, E.d0_from + (item - s_pre[q]), M, eps, line_count, emitters,
-                               &gA, &gB);
-            if (gA != 0.0f)
-                atomicAdd(&s_k4[lf][combo][0], gA);
-            if (gB != 0.0f)
-                atomicAdd(&s_k4[lf][combo][1], gB);
-        }
-        __syncthreads();
-    }
-    if (!valid)
-        return;
-    float gface[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++)
-        gface[k] = 0.0f;
-    if (hit) {
-        if (want_depth) {
-            float inv[9], tmp[2];
-            hoc_face_inv(f, S, inv);
-            const float *ad = acc_d + ((long)b * F + fi) * 3;
-#pragma unroll
-            for (int l = 0; l < 2; l++)
-                tmp[l] = inv[l] / f[2] + inv[3 + l] / f[5] + inv[6 + l] / f[8];
+        for (int k = 0; k < 9; k++)
+            f[k] = __ldg(src + k);
+        float I[4] = {1.0f, 0.0f, 0.0f, 0.0f}, g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (M.use_alpha)
+            g[0] = g_alpha[hoc_plane_off(layout, S, b, py, px)];
+        if (M.use_rgb) {
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float zk = f[3 * k + 2];
-                const float a = ad[k];
-                gface[3 * k + 2] = a / (zk * zk);
-                gface[3 * k + 0] = a * tmp[0] * (float)S / 2.0f;
-                gface[3 * k + 1] = a * tmp[1] * (float)S / 2.0f;
+                const long o = hoc_rgb_off(layout, S, b, py, px, k);
+                I[1 + k] = rgb[o];
+                g[1 + k] = g_rgb[o];
             }
         }
-        if (want_k4) {
-#pragma unroll
-            for (int combo = 0; combo < 6; combo++) {
-                const int edge = combo >> 1, axis = combo & 1;
-                gface[edge * 3 + (1 - axis)] += s_k4[tid][combo][0];
-                gface[((edge + 1) % 3) * 3 + (1 - axis)] += s_k4[tid][combo][1];
-            }
-        }
+        if (!hoc_face_xy_finite(f) || hoc_face_back(f))
+            continue; /* cannot own a pixel; keeps a corrupted map from producing garbage */
+        float *gf = grad_faces + ((long)b * F + fi) * 9;
+        unsigned fl0 = 0u, fl1 = 0u;
+        /* edge 0: A = v0, B = v1, C = v2;  edge 1: A = v1, B = v2, C = v0;  edge 2: A = v2, B = v0, C = v1 */
+        fl0 |= hoc_k4_pixel_combo(f[0], f[1], f[3], f[4], f[6], f[7], 0, 0, px, py, M, I, g, eps, gf + 0, gf + 3);
+        fl1 |= hoc_k4_pixel_combo(f[0], f[1], f[3], f[4], f[6], f[7], 0, 1, px, py, M, I, g, eps, gf + 0, gf + 3);
+        fl0 |= hoc_k4_pixel_combo(f[3], f[4], f[6], f[7], f[0], f[1], 1, 0, px, py, M, I, g, eps, gf + 3, gf + 6);
+        fl1 |= hoc_k4_pixel_combo(f[3], f[4], f[6], f[7], f[0], f[1], 1, 1, px, py, M, I, g, eps, gf + 3, gf + 6);
+        fl0 |= hoc_k4_pixel_combo(f[6], f[7], f[0], f[1], f[3], f[4], 2, 0, px, py, M, I, g, eps, gf + 6, gf + 0);
+        fl1 |= hoc_k4_pixel_combo(f[6], f[7], f[0], f[1], f[3], f[4], 2, 1, px, py, M, I, g, eps, gf + 6, gf + 0);
+        s_flag[0][lx][ly] = (uint8_t)fl0;
+        s_flag[1][ly][lx] = (uint8_t)fl1;
     }
-    float *gf = grad_faces + ((long)b * F + fi) * 9;
+    __syncthreads();
+    /* flag tiles out, 32 contiguous bytes per warp: plane 1 rows are image rows, plane 0 rows are image columns */
+    uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * S;
+    uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * S;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int lr = r * 8 + ty;
+        const int yi = blockIdx.y * 32 + lr;
+        if (xi < S && yi < S)
+            fl_row[(long)yi * S + xi] = s_flag[1][lr][tx];
+        const int cx = blockIdx.x * 32 + lr, cy = blockIdx.y * 32 + tx;
+        if (cx < S && cy < S)
+            fl_col[(long)cx * S + cy] = s_flag[0][lr][tx];
+    }
+}
+
+/* backward_depth_map's per-face epilogue: grad_faces += J^T acc_d (z directly, x / y through the weights). */
+__global__ void __launch_bounds__(256)
+hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__restrict__ acc_d, long n_faces, int S,
+                            float *__restrict__ grad_faces)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_faces)
+        return;
+    const float *ad = acc_d + i * 3;
+    const float a0 = ad[0], a1 = ad[1], a2 = ad[2];
+    if (a0 == 0.0f && a1 == 0.0f && a2 == 0.0f)
+        return;
+    float f[9], inv[9], tmp[2];
 #pragma unroll
     for (int k = 0; k < 9; k++)
-        gf[k] = gface[k];
+        f[k] = __ldg(faces + i * 9 + k);
+    if (!hoc_face_xy_finite(f) || hoc_face_back(f))
+        return;
+    hoc_face_inv(f, S, inv);
+#pragma unroll
+    for (int l = 0; l < 2; l++)
+        tmp[l] = inv[l] / f[2] + inv[3 + l] / f[5] + inv[6 + l] / f[8];
+    float *gf = grad_faces + i * 9;
+    const float a[3] = {a0, a1, a2};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float zk = f[3 * k + 2];
+        gf[3 * k + 2] += a[k] / (zk * zk);
+        gf[3 * k + 0] += a[k] * tmp[0] * (float)S / 2.0f;
+        gf[3 * k + 1] += a[k] * tmp[1] * (float)S / 2.0f;
+    }
 }
 
 /*
- * Line pass.  grid (S, 2, B): one CTA per image column (axis 0) or row (axis 1).  The span of the line
- * where the incoming gradient is non-zero is staged in shared memory once (I = (alpha, r, g, b) and
- * dL/dI per pixel); every lane then runs one queued outward scan from shared memory.
+ * Line pass.  grid (S, 2, B): one CTA per image column (axis 0) or row (axis 1).
  */
-#define LN_THREADS 256
+#define LN_THREADS 128
+#define LN_WARPS (LN_THREADS / 32)
 __global__ void __launch_bounds__(LN_THREADS)
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
-                           const int *__restrict__ ext, const int *__restrict__ line_count,
-                           const int *__restrict__ emitters, float *__restrict__ grad_faces)
+                           const int *__restrict__ ext, const uint8_t *__restrict__ flags,
+                           float *__restrict__ grad_faces)
 {
-    /* per pixel of the span: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch (alpha included), then g_alpha:
+    /* dynamic shared memory: float4 s_line4[S] | float s_ga[S] | ushort s_queue[3 S]
+     * per pixel of the span: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch (alpha included), then g_alpha:
      * delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_ch Iin_ch g_ch -- one 16-byte shared load and three FMAs
      * per scanned pixel (<= 1 ulp of |P| from the reference's summation order, gradients carry 1e-3) */
     extern __shared__ float4 s_line4[];
+    __shared__ int s_wtot[LN_WARPS];
     const int d0 = blockIdx.x, axis = blockIdx.y, b = blockIdx.z;
-    const long line = ((long)b * 2 + axis) * S + d0;
-    const int n = min(line_count[line], 3 * S);
-    if (n <= 0)
-        return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int *e = ext + (long)b * 4 * S;
     const int lo = (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0];
     const int hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
     if (lo > hi)
         return; /* no incoming gradient anywhere on this line: every outward scan sums zeros */
     const int len = hi - lo + 1;
+    float *s_ga = reinterpret_cast<float *>(s_line4 + S);
+    unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_ga + S);
+    const int cap = 3 * S;
+
+    /* 1. the line's scans, compacted in position order: towards + from the front of the queue (length falls
+     *    with position), towards - from the back (length grows with position).  A scan that starts beyond the
+     *    span of non-zero gradient has nothing to sum and is dropped here. */
+    const uint8_t *fl = flags + (((long)b * 2 + axis) * S + d0) * S;
+    int nP = 0, nN = 0;
+    for (int base = 0; base < S; base += LN_THREADS) {
+        const int i = base + tid;
+        unsigned v = (i < S) ? fl[i] : 0u;
+        unsigned mP = v & (v >> 3) & 7u, mN = v & ~(v >> 3) & 7u;
+        if (i + 1 > hi)
+            mP = 0u;
+        if (i - 1 < lo)
+            mN = 0u;
+        const int mine = __popc(mP) | (__popc(mN) << 16);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_wtot[wid] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; w++) {
+            const int t = s_wtot[w];
+            if (w < wid)
+                before += t;
+            total += t;
+        }
+        const int excl = before + incl - mine;
+        int pP = nP + (excl & 0xffff), pN = nN + (excl >> 16);
+#pragma unroll
+        for (int ed = 0; ed < 3; ed++) {
+            if (mP & (1u << ed))
+                s_queue[pP++] = (unsigned short)(i | (ed << 11));
+            if (mN & (1u << ed))
+                s_queue[cap - 1 - (pN++)] = (unsigned short)(i | (ed << 11));
+        }
+        nP += total & 0xffff;
+        nN += total >> 16;
+        __syncthreads();
+    }
+    const int n = nP + nN;
+    if (n == 0)
+        return;
 
     HocBwdMaps M;
     M.idx = face_index_map + (long)b * S * S;
@@ -521,7 +510,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     M.use_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     M.use_rgb = (rgb != nullptr) && (g_rgb != nullptr);
 
-    for (int i = threadIdx.x; i < len; i += LN_THREADS) {
+    /* 2. stage the span */
+    for (int i = tid; i < len; i += LN_THREADS) {
         const int d1 = lo + i;
         const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
         float I[4];
@@ -536,49 +526,65 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         }
         s_line4[i] = make_float4(I[0] * g[0] + I[1] * g[1] + I[2] * g[2] + I[3] * g[3], g[1], g[2], g[3]);
         if (M.use_alpha)
-            reinterpret_cast<float *>(s_line4 + len)[i] = g[0];
+            s_ga[i] = g[0];
     }
     __syncthreads();
-    const float *s_ga = reinterpret_cast<const float *>(s_line4 + len);
 
-    const int *bucket = emitters + line * 3 * S;
-    for (int q = threadIdx.x; q < n; q += LN_THREADS) {
-        const int rec = bucket[q];
-        const int fi = rec & 0x1fffffff;
-        const int edge = (rec >> 29) & 3;
-        float f[9];
-        const float *src = faces + ((long)b * F + fi) * 9;
+    /* 3. one outward scan per lane */
+    const float scale = 2.0f / (float)S;
+    for (int q = tid; q < n; q += LN_THREADS) {
+        const int rec = (q < nP) ? s_queue[q] : s_queue[cap - 1 - (q - nP)];
+        const int d1_in = rec & 0x7ff, edge = rec >> 11;
+        const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+        const int fi = M.idx[(long)yin * S + xin];
+        float I_in[4] = {1.0f, 0.0f, 0.0f, 0.0f}; /* the inside pixel is owned, alpha = 1 */
+        if (M.use_rgb) {
 #pragma unroll
-        for (int k = 0; k < 9; k++)
-            f[k] = __ldg(src + k);
+            for (int k = 0; k < 3; k++)
+                I_in[1 + k] = rgb[hoc_rgb_off(layout, S, b, yin, xin, k)];
+        }
+        if (fi < 0)
+            continue; /* unreachable: the pixel pass flags owned pixels only */
+        const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
+        const float *src = faces + ((long)b * F + fi) * 9;
+        const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
+        const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
         HocK4Edge E;
-        hoc_k4_edge(f, S, edge, axis, &E);
+        hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
         float d1_cross;
-        int d1_in, d1_out;
-        if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out))
-            continue; /* unreachable: the face pass queued this column because it passed the same test */
-        float I_in[4];
-        hoc_load_I(M, axis == 0 ? d0 : d1_in, axis == 0 ? d1_in : d0, I_in);
-        const int d1_limit = (0 < E.dir) ? S - 1 : 0;
-        const int d1_from = max(max(min(d1_out, d1_limit), 0), lo);
-        const int d1_to = min(min(max(d1_out, d1_limit), S - 1), hi);
-        float gA = 0.0f, gB = 0.0f;
+        int d1_chk, d1_out;
+        if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_chk, &d1_out))
+            continue; /* unreachable: the pixel pass flagged this column because it passed the same test */
+        const int d1_from = (0 < E.dir) ? max(d1_out, lo) : lo;
+        const int d1_to = (0 < E.dir) ? hi : min(d1_out, hi);
         HocK4Col C;
         hoc_k4_col(&E, S, d0, d1_cross, &C);
-        for (int d1 = d1_from; d1 <= d1_to; d1++) {
-            const int i = d1 - lo;
-            const float4 pg = s_line4[i];
-            float delta = pg.x - (I_in[1] * pg.y + I_in[2] * pg.z + I_in[3] * pg.w);
+        const float cA = C.cA * scale, cB = C.cB * scale;
+        const float peps = eps, neps = -eps;
+        float gA = 0.0f, gB = 0.0f;
+        float u = (float)d1_from - d1_cross;
+        const float4 *sp = s_line4 + (d1_from - lo);
+        const float *sa = s_ga + (d1_from - lo);
+        for (int k = d1_to - d1_from; k >= 0; k--, sp++, sa++, u += 1.0f) {
+            const float4 pg = *sp;
+            float delta = pg.x - __fmaf_rn(I_in[3], pg.w, __fmaf_rn(I_in[2], pg.z, I_in[1] * pg.y));
             if (M.use_alpha)
-                delta -= I_in[0] * s_ga[i];
-            if (!(delta <= 0.0f))
-                hoc_k4_accum_col(&C, d1, eps, delta, &gA, &gB);
+                delta -= *sa;
+            if (!(delta <= 0.0f)) {
+                float dA = cA * u, dB = cB * u;
+                dA += (0.0f < dA) ? peps : neps;
+                dB += (0.0f < dB) ? peps : neps;
+                if (C.hasA)
+                    gA -= HOC_FAST_DIV(delta, dA);
+                if (C.hasB)
+                    gB -= HOC_FAST_DIV(delta, dB);
+            }
         }
         float *gf = grad_faces + ((long)b * F + fi) * 9;
         if (gA != 0.0f)
-            atomicAdd(gf + edge * 3 + (1 - axis), gA);
+            atomicAdd(gf + ia * 3 + (1 - axis), gA);
         if (gB != 0.0f)
-            atomicAdd(gf + ((edge + 1) % 3) * 3 + (1 - axis), gB);
+            atomicAdd(gf + ib * 3 + (1 - axis), gB);
     }
 }
 
@@ -625,7 +631,11 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
 
-    cudaError_t e = cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, st);
+    cudaError_t e = cudaSuccess;
+    if (want_depth)
+        e = cudaMemsetAsync(w.acc_d, 0, w.acc_bytes, st);
+    if (e == cudaSuccess && grad_faces != nullptr) /* accumulated with atomics by the pixel and line passes */
+        e = cudaMemsetAsync(grad_faces, 0, sizeof(float) * 9 * (size_t)B * F, st);
     if (e == cudaSuccess && k4) { /* hi rows = -1, lo rows (every second row of S ints) = 0x7f7f7f7f */
         e = cudaMemsetAsync(w.ext, 0xff, sizeof(int) * 4 * (size_t)B * S, st);
         if (e == cudaSuccess)
@@ -640,30 +650,34 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     {
         dim3 pg((S + 31) / 32, (S + 31) / 32, B);
         float *gt = (grad_rgb != nullptr) ? grad_textures : nullptr;
-        if (ts == 2)
-            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
-                       (hoc_raster_bwd_pixel_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
-                           faces, face_index_map, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_,
-                           eps, layout, k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
+#define HOC_PIXEL_LAUNCH(TS2, K4)                                                                                    \
+    HOC_LAUNCH(K4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BWD_PIXEL, st,                                           \
+               (hoc_raster_bwd_pixel_kernel<TS2, K4><<<pg, dim3(32, 8), 0, st>>>(                                     \
+                   faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
+                   eps, layout, use_alpha, tex_grad_mode, w.ext, want_depth ? w.acc_d : nullptr, w.flags, grad_faces,  \
+                   gt)))
+        if (ts == 2 && k4)
+            HOC_PIXEL_LAUNCH(true, true);
+        else if (ts == 2)
+            HOC_PIXEL_LAUNCH(true, false);
+        else if (k4)
+            HOC_PIXEL_LAUNCH(false, true);
         else
-            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
-                       (hoc_raster_bwd_pixel_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
-                           faces, face_index_map, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_,
-                           eps, layout, k4 ? 1 : 0, tex_grad_mode, w.ext, w.owned, want_depth ? w.acc_d : nullptr, gt)));
+            HOC_PIXEL_LAUNCH(false, false);
+#undef HOC_PIXEL_LAUNCH
         HOC_CHECK_LAUNCH("hoc_raster_bwd_pixel_kernel");
     }
     if (grad_faces == nullptr)
         return HOC_OK;
-    {
-        dim3 grid((F + BW_THREADS - 1) / BW_THREADS, B);
+    if (want_depth) {
+        const long nf = (long)B * F;
         HOC_LAUNCH(HOC_K_RASTER_BACKWARD, st,
-                   (hoc_raster_bwd_face_kernel<<<grid, BW_THREADS, 0, st>>>(
-                       faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, want_depth ? 1 : 0,
-                       w.owned, w.acc_d, w.line_count, w.emitters, grad_faces)));
-        HOC_CHECK_LAUNCH("hoc_raster_bwd_face_kernel");
+                   (hoc_raster_bwd_depth_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(faces, w.acc_d, nf, S,
+                                                                                              grad_faces)));
+        HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
     }
     if (k4) {
-        const size_t smem = sizeof(float) * 5 * (size_t)S + 16;
+        const size_t smem = (sizeof(float) * 5 + sizeof(unsigned short) * 3) * (size_t)S;
         if (smem > 48 * 1024) {
             e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) {
@@ -675,8 +689,8 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         dim3 grid(S, 2, B);
         HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
                    (hoc_raster_bwd_line_kernel<<<grid, LN_THREADS, smem, st>>>(
-                       faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,
-                       w.emitters, grad_faces)));
+                       faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.flags,
+                       grad_faces)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_line_kernel");
     }
     return HOC_OK;

@@ -155,12 +155,13 @@ struct HocK4Edge {
     int d0_to;    /* last one (inclusive); empty when d0_to < d0_from */
 };
 
-HOC_HD void hoc_k4_edge(const float *f, int S, int edge, int axis, HocK4Edge *E)
+/* (ax, ay), (bx, by), (cx, cy): the three vertices in NDC, A = first vertex of the edge. */
+HOC_HD void hoc_k4_edge_pts(float ax_ndc, float ay_ndc, float bx_ndc, float by_ndc, float cx_ndc, float cy_ndc, int S,
+                            int axis, HocK4Edge *E)
 {
-    const int ia = edge, ib = (edge + 1) % 3, ic = (edge + 2) % 3;
-    const float ax = hoc_ndc_to_pix(f[3 * ia], S), ay = hoc_ndc_to_pix(f[3 * ia + 1], S);
-    const float bx = hoc_ndc_to_pix(f[3 * ib], S), by = hoc_ndc_to_pix(f[3 * ib + 1], S);
-    const float cx = hoc_ndc_to_pix(f[3 * ic], S), cy = hoc_ndc_to_pix(f[3 * ic + 1], S);
+    const float ax = hoc_ndc_to_pix(ax_ndc, S), ay = hoc_ndc_to_pix(ay_ndc, S);
+    const float bx = hoc_ndc_to_pix(bx_ndc, S), by = hoc_ndc_to_pix(by_ndc, S);
+    const float cx = hoc_ndc_to_pix(cx_ndc, S), cy = hoc_ndc_to_pix(cy_ndc, S);
     if (axis == 0) {
         E->a0 = ax; E->a1 = ay; E->b0 = bx; E->b1 = by; E->c0 = cx; E->c1 = cy;
         E->dir = (E->a0 < E->b0) ? -1 : 1;
@@ -174,6 +175,12 @@ HOC_HD void hoc_k4_edge(const float *f, int S, int edge, int axis, HocK4Edge *E)
      * still visits column 0.  Clamps only keep the conversions in range. */
     E->d0_from = (int)fminf(lo, (float)S);
     E->d0_to = (int)fmaxf(hi, -2.0f);
+}
+
+HOC_HD void hoc_k4_edge(const float *f, int S, int edge, int axis, HocK4Edge *E)
+{
+    const int ia = edge, ib = (edge + 1) % 3, ic = (edge + 2) % 3;
+    hoc_k4_edge_pts(f[3 * ia], f[3 * ia + 1], f[3 * ib], f[3 * ib + 1], f[3 * ic], f[3 * ic + 1], S, axis, E);
 }
 
 /* Column d0 of an (edge, axis): crossing of AB, the pixel just inside and just outside.

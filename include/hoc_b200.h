@@ -53,7 +53,7 @@ const char *hoc_last_error(void);
 #define HOC_K_RASTER_ZBUF 0
 #define HOC_K_RASTER_RESOLVE 1
 #define HOC_K_GRAD_EXTENT 2 /* retired: merged into HOC_K_RASTER_BWD_PIXEL */
-#define HOC_K_RASTER_BACKWARD 3 /* hoc_raster_bwd_face_kernel */
+#define HOC_K_RASTER_BACKWARD 3 /* hoc_raster_bwd_depth_kernel (per-face epilogue of backward_depth_map) */
 #define HOC_K_WARP_PHOTO_FWD 4
 #define HOC_K_WARP_PHOTO_BWD 5
 #define HOC_K_WARP 6
@@ -69,6 +69,7 @@ const char *hoc_last_error(void);
 #define HOC_K_FLOW_VERTICES_BWD 16
 #define HOC_K_MANO_FWD 17
 #define HOC_K_MANO_BWD 18
+#define HOC_K_RASTER_BWD_PIXEL_K4 19 /* hoc_raster_bwd_pixel_kernel<.., true>: pixel pass + pseudo-gradient */
 #define HOC_KERNEL_COUNT 24
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
@@ -120,8 +121,8 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
  *   use_alpha        1 when the forward produced alpha (return_alpha), else 0
  *   grad_faces       [B,F,3,3] out (fully overwritten) or NULL to skip the geometry gradient
  *   grad_textures    [B,F,ts,ts,ts,3] out (fully overwritten) or NULL to skip it
- *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes (dominated by the outward-scan queue,
- *                    24 S^2 B bytes worst case, of which only the used part is ever touched)
+ *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes (line spans, per-face depth sums and two
+ *                    outward-scan flag bytes per pixel)
  */
 /* tex_grad_mode: CUBE = grad_textures is [B,F,ts,ts,ts,3] (the reference's backward_textures);
  * VERTEX = the cubes were built by hoc_mesh_gather from three vertex values per face (ts == 2): grad_textures

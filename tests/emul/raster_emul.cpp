@@ -275,56 +275,96 @@ extern "C" void emul_raster_backward(const float *faces, const int32_t *face_ind
                     gf[3 * k + 1] = acc_d[k] * tmp[1] * (float)S / 2.0f;
                 }
             }
-            Maps M = {idx, rgb, g_rgb, g_alpha, S, layout, b, use_alpha && g_alpha, rgb && g_rgb};
-            if (!(M.use_alpha || M.use_rgb))
-                continue;
-            const int *e = ext.data() + (size_t)b * 4 * S;
-            for (int combo = 0; combo < 6; combo++) {
-                const int edge = combo >> 1, axis = combo & 1;
-                HocK4Edge E;
-                hoc_k4_edge(f, S, edge, axis, &E);
-                float gA = 0.0f, gB = 0.0f;
-                for (int d0 = E.d0_from; d0 <= E.d0_to; d0++) {
+        }
+    if (!grad_faces)
+        return;
+    /* Pseudo-gradient, decomposed like the kernels: (1) from every covered pixel, its own term of the inward scan
+     * of each (edge, axis) column it lies on, plus a flag byte when it is the pixel just inside the edge;
+     * (2) per line, the flagged outward scans clipped to the span of non-zero incoming gradient. */
+    std::vector<uint8_t> flags((size_t)B * 2 * S * S, 0);
+    for (int b = 0; b < B; b++) {
+        const int32_t *idx = face_index_map + (long)b * S * S;
+        Maps M = {idx, rgb, g_rgb, g_alpha, S, layout, b, use_alpha && g_alpha, rgb && g_rgb};
+        if (!(M.use_alpha || M.use_rgb))
+            continue;
+        for (int yi = 0; yi < S; yi++)
+            for (int xi = 0; xi < S; xi++) {
+                const int fi = idx[(long)yi * S + xi];
+                if (fi < 0)
+                    continue;
+                const float *f = faces + ((long)b * F + fi) * 9;
+                if (!hoc_face_xy_finite(f) || hoc_face_back(f))
+                    continue;
+                float *gf = grad_faces + ((long)b * F + fi) * 9;
+                for (int combo = 0; combo < 6; combo++) {
+                    const int edge = combo >> 1, axis = combo & 1;
+                    HocK4Edge E;
+                    hoc_k4_edge(f, S, edge, axis, &E);
+                    const int d0 = axis == 0 ? xi : yi, d1p = axis == 0 ? yi : xi;
+                    if (d0 < E.d0_from || d0 > E.d0_to)
+                        continue;
                     float d1_cross;
                     int d1_in, d1_out;
                     if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out))
                         continue;
-                    const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
-                    const int xout = axis == 0 ? d0 : d1_out, yout = axis == 0 ? d1_out : d0;
-                    float I_in[4], I_out[4];
-                    load_I(M, xin, yin, I_in);
-                    load_I(M, xout, yout, I_out);
-                    if (idx[(long)yin * S + xin] == fi) {
-                        const int d1_limit = (0 < E.dir) ? S - 1 : 0;
-                        int d1_from = std::max(std::min(d1_out, d1_limit), 0);
-                        int d1_to = std::min(std::max(d1_out, d1_limit), S - 1);
-                        const int lo = axis == 0 ? e[2 * S + d0] : e[0 * S + d0];
-                        const int hi = axis == 0 ? e[3 * S + d0] : e[1 * S + d0];
-                        d1_from = std::max(d1_from, lo);
-                        d1_to = std::min(d1_to, hi);
+                    if (d1_in == d1p)
+                        flags[(((size_t)b * 2 + axis) * S + d0) * S + d1p] |=
+                            (uint8_t)((1u << edge) | ((0 < E.dir) ? (8u << edge) : 0u));
+                    const int lim = hoc_k4_inward_limit(&E, d0);
+                    const int d1_from = std::max(std::min(d1_in, lim), 0);
+                    const int d1_to = std::min(std::max(d1_in, lim), S - 1);
+                    if (d1p < d1_from || d1p > d1_to)
+                        continue;
+                    float I_out[4];
+                    load_I(M, axis == 0 ? d0 : d1_out, axis == 0 ? d1_out : d0, I_out);
+                    const float delta = delta_at(M, xi, yi, I_out);
+                    if (delta <= 0.0f)
+                        continue;
+                    float gA = 0.0f, gB = 0.0f;
+                    hoc_k4_accum(&E, S, d0, d1p, d1_cross, eps, delta, &gA, &gB);
+                    gf[edge * 3 + (1 - axis)] += gA;
+                    gf[((edge + 1) % 3) * 3 + (1 - axis)] += gB;
+                }
+            }
+        const int *e = ext.data() + (size_t)b * 4 * S;
+        for (int axis = 0; axis < 2; axis++)
+            for (int d0 = 0; d0 < S; d0++) {
+                const int lo = axis == 0 ? e[2 * S + d0] : e[0 * S + d0];
+                const int hi = axis == 0 ? e[3 * S + d0] : e[1 * S + d0];
+                if (lo > hi)
+                    continue;
+                const uint8_t *fl = flags.data() + (((size_t)b * 2 + axis) * S + d0) * S;
+                for (int i = 0; i < S; i++)
+                    for (int edge = 0; edge < 3; edge++) {
+                        if (!(fl[i] & (1u << edge)))
+                            continue;
+                        const bool pos = fl[i] & (8u << edge);
+                        if (pos ? (i + 1 > hi) : (i - 1 < lo))
+                            continue;
+                        const int xin = axis == 0 ? d0 : i, yin = axis == 0 ? i : d0;
+                        const int fi = idx[(long)yin * S + xin];
+                        const float *f = faces + ((long)b * F + fi) * 9;
+                        HocK4Edge E;
+                        hoc_k4_edge(f, S, edge, axis, &E);
+                        float d1_cross;
+                        int d1_in, d1_out;
+                        if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_in, &d1_out) || d1_in != i || (0 < E.dir) != pos)
+                            continue; /* unreachable */
+                        float I_in[4];
+                        load_I(M, xin, yin, I_in);
+                        const int d1_from = pos ? std::max(d1_out, lo) : lo;
+                        const int d1_to = pos ? hi : std::min(d1_out, hi);
+                        float gA = 0.0f, gB = 0.0f;
                         for (int d1 = d1_from; d1 <= d1_to; d1++) {
-                            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-                            const float delta = delta_at(M, xi, yi, I_in);
+                            const float delta = delta_at(M, axis == 0 ? d0 : d1, axis == 0 ? d1 : d0, I_in);
                             if (delta <= 0.0f)
                                 continue;
                             hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
                         }
+                        float *gf = grad_faces + ((long)b * F + fi) * 9;
+                        gf[edge * 3 + (1 - axis)] += gA;
+                        gf[((edge + 1) % 3) * 3 + (1 - axis)] += gB;
                     }
-                    const int lim = hoc_k4_inward_limit(&E, d0);
-                    const int d1_from = std::max(std::min(d1_in, lim), 0);
-                    const int d1_to = std::min(std::max(d1_in, lim), S - 1);
-                    for (int d1 = d1_from; d1 <= d1_to; d1++) {
-                        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-                        if (idx[(long)yi * S + xi] != fi)
-                            continue;
-                        const float delta = delta_at(M, xi, yi, I_out);
-                        if (delta <= 0.0f)
-                            continue;
-                        hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
-                    }
-                }
-                gf[edge * 3 + (1 - axis)] += gA;
-                gf[((edge + 1) % 3) * 3 + (1 - axis)] += gB;
             }
-        }
+    }
 }

@@ -39,7 +39,8 @@ def test_every_entry_point_cites_the_reference():
 def test_argument_errors_are_codes_not_crashes():
     L = _lib.lib()
     assert L.hoc_raster_forward_workspace_bytes(2, 10, 16) == 2 * 16 * 16 * 8
-    assert L.hoc_raster_backward_workspace_bytes(2, 10, 16) >= 2 * 2 * 16 * 48 * 4
+    # line spans (4 ints per line) + per-face depth sums + two flag bytes per pixel
+    assert L.hoc_raster_backward_workspace_bytes(2, 10, 16) >= 2 * 4 * 16 * 4 + 2 * 10 * 3 * 4 + 2 * 2 * 16 * 16
     bg = (ctypes.c_float * 3)(0, 0, 0)
     # image size out of range / missing index map: rejected before anything touches the device
     code = L.hoc_raster_forward(None, None, 1, 0, 4096, 0, 0.1, 100.0, 1e-3, bg, None, 0, None, None, None, None, None,
