@@ -296,9 +296,12 @@ def run_native(args, rank, world, local_rank):
     algo = {
         "raster_zbuf": PAIRS * F2 * 36 + npx * 8,                       # faces in, 8-byte depth/face key per pixel
         "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 96) + npx * 24,   # key, faces+textures, rgb12+alpha4+depth4+idx4
-        # pixel pass: idx, grad_rgb, weights, depth in; faces in; grad of the 9 vertex values out
-        "raster_bwd_pixel": npx * (4 + 12 + 12 + 4) + PAIRS * F2 * (36 + 36),
-        # ... with the pseudo-gradient: + rgb in, two flag bytes per pixel out, grad_faces (memset + update)
+        # scan pass (streaming): idx + grad_rgb in; covered-pixel list (4 B per covered pixel, counted as idx-sized)
+        # and two zeroed flag bytes per pixel out
+        "raster_bwd_pixel": npx * (4 + 12 + 2),
+        # cover pass, texture gradient only: per listed pixel idx, grad_rgb, weights, depth; faces in; 9 sums per face out
+        "raster_bwd_cover": npx * (4 + 12 + 12 + 4) + PAIRS * F2 * (36 + 36),
+        # cover pass with the pseudo-gradient: + rgb in, flag bytes out, grad_faces (memset + update)
         "raster_bwd_pixel_k4": npx * (4 + 12 + 12 + 4 + 12 + 2) + PAIRS * F2 * (36 + 36 + 36),
         "raster_backward": PAIRS * F2 * (36 + 12 + 36),                  # depth epilogue (only with dL/ddepth)
         "raster_bwd_line": npx * (12 + 12 + 4 + 2) + PAIRS * F2 * 36,    # line pass: rgb, grad_rgb, idx, flags once; grad_faces update
@@ -319,7 +322,8 @@ def run_native(args, rank, world, local_rank):
                       "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
     table.sort(key=lambda r: -r["share_of_step"])
     kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve_kernel",
-             "raster_bwd_pixel": "hoc_raster_bwd_pixel_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_pixel_kernel<K4>", "raster_backward": "hoc_raster_bwd_depth_kernel",
+             "raster_bwd_pixel": "hoc_raster_bwd_scan_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel<K4>",
+             "raster_bwd_cover": "hoc_raster_bwd_cover_kernel", "raster_backward": "hoc_raster_bwd_depth_kernel",
              "raster_bwd_line": "hoc_raster_bwd_line_kernel", "warp_photo_fwd": "hoc_warp_photo_forward_kernel",
              "warp_photo_bwd": "hoc_warp_photo_backward_kernel", "flow_finalize": "hoc_flow_finalize_kernel",
              "flow_finalize_bwd": "hoc_flow_finalize_backward_kernel", "mesh_gather": "hoc_mesh_gather_kernel",
@@ -331,10 +335,11 @@ def run_native(args, rank, world, local_rank):
         with open(tpath) as f:
             traffic_tab = json.load(f)
     # `roofline`: the kernel with the largest share of the step (table[0]); `roofline_raster_backward`: the kernel
-    # BASELINE.json's north_star names -- two launches here (pixel pass, line pass), reported together with the
+    # BASELINE.json's north_star names -- three launches here (scan, cover, line pass), reported together with the
     # bytes of the whole backward of one render counted once
     dom = next((r for r in table if r["algorithmic_bytes_per_launch"]), None)
-    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel_k4", "raster_backward", "raster_bwd_line")]
+    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel", "raster_bwd_pixel_k4", "raster_backward",
+                                               "raster_bwd_line")]
     bwd_bytes = npx * (4 + 12 + 12) + PAIRS * F2 * (36 + 36 + 36)
     bwd_ms = sum(r["avg_ms"] for r in bwd)
     traffic = traffic_tab.get(kname[dom["kernel"]].split("<")[0]) if dom else None
@@ -372,7 +377,7 @@ def run_native(args, rank, world, local_rank):
             "achieved": (bwd_bytes / (bwd_ms * 1e-3) / 1e9) if bwd and bwd_ms > 0 else None, "peak": peak, "unit": "GB/s",
             "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak) if bwd and bwd_ms > 0 else None,
             "traffic": sum(traffic_tab.get(kname[r["kernel"]].split("<")[0], 0) for r in bwd) or None,
-            "note": "pixel pass + line pass of the render whose geometry gradient is needed (the per-face pass of earlier builds is gone: the pseudo-gradient runs from the pixels)"},
+            "note": "scan + cover + line pass of the render whose geometry gradient is needed (no per-face pass: the pseudo-gradient runs from the covered pixels)"},
         "kernels": table,
     }
     return out

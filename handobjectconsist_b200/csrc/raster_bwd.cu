@@ -37,18 +37,22 @@
 #define EXT_COL_LO 2
 #define EXT_COL_HI 3
 
-/* Workspace carved by hoc_raster_backward (16-byte aligned regions):
+/* Workspace carved by hoc_raster_backward (256-byte aligned regions):
  *   ext        int   [B][4][S]     {row_lo, row_hi, col_lo, col_hi}: span of non-zero incoming gradient
+ *   cov_count  int   [B]           covered pixels listed per sample                      (zero-filled)
  *   acc_d      float [B][F][3]     sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
+ *   cov_list   int   [B][S*S]      the covered pixels (yi * S + xi) that have work, in tile order
  *   flags      uint8 [B][2][S][S]  outward-scan flags; plane 0 (column scans) is stored [x][y], plane 1 (row
  *                                  scans) [y][x], so a line's bytes are contiguous.  Bit e: edge e of the face
  *                                  owning this pixel starts an outward scan here; bit 3+e: it runs towards +.
- *                                  Every byte is written by the pixel pass (no zero-fill). */
+ *                                  Zero-filled by the scan pass, set by the cover pass. */
 struct HocBwdWorkspace {
     int *ext;
+    int *cov_count;
     float *acc_d;
+    int *cov_list;
     uint8_t *flags;
-    size_t acc_bytes;
+    size_t count_bytes, acc_bytes;
     size_t total;
 };
 
@@ -60,9 +64,14 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     char *p = (char *)base;
     w.ext = (int *)(p + off);
     off = up(off + sizeof(int) * 4 * (size_t)B * S);
-    w.acc_d = (float *)(p + off);
+    w.cov_count = (int *)(p + off);
+    w.count_bytes = up(sizeof(int) * (size_t)B);
+    off += w.count_bytes;
+    w.acc_d = (float *)(p + off); /* directly after cov_count: one memset covers both */
     w.acc_bytes = sizeof(float) * 3 * (size_t)B * F;
     off = up(off + w.acc_bytes);
+    w.cov_list = (int *)(p + off);
+    off = up(off + sizeof(int) * (size_t)B * S * S);
     w.flags = (uint8_t *)(p + off);
     off = up(off + 2 * (size_t)B * S * S);
     w.total = off;
@@ -144,38 +153,25 @@ __device__ __forceinline__ unsigned hoc_k4_pixel_combo(float ax, float ay, float
 }
 
 /*
- * Pixel pass.  Block (32, 8) covers a 32 x 32 pixel tile (4 rows per thread).
+ * Scan pass.  Block (32, 8) covers a 32 x 32 pixel tile (4 rows per thread).  Pure streaming: reads
+ * face_index_map and the incoming gradients once, writes the line spans, the list of covered pixels that have
+ * work (all of them when the pseudo-gradient is wanted, else those with a texture / depth gradient) and, for the
+ * pseudo-gradient, zeroes the tile's flag bytes.  One global atomic per CTA reserves the tile's list slots.
  */
-template <bool TS2, bool K4>
+template <bool K4>
 __global__ void __launch_bounds__(256)
-hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
-                            const float *__restrict__ rgb, const float *__restrict__ weight_map,
-                            const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
-                            const float *__restrict__ g_alpha, const float *__restrict__ g_depth, int F, int S, int ts,
-                            float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
-                            int *__restrict__ ext, float *__restrict__ acc_d, uint8_t *__restrict__ flags,
-                            float *__restrict__ grad_faces, float *__restrict__ grad_textures)
+hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb,
+                           const float *__restrict__ g_alpha, int S, int layout, int list_all, int *__restrict__ ext,
+                           int *__restrict__ cov_count, int *__restrict__ cov_list, uint8_t *__restrict__ flags)
 {
     __shared__ int s_lo[8][32];
     __shared__ int s_hi[8][32];
-    __shared__ unsigned short s_cov[1024]; /* covered pixels of the tile: ly << 5 | lx */
-    __shared__ __align__(16) uint8_t s_flag[2][32][36];  /* [0][lx][ly] (transposed), [1][ly][lx] */
-    __shared__ int s_ncov;
+    __shared__ int s_cnt[33]; /* per warp-row (r * 8 + ty) count, then exclusive prefix; [32] = tile base */
     const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * 32 + tx;
     const int b = blockIdx.z;
     const int xi = blockIdx.x * 32 + tx;
     int *e = ext + (long)b * 4 * S;
-    const int tex_n = ts * ts * ts * 3;
     int c_lo = 0x7f7f7f7f, c_hi = -1;
-    if (K4) {
-        if (tid == 0)
-            s_ncov = 0;
-        for (int i = tid; i < 2 * 32 * 36 / 4; i += 256)
-            reinterpret_cast<uint32_t *>(&s_flag[0][0][0])[i] = 0u;
-        __syncthreads();
-    }
-    /* issue the loads of all four rows first (memory-level parallelism), then do the per-pixel work */
     float gr[4][3], ga[4];
     int fis[4];
 #pragma unroll
@@ -196,105 +192,14 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
             fis[r] = face_index_map[((long)b * S + yi) * S + xi];
         }
     }
-    const bool want_tex = (grad_textures != nullptr) && (g_rgb != nullptr);
-    const bool want_depth = (acc_d != nullptr) && (g_depth != nullptr);
+    unsigned want[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int yi = blockIdx.y * 32 + r * 8 + ty;
         const bool nz = !(gr[r][0] == 0.0f) || !(gr[r][1] == 0.0f) || !(gr[r][2] == 0.0f) || !(ga[r] == 0.0f);
-        const int fi = fis[r];
-        if (K4) { /* ordered compaction of the covered pixels of this warp row */
-            const unsigned cm = __ballot_sync(HOC_FULL_MASK, fi >= 0);
-            int base = 0;
-            if (tx == 0 && cm != 0)
-                base = atomicAdd(&s_ncov, __popc(cm));
-            base = __shfl_sync(HOC_FULL_MASK, base, 0);
-            if (fi >= 0)
-                s_cov[base + __popc(cm & ((1u << tx) - 1u))] = (unsigned short)(((r * 8 + ty) << 5) | tx);
-        }
-        if (fi >= 0) {
-            if ((want_tex && nz) || want_depth) {
-                float f[9], w[3], zp;
-                const float *src = faces + ((long)b * F + fi) * 9;
-                if (weight_map != nullptr && depth_map != nullptr) {
-                    /* the forward saved its weights and depth: only the three vertex depths are needed */
-                    const float *wm = weight_map + (((long)b * S + yi) * S + xi) * 3;
-                    w[0] = wm[0];
-                    w[1] = wm[1];
-                    w[2] = wm[2];
-                    zp = depth_map[hoc_plane_off(layout, S, b, yi, xi)];
-                    f[2] = __ldg(src + 2);
-                    f[5] = __ldg(src + 5);
-                    f[8] = __ldg(src + 8);
-                } else { /* recompute with the forward's functions (bit-identical) */
-                    float inv[9];
-#pragma unroll
-                    for (int k = 0; k < 9; k++)
-                        f[k] = __ldg(src + k);
-                    hoc_face_inv(f, S, inv);
-                    hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
-                }
-                if (want_depth) {
-                    const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
-                    if (gz != 0.0f) {
-                        float *ad = acc_d + ((long)b * F + fi) * 3;
-#pragma unroll
-                        for (int k = 0; k < 3; k++)
-                            atomicAdd(ad + k, gz * w[k]);
-                    }
-                }
-                if (want_tex && nz && tex_mode == HOC_TEX_GRAD_VERTEX) {
-                    /* textures are the multilinear extension of three vertex values (T[i,j,k] = i c0 + j c1 +
-                     * k c2, ts == 2): d rgb / d c_k = t_k, so nine sums per face instead of twenty-four */
-                    float *gt = grad_textures + ((long)b * F + fi) * 9;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, 2, eps);
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const float v = t * gr[r][c];
-                            if (v != 0.0f)
-                                atomicAdd(gt + 3 * k + c, v);
-                        }
-                    }
-                } else if (want_tex && nz) {
-                    float *gt = grad_textures + ((long)b * F + fi) * tex_n;
-                    float tf[3];
-                    int ti[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
-                        ti[k] = hoc_tex_cell(t, ts);
-                        tf[k] = t - (float)ti[k];
-                    }
-#pragma unroll
-                    for (int pn = 0; pn < 8; pn++) {
-                        float ww = 1.0f;
-                        int isc = 0;
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            if (((pn >> k) & 1) == 0) {
-                                ww *= 1.0f - tf[k];
-                                isc = isc * ts + ti[k];
-                            } else {
-                                ww *= tf[k];
-                                isc = isc * ts + ti[k] + 1;
-                            }
-                        }
-                        if (!TS2 && ts == 1)
-                            isc = 0;
-                        if (ww != 0.0f) {
-#pragma unroll
-                            for (int c = 0; c < 3; c++) {
-                                const float v = ww * gr[r][c];
-                                if (v != 0.0f)
-                                    atomicAdd(gt + isc * 3 + c, v);
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        want[r] = __ballot_sync(HOC_FULL_MASK, fis[r] >= 0 && (list_all || nz));
+        if (tx == 0)
+            s_cnt[r * 8 + ty] = __popc(want[r]);
         if (K4) {
             const unsigned m = __ballot_sync(HOC_FULL_MASK, nz);
             if (m != 0 && tx == 0) {
@@ -307,26 +212,196 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
             }
         }
     }
-    if (!K4)
-        return;
-    s_lo[ty][tx] = c_lo;
-    s_hi[ty][tx] = c_hi;
+    if (K4) {
+        s_lo[ty][tx] = c_lo;
+        s_hi[ty][tx] = c_hi;
+    }
     __syncthreads();
-    if (ty == 0 && xi < S) {
+    if (ty == 0) { /* exclusive prefix over the 32 warp-rows + one atomic for the tile */
+        const int mine = s_cnt[tx];
+        int incl = mine;
 #pragma unroll
-        for (int r = 1; r < 8; r++) {
-            c_lo = min(c_lo, s_lo[r][tx]);
-            c_hi = max(c_hi, s_hi[r][tx]);
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+            if (tx >= o)
+                incl += t;
         }
-        if (c_hi >= 0) {
-            atomicMin(&e[EXT_COL_LO * S + xi], c_lo);
-            atomicMax(&e[EXT_COL_HI * S + xi], c_hi);
+        s_cnt[tx] = incl - mine;
+        if (tx == 31)
+            s_cnt[32] = (incl > 0) ? atomicAdd(cov_count + b, incl) : 0;
+        if (K4 && xi < S) {
+#pragma unroll
+            for (int r = 1; r < 8; r++) {
+                c_lo = min(c_lo, s_lo[r][tx]);
+                c_hi = max(c_hi, s_hi[r][tx]);
+            }
+            if (c_hi >= 0) {
+                atomicMin(&e[EXT_COL_LO * S + xi], c_lo);
+                atomicMax(&e[EXT_COL_HI * S + xi], c_hi);
+            }
         }
     }
+    __syncthreads();
+    int *list = cov_list + (long)b * S * S + s_cnt[32];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int lr = r * 8 + ty;
+        const int yi = blockIdx.y * 32 + lr;
+        if ((want[r] >> tx) & 1u)
+            list[s_cnt[lr] + __popc(want[r] & ((1u << tx) - 1u))] = yi * S + xi;
+        if (K4) { /* the tile's flag bytes, 32 contiguous bytes per warp in both planes */
+            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * S;
+            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * S;
+            if (xi < S && yi < S)
+                fl_row[(long)yi * S + xi] = 0;
+            const int cx = blockIdx.x * 32 + lr, cy = blockIdx.y * 32 + tx;
+            if (cx < S && cy < S)
+                fl_col[(long)cx * S + cy] = 0;
+        }
+    }
+}
 
-    /* Phase 2: the pseudo-gradient from the covered pixels of the tile, one pixel per thread. */
+/* Texture (backward_textures) and depth (backward_depth_map) gradient of one covered pixel. */
+template <bool TS2>
+__device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ faces,
+                                                    const float *__restrict__ weight_map,
+                                                    const float *__restrict__ depth_map,
+                                                    const float *__restrict__ g_rgb,
+                                                    const float *__restrict__ g_depth, int b, int fi, int xi, int yi,
+                                                    int F, int S, int ts, float near_, float far_, float eps, int layout,
+                                                    int tex_mode, float *__restrict__ acc_d,
+                                                    float *__restrict__ grad_textures)
+{
+    const bool want_tex = (grad_textures != nullptr) && (g_rgb != nullptr);
+    const bool want_depth = (acc_d != nullptr) && (g_depth != nullptr);
+    float gr[3] = {0.0f, 0.0f, 0.0f};
+    if (want_tex) {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            gr[c] = g_rgb[hoc_rgb_off(layout, S, b, yi, xi, c)];
+    }
+    const bool nz = !(gr[0] == 0.0f) || !(gr[1] == 0.0f) || !(gr[2] == 0.0f);
+    if (!((want_tex && nz) || want_depth))
+        return;
+    const int tex_n = ts * ts * ts * 3;
+    float f[9], w[3], zp;
+    const float *src = faces + ((long)b * F + fi) * 9;
+    if (weight_map != nullptr && depth_map != nullptr) {
+        /* the forward saved its weights and depth: only the three vertex depths are needed */
+        const float *wm = weight_map + (((long)b * S + yi) * S + xi) * 3;
+        w[0] = wm[0];
+        w[1] = wm[1];
+        w[2] = wm[2];
+        zp = depth_map[hoc_plane_off(layout, S, b, yi, xi)];
+        f[2] = __ldg(src + 2);
+        f[5] = __ldg(src + 5);
+        f[8] = __ldg(src + 8);
+    } else { /* recompute with the forward's functions (bit-identical) */
+        float inv[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            f[k] = __ldg(src + k);
+        hoc_face_inv(f, S, inv);
+        hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
+    }
+    if (want_depth) {
+        const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
+        if (gz != 0.0f) {
+            float *ad = acc_d + ((long)b * F + fi) * 3;
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                atomicAdd(ad + k, gz * w[k]);
+        }
+    }
+    if (want_tex && nz && tex_mode == HOC_TEX_GRAD_VERTEX) {
+        /* textures are the multilinear extension of three vertex values (T[i,j,k] = i c0 + j c1 + k c2, ts == 2):
+         * d rgb / d c_k = t_k, so nine sums per face instead of twenty-four */
+        float *gt = grad_textures + ((long)b * F + fi) * 9;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, 2, eps);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const float v = t * gr[c];
+                if (v != 0.0f)
+                    atomicAdd(gt + 3 * k + c, v);
+            }
+        }
+    } else if (want_tex && nz) {
+        float *gt = grad_textures + ((long)b * F + fi) * tex_n;
+        float tf[3];
+        int ti[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, ts, eps);
+            ti[k] = hoc_tex_cell(t, ts);
+            tf[k] = t - (float)ti[k];
+        }
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) {
+            float ww = 1.0f;
+            int isc = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (((pn >> k) & 1) == 0) {
+                    ww *= 1.0f - tf[k];
+                    isc = isc * ts + ti[k];
+                } else {
+                    ww *= tf[k];
+                    isc = isc * ts + ti[k] + 1;
+                }
+            }
+            if (!TS2 && ts == 1)
+                isc = 0;
+            if (ww != 0.0f) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float v = ww * gr[c];
+                    if (v != 0.0f)
+                        atomicAdd(gt + isc * 3 + c, v);
+                }
+            }
+        }
+    }
+}
+
+/*
+ * Cover pass: the work of the covered pixels, spread evenly over the GPU (the scan pass listed them).
+ * K4 = false: 128 threads, one listed pixel each -> texture / depth gradient.
+ * K4 = true:  224 threads work on 32 listed pixels at a time: warp c < 6 runs (edge c >> 1, axis c & 1) of the
+ *             pseudo-gradient for the 32 pixels (uniform edge / axis per warp), warp 6 their texture / depth
+ *             gradient; warp 0 then merges the six flag contributions and stores the two flag bytes per pixel.
+ */
+#define CV_THREADS_K4 224
+#define CV_THREADS 128
+template <bool TS2, bool K4>
+__global__ void __launch_bounds__(K4 ? CV_THREADS_K4 : CV_THREADS)
+hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
+                            const float *__restrict__ rgb, const float *__restrict__ weight_map,
+                            const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
+                            const float *__restrict__ g_alpha, const float *__restrict__ g_depth, int F, int S, int ts,
+                            float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
+                            const int *__restrict__ cov_count, const int *__restrict__ cov_list,
+                            float *__restrict__ acc_d, uint8_t *__restrict__ flags, float *__restrict__ grad_faces,
+                            float *__restrict__ grad_textures)
+{
+    const int b = blockIdx.y;
+    const int count = min(cov_count[b], S * S);
+    const int *list = cov_list + (long)b * S * S;
+    const int32_t *idx = face_index_map + (long)b * S * S;
+    if (!K4) {
+        for (int i = blockIdx.x * CV_THREADS + threadIdx.x; i < count; i += gridDim.x * CV_THREADS) {
+            const int p = list[i];
+            const int yi = p / S, xi = p - yi * S;
+            hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, idx[p], xi, yi, F, S, ts, near_,
+                                     far_, eps, layout, tex_mode, acc_d, grad_textures);
+        }
+        return;
+    }
+    __shared__ uint8_t s_fl[6][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     HocBwdMaps M;
-    M.idx = face_index_map + (long)b * S * S;
+    M.idx = idx;
     M.rgb = rgb;
     M.g_rgb = g_rgb;
     M.g_alpha = g_alpha;
@@ -335,55 +410,67 @@ hoc_raster_bwd_pixel_kernel(const float *__restrict__ faces, const int32_t *__re
     M.b = b;
     M.use_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     M.use_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    const int ncov = s_ncov;
-    for (int i = tid; i < ncov; i += 256) {
-        const int l = s_cov[i];
-        const int lx = l & 31, ly = l >> 5;
-        const int px = blockIdx.x * 32 + lx, py = blockIdx.y * 32 + ly;
-        const int fi = M.idx[(long)py * S + px];
-        float f[9];
-        const float *src = faces + ((long)b * F + fi) * 9;
+    for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {
+        const int i = base + lane;
+        const bool live = i < count;
+        const int p = live ? list[i] : 0;
+        const int yi = p / S, xi = p - yi * S;
+        const int fi = live ? idx[p] : -1;
+        if (wid == 6) {
+            if (fi >= 0)
+                hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, fi, xi, yi, F, S, ts, near_,
+                                         far_, eps, layout, tex_mode, acc_d, grad_textures);
+        } else {
+            unsigned fl = 0u;
+            if (fi >= 0) {
+                const int edge = wid >> 1, axis = wid & 1;
+                const int ia = edge, ib = (edge == 2) ? 0 : edge + 1, ic = (edge == 0) ? 2 : edge - 1;
+                const float *src = faces + ((long)b * F + fi) * 9;
+                const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
+                const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
+                const float cx = __ldg(src + 3 * ic), cy = __ldg(src + 3 * ic + 1);
+                float I[4] = {1.0f, 0.0f, 0.0f, 0.0f}, g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (M.use_alpha)
+                    g[0] = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+                if (M.use_rgb) {
 #pragma unroll
-        for (int k = 0; k < 9; k++)
-            f[k] = __ldg(src + k);
-        float I[4] = {1.0f, 0.0f, 0.0f, 0.0f}, g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (M.use_alpha)
-            g[0] = g_alpha[hoc_plane_off(layout, S, b, py, px)];
-        if (M.use_rgb) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const long o = hoc_rgb_off(layout, S, b, py, px, k);
-                I[1 + k] = rgb[o];
-                g[1 + k] = g_rgb[o];
+                    for (int k = 0; k < 3; k++) {
+                        const long o = hoc_rgb_off(layout, S, b, yi, xi, k);
+                        I[1 + k] = rgb[o];
+                        g[1 + k] = g_rgb[o];
+                    }
+                }
+                /* the owner of a pixel is front-facing with finite xy (the forward's tests); re-checked so that a
+                 * corrupted map cannot produce garbage.  Same expression as hoc_face_back on the rotated vertices
+                 * is NOT bit-identical, so test the face in its stored order. */
+                float f[9];
+                f[0] = (edge == 0) ? ax : ((edge == 1) ? cx : bx);
+                f[1] = (edge == 0) ? ay : ((edge == 1) ? cy : by);
+                f[3] = (edge == 0) ? bx : ((edge == 1) ? ax : cx);
+                f[4] = (edge == 0) ? by : ((edge == 1) ? ay : cy);
+                f[6] = (edge == 0) ? cx : ((edge == 1) ? bx : ax);
+                f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
+                f[2] = f[5] = f[8] = 0.0f;
+                if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
+                    float *gf = grad_faces + ((long)b * F + fi) * 9;
+                    fl = hoc_k4_pixel_combo(ax, ay, bx, by, cx, cy, edge, axis, xi, yi, M, I, g, eps, gf + 3 * ia,
+                                            gf + 3 * ib);
+                }
             }
+            s_fl[wid][lane] = (uint8_t)fl;
         }
-        if (!hoc_face_xy_finite(f) || hoc_face_back(f))
-            continue; /* cannot own a pixel; keeps a corrupted map from producing garbage */
-        float *gf = grad_faces + ((long)b * F + fi) * 9;
-        unsigned fl0 = 0u, fl1 = 0u;
-        /* edge 0: A = v0, B = v1, C = v2;  edge 1: A = v1, B = v2, C = v0;  edge 2: A = v2, B = v0, C = v1 */
-        fl0 |= hoc_k4_pixel_combo(f[0], f[1], f[3], f[4], f[6], f[7], 0, 0, px, py, M, I, g, eps, gf + 0, gf + 3);
-        fl1 |= hoc_k4_pixel_combo(f[0], f[1], f[3], f[4], f[6], f[7], 0, 1, px, py, M, I, g, eps, gf + 0, gf + 3);
-        fl0 |= hoc_k4_pixel_combo(f[3], f[4], f[6], f[7], f[0], f[1], 1, 0, px, py, M, I, g, eps, gf + 3, gf + 6);
-        fl1 |= hoc_k4_pixel_combo(f[3], f[4], f[6], f[7], f[0], f[1], 1, 1, px, py, M, I, g, eps, gf + 3, gf + 6);
-        fl0 |= hoc_k4_pixel_combo(f[6], f[7], f[0], f[1], f[3], f[4], 2, 0, px, py, M, I, g, eps, gf + 6, gf + 0);
-        fl1 |= hoc_k4_pixel_combo(f[6], f[7], f[0], f[1], f[3], f[4], 2, 1, px, py, M, I, g, eps, gf + 6, gf + 0);
-        s_flag[0][lx][ly] = (uint8_t)fl0;
-        s_flag[1][ly][lx] = (uint8_t)fl1;
-    }
-    __syncthreads();
-    /* flag tiles out, 32 contiguous bytes per warp: plane 1 rows are image rows, plane 0 rows are image columns */
-    uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * S;
-    uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * S;
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int lr = r * 8 + ty;
-        const int yi = blockIdx.y * 32 + lr;
-        if (xi < S && yi < S)
-            fl_row[(long)yi * S + xi] = s_flag[1][lr][tx];
-        const int cx = blockIdx.x * 32 + lr, cy = blockIdx.y * 32 + tx;
-        if (cx < S && cy < S)
-            fl_col[(long)cx * S + cy] = s_flag[0][lr][tx];
+        __syncthreads();
+        if (wid == 0 && fi >= 0) {
+            const unsigned fl0 = s_fl[0][lane] | s_fl[2][lane] | s_fl[4][lane];
+            const unsigned fl1 = s_fl[1][lane] | s_fl[3][lane] | s_fl[5][lane];
+            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * S;
+            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * S;
+            if (fl0)
+                fl_col[(long)xi * S + yi] = (uint8_t)fl0;
+            if (fl1)
+                fl_row[(long)yi * S + xi] = (uint8_t)fl1;
+        }
+        __syncthreads();
     }
 }
 
@@ -631,10 +718,9 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
 
-    cudaError_t e = cudaSuccess;
-    if (want_depth)
-        e = cudaMemsetAsync(w.acc_d, 0, w.acc_bytes, st);
-    if (e == cudaSuccess && grad_faces != nullptr) /* accumulated with atomics by the pixel and line passes */
+    /* cov_count and (directly behind it) acc_d are zero-filled by one memset */
+    cudaError_t e = cudaMemsetAsync(w.cov_count, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
+    if (e == cudaSuccess && grad_faces != nullptr) /* accumulated with atomics by the cover and line passes */
         e = cudaMemsetAsync(grad_faces, 0, sizeof(float) * 9 * (size_t)B * F, st);
     if (e == cudaSuccess && k4) { /* hi rows = -1, lo rows (every second row of S ints) = 0x7f7f7f7f */
         e = cudaMemsetAsync(w.ext, 0xff, sizeof(int) * 4 * (size_t)B * S, st);
@@ -647,25 +733,44 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         hoc_set_error("hoc_raster_backward: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;
     }
+    float *gt = (grad_rgb != nullptr) ? grad_textures : nullptr;
     {
+        /* without the pseudo-gradient only pixels with a texture gradient (non-zero dL/drgb) or a depth
+         * gradient have work */
         dim3 pg((S + 31) / 32, (S + 31) / 32, B);
-        float *gt = (grad_rgb != nullptr) ? grad_textures : nullptr;
-#define HOC_PIXEL_LAUNCH(TS2, K4)                                                                                    \
-    HOC_LAUNCH(K4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BWD_PIXEL, st,                                           \
-               (hoc_raster_bwd_pixel_kernel<TS2, K4><<<pg, dim3(32, 8), 0, st>>>(                                     \
-                   faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
-                   eps, layout, use_alpha, tex_grad_mode, w.ext, want_depth ? w.acc_d : nullptr, w.flags, grad_faces,  \
-                   gt)))
-        if (ts == 2 && k4)
-            HOC_PIXEL_LAUNCH(true, true);
-        else if (ts == 2)
-            HOC_PIXEL_LAUNCH(true, false);
-        else if (k4)
-            HOC_PIXEL_LAUNCH(false, true);
+        const int list_all = (k4 || want_depth) ? 1 : 0;
+        if (k4)
+            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
+                       (hoc_raster_bwd_scan_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
+                           face_index_map, grad_rgb, g_alpha, S, layout, list_all, w.ext, w.cov_count, w.cov_list,
+                           w.flags)));
         else
-            HOC_PIXEL_LAUNCH(false, false);
-#undef HOC_PIXEL_LAUNCH
-        HOC_CHECK_LAUNCH("hoc_raster_bwd_pixel_kernel");
+            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
+                       (hoc_raster_bwd_scan_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
+                           face_index_map, gt != nullptr ? grad_rgb : nullptr, nullptr, S, layout, list_all, w.ext,
+                           w.cov_count, w.cov_list, w.flags)));
+        HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
+    }
+    {
+        const long npix = (long)S * S;
+        const int per = k4 ? 32 : CV_THREADS;
+        dim3 cg((unsigned)((npix + per - 1) / per < 296 ? (npix + per - 1) / per : 296), B);
+#define HOC_COVER_LAUNCH(TS2, K4)                                                                                    \
+    HOC_LAUNCH(K4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, st,                                      \
+               (hoc_raster_bwd_cover_kernel<TS2, K4><<<cg, K4 ? CV_THREADS_K4 : CV_THREADS, 0, st>>>(                 \
+                   faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
+                   eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
+                   w.flags, grad_faces, gt)))
+        if (ts == 2 && k4)
+            HOC_COVER_LAUNCH(true, true);
+        else if (ts == 2)
+            HOC_COVER_LAUNCH(true, false);
+        else if (k4)
+            HOC_COVER_LAUNCH(false, true);
+        else
+            HOC_COVER_LAUNCH(false, false);
+#undef HOC_COVER_LAUNCH
+        HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
     }
     if (grad_faces == nullptr)
         return HOC_OK;

@@ -63,13 +63,14 @@ const char *hoc_last_error(void);
 #define HOC_K_MESH_SCATTER 10
 #define HOC_K_FLOW_FINALIZE 11
 #define HOC_K_FLOW_FINALIZE_BWD 12
-#define HOC_K_RASTER_BWD_PIXEL 13
+#define HOC_K_RASTER_BWD_PIXEL 13 /* hoc_raster_bwd_scan_kernel (streaming pass) */
 #define HOC_K_RASTER_BWD_LINE 14
 #define HOC_K_FLOW_VERTICES 15
 #define HOC_K_FLOW_VERTICES_BWD 16
 #define HOC_K_MANO_FWD 17
 #define HOC_K_MANO_BWD 18
-#define HOC_K_RASTER_BWD_PIXEL_K4 19 /* hoc_raster_bwd_pixel_kernel<.., true>: pixel pass + pseudo-gradient */
+#define HOC_K_RASTER_BWD_PIXEL_K4 19 /* hoc_raster_bwd_cover_kernel<.., true>: covered pixels incl. pseudo-gradient */
+#define HOC_K_RASTER_BACKWARD_COVER 20 /* hoc_raster_bwd_cover_kernel<.., false>: texture / depth gradient only */
 #define HOC_KERNEL_COUNT 24
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
