@@ -42,10 +42,13 @@
  *   cov_count  int   [B]           covered pixels listed per sample                      (zero-filled)
  *   acc_d      float [B][F][3]     sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
  *   cov_list   int   [B][S*S]      the covered pixels (yi * S + xi) that have work, in tile order
- *   flags      uint8 [B][2][S][S]  outward-scan flags; plane 0 (column scans) is stored [x][y], plane 1 (row
+ *   flags      uint8 [B][2][S][P]  (P = S rounded up to 16) outward-scan flags; plane 0 (column scans) is stored [x][y], plane 1 (row
  *                                  scans) [y][x], so a line's bytes are contiguous.  Bit e: edge e of the face
  *                                  owning this pixel starts an outward scan here; bit 3+e: it runs towards +.
  *                                  Zero-filled by the scan pass, set by the cover pass. */
+/* Row pitch of the flag planes: lines start 16-byte aligned so that the line pass can read 4 flags per load. */
+__host__ __device__ __forceinline__ int hoc_flag_pitch(int S) { return (S + 15) & ~15; }
+
 struct HocBwdWorkspace {
     int *ext;
     int *cov_count;
@@ -73,7 +76,7 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     w.cov_list = (int *)(p + off);
     off = up(off + sizeof(int) * (size_t)B * S * S);
     w.flags = (uint8_t *)(p + off);
-    off = up(off + 2 * (size_t)B * S * S);
+    off = up(off + 2 * (size_t)B * S * hoc_flag_pitch(S));
     w.total = off;
     return w;
 }
@@ -100,6 +103,14 @@ __device__ __forceinline__ void hoc_load_I(const HocBwdMaps &M, int xi, int yi, 
         I[2] = M.rgb[hoc_rgb_off(M.layout, M.S, M.b, yi, xi, 1)];
         I[3] = M.rgb[hoc_rgb_off(M.layout, M.S, M.b, yi, xi, 2)];
     }
+}
+
+/* 1 / x, one MUFU.RCP. */
+__device__ __forceinline__ float hoc_rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 /* One (edge, axis) of the face owning pixel (xi, yi): the pixel's term of the inward scan of the column it
@@ -250,13 +261,14 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         if ((want[r] >> tx) & 1u)
             list[s_cnt[lr] + __popc(want[r] & ((1u << tx) - 1u))] = yi * S + xi;
         if (K4) { /* the tile's flag bytes, 32 contiguous bytes per warp in both planes */
-            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * S;
-            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * S;
+            const int P = hoc_flag_pitch(S);
+            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * P;
+            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * P;
             if (xi < S && yi < S)
-                fl_row[(long)yi * S + xi] = 0;
+                fl_row[(long)yi * P + xi] = 0;
             const int cx = blockIdx.x * 32 + lr, cy = blockIdx.y * 32 + tx;
             if (cx < S && cy < S)
-                fl_col[(long)cx * S + cy] = 0;
+                fl_col[(long)cx * P + cy] = 0;
         }
     }
 }
@@ -463,12 +475,13 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
         if (wid == 0 && fi >= 0) {
             const unsigned fl0 = s_fl[0][lane] | s_fl[2][lane] | s_fl[4][lane];
             const unsigned fl1 = s_fl[1][lane] | s_fl[3][lane] | s_fl[5][lane];
-            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * S;
-            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * S;
+            const int P = hoc_flag_pitch(S);
+            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * P;
+            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * P;
             if (fl0)
-                fl_col[(long)xi * S + yi] = (uint8_t)fl0;
+                fl_col[(long)xi * P + yi] = (uint8_t)fl0;
             if (fl1)
-                fl_row[(long)yi * S + xi] = (uint8_t)fl1;
+                fl_row[(long)yi * P + xi] = (uint8_t)fl1;
         }
         __syncthreads();
     }
@@ -508,49 +521,110 @@ hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__rest
 }
 
 /*
- * Line pass.  grid (S, 2, B): one CTA per image column (axis 0) or row (axis 1).
+ * Line pass.  grid (ceil(S / G), 2, B): one CTA per group of G adjacent image columns (axis 0) or rows
+ * (axis 1) -- a single line rarely carries enough outward scans to fill the CTA's warps, G lines do, and G
+ * adjacent columns are read from HBM as 4 G contiguous bytes per row.
  */
-#define LN_THREADS 128
+#define LN_THREADS 256
 #define LN_WARPS (LN_THREADS / 32)
+template <int G>
 __global__ void __launch_bounds__(LN_THREADS)
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
-                           const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
-                           const int *__restrict__ ext, const uint8_t *__restrict__ flags,
-                           float *__restrict__ grad_faces)
+                           const float *__restrict__ g_alpha, int B, int F, int S, float eps, int layout,
+                           int use_alpha, const int *__restrict__ ext, const uint8_t *__restrict__ flags,
+                           float *__restrict__ grad_faces, int seg)
 {
-    /* dynamic shared memory: float4 s_line4[S] | float s_ga[S] | ushort s_queue[3 S]
-     * per pixel of the span: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch (alpha included), then g_alpha:
-     * delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_ch Iin_ch g_ch -- one 16-byte shared load and three FMAs
-     * per scanned pixel (<= 1 ulp of |P| from the reference's summation order, gradients carry 1e-3) */
+    /* dynamic shared memory: float4 s_line4[G][S] | ushort s_queue[G * 3 S]
+     * per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (the inside pixel of a scan
+     * is covered, its alpha is 1): delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_rgb Iin_ch g_ch -- one 16-byte
+     * shared load and three FMAs per scanned pixel (<= 1 ulp of |P| from the reference's summation order,
+     * gradients carry 1e-3) */
     extern __shared__ float4 s_line4[];
     __shared__ int s_wtot[LN_WARPS];
-    const int d0 = blockIdx.x, axis = blockIdx.y, b = blockIdx.z;
+    __shared__ int s_lo[G], s_hi[G];
+    /* 1-D grid, sample fastest, line groups ordered from the image centre outwards: the lines that carry the
+     * most scans (meshes are centred by the crop) are dispatched first, the empty border lines form the tail */
+    const int ngroups = (S + G - 1) / G;
+    const int b = blockIdx.x % B;
+    const int rest = blockIdx.x / B;
+    const int axis = rest & 1;
+    const int k = rest >> 1;
+    const int grp = (ngroups >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1)); /* c, c-1, c+1, c-2, ...: a bijection */
+    const int d0_base = grp * G;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int *e = ext + (long)b * 4 * S;
-    const int lo = (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0];
-    const int hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
-    if (lo > hi)
-        return; /* no incoming gradient anywhere on this line: every outward scan sums zeros */
-    const int len = hi - lo + 1;
-    float *s_ga = reinterpret_cast<float *>(s_line4 + S);
-    unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_ga + S);
-    const int cap = 3 * S;
+    int ulo, uhi;
+    if (G == 1) { /* a line without incoming gradient: leave before anything else is computed */
+        ulo = e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
+        uhi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_base];
+        if (ulo > uhi)
+            return;
+        if (tid == 0) {
+            s_lo[0] = ulo;
+            s_hi[0] = uhi;
+        }
+        __syncthreads();
+    } else {
+        if (tid < G) {
+            const int d0 = d0_base + tid;
+            int lo = 0x7f7f7f7f, hi = -1;
+            if (d0 < S) {
+                lo = (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0];
+                hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
+            }
+            s_lo[tid] = lo;
+            s_hi[tid] = hi;
+        }
+        __syncthreads();
+        ulo = 0x7f7f7f7f;
+        uhi = -1;
+#pragma unroll
+        for (int l = 0; l < G; l++) {
+            ulo = min(ulo, s_lo[l]);
+            uhi = max(uhi, s_hi[l]);
+        }
+        if (ulo > uhi)
+            return; /* no incoming gradient anywhere on these lines: every outward scan sums zeros */
+    }
+    const int ulen = uhi - ulo + 1;
+    unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_line4 + (size_t)G * S);
+    const int cap = G * 3 * S;
 
-    /* 1. the line's scans, compacted in position order: towards + from the front of the queue (length falls
-     *    with position), towards - from the back (length grows with position).  A scan that starts beyond the
-     *    span of non-zero gradient has nothing to sum and is dropped here. */
-    const uint8_t *fl = flags + (((long)b * 2 + axis) * S + d0) * S;
+    /* 1. the scans of the G lines, compacted in position order (4 positions x G lines at a time): towards + from
+     *    the front of the queue (length falls with position), towards - from the back (length grows with
+     *    position), so that the lanes of a warp get scans of nearly equal length.  A scan that starts beyond the
+     *    span of non-zero gradient of its line has nothing to sum and is dropped here.
+     *    entry = position | edge << 11 | line << 13 */
+    const int P = hoc_flag_pitch(S);
+    const int my_l = tid % G, my_grp = tid / G;
+    const int my_d0 = d0_base + my_l;
+    const uint8_t *fl = flags + (((long)b * 2 + axis) * S + min(my_d0, S - 1)) * P;
+    const int my_lo = s_lo[my_l], my_hi = s_hi[my_l];
+    const int T = blockDim.x; /* multiple of 32 and of G, <= LN_THREADS */
+    const int POS_PER_ITER = 4 * (T / G);
     int nP = 0, nN = 0;
-    for (int base = 0; base < S; base += LN_THREADS) {
-        const int i = base + tid;
-        unsigned v = (i < S) ? fl[i] : 0u;
-        unsigned mP = v & (v >> 3) & 7u, mN = v & ~(v >> 3) & 7u;
-        if (i + 1 > hi)
-            mP = 0u;
-        if (i - 1 < lo)
-            mN = 0u;
-        const int mine = __popc(mP) | (__popc(mN) << 16);
+    for (int base = 0; base < S; base += POS_PER_ITER) {
+        const int i0 = base + 4 * my_grp;
+        uint32_t v4 = 0u;
+        if (i0 < S && my_lo <= my_hi)
+            v4 = *reinterpret_cast<const uint32_t *>(fl + i0);
+        unsigned mP[4], mN[4];
+        int cP = 0, cN = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = i0 + k;
+            const unsigned v = (i < S) ? ((v4 >> (8 * k)) & 0xffu) : 0u;
+            mP[k] = v & (v >> 3) & 7u;
+            mN[k] = v & ~(v >> 3) & 7u;
+            if (i + 1 > my_hi)
+                mP[k] = 0u;
+            if (i - 1 < my_lo)
+                mN[k] = 0u;
+            cP += __popc(mP[k]);
+            cN += __popc(mN[k]);
+        }
+        const int mine = cP | (cN << 16);
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -562,21 +636,26 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
             s_wtot[wid] = incl;
         __syncthreads();
         int before = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; w++) {
+        for (int w = 0; w < (T >> 5); w++) {
             const int t = s_wtot[w];
             if (w < wid)
                 before += t;
             total += t;
         }
-        const int excl = before + incl - mine;
-        int pP = nP + (excl & 0xffff), pN = nN + (excl >> 16);
+        if (mine != 0) {
+            const int excl = before + incl - mine;
+            int pP = nP + (excl & 0xffff), pN = nN + (excl >> 16);
 #pragma unroll
-        for (int ed = 0; ed < 3; ed++) {
-            if (mP & (1u << ed))
-                s_queue[pP++] = (unsigned short)(i | (ed << 11));
-            if (mN & (1u << ed))
-                s_queue[cap - 1 - (pN++)] = (unsigned short)(i | (ed << 11));
+            for (int k = 0; k < 4; k++) {
+                const int rec = (i0 + k) | (my_l << 13);
+#pragma unroll
+                for (int ed = 0; ed < 3; ed++) {
+                    if (mP[k] & (1u << ed))
+                        s_queue[pP++] = (unsigned short)(rec | (ed << 11));
+                    if (mN[k] & (1u << ed))
+                        s_queue[cap - 1 - (pN++)] = (unsigned short)(rec | (ed << 11));
+                }
+            }
         }
         nP += total & 0xffff;
         nN += total >> 16;
@@ -586,93 +665,194 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     if (n == 0)
         return;
 
-    HocBwdMaps M;
-    M.idx = face_index_map + (long)b * S * S;
-    M.rgb = rgb;
-    M.g_rgb = g_rgb;
-    M.g_alpha = g_alpha;
-    M.S = S;
-    M.layout = layout;
-    M.b = b;
-    M.use_alpha = (use_alpha != 0) && (g_alpha != nullptr);
-    M.use_rgb = (rgb != nullptr) && (g_rgb != nullptr);
+    const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
+    const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
+    const int32_t *idx = face_index_map + (long)b * S * S;
 
-    /* 2. stage the span */
-    for (int i = tid; i < len; i += LN_THREADS) {
-        const int d1 = lo + i;
-        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-        float I[4];
-        hoc_load_I(M, xi, yi, I);
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
-        if (M.use_alpha)
-            g[0] = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
-        if (M.use_rgb) {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                g[1 + k] = g_rgb[hoc_rgb_off(layout, S, b, yi, xi, k)];
+    /* 2. stage the union of the spans of the G lines (zero gradient outside a line's own span) */
+    for (int t = tid; t < G * ulen; t += T) {
+        /* consecutive threads read consecutive x: along the line for rows, across the lines for columns */
+        const int l = (axis == 0) ? t % G : t / ulen;
+        const int i = (axis == 0) ? t / G : t % ulen;
+        const int d0 = d0_base + l, d1 = ulo + i;
+        float4 pg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (d0 < S) {
+            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+            if (has_rgb) {
+                const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
+                           o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
+                pg.y = g_rgb[o0];
+                pg.z = g_rgb[o1];
+                pg.w = g_rgb[o2];
+                pg.x = rgb[o0] * pg.y + rgb[o1] * pg.z + rgb[o2] * pg.w;
+            }
+            if (has_alpha) {
+                const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+                const float a = (idx[(long)yi * S + xi] >= 0) ? 1.0f : 0.0f;
+                pg.x += a * ga - ga;
+            }
         }
-        s_line4[i] = make_float4(I[0] * g[0] + I[1] * g[1] + I[2] * g[2] + I[3] * g[3], g[1], g[2], g[3]);
-        if (M.use_alpha)
-            s_ga[i] = g[0];
+        s_line4[l * S + i] = pg;
     }
     __syncthreads();
 
-    /* 3. one outward scan per lane */
+    /* 3. the scans, LN_THREADS at a time.  (a) One lane sets up one scan (edge geometry, colour of the inside
+     *    pixel, range) and leaves it in shared memory; (b) the scans are cut into segments of at most `seg`
+     *    pixels and every lane sums one segment, so that a warp's lanes finish together however different the
+     *    scan lengths are; each segment adds its two vertex contributions to grad_faces. */
     const float scale = 2.0f / (float)S;
-    for (int q = tid; q < n; q += LN_THREADS) {
-        const int rec = (q < nP) ? s_queue[q] : s_queue[cap - 1 - (q - nP)];
-        const int d1_in = rec & 0x7ff, edge = rec >> 11;
-        const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
-        const int fi = M.idx[(long)yin * S + xin];
-        float I_in[4] = {1.0f, 0.0f, 0.0f, 0.0f}; /* the inside pixel is owned, alpha = 1 */
-        if (M.use_rgb) {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                I_in[1 + k] = rgb[hoc_rgb_off(layout, S, b, yin, xin, k)];
+    __shared__ float r_cA[LN_THREADS], r_cB[LN_THREADS], r_cross[LN_THREADS], r_I1[LN_THREADS], r_I2[LN_THREADS],
+        r_I3[LN_THREADS];
+    __shared__ int r_from[LN_THREADS], r_to[LN_THREADS], r_gfA[LN_THREADS], r_gfB[LN_THREADS], r_row[LN_THREADS];
+    __shared__ int s_pre[LN_THREADS + 1];
+    for (int q0 = 0; q0 < n; q0 += T) {
+        const int q = q0 + tid;
+        int nseg = 0;
+        if (q < n) {
+            const int rec = (q < nP) ? s_queue[q] : s_queue[cap - 1 - (q - nP)];
+            const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3, l = rec >> 13;
+            const int d0 = d0_base + l;
+            const int lo = s_lo[l], hi = s_hi[l];
+            const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+            const int fi = idx[(long)yin * S + xin];
+            float I1 = 0.0f, I2 = 0.0f, I3 = 0.0f; /* rgb of the inside pixel (its alpha is 1: folded into P) */
+            if (has_rgb) {
+                I1 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 0)];
+                I2 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 1)];
+                I3 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 2)];
+            }
+            if (fi >= 0) { /* always: the cover pass flags owned pixels only */
+                const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
+                const float *src = faces + ((long)b * F + fi) * 9;
+                const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
+                const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
+                HocK4Edge E;
+                hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
+                float d1_cross;
+                int d1_chk, d1_out;
+                /* always true: the cover pass flagged this column because it passed the same test */
+                if (hoc_k4_column(&E, S, d0, &d1_cross, &d1_chk, &d1_out)) {
+                    const int d1_from = (0 < E.dir) ? max(d1_out, lo) : lo;
+                    const int d1_to = (0 < E.dir) ? hi : min(d1_out, hi);
+                    HocK4Col C;
+                    hoc_k4_col(&E, S, d0, d1_cross, &C);
+                    /* a vertex that gets no contribution: infinite distance -> 1 / dist = 0 (d1 - cross != 0) */
+                    r_cA[tid] = C.hasA ? C.cA * scale : __int_as_float(0x7f800000);
+                    r_cB[tid] = C.hasB ? C.cB * scale : __int_as_float(0x7f800000);
+                    r_cross[tid] = d1_cross;
+                    r_I1[tid] = I1;
+                    r_I2[tid] = I2;
+                    r_I3[tid] = I3;
+                    r_from[tid] = d1_from;
+                    r_to[tid] = d1_to;
+                    r_row[tid] = l * S - ulo;
+                    const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
+                    r_gfA[tid] = gbase + ia * 3;
+                    r_gfB[tid] = gbase + ib * 3;
+                    if (d1_to >= d1_from)
+                        nseg = (d1_to - d1_from + seg) / seg;
+                }
+            }
         }
-        if (fi < 0)
-            continue; /* unreachable: the pixel pass flags owned pixels only */
-        const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
-        const float *src = faces + ((long)b * F + fi) * 9;
-        const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
-        const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
-        HocK4Edge E;
-        hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
-        float d1_cross;
-        int d1_chk, d1_out;
-        if (!hoc_k4_column(&E, S, d0, &d1_cross, &d1_chk, &d1_out))
-            continue; /* unreachable: the pixel pass flagged this column because it passed the same test */
-        const int d1_from = (0 < E.dir) ? max(d1_out, lo) : lo;
-        const int d1_to = (0 < E.dir) ? hi : min(d1_out, hi);
-        HocK4Col C;
-        hoc_k4_col(&E, S, d0, d1_cross, &C);
-        const float cA = C.cA * scale, cB = C.cB * scale;
-        const float peps = eps, neps = -eps;
-        float gA = 0.0f, gB = 0.0f;
-        float u = (float)d1_from - d1_cross;
-        const float4 *sp = s_line4 + (d1_from - lo);
-        const float *sa = s_ga + (d1_from - lo);
-        for (int k = d1_to - d1_from; k >= 0; k--, sp++, sa++, u += 1.0f) {
-            const float4 pg = *sp;
-            float delta = pg.x - __fmaf_rn(I_in[3], pg.w, __fmaf_rn(I_in[2], pg.z, I_in[1] * pg.y));
-            if (M.use_alpha)
-                delta -= *sa;
-            if (!(delta <= 0.0f)) {
+        /* exclusive prefix of the segment counts */
+        int incl = nseg;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_wtot[wid] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < (T >> 5); w++) {
+            const int t = s_wtot[w];
+            if (w < wid)
+                before += t;
+            total += t;
+        }
+        s_pre[tid] = before + incl - nseg;
+        if (tid == 0)
+            s_pre[T] = total;
+        __syncthreads();
+        for (int j = tid; j < total; j += T) {
+            int a = 0, c = T; /* last scan with s_pre[scan] <= j */
+            while (c - a > 1) {
+                const int mid = (a + c) >> 1;
+                if (s_pre[mid] <= j)
+                    a = mid;
+                else
+                    c = mid;
+            }
+            const int d1_from = r_from[a] + (j - s_pre[a]) * seg;
+            const int d1_to = min(r_to[a], d1_from + seg - 1);
+            const float cA = r_cA[a], cB = r_cB[a], I1 = r_I1[a], I2 = r_I2[a], I3 = r_I3[a];
+            const float peps = eps, neps = -eps;
+            float gA = 0.0f, gB = 0.0f;
+            float u = (float)d1_from - r_cross[a];
+            const float4 *sp = s_line4 + (r_row[a] + d1_from);
+            /* branch-free body: a pixel with delta <= 0 adds 0 * (1 / dist); MUFU.RCP (2 ulp) for 1 / dist -- the
+             * pseudo-gradient carries a 1e-3 tolerance and this quotient is the hot instruction of the pass */
+            for (int k = d1_to - d1_from; k >= 0; k--, sp++, u += 1.0f) {
+                const float4 pg = *sp;
+                float delta = pg.x - __fmaf_rn(I3, pg.w, __fmaf_rn(I2, pg.z, I1 * pg.y));
+                delta = (delta <= 0.0f) ? 0.0f : delta;
                 float dA = cA * u, dB = cB * u;
                 dA += (0.0f < dA) ? peps : neps;
                 dB += (0.0f < dB) ? peps : neps;
-                if (C.hasA)
-                    gA -= HOC_FAST_DIV(delta, dA);
-                if (C.hasB)
-                    gB -= HOC_FAST_DIV(delta, dB);
+                gA = __fmaf_rn(-delta, hoc_rcp_approx(dA), gA);
+                gB = __fmaf_rn(-delta, hoc_rcp_approx(dB), gB);
             }
+            if (gA != 0.0f)
+                atomicAdd(grad_faces + r_gfA[a], gA);
+            if (gB != 0.0f)
+                atomicAdd(grad_faces + r_gfB[a], gB);
         }
-        float *gf = grad_faces + ((long)b * F + fi) * 9;
-        if (gA != 0.0f)
-            atomicAdd(gf + ia * 3 + (1 - axis), gA);
-        if (gB != 0.0f)
-            atomicAdd(gf + ib * 3 + (1 - axis), gB);
+        __syncthreads();
     }
+}
+
+/* Tuning knobs of the line pass (hoc_set_tuning): lines per CTA (0 = by image size), threads per CTA, segment
+ * length in pixels. */
+static int g_line_G = 0, g_line_threads = 128, g_line_seg = 16;
+
+extern "C" int hoc_set_tuning(int key, int value)
+{
+    if (key == HOC_TUNE_LINE_GROUP && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8))
+        g_line_G = value;
+    else if (key == HOC_TUNE_LINE_THREADS && value >= 32 && value <= LN_THREADS && value % 32 == 0)
+        g_line_threads = value;
+    else if (key == HOC_TUNE_LINE_SEGMENT && value >= 1 && value <= 4096)
+        g_line_seg = value;
+    else {
+        hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
+        return HOC_ERR_INVALID_ARG;
+    }
+    return HOC_OK;
+}
+
+template <int G>
+static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index_map, const float *rgb,
+                                   const float *grad_rgb, const float *g_alpha, int B, int F, int S, float eps,
+                                   int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
+                                   cudaStream_t st)
+{
+    static size_t smem_allowed = 32 * 1024; /* static arrays of the kernel take ~13 KB of the default 48 KB */
+    const size_t smem = (size_t)G * S * (sizeof(float4) + 3 * sizeof(unsigned short));
+    if (smem > smem_allowed) {
+        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess)
+            return e;
+        smem_allowed = smem;
+    }
+    const unsigned grid = (unsigned)((S + G - 1) / G) * 2u * (unsigned)B;
+    HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
+               (hoc_raster_bwd_line_kernel<G><<<grid, g_line_threads, smem, st>>>(
+                   faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w.ext, w.flags,
+                   grad_faces, g_line_seg)));
+    return cudaSuccess;
 }
 
 extern "C" size_t hoc_raster_backward_workspace_bytes(int B, int F, int S)
@@ -782,20 +962,18 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
     }
     if (k4) {
-        const size_t smem = (sizeof(float) * 5 + sizeof(unsigned short) * 3) * (size_t)S;
-        if (smem > 48 * 1024) {
-            e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) {
-                hoc_set_error("hoc_raster_backward: cannot reserve %zu bytes of shared memory: %s", smem,
-                              cudaGetErrorString(e));
-                return HOC_ERR_CUDA;
-            }
+        /* lines per CTA: bounded by staging + queue (22 bytes per pixel of a line) */
+        int G = g_line_G ? g_line_G : 1;
+        while (G > 1 && (size_t)G * S * 22 > 96 * 1024)
+            G >>= 1;
+#define HOC_LINE(G_) hoc_launch_line<G_>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w, grad_faces, st)
+        e = (G == 8) ? HOC_LINE(8) : (G == 4) ? HOC_LINE(4) : (G == 2) ? HOC_LINE(2) : HOC_LINE(1);
+#undef HOC_LINE
+        if (e != cudaSuccess) {
+            hoc_set_error("hoc_raster_backward: cannot reserve shared memory for the line pass: %s",
+                          cudaGetErrorString(e));
+            return HOC_ERR_CUDA;
         }
-        dim3 grid(S, 2, B);
-        HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-                   (hoc_raster_bwd_line_kernel<<<grid, LN_THREADS, smem, st>>>(
-                       faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.flags,
-                       grad_faces)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_line_kernel");
     }
     return HOC_OK;

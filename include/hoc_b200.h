@@ -73,6 +73,15 @@ const char *hoc_last_error(void);
 #define HOC_K_RASTER_BACKWARD_COVER 20 /* hoc_raster_bwd_cover_kernel<.., false>: texture / depth gradient only */
 #define HOC_KERNEL_COUNT 24
 
+/* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
+ *   HOC_TUNE_LINE_GROUP    image lines per CTA of the rasterizer backward's line pass (0 = default, 1/2/4/8)
+ *   HOC_TUNE_LINE_THREADS  threads per CTA of that pass (multiple of 32, <= 256)
+ *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan */
+#define HOC_TUNE_LINE_GROUP 0
+#define HOC_TUNE_LINE_THREADS 1
+#define HOC_TUNE_LINE_SEGMENT 2
+int hoc_set_tuning(int key, int value);
+
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
 unsigned long long hoc_launch_count(int kernel_id);
 /* Arm / read the device timer: between begin and end every launch of a kernel whose bit is set in
