@@ -38,24 +38,22 @@
 #define EXT_COL_HI 3
 
 /* Workspace carved by hoc_raster_backward (256-byte aligned regions):
- *   ext        int   [B][4][S]     {row_lo, row_hi, col_lo, col_hi}: span of non-zero incoming gradient
- *   cov_count  int   [B]           covered pixels listed per sample                      (zero-filled)
- *   acc_d      float [B][F][3]     sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
- *   cov_list   int   [B][S*S]      the covered pixels (yi * S + xi) that have work, in tile order
- *   flags      uint8 [B][2][S][P]  (P = S rounded up to 16) outward-scan flags; plane 0 (column scans) is stored [x][y], plane 1 (row
- *                                  scans) [y][x], so a line's bytes are contiguous.  Bit e: edge e of the face
- *                                  owning this pixel starts an outward scan here; bit 3+e: it runs towards +.
- *                                  Zero-filled by the scan pass, set by the cover pass. */
-/* Row pitch of the flag planes: lines start 16-byte aligned so that the line pass can read 4 flags per load. */
-__host__ __device__ __forceinline__ int hoc_flag_pitch(int S) { return (S + 15) & ~15; }
-
+ *   ext        int    [B][4][S]      {row_lo, row_hi, col_lo, col_hi}: span of non-zero incoming gradient
+ *   cov_count  int    [B]            covered pixels listed per sample                      (zero-filled)
+ *   line_count int    [B][2][S]      outward scans queued on each line (axis 0: column x, axis 1: row y)  (zero-filled)
+ *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
+ *   cov_list   int    [B][S*S]       the covered pixels (yi * S + xi) that have work, in tile order
+ *   emitters   ushort [B][2][S][3S]  the queues: position on the line | edge << 11.  3S is a hard bound: a scan is
+ *                                    keyed by its inside pixel on the line, which is owned by exactly one face with
+ *                                    3 edges; only the used part is ever touched */
 struct HocBwdWorkspace {
     int *ext;
     int *cov_count;
+    int *line_count;
     float *acc_d;
     int *cov_list;
-    uint8_t *flags;
-    size_t count_bytes, acc_bytes;
+    unsigned short *emitters;
+    size_t count_bytes, acc_bytes; /* cov_count + line_count, then acc_d: one contiguous zero-fill */
     size_t total;
 };
 
@@ -67,16 +65,19 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     char *p = (char *)base;
     w.ext = (int *)(p + off);
     off = up(off + sizeof(int) * 4 * (size_t)B * S);
+    const size_t zero_begin = off;
     w.cov_count = (int *)(p + off);
-    w.count_bytes = up(sizeof(int) * (size_t)B);
-    off += w.count_bytes;
-    w.acc_d = (float *)(p + off); /* directly after cov_count: one memset covers both */
+    off = up(off + sizeof(int) * (size_t)B);
+    w.line_count = (int *)(p + off);
+    off = up(off + sizeof(int) * 2 * (size_t)B * S);
+    w.count_bytes = off - zero_begin;
+    w.acc_d = (float *)(p + off); /* directly after the counters: one memset covers both */
     w.acc_bytes = sizeof(float) * 3 * (size_t)B * F;
     off = up(off + w.acc_bytes);
     w.cov_list = (int *)(p + off);
     off = up(off + sizeof(int) * (size_t)B * S * S);
-    w.flags = (uint8_t *)(p + off);
-    off = up(off + 2 * (size_t)B * S * hoc_flag_pitch(S));
+    w.emitters = (unsigned short *)(p + off);
+    off = up(off + sizeof(unsigned short) * 2 * (size_t)B * S * 3 * (size_t)S);
     w.total = off;
     return w;
 }
@@ -114,27 +115,31 @@ __device__ __forceinline__ float hoc_rcp_approx(float x)
 }
 
 /* One (edge, axis) of the face owning pixel (xi, yi): the pixel's term of the inward scan of the column it
- * lies on (added to grad_faces) and, when it is the pixel just inside the edge, the outward-scan flag.
+ * lies on (added to grad_faces) and, when it is the pixel just inside the edge, the queued outward scan.
  * (ax..cy) are the face's vertices in NDC rotated so that A is the first vertex of the edge; gfA / gfB point
  * at the x component of vertex A / B in grad_faces.  I / g: (alpha, r, g, b) of the pixel and its incoming
  * gradient. */
-__device__ __forceinline__ unsigned hoc_k4_pixel_combo(float ax, float ay, float bx, float by, float cx, float cy,
-                                                       int edge, int axis, int xi, int yi, const HocBwdMaps &M,
-                                                       const float *I, const float *g, float eps,
-                                                       float *__restrict__ gfA, float *__restrict__ gfB)
+__device__ __forceinline__ void hoc_k4_pixel_combo(float ax, float ay, float bx, float by, float cx, float cy,
+                                                   int edge, int axis, int xi, int yi, const HocBwdMaps &M,
+                                                   const float *I, const float *g, float eps,
+                                                   int *__restrict__ line_count, unsigned short *__restrict__ emitters,
+                                                   float *__restrict__ gfA, float *__restrict__ gfB)
 {
     HocK4Edge E;
     hoc_k4_edge_pts(ax, ay, bx, by, cx, cy, M.S, axis, &E);
     const int d0 = axis == 0 ? xi : yi, d1p = axis == 0 ? yi : xi;
     if (d0 < E.d0_from || d0 > E.d0_to)
-        return 0u;
+        return;
     float d1_cross;
     int d1_in, d1_out;
     if (!hoc_k4_column(&E, M.S, d0, &d1_cross, &d1_in, &d1_out))
-        return 0u;
-    unsigned flag = 0u;
-    if (d1_in == d1p)
-        flag = (1u << edge) | ((0 < E.dir) ? (8u << edge) : 0u);
+        return;
+    if (d1_in == d1p) { /* this pixel is the one just inside the edge: queue the outward scan on its line */
+        const long line = ((long)M.b * 2 + axis) * M.S + d0;
+        const int pos = atomicAdd(line_count + line, 1);
+        if (pos < 3 * M.S) /* cannot fail (see HocBwdWorkspace); keeps a corrupted map from overrunning */
+            emitters[line * 3 * M.S + pos] = (unsigned short)(d1p | (edge << 11));
+    }
     const int lim = hoc_k4_inward_limit(&E, d0);
     const int d1_from = max(min(d1_in, lim), 0);
     const int d1_to = min(max(d1_in, lim), M.S - 1);
@@ -160,20 +165,19 @@ __device__ __forceinline__ unsigned hoc_k4_pixel_combo(float ax, float ay, float
                 atomicAdd(gfB + (1 - axis), gB);
         }
     }
-    return flag;
 }
 
 /*
  * Scan pass.  Block (32, 8) covers a 32 x 32 pixel tile (4 rows per thread).  Pure streaming: reads
  * face_index_map and the incoming gradients once, writes the line spans, the list of covered pixels that have
- * work (all of them when the pseudo-gradient is wanted, else those with a texture / depth gradient) and, for the
- * pseudo-gradient, zeroes the tile's flag bytes.  One global atomic per CTA reserves the tile's list slots.
+ * work (all of them when the pseudo-gradient is wanted, else those with a texture / depth gradient).  One global
+ * atomic per CTA reserves the tile's list slots.
  */
 template <bool K4>
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int S, int layout, int list_all, int *__restrict__ ext,
-                           int *__restrict__ cov_count, int *__restrict__ cov_list, uint8_t *__restrict__ flags)
+                           int *__restrict__ cov_count, int *__restrict__ cov_list)
 {
     __shared__ int s_lo[8][32];
     __shared__ int s_hi[8][32];
@@ -260,16 +264,6 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         const int yi = blockIdx.y * 32 + lr;
         if ((want[r] >> tx) & 1u)
             list[s_cnt[lr] + __popc(want[r] & ((1u << tx) - 1u))] = yi * S + xi;
-        if (K4) { /* the tile's flag bytes, 32 contiguous bytes per warp in both planes */
-            const int P = hoc_flag_pitch(S);
-            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * P;
-            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * P;
-            if (xi < S && yi < S)
-                fl_row[(long)yi * P + xi] = 0;
-            const int cx = blockIdx.x * 32 + lr, cy = blockIdx.y * 32 + tx;
-            if (cx < S && cy < S)
-                fl_col[(long)cx * P + cy] = 0;
-        }
     }
 }
 
@@ -381,8 +375,8 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
  * Cover pass: the work of the covered pixels, spread evenly over the GPU (the scan pass listed them).
  * K4 = false: 128 threads, one listed pixel each -> texture / depth gradient.
  * K4 = true:  224 threads work on 32 listed pixels at a time: warp c < 6 runs (edge c >> 1, axis c & 1) of the
- *             pseudo-gradient for the 32 pixels (uniform edge / axis per warp), warp 6 their texture / depth
- *             gradient; warp 0 then merges the six flag contributions and stores the two flag bytes per pixel.
+ *             pseudo-gradient for the 32 pixels (uniform edge / axis per warp: inward-scan terms into grad_faces,
+ *             outward scans queued on their lines), warp 6 their texture / depth gradient.  Warps are independent.
  */
 #define CV_THREADS_K4 224
 #define CV_THREADS 128
@@ -394,7 +388,8 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                             const float *__restrict__ g_alpha, const float *__restrict__ g_depth, int F, int S, int ts,
                             float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
                             const int *__restrict__ cov_count, const int *__restrict__ cov_list,
-                            float *__restrict__ acc_d, uint8_t *__restrict__ flags, float *__restrict__ grad_faces,
+                            float *__restrict__ acc_d, int *__restrict__ line_count,
+                            unsigned short *__restrict__ emitters, float *__restrict__ grad_faces,
                             float *__restrict__ grad_textures)
 {
     const int b = blockIdx.y;
@@ -410,7 +405,6 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
         }
         return;
     }
-    __shared__ uint8_t s_fl[6][32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     HocBwdMaps M;
     M.idx = idx;
@@ -432,58 +426,41 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
             if (fi >= 0)
                 hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, fi, xi, yi, F, S, ts, near_,
                                          far_, eps, layout, tex_mode, acc_d, grad_textures);
-        } else {
-            unsigned fl = 0u;
-            if (fi >= 0) {
-                const int edge = wid >> 1, axis = wid & 1;
-                const int ia = edge, ib = (edge == 2) ? 0 : edge + 1, ic = (edge == 0) ? 2 : edge - 1;
-                const float *src = faces + ((long)b * F + fi) * 9;
-                const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
-                const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
-                const float cx = __ldg(src + 3 * ic), cy = __ldg(src + 3 * ic + 1);
-                float I[4] = {1.0f, 0.0f, 0.0f, 0.0f}, g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                if (M.use_alpha)
-                    g[0] = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
-                if (M.use_rgb) {
+        } else if (fi >= 0) {
+            const int edge = wid >> 1, axis = wid & 1;
+            const int ia = edge, ib = (edge == 2) ? 0 : edge + 1, ic = (edge == 0) ? 2 : edge - 1;
+            const float *src = faces + ((long)b * F + fi) * 9;
+            const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
+            const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
+            const float cx = __ldg(src + 3 * ic), cy = __ldg(src + 3 * ic + 1);
+            float I[4] = {1.0f, 0.0f, 0.0f, 0.0f}, g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (M.use_alpha)
+                g[0] = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+            if (M.use_rgb) {
 #pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const long o = hoc_rgb_off(layout, S, b, yi, xi, k);
-                        I[1 + k] = rgb[o];
-                        g[1 + k] = g_rgb[o];
-                    }
-                }
-                /* the owner of a pixel is front-facing with finite xy (the forward's tests); re-checked so that a
-                 * corrupted map cannot produce garbage.  Same expression as hoc_face_back on the rotated vertices
-                 * is NOT bit-identical, so test the face in its stored order. */
-                float f[9];
-                f[0] = (edge == 0) ? ax : ((edge == 1) ? cx : bx);
-                f[1] = (edge == 0) ? ay : ((edge == 1) ? cy : by);
-                f[3] = (edge == 0) ? bx : ((edge == 1) ? ax : cx);
-                f[4] = (edge == 0) ? by : ((edge == 1) ? ay : cy);
-                f[6] = (edge == 0) ? cx : ((edge == 1) ? bx : ax);
-                f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
-                f[2] = f[5] = f[8] = 0.0f;
-                if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
-                    float *gf = grad_faces + ((long)b * F + fi) * 9;
-                    fl = hoc_k4_pixel_combo(ax, ay, bx, by, cx, cy, edge, axis, xi, yi, M, I, g, eps, gf + 3 * ia,
-                                            gf + 3 * ib);
+                for (int k = 0; k < 3; k++) {
+                    const long o = hoc_rgb_off(layout, S, b, yi, xi, k);
+                    I[1 + k] = rgb[o];
+                    g[1 + k] = g_rgb[o];
                 }
             }
-            s_fl[wid][lane] = (uint8_t)fl;
+            /* the owner of a pixel is front-facing with finite xy (the forward's tests); re-checked so that a
+             * corrupted map cannot produce garbage.  hoc_face_back on the rotated vertices is NOT bit-identical,
+             * so the face is tested in its stored order. */
+            float f[9];
+            f[0] = (edge == 0) ? ax : ((edge == 1) ? cx : bx);
+            f[1] = (edge == 0) ? ay : ((edge == 1) ? cy : by);
+            f[3] = (edge == 0) ? bx : ((edge == 1) ? ax : cx);
+            f[4] = (edge == 0) ? by : ((edge == 1) ? ay : cy);
+            f[6] = (edge == 0) ? cx : ((edge == 1) ? bx : ax);
+            f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
+            f[2] = f[5] = f[8] = 0.0f;
+            if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
+                float *gf = grad_faces + ((long)b * F + fi) * 9;
+                hoc_k4_pixel_combo(ax, ay, bx, by, cx, cy, edge, axis, xi, yi, M, I, g, eps, line_count, emitters,
+                                   gf + 3 * ia, gf + 3 * ib);
+            }
         }
-        __syncthreads();
-        if (wid == 0 && fi >= 0) {
-            const unsigned fl0 = s_fl[0][lane] | s_fl[2][lane] | s_fl[4][lane];
-            const unsigned fl1 = s_fl[1][lane] | s_fl[3][lane] | s_fl[5][lane];
-            const int P = hoc_flag_pitch(S);
-            uint8_t *fl_col = flags + ((long)b * 2 + 0) * S * P;
-            uint8_t *fl_row = flags + ((long)b * 2 + 1) * S * P;
-            if (fl0)
-                fl_col[(long)xi * P + yi] = (uint8_t)fl0;
-            if (fl1)
-                fl_row[(long)yi * P + xi] = (uint8_t)fl1;
-        }
-        __syncthreads();
     }
 }
 
@@ -527,35 +504,36 @@ hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__rest
  */
 #define LN_THREADS 256
 #define LN_WARPS (LN_THREADS / 32)
-template <int G>
+template <int G, int CH>
 __global__ void __launch_bounds__(LN_THREADS)
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int B, int F, int S, float eps, int layout,
-                           int use_alpha, const int *__restrict__ ext, const uint8_t *__restrict__ flags,
-                           float *__restrict__ grad_faces, int seg)
+                           int use_alpha, const int *__restrict__ ext, const int *__restrict__ line_count,
+                           const unsigned short *__restrict__ emitters, float *__restrict__ grad_faces)
 {
-    /* dynamic shared memory: float4 s_line4[G][S] | ushort s_queue[G * 3 S]
+    /* dynamic shared memory: float4 s_line4[G][S]
      * per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (the inside pixel of a scan
      * is covered, its alpha is 1): delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_rgb Iin_ch g_ch -- one 16-byte
      * shared load and three FMAs per scanned pixel (<= 1 ulp of |P| from the reference's summation order,
      * gradients carry 1e-3) */
     extern __shared__ float4 s_line4[];
-    __shared__ int s_wtot[LN_WARPS];
-    __shared__ int s_lo[G], s_hi[G];
-    /* 1-D grid, sample fastest, line groups ordered from the image centre outwards: the lines that carry the
-     * most scans (meshes are centred by the crop) are dispatched first, the empty border lines form the tail */
-    const int ngroups = (S + G - 1) / G;
-    const int b = blockIdx.x % B;
-    const int rest = blockIdx.x / B;
-    const int axis = rest & 1;
-    const int k = rest >> 1;
+    __shared__ int s_lo[G], s_hi[G], s_n[G + 1];
+    /* grid (B, 2, groups): sample fastest, line groups ordered from the image centre outwards: the lines that
+     * carry the most scans (meshes are centred by the crop) are dispatched first, the empty border lines last */
+    const int ngroups = gridDim.z;
+    const int b = blockIdx.x, axis = blockIdx.y, k = blockIdx.z;
     const int grp = (ngroups >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1)); /* c, c-1, c+1, c-2, ...: a bijection */
     const int d0_base = grp * G;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
     const int *e = ext + (long)b * 4 * S;
-    int ulo, uhi;
-    if (G == 1) { /* a line without incoming gradient: leave before anything else is computed */
+    const int *lc = line_count + ((long)b * 2 + axis) * S;
+    int ulo, uhi, n;
+    if (G == 1) { /* a line without scans or without incoming gradient: leave before anything else is computed */
+        n = min(lc[d0_base], 3 * S);
+        if (n == 0)
+            return;
         ulo = e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
         uhi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_base];
         if (ulo > uhi)
@@ -563,107 +541,44 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         if (tid == 0) {
             s_lo[0] = ulo;
             s_hi[0] = uhi;
+            s_n[0] = 0;
+            s_n[1] = n;
         }
         __syncthreads();
     } else {
-        if (tid < G) {
-            const int d0 = d0_base + tid;
-            int lo = 0x7f7f7f7f, hi = -1;
-            if (d0 < S) {
-                lo = (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0];
-                hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
+        if (tid == 0) {
+            int run = 0;
+            for (int l = 0; l < G; l++) {
+                const int d0 = d0_base + l;
+                int lo = 0x7f7f7f7f, hi = -1, cnt = 0;
+                if (d0 < S) {
+                    lo = (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0];
+                    hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
+                    cnt = (lo <= hi) ? min(lc[d0], 3 * S) : 0;
+                }
+                s_lo[l] = lo;
+                s_hi[l] = hi;
+                s_n[l] = run; /* exclusive prefix of the queue lengths */
+                run += cnt;
             }
-            s_lo[tid] = lo;
-            s_hi[tid] = hi;
+            s_n[G] = run;
         }
         __syncthreads();
+        n = s_n[G];
+        if (n == 0)
+            return; /* no scans, or no incoming gradient anywhere on these lines */
         ulo = 0x7f7f7f7f;
         uhi = -1;
 #pragma unroll
         for (int l = 0; l < G; l++) {
-            ulo = min(ulo, s_lo[l]);
-            uhi = max(uhi, s_hi[l]);
-        }
-        if (ulo > uhi)
-            return; /* no incoming gradient anywhere on these lines: every outward scan sums zeros */
-    }
-    const int ulen = uhi - ulo + 1;
-    unsigned short *s_queue = reinterpret_cast<unsigned short *>(s_line4 + (size_t)G * S);
-    const int cap = G * 3 * S;
-
-    /* 1. the scans of the G lines, compacted in position order (4 positions x G lines at a time): towards + from
-     *    the front of the queue (length falls with position), towards - from the back (length grows with
-     *    position), so that the lanes of a warp get scans of nearly equal length.  A scan that starts beyond the
-     *    span of non-zero gradient of its line has nothing to sum and is dropped here.
-     *    entry = position | edge << 11 | line << 13 */
-    const int P = hoc_flag_pitch(S);
-    const int my_l = tid % G, my_grp = tid / G;
-    const int my_d0 = d0_base + my_l;
-    const uint8_t *fl = flags + (((long)b * 2 + axis) * S + min(my_d0, S - 1)) * P;
-    const int my_lo = s_lo[my_l], my_hi = s_hi[my_l];
-    const int T = blockDim.x; /* multiple of 32 and of G, <= LN_THREADS */
-    const int POS_PER_ITER = 4 * (T / G);
-    int nP = 0, nN = 0;
-    for (int base = 0; base < S; base += POS_PER_ITER) {
-        const int i0 = base + 4 * my_grp;
-        uint32_t v4 = 0u;
-        if (i0 < S && my_lo <= my_hi)
-            v4 = *reinterpret_cast<const uint32_t *>(fl + i0);
-        unsigned mP[4], mN[4];
-        int cP = 0, cN = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = i0 + k;
-            const unsigned v = (i < S) ? ((v4 >> (8 * k)) & 0xffu) : 0u;
-            mP[k] = v & (v >> 3) & 7u;
-            mN[k] = v & ~(v >> 3) & 7u;
-            if (i + 1 > my_hi)
-                mP[k] = 0u;
-            if (i - 1 < my_lo)
-                mN[k] = 0u;
-            cP += __popc(mP[k]);
-            cN += __popc(mN[k]);
-        }
-        const int mine = cP | (cN << 16);
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        if (lane == 31)
-            s_wtot[wid] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < (T >> 5); w++) {
-            const int t = s_wtot[w];
-            if (w < wid)
-                before += t;
-            total += t;
-        }
-        if (mine != 0) {
-            const int excl = before + incl - mine;
-            int pP = nP + (excl & 0xffff), pN = nN + (excl >> 16);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int rec = (i0 + k) | (my_l << 13);
-#pragma unroll
-                for (int ed = 0; ed < 3; ed++) {
-                    if (mP[k] & (1u << ed))
-                        s_queue[pP++] = (unsigned short)(rec | (ed << 11));
-                    if (mN[k] & (1u << ed))
-                        s_queue[cap - 1 - (pN++)] = (unsigned short)(rec | (ed << 11));
-                }
+            if (s_n[l + 1] > s_n[l]) {
+                ulo = min(ulo, s_lo[l]);
+                uhi = max(uhi, s_hi[l]);
             }
         }
-        nP += total & 0xffff;
-        nN += total >> 16;
-        __syncthreads();
     }
-    const int n = nP + nN;
-    if (n == 0)
-        return;
+    const int ulen = uhi - ulo + 1;
+    const unsigned short *queue = emitters + (((long)b * 2 + axis) * S + d0_base) * 3 * S;
 
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
@@ -696,108 +611,97 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     }
     __syncthreads();
 
-    /* 3. the scans, LN_THREADS at a time.  (a) One lane sets up one scan (edge geometry, colour of the inside
-     *    pixel, range) and leaves it in shared memory; (b) the scans are cut into segments of at most `seg`
-     *    pixels and every lane sums one segment, so that a warp's lanes finish together however different the
-     *    scan lengths are; each segment adds its two vertex contributions to grad_faces. */
+    /* 3. the scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane sets up
+     *    one scan (edge geometry, colour of the inside pixel, range) in registers; (b) the warp's scans are cut
+     *    into chunks of CH pixels and every lane sums one chunk -- it finds its scan with a 5-step search over the
+     *    warp's prefix sums and fetches the scan's constants with shuffles -- so that the lanes finish together
+     *    however different the scan lengths are.  The chunk loop is fully unrolled and branch-free: a pixel beyond
+     *    the end of the scan, or with delta <= 0, adds 0 * (1 / dist).  Each chunk adds its two vertex
+     *    contributions to grad_faces. */
     const float scale = 2.0f / (float)S;
-    __shared__ float r_cA[LN_THREADS], r_cB[LN_THREADS], r_cross[LN_THREADS], r_I1[LN_THREADS], r_I2[LN_THREADS],
-        r_I3[LN_THREADS];
-    __shared__ int r_from[LN_THREADS], r_to[LN_THREADS], r_gfA[LN_THREADS], r_gfB[LN_THREADS], r_row[LN_THREADS];
-    __shared__ int s_pre[LN_THREADS + 1];
-    for (int q0 = 0; q0 < n; q0 += T) {
-        const int q = q0 + tid;
-        int nseg = 0;
+    const float peps = eps, neps = -eps;
+    for (int q0 = wid * 32; q0 < n; q0 += T) {
+        const int q = q0 + lane;
+        float r_cA = 0.0f, r_cB = 0.0f, r_cross = 0.0f, r_I1 = 0.0f, r_I2 = 0.0f, r_I3 = 0.0f;
+        int r_from = 0, r_to = -1, r_row = 0, r_gfA = 0, r_gfB = 0, nchunk = 0;
         if (q < n) {
-            const int rec = (q < nP) ? s_queue[q] : s_queue[cap - 1 - (q - nP)];
-            const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3, l = rec >> 13;
+            int l = 0;
+#pragma unroll
+            for (int j = 1; j < G; j++)
+                l += (q >= s_n[j]) ? 1 : 0;
+            const int rec = queue[(long)l * 3 * S + (q - s_n[l])];
+            const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3;
             const int d0 = d0_base + l;
             const int lo = s_lo[l], hi = s_hi[l];
             const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
             const int fi = idx[(long)yin * S + xin];
-            float I1 = 0.0f, I2 = 0.0f, I3 = 0.0f; /* rgb of the inside pixel (its alpha is 1: folded into P) */
-            if (has_rgb) {
-                I1 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 0)];
-                I2 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 1)];
-                I3 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 2)];
+            if (has_rgb) { /* rgb of the inside pixel (its alpha is 1: folded into P) */
+                r_I1 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 0)];
+                r_I2 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 1)];
+                r_I3 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 2)];
             }
-            if (fi >= 0) { /* always: the cover pass flags owned pixels only */
+            if (fi >= 0) { /* always: the cover pass queues owned pixels only */
                 const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
                 const float *src = faces + ((long)b * F + fi) * 9;
                 const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
                 const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
                 HocK4Edge E;
                 hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
-                float d1_cross;
                 int d1_chk, d1_out;
-                /* always true: the cover pass flagged this column because it passed the same test */
-                if (hoc_k4_column(&E, S, d0, &d1_cross, &d1_chk, &d1_out)) {
-                    const int d1_from = (0 < E.dir) ? max(d1_out, lo) : lo;
-                    const int d1_to = (0 < E.dir) ? hi : min(d1_out, hi);
+                /* always true: the cover pass queued this column because it passed the same test */
+                if (hoc_k4_column(&E, S, d0, &r_cross, &d1_chk, &d1_out)) {
+                    r_from = (0 < E.dir) ? max(d1_out, lo) : lo;
+                    r_to = (0 < E.dir) ? hi : min(d1_out, hi);
                     HocK4Col C;
-                    hoc_k4_col(&E, S, d0, d1_cross, &C);
+                    hoc_k4_col(&E, S, d0, r_cross, &C);
                     /* a vertex that gets no contribution: infinite distance -> 1 / dist = 0 (d1 - cross != 0) */
-                    r_cA[tid] = C.hasA ? C.cA * scale : __int_as_float(0x7f800000);
-                    r_cB[tid] = C.hasB ? C.cB * scale : __int_as_float(0x7f800000);
-                    r_cross[tid] = d1_cross;
-                    r_I1[tid] = I1;
-                    r_I2[tid] = I2;
-                    r_I3[tid] = I3;
-                    r_from[tid] = d1_from;
-                    r_to[tid] = d1_to;
-                    r_row[tid] = l * S - ulo;
+                    r_cA = C.hasA ? C.cA * scale : __int_as_float(0x7f800000);
+                    r_cB = C.hasB ? C.cB * scale : __int_as_float(0x7f800000);
+                    r_row = l * S - ulo;
                     const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
-                    r_gfA[tid] = gbase + ia * 3;
-                    r_gfB[tid] = gbase + ib * 3;
-                    if (d1_to >= d1_from)
-                        nseg = (d1_to - d1_from + seg) / seg;
+                    r_gfA = gbase + ia * 3;
+                    r_gfB = gbase + ib * 3;
+                    if (r_to >= r_from)
+                        nchunk = (r_to - r_from + CH) / CH;
                 }
             }
         }
-        /* exclusive prefix of the segment counts */
-        int incl = nseg;
+        int incl = nchunk;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
             if (lane >= o)
                 incl += t;
         }
-        if (lane == 31)
-            s_wtot[wid] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < (T >> 5); w++) {
-            const int t = s_wtot[w];
-            if (w < wid)
-                before += t;
-            total += t;
-        }
-        s_pre[tid] = before + incl - nseg;
-        if (tid == 0)
-            s_pre[T] = total;
-        __syncthreads();
-        for (int j = tid; j < total; j += T) {
-            int a = 0, c = T; /* last scan with s_pre[scan] <= j */
-            while (c - a > 1) {
-                const int mid = (a + c) >> 1;
-                if (s_pre[mid] <= j)
-                    a = mid;
-                else
-                    c = mid;
+        const int pre = incl - nchunk;
+        const int total = __shfl_sync(HOC_FULL_MASK, incl, 31);
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = min(j0 + lane, total - 1);
+            const bool live = j0 + lane < total;
+            int a = 0; /* last scan with pre <= j */
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+                const int pv = __shfl_sync(HOC_FULL_MASK, pre, (a + st) & 31);
+                if (a + st < 32 && pv <= j)
+                    a += st;
             }
-            const int d1_from = r_from[a] + (j - s_pre[a]) * seg;
-            const int d1_to = min(r_to[a], d1_from + seg - 1);
-            const float cA = r_cA[a], cB = r_cB[a], I1 = r_I1[a], I2 = r_I2[a], I3 = r_I3[a];
-            const float peps = eps, neps = -eps;
+            const int c0 = (j - __shfl_sync(HOC_FULL_MASK, pre, a)) * CH;
+            const int d1_from = __shfl_sync(HOC_FULL_MASK, r_from, a) + c0;
+            const int to_a = __shfl_sync(HOC_FULL_MASK, r_to, a); /* (every shuffle outside any lane-dependent branch) */
+            const int left = live ? to_a - d1_from : -1;          /* pixels beyond the first */
+            const float cA = __shfl_sync(HOC_FULL_MASK, r_cA, a), cB = __shfl_sync(HOC_FULL_MASK, r_cB, a);
+            const float I1 = __shfl_sync(HOC_FULL_MASK, r_I1, a), I2 = __shfl_sync(HOC_FULL_MASK, r_I2, a),
+                        I3 = __shfl_sync(HOC_FULL_MASK, r_I3, a);
+            const float u0 = (float)d1_from - __shfl_sync(HOC_FULL_MASK, r_cross, a);
+            const float4 *sp = s_line4 + (__shfl_sync(HOC_FULL_MASK, r_row, a) + d1_from);
+            const int gfA = __shfl_sync(HOC_FULL_MASK, r_gfA, a), gfB = __shfl_sync(HOC_FULL_MASK, r_gfB, a);
             float gA = 0.0f, gB = 0.0f;
-            float u = (float)d1_from - r_cross[a];
-            const float4 *sp = s_line4 + (r_row[a] + d1_from);
-            /* branch-free body: a pixel with delta <= 0 adds 0 * (1 / dist); MUFU.RCP (2 ulp) for 1 / dist -- the
-             * pseudo-gradient carries a 1e-3 tolerance and this quotient is the hot instruction of the pass */
-            for (int k = d1_to - d1_from; k >= 0; k--, sp++, u += 1.0f) {
-                const float4 pg = *sp;
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const float4 pg = sp[k]; /* at most CH - 1 entries past the staged span: the buffer is padded */
                 float delta = pg.x - __fmaf_rn(I3, pg.w, __fmaf_rn(I2, pg.z, I1 * pg.y));
-                delta = (delta <= 0.0f) ? 0.0f : delta;
+                delta = (delta <= 0.0f || k > left) ? 0.0f : delta;
+                const float u = u0 + (float)k;
                 float dA = cA * u, dB = cB * u;
                 dA += (0.0f < dA) ? peps : neps;
                 dB += (0.0f < dB) ? peps : neps;
@@ -805,11 +709,10 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 gB = __fmaf_rn(-delta, hoc_rcp_approx(dB), gB);
             }
             if (gA != 0.0f)
-                atomicAdd(grad_faces + r_gfA[a], gA);
+                atomicAdd(grad_faces + gfA, gA);
             if (gB != 0.0f)
-                atomicAdd(grad_faces + r_gfB[a], gB);
+                atomicAdd(grad_faces + gfB, gB);
         }
-        __syncthreads();
     }
 }
 
@@ -825,6 +728,7 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_line_threads = value;
     else if (key == HOC_TUNE_LINE_SEGMENT && value >= 1 && value <= 4096)
         g_line_seg = value;
+
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -832,26 +736,26 @@ extern "C" int hoc_set_tuning(int key, int value)
     return HOC_OK;
 }
 
-template <int G>
+template <int G, int CH>
 static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index_map, const float *rgb,
                                    const float *grad_rgb, const float *g_alpha, int B, int F, int S, float eps,
                                    int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
                                    cudaStream_t st)
 {
-    static size_t smem_allowed = 32 * 1024; /* static arrays of the kernel take ~13 KB of the default 48 KB */
-    const size_t smem = (size_t)G * S * (sizeof(float4) + 3 * sizeof(unsigned short));
+    static size_t smem_allowed = 48 * 1024;
+    const size_t smem = ((size_t)G * S + 16) * sizeof(float4); /* + padding for the unrolled chunk loop */
     if (smem > smem_allowed) {
-        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<G, CH>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
         smem_allowed = smem;
     }
-    const unsigned grid = (unsigned)((S + G - 1) / G) * 2u * (unsigned)B;
+    dim3 grid(B, 2, (S + G - 1) / G);
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_raster_bwd_line_kernel<G><<<grid, g_line_threads, smem, st>>>(
-                   faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w.ext, w.flags,
-                   grad_faces, g_line_seg)));
+               (hoc_raster_bwd_line_kernel<G, CH><<<grid, g_line_threads, smem, st>>>(
+                   faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w.ext, w.line_count,
+                   w.emitters, grad_faces)));
     return cudaSuccess;
 }
 
@@ -876,7 +780,7 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_backward: image_size %d outside [1, 2048]", S);
     HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_backward: bad layout %d",
                   layout);
-    HOC_CHECK_ARG(B <= 65535, "hoc_raster_backward: batch %d exceeds 65535", B);
+    HOC_CHECK_ARG(B <= 65535, "hoc_raster_backward: batch %d exceeds 65535", B); /* grid.y / grid.z limits */
     HOC_CHECK_ARG(F < (1 << 29), "hoc_raster_backward: face count %d exceeds 2^29", F);
     HOC_CHECK_ARG(grad_textures == nullptr || ts >= 1, "hoc_raster_backward: texture_size %d", ts);
     HOC_CHECK_ARG(grad_rgb == nullptr || rgb != nullptr, "hoc_raster_backward: grad_rgb given without rgb");
@@ -922,13 +826,12 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         if (k4)
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
-                           face_index_map, grad_rgb, g_alpha, S, layout, list_all, w.ext, w.cov_count, w.cov_list,
-                           w.flags)));
+                           face_index_map, grad_rgb, g_alpha, S, layout, list_all, w.ext, w.cov_count, w.cov_list)));
         else
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
                            face_index_map, gt != nullptr ? grad_rgb : nullptr, nullptr, S, layout, list_all, w.ext,
-                           w.cov_count, w.cov_list, w.flags)));
+                           w.cov_count, w.cov_list)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
     }
     {
@@ -940,7 +843,7 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                (hoc_raster_bwd_cover_kernel<TS2, K4><<<cg, K4 ? CV_THREADS_K4 : CV_THREADS, 0, st>>>(                 \
                    faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
                    eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
-                   w.flags, grad_faces, gt)))
+                   w.line_count, w.emitters, grad_faces, gt)))
         if (ts == 2 && k4)
             HOC_COVER_LAUNCH(true, true);
         else if (ts == 2)
@@ -962,12 +865,15 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
     }
     if (k4) {
-        /* lines per CTA: bounded by staging + queue (22 bytes per pixel of a line) */
+        /* lines per CTA: bounded by the staging buffer (16 bytes per pixel of a line) */
         int G = g_line_G ? g_line_G : 1;
-        while (G > 1 && (size_t)G * S * 22 > 96 * 1024)
+        while (G > 1 && (size_t)G * S * 16 > 96 * 1024)
             G >>= 1;
-#define HOC_LINE(G_) hoc_launch_line<G_>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w, grad_faces, st)
-        e = (G == 8) ? HOC_LINE(8) : (G == 4) ? HOC_LINE(4) : (G == 2) ? HOC_LINE(2) : HOC_LINE(1);
+#define HOC_LINE(G_, C_) hoc_launch_line<G_, C_>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w, grad_faces, st)
+        if (g_line_seg >= 16)
+            e = (G == 8) ? HOC_LINE(8, 16) : (G == 4) ? HOC_LINE(4, 16) : (G == 2) ? HOC_LINE(2, 16) : HOC_LINE(1, 16);
+        else
+            e = (G == 8) ? HOC_LINE(8, 8) : (G == 4) ? HOC_LINE(4, 8) : (G == 2) ? HOC_LINE(2, 8) : HOC_LINE(1, 8);
 #undef HOC_LINE
         if (e != cudaSuccess) {
             hoc_set_error("hoc_raster_backward: cannot reserve shared memory for the line pass: %s",
