@@ -419,6 +419,44 @@ def cpu_baseline(sample_pairs=4, steps=4, warmup=1):
                       f"oracle/ C restatement (pthreads over pixels/faces) + torch CPU warp/loss"}
 
 
+def gpu_ref_equiv(steps=3, warmup=1):
+    """the reference's launch structure restated on the same GPU (baseline/ref_equiv: per-pixel
+    all-faces forward, one serial thread per face for the pseudo-gradient, ATen grid_sample, separate element-wise
+    ops), same workload, inputs resident, CUDA-event timed.  A labelled RESTATEMENT -- the upstream CUDA extension is
+    not installable here -- used as the denominator of the north star's ">= 10x on one B200"."""
+    import torch
+
+    from baseline import ref_equiv  # benchmark baseline; never on the product path
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    sets = _make_sets(2, PAIRS, SIZE, dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def one(i):
+        sc = sets[i % 2]
+        v1 = sc["verts1"].clone().requires_grad_(True)
+        loss, _ = ref_equiv.consist_step(v1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                         sc["jitter_mask_ref"], sc["jitter_mask"], SIZE, (SIZE, SIZE),
+                                         sc["hand_ignore_faces"], detach_renders=False, use_backward=True)
+        loss.backward()
+        return loss
+
+    for i in range(warmup):
+        one(i)
+    torch.cuda.synchronize()
+    t0.record()
+    for i in range(steps):
+        loss = one(i)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    return {"value": 2 * PAIRS / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "kind": "restated",
+            "loss": float(loss.detach()),
+            "note": "baseline/ref_equiv: the reference's five rasterizer kernels restated one thread per item "
+                    "(all-faces forward, serial per-face pseudo-gradient) + the reference's op-by-op torch composition "
+                    "with ATen grid_sample, on this GPU, same workload; NOT the upstream binary (not installable)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return None
@@ -450,6 +488,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-equiv", action="store_true", help="skip the GPU reference-equivalent baseline leg")
     ap.add_argument("--eager-only", action="store_true", help="profiling aid: run only the eager arm (ncu)")
     ap.add_argument("--pairs", type=int, default=PAIRS, help="frame pairs per rank and step (default: configs[2])")
     ap.add_argument("--size", type=int, default=SIZE, help="raster / image side (default: configs[2])")
@@ -478,6 +517,12 @@ def main():
     args.warmup = max(args.warmup, 3)
     out = run_native(args, rank, world, local_rank)
     if out is not None:
+        if world == 1 and not args.no_ref_equiv:
+            try:
+                out["gpu_ref_equiv"] = gpu_ref_equiv()
+                out["gpu_ref_equiv"]["speedup_of_value"] = out["value"] / out["gpu_ref_equiv"]["value"]
+            except Exception as exc:  # a baseline leg must never cost the bench line
+                out["gpu_ref_equiv"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), flush=True)

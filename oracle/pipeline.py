@@ -50,11 +50,13 @@ class RasterizeFunctionOracle(Function):
 
 
 def rasterize_rgbad(faces, textures, image_size, anti_aliasing, near, far, eps, background_color, return_rgb=True,
-                    return_alpha=True, return_depth=True, grad_dtype=np.float32):
+                    return_alpha=True, return_depth=True, grad_dtype=np.float32, raster_fn=None):
+    """``raster_fn``: a drop-in for ``RasterizeFunctionOracle.apply`` (same 11 arguments, same 6 outputs); the GPU
+    reference-equivalent baseline (baseline/ref_equiv) plugs its one-thread-per-item CUDA drivers in here."""
     S = image_size * 2 if anti_aliasing else image_size
-    rgb, alpha, depth, idx, inv, w = RasterizeFunctionOracle.apply(faces, textures, S, near, far, eps,
-                                                                   background_color, return_rgb, return_alpha,
-                                                                   return_depth, grad_dtype)
+    raster_fn = RasterizeFunctionOracle.apply if raster_fn is None else raster_fn
+    rgb, alpha, depth, idx, inv, w = raster_fn(faces, textures, S, near, far, eps, background_color, return_rgb,
+                                               return_alpha, return_depth, grad_dtype)
     if return_rgb:
         rgb = rgb.permute(0, 3, 1, 2).flip(2)
     if return_alpha:
@@ -71,20 +73,20 @@ def rasterize_rgbad(faces, textures, image_size, anti_aliasing, near, far, eps, 
 
 
 def render(vertices, faces, textures, K, image_size, detach_renders=False, fill_back=True, anti_aliasing=False,
-           near=0.1, far=100.0, eps=1e-3, background_color=(0, 0, 0), grad_dtype=np.float32):
+           near=0.1, far=100.0, eps=1e-3, background_color=(0, 0, 0), grad_dtype=np.float32, raster_fn=None):
     """Renderer.render with the WarpRegNet settings (R = I, t = 0, no distortion, no light)."""
     if fill_back:
         faces, textures = nrfuncs.fill_back(faces, textures)
         faces = faces.detach()
-    R = torch.eye(3, dtype=vertices.dtype)[None]
-    t = torch.zeros(1, 1, 3, dtype=vertices.dtype)
-    dist = torch.zeros(1, 5, dtype=vertices.dtype)
+    R = torch.eye(3, dtype=vertices.dtype, device=vertices.device)[None]
+    t = torch.zeros(1, 1, 3, dtype=vertices.dtype, device=vertices.device)
+    dist = torch.zeros(1, 5, dtype=vertices.dtype, device=vertices.device)
     ndc = nrfuncs.projection(vertices, K, R, t, dist, float(image_size))
     f = nrfuncs.vertices_to_faces(ndc, faces)
     if detach_renders:
         f = f.detach()
     return rasterize_rgbad(f, textures, image_size, anti_aliasing, near, far, eps, background_color,
-                           grad_dtype=grad_dtype)
+                           grad_dtype=grad_dtype, raster_fn=raster_fn)
 
 
 def _ignore_mask(face_index_map, ignore_face_idxs):
@@ -95,21 +97,23 @@ def _ignore_mask(face_index_map, ignore_face_idxs):
 
 def get_opticalflow(verts_cam, faces, camintrs, image_size, orig_img_size=None, mask_occlusions=True,
                     detach_textures=False, detach_renders=True, ignore_face_idxs=None, grad_dtype=np.float32,
-                    warp_device=None):
+                    warp_device=None, raster_fn=None):
     loc1 = nrfuncs.batch_proj2d(verts_cam[0], camintrs[0])
     loc2 = nrfuncs.batch_proj2d(verts_cam[1], camintrs[1])
     d12 = loc2 - loc1
     tex = nrfuncs.batch_vertex_textures(faces, torch.cat([d12, torch.ones_like(d12[:, :, :1])], -1))
     if detach_textures:
         tex = tex.detach()
-    out = render(verts_cam[0], faces, tex, camintrs[0], image_size, detach_renders, grad_dtype=grad_dtype)
+    out = render(verts_cam[0], faces, tex, camintrs[0], image_size, detach_renders, grad_dtype=grad_dtype,
+                 raster_fn=raster_fn)
     mask1 = (out["alpha"].unsqueeze(1) > 0.99999).float()
     if ignore_face_idxs is not None:
         mask1 = mask1 * _ignore_mask(out["face_index_map"], ignore_face_idxs)
     flow12 = out["rgb"] * mask1
     d21 = loc1 - loc2
     tex = nrfuncs.batch_vertex_textures(faces, torch.cat([d21, torch.ones_like(d21[:, :, :1])], -1))
-    out = render(verts_cam[1], faces, tex, camintrs[1], image_size, detach_renders, grad_dtype=grad_dtype)
+    out = render(verts_cam[1], faces, tex, camintrs[1], image_size, detach_renders, grad_dtype=grad_dtype,
+                 raster_fn=raster_fn)
     mask2 = (out["alpha"].unsqueeze(1) > 0.99999).float()
     if ignore_face_idxs is not None:
         mask2 = mask2 * _ignore_mask(out["face_index_map"], ignore_face_idxs)
@@ -120,7 +124,7 @@ def get_opticalflow(verts_cam, faces, camintrs, image_size, orig_img_size=None, 
             if warp_device is not None:  # the reference runs these ATen ops on CUDA
                 o1, o2 = owarp.get_occlusion_mask(mask1.to(warp_device), mask2.to(warp_device),
                                                   flow12.to(warp_device), flow21.to(warp_device))
-                o1, o2 = o1.cpu(), o2.cpu()
+                o1, o2 = o1.to(mask1.device), o2.to(mask1.device)
             else:
                 o1, o2 = owarp.get_occlusion_mask(mask1, mask2, flow12, flow21)
         mask1 = mask1 * o1.unsqueeze(1)
@@ -137,14 +141,14 @@ def get_opticalflow(verts_cam, faces, camintrs, image_size, orig_img_size=None, 
 
 def consist_step(verts1, verts2, faces, K, image_ref, image, jitter_mask_ref, jitter_mask, image_size, orig_img_size,
                  ignore_face_idxs=None, detach_renders=True, use_backward=True, grad_dtype=np.float32,
-                 warp_device=None):
+                 warp_device=None, raster_fn=None):
     """flows -> pair_consist -> mean over the batch (warpbranch.py:57-88 for one pair).
 
     ``warp_device``: run the warp / mask / loss ATen ops there (autograd crosses devices).  The
     reference's masks hold exact float tests (== 1, >= 0.99999) whose outcome depends on the rounding
     of ATen's CPU vs CUDA grid_sampler; the reference runs them on CUDA, so the GPU tests pass "cuda"."""
     flows = get_opticalflow([verts1, verts2], faces, [K, K], image_size, orig_img_size, True, False, detach_renders,
-                            ignore_face_idxs, grad_dtype, warp_device)
+                            ignore_face_idxs, grad_dtype, warp_device, raster_fn)
     if warp_device is not None:
         mv = lambda t: t.to(warp_device)
         flows = [mv(f) for f in flows]
