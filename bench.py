@@ -296,15 +296,17 @@ def run_native(args, rank, world, local_rank):
     algo = {
         "raster_zbuf": PAIRS * F2 * 36 + npx * 8,                       # faces in, 8-byte depth/face key per pixel
         "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 96) + npx * 24,   # key, faces+textures, rgb12+alpha4+depth4+idx4
-        # scan pass (streaming): idx + grad_rgb in; covered-pixel list (4 B per covered pixel, counted as idx-sized)
-        # and two zeroed flag bytes per pixel out
-        "raster_bwd_pixel": npx * (4 + 12 + 2),
+        # scan pass (streaming): idx + grad_rgb in; list of covered pixels (4 B per listed pixel, bounded by npx * 4,
+        # counted at the measured 7 % coverage) and the zero-fill of grad_faces + grad of the 9 vertex values out
+        "raster_bwd_pixel": npx * (4 + 12) + int(0.07 * npx) * 4 + PAIRS * F2 * (36 + 36),
         # cover pass, texture gradient only: per listed pixel idx, grad_rgb, weights, depth; faces in; 9 sums per face out
-        "raster_bwd_cover": npx * (4 + 12 + 12 + 4) + PAIRS * F2 * (36 + 36),
-        # cover pass with the pseudo-gradient: + rgb in, flag bytes out, grad_faces (memset + update)
-        "raster_bwd_pixel_k4": npx * (4 + 12 + 12 + 4 + 12 + 2) + PAIRS * F2 * (36 + 36 + 36),
+        "raster_bwd_cover": int(0.07 * npx) * (4 + 4 + 12 + 12 + 4) + PAIRS * F2 * (36 + 36),
+        # cover pass with the pseudo-gradient: + rgb in, scan records out, grad_faces update
+        "raster_bwd_pixel_k4": int(0.07 * npx) * (4 + 4 + 12 + 12 + 4 + 12 + 2) + PAIRS * F2 * (36 + 36 + 36),
         "raster_backward": PAIRS * F2 * (36 + 12 + 36),                  # depth epilogue (only with dL/ddepth)
-        "raster_bwd_line": npx * (12 + 12 + 4 + 2) + PAIRS * F2 * 36,    # line pass: rgb, grad_rgb, idx, flags once; grad_faces update
+        # line pass: rgb + grad_rgb of the lines' spans once per axis (bounded by the whole map), scan records, faces of
+        # the queued scans, grad_faces update
+        "raster_bwd_line": 2 * npx * (12 + 12) + PAIRS * F2 * (36 + 36),
         "warp_photo_fwd": npx * (12 + 8 + 12 + 4 + 4 + 12 + 12 + 12 + 1),
         "warp_photo_bwd": npx * (12 + 8 + 12 + 1 + 8),
         "flow_finalize": 2 * npx * (2 * (8 + 4 + 4) + 8 + 4),

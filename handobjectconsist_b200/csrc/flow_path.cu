@@ -489,6 +489,59 @@ hoc_flow_vertices_backward_kernel(const float *__restrict__ verts1, const float 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* batch_cat_meshes for a hand + object pair, both frames of a pair in one launch: verts = cat(hand, obj) along the
+ * vertex axis, faces = cat(hand_faces, obj_faces + Vh) along the face axis (the hand's table may be shared by the
+ * whole batch). */
+__global__ void __launch_bounds__(FP_THREADS)
+hoc_cat_meshes_kernel(const float *__restrict__ hand_a, const float *__restrict__ obj_a,
+                      const float *__restrict__ hand_b, const float *__restrict__ obj_b,
+                      const long long *__restrict__ hand_faces, int hand_faces_batched,
+                      const long long *__restrict__ obj_faces, int B, int Vh, int Vo, int Fh, int Fo,
+                      float *__restrict__ verts_a, float *__restrict__ verts_b, long long *__restrict__ faces)
+{
+    const long nv = (long)B * (Vh + Vo) * 3, nf = (faces != nullptr) ? (long)B * (Fh + Fo) * 3 : 0;
+    const long total = nv * (verts_b != nullptr ? 2 : 1) + nf;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        if (i >= total - nf) { /* the face table */
+            const long j = i - (total - nf);
+            const int per = (Fh + Fo) * 3;
+            const int b = (int)(j / per), r = (int)(j - (long)b * per);
+            faces[j] = (r < Fh * 3) ? hand_faces[(hand_faces_batched ? (long)b * Fh * 3 : 0) + r]
+                                    : obj_faces[(long)b * Fo * 3 + (r - Fh * 3)] + Vh;
+        } else {
+            const bool second = i >= nv;
+            const long j = second ? i - nv : i;
+            const int per = (Vh + Vo) * 3;
+            const int b = (int)(j / per), r = (int)(j - (long)b * per);
+            const float *hand = second ? hand_b : hand_a, *obj = second ? obj_b : obj_a;
+            (second ? verts_b : verts_a)[j] = (r < Vh * 3) ? hand[(long)b * Vh * 3 + r] : obj[(long)b * Vo * 3 + (r - Vh * 3)];
+        }
+    }
+}
+
+extern "C" int hoc_cat_meshes(const float *hand_a, const float *obj_a, const float *hand_b, const float *obj_b,
+                              const long long *hand_faces, int hand_faces_batched, const long long *obj_faces, int B,
+                              int Vh, int Vo, int Fh, int Fo, float *verts_a, float *verts_b, long long *faces,
+                              void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && Vh >= 0 && Vo >= 0 && Fh >= 0 && Fo >= 0, "hoc_cat_meshes: bad shape");
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(hand_a && obj_a && verts_a, "hoc_cat_meshes: NULL vertices");
+    HOC_CHECK_ARG((verts_b == nullptr) || (hand_b && obj_b), "hoc_cat_meshes: second frame requested without inputs");
+    HOC_CHECK_ARG((faces == nullptr) || (hand_faces && obj_faces), "hoc_cat_meshes: faces requested without inputs");
+    const long total = (long)B * (Vh + Vo) * 3 * (verts_b ? 2 : 1) + (faces ? (long)B * (Fh + Fo) * 3 : 0);
+    const unsigned grid = (unsigned)((total + FP_THREADS - 1) / FP_THREADS < 1184 ? (total + FP_THREADS - 1) / FP_THREADS
+                                                                                   : 1184);
+    HOC_LAUNCH(HOC_K_CAT_MESHES, (cudaStream_t)stream,
+               (hoc_cat_meshes_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   hand_a, obj_a, hand_b, obj_b, hand_faces, hand_faces_batched, obj_faces, B, Vh, Vo, Fh, Fo, verts_a,
+                   verts_b, faces)));
+    HOC_CHECK_LAUNCH("hoc_cat_meshes_kernel");
+    return HOC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 extern "C" int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                                int fill_back, float *faces_out, float *textures_out, void *stream)
 {

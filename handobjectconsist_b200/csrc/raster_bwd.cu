@@ -38,7 +38,8 @@
 #define EXT_COL_HI 3
 
 /* Workspace carved by hoc_raster_backward (256-byte aligned regions):
- *   ext        int    [B][4][S]      {row_lo, row_hi, col_lo, col_hi}: span of non-zero incoming gradient
+ *   ext        int    [B][4][S]      {row_nlo, row_hi, col_nlo, col_hi}: span of non-zero incoming gradient, the low
+ *                                    end stored as S - 1 - lo so that both ends are max-reduced from -1 (one 0xff fill)
  *   cov_count  int    [B]            covered pixels listed per sample                      (zero-filled)
  *   line_count int    [B][2][S]      outward scans queued on each line (axis 0: column x, axis 1: row y)  (zero-filled)
  *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
@@ -177,8 +178,18 @@ template <bool K4>
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int S, int layout, int list_all, int *__restrict__ ext,
-                           int *__restrict__ cov_count, int *__restrict__ cov_list)
+                           int *__restrict__ cov_count, int *__restrict__ cov_list, float *__restrict__ zero_a,
+                           long n_a, float *__restrict__ zero_b, long n_b)
 {
+    { /* zero-fill of the two gradient outputs (accumulated with atomics by the later passes), spread over the grid */
+        const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
+        const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 32 +
+                        threadIdx.x;
+        for (long i = t0; i < n_a; i += nthreads)
+            zero_a[i] = 0.0f;
+        for (long i = t0; i < n_b; i += nthreads)
+            zero_b[i] = 0.0f;
+    }
     __shared__ int s_lo[8][32];
     __shared__ int s_hi[8][32];
     __shared__ int s_cnt[33]; /* per warp-row (r * 8 + ty) count, then exclusive prefix; [32] = tile base */
@@ -218,7 +229,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         if (K4) {
             const unsigned m = __ballot_sync(HOC_FULL_MASK, nz);
             if (m != 0 && tx == 0) {
-                atomicMin(&e[EXT_ROW_LO * S + yi], blockIdx.x * 32 + (__ffs(m) - 1));
+                atomicMax(&e[EXT_ROW_LO * S + yi], S - 1 - (blockIdx.x * 32 + (__ffs(m) - 1)));
                 atomicMax(&e[EXT_ROW_HI * S + yi], blockIdx.x * 32 + (31 - __clz(m)));
             }
             if (nz) {
@@ -251,7 +262,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
                 c_hi = max(c_hi, s_hi[r][tx]);
             }
             if (c_hi >= 0) {
-                atomicMin(&e[EXT_COL_LO * S + xi], c_lo);
+                atomicMax(&e[EXT_COL_LO * S + xi], S - 1 - c_lo);
                 atomicMax(&e[EXT_COL_HI * S + xi], c_hi);
             }
         }
@@ -534,7 +545,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         n = min(lc[d0_base], 3 * S);
         if (n == 0)
             return;
-        ulo = e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
+        ulo = S - 1 - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
         uhi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_base];
         if (ulo > uhi)
             return;
@@ -552,7 +563,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 const int d0 = d0_base + l;
                 int lo = 0x7f7f7f7f, hi = -1, cnt = 0;
                 if (d0 < S) {
-                    lo = (axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0];
+                    lo = S - 1 - ((axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0]);
                     hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
                     cnt = (lo <= hi) ? min(lc[d0], 3 * S) : 0;
                 }
@@ -802,21 +813,17 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
 
-    /* cov_count and (directly behind it) acc_d are zero-filled by one memset */
+    /* counters and (directly behind them) acc_d are zero-filled by one memset, the spans by another; the gradient
+     * outputs are zero-filled by the scan pass */
     cudaError_t e = cudaMemsetAsync(w.cov_count, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
-    if (e == cudaSuccess && grad_faces != nullptr) /* accumulated with atomics by the cover and line passes */
-        e = cudaMemsetAsync(grad_faces, 0, sizeof(float) * 9 * (size_t)B * F, st);
-    if (e == cudaSuccess && k4) { /* hi rows = -1, lo rows (every second row of S ints) = 0x7f7f7f7f */
+    if (e == cudaSuccess && k4)
         e = cudaMemsetAsync(w.ext, 0xff, sizeof(int) * 4 * (size_t)B * S, st);
-        if (e == cudaSuccess)
-            e = cudaMemset2DAsync(w.ext, 2 * S * sizeof(int), 0x7f, S * sizeof(int), (size_t)B * 2, st);
-    }
-    if (e == cudaSuccess && grad_textures != nullptr)
-        e = cudaMemsetAsync(grad_textures, 0, tex_bytes, st);
     if (e != cudaSuccess) {
         hoc_set_error("hoc_raster_backward: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;
     }
+    const long n_gf = (grad_faces != nullptr) ? 9l * B * F : 0;
+    const long n_gt = (grad_textures != nullptr) ? (long)(tex_bytes / sizeof(float)) : 0;
     float *gt = (grad_rgb != nullptr) ? grad_textures : nullptr;
     {
         /* without the pseudo-gradient only pixels with a texture gradient (non-zero dL/drgb) or a depth
@@ -826,12 +833,13 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         if (k4)
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
-                           face_index_map, grad_rgb, g_alpha, S, layout, list_all, w.ext, w.cov_count, w.cov_list)));
+                           face_index_map, grad_rgb, g_alpha, S, layout, list_all, w.ext, w.cov_count, w.cov_list, grad_faces,
+                           n_gf, grad_textures, n_gt)));
         else
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
                            face_index_map, gt != nullptr ? grad_rgb : nullptr, nullptr, S, layout, list_all, w.ext,
-                           w.cov_count, w.cov_list)));
+                           w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
     }
     {

@@ -303,6 +303,17 @@ __global__ void hoc_masked_mean_kernel(const double *__restrict__ sums, int B, f
         loss[b] = (float)(sums[2 * b] / fmax(sums[2 * b + 1], 1.0));
 }
 
+/* pair_consist's loss of one frame pair (imgflowarp.py:108-114): loss_bwd + loss_fwd (that order) or loss_fwd. */
+__global__ void hoc_pair_loss_kernel(const double *__restrict__ sums_fwd, const double *__restrict__ sums_bwd, int B,
+                                     float *__restrict__ loss)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
+        const float lf = (float)(sums_fwd[2 * b] / fmax(sums_fwd[2 * b + 1], 1.0));
+        loss[b] = (sums_bwd != nullptr) ? (float)(sums_bwd[2 * b] / fmax(sums_bwd[2 * b + 1], 1.0)) + lf : lf;
+    }
+}
+
 /* d loss[b] / d flow.  loss[b] = sum_valid |warp - target| / max(count, 1); the thresholded masks
  * carry no gradient, so only the bilinear taps of `src` depend on the flow. */
 __global__ void __launch_bounds__(WP_THREADS)
@@ -559,6 +570,18 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
         hoc_masked_mean_kernel<<<(B + 127) / 128, 128, 0, st>>>(sums, B, loss);
         HOC_CHECK_LAUNCH("hoc_masked_mean_kernel");
     }
+    return HOC_OK;
+}
+
+extern "C" int hoc_pair_loss(const double *sums_fwd, const double *sums_bwd, int B, float *loss, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0, "hoc_pair_loss: negative batch %d", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(sums_fwd && loss, "hoc_pair_loss: NULL argument");
+    HOC_LAUNCH(HOC_K_PAIR_LOSS, (cudaStream_t)stream,
+               (hoc_pair_loss_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums_fwd, sums_bwd, B, loss)));
+    HOC_CHECK_LAUNCH("hoc_pair_loss_kernel");
     return HOC_OK;
 }
 

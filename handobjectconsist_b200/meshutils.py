@@ -5,6 +5,9 @@
 Differentiable torch ops on a few thousand vertices; they run on the device of their inputs.
 """
 import torch
+from torch.autograd import Function
+
+from . import _lib
 
 
 def batch_proj2d(verts, camintr):
@@ -37,3 +40,44 @@ def batch_cat_meshes(verts_list, faces_list):
         faces_out.append(faces + offset)
         offset += verts.shape[1]
     return torch.cat(verts_list, 1), torch.cat(faces_out, 1), None
+
+
+class _CatHandObjectFunction(Function):
+    """``batch_cat_meshes([hand, obj], [hand_faces, obj_faces])`` for both frames of a pair in one launch
+    (hoc_cat_meshes); the adjoint of a concatenation is a pair of slices, so the backward launches nothing."""
+
+    @staticmethod
+    def forward(ctx, hand_a, obj_a, hand_b, obj_b, hand_faces, obj_faces):
+        L = _lib.lib()
+        c = lambda t: t.detach().contiguous().float()
+        ha, oa, hb, ob = c(hand_a), c(obj_a), c(hand_b), c(obj_b)
+        hf, of = hand_faces.detach().contiguous().long(), obj_faces.detach().contiguous().long()
+        B, Vh, Vo = ha.shape[0], ha.shape[1], oa.shape[1]
+        if hf.dim() == 3 and hf.shape[0] == 1:
+            hf = hf[0]
+        Fh, Fo = hf.shape[-2], of.shape[1]
+        dev = ha.device
+        with torch.cuda.device(dev):
+            va = torch.empty((B, Vh + Vo, 3), dtype=torch.float32, device=dev)
+            vb = torch.empty((B, Vh + Vo, 3), dtype=torch.float32, device=dev)
+            faces = torch.empty((B, Fh + Fo, 3), dtype=torch.int64, device=dev)
+            _lib.check(L.hoc_cat_meshes(_lib.ptr(ha), _lib.ptr(oa), _lib.ptr(hb), _lib.ptr(ob), _lib.ptr(hf),
+                                        int(hf.dim() == 3), _lib.ptr(of), B, Vh, Vo, Fh, Fo, _lib.ptr(va), _lib.ptr(vb),
+                                        _lib.ptr(faces), _lib.stream_ptr()), "hoc_cat_meshes")
+        ctx.vh = Vh
+        ctx.mark_non_differentiable(faces)
+        ctx.set_materialize_grads(False)
+        return va, vb, faces
+
+    @staticmethod
+    def backward(ctx, g_a, g_b, g_faces):
+        Vh = ctx.vh
+        sl = lambda g: (None, None) if g is None else (g[:, :Vh], g[:, Vh:])
+        (gha, goa), (ghb, gob) = sl(g_a), sl(g_b)
+        return gha, goa, ghb, gob, None, None
+
+
+def cat_hand_object_pair(hand_a, obj_a, hand_b, obj_b, hand_faces, obj_faces):
+    """(verts_a, verts_b, faces) of a frame pair: what two ``batch_cat_meshes`` calls return (warpbranch.py:50-52)."""
+    _lib.require_cuda(hand_a, obj_a, hand_b, obj_b, hand_faces, obj_faces, what="cat_hand_object_pair")
+    return _CatHandObjectFunction.apply(hand_a, obj_a, hand_b, obj_b, hand_faces, obj_faces)

@@ -8,7 +8,7 @@ lookup goes by member NAME.
 """
 import torch
 
-from .meshutils import batch_cat_meshes
+from .meshutils import batch_cat_meshes, cat_hand_object_pair
 from .warping import imgflowarp, opticalflow
 
 
@@ -52,25 +52,31 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
     obj_verts = [result["recov_objverts3d"] for result in all_results]
     obj_faces = [_base(sample, "OBJFACES").cuda(non_blocking=True).long() for sample in samples]
     hand_verts = [result["recov_handverts3d"] for result in all_results]
-    hand_faces_b = hand_face.repeat(obj_verts[0].shape[0], 1, 1).long()
-    hand_faces = [hand_faces_b for _ in range(len(samples))]
     if gt_refs:
         for sample_idx in range(1, len(samples)):
             obj_verts[sample_idx] = _base(samples[sample_idx], "OBJVERTS3D").cuda(non_blocking=True)
             hand_verts[sample_idx] = _base(samples[sample_idx], "HANDVERTS3D").cuda(non_blocking=True)
     verts_world = []
     last = len(samples) - 1
-    for seq_idx in range(len(samples)):
-        if seq_idx == last:
-            # the reference concatenates the faces of every frame but only the last frame's survive the loop
-            # (warpbranch.py:50-52,57-60): build that one
-            all_verts, all_faces, _ = batch_cat_meshes([hand_verts[seq_idx], obj_verts[seq_idx]],
-                                                       [hand_faces[seq_idx], obj_faces[seq_idx]])
-        else:
-            all_verts = torch.cat([hand_verts[seq_idx], obj_verts[seq_idx]], 1)
-        if first_only and seq_idx > 0:
-            all_verts = all_verts.detach()
-        verts_world.append(all_verts)
+    if len(samples) == 2 and hand_face.dim() in (2, 3) and (hand_face.dim() == 2 or hand_face.shape[0] == 1):
+        # one frame pair (the training setting): both concatenations and the face table in one launch
+        verts_a, verts_b, all_faces = cat_hand_object_pair(hand_verts[0], obj_verts[0], hand_verts[1], obj_verts[1],
+                                                           hand_face.cuda(non_blocking=True), obj_faces[last])
+        verts_world = [verts_a, verts_b.detach() if first_only else verts_b]
+    else:
+        hand_faces_b = hand_face.repeat(obj_verts[0].shape[0], 1, 1).long()
+        hand_faces = [hand_faces_b for _ in range(len(samples))]
+        for seq_idx in range(len(samples)):
+            if seq_idx == last:
+                # the reference concatenates the faces of every frame but only the last frame's survive the loop
+                # (warpbranch.py:50-52,57-60): build that one
+                all_verts, all_faces, _ = batch_cat_meshes([hand_verts[seq_idx], obj_verts[seq_idx]],
+                                                           [hand_faces[seq_idx], obj_faces[seq_idx]])
+            else:
+                all_verts = torch.cat([hand_verts[seq_idx], obj_verts[seq_idx]], 1)
+            if first_only and seq_idx > 0:
+                all_verts = all_verts.detach()
+            verts_world.append(all_verts)
 
     recons_flows = opticalflow.get_opticalflows(verts_world, all_faces, camintrs, renderer, image_size,
                                                 detach_textures=False, detach_renders=detach_renders,
@@ -84,7 +90,8 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
         full_losses.append(warp_loss)
         all_warps.append(warps)
         all_diffs.append(diffs)
-    stack_losses = torch.stack(full_losses)
+    # torch.stack of a single [B] tensor is that tensor with a leading axis: no copy kernel for one pair
+    stack_losses = full_losses[0].unsqueeze(0) if len(full_losses) == 1 else torch.stack(full_losses)
     full_loss = stack_losses.mean()
     pair_results = {"masks": all_masks, "warps": all_warps, "recons_flows": recons_flows, "diffs": all_diffs,
                     "diff_losses": stack_losses}

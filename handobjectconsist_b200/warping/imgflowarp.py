@@ -16,7 +16,7 @@ _SIDE_STREAMS = {}
 
 
 def _side_stream(device):
-    key = str(device)
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)  # one side stream per launching stream
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
@@ -144,6 +144,89 @@ class _WarpPhotoFunction(Function):
         return grad_flow, None, None, None, None
 
 
+class _PairWarpPhotoFunction(Function):
+    """Both directions of pair_consist with the L1 criterion behind ONE autograd node: two
+    hoc_warp_photo_forward launches (the second on the side stream) and hoc_pair_loss; the backward hands
+    d loss straight to the two hoc_warp_photo_backward launches (no per-direction loss tensors, no add node)."""
+
+    @staticmethod
+    def forward(ctx, flow12, flow21, image_ref, image, jitter_ref, jitter, thresh, use_backward):
+        _lib.require_cuda(flow12, flow21, image_ref, image, jitter_ref, jitter, what="pair_consist")
+        L = _lib.lib()
+        c = lambda t: t.detach().contiguous().float()
+        f12, f21, ir, im, jr, jm = c(flow12), c(flow21), c(image_ref), c(image), c(jitter_ref), c(jitter)
+        B, C, H, W = ir.shape
+        if f12.shape != (B, H, W, 2) or f21.shape != (B, H, W, 2):
+            raise ValueError(f"flows must be [{B}, {H}, {W}, 2], got {tuple(f12.shape)} / {tuple(f21.shape)}")
+        if im.shape != ir.shape or jr.shape[0] != B or jm.shape[0] != B or jr.shape[2:] != (H, W) or jm.shape[2:] != (H, W):
+            raise ValueError("pair_consist: image / jitter mask shapes do not match")
+        dev = ir.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if _config.overlap_streams else main
+        outs = []
+        with torch.cuda.device(dev):
+            sums = torch.empty((2, B, 2), dtype=torch.float64, device=dev)
+            loss = torch.empty((B,), dtype=torch.float32, device=dev)
+            side.wait_stream(main)
+            # direction 1 (index 0): warp(image_ref, flow21) against image, jitter_mask warped with flow21
+            # direction 2 (index 1): warp(image, flow12) against image_ref, jitter_mask_ref warped with flow12
+            for k, (src, tgt, fl, jit) in enumerate(((ir, im, f21, jm), (im, ir, f12, jr))):
+                with torch.cuda.stream(main if k == 0 else side):
+                    warped, warp_mask, diff = torch.empty_like(src), torch.empty_like(src), torch.empty_like(src)
+                    valid = torch.empty((B, H, W), dtype=torch.bool, device=dev)
+                    flow_mask = torch.empty((B, H, W, 2), dtype=torch.bool, device=dev)
+                    _lib.check(L.hoc_warp_photo_forward(_lib.ptr(src), _lib.ptr(tgt), _lib.ptr(fl), _lib.ptr(jit), B, C,
+                                                        jit.shape[1], H, W, float(thresh), _lib.ptr(warped),
+                                                        _lib.ptr(warp_mask), _lib.ptr(valid), _lib.ptr(flow_mask),
+                                                        _lib.ptr(diff), _lib.ptr(sums[k]), None, _lib.stream_ptr()),
+                               "hoc_warp_photo_forward")
+                    for t in (warped, warp_mask, diff, valid, flow_mask):
+                        t.record_stream(main)
+                    outs.append((warped, warp_mask, valid, flow_mask, diff))
+            main.wait_stream(side)
+            _lib.check(L.hoc_pair_loss(_lib.ptr(sums[0]), _lib.ptr(sums[1]) if use_backward else None, B,
+                                       _lib.ptr(loss), _lib.stream_ptr()), "hoc_pair_loss")
+        ctx.save_for_backward(ir, im, f12, f21, outs[0][2], outs[1][2], sums)
+        ctx.cfg = (float(thresh), bool(use_backward))
+        flat = outs[0] + outs[1]
+        ctx.mark_non_differentiable(*[t for o in outs for t in o[1:4]])
+        ctx.set_materialize_grads(False)
+        return (loss,) + flat
+
+    @staticmethod
+    def backward(ctx, grad_loss, *others):
+        if any(g is not None for g in others):
+            raise NotImplementedError("pair_consist: only the loss output is differentiable in the fused path")
+        ir, im, f12, f21, valid1, valid2, sums = ctx.saved_tensors
+        thresh, use_backward = ctx.cfg
+        if grad_loss is None or not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            return (None,) * 8
+        L = _lib.lib()
+        B, C, H, W = ir.shape
+        gl = grad_loss.contiguous().float()
+        dev = ir.device
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev) if _config.overlap_streams else main
+        g12 = g21 = None
+        with torch.cuda.device(dev):
+            side.wait_stream(main)
+            if ctx.needs_input_grad[1]:  # d loss_fwd / d flow21
+                g21 = torch.empty_like(f21)
+                _lib.check(L.hoc_warp_photo_backward(_lib.ptr(ir), _lib.ptr(im), _lib.ptr(f21), _lib.ptr(valid1),
+                                                     _lib.ptr(sums[0]), _lib.ptr(gl), B, C, H, W, thresh, _lib.ptr(g21),
+                                                     _lib.stream_ptr()), "hoc_warp_photo_backward")
+            if ctx.needs_input_grad[0] and use_backward:  # d loss_bwd / d flow12
+                with torch.cuda.stream(side):
+                    g12 = torch.empty_like(f12)
+                    _lib.check(L.hoc_warp_photo_backward(_lib.ptr(im), _lib.ptr(ir), _lib.ptr(f12), _lib.ptr(valid2),
+                                                         _lib.ptr(sums[1]), _lib.ptr(gl), B, C, H, W, thresh,
+                                                         _lib.ptr(g12), _lib.stream_ptr()), "hoc_warp_photo_backward")
+                    g12.record_stream(main)
+                    gl.record_stream(side)
+            main.wait_stream(side)
+        return g12, g21, None, None, None, None, None, None
+
+
 def _criterion_is_fused_l1(criterion):
     return getattr(criterion, "name", None) == "l1" and getattr(criterion, "level_nb", 1) == 1
 
@@ -178,6 +261,15 @@ def pair_consist(recons_flow, image_ref: torch.Tensor, image: torch.Tensor, jitt
     """
     image_ref, image = image_ref.cuda(), image.cuda()
     jitter_mask_ref, jitter_mask = jitter_mask_ref.cuda(), jitter_mask.cuda()
+    if _criterion_is_fused_l1(criterion):
+        (warp_loss, warp1, warp_mask1, valid_mask1, flow_mask1, diffs_fwd, warp2, warp_mask2, valid_mask2, flow_mask2,
+         diffs_bwd) = _PairWarpPhotoFunction.apply(recons_flow[0], recons_flow[1], image_ref, image, jitter_mask_ref,
+                                                   jitter_mask, 0.99999, use_backward)
+        masks = [
+            {"warp_mask": warp_mask1, "full_mask": valid_mask1, "flow_mask": flow_mask1},
+            {"warp_mask": warp_mask2, "full_mask": valid_mask2, "flow_mask": flow_mask2},
+        ]
+        return warp_loss, masks, [warp1, warp2], [diffs_fwd, diffs_bwd]
     # the two directions are independent: the second runs on a side stream (its kernels overlap the first's)
     dev = image.device
     main = torch.cuda.current_stream(dev)

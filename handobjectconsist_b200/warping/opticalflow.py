@@ -22,7 +22,8 @@ _SIDE_STREAMS = {}
 
 
 def _side_stream(device):
-    key = str(device)
+    # one side stream per launching stream: independent chains (GraphedConsistStep micro-batches) must not meet on it
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]

@@ -71,6 +71,8 @@ const char *hoc_last_error(void);
 #define HOC_K_MANO_BWD 18
 #define HOC_K_RASTER_BWD_PIXEL_K4 19 /* hoc_raster_bwd_cover_kernel<.., true>: covered pixels incl. pseudo-gradient */
 #define HOC_K_RASTER_BACKWARD_COVER 20 /* hoc_raster_bwd_cover_kernel<.., false>: texture / depth gradient only */
+#define HOC_K_CAT_MESHES 21
+#define HOC_K_PAIR_LOSS 22
 #define HOC_KERNEL_COUNT 24
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
@@ -168,6 +170,10 @@ int hoc_warp_photo_forward(const float *src, const float *target, const float *f
                            uint8_t *valid_mask, uint8_t *flow_mask, float *diff, double *sums, float *loss,
                            void *stream);
 
+/* pair_consist's per-sample loss from the sums of its two directions (imgflowarp.py:108-114):
+ * loss[b] = masked_mean(bwd) + masked_mean(fwd) (that order, float) when sums_bwd is given, else masked_mean(fwd). */
+int hoc_pair_loss(const double *sums_fwd, const double *sums_bwd, int B, float *loss, void *stream);
+
 /* Gradient of loss[b] w.r.t. flow, the only differentiable input (imgflowarp.py:52-53: the
  * thresholded masks carry no gradient).  grad_loss [B]; valid_mask / sums from the forward;
  * grad_flow [B,H,W,2] out (fully overwritten). */
@@ -199,6 +205,13 @@ int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow
  *   faces F..2F-1 are the reversed windings, their cubes the permute(0,1,4,3,2,5) of the originals). */
 int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                     int fill_back, float *faces_out, float *textures_out, void *stream);
+/* batch_cat_meshes (libyana.renderutils.catmesh, called at /root/reference/meshreg/models/warpbranch.py:50-52) for
+ * the hand + object pair of one or two frames in ONE launch: verts_x [B,Vh+Vo,3] = cat(hand_x, obj_x),
+ * faces [B,Fh+Fo,3] = cat(hand_faces, obj_faces + Vh).  hand_faces is [Fh,3] (shared) or [B,Fh,3]
+ * (`hand_faces_batched`); verts_b / faces may be NULL to skip them. */
+int hoc_cat_meshes(const float *hand_a, const float *obj_a, const float *hand_b, const float *obj_b,
+                   const long long *hand_faces, int hand_faces_batched, const long long *obj_faces, int B, int Vh,
+                   int Vo, int Fh, int Fo, float *verts_a, float *verts_b, long long *faces, void *stream);
 /* Adjoint: grad_faces [B,F',3,3] / grad_textures (either may be NULL together with its output)
  * -> grad_verts [B,V,3], grad_attrs [B,V,3] (zero-filled by the call, accumulated with atomics).
  * tex_grad_mode as in hoc_raster_backward: CUBE = grad_textures [B,F',2,2,2,3], VERTEX = [B,F',3,3]. */
