@@ -4,3 +4,18 @@
 # kernels overlap (eager mode and inside captured graphs).  bench.py turns it off while it captures the
 # instrumented graph it uses to time kernels one at a time.
 overlap_streams = True
+
+
+_SIDE_STREAMS = {}
+
+
+def side_stream(device):
+    """The side stream that accompanies the CURRENT stream on `device` (one per launching stream, so that
+    independent chains never meet on it).  Shared by the flow renders and pair_consist: inside a captured step the
+    stream forked for the second render is the one pair_consist reuses."""
+    import torch
+
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]

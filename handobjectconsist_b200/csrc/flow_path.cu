@@ -24,8 +24,14 @@
 __global__ void __launch_bounds__(FP_THREADS)
 hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict__ attrs,
                        const long long *__restrict__ faces_idx, int V, int F, int fill_back,
-                       float *__restrict__ faces_out, float *__restrict__ tex_out)
+                       float *__restrict__ faces_out, float *__restrict__ tex_out, uint4 *__restrict__ clear,
+                       long n_clear)
 {
+    if (clear != nullptr) { /* 0xff fill of the z-buffer keys of the forward that follows, spread over the grid */
+        const long nthreads = (long)gridDim.x * gridDim.y * FP_THREADS;
+        for (long i = ((long)blockIdx.y * gridDim.x + blockIdx.x) * FP_THREADS + threadIdx.x; i < n_clear; i += nthreads)
+            clear[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
     /* per-face records are staged in shared memory and written out as contiguous, coalesced runs */
     __shared__ __align__(16) float s_tex[FP_THREADS * 24];
     __shared__ float s_face[FP_THREADS * 9];
@@ -542,9 +548,28 @@ extern "C" int hoc_cat_meshes(const float *hand_a, const float *obj_a, const flo
 }
 
 /* ------------------------------------------------------------------------------------------ */
+extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V,
+                                     int F, int fill_back, float *faces_out, float *textures_out, void *clear,
+                                     size_t clear_bytes, void *stream);
+
 extern "C" int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                                int fill_back, float *faces_out, float *textures_out, void *stream)
 {
+    return hoc_mesh_gather_clear(verts, attrs, faces_idx, B, V, F, fill_back, faces_out, textures_out, nullptr, 0, stream);
+}
+
+extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V,
+                                     int F, int fill_back, float *faces_out, float *textures_out, void *clear,
+                                     size_t clear_bytes, void *stream)
+{
+    HOC_CHECK_ARG(clear == nullptr || (clear_bytes % 16 == 0 && ((uintptr_t)clear & 15) == 0),
+                  "hoc_mesh_gather_clear: clear buffer must be 16-byte aligned with a size multiple of 16");
+    if (clear != nullptr && (B == 0 || F == 0)) { /* nothing to gather: still honour the fill */
+        if (cudaMemsetAsync(clear, 0xff, clear_bytes, (cudaStream_t)stream) != cudaSuccess) {
+            hoc_set_error("hoc_mesh_gather_clear: memset failed");
+            return HOC_ERR_CUDA;
+        }
+    }
     HOC_CHECK_ARG(B >= 0 && V >= 0 && F >= 0, "hoc_mesh_gather: bad shape B=%d V=%d F=%d", B, V, F);
     HOC_CHECK_ARG(B <= 65535, "hoc_mesh_gather: batch %d exceeds 65535", B);
     if (B == 0 || F == 0)
@@ -554,9 +579,9 @@ extern "C" int hoc_mesh_gather(const float *verts, const float *attrs, const lon
     const int Fo = fill_back ? 2 * F : F;
     dim3 grid((Fo + FP_THREADS - 1) / FP_THREADS, B);
     HOC_LAUNCH(HOC_K_MESH_GATHER, (cudaStream_t)stream,
-               (hoc_mesh_gather_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(verts, attrs, faces_idx, V, F,
-                                                                                      fill_back, faces_out,
-                                                                                      textures_out)));
+               (hoc_mesh_gather_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   verts, attrs, faces_idx, V, F, fill_back, faces_out, textures_out, (uint4 *)clear,
+                   (long)(clear_bytes / 16))));
     HOC_CHECK_LAUNCH("hoc_mesh_gather_kernel");
     return HOC_OK;
 }
@@ -571,10 +596,15 @@ extern "C" int hoc_mesh_scatter(const float *grad_faces, const float *grad_textu
     if (B == 0)
         return HOC_OK;
     cudaError_t e = cudaSuccess;
-    if (grad_verts != nullptr)
-        e = cudaMemsetAsync(grad_verts, 0, sizeof(float) * 3 * (size_t)B * V, st);
-    if (e == cudaSuccess && grad_attrs != nullptr)
-        e = cudaMemsetAsync(grad_attrs, 0, sizeof(float) * 3 * (size_t)B * V, st);
+    const size_t nbytes = sizeof(float) * 3 * (size_t)B * V;
+    if (grad_verts != nullptr && grad_attrs == grad_verts + 3 * (size_t)B * V) {
+        e = cudaMemsetAsync(grad_verts, 0, 2 * nbytes, st); /* adjacent outputs: one fill */
+    } else {
+        if (grad_verts != nullptr)
+            e = cudaMemsetAsync(grad_verts, 0, nbytes, st);
+        if (e == cudaSuccess && grad_attrs != nullptr)
+            e = cudaMemsetAsync(grad_attrs, 0, nbytes, st);
+    }
     if (e != cudaSuccess) {
         hoc_set_error("hoc_mesh_scatter: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;

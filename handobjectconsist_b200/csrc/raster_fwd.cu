@@ -328,6 +328,8 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
 {
     HOC_CHECK_ARG(B >= 0 && F >= 0, "hoc_raster_forward: negative batch (%d) or face count (%d)", B, F);
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_forward: image_size %d outside [1, 2048]", S);
+    const bool keys_cleared = (layout & HOC_LAYOUT_KEYS_CLEARED) != 0; /* the caller filled the workspace with 0xff */
+    layout &= ~HOC_LAYOUT_KEYS_CLEARED;
     HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_forward: bad layout %d", layout);
     HOC_CHECK_ARG(face_index_map != nullptr, "hoc_raster_forward: face_index_map is required");
     HOC_CHECK_ARG(rgb == nullptr || ((textures != nullptr || F == 0) && ts >= 1),
@@ -343,7 +345,7 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     }
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *zbuf = (unsigned long long *)workspace;
-    cudaError_t e = cudaMemsetAsync(zbuf, 0xff, need, st);
+    cudaError_t e = keys_cleared ? cudaSuccess : cudaMemsetAsync(zbuf, 0xff, need, st);
     if (e != cudaSuccess) {
         hoc_set_error("hoc_raster_forward: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;

@@ -533,10 +533,33 @@ hoc_occlusion_kernel(const float *__restrict__ mask1, const float *__restrict__ 
 }
 
 /* ------------------------------------------------------------------------------------------ */
+static int hoc_warp_photo_forward_impl(const float *src, const float *target, const float *flow, const float *jitter,
+                                       int B, int C, int Cj, int H, int W, float thresh, float *warped,
+                                       float *warp_mask, uint8_t *valid_mask, uint8_t *flow_mask, float *diff,
+                                       double *sums, float *loss, void *stream, bool zero_sums);
+
 extern "C" int hoc_warp_photo_forward(const float *src, const float *target, const float *flow, const float *jitter,
                                       int B, int C, int Cj, int H, int W, float thresh, float *warped,
                                       float *warp_mask, uint8_t *valid_mask, uint8_t *flow_mask, float *diff,
                                       double *sums, float *loss, void *stream)
+{
+    return hoc_warp_photo_forward_impl(src, target, flow, jitter, B, C, Cj, H, W, thresh, warped, warp_mask, valid_mask,
+                                       flow_mask, diff, sums, loss, stream, true);
+}
+
+extern "C" int hoc_warp_photo_forward_acc(const float *src, const float *target, const float *flow, const float *jitter,
+                                          int B, int C, int Cj, int H, int W, float thresh, float *warped,
+                                          float *warp_mask, uint8_t *valid_mask, uint8_t *flow_mask, float *diff,
+                                          double *sums, float *loss, void *stream)
+{
+    return hoc_warp_photo_forward_impl(src, target, flow, jitter, B, C, Cj, H, W, thresh, warped, warp_mask, valid_mask,
+                                       flow_mask, diff, sums, loss, stream, false);
+}
+
+static int hoc_warp_photo_forward_impl(const float *src, const float *target, const float *flow, const float *jitter,
+                                       int B, int C, int Cj, int H, int W, float thresh, float *warped,
+                                       float *warp_mask, uint8_t *valid_mask, uint8_t *flow_mask, float *diff,
+                                       double *sums, float *loss, void *stream, bool zero_sums)
 {
     HOC_CHECK_ARG(B >= 0 && C >= 1 && H >= 1 && W >= 1 && (long)H * W < (1l << 31),
                   "hoc_warp_photo_forward: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
@@ -548,7 +571,7 @@ extern "C" int hoc_warp_photo_forward(const float *src, const float *target, con
         return HOC_OK;
     HOC_CHECK_ARG(src && target && flow, "hoc_warp_photo_forward: NULL input");
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, st);
+    cudaError_t e = zero_sums ? cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B, st) : cudaSuccess;
     if (e != cudaSuccess) {
         hoc_set_error("hoc_warp_photo_forward: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;

@@ -12,14 +12,7 @@ from torch.autograd import Function
 from .. import _config, _lib
 
 
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream)  # one side stream per launching stream
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
+_side_stream = _config.side_stream
 
 
 def get_spatial_meshgrid(x: torch.Tensor, scale=False):
@@ -163,9 +156,17 @@ class _PairWarpPhotoFunction(Function):
         dev = ir.device
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev) if _config.overlap_streams else main
+        main_capturing = torch.cuda.is_current_stream_capturing()
         outs = []
         with torch.cuda.device(dev):
-            sums = torch.empty((2, B, 2), dtype=torch.float64, device=dev)
+            # the sums are zero-filled on the side stream BEFORE it joins the main one: the fill does not depend on
+            # the flows, so it leaves the critical path (flow_finalize -> warp kernel) of the captured step
+            with torch.cuda.stream(side):
+                if torch.cuda.is_current_stream_capturing() != main_capturing:
+                    side.wait_stream(main)  # a capture the side stream has not joined yet: fork it first
+                sums = torch.zeros((2, B, 2), dtype=torch.float64, device=dev)
+                sums.record_stream(main)
+            main.wait_stream(side)
             loss = torch.empty((B,), dtype=torch.float32, device=dev)
             side.wait_stream(main)
             # direction 1 (index 0): warp(image_ref, flow21) against image, jitter_mask warped with flow21
@@ -175,11 +176,11 @@ class _PairWarpPhotoFunction(Function):
                     warped, warp_mask, diff = torch.empty_like(src), torch.empty_like(src), torch.empty_like(src)
                     valid = torch.empty((B, H, W), dtype=torch.bool, device=dev)
                     flow_mask = torch.empty((B, H, W, 2), dtype=torch.bool, device=dev)
-                    _lib.check(L.hoc_warp_photo_forward(_lib.ptr(src), _lib.ptr(tgt), _lib.ptr(fl), _lib.ptr(jit), B, C,
-                                                        jit.shape[1], H, W, float(thresh), _lib.ptr(warped),
-                                                        _lib.ptr(warp_mask), _lib.ptr(valid), _lib.ptr(flow_mask),
-                                                        _lib.ptr(diff), _lib.ptr(sums[k]), None, _lib.stream_ptr()),
-                               "hoc_warp_photo_forward")
+                    _lib.check(L.hoc_warp_photo_forward_acc(_lib.ptr(src), _lib.ptr(tgt), _lib.ptr(fl), _lib.ptr(jit), B,
+                                                            C, jit.shape[1], H, W, float(thresh), _lib.ptr(warped),
+                                                            _lib.ptr(warp_mask), _lib.ptr(valid), _lib.ptr(flow_mask),
+                                                            _lib.ptr(diff), _lib.ptr(sums[k]), None,
+                                                            _lib.stream_ptr()), "hoc_warp_photo_forward_acc")
                     for t in (warped, warp_mask, diff, valid, flow_mask):
                         t.record_stream(main)
                     outs.append((warped, warp_mask, valid, flow_mask, diff))

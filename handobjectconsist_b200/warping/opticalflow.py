@@ -18,15 +18,7 @@ from ..meshutils import batch_proj2d, batch_vertex_textures
 from . import imgflowarp
 
 _IGNORE_CACHE = {}
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    # one side stream per launching stream: independent chains (GraphedConsistStep micro-batches) must not meet on it
-    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
+_side_stream = _config.side_stream
 
 
 def _ignore_tensor(ignore_face_idxs, device):
@@ -58,17 +50,20 @@ class _MeshRasterFunction(Function):
             faces = torch.empty((B, Fo, 3, 3), dtype=torch.float32, device=dev)
             tex = torch.empty((B, Fo, 2, 2, 2, 3), dtype=torch.float32, device=dev)
             st = _lib.stream_ptr()
-            _lib.check(L.hoc_mesh_gather(_lib.ptr(v), _lib.ptr(a), _lib.ptr(fi), B, V, Fn, int(fill_back),
-                                         _lib.ptr(faces), _lib.ptr(tex), st), "hoc_mesh_gather")
+            # the gather also 0xff-fills the z-buffer keys of the forward below (one graph node less between them)
+            ws_bytes = L.hoc_raster_forward_workspace_bytes(B, Fo, S)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            _lib.check(L.hoc_mesh_gather_clear(_lib.ptr(v), _lib.ptr(a), _lib.ptr(fi), B, V, Fn, int(fill_back),
+                                               _lib.ptr(faces), _lib.ptr(tex), _lib.ptr(ws), ws_bytes, st),
+                       "hoc_mesh_gather_clear")
             rgb = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
             alpha = torch.empty((B, S, S), dtype=torch.float32, device=dev)
             depth = torch.empty((B, S, S), dtype=torch.float32, device=dev)
             idx = torch.empty((B, S, S), dtype=torch.int32, device=dev)
             wmap = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)  # saved for the backward
-            ws_bytes = L.hoc_raster_forward_workspace_bytes(B, Fo, S)
-            ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
             _lib.check(L.hoc_raster_forward(_lib.ptr(faces), _lib.ptr(tex), B, Fo, S, 2, float(near), float(far),
-                                            float(eps), bg, None, _lib.HOC_LAYOUT_IMAGE, _lib.ptr(rgb),
+                                            float(eps), bg, None,
+                                            _lib.HOC_LAYOUT_IMAGE | _lib.HOC_LAYOUT_KEYS_CLEARED, _lib.ptr(rgb),
                                             _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx), _lib.ptr(wmap), None,
                                             _lib.ptr(ws), ws_bytes, st), "hoc_raster_forward")
         ctx.save_for_backward(faces, fi, idx, rgb, wmap, depth)
@@ -100,8 +95,12 @@ class _MeshRasterFunction(Function):
                                              _lib.ptr(g_alpha), _lib.ptr(g_depth), B, Fo, S, 2, near, far, eps,
                                              _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_faces),
                                              _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st), "hoc_raster_backward")
-            grad_verts = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_v else None
-            grad_attrs = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_a else None
+            if need_v and need_a:  # adjacent: hoc_mesh_scatter zero-fills both with one memset
+                both = torch.empty((2, B, V, 3), dtype=torch.float32, device=dev)
+                grad_verts, grad_attrs = both[0], both[1]
+            else:
+                grad_verts = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_v else None
+                grad_attrs = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_a else None
             _lib.check(L.hoc_mesh_scatter(_lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(fi), B, V, Fn,
                                           int(fill_back), _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_verts),
                                           _lib.ptr(grad_attrs), st),

@@ -45,6 +45,9 @@ extern "C" {
  * face_index_map / weight_map / face_inv_map are never flipped (rasterize.py:443-445). */
 #define HOC_LAYOUT_RAW 0
 #define HOC_LAYOUT_IMAGE 1
+/* OR-ed into `layout` of hoc_raster_forward: the workspace already holds 0xff bytes (hoc_mesh_gather_clear did it),
+ * so the forward skips its own fill -- one graph node less on the critical path of the fused flow path */
+#define HOC_LAYOUT_KEYS_CLEARED 0x100
 
 int hoc_abi_version(void);
 const char *hoc_last_error(void);
@@ -170,6 +173,12 @@ int hoc_warp_photo_forward(const float *src, const float *target, const float *f
                            uint8_t *valid_mask, uint8_t *flow_mask, float *diff, double *sums, float *loss,
                            void *stream);
 
+/* Same, but ACCUMULATES into `sums` (the caller zero-filled it, e.g. ahead of time on another stream). */
+int hoc_warp_photo_forward_acc(const float *src, const float *target, const float *flow, const float *jitter, int B,
+                               int C, int Cj, int H, int W, float thresh, float *warped, float *warp_mask,
+                               uint8_t *valid_mask, uint8_t *flow_mask, float *diff, double *sums, float *loss,
+                               void *stream);
+
 /* pair_consist's per-sample loss from the sums of its two directions (imgflowarp.py:108-114):
  * loss[b] = masked_mean(bwd) + masked_mean(fwd) (that order, float) when sums_bwd is given, else masked_mean(fwd). */
 int hoc_pair_loss(const double *sums_fwd, const double *sums_bwd, int B, float *loss, void *stream);
@@ -205,6 +214,11 @@ int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow
  *   faces F..2F-1 are the reversed windings, their cubes the permute(0,1,4,3,2,5) of the originals). */
 int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                     int fill_back, float *faces_out, float *textures_out, void *stream);
+/* hoc_mesh_gather that also fills `clear` (clear_bytes, a multiple of 16, 16-byte aligned) with 0xff bytes: the
+ * z-buffer workspace of the hoc_raster_forward call that follows (pass HOC_LAYOUT_KEYS_CLEARED there). */
+int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
+                          int fill_back, float *faces_out, float *textures_out, void *clear, size_t clear_bytes,
+                          void *stream);
 /* batch_cat_meshes (libyana.renderutils.catmesh, called at /root/reference/meshreg/models/warpbranch.py:50-52) for
  * the hand + object pair of one or two frames in ONE launch: verts_x [B,Vh+Vo,3] = cat(hand_x, obj_x),
  * faces [B,Fh+Fo,3] = cat(hand_faces, obj_faces + Vh).  hand_faces is [Fh,3] (shared) or [B,Fh,3]
