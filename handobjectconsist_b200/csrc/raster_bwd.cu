@@ -38,8 +38,8 @@
 #define EXT_COL_HI 3
 
 /* Workspace carved by hoc_raster_backward (256-byte aligned regions):
- *   ext        int    [B][4][S]      {row_nlo, row_hi, col_nlo, col_hi}: span of non-zero incoming gradient, the low
- *                                    end stored as S - 1 - lo so that both ends are max-reduced from -1 (one 0xff fill)
+ *   ext        int    [B][4][S]      {row_nlo, row_hi, col_nlo, col_hi}: span of non-zero incoming gradient, stored as
+ *                                    S - lo and hi + 1 so that both ends are max-reduced from 0      (zero-filled)
  *   cov_count  int    [B]            covered pixels listed per sample                      (zero-filled)
  *   line_count int    [B][2][S]      outward scans queued on each line (axis 0: column x, axis 1: row y)  (zero-filled)
  *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
@@ -54,7 +54,7 @@ struct HocBwdWorkspace {
     float *acc_d;
     int *cov_list;
     unsigned short *emitters;
-    size_t count_bytes, acc_bytes; /* cov_count + line_count, then acc_d: one contiguous zero-fill */
+    size_t count_bytes, acc_bytes; /* ext + cov_count + line_count, then acc_d: one contiguous zero-fill */
     size_t total;
 };
 
@@ -64,9 +64,9 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     HocBwdWorkspace w;
     size_t off = 0;
     char *p = (char *)base;
+    const size_t zero_begin = off;
     w.ext = (int *)(p + off);
     off = up(off + sizeof(int) * 4 * (size_t)B * S);
-    const size_t zero_begin = off;
     w.cov_count = (int *)(p + off);
     off = up(off + sizeof(int) * (size_t)B);
     w.line_count = (int *)(p + off);
@@ -229,8 +229,8 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         if (K4) {
             const unsigned m = __ballot_sync(HOC_FULL_MASK, nz);
             if (m != 0 && tx == 0) {
-                atomicMax(&e[EXT_ROW_LO * S + yi], S - 1 - (blockIdx.x * 32 + (__ffs(m) - 1)));
-                atomicMax(&e[EXT_ROW_HI * S + yi], blockIdx.x * 32 + (31 - __clz(m)));
+                atomicMax(&e[EXT_ROW_LO * S + yi], S - (blockIdx.x * 32 + (__ffs(m) - 1)));
+                atomicMax(&e[EXT_ROW_HI * S + yi], blockIdx.x * 32 + (31 - __clz(m)) + 1);
             }
             if (nz) {
                 c_lo = min(c_lo, yi);
@@ -262,8 +262,8 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
                 c_hi = max(c_hi, s_hi[r][tx]);
             }
             if (c_hi >= 0) {
-                atomicMax(&e[EXT_COL_LO * S + xi], S - 1 - c_lo);
-                atomicMax(&e[EXT_COL_HI * S + xi], c_hi);
+                atomicMax(&e[EXT_COL_LO * S + xi], S - c_lo);
+                atomicMax(&e[EXT_COL_HI * S + xi], c_hi + 1);
             }
         }
     }
@@ -545,8 +545,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         n = min(lc[d0_base], 3 * S);
         if (n == 0)
             return;
-        ulo = S - 1 - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
-        uhi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_base];
+        ulo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
+        uhi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_base] - 1;
         if (ulo > uhi)
             return;
         if (tid == 0) {
@@ -563,8 +563,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 const int d0 = d0_base + l;
                 int lo = 0x7f7f7f7f, hi = -1, cnt = 0;
                 if (d0 < S) {
-                    lo = S - 1 - ((axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0]);
-                    hi = (axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0];
+                    lo = S - ((axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0]);
+                    hi = ((axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0]) - 1;
                     cnt = (lo <= hi) ? min(lc[d0], 3 * S) : 0;
                 }
                 s_lo[l] = lo;
@@ -813,11 +813,9 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
 
-    /* counters and (directly behind them) acc_d are zero-filled by one memset, the spans by another; the gradient
-     * outputs are zero-filled by the scan pass */
-    cudaError_t e = cudaMemsetAsync(w.cov_count, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
-    if (e == cudaSuccess && k4)
-        e = cudaMemsetAsync(w.ext, 0xff, sizeof(int) * 4 * (size_t)B * S, st);
+    /* spans, counters and (directly behind them) acc_d are zero-filled by ONE memset; the gradient outputs are
+     * zero-filled by the scan pass */
+    cudaError_t e = cudaMemsetAsync(w.ext, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
     if (e != cudaSuccess) {
         hoc_set_error("hoc_raster_backward: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;

@@ -50,7 +50,12 @@ class GraphedConsistStep:
         if before_capture is not None:
             before_capture()  # e.g. arm the library's device timer so that the capture is instrumented
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on a HIGH-priority stream: the chain that stays on it (the render whose geometry gradient is needed,
+        # i.e. scan -> cover -> line pass of the rasterizer backward) is the critical path of the step, and kernel
+        # nodes inherit the priority of the stream they were captured on -- the side stream's work (default priority)
+        # fills in around it instead of delaying it
+        self.capture_stream = torch.cuda.Stream(device=dev, priority=-1)
+        with torch.cuda.graph(self.graph, stream=self.capture_stream):
             self.loss, self.grad_hand, self.grad_obj = self._run()
 
     def _run(self):
