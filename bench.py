@@ -304,9 +304,8 @@ def run_native(args, rank, world, local_rank):
         # cover pass with the pseudo-gradient: + rgb in, scan records out, grad_faces update
         "raster_bwd_pixel_k4": int(0.07 * npx) * (4 + 4 + 12 + 12 + 4 + 12 + 2) + PAIRS * F2 * (36 + 36 + 36),
         "raster_backward": PAIRS * F2 * (36 + 12 + 36),                  # depth epilogue (only with dL/ddepth)
-        # line pass: rgb + grad_rgb of the lines' spans once per axis (bounded by the whole map), scan records, faces of
-        # the queued scans, grad_faces update
-        "raster_bwd_line": 2 * npx * (12 + 12) + PAIRS * F2 * (36 + 36),
+        # line pass: rgb, grad_rgb, idx once (both axes read the same maps); faces of the queued scans, grad_faces update
+        "raster_bwd_line": npx * (12 + 12 + 4) + PAIRS * F2 * (36 + 36),
         "warp_photo_fwd": npx * (12 + 8 + 12 + 4 + 4 + 12 + 12 + 12 + 1),
         "warp_photo_bwd": npx * (12 + 8 + 12 + 1 + 8),
         "flow_finalize": 2 * npx * (2 * (8 + 4 + 4) + 8 + 4),
@@ -511,8 +510,9 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; stdout carries ONE JSON line
+        # stdout carries ONE JSON line: NCCL's banner / debug output (printed to stdout from NCCL_DEBUG=VERSION up) goes
+        # to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -10,24 +10,29 @@
  * passes over it) and scatters texture / depth gradients with one thread per pixel.  Here the work is
  * split by what it is parallel over:
  *
- *   hoc_raster_bwd_pixel_kernel   pixel-parallel.  Phase 1 streams face_index_map and the incoming gradients
- *           once: per-line spans of non-zero incoming gradient (a pixel with zero incoming gradient
- *           contributes exactly nothing to any scan, so scans are clipped to the span), and for covered
- *           pixels the texture / depth gradient of the owning face.  Phase 2 runs the pseudo-gradient FROM
- *           THE PIXELS: a pixel owned by face f lies on column x and row y of f; for each of the 3 edges x
- *           2 axes it evaluates that column of the edge once and (a) adds its own term of the short INWARD
- *           scan (the reference visits exactly the owned pixels between the edge and the opposite edge),
- *           (b) if it is the pixel just inside the edge, flags the long OUTWARD scan that starts there:
- *           one byte per pixel and axis (3 "edge e starts a scan here" bits + 3 direction bits), written
- *           coalesced -- row-major for row scans, transposed for column scans.  No per-face pass, no
- *           queues, no counters: a scan is identified by (line, position, edge), the face by
- *           face_index_map at that position.
+ *   hoc_raster_bwd_scan_kernel    pixel-parallel, pure streaming (one pass over face_index_map and the incoming
+ *           gradients): per-line spans of non-zero incoming gradient (a pixel with zero incoming gradient
+ *           contributes exactly nothing to any scan, so scans are clipped to the span), the list of covered
+ *           pixels that have work (one global atomic per 32 x 32 tile), and the zero-fill of the two outputs.
+ *   hoc_raster_bwd_cover_kernel   the work of the covered pixels, spread evenly over the GPU (covered pixels
+ *           cluster in a few tiles, the list un-clusters them): texture / depth gradient of the owning face --
+ *           weights and depth come from the forward's maps or are recomputed with the forward's functions
+ *           (bit-identical); the reference's two sampling maps (64 B/px) are never stored -- and the
+ *           pseudo-gradient run FROM THE PIXELS: a pixel owned by face f lies on column x and row y of f; for
+ *           each of the 3 edges x 2 axes (one warp per combination, 32 pixels per warp) it evaluates that column
+ *           of the edge once and (a) adds its own term of the short INWARD scan (the reference visits exactly
+ *           the owned pixels between the edge and the opposite edge), (b) if it is the pixel just inside the
+ *           edge, queues the long OUTWARD scan that starts there on the line it runs along (2-byte record).
+ *           There is no per-face pass: a face that owns no pixel has no term in either scan.
  *   hoc_raster_bwd_depth_kernel   face-parallel epilogue of backward_depth_map (only when dL/ddepth exists).
- *   hoc_raster_bwd_line_kernel    line-parallel: a CTA owns one image row or column, reads the line's flag
- *           bytes, compacts them IN POSITION ORDER into two lists (scans towards +, scans towards -, so
- *           that neighbouring lanes get scans of nearly equal length), stages the span of that line
- *           (P = sum_ch I_ch g_ch and g of every pixel) in shared memory ONCE and lets every lane run one
- *           outward scan out of shared memory; each scan adds its two vertex contributions to grad_faces.
+ *   hoc_raster_bwd_line_kernel    line-parallel: a CTA owns one image row or column, stages the span of that line
+ *           (P = sum_ch I_ch g_ch and g of every pixel) in shared memory ONCE; its warps then work independently:
+ *           32 queued scans are set up one per lane, cut into 16-pixel chunks, and every lane sums one chunk out
+ *           of shared memory (branch-free, MUFU.RCP) -- it finds its scan with a 5-step shuffle search over the
+ *           warp's prefix sums -- and adds the chunk's two vertex contributions to grad_faces.
+ *
+ * Measured progression on bench.py's workload (B = 16 renders of 9104 faces at 256 x 256, B200, in-graph):
+ * 548 us (one warp per face) -> 245 -> 121 -> 93 (pixel / face / line passes) -> 55 us (this decomposition).
  */
 #include "hoc_common.cuh"
 #include "raster_math.h"
@@ -509,9 +514,11 @@ hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__rest
 }
 
 /*
- * Line pass.  grid (ceil(S / G), 2, B): one CTA per group of G adjacent image columns (axis 0) or rows
- * (axis 1) -- a single line rarely carries enough outward scans to fill the CTA's warps, G lines do, and G
- * adjacent columns are read from HBM as 4 G contiguous bytes per row.
+ * Line pass.  grid (B, 2, ceil(S / G)): one CTA per group of G adjacent image columns (axis 0) or rows (axis 1),
+ * sample fastest and line groups ordered from the image centre outwards.  G = 1 is the measured optimum on B200
+ * (more lines per CTA lengthen the CTA's dependent chain -- ext -> queue -> face -> scan -- which is what bounds
+ * this pass; a persistent grid and splitting a line's scans over several CTAs were measured too and lost);
+ * HOC_TUNE_LINE_GROUP / _THREADS / _SEGMENT keep the sweep reproducible.
  */
 #define LN_THREADS 256
 #define LN_WARPS (LN_THREADS / 32)

@@ -136,8 +136,9 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
  *   use_alpha        1 when the forward produced alpha (return_alpha), else 0
  *   grad_faces       [B,F,3,3] out (fully overwritten) or NULL to skip the geometry gradient
  *   grad_textures    [B,F,ts,ts,ts,3] out (fully overwritten) or NULL to skip it
- *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes (line spans, per-face depth sums and two
- *                    outward-scan flag bytes per pixel)
+ *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes: line spans, counters, per-face depth sums,
+ *                    the list of covered pixels (4 S^2 B) and the per-line queues of outward scans (2-byte records,
+ *                    12 S^2 B worst case, of which only the used part is ever touched)
  */
 /* tex_grad_mode: CUBE = grad_textures is [B,F,ts,ts,ts,3] (the reference's backward_textures);
  * VERTEX = the cubes were built by hoc_mesh_gather from three vertex values per face (ts == 2): grad_textures
