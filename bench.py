@@ -458,6 +458,59 @@ def gpu_ref_equiv(steps=3, warmup=1):
                     "with ATen grid_sample, on this GPU, same workload; NOT the upstream binary (not installable)"}
 
 
+def mano_leg(hands=None, iters=50):
+    """ManoLayer forward + backward (hoc_mano_forward / hoc_mano_backward) on one hand per rendered
+    frame of the workload, inputs resident, CUDA-event timed.  Not part of `value` (the metric is render + warp +
+    photometric); reported beside it because the skinning is on the path."""
+    import torch
+
+    from handobjectconsist_b200 import synth
+    from handobjectconsist_b200.mano.manolayer import ManoLayer
+
+    hands = 2 * PAIRS if hands is None else hands
+    dev = torch.device("cuda", torch.cuda.current_device())
+    layer = ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=15, side="right", use_pca=True,
+                      model=synth.mano_model(seed=3)).to(dev)
+    g = torch.Generator().manual_seed(0)
+    pose = (torch.randn(hands, 18, generator=g) * 0.68).to(dev).requires_grad_(True)
+    betas = (torch.randn(hands, 10, generator=g) * 0.02).to(dev).requires_grad_(True)
+    gv = torch.randn(hands, 778, 3, generator=g).to(dev)
+
+    def one():
+        verts, joints = layer(pose, th_betas=betas)
+        torch.autograd.grad((verts * gv).sum() + joints.sum(), [pose, betas])
+
+    for _ in range(5):
+        one()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(iters):
+        one()
+    t1.record()
+    torch.cuda.synchronize()
+    us = t0.elapsed_time(t1) / iters * 1e3
+    # the two kernels alone (event-bracketed by the library)
+    from handobjectconsist_b200 import _lib
+    L = _lib.lib()
+    ids = _lib.KERNEL_IDS
+    L.hoc_timer_begin((1 << ids["mano_fwd"]) | (1 << ids["mano_bwd"]))
+    for _ in range(10):
+        one()
+    torch.cuda.synchronize()
+    buf, kid = (ctypes.c_float * 64)(), (ctypes.c_int * 64)()
+    n = L.hoc_timer_end(buf, kid, 64)
+    k_us = {}
+    for j in range(n):
+        k_us.setdefault(kid[j], []).append(buf[j] * 1e3)
+    med = lambda v: sorted(v)[len(v) // 2] if v else None
+    return {"hands": hands, "fwd_bwd_us": us, "hands_per_s": hands / (us * 1e-6),
+            "forward_kernel_us": med(k_us.get(ids["mano_fwd"], [])),
+            "backward_kernel_us": med(k_us.get(ids["mano_bwd"], [])),
+            "note": "ManoLayer forward + backward, eager (launch-bound: two kernels of this library plus the torch ops "
+                    "of the toy loss), synthetic MANO-shaped model"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return None
@@ -525,6 +578,11 @@ def main():
                 out["gpu_ref_equiv"]["speedup_of_value"] = out["value"] / out["gpu_ref_equiv"]["value"]
             except Exception as exc:  # a baseline leg must never cost the bench line
                 out["gpu_ref_equiv"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+        if world == 1:
+            try:
+                out["mano"] = mano_leg()
+            except Exception as exc:
+                out["mano"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), flush=True)

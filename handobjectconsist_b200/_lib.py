@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libhoc_b200.so")
 HOC_LAYOUT_RAW = 0
 HOC_LAYOUT_IMAGE = 1
 HOC_LAYOUT_KEYS_CLEARED = 0x100
+HOC_LAYOUT_TEX_VERTEX = 0x200
 HOC_TEX_GRAD_CUBE = 0
 HOC_TEX_GRAD_VERTEX = 1
 
@@ -41,7 +42,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_set_tuning": (_i, [_i, _i]),
-    "hoc_mesh_gather_clear": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_mesh_gather_clear": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "hoc_pair_loss": (_i, [_vp, _vp, _i, _vp, _vp]),
     "hoc_cat_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,

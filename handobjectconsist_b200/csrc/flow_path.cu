@@ -24,8 +24,8 @@
 __global__ void __launch_bounds__(FP_THREADS)
 hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict__ attrs,
                        const long long *__restrict__ faces_idx, int V, int F, int fill_back,
-                       float *__restrict__ faces_out, float *__restrict__ tex_out, uint4 *__restrict__ clear,
-                       long n_clear)
+                       float *__restrict__ faces_out, float *__restrict__ tex_out, int tex_vertex,
+                       uint4 *__restrict__ clear, long n_clear)
 {
     if (clear != nullptr) { /* 0xff fill of the z-buffer keys of the forward that follows, spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * FP_THREADS;
@@ -63,7 +63,14 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
                 c[k][2] = as[2];
             }
         }
-        if (tex_out != nullptr) {
+        if (tex_out != nullptr && tex_vertex) {
+            /* vertex mode: the three vertex values; the rasterizer evaluates the cube's texels on the fly */
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++)
+                    s_tex[threadIdx.x * 9 + 3 * k + ch] = c[k][ch];
+        } else if (tex_out != nullptr) {
             /* cube whose trilinear sample at the barycentric coordinates is b0 c0 + b1 c1 + b2 c2:
              * T[i,j,k] = i c0 + j c1 + k c2 (the reversed copy is the permute(0,1,4,3,2,5) of the original) */
 #pragma unroll
@@ -80,7 +87,11 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
     float *fd = faces_out + ((long)b * Fo + fo0) * 9;
     for (int i = threadIdx.x; i < nf * 9; i += FP_THREADS)
         fd[i] = s_face[i];
-    if (tex_out != nullptr) {
+    if (tex_out != nullptr && tex_vertex) {
+        float *td = tex_out + ((long)b * Fo + fo0) * 9;
+        for (int i = threadIdx.x; i < nf * 9; i += FP_THREADS)
+            td[i] = s_tex[i];
+    } else if (tex_out != nullptr) {
         float4 *td = reinterpret_cast<float4 *>(tex_out + ((long)b * Fo + fo0) * 24);
         const float4 *ts4 = reinterpret_cast<const float4 *>(s_tex);
         for (int i = threadIdx.x; i < nf * 6; i += FP_THREADS)
@@ -549,19 +560,22 @@ extern "C" int hoc_cat_meshes(const float *hand_a, const float *obj_a, const flo
 
 /* ------------------------------------------------------------------------------------------ */
 extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V,
-                                     int F, int fill_back, float *faces_out, float *textures_out, void *clear,
-                                     size_t clear_bytes, void *stream);
+                                     int F, int fill_back, int tex_mode, float *faces_out, float *textures_out,
+                                     void *clear, size_t clear_bytes, void *stream);
 
 extern "C" int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                                int fill_back, float *faces_out, float *textures_out, void *stream)
 {
-    return hoc_mesh_gather_clear(verts, attrs, faces_idx, B, V, F, fill_back, faces_out, textures_out, nullptr, 0, stream);
+    return hoc_mesh_gather_clear(verts, attrs, faces_idx, B, V, F, fill_back, HOC_TEX_GRAD_CUBE, faces_out, textures_out,
+                                 nullptr, 0, stream);
 }
 
 extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V,
-                                     int F, int fill_back, float *faces_out, float *textures_out, void *clear,
-                                     size_t clear_bytes, void *stream)
+                                     int F, int fill_back, int tex_mode, float *faces_out, float *textures_out,
+                                     void *clear, size_t clear_bytes, void *stream)
 {
+    HOC_CHECK_ARG(tex_mode == HOC_TEX_GRAD_CUBE || tex_mode == HOC_TEX_GRAD_VERTEX, "hoc_mesh_gather_clear: tex_mode %d",
+                  tex_mode);
     HOC_CHECK_ARG(clear == nullptr || (clear_bytes % 16 == 0 && ((uintptr_t)clear & 15) == 0),
                   "hoc_mesh_gather_clear: clear buffer must be 16-byte aligned with a size multiple of 16");
     if (clear != nullptr && (B == 0 || F == 0)) { /* nothing to gather: still honour the fill */
@@ -580,8 +594,8 @@ extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, con
     dim3 grid((Fo + FP_THREADS - 1) / FP_THREADS, B);
     HOC_LAUNCH(HOC_K_MESH_GATHER, (cudaStream_t)stream,
                (hoc_mesh_gather_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
-                   verts, attrs, faces_idx, V, F, fill_back, faces_out, textures_out, (uint4 *)clear,
-                   (long)(clear_bytes / 16))));
+                   verts, attrs, faces_idx, V, F, fill_back, faces_out, textures_out,
+                   tex_mode == HOC_TEX_GRAD_VERTEX ? 1 : 0, (uint4 *)clear, (long)(clear_bytes / 16))));
     HOC_CHECK_LAUNCH("hoc_mesh_gather_kernel");
     return HOC_OK;
 }

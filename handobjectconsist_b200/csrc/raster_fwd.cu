@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(RS_THREADS)
 hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
                           const unsigned long long *__restrict__ zbuf, int F, int S, int ts, float near_, float far_,
                           float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int layout,
-                          float *__restrict__ rgb, float *__restrict__ alpha, float *__restrict__ depth,
+                          int tex_vertex, float *__restrict__ rgb, float *__restrict__ alpha, float *__restrict__ depth,
                           int32_t *__restrict__ face_index_map, float *__restrict__ weight_map,
                           float *__restrict__ face_inv_map)
 {
@@ -251,7 +251,16 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
             hoc_face_inv(f, S, inv);
             hoc_pixel_weights_depth(f, inv, xi, yi, near_, far_, w, &zp);
             if (rgb != nullptr) {
-                const float *tex = textures + ((long)b * F + fidx) * ts * ts * ts * 3;
+                /* cube mode: [ts,ts,ts,3] texels per face.  vertex mode (ts == 2): three vertex values c0, c1, c2 per
+                 * face; the texel of corner (i, j, k) is i c0 + j c1 + k c2, evaluated with hoc_mesh_gather's
+                 * expression so that the sample is bit-identical to the one taken from the materialised cube */
+                const float *tex = textures + ((long)b * F + fidx) * (tex_vertex ? 9 : ts * ts * ts * 3);
+                float cv[3][3];
+                if (tex_vertex) {
+#pragma unroll
+                    for (int k = 0; k < 9; k++)
+                        cv[k / 3][k % 3] = __ldg(tex + k);
+                }
                 float tf[3];
                 int ti[3];
 #pragma unroll
@@ -278,9 +287,16 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
                     /* a tap with zero weight may point one past the cube when ts == 1 */
                     if (ts == 1)
                         isc = 0;
+                    if (tex_vertex) {
+                        const float wi = (float)((isc >> 2) & 1), wj = (float)((isc >> 1) & 1), wk = (float)(isc & 1);
 #pragma unroll
-                    for (int c = 0; c < 3; c++)
-                        acc[c] += ww * __ldg(tex + isc * 3 + c);
+                        for (int c = 0; c < 3; c++)
+                            acc[c] += ww * (wi * cv[0][c] + wj * cv[1][c] + wk * cv[2][c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            acc[c] += ww * __ldg(tex + isc * 3 + c);
+                    }
                 }
                 col[0] = acc[0];
                 col[1] = acc[1];
@@ -329,7 +345,9 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     HOC_CHECK_ARG(B >= 0 && F >= 0, "hoc_raster_forward: negative batch (%d) or face count (%d)", B, F);
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_forward: image_size %d outside [1, 2048]", S);
     const bool keys_cleared = (layout & HOC_LAYOUT_KEYS_CLEARED) != 0; /* the caller filled the workspace with 0xff */
-    layout &= ~HOC_LAYOUT_KEYS_CLEARED;
+    const int tex_vertex = (layout & HOC_LAYOUT_TEX_VERTEX) ? 1 : 0;   /* textures = [B,F,3,3] vertex values */
+    layout &= ~(HOC_LAYOUT_KEYS_CLEARED | HOC_LAYOUT_TEX_VERTEX);
+    HOC_CHECK_ARG(!tex_vertex || ts == 2, "hoc_raster_forward: vertex textures need texture_size 2, got %d", ts);
     HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_forward: bad layout %d", layout);
     HOC_CHECK_ARG(face_index_map != nullptr, "hoc_raster_forward: face_index_map is required");
     HOC_CHECK_ARG(rgb == nullptr || ((textures != nullptr || F == 0) && ts >= 1),
@@ -367,9 +385,9 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     dim3 grid2((unsigned)((npix + RS_THREADS - 1) / RS_THREADS), B);
     HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
                (hoc_raster_resolve_kernel<<<grid2, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
-                                                                        bg[0], bg[1], bg[2], background_dev, layout, rgb,
-                                                                        alpha, depth, face_index_map, weight_map,
-                                                                        face_inv_map)));
+                                                                        bg[0], bg[1], bg[2], background_dev, layout,
+                                                                        tex_vertex, rgb, alpha, depth, face_index_map,
+                                                                        weight_map, face_inv_map)));
     HOC_CHECK_LAUNCH("hoc_raster_resolve_kernel");
     return HOC_OK;
 }

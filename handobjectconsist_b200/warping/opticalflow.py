@@ -48,13 +48,15 @@ class _MeshRasterFunction(Function):
         bg = (ctypes.c_float * 3)(*[float(c) for c in background_color])
         with torch.cuda.device(dev):
             faces = torch.empty((B, Fo, 3, 3), dtype=torch.float32, device=dev)
-            tex = torch.empty((B, Fo, 2, 2, 2, 3), dtype=torch.float32, device=dev)
+            # three vertex values per face: the forward evaluates the cube T[i,j,k] = i c0 + j c1 + k c2 on the fly
+            tex = torch.empty((B, Fo, 3, 3), dtype=torch.float32, device=dev)
             st = _lib.stream_ptr()
             # the gather also 0xff-fills the z-buffer keys of the forward below (one graph node less between them)
             ws_bytes = L.hoc_raster_forward_workspace_bytes(B, Fo, S)
             ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
             _lib.check(L.hoc_mesh_gather_clear(_lib.ptr(v), _lib.ptr(a), _lib.ptr(fi), B, V, Fn, int(fill_back),
-                                               _lib.ptr(faces), _lib.ptr(tex), _lib.ptr(ws), ws_bytes, st),
+                                               _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(faces), _lib.ptr(tex), _lib.ptr(ws),
+                                               ws_bytes, st),
                        "hoc_mesh_gather_clear")
             rgb = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
             alpha = torch.empty((B, S, S), dtype=torch.float32, device=dev)
@@ -63,7 +65,8 @@ class _MeshRasterFunction(Function):
             wmap = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)  # saved for the backward
             _lib.check(L.hoc_raster_forward(_lib.ptr(faces), _lib.ptr(tex), B, Fo, S, 2, float(near), float(far),
                                             float(eps), bg, None,
-                                            _lib.HOC_LAYOUT_IMAGE | _lib.HOC_LAYOUT_KEYS_CLEARED, _lib.ptr(rgb),
+                                            _lib.HOC_LAYOUT_IMAGE | _lib.HOC_LAYOUT_KEYS_CLEARED | _lib.HOC_LAYOUT_TEX_VERTEX,
+                                            _lib.ptr(rgb),
                                             _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx), _lib.ptr(wmap), None,
                                             _lib.ptr(ws), ws_bytes, st), "hoc_raster_forward")
         ctx.save_for_backward(faces, fi, idx, rgb, wmap, depth)

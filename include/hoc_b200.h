@@ -48,6 +48,10 @@ extern "C" {
 /* OR-ed into `layout` of hoc_raster_forward: the workspace already holds 0xff bytes (hoc_mesh_gather_clear did it),
  * so the forward skips its own fill -- one graph node less on the critical path of the fused flow path */
 #define HOC_LAYOUT_KEYS_CLEARED 0x100
+/* OR-ed into `layout` of hoc_raster_forward: `textures` is [B,F,3,3] -- three vertex values c0, c1, c2 per face -- and
+ * stands for the cube T[i,j,k] = i c0 + j c1 + k c2 (texture_size 2), whose texels the forward evaluates on the fly
+ * with hoc_mesh_gather's expression: same bits as sampling the materialised cube, 36 instead of 96 bytes per face */
+#define HOC_LAYOUT_TEX_VERTEX 0x200
 
 int hoc_abi_version(void);
 const char *hoc_last_error(void);
@@ -215,11 +219,13 @@ int hoc_occlusion_mask(const float *mask1, const float *mask2, const float *flow
  *   faces F..2F-1 are the reversed windings, their cubes the permute(0,1,4,3,2,5) of the originals). */
 int hoc_mesh_gather(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
                     int fill_back, float *faces_out, float *textures_out, void *stream);
-/* hoc_mesh_gather that also fills `clear` (clear_bytes, a multiple of 16, 16-byte aligned) with 0xff bytes: the
- * z-buffer workspace of the hoc_raster_forward call that follows (pass HOC_LAYOUT_KEYS_CLEARED there). */
+/* hoc_mesh_gather that also fills `clear` (clear_bytes, a multiple of 16, 16-byte aligned; may be NULL) with 0xff
+ * bytes: the z-buffer workspace of the hoc_raster_forward call that follows (pass HOC_LAYOUT_KEYS_CLEARED there).
+ * tex_mode HOC_TEX_GRAD_VERTEX: textures_out is [B,F',3,3], the three vertex values of every face (for
+ * HOC_LAYOUT_TEX_VERTEX) instead of the [B,F',2,2,2,3] cubes. */
 int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V, int F,
-                          int fill_back, float *faces_out, float *textures_out, void *clear, size_t clear_bytes,
-                          void *stream);
+                          int fill_back, int tex_mode, float *faces_out, float *textures_out, void *clear,
+                          size_t clear_bytes, void *stream);
 /* batch_cat_meshes (libyana.renderutils.catmesh, called at /root/reference/meshreg/models/warpbranch.py:50-52) for
  * the hand + object pair of one or two frames in ONE launch: verts_x [B,Vh+Vo,3] = cat(hand_x, obj_x),
  * faces [B,Fh+Fo,3] = cat(hand_faces, obj_faces + Vh).  hand_faces is [Fh,3] (shared) or [B,Fh,3]

@@ -166,3 +166,51 @@ def test_graphed_step_matches_eager():
     dres[0] = {"recov_handverts3d": h2, "recov_objverts3d": dres[0]["recov_objverts3d"].detach()}
     (gstep.apply(samples, dres) * 3.0).backward()
     assert helpers.rel_err(h2.grad.cpu().numpy(), 3.0 * h.grad.cpu().numpy()) < 1e-4
+
+
+def test_vertex_texture_mode_is_bit_identical_to_cubes():
+    """hoc_mesh_gather_clear(VERTEX) + hoc_raster_forward(HOC_LAYOUT_TEX_VERTEX) evaluates the cube texels on the fly:
+    rgb must equal, bit for bit, the render of the materialised [B,F',2,2,2,3] cubes (and the gather's key fill must
+    leave the forward's result unchanged)."""
+    import ctypes
+
+    from handobjectconsist_b200 import _lib
+    from oracle import nrfuncs
+
+    L = _lib.lib()
+    S, B = 64, 2
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, S, seed=11)
+    R, t, dist = torch.eye(3)[None], torch.zeros(1, 1, 3), torch.zeros(1, 5)
+    ndc = nrfuncs.projection(sc["verts1"], sc["K"], R, t, dist, float(S)).to(dev).contiguous()
+    attrs = torch.randn(B, ndc.shape[1], 3, generator=torch.Generator().manual_seed(0)).to(dev)
+    fi = sc["faces"].to(dev).long().contiguous()
+    V, Fn = ndc.shape[1], fi.shape[1]
+    Fo = 2 * Fn
+    st = _lib.stream_ptr()
+    bg = (ctypes.c_float * 3)(0.0, 0.0, 0.0)
+    outs = []
+    for mode in (_lib.HOC_TEX_GRAD_CUBE, _lib.HOC_TEX_GRAD_VERTEX):
+        faces = torch.empty((B, Fo, 3, 3), device=dev)
+        tex = torch.empty((B, Fo, 2, 2, 2, 3) if mode == _lib.HOC_TEX_GRAD_CUBE else (B, Fo, 3, 3), device=dev)
+        n = L.hoc_raster_forward_workspace_bytes(B, Fo, S)
+        ws = torch.empty(n, dtype=torch.uint8, device=dev)
+        layout = _lib.HOC_LAYOUT_IMAGE
+        if mode == _lib.HOC_TEX_GRAD_VERTEX:
+            _lib.check(L.hoc_mesh_gather_clear(_lib.ptr(ndc), _lib.ptr(attrs), _lib.ptr(fi), B, V, Fn, 1, mode,
+                                               _lib.ptr(faces), _lib.ptr(tex), _lib.ptr(ws), n, st), "gather_clear")
+            layout |= _lib.HOC_LAYOUT_KEYS_CLEARED | _lib.HOC_LAYOUT_TEX_VERTEX
+        else:
+            _lib.check(L.hoc_mesh_gather(_lib.ptr(ndc), _lib.ptr(attrs), _lib.ptr(fi), B, V, Fn, 1, _lib.ptr(faces),
+                                         _lib.ptr(tex), st), "gather")
+        rgb = torch.empty((B, 3, S, S), device=dev)
+        alpha, depth = torch.empty((B, S, S), device=dev), torch.empty((B, S, S), device=dev)
+        idx = torch.empty((B, S, S), dtype=torch.int32, device=dev)
+        _lib.check(L.hoc_raster_forward(_lib.ptr(faces), _lib.ptr(tex), B, Fo, S, 2, 0.1, 100.0, 1e-3, bg, None, layout,
+                                        _lib.ptr(rgb), _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx), None, None,
+                                        _lib.ptr(ws), n, st), "forward")
+        outs.append((rgb, alpha, depth, idx))
+    torch.cuda.synchronize()
+    assert (outs[0][3] >= 0).float().mean().item() > 0.02  # the scene covers something
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
