@@ -42,6 +42,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_set_tuning": (_i, [_i, _i]),
+    "hoc_flow_finalize_backward_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hoc_mesh_gather_clear": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "hoc_pair_loss": (_i, [_vp, _vp, _i, _vp, _vp]),
     "hoc_cat_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
@@ -75,14 +76,16 @@ KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_b
 
 class ManoModelStruct(ctypes.Structure):
     """``hoc_mano_model`` of include/hoc_b200.h."""
-    _fields_ = [("v_template", _vp), ("shapedirs", _vp), ("posedirs", _vp), ("j_regressor", _vp), ("weights", _vp),
+    _fields_ = [("v_template", _vp), ("shapedirs", _vp), ("posedirs", _vp), ("j_regressor", _vp), ("posedirs_t", _vp),
+                ("j_template", _vp), ("j_shapedirs", _vp), ("weights", _vp),
                 ("hands_components", _vp), ("hands_mean", _vp), ("num_verts", _i), ("ncomps", _i), ("use_pca", _i),
                 ("center_idx", _i), ("tip_ids", _i * 5)]
 
 
 SIGNATURES["hoc_mano_forward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp, _vp, _i, _vp, _vp, _vp])
+SIGNATURES["hoc_mano_backward_workspace_bytes"] = (_sz, [_i])
 SIGNATURES["hoc_mano_backward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
-                                        _vp])
+                                        _vp, _sz, _vp])
 
 _LIB = None
 

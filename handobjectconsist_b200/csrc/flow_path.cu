@@ -317,8 +317,14 @@ hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const 
 /* grad_rgb [B,3,S,S] (image layout) = grad_flow [B,H,W,2] * mult inside the crop, 0 elsewhere / channel 2 */
 __global__ void __launch_bounds__(FP_THREADS)
 hoc_flow_finalize_backward_kernel(const float *__restrict__ grad_flow, const float *__restrict__ mult, int S, int H,
-                                  int W, float *__restrict__ grad_rgb)
+                                  int W, float *__restrict__ grad_rgb, const float *__restrict__ grad_flow_b,
+                                  const float *__restrict__ mult_b, float *__restrict__ grad_rgb_b)
 {
+    if (blockIdx.z == 1) { /* the second direction of a pair, same launch */
+        grad_flow = grad_flow_b;
+        mult = mult_b;
+        grad_rgb = grad_rgb_b;
+    }
     const int b = blockIdx.y;
     const long pix = (long)blockIdx.x * FP_THREADS + threadIdx.x;
     const long npix = (long)S * S;
@@ -672,8 +678,28 @@ extern "C" int hoc_flow_finalize_backward(const float *grad_flow, const float *m
     const long npix = (long)S * S;
     dim3 grid((unsigned)((npix + FP_THREADS - 1) / FP_THREADS), B);
     HOC_LAUNCH(HOC_K_FLOW_FINALIZE_BWD, (cudaStream_t)stream,
-               (hoc_flow_finalize_backward_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(grad_flow, mult, S, H,
-                                                                                                W, grad_rgb)));
+               (hoc_flow_finalize_backward_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   grad_flow, mult, S, H, W, grad_rgb, nullptr, nullptr, nullptr)));
+    HOC_CHECK_LAUNCH("hoc_flow_finalize_backward_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_flow_finalize_backward_pair(const float *grad_flow12, const float *mult1, const float *grad_flow21,
+                                               const float *mult2, int B, int S, int H, int W, float *grad_rgb1,
+                                               float *grad_rgb2, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && S >= 1 && H >= 1 && W >= 1 && H <= S && W <= S,
+                  "hoc_flow_finalize_backward_pair: bad shape B=%d S=%d H=%d W=%d", B, S, H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_flow_finalize_backward_pair: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(grad_flow12 && mult1 && grad_rgb1 && grad_flow21 && mult2 && grad_rgb2,
+                  "hoc_flow_finalize_backward_pair: NULL argument");
+    const long npix = (long)S * S;
+    dim3 grid((unsigned)((npix + FP_THREADS - 1) / FP_THREADS), B, 2);
+    HOC_LAUNCH(HOC_K_FLOW_FINALIZE_BWD, (cudaStream_t)stream,
+               (hoc_flow_finalize_backward_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   grad_flow12, mult1, S, H, W, grad_rgb1, grad_flow21, mult2, grad_rgb2)));
     HOC_CHECK_LAUNCH("hoc_flow_finalize_backward_kernel");
     return HOC_OK;
 }

@@ -9,11 +9,16 @@
  *   forward kinematics (root + 5 fingers x 3 levels), rest joints removed
  *   per-vertex blend of the 16 transforms, fingertip vertices appended to the joints, joint reorder,
  *   centring on `center_idx` (or + trans), millimetres.
- * In torch this is ~60 tiny launches (batched 4x4 matmuls, cats, index selects); here ONE CTA per sample
- * does the whole forward, and one CTA per sample the whole backward: the big linear maps (posedirs,
- * shapedirs, J_regressor, skinning weights) are reversed by hand, the 16-joint kinematic chain and the
- * Rodrigues formula are differentiated with forward-mode dual numbers (96 seeds: 48 pose + 48 joint
- * coordinates, one per thread) through the SAME templated code the forward runs.
+ * In torch this is ~60 tiny launches (batched 4x4 matmuls, cats, index selects).  Here the forward is ONE launch with
+ * a CTA per (64-vertex slice, sample): every CTA rebuilds the sample's small state (16 rotations, joints, kinematic
+ * chain: a few hundred flops) and produces its slice -- the joint regression is folded into two model constants
+ * (J = j_template + j_shapedirs . betas), so no CTA needs the whole shaped mesh, and the pose blend shapes are read
+ * through a transposed copy, coalesced.  (One CTA per sample, the first version, left 116 of 148 SMs idle at B = 32
+ * and took 265 us.)  The backward is two launches: the vertex-parallel part per (slice, sample) -- the big linear maps
+ * (posedirs, shapedirs, skinning weights) reversed by hand, reduced in the CTA and added to per-sample accumulators --
+ * and a small per-sample kernel that differentiates the 16-joint kinematic chain and the Rodrigues formula with
+ * forward-mode dual numbers (96 seeds: 48 pose + 48 joint coordinates, one per thread) through the SAME templated
+ * code the forward runs.
  */
 #include "hoc_common.cuh"
 
@@ -135,7 +140,10 @@ __device__ __forceinline__ void mano_fk(GetR getR, GetJ getJ, Sink sink)
     }
 }
 
-struct ManoShared {
+__constant__ int c_reorder_joints[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
+
+/* Per-sample state every CTA that works on the sample rebuilds for itself (a few hundred flops). */
+struct ManoPose {
     float full_pose[48];
     float R[16][9];
     float pose_map[135];
@@ -144,17 +152,21 @@ struct ManoShared {
     float AR[16][9]; /* skinning transforms: rotation */
     float At[16][3]; /*                       translation (rest joint removed) */
     float Gt[16][3]; /* global joint positions */
+    float tipvp[5][3]; /* posed rest position of the five fingertip vertices */
+    float tip[5][3];   /* their skinned position */
     float centre[3];
-    float vs[MN_MAXV * 3]; /* v_shaped, then v_posed */
 };
 
-__constant__ int c_reorder_joints[21] = {0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20};
+#define MN_VS 64              /* vertices per CTA */
+#define MN_CS (3 * MN_VS)     /* coordinates per CTA */
+#define MN_ACC 352            /* per-sample accumulators of the backward: gA [16][12], gpm [135], gbetas [10], pad */
 
-/* Steps shared by forward and backward: everything up to the skinning transforms, in shared memory. */
-__device__ void mano_prepare(const hoc_mano_model &M, const float *pose, const float *betas, int b, ManoShared &S)
+/* pose -> full pose -> 16 rotations, pose_map; betas -> J (J = j_template + j_shapedirs . betas: the joint
+ * regression of the shaped template is linear in betas, so it is folded into two model constants). */
+__device__ __forceinline__ void mano_pose_setup(const hoc_mano_model &M, const float *pose, const float *betas, int b,
+                                                ManoPose &P)
 {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int V = M.num_verts;
+    const int tid = threadIdx.x;
     const int npose = 3 + M.ncomps;
     if (tid < 48) {
         float p;
@@ -170,101 +182,115 @@ __device__ void mano_prepare(const hoc_mano_model &M, const float *pose, const f
                 p += pose[(long)b * npose + 3 + t];
             }
         }
-        S.full_pose[tid] = p;
+        P.full_pose[tid] = p;
     }
     if (tid >= 64 && tid < 74)
-        S.betas[tid - 64] = (betas != nullptr) ? betas[(long)b * 10 + tid - 64] : 0.0f;
+        P.betas[tid - 64] = (betas != nullptr) ? betas[(long)b * 10 + tid - 64] : 0.0f;
     __syncthreads();
     if (tid < 16) {
         float R[9];
-        mano_rodrigues<float>(&S.full_pose[3 * tid], R);
+        mano_rodrigues<float>(&P.full_pose[3 * tid], R);
 #pragma unroll
         for (int k = 0; k < 9; k++) {
-            S.R[tid][k] = R[k];
+            P.R[tid][k] = R[k];
             if (tid > 0)
-                S.pose_map[(tid - 1) * 9 + k] = R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f);
+                P.pose_map[(tid - 1) * 9 + k] = R[k] - ((k == 0 || k == 4 || k == 8) ? 1.0f : 0.0f);
         }
     }
-    /* v_shaped */
-    for (int i = tid; i < V * 3; i += MN_THREADS) {
-        float a = M.v_template[i];
-        const float *sd = M.shapedirs + (long)i * 10;
+    if (tid >= 64 && tid < 112) {
+        const int e = tid - 64; /* joint e / 3, coordinate e % 3 */
+        float a = M.j_template[e];
 #pragma unroll
         for (int k = 0; k < 10; k++)
-            a += sd[k] * S.betas[k];
-        S.vs[i] = a;
-    }
-    __syncthreads();
-    /* J = J_regressor . v_shaped : warp w handles joints w, w + 8 */
-    for (int j = warp; j < 16; j += MN_THREADS / 32) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-        for (int v = lane; v < V; v += 32) {
-            const float r = M.j_regressor[(long)j * V + v];
-            a0 += r * S.vs[3 * v];
-            a1 += r * S.vs[3 * v + 1];
-            a2 += r * S.vs[3 * v + 2];
-        }
-        a0 = hoc_warp_sum(a0);
-        a1 = hoc_warp_sum(a1);
-        a2 = hoc_warp_sum(a2);
-        if (lane == 0) {
-            S.J[j][0] = a0;
-            S.J[j][1] = a1;
-            S.J[j][2] = a2;
-        }
-    }
-    __syncthreads();
-    /* v_posed = v_shaped + posedirs . pose_map : one warp per output coordinate, coalesced over the 135 */
-    for (int i = warp; i < V * 3; i += MN_THREADS / 32) {
-        const float *pd = M.posedirs + (long)i * 135;
-        float a = 0.f;
-        for (int k = lane; k < 135; k += 32)
-            a += pd[k] * S.pose_map[k];
-        a = hoc_warp_sum(a);
-        if (lane == 0)
-            S.vs[i] += a;
-    }
-    /* forward kinematics (thread 0; 16 small transforms) */
-    if (tid == 0) {
-        mano_fk<float>([&](int j, float *R) {
-#pragma unroll
-            for (int k = 0; k < 9; k++)
-                R[k] = S.R[j][k]; },
-                       [&](int j, float *J) {
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                J[k] = S.J[j][k]; },
-                       [&](int j, const float *GR, const float *Gt) {
-#pragma unroll
-            for (int k = 0; k < 9; k++)
-                S.AR[j][k] = GR[k];
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                S.Gt[j][r] = Gt[r];
-                S.At[j][r] = Gt[r] - (GR[3 * r] * S.J[j][0] + GR[3 * r + 1] * S.J[j][1] + GR[3 * r + 2] * S.J[j][2]);
-            } });
+            a += M.j_shapedirs[e * 10 + k] * P.betas[k];
+        (&P.J[0][0])[e] = a;
     }
     __syncthreads();
 }
 
-/* blended transform of vertex v applied to its posed rest position */
-__device__ __forceinline__ void mano_skin(const hoc_mano_model &M, const ManoShared &S, int v, float *out, float *TR)
+/* forward kinematics: 16 small transforms, one thread */
+__device__ __forceinline__ void mano_pose_fk(ManoPose &P)
+{
+    mano_fk<float>([&](int j, float *R) {
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            R[k] = P.R[j][k]; },
+                   [&](int j, float *J) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            J[k] = P.J[j][k]; },
+                   [&](int j, const float *GR, const float *Gt) {
+#pragma unroll
+        for (int k = 0; k < 9; k++)
+            P.AR[j][k] = GR[k];
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            P.Gt[j][r] = Gt[r];
+            P.At[j][r] = Gt[r] - (GR[3 * r] * P.J[j][0] + GR[3 * r + 1] * P.J[j][1] + GR[3 * r + 2] * P.J[j][2]);
+        } });
+}
+
+/* v_posed coordinate i = template + shapedirs . betas + posedirs . pose_map, one thread, coalesced over i through the
+ * transposed pose blend shapes [135][3V] */
+__device__ __forceinline__ float mano_vposed_coord(const hoc_mano_model &M, const ManoPose &P, int i)
+{
+    const int n = 3 * M.num_verts;
+    float a = M.v_template[i];
+    const float *sd = M.shapedirs + (long)i * 10;
+#pragma unroll
+    for (int k = 0; k < 10; k++)
+        a += sd[k] * P.betas[k];
+    const float *pt = M.posedirs_t + i;
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 5
+    for (int k = 0; k < 135; k += 5) {
+#pragma unroll
+        for (int u = 0; u < 5; u++)
+            acc[u] += __ldg(pt + (long)(k + u) * n) * P.pose_map[k + u];
+    }
+    return a + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + acc[4]);
+}
+
+/* the same for one coordinate by a whole warp (lanes over the 135 pose-map entries) */
+__device__ __forceinline__ float mano_vposed_coord_warp(const hoc_mano_model &M, const ManoPose &P, int i, int lane)
+{
+    const float *pd = M.posedirs + (long)i * 135;
+    float a = 0.0f;
+    for (int k = lane; k < 135; k += 32)
+        a += pd[k] * P.pose_map[k];
+    a = hoc_warp_sum(a);
+    float base = M.v_template[i];
+    const float *sd = M.shapedirs + (long)i * 10;
+#pragma unroll
+    for (int k = 0; k < 10; k++)
+        base += sd[k] * P.betas[k];
+    return base + a;
+}
+
+/* blended transform of vertex v applied to its posed rest position (x, y, z) */
+__device__ __forceinline__ void mano_skin(const hoc_mano_model &M, const ManoPose &P, int v, float x, float y, float z,
+                                          float *out, float *TR)
 {
     float T[12];
 #pragma unroll
     for (int k = 0; k < 12; k++)
         T[k] = 0.0f;
-    const float *w = M.weights + (long)v * 16;
-    for (int j = 0; j < 16; j++) {
-        const float wj = w[j];
+    const float4 *w4 = reinterpret_cast<const float4 *>(M.weights + (long)v * 16);
 #pragma unroll
-        for (int k = 0; k < 9; k++)
-            T[k] += wj * S.AR[j][k];
+    for (int q = 0; q < 4; q++) {
+        const float4 wq = __ldg(w4 + q);
+        const float wv[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
-        for (int k = 0; k < 3; k++)
-            T[9 + k] += wj * S.At[j][k];
+        for (int u = 0; u < 4; u++) {
+            const int j = 4 * q + u;
+#pragma unroll
+            for (int k = 0; k < 9; k++)
+                T[k] += wv[u] * P.AR[j][k];
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                T[9 + k] += wv[u] * P.At[j][k];
+        }
     }
-    const float x = S.vs[3 * v], y = S.vs[3 * v + 1], z = S.vs[3 * v + 2];
 #pragma unroll
     for (int r = 0; r < 3; r++)
         out[r] = T[3 * r] * x + T[3 * r + 1] * y + T[3 * r + 2] * z + T[9 + r];
@@ -275,17 +301,34 @@ __device__ __forceinline__ void mano_skin(const hoc_mano_model &M, const ManoSha
     }
 }
 
-__global__ void __launch_bounds__(MN_THREADS)
-hoc_mano_forward_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
-                        const float *__restrict__ trans, float *__restrict__ verts, float *__restrict__ joints)
+/* Steps shared by the forward and the first backward kernel: pose set-up, then -- concurrently -- forward kinematics
+ * (thread 0), the slice's posed rest positions (threads 32 .. 32 + MN_CS) and the fingertips' (warp 7); then the
+ * skinned fingertips and the centre. */
+__device__ __forceinline__ void mano_slice_setup(const hoc_mano_model &M, const float *pose, const float *betas,
+                                                 const float *trans, int b, int v0, ManoPose &P, float *s_vp)
 {
-    extern __shared__ unsigned char smem_raw[];
-    ManoShared &S = *reinterpret_cast<ManoShared *>(smem_raw);
-    const int b = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int V = M.num_verts;
-    mano_prepare(M, pose, betas, b, S);
-    /* centre: reordered joint `center_idx` = original joint (< 16) or fingertip vertex */
+    mano_pose_setup(M, pose, betas, b, P);
+    if (tid == 0)
+        mano_pose_fk(P);
+    if (tid >= 32 && tid < 32 + MN_CS) {
+        const int il = tid - 32, i = 3 * v0 + il;
+        s_vp[il] = (i < 3 * V) ? mano_vposed_coord(M, P, i) : 0.0f;
+    }
+    if (tid >= 224) {
+        for (int e = 0; e < 15; e++) {
+            const float a = mano_vposed_coord_warp(M, P, 3 * M.tip_ids[e / 3] + e % 3, lane);
+            if (lane == 0)
+                P.tipvp[e / 3][e % 3] = a;
+        }
+    }
+    __syncthreads();
+    if (tid < 5)
+        mano_skin(M, P, M.tip_ids[tid], P.tipvp[tid][0], P.tipvp[tid][1], P.tipvp[tid][2], P.tip[tid], nullptr);
+    __syncthreads();
     if (tid == 0) {
+        /* centre: -trans, or reordered joint `center_idx` = original joint (< 16) or fingertip vertex */
         float c[3] = {0.f, 0.f, 0.f};
         if (trans != nullptr) {
 #pragma unroll
@@ -293,161 +336,217 @@ hoc_mano_forward_kernel(hoc_mano_model M, const float *__restrict__ pose, const 
                 c[k] = -trans[(long)b * 3 + k];
         } else if (M.center_idx >= 0) {
             const int src = c_reorder_joints[M.center_idx];
-            if (src < 16) {
-#pragma unroll
-                for (int k = 0; k < 3; k++)
-                    c[k] = S.Gt[src][k];
-            } else {
-                mano_skin(M, S, M.tip_ids[src - 16], c, nullptr);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            S.centre[k] = c[k];
-    }
-    __syncthreads();
-    for (int v = tid; v < V; v += MN_THREADS) {
-        float o[3];
-        mano_skin(M, S, v, o, nullptr);
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            verts[((long)b * V + v) * 3 + k] = (o[k] - S.centre[k]) * 1000.0f;
-    }
-    if (tid < 21) {
-        const int src = c_reorder_joints[tid];
-        float o[3];
-        if (src < 16) {
 #pragma unroll
             for (int k = 0; k < 3; k++)
-                o[k] = S.Gt[src][k];
-        } else {
-            mano_skin(M, S, M.tip_ids[src - 16], o, nullptr);
+                c[k] = (src < 16) ? P.Gt[src][k] : P.tip[src - 16][k];
         }
 #pragma unroll
         for (int k = 0; k < 3; k++)
-            joints[((long)b * 21 + tid) * 3 + k] = (o[k] - S.centre[k]) * 1000.0f;
+            P.centre[k] = c[k];
+    }
+    __syncthreads();
+}
+
+/* grid (ceil(V / MN_VS), B): CTA (s, b) produces vertices [s MN_VS, (s + 1) MN_VS) of sample b; CTA (0, b) also the
+ * 21 joints. */
+__global__ void __launch_bounds__(MN_THREADS)
+hoc_mano_forward_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
+                        const float *__restrict__ trans, float *__restrict__ verts, float *__restrict__ joints)
+{
+    __shared__ ManoPose P;
+    __shared__ float s_vp[MN_CS];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int V = M.num_verts;
+    const int v0 = blockIdx.x * MN_VS;
+    mano_slice_setup(M, pose, betas, trans, b, v0, P, s_vp);
+    if (tid < MN_VS && v0 + tid < V) {
+        const int v = v0 + tid;
+        float o[3];
+        mano_skin(M, P, v, s_vp[3 * tid], s_vp[3 * tid + 1], s_vp[3 * tid + 2], o, nullptr);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            verts[((long)b * V + v) * 3 + k] = (o[k] - P.centre[k]) * 1000.0f;
+    }
+    if (blockIdx.x == 0 && tid >= 64 && tid < 85) {
+        const int q = tid - 64, src = c_reorder_joints[q];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float o = (src < 16) ? P.Gt[src][k] : P.tip[src - 16][k];
+            joints[((long)b * 21 + q) * 3 + k] = (o - P.centre[k]) * 1000.0f;
+        }
     }
 }
 
-struct ManoBwdShared {
-    float gv[MN_MAXV * 3];  /* dL/d(skinned vertex), then dL/d v_posed */
-    float gAR[16][9], gAt[16][3], gGt[16][3];
-    float gpm[135];         /* dL/d pose_map */
-    float gfull[48];        /* dL/d full_pose */
-    float gJ[16][3];
-    float gcentre[3];
-    float gbetas[10];
-};
-
-__global__ void __launch_bounds__(MN_THREADS)
-hoc_mano_backward_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
-                         const float *__restrict__ trans, const float *__restrict__ g_verts,
-                         const float *__restrict__ g_joints, float *__restrict__ g_pose, float *__restrict__ g_betas,
-                         float *__restrict__ g_trans)
+/* sum over all outputs of the incoming gradient (x 1000): every output had the same centre subtracted */
+__device__ __forceinline__ void mano_grad_centre(const float *g_verts, const float *g_joints, int b, int V, float *s_red,
+                                                 float *out3)
 {
-    extern __shared__ unsigned char smem_raw[];
-    ManoShared &S = *reinterpret_cast<ManoShared *>(smem_raw);
-    ManoBwdShared &G = *reinterpret_cast<ManoBwdShared *>(smem_raw + ((sizeof(ManoShared) + 15) & ~(size_t)15));
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float a[3] = {0.f, 0.f, 0.f};
+    if (g_verts != nullptr)
+        for (int i = tid; i < V * 3; i += blockDim.x)
+            a[i % 3] += g_verts[(long)b * V * 3 + i];
+    if (g_joints != nullptr && tid < 63)
+        a[tid % 3] += g_joints[(long)b * 63 + tid];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        a[k] = hoc_warp_sum(a[k]);
+        if (lane == 0)
+            s_red[warp * 3 + k] = a[k];
+    }
+    __syncthreads();
+    if (tid < 3) {
+        float t = 0.0f;
+        for (int w = 0; w < nw; w++)
+            t += s_red[w * 3 + tid];
+        out3[tid] = -1000.0f * t;
+    }
+    __syncthreads();
+}
+
+/*
+ * Backward, kernel A.  grid (ceil(V / MN_VS), B): the vertex-parallel part for one slice of one sample -- skinning
+ * adjoint (dL/dA_j, 192 sums), dL/d v_posed = T_v^T g_v, and its products with the pose / shape blend shapes
+ * (dL/d pose_map, 135 sums; direct part of dL/d betas, 10 sums) -- reduced over the slice in the CTA and added to
+ * the sample's accumulators [MN_ACC] with one atomic per sum.
+ */
+__global__ void __launch_bounds__(MN_THREADS)
+hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
+                               const float *__restrict__ trans, const float *__restrict__ g_verts,
+                               const float *__restrict__ g_joints, float *__restrict__ acc)
+{
+    __shared__ ManoPose P;
+    __shared__ float s_vp[MN_CS], s_g[MN_CS], s_gvp[MN_CS];
+    __shared__ float s_w[MN_VS * 16];
+    __shared__ float s_red[(MN_THREADS / 32) * 3], s_gc[3];
+    const int b = blockIdx.y, tid = threadIdx.x;
     const int V = M.num_verts;
-    const int npose = 3 + M.ncomps;
-    mano_prepare(M, pose, betas, b, S);
-
-    /* B1: incoming gradients (x1000, minus-centre coupling), joints routed to transforms / tip vertices */
-    for (int i = tid; i < V * 3; i += MN_THREADS)
-        G.gv[i] = (g_verts != nullptr) ? 1000.0f * g_verts[(long)b * V * 3 + i] : 0.0f;
-    if (tid < 48) {
-        (&G.gGt[0][0])[tid] = 0.0f;
-        (&G.gJ[0][0])[tid] = 0.0f;
-    }
-    if (tid < 3)
-        G.gcentre[tid] = 0.0f;
-    __syncthreads();
-    if (tid == 0 && g_joints != nullptr) {
-        for (int q = 0; q < 21; q++) {
-            const int src = c_reorder_joints[q];
-            for (int k = 0; k < 3; k++) {
-                const float g = 1000.0f * g_joints[((long)b * 21 + q) * 3 + k];
-                if (src < 16)
-                    G.gGt[src][k] += g;
-                else
-                    G.gv[3 * M.tip_ids[src - 16] + k] += g;
-                G.gcentre[k] -= g;
-            }
-        }
-    }
-    __syncthreads();
-    {   /* dL/d centre -= sum of vertex gradients (the raw incoming ones, before the tip routing matters not:
-           every output had the same centre subtracted) */
-        float a[3] = {0.f, 0.f, 0.f};
-        if (g_verts != nullptr)
-            for (int v = tid; v < V; v += MN_THREADS)
+    const int v0 = blockIdx.x * MN_VS;
+    const int nv = min(MN_VS, V - v0);
+    mano_slice_setup(M, pose, betas, trans, b, v0, P, s_vp);
+    mano_grad_centre(g_verts, g_joints, b, V, s_red, s_gc);
+    for (int i = tid; i < MN_VS * 16; i += MN_THREADS)
+        s_w[i] = (i < nv * 16) ? M.weights[(long)v0 * 16 + i] : 0.0f;
+    /* incoming gradient of the slice's vertices: x 1000, fingertip joints routed to their vertices, centre coupling */
+    if (tid < MN_VS) {
+        float g[3] = {0.f, 0.f, 0.f};
+        if (tid < nv) {
+            const int v = v0 + tid;
+            if (g_verts != nullptr)
 #pragma unroll
                 for (int k = 0; k < 3; k++)
-                    a[k] += 1000.0f * g_verts[((long)b * V + v) * 3 + k];
+                    g[k] = 1000.0f * g_verts[((long)b * V + v) * 3 + k];
+            const int csrc = (trans == nullptr && M.center_idx >= 0) ? c_reorder_joints[M.center_idx] : -1;
+            for (int q = 0; q < 21; q++) {
+                const int src = c_reorder_joints[q];
+                if (src >= 16 && M.tip_ids[src - 16] == v && g_joints != nullptr)
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            a[k] = hoc_warp_sum(a[k]);
-            if (lane == 0 && a[k] != 0.0f)
-                atomicAdd(&G.gcentre[k], -a[k]);
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        if (trans != nullptr) {
-            if (g_trans != nullptr)
+                    for (int k = 0; k < 3; k++)
+                        g[k] += 1000.0f * g_joints[((long)b * 21 + q) * 3 + k];
+            }
+            if (csrc >= 16 && M.tip_ids[csrc - 16] == v)
 #pragma unroll
                 for (int k = 0; k < 3; k++)
-                    g_trans[(long)b * 3 + k] = -G.gcentre[k]; /* outputs = (x + trans) * 1000 */
-        } else if (M.center_idx >= 0) {
-            const int src = c_reorder_joints[M.center_idx];
+                    g[k] += s_gc[k];
+            float o[3], TR[9];
+            mano_skin(M, P, v, s_vp[3 * tid], s_vp[3 * tid + 1], s_vp[3 * tid + 2], o, TR);
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                if (src < 16)
-                    G.gGt[src][k] += G.gcentre[k];
-                else
-                    G.gv[3 * M.tip_ids[src - 16] + k] += G.gcentre[k];
-            }
+            for (int c = 0; c < 3; c++)
+                s_gvp[3 * tid + c] = TR[c] * g[0] + TR[3 + c] * g[1] + TR[6 + c] * g[2];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                s_gvp[3 * tid + c] = 0.0f;
         }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            s_g[3 * tid + k] = g[k];
     }
     __syncthreads();
-
-    /* B2: skinning adjoint.  dL/dA_j = sum_v w_vj g_v (x) [v_posed; 1]  (192 sums, one thread each) */
-    if (tid < 192) {
+    float *A = acc + (long)b * MN_ACC;
+    if (tid < 192) { /* dL/dA_j = sum_v w_vj g_v (x) [v_posed; 1] */
         const int j = tid / 12, e = tid % 12; /* e < 9: rotation entry (r, c); e >= 9: translation r */
         const int r = e < 9 ? e / 3 : e - 9, c = e < 9 ? e % 3 : -1;
         float a = 0.0f;
-        for (int v = 0; v < V; v++) {
-            const float w = M.weights[(long)v * 16 + j];
-            a += w * G.gv[3 * v + r] * (c >= 0 ? S.vs[3 * v + c] : 1.0f);
-        }
-        if (e < 9)
-            G.gAR[j][e] = a;
-        else
-            G.gAt[j][r] = a;
-    }
-    __syncthreads();
-    /* dL/d v_posed = T_v^T g_v (in place) */
-    for (int v = tid; v < V; v += MN_THREADS) {
-        float o[3], TR[9];
-        mano_skin(M, S, v, o, TR);
-        const float g0 = G.gv[3 * v], g1 = G.gv[3 * v + 1], g2 = G.gv[3 * v + 2];
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-            G.gv[3 * v + c] = TR[c] * g0 + TR[3 + c] * g1 + TR[6 + c] * g2;
-    }
-    __syncthreads();
-    /* B3a: dL/d pose_map[k] = sum_i posedirs[i][k] g_vposed[i]  (thread k, coalesced across threads) */
-    if (tid < 135) {
+        for (int v = 0; v < nv; v++)
+            a += s_w[v * 16 + j] * s_g[3 * v + r] * (c >= 0 ? s_vp[3 * v + c] : 1.0f);
+        if (a != 0.0f)
+            atomicAdd(A + tid, a);
+    } else if (tid < 192 + 10) { /* direct part of dL/d betas = shapedirs^T dL/d v_posed */
+        const int k = tid - 192;
         float a = 0.0f;
-        for (int i = 0; i < V * 3; i++)
-            a += M.posedirs[(long)i * 135 + tid] * G.gv[i];
-        G.gpm[tid] = a;
+        for (int i = 0; i < 3 * nv; i++)
+            a += M.shapedirs[((long)3 * v0 + i) * 10 + k] * s_gvp[i];
+        if (a != 0.0f)
+            atomicAdd(A + 192 + 135 + k, a);
+    }
+    if (tid < 135) { /* dL/d pose_map[k] = sum_i posedirs[i][k] dL/d v_posed[i]  (coalesced across threads) */
+        float a0 = 0.0f, a1 = 0.0f;
+        const float *pd = M.posedirs + (long)3 * v0 * 135 + tid;
+        int i = 0;
+        for (; i + 1 < 3 * nv; i += 2) {
+            a0 += __ldg(pd + (long)i * 135) * s_gvp[i];
+            a1 += __ldg(pd + (long)(i + 1) * 135) * s_gvp[i + 1];
+        }
+        if (i < 3 * nv)
+            a0 += __ldg(pd + (long)i * 135) * s_gvp[i];
+        a0 += a1;
+        if (a0 != 0.0f)
+            atomicAdd(A + 192 + tid, a0);
+    }
+}
+
+/*
+ * Backward, kernel B.  grid (B), 128 threads: the per-sample part -- forward-mode duals through Rodrigues and the
+ * kinematic chain (96 seeds: 48 pose + 48 joint coordinates, one per thread, through the SAME templated code as the
+ * forward), then the PCA / shape maps.  Objective: <gA, A> + <gGt, Gt> + <gpm, R[1:]>.
+ */
+#define MN_THREADS_B 128
+__global__ void __launch_bounds__(MN_THREADS_B)
+hoc_mano_backward_pose_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
+                              const float *__restrict__ trans, const float *__restrict__ g_verts,
+                              const float *__restrict__ g_joints, const float *__restrict__ acc,
+                              float *__restrict__ g_pose, float *__restrict__ g_betas, float *__restrict__ g_trans)
+{
+    __shared__ ManoPose P;
+    __shared__ float gAR[16][9], gAt[16][3], gGt[16][3], gpm[135], gfull[48], gJ[48];
+    __shared__ float s_red[(MN_THREADS_B / 32) * 3], s_gc[3];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int npose = 3 + M.ncomps;
+    mano_pose_setup(M, pose, betas, b, P);
+    const float *A = acc + (long)b * MN_ACC;
+    for (int i = tid; i < 192; i += MN_THREADS_B) {
+        const int j = i / 12, e = i % 12;
+        if (e < 9)
+            gAR[j][e] = A[i];
+        else
+            gAt[j][e - 9] = A[i];
+    }
+    for (int i = tid; i < 135; i += MN_THREADS_B)
+        gpm[i] = A[192 + i];
+    if (tid < 48)
+        (&gGt[0][0])[tid] = 0.0f;
+    mano_grad_centre(g_verts, g_joints, b, M.num_verts, s_red, s_gc); /* (syncs) */
+    if (tid == 0) {
+        if (g_joints != nullptr)
+            for (int q = 0; q < 21; q++) {
+                const int src = c_reorder_joints[q];
+                if (src < 16)
+                    for (int k = 0; k < 3; k++)
+                        gGt[src][k] += 1000.0f * g_joints[((long)b * 21 + q) * 3 + k];
+            }
+        if (trans != nullptr) {
+            if (g_trans != nullptr)
+                for (int k = 0; k < 3; k++)
+                    g_trans[(long)b * 3 + k] = -s_gc[k]; /* outputs = (x + trans) * 1000 */
+        } else if (M.center_idx >= 0) {
+            const int src = c_reorder_joints[M.center_idx];
+            if (src < 16)
+                for (int k = 0; k < 3; k++)
+                    gGt[src][k] += s_gc[k];
+        }
     }
     __syncthreads();
-
-    /* B4/B5: forward-mode duals through Rodrigues + kinematic chain.  Seed s < 48: full_pose[s];
-     * s >= 48: J[(s-48)/3][(s-48)%3].  Objective: <gA, A> + <gGt, Gt> + <gpm, R[1:]>. */
     if (tid < 96) {
         const int s = tid;
         const int jd = s < 48 ? s / 3 : -1;
@@ -456,96 +555,65 @@ hoc_mano_backward_kernel(hoc_mano_model M, const float *__restrict__ pose, const
             Dual aa[3];
 #pragma unroll
             for (int k = 0; k < 3; k++)
-                aa[k] = mk(S.full_pose[3 * jd + k], (3 * jd + k == s) ? 1.0f : 0.0f);
+                aa[k] = mk(P.full_pose[3 * jd + k], (3 * jd + k == s) ? 1.0f : 0.0f);
             mano_rodrigues<Dual>(aa, Rd);
         }
-        float acc = 0.0f;
+        float a = 0.0f;
         if (jd >= 1) {
 #pragma unroll
             for (int k = 0; k < 9; k++)
-                acc += G.gpm[(jd - 1) * 9 + k] * Rd[k].d;
+                a += gpm[(jd - 1) * 9 + k] * Rd[k].d;
         }
         mano_fk<Dual>([&](int j, Dual *R) {
 #pragma unroll
             for (int k = 0; k < 9; k++)
-                R[k] = (j == jd) ? Rd[k] : mk(S.R[j][k]); },
+                R[k] = (j == jd) ? Rd[k] : mk(P.R[j][k]); },
                       [&](int j, Dual *J) {
 #pragma unroll
             for (int k = 0; k < 3; k++)
-                J[k] = mk(S.J[j][k], (s >= 48 && s - 48 == 3 * j + k) ? 1.0f : 0.0f); },
+                J[k] = mk(P.J[j][k], (s >= 48 && s - 48 == 3 * j + k) ? 1.0f : 0.0f); },
                       [&](int j, const Dual *GR, const Dual *Gt) {
 #pragma unroll
             for (int k = 0; k < 9; k++)
-                acc += G.gAR[j][k] * GR[k].d;
+                a += gAR[j][k] * GR[k].d;
 #pragma unroll
             for (int r = 0; r < 3; r++) {
-                acc += G.gGt[j][r] * Gt[r].d;
+                a += gGt[j][r] * Gt[r].d;
                 /* At = Gt - GR J_j */
                 Dual at = Gt[r];
 #pragma unroll
                 for (int c = 0; c < 3; c++)
-                    at = at - GR[3 * r + c] * mk(S.J[j][c], (s >= 48 && s - 48 == 3 * j + c) ? 1.0f : 0.0f);
-                acc += G.gAt[j][r] * at.d;
+                    at = at - GR[3 * r + c] * mk(P.J[j][c], (s >= 48 && s - 48 == 3 * j + c) ? 1.0f : 0.0f);
+                a += gAt[j][r] * at.d;
             } });
         if (s < 48)
-            G.gfull[s] = acc;
+            gfull[s] = a;
         else
-            (&G.gJ[0][0])[s - 48] = acc;
+            gJ[s - 48] = a;
     }
     __syncthreads();
-
-    /* B3b: dL/d v_shaped = dL/d v_posed + J_regressor^T dL/dJ ; dL/d betas = shapedirs^T dL/d v_shaped */
-    if (g_betas != nullptr) {
-        float a[10];
-#pragma unroll
-        for (int k = 0; k < 10; k++)
-            a[k] = 0.0f;
-        for (int i = tid; i < V * 3; i += MN_THREADS) {
-            const int v = i / 3, c = i - 3 * v;
-            float g = G.gv[i];
-            for (int j = 0; j < 16; j++)
-                g += M.j_regressor[(long)j * V + v] * G.gJ[j][c];
-            const float *sd = M.shapedirs + (long)i * 10;
-#pragma unroll
-            for (int k = 0; k < 10; k++)
-                a[k] += sd[k] * g;
-        }
-        if (tid < 10)
-            G.gbetas[tid] = 0.0f;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 10; k++) {
-            a[k] = hoc_warp_sum(a[k]);
-            if (lane == 0)
-                atomicAdd(&G.gbetas[k], a[k]);
-        }
-        __syncthreads();
-        if (tid < 10)
-            g_betas[(long)b * 10 + tid] = G.gbetas[tid];
+    /* dL/d betas = direct part (kernel A) + j_shapedirs^T dL/dJ */
+    if (g_betas != nullptr && tid < 10) {
+        float a = A[192 + 135 + tid];
+        for (int e = 0; e < 48; e++)
+            a += M.j_shapedirs[e * 10 + tid] * gJ[e];
+        g_betas[(long)b * 10 + tid] = a;
     }
-    /* B6: dL/d pose */
-    if (g_pose != nullptr && tid < npose) {
+    /* dL/d pose */
+    if (g_pose != nullptr && tid >= 32 && tid < 32 + npose) {
+        const int t = tid - 32;
         float a;
-        if (tid < 3) {
-            a = G.gfull[tid];
+        if (t < 3) {
+            a = gfull[t];
         } else if (M.use_pca) {
             a = 0.0f;
-            for (int t = 0; t < 45; t++)
-                a += M.hands_components[(tid - 3) * 45 + t] * G.gfull[3 + t];
+            for (int u = 0; u < 45; u++)
+                a += M.hands_components[(t - 3) * 45 + u] * gfull[3 + u];
         } else {
-            a = G.gfull[tid];
+            a = gfull[t];
         }
-        g_pose[(long)b * npose + tid] = a;
+        g_pose[(long)b * npose + t] = a;
     }
-    (void)warp;
-}
-
-static size_t hoc_mano_smem(bool backward)
-{
-    size_t n = (sizeof(ManoShared) + 15) & ~(size_t)15;
-    if (backward)
-        n += sizeof(ManoBwdShared);
-    return n;
 }
 
 static int hoc_mano_check(const hoc_mano_model *m, int B, const char *who)
@@ -556,13 +624,14 @@ static int hoc_mano_check(const hoc_mano_model *m, int B, const char *who)
     HOC_CHECK_ARG(m->ncomps >= 1 && m->ncomps <= 45, "%s: ncomps %d outside [1, 45]", who, m->ncomps);
     HOC_CHECK_ARG(m->use_pca || m->ncomps == 45, "%s: axis-angle input needs ncomps == 45", who);
     HOC_CHECK_ARG(m->center_idx >= -1 && m->center_idx < 21, "%s: center_idx %d", who, m->center_idx);
-    HOC_CHECK_ARG(m->v_template && m->shapedirs && m->posedirs && m->j_regressor && m->weights && m->hands_mean &&
-                      (m->hands_components || !m->use_pca),
+    HOC_CHECK_ARG(m->v_template && m->shapedirs && m->posedirs && m->posedirs_t && m->j_template && m->j_shapedirs &&
+                      m->weights && m->hands_mean && (m->hands_components || !m->use_pca),
                   "%s: model tensor is NULL", who);
+    HOC_CHECK_ARG(((uintptr_t)m->weights & 15) == 0, "%s: weights must be 16-byte aligned", who);
     for (int k = 0; k < 5; k++)
         HOC_CHECK_ARG(m->tip_ids[k] >= 0 && m->tip_ids[k] < m->num_verts, "%s: tip vertex %d out of range", who,
                       m->tip_ids[k]);
-    HOC_CHECK_ARG(B >= 0 && B <= 1000000, "%s: batch %d", who, B);
+    HOC_CHECK_ARG(B >= 0 && B <= 65535, "%s: batch %d", who, B);
     return HOC_OK;
 }
 
@@ -575,17 +644,23 @@ extern "C" int hoc_mano_forward(const hoc_mano_model *model, const float *pose, 
     if (B == 0)
         return HOC_OK;
     HOC_CHECK_ARG(pose && verts && joints, "hoc_mano_forward: NULL argument");
-    const size_t smem = hoc_mano_smem(false); /* ~15 KB, under the 48 KB default limit */
+    dim3 grid((model->num_verts + MN_VS - 1) / MN_VS, B);
     HOC_LAUNCH(HOC_K_MANO_FWD, (cudaStream_t)stream,
-               (hoc_mano_forward_kernel<<<B, MN_THREADS, smem, (cudaStream_t)stream>>>(*model, pose, betas, trans, verts,
+               (hoc_mano_forward_kernel<<<grid, MN_THREADS, 0, (cudaStream_t)stream>>>(*model, pose, betas, trans, verts,
                                                                                        joints)));
     HOC_CHECK_LAUNCH("hoc_mano_forward_kernel");
     return HOC_OK;
 }
 
+extern "C" size_t hoc_mano_backward_workspace_bytes(int B)
+{
+    return B > 0 ? sizeof(float) * MN_ACC * (size_t)B : 0;
+}
+
 extern "C" int hoc_mano_backward(const hoc_mano_model *model, const float *pose, const float *betas,
                                  const float *trans, const float *grad_verts, const float *grad_joints, int B,
-                                 float *grad_pose, float *grad_betas, float *grad_trans, void *stream)
+                                 float *grad_pose, float *grad_betas, float *grad_trans, void *workspace,
+                                 size_t workspace_bytes, void *stream)
 {
     const int rc = hoc_mano_check(model, B, "hoc_mano_backward");
     if (rc != HOC_OK)
@@ -593,10 +668,26 @@ extern "C" int hoc_mano_backward(const hoc_mano_model *model, const float *pose,
     if (B == 0)
         return HOC_OK;
     HOC_CHECK_ARG(pose != nullptr, "hoc_mano_backward: pose is NULL");
-    const size_t smem = hoc_mano_smem(true); /* ~29 KB */
-    HOC_LAUNCH(HOC_K_MANO_BWD, (cudaStream_t)stream,
-               (hoc_mano_backward_kernel<<<B, MN_THREADS, smem, (cudaStream_t)stream>>>(
-                   *model, pose, betas, trans, grad_verts, grad_joints, grad_pose, grad_betas, grad_trans)));
-    HOC_CHECK_LAUNCH("hoc_mano_backward_kernel");
+    const size_t need = hoc_mano_backward_workspace_bytes(B);
+    if (workspace == nullptr || workspace_bytes < need) {
+        hoc_set_error("hoc_mano_backward: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+        return HOC_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) {
+        hoc_set_error("hoc_mano_backward: memset failed");
+        return HOC_ERR_CUDA;
+    }
+    float *acc = (float *)workspace;
+    dim3 grid((model->num_verts + MN_VS - 1) / MN_VS, B);
+    HOC_LAUNCH(HOC_K_MANO_BWD, st,
+               (hoc_mano_backward_verts_kernel<<<grid, MN_THREADS, 0, st>>>(*model, pose, betas, trans, grad_verts,
+                                                                            grad_joints, acc)));
+    HOC_CHECK_LAUNCH("hoc_mano_backward_verts_kernel");
+    HOC_LAUNCH(HOC_K_MANO_BWD, st,
+               (hoc_mano_backward_pose_kernel<<<B, MN_THREADS_B, 0, st>>>(*model, pose, betas, trans, grad_verts,
+                                                                          grad_joints, acc, grad_pose, grad_betas,
+                                                                          grad_trans)));
+    HOC_CHECK_LAUNCH("hoc_mano_backward_pose_kernel");
     return HOC_OK;
 }

@@ -76,9 +76,11 @@ class _ManoFunction(Function):
             gp = torch.empty_like(p) if ctx.needs_input_grad[0] else None
             gb = torch.empty_like(b) if (b is not None and ctx.needs_input_grad[1]) else None
             gt = torch.empty_like(t) if (t is not None and ctx.needs_input_grad[2]) else None
+            ws_bytes = L.hoc_mano_backward_workspace_bytes(B)
+            ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
             _lib.check(L.hoc_mano_backward(ctypes.byref(st), _lib.ptr(p), _lib.ptr(b), _lib.ptr(t), _lib.ptr(g_verts),
                                            _lib.ptr(g_joints), B, _lib.ptr(gp), _lib.ptr(gb), _lib.ptr(gt),
-                                           _lib.stream_ptr()), "hoc_mano_backward")
+                                           _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "hoc_mano_backward")
         return gp, gb, gt, None
 
 
@@ -102,6 +104,12 @@ class ManoLayer(torch.nn.Module):
         self.register_buffer("th_posedirs", t(model["posedirs"]))
         self.register_buffer("th_J_regressor", t(model["j_regressor"]))
         self.register_buffer("th_weights", t(model["weights"]))
+        # constants derived once per model for the kernels (include/hoc_b200.h, hoc_mano_model): transposed pose blend
+        # shapes, and the joint regression folded through the template / the shape blend shapes
+        self.register_buffer("th_posedirs_t", self.th_posedirs.reshape(-1, 135).t().contiguous())
+        self.register_buffer("th_J_template", (self.th_J_regressor @ self.th_v_template).contiguous())
+        self.register_buffer("th_J_shapedirs",
+                             torch.einsum("jv,vck->jck", self.th_J_regressor, self.th_shapedirs).contiguous())
         comps = t(model["hands_components"])
         self.register_buffer("th_comps", comps)
         self.register_buffer("th_selected_comps", comps[: self.ncomps].contiguous())
@@ -123,6 +131,9 @@ class ManoLayer(torch.nn.Module):
         st.shapedirs = self.th_shapedirs.data_ptr()
         st.posedirs = self.th_posedirs.data_ptr()
         st.j_regressor = self.th_J_regressor.data_ptr()
+        st.posedirs_t = self.th_posedirs_t.data_ptr()
+        st.j_template = self.th_J_template.data_ptr()
+        st.j_shapedirs = self.th_J_shapedirs.data_ptr()
         st.weights = self.th_weights.data_ptr()
         st.hands_components = self.th_selected_comps.data_ptr()
         st.hands_mean = self.th_hands_mean.data_ptr()

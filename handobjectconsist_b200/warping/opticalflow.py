@@ -143,6 +143,13 @@ class _FlowFinalizeFunction(Function):
         dev = mult1.device
         outs = []
         with torch.cuda.device(dev):
+            if g12 is not None and g21 is not None and ctx.needs_input_grad[0] and ctx.needs_input_grad[3]:
+                grad_rgb = torch.empty((2, B, 3, S, S), dtype=torch.float32, device=dev)  # both directions, one launch
+                _lib.check(L.hoc_flow_finalize_backward_pair(_lib.ptr(g12.contiguous().float()), _lib.ptr(mult1),
+                                                             _lib.ptr(g21.contiguous().float()), _lib.ptr(mult2), B, S, H,
+                                                             W, _lib.ptr(grad_rgb[0]), _lib.ptr(grad_rgb[1]),
+                                                             _lib.stream_ptr()), "hoc_flow_finalize_backward_pair")
+                return grad_rgb[0], None, None, grad_rgb[1], None, None, None, None, None
             for g, mult, need in ((g12, mult1, ctx.needs_input_grad[0]), (g21, mult2, ctx.needs_input_grad[3])):
                 if g is None or not need:
                     outs.append(None)

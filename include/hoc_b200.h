@@ -250,6 +250,10 @@ int hoc_flow_finalize(const float *rgb1, const float *alpha1, const int32_t *idx
 /* grad_flow [B,H,W,2], mult [B,H,W] -> grad_rgb [B,3,S,S] (fully overwritten; zero outside the crop). */
 int hoc_flow_finalize_backward(const float *grad_flow, const float *mult, int B, int S, int H, int W,
                                float *grad_rgb, void *stream);
+/* Both directions of a pair in one launch. */
+int hoc_flow_finalize_backward_pair(const float *grad_flow12, const float *mult1, const float *grad_flow21,
+                                    const float *mult2, int B, int S, int H, int W, float *grad_rgb1, float *grad_rgb2,
+                                    void *stream);
 
 /* Per-vertex front end of get_opticalflow for one frame pair: batch_proj2d of both frames, the displacement
  * attributes [dx, dy, 1] of both directions (opticalflow.py:98-102,121-122) and nr.projection of both meshes
@@ -276,12 +280,20 @@ int hoc_flow_vertices_backward(const float *verts1, const float *verts2, const f
  * used; ignored when use_pca == 0), hands_mean [45] (zeros for flat_hand_mean).
  *   pose  [B,3+ncomps] (use_pca) or [B,48] (axis-angle, ncomps = 45); betas [B,10] or NULL (zeros);
  *   trans [B,3] or NULL (then the outputs are centred on reordered joint `center_idx`, -1 = no centring);
- *   verts [B,V,3], joints [B,21,3] out, millimetres and joint order of manopth. */
+ *   verts [B,V,3], joints [B,21,3] out, millimetres and joint order of manopth.
+ * weights [V,16] must be 16-byte aligned. */
 typedef struct hoc_mano_model {
-    const float *v_template;
-    const float *shapedirs;
-    const float *posedirs;
-    const float *j_regressor;
+    const float *v_template;  /* [V,3] */
+    const float *shapedirs;   /* [V,3,10] */
+    const float *posedirs;    /* [V,3,135] */
+    const float *j_regressor; /* [16,V] (kept for reference; the kernels use the two folded constants below) */
+    /* derived constants, computed once per model by the caller:
+     *   posedirs_t  [135][3V]    = posedirs transposed (coalesced per-coordinate reads)
+     *   j_template  [16][3]      = j_regressor . v_template
+     *   j_shapedirs [16][3][10]  = j_regressor . shapedirs   (J = j_template + j_shapedirs . betas) */
+    const float *posedirs_t;
+    const float *j_template;
+    const float *j_shapedirs;
     const float *weights;
     const float *hands_components;
     const float *hands_mean;
@@ -295,10 +307,12 @@ typedef struct hoc_mano_model {
 int hoc_mano_forward(const hoc_mano_model *model, const float *pose, const float *betas, const float *trans, int B,
                      float *verts, float *joints, void *stream);
 /* grad_verts [B,V,3] / grad_joints [B,21,3] (either may be NULL) -> grad_pose [B,3+ncomps], grad_betas [B,10],
- * grad_trans [B,3] (any may be NULL; fully overwritten). */
+ * grad_trans [B,3] (any may be NULL; fully overwritten).  workspace: hoc_mano_backward_workspace_bytes(B) bytes
+ * (per-sample accumulators of the vertex-parallel pass). */
+size_t hoc_mano_backward_workspace_bytes(int B);
 int hoc_mano_backward(const hoc_mano_model *model, const float *pose, const float *betas, const float *trans,
                       const float *grad_verts, const float *grad_joints, int B, float *grad_pose, float *grad_betas,
-                      float *grad_trans, void *stream);
+                      float *grad_trans, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }
