@@ -185,7 +185,7 @@ def run_native(args, rank, world, local_rank):
 
     if args.eager_only:
         if rank == 0:
-            print(json.dumps({"eager_ms_per_step": eager_ms / args.steps}), flush=True)
+            _emit({"eager_ms_per_step": eager_ms / args.steps})
         return None
 
     # ---- graphed arm, inputs resident in HBM: the headline `value` ----
@@ -535,6 +535,25 @@ def run_reference(args, rank):
     }
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries ONE JSON line: keep a private handle on the real stdout and point file descriptor 1 at stderr,
+    so that nothing a library prints (NCCL's version banner, warnings) can land next to the result."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -547,6 +566,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS, help="frame pairs per rank and step (default: configs[2])")
     ap.add_argument("--size", type=int, default=SIZE, help="raster / image side (default: configs[2])")
     args = ap.parse_args()
+    _claim_stdout()
     globals()["PAIRS"], globals()["SIZE"] = args.pairs, args.size
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -555,7 +575,7 @@ def main():
     if args.impl == "reference":
         out = run_reference(args, rank)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            _emit(out)
         return
 
     import torch.distributed as dist
@@ -563,9 +583,6 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        # stdout carries ONE JSON line: NCCL's banner / debug output (printed to stdout from NCCL_DEBUG=VERSION up) goes
-        # to stderr instead
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -585,7 +602,7 @@ def main():
                 out["mano"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out), flush=True)
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 

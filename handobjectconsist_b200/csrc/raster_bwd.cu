@@ -514,143 +514,87 @@ hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__rest
 }
 
 /*
- * Line pass.  grid (B, 2, ceil(S / G)): one CTA per group of G adjacent image columns (axis 0) or rows (axis 1),
- * sample fastest and line groups ordered from the image centre outwards.  G = 1 is the measured optimum on B200
- * (more lines per CTA lengthen the CTA's dependent chain -- ext -> queue -> face -> scan -- which is what bounds
- * this pass; a persistent grid and splitting a line's scans over several CTAs were measured too and lost);
- * HOC_TUNE_LINE_GROUP / _THREADS / _SEGMENT keep the sweep reproducible.
+ * Line pass.  grid (B, 2, S): one CTA per image column (axis 0) or row (axis 1) of one sample, sample fastest and
+ * lines ordered from the image centre outwards: the lines that carry the most scans (meshes are centred by the crop)
+ * are dispatched first, the empty border lines last.  One line per CTA is the measured optimum on B200: several
+ * lines per CTA lengthen the CTA's dependent chain (count -> queue record -> face_index_map -> face -> scan), which is
+ * what bounds this pass; a persistent grid walking the lines and splitting a line's scans over several CTAs were
+ * measured too and lost.
  */
 #define LN_THREADS 256
-#define LN_WARPS (LN_THREADS / 32)
-template <int G, int CH>
+template <int CH>
 __global__ void __launch_bounds__(LN_THREADS)
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
-                           const float *__restrict__ g_alpha, int B, int F, int S, float eps, int layout,
-                           int use_alpha, const int *__restrict__ ext, const int *__restrict__ line_count,
+                           const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
+                           const int *__restrict__ ext, const int *__restrict__ line_count,
                            const unsigned short *__restrict__ emitters, float *__restrict__ grad_faces)
 {
-    /* dynamic shared memory: float4 s_line4[G][S]
+    /* dynamic shared memory: float4 s_line4[S + 16]
      * per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (the inside pixel of a scan
      * is covered, its alpha is 1): delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_rgb Iin_ch g_ch -- one 16-byte
      * shared load and three FMAs per scanned pixel (<= 1 ulp of |P| from the reference's summation order,
      * gradients carry 1e-3) */
     extern __shared__ float4 s_line4[];
-    __shared__ int s_lo[G], s_hi[G], s_n[G + 1];
-    /* grid (B, 2, groups): sample fastest, line groups ordered from the image centre outwards: the lines that
-     * carry the most scans (meshes are centred by the crop) are dispatched first, the empty border lines last */
-    const int ngroups = gridDim.z;
     const int b = blockIdx.x, axis = blockIdx.y, k = blockIdx.z;
-    const int grp = (ngroups >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1)); /* c, c-1, c+1, c-2, ...: a bijection */
-    const int d0_base = grp * G;
+    const int d0 = (S >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1)); /* c, c-1, c+1, c-2, ...: a bijection of [0, S) */
+    const long line = ((long)b * 2 + axis) * S + d0;
+    /* a line without scans or without incoming gradient: leave before anything else is computed */
+    const int n = min(line_count[line], 3 * S);
+    if (n == 0)
+        return;
+    const int *e = ext + (long)b * 4 * S;
+    const int lo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
+    const int hi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0] - 1;
+    if (lo > hi)
+        return; /* no incoming gradient anywhere on this line: every outward scan sums zeros */
+    const int len = hi - lo + 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
-    const int *e = ext + (long)b * 4 * S;
-    const int *lc = line_count + ((long)b * 2 + axis) * S;
-    int ulo, uhi, n;
-    if (G == 1) { /* a line without scans or without incoming gradient: leave before anything else is computed */
-        n = min(lc[d0_base], 3 * S);
-        if (n == 0)
-            return;
-        ulo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_base];
-        uhi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_base] - 1;
-        if (ulo > uhi)
-            return;
-        if (tid == 0) {
-            s_lo[0] = ulo;
-            s_hi[0] = uhi;
-            s_n[0] = 0;
-            s_n[1] = n;
-        }
-        __syncthreads();
-    } else {
-        if (tid == 0) {
-            int run = 0;
-            for (int l = 0; l < G; l++) {
-                const int d0 = d0_base + l;
-                int lo = 0x7f7f7f7f, hi = -1, cnt = 0;
-                if (d0 < S) {
-                    lo = S - ((axis == 0) ? e[EXT_COL_LO * S + d0] : e[EXT_ROW_LO * S + d0]);
-                    hi = ((axis == 0) ? e[EXT_COL_HI * S + d0] : e[EXT_ROW_HI * S + d0]) - 1;
-                    cnt = (lo <= hi) ? min(lc[d0], 3 * S) : 0;
-                }
-                s_lo[l] = lo;
-                s_hi[l] = hi;
-                s_n[l] = run; /* exclusive prefix of the queue lengths */
-                run += cnt;
-            }
-            s_n[G] = run;
-        }
-        __syncthreads();
-        n = s_n[G];
-        if (n == 0)
-            return; /* no scans, or no incoming gradient anywhere on these lines */
-        ulo = 0x7f7f7f7f;
-        uhi = -1;
-#pragma unroll
-        for (int l = 0; l < G; l++) {
-            if (s_n[l + 1] > s_n[l]) {
-                ulo = min(ulo, s_lo[l]);
-                uhi = max(uhi, s_hi[l]);
-            }
-        }
-    }
-    const int ulen = uhi - ulo + 1;
-    const unsigned short *queue = emitters + (((long)b * 2 + axis) * S + d0_base) * 3 * S;
-
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
+    const unsigned short *queue = emitters + line * 3 * S;
     const int32_t *idx = face_index_map + (long)b * S * S;
 
-    /* 2. stage the union of the spans of the G lines (zero gradient outside a line's own span) */
-    for (int t = tid; t < G * ulen; t += T) {
-        /* consecutive threads read consecutive x: along the line for rows, across the lines for columns */
-        const int l = (axis == 0) ? t % G : t / ulen;
-        const int i = (axis == 0) ? t / G : t % ulen;
-        const int d0 = d0_base + l, d1 = ulo + i;
+    /* 1. stage the span of non-zero gradient */
+    for (int i = tid; i < len; i += T) {
+        const int d1 = lo + i;
+        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
         float4 pg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (d0 < S) {
-            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-            if (has_rgb) {
-                const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
-                           o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
-                pg.y = g_rgb[o0];
-                pg.z = g_rgb[o1];
-                pg.w = g_rgb[o2];
-                pg.x = rgb[o0] * pg.y + rgb[o1] * pg.z + rgb[o2] * pg.w;
-            }
-            if (has_alpha) {
-                const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
-                const float a = (idx[(long)yi * S + xi] >= 0) ? 1.0f : 0.0f;
-                pg.x += a * ga - ga;
-            }
+        if (has_rgb) {
+            const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
+                       o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
+            pg.y = g_rgb[o0];
+            pg.z = g_rgb[o1];
+            pg.w = g_rgb[o2];
+            pg.x = rgb[o0] * pg.y + rgb[o1] * pg.z + rgb[o2] * pg.w;
         }
-        s_line4[l * S + i] = pg;
+        if (has_alpha) {
+            const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+            const float a = (idx[(long)yi * S + xi] >= 0) ? 1.0f : 0.0f;
+            pg.x += a * ga - ga;
+        }
+        s_line4[i] = pg;
     }
     __syncthreads();
 
-    /* 3. the scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane sets up
-     *    one scan (edge geometry, colour of the inside pixel, range) in registers; (b) the warp's scans are cut
-     *    into chunks of CH pixels and every lane sums one chunk -- it finds its scan with a 5-step search over the
-     *    warp's prefix sums and fetches the scan's constants with shuffles -- so that the lanes finish together
-     *    however different the scan lengths are.  The chunk loop is fully unrolled and branch-free: a pixel beyond
-     *    the end of the scan, or with delta <= 0, adds 0 * (1 / dist).  Each chunk adds its two vertex
-     *    contributions to grad_faces. */
+    /* 2. the scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane sets up one
+     *    scan (edge geometry, colour of the inside pixel, range) in registers; (b) the warp's scans are cut into
+     *    chunks of CH pixels and every lane sums one chunk -- it finds its scan with a 5-step search over the warp's
+     *    prefix sums and fetches the scan's constants with shuffles -- so that the lanes finish together however
+     *    different the scan lengths are.  The chunk loop is fully unrolled and branch-free: a pixel beyond the end
+     *    of the scan, or with delta <= 0, adds 0 * (1 / dist); 1 / dist is one MUFU.RCP (2 ulp: the pseudo-gradient
+     *    carries a 1e-3 tolerance and this quotient is the hot instruction of the pass).  Each chunk adds its two
+     *    vertex contributions to grad_faces. */
     const float scale = 2.0f / (float)S;
     const float peps = eps, neps = -eps;
     for (int q0 = wid * 32; q0 < n; q0 += T) {
         const int q = q0 + lane;
         float r_cA = 0.0f, r_cB = 0.0f, r_cross = 0.0f, r_I1 = 0.0f, r_I2 = 0.0f, r_I3 = 0.0f;
-        int r_from = 0, r_to = -1, r_row = 0, r_gfA = 0, r_gfB = 0, nchunk = 0;
+        int r_from = 0, r_to = -1, r_gfA = 0, r_gfB = 0, nchunk = 0;
         if (q < n) {
-            int l = 0;
-#pragma unroll
-            for (int j = 1; j < G; j++)
-                l += (q >= s_n[j]) ? 1 : 0;
-            const int rec = queue[(long)l * 3 * S + (q - s_n[l])];
+            const int rec = queue[q];
             const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3;
-            const int d0 = d0_base + l;
-            const int lo = s_lo[l], hi = s_hi[l];
             const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
             const int fi = idx[(long)yin * S + xin];
             if (has_rgb) { /* rgb of the inside pixel (its alpha is 1: folded into P) */
@@ -675,7 +619,6 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                     /* a vertex that gets no contribution: infinite distance -> 1 / dist = 0 (d1 - cross != 0) */
                     r_cA = C.hasA ? C.cA * scale : __int_as_float(0x7f800000);
                     r_cB = C.hasB ? C.cB * scale : __int_as_float(0x7f800000);
-                    r_row = l * S - ulo;
                     const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
                     r_gfA = gbase + ia * 3;
                     r_gfB = gbase + ib * 3;
@@ -703,23 +646,24 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 if (a + st < 32 && pv <= j)
                     a += st;
             }
+            /* (every shuffle stays outside any lane-dependent branch: a predicated shuffle desynchronises the warp) */
             const int c0 = (j - __shfl_sync(HOC_FULL_MASK, pre, a)) * CH;
             const int d1_from = __shfl_sync(HOC_FULL_MASK, r_from, a) + c0;
-            const int to_a = __shfl_sync(HOC_FULL_MASK, r_to, a); /* (every shuffle outside any lane-dependent branch) */
-            const int left = live ? to_a - d1_from : -1;          /* pixels beyond the first */
+            const int to_a = __shfl_sync(HOC_FULL_MASK, r_to, a);
+            const int left = live ? to_a - d1_from : -1; /* pixels beyond the first */
             const float cA = __shfl_sync(HOC_FULL_MASK, r_cA, a), cB = __shfl_sync(HOC_FULL_MASK, r_cB, a);
             const float I1 = __shfl_sync(HOC_FULL_MASK, r_I1, a), I2 = __shfl_sync(HOC_FULL_MASK, r_I2, a),
                         I3 = __shfl_sync(HOC_FULL_MASK, r_I3, a);
             const float u0 = (float)d1_from - __shfl_sync(HOC_FULL_MASK, r_cross, a);
-            const float4 *sp = s_line4 + (__shfl_sync(HOC_FULL_MASK, r_row, a) + d1_from);
             const int gfA = __shfl_sync(HOC_FULL_MASK, r_gfA, a), gfB = __shfl_sync(HOC_FULL_MASK, r_gfB, a);
+            const float4 *sp = s_line4 + (d1_from - lo);
             float gA = 0.0f, gB = 0.0f;
 #pragma unroll
-            for (int k = 0; k < CH; k++) {
-                const float4 pg = sp[k]; /* at most CH - 1 entries past the staged span: the buffer is padded */
+            for (int kk = 0; kk < CH; kk++) {
+                const float4 pg = sp[kk]; /* at most CH - 1 entries past the staged span: the buffer is padded */
                 float delta = pg.x - __fmaf_rn(I3, pg.w, __fmaf_rn(I2, pg.z, I1 * pg.y));
-                delta = (delta <= 0.0f || k > left) ? 0.0f : delta;
-                const float u = u0 + (float)k;
+                delta = (delta <= 0.0f || kk > left) ? 0.0f : delta;
+                const float u = u0 + (float)kk;
                 float dA = cA * u, dB = cB * u;
                 dA += (0.0f < dA) ? peps : neps;
                 dB += (0.0f < dB) ? peps : neps;
@@ -734,19 +678,15 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     }
 }
 
-/* Tuning knobs of the line pass (hoc_set_tuning): lines per CTA (0 = by image size), threads per CTA, segment
- * length in pixels. */
-static int g_line_G = 0, g_line_threads = 128, g_line_seg = 16;
+/* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
+static int g_line_threads = 128, g_line_seg = 16;
 
 extern "C" int hoc_set_tuning(int key, int value)
 {
-    if (key == HOC_TUNE_LINE_GROUP && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8))
-        g_line_G = value;
-    else if (key == HOC_TUNE_LINE_THREADS && value >= 32 && value <= LN_THREADS && value % 32 == 0)
+    if (key == HOC_TUNE_LINE_THREADS && value >= 32 && value <= LN_THREADS && value % 32 == 0)
         g_line_threads = value;
-    else if (key == HOC_TUNE_LINE_SEGMENT && value >= 1 && value <= 4096)
+    else if (key == HOC_TUNE_LINE_SEGMENT && (value == 8 || value == 16))
         g_line_seg = value;
-
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -754,25 +694,17 @@ extern "C" int hoc_set_tuning(int key, int value)
     return HOC_OK;
 }
 
-template <int G, int CH>
+template <int CH>
 static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index_map, const float *rgb,
                                    const float *grad_rgb, const float *g_alpha, int B, int F, int S, float eps,
                                    int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
                                    cudaStream_t st)
 {
-    static size_t smem_allowed = 48 * 1024;
-    const size_t smem = ((size_t)G * S + 16) * sizeof(float4); /* + padding for the unrolled chunk loop */
-    if (smem > smem_allowed) {
-        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<G, CH>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess)
-            return e;
-        smem_allowed = smem;
-    }
-    dim3 grid(B, 2, (S + G - 1) / G);
+    const size_t smem = ((size_t)S + 16) * sizeof(float4); /* + padding for the unrolled chunk loop; <= 33 KB */
+    dim3 grid(B, 2, S);
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_raster_bwd_line_kernel<G, CH><<<grid, g_line_threads, smem, st>>>(
-                   faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w.ext, w.line_count,
+               (hoc_raster_bwd_line_kernel<CH><<<grid, g_line_threads, smem, st>>>(
+                   faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,
                    w.emitters, grad_faces)));
     return cudaSuccess;
 }
@@ -878,18 +810,14 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
     }
     if (k4) {
-        /* lines per CTA: bounded by the staging buffer (16 bytes per pixel of a line) */
-        int G = g_line_G ? g_line_G : 1;
-        while (G > 1 && (size_t)G * S * 16 > 96 * 1024)
-            G >>= 1;
-#define HOC_LINE(G_, C_) hoc_launch_line<G_, C_>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w, grad_faces, st)
         if (g_line_seg >= 16)
-            e = (G == 8) ? HOC_LINE(8, 16) : (G == 4) ? HOC_LINE(4, 16) : (G == 2) ? HOC_LINE(2, 16) : HOC_LINE(1, 16);
+            e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w,
+                                    grad_faces, st);
         else
-            e = (G == 8) ? HOC_LINE(8, 8) : (G == 4) ? HOC_LINE(4, 8) : (G == 2) ? HOC_LINE(2, 8) : HOC_LINE(1, 8);
-#undef HOC_LINE
+            e = hoc_launch_line<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w,
+                                   grad_faces, st);
         if (e != cudaSuccess) {
-            hoc_set_error("hoc_raster_backward: cannot reserve shared memory for the line pass: %s",
+            hoc_set_error("hoc_raster_backward: line pass: %s",
                           cudaGetErrorString(e));
             return HOC_ERR_CUDA;
         }

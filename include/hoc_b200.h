@@ -83,10 +83,8 @@ const char *hoc_last_error(void);
 #define HOC_KERNEL_COUNT 24
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
- *   HOC_TUNE_LINE_GROUP    image lines per CTA of the rasterizer backward's line pass (0 = default, 1/2/4/8)
- *   HOC_TUNE_LINE_THREADS  threads per CTA of that pass (multiple of 32, <= 256)
- *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan */
-#define HOC_TUNE_LINE_GROUP 0
+ *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
+ *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan (8 or 16) */
 #define HOC_TUNE_LINE_THREADS 1
 #define HOC_TUNE_LINE_SEGMENT 2
 int hoc_set_tuning(int key, int value);
