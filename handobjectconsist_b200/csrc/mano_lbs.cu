@@ -14,7 +14,7 @@
  * chain: a few hundred flops) and produces its slice -- the joint regression is folded into two model constants
  * (J = j_template + j_shapedirs . betas), so no CTA needs the whole shaped mesh, and the pose blend shapes are read
  * through a transposed copy, coalesced.  (One CTA per sample, the first version, left 116 of 148 SMs idle at B = 32
- * and took 265 us.)  The backward is two launches: the vertex-parallel part per (slice, sample) -- the big linear maps
+ * and took 265 us; this one 20 us.)  The backward is two launches: the vertex-parallel part per (slice, sample) -- the big linear maps
  * (posedirs, shapedirs, skinning weights) reversed by hand, reduced in the CTA and added to per-sample accumulators --
  * and a small per-sample kernel that differentiates the 16-joint kinematic chain and the Rodrigues formula with
  * forward-mode dual numbers (96 seeds: 48 pose + 48 joint coordinates, one per thread) through the SAME templated
@@ -242,29 +242,18 @@ __device__ __forceinline__ float mano_vposed_coord(const hoc_mano_model &M, cons
         a += sd[k] * P.betas[k];
     const float *pt = M.posedirs_t + i;
     float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 5
-    for (int k = 0; k < 135; k += 5) {
+    /* 9 batches of 15 independent loads (the reads hit L2: latency, not bandwidth, is what this loop waits for) */
+#pragma unroll 1
+    for (int k = 0; k < 135; k += 15) {
+        float v[15];
 #pragma unroll
-        for (int u = 0; u < 5; u++)
-            acc[u] += __ldg(pt + (long)(k + u) * n) * P.pose_map[k + u];
+        for (int u = 0; u < 15; u++)
+            v[u] = __ldg(pt + (long)(k + u) * n);
+#pragma unroll
+        for (int u = 0; u < 15; u++)
+            acc[u % 5] += v[u] * P.pose_map[k + u];
     }
     return a + ((acc[0] + acc[1]) + (acc[2] + acc[3]) + acc[4]);
-}
-
-/* the same for one coordinate by a whole warp (lanes over the 135 pose-map entries) */
-__device__ __forceinline__ float mano_vposed_coord_warp(const hoc_mano_model &M, const ManoPose &P, int i, int lane)
-{
-    const float *pd = M.posedirs + (long)i * 135;
-    float a = 0.0f;
-    for (int k = lane; k < 135; k += 32)
-        a += pd[k] * P.pose_map[k];
-    a = hoc_warp_sum(a);
-    float base = M.v_template[i];
-    const float *sd = M.shapedirs + (long)i * 10;
-#pragma unroll
-    for (int k = 0; k < 10; k++)
-        base += sd[k] * P.betas[k];
-    return base + a;
 }
 
 /* blended transform of vertex v applied to its posed rest position (x, y, z) */
@@ -302,12 +291,12 @@ __device__ __forceinline__ void mano_skin(const hoc_mano_model &M, const ManoPos
 }
 
 /* Steps shared by the forward and the first backward kernel: pose set-up, then -- concurrently -- forward kinematics
- * (thread 0), the slice's posed rest positions (threads 32 .. 32 + MN_CS) and the fingertips' (warp 7); then the
- * skinned fingertips and the centre. */
+ * (thread 0), the slice's posed rest positions (threads 32 .. 32 + MN_CS) and the fingertips' (15 threads of warp 7);
+ * then the skinned fingertips and the centre. */
 __device__ __forceinline__ void mano_slice_setup(const hoc_mano_model &M, const float *pose, const float *betas,
                                                  const float *trans, int b, int v0, ManoPose &P, float *s_vp)
 {
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int V = M.num_verts;
     mano_pose_setup(M, pose, betas, b, P);
     if (tid == 0)
@@ -316,12 +305,9 @@ __device__ __forceinline__ void mano_slice_setup(const hoc_mano_model &M, const 
         const int il = tid - 32, i = 3 * v0 + il;
         s_vp[il] = (i < 3 * V) ? mano_vposed_coord(M, P, i) : 0.0f;
     }
-    if (tid >= 224) {
-        for (int e = 0; e < 15; e++) {
-            const float a = mano_vposed_coord_warp(M, P, 3 * M.tip_ids[e / 3] + e % 3, lane);
-            if (lane == 0)
-                P.tipvp[e / 3][e % 3] = a;
-        }
+    if (tid >= 224 && tid < 224 + 15) { /* the fingertips' 15 coordinates, like any other coordinate */
+        const int e = tid - 224;
+        P.tipvp[e / 3][e % 3] = mano_vposed_coord(M, P, 3 * M.tip_ids[e / 3] + e % 3);
     }
     __syncthreads();
     if (tid < 5)
@@ -474,23 +460,46 @@ hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose,
             atomicAdd(A + tid, a);
     } else if (tid < 192 + 10) { /* direct part of dL/d betas = shapedirs^T dL/d v_posed */
         const int k = tid - 192;
-        float a = 0.0f;
-        for (int i = 0; i < 3 * nv; i++)
-            a += M.shapedirs[((long)3 * v0 + i) * 10 + k] * s_gvp[i];
+        float a = 0.0f, a2 = 0.0f;
+        const float *sd = M.shapedirs + (long)3 * v0 * 10 + k;
+        int i = 0;
+        for (; i + 7 < 3 * nv; i += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                v[u] = __ldg(sd + (long)(i + u) * 10);
+#pragma unroll
+            for (int u = 0; u < 8; u += 2) {
+                a += v[u] * s_gvp[i + u];
+                a2 += v[u + 1] * s_gvp[i + u + 1];
+            }
+        }
+        for (; i < 3 * nv; i++)
+            a += __ldg(sd + (long)i * 10) * s_gvp[i];
+        a += a2;
         if (a != 0.0f)
             atomicAdd(A + 192 + 135 + k, a);
     }
     if (tid < 135) { /* dL/d pose_map[k] = sum_i posedirs[i][k] dL/d v_posed[i]  (coalesced across threads) */
-        float a0 = 0.0f, a1 = 0.0f;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
         const float *pd = M.posedirs + (long)3 * v0 * 135 + tid;
         int i = 0;
-        for (; i + 1 < 3 * nv; i += 2) {
-            a0 += __ldg(pd + (long)i * 135) * s_gvp[i];
-            a1 += __ldg(pd + (long)(i + 1) * 135) * s_gvp[i + 1];
+        for (; i + 11 < 3 * nv; i += 12) { /* 12 independent loads per batch (L2 latency bound) */
+            float v[12];
+#pragma unroll
+            for (int u = 0; u < 12; u++)
+                v[u] = __ldg(pd + (long)(i + u) * 135);
+#pragma unroll
+            for (int u = 0; u < 12; u += 4) {
+                a0 += v[u] * s_gvp[i + u];
+                a1 += v[u + 1] * s_gvp[i + u + 1];
+                a2 += v[u + 2] * s_gvp[i + u + 2];
+                a3 += v[u + 3] * s_gvp[i + u + 3];
+            }
         }
-        if (i < 3 * nv)
+        for (; i < 3 * nv; i++)
             a0 += __ldg(pd + (long)i * 135) * s_gvp[i];
-        a0 += a1;
+        a0 = (a0 + a1) + (a2 + a3);
         if (a0 != 0.0f)
             atomicAdd(A + 192 + tid, a0);
     }
