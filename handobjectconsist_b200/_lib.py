@@ -42,6 +42,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_set_tuning": (_i, [_i, _i]),
+    "hoc_unpack_u8": (_i, [_vp, _vp, ctypes.c_longlong, _f, _f, _vp]),
     "hoc_flow_finalize_backward_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hoc_mesh_gather_clear": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "hoc_pair_loss": (_i, [_vp, _vp, _i, _vp, _vp]),
@@ -70,7 +71,7 @@ SIGNATURES = {
 KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_backward": 3, "warp_photo_fwd": 4,
               "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8, "mesh_gather": 9, "mesh_scatter": 10,
               "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16, "mano_fwd": 17,
-              "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22}
+              "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22, "unpack_u8": 23}
 
 
 

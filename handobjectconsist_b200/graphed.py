@@ -33,8 +33,17 @@ class GraphedConsistStep:
         self.kw = dict(gt_refs=gt_refs, first_only=first_only, hand_ignore_faces=hand_ignore_faces,
                        use_backward=use_backward, detach_renders=detach_renders)
         self.hand_face = hand_face.to(dev)
+        self._u8_stage = {}
         # static inputs
-        self.samples = [{k: v.to(dev).clone() if torch.is_tensor(v) else v for k, v in s.items()} for s in samples]
+        def static(k, v):
+            if not torch.is_tensor(v):
+                return v
+            if v.dtype == torch.uint8 and _name(k) in ("IMAGE", "JITTERMASK"):  # uint8 frames: see _load_u8
+                f = v.to(dev).float().div(255.0)
+                return f - 0.5 if _name(k) == "IMAGE" else f
+            return v.to(dev).clone()
+
+        self.samples = [{k: static(k, v) for k, v in s.items()} for s in samples]
         self.results = [{k: v.detach().to(dev).clone() for k, v in r.items() if torch.is_tensor(v)}
                         for r in all_results]
         self.hand = self.results[0]["recov_handverts3d"].requires_grad_(True)
@@ -68,14 +77,33 @@ class GraphedConsistStep:
             go = torch.zeros_like(self.obj)
         return loss.detach(), gh, go
 
+    def _load_u8(self, buf, src, name):
+        """uint8 frame / jitter mask -> the static fp32 buffer: the bytes cross PCIe as uint8 (a quarter of fp32) and
+        are widened on the device with the two operations of the reference's `to_tensor` + `normalize`
+        (handobjset.py:368-379): x / 255 - 0.5 for IMAGE, x / 255 for JITTERMASK."""
+        from . import _lib
+        key = id(buf)
+        stage = self._u8_stage.get(key)
+        if stage is None or stage.shape != src.shape:
+            stage = self._u8_stage[key] = torch.empty(src.shape, dtype=torch.uint8, device=self.device)
+        stage.copy_(src, non_blocking=True)
+        sub = 0.5 if name == "IMAGE" else 0.0
+        _lib.check(_lib.lib().hoc_unpack_u8(_lib.ptr(stage), _lib.ptr(buf), buf.numel(), 255.0, sub,
+                                            _lib.stream_ptr()), "hoc_unpack_u8")
+
     def load(self, samples, all_results):
-        """Copy a new batch into the static buffers (stream-ordered; pinned host tensors copy asynchronously)."""
+        """Copy a new batch into the static buffers (stream-ordered; pinned host tensors copy asynchronously).
+        IMAGE / JITTERMASK may be given as uint8 tensors (0..255): see ``_load_u8``."""
         with torch.no_grad():
             for dst, src in zip(self.samples, samples):
                 by_name = {(_name(k), type(k).__name__): v for k, v in src.items()}
                 for k, buf in dst.items():
                     if torch.is_tensor(buf):
-                        buf.copy_(by_name[(_name(k), type(k).__name__)], non_blocking=True)
+                        val = by_name[(_name(k), type(k).__name__)]
+                        if val.dtype == torch.uint8 and buf.dtype == torch.float32 and _name(k) in ("IMAGE", "JITTERMASK"):
+                            self._load_u8(buf, val, _name(k))
+                        else:
+                            buf.copy_(val, non_blocking=True)
             for dst, src in zip(self.results, all_results):
                 for k, buf in dst.items():
                     buf.copy_(src[k].detach(), non_blocking=True)

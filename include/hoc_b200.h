@@ -80,6 +80,7 @@ const char *hoc_last_error(void);
 #define HOC_K_RASTER_BACKWARD_COVER 20 /* hoc_raster_bwd_cover_kernel<.., false>: texture / depth gradient only */
 #define HOC_K_CAT_MESHES 21
 #define HOC_K_PAIR_LOSS 22
+#define HOC_K_UNPACK_U8 23
 #define HOC_KERNEL_COUNT 24
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
@@ -181,6 +182,12 @@ int hoc_warp_photo_forward_acc(const float *src, const float *target, const floa
                                int C, int Cj, int H, int W, float thresh, float *warped, float *warp_mask,
                                uint8_t *valid_mask, uint8_t *flow_mask, float *diff, double *sums, float *loss,
                                void *stream);
+
+/* Input side of the path: frames and jitter masks can cross PCIe as uint8 (a quarter of the fp32 bytes)
+ * and be widened on the device: dst[i] = src[i] / div - sub, the two IEEE operations of torchvision's `to_tensor`
+ * followed by `normalize(mean, 1)` (/root/reference/meshreg/datasets/handobjset.py:368-372: div = 255, sub = 0.5);
+ * div = 255, sub = 0 for the jitter masks, `to_tensor` of a warped white image (handobjset.py:375-379). */
+int hoc_unpack_u8(const uint8_t *src, float *dst, long long n, float div, float sub, void *stream);
 
 /* pair_consist's per-sample loss from the sums of its two directions (imgflowarp.py:108-114):
  * loss[b] = masked_mean(bwd) + masked_mean(fwd) (that order, float) when sums_bwd is given, else masked_mean(fwd). */

@@ -214,3 +214,47 @@ def test_vertex_texture_mode_is_bit_identical_to_cubes():
     assert (outs[0][3] >= 0).float().mean().item() > 0.02  # the scene covers something
     for a, b in zip(outs[0], outs[1]):
         assert torch.equal(a, b)
+
+
+def test_graphed_step_accepts_uint8_frames():
+    """GraphedConsistStep.load with uint8 IMAGE / JITTERMASK (pinned host memory) gives what the equivalent fp32
+    tensors (x / 255 - 0.5, x / 255, computed on the CPU like the reference's dataset workers do) give."""
+    from handobjectconsist_b200.graphed import GraphedConsistStep
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+    S, B, hv = 64, 2, 778
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, S, seed=31)
+    obj_faces = (sc["faces"][:, 1552:] - hv).contiguous()
+
+    def batch(as_u8):
+        samples, results = [], []
+        for verts, img, jit in ((sc["verts1"], sc["image_ref"], sc["jitter_mask_ref"]),
+                                (sc["verts2"], sc["image"], sc["jitter_mask"])):
+            iu = ((img + 0.5) * 255.0).round().clamp(0, 255).to(torch.uint8)
+            ju = (jit * 255.0).round().clamp(0, 255).to(torch.uint8)
+            if as_u8:
+                im, jm = iu.pin_memory(), ju.pin_memory()
+            else:
+                im, jm = iu.float().div(255.0).sub(0.5), ju.float().div(255.0)
+            samples.append({TransQueries.IMAGE: im, TransQueries.JITTERMASK: jm, TransQueries.CAMINTR: sc["K"],
+                            BaseQueries.OBJFACES: obj_faces, BaseQueries.OBJVERTS3D: verts[:, hv:].contiguous(),
+                            BaseQueries.HANDVERTS3D: verts[:, :hv].contiguous()})
+            results.append({"recov_handverts3d": verts[:, :hv].contiguous(), "recov_objverts3d": verts[:, hv:].contiguous()})
+        return samples, results
+
+    fs, fr = batch(False)
+    gstep = GraphedConsistStep(_renderer(S, dev), PyramidCriterion("l1"), (S, S), sc["faces"][0, :1552].to(dev), fs, fr,
+                               hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)
+    ref = [t.clone() for t in gstep(fs, fr)]
+    us, ur = batch(True)
+    got = [t.clone() for t in gstep(us, ur)]
+    assert ref[0].item() > 0
+    assert abs(ref[0].item() - got[0].item()) <= 1e-6
+    for a, b in zip(ref[1:], got[1:]):  # float atomics: two replays of the same inputs agree to rounding, not bit for bit
+        assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item()
+    # and a step captured from a uint8 example batch
+    gstep2 = GraphedConsistStep(_renderer(S, dev), PyramidCriterion("l1"), (S, S), sc["faces"][0, :1552].to(dev), us, ur,
+                                hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)
+    got2 = gstep2(us, ur)
+    assert torch.allclose(ref[0], got2[0], rtol=0, atol=1e-6)

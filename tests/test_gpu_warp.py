@@ -115,3 +115,21 @@ def test_occlusion_mask_matches_oracle(B, H, W, seed):
     assert 0.02 < o1.mean().item() < 0.98
     assert (r1 != o1).float().mean().item() <= 1e-4  # thresholded at |d| < 0.03: allow ulp-level ties
     assert (r2 != o2).float().mean().item() <= 1e-4
+
+
+def test_unpack_u8_matches_to_tensor_normalize_bit_for_bit():
+    """hoc_unpack_u8 = torchvision's to_tensor (x / 255) followed by normalize(mean, 1) (x - mean) as the reference's
+    dataset workers compute them -- on the CPU, where ATen divides (its CUDA kernel multiplies by the reciprocal) -- bit
+    for bit, also for sizes and offsets that are not multiples of the 16-byte vector path."""
+    from handobjectconsist_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    for n, off in ((16 * 1000, 0), (12345, 0), (777, 3), (5, 1)):
+        raw = torch.randint(0, 256, (n + off,), dtype=torch.uint8, generator=g).to(dev)
+        src = raw[off:]
+        for div, sub in ((255.0, 0.5), (255.0, 0.0)):
+            dst = torch.full((n,), float("nan"), device=dev)
+            _lib.check(L.hoc_unpack_u8(_lib.ptr(src), _lib.ptr(dst), n, div, sub, _lib.stream_ptr()), "hoc_unpack_u8")
+            want = src.cpu().float().div(div).sub(sub)
+            assert torch.equal(dst.cpu(), want)
