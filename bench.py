@@ -322,7 +322,7 @@ def run_native(args, rank, world, local_rank):
     # ALGORITHMIC bytes per launch: every datum the kernel needs crosses HBM once.
     algo = {
         "raster_zbuf": PAIRS * F2 * 36 + npx * 8,                       # faces in, 8-byte depth/face key per pixel
-        "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 96) + npx * 24,   # key, faces+textures, rgb12+alpha4+depth4+idx4
+        "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 36) + npx * 36,   # key, faces + vertex values, rgb12+alpha4+depth4+idx4+weights12
         # scan pass (streaming): idx + grad_rgb in; list of covered pixels (4 B per listed pixel, bounded by npx * 4,
         # counted at the measured 7 % coverage) and the zero-fill of grad_faces + grad of the 9 vertex values out
         "raster_bwd_pixel": npx * (4 + 12) + int(0.07 * npx) * 4 + PAIRS * F2 * (36 + 36),
@@ -337,8 +337,8 @@ def run_native(args, rank, world, local_rank):
         "warp_photo_bwd": npx * (12 + 8 + 12 + 1 + 8),
         "flow_finalize": 2 * npx * (2 * (8 + 4 + 4) + 8 + 4),
         "flow_finalize_bwd": npx * (8 + 4 + 12),
-        "mesh_gather": PAIRS * (2280 * 24 + 4552 * 24 + F2 * (36 + 96)),
-        "mesh_scatter": PAIRS * (F2 * (36 + 96) + 4552 * 24 + 2280 * 24),
+        "mesh_gather": PAIRS * (2280 * 24 + 4552 * 24 + F2 * (36 + 36)) + npx * 8,  # + the z-buffer key fill
+        "mesh_scatter": PAIRS * (F2 * (36 + 36) + 4552 * 24 + 2280 * 24),  # grad_faces + grad of the 9 vertex values in
     }
     table = []
     for name, v in per_kernel.items():
