@@ -39,8 +39,10 @@ def test_every_entry_point_cites_the_reference():
 def test_argument_errors_are_codes_not_crashes():
     L = _lib.lib()
     assert L.hoc_raster_forward_workspace_bytes(2, 10, 16) == 2 * 16 * 16 * 8
-    # line spans (4 ints per line) + per-face depth sums + two flag bytes per pixel
-    assert L.hoc_raster_backward_workspace_bytes(2, 10, 16) >= 2 * 4 * 16 * 4 + 2 * 10 * 3 * 4 + 2 * 2 * 16 * 16
+    # line spans (4 ints per line) + counters + per-face depth sums + list of covered pixels + 2-byte scan queues
+    assert L.hoc_raster_backward_workspace_bytes(2, 10, 16) >= (2 * 4 * 16 * 4 + 2 * 4 + 2 * 2 * 16 * 4 + 2 * 10 * 3 * 4 +
+                                                                2 * 16 * 16 * 4 + 2 * 2 * 16 * 48 * 2)
+    assert L.hoc_mano_backward_workspace_bytes(3) >= 3 * (192 + 135 + 10) * 4
     bg = (ctypes.c_float * 3)(0, 0, 0)
     # image size out of range / missing index map: rejected before anything touches the device
     code = L.hoc_raster_forward(None, None, 1, 0, 4096, 0, 0.1, 100.0, 1e-3, bg, None, 0, None, None, None, None, None,
@@ -51,6 +53,20 @@ def test_argument_errors_are_codes_not_crashes():
     assert code == -1 and b"face_index_map" in L.hoc_last_error()
     code = L.hoc_warp(None, None, 1, 3, 8, 8, 0.99999, 7, None, None, None)
     assert code == -1 and b"mode" in L.hoc_last_error()
+    # the newer entry points: same contract (a code and a message, nothing launched)
+    assert L.hoc_set_tuning(99, 1) == -1 and b"hoc_set_tuning" in L.hoc_last_error()
+    assert L.hoc_set_tuning(1, 100) == -1            # threads per CTA must be a multiple of 32
+    assert L.hoc_set_tuning(1, 128) == 0 and L.hoc_set_tuning(2, 16) == 0
+    assert L.hoc_unpack_u8(None, None, 16, 255.0, 0.5, None) == -1 and b"hoc_unpack_u8" in L.hoc_last_error()
+    assert L.hoc_unpack_u8(None, None, 0, 255.0, 0.5, None) == 0   # nothing to do
+    assert L.hoc_cat_meshes(None, None, None, None, None, 0, None, 0, 778, 1502, 1552, 3000, None, None, None, None) == 0
+    assert L.hoc_cat_meshes(None, None, None, None, None, 0, None, 2, 778, 1502, 1552, 3000, None, None, None, None) == -1
+    assert L.hoc_pair_loss(None, None, 4, None, None) == -1 and b"hoc_pair_loss" in L.hoc_last_error()
+    assert L.hoc_mesh_gather_clear(None, None, None, 1, 4, 2, 1, 7, None, None, None, 0, None) == -1
+    assert b"tex_mode" in L.hoc_last_error()
+    assert L.hoc_raster_forward(None, None, 1, 0, 16, 3, 0.1, 100.0, 1e-3, bg, None, 0x200, None, None, None, None, None,
+                                None, None, 0, None) == -1      # vertex textures need texture_size 2
+    assert b"texture_size 2" in L.hoc_last_error()
 
 
 def test_pixel_centre_float_equals_reference_double_formula():
