@@ -322,7 +322,8 @@ def run_native(args, rank, world, local_rank):
     # ALGORITHMIC bytes per launch: every datum the kernel needs crosses HBM once.
     algo = {
         "raster_zbuf": PAIRS * F2 * 36 + npx * 8,                       # faces in, 8-byte depth/face key per pixel
-        "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 36) + npx * 36,   # key, faces + vertex values, rgb12+alpha4+depth4+idx4+weights12
+        # key in; faces + vertex values in; rgb12 + alpha4 + idx4 out, depth4 + weights12 out at the covered 7 % only
+        "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 36) + npx * 20 + int(0.07 * npx) * 16,
         # scan pass (streaming): idx + grad_rgb in; list of covered pixels (4 B per listed pixel, bounded by npx * 4,
         # counted at the measured 7 % coverage) and the zero-fill of grad_faces + grad of the 9 vertex values out
         "raster_bwd_pixel": npx * (4 + 12) + int(0.07 * npx) * 4 + PAIRS * F2 * (36 + 36),

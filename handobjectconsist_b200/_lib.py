@@ -14,6 +14,7 @@ HOC_LAYOUT_RAW = 0
 HOC_LAYOUT_IMAGE = 1
 HOC_LAYOUT_KEYS_CLEARED = 0x100
 HOC_LAYOUT_TEX_VERTEX = 0x200
+HOC_LAYOUT_SPARSE_SAVED = 0x400
 HOC_TEX_GRAD_CUBE = 0
 HOC_TEX_GRAD_VERTEX = 1
 

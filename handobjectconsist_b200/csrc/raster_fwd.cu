@@ -276,9 +276,9 @@ __global__ void __launch_bounds__(RS_THREADS)
 hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
                           const unsigned long long *__restrict__ zbuf, int F, int S, int ts, float near_, float far_,
                           float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int layout,
-                          int tex_vertex, float *__restrict__ rgb, float *__restrict__ alpha, float *__restrict__ depth,
-                          int32_t *__restrict__ face_index_map, float *__restrict__ weight_map,
-                          float *__restrict__ face_inv_map)
+                          int tex_vertex, int sparse_saved, float *__restrict__ rgb, float *__restrict__ alpha,
+                          float *__restrict__ depth, int32_t *__restrict__ face_index_map,
+                          float *__restrict__ weight_map, float *__restrict__ face_inv_map)
 {
     __shared__ float s_stage[RS_THREADS * 9];
 
@@ -320,8 +320,14 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
         const long po = hoc_plane_off(layout, S, b, yi, xi);
         if (alpha != nullptr)
             alpha[po] = (fidx >= 0) ? 1.0f : 0.0f;
-        if (depth != nullptr)
+        if (depth != nullptr && (!sparse_saved || fidx >= 0))
             depth[po] = zp;
+        if (sparse_saved && weight_map != nullptr && fidx >= 0) { /* covered pixels only: 7 % of 12 bytes per pixel */
+            float *wd = weight_map + ((long)b * npix + pix) * 3;
+            wd[0] = w[0];
+            wd[1] = w[1];
+            wd[2] = w[2];
+        }
         if (rgb != nullptr && layout == HOC_LAYOUT_IMAGE) {
 #pragma unroll
             for (int c = 0; c < 3; c++)
@@ -331,7 +337,7 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
     const long left = npix - pix0; /* pixels of this block that exist */
     if (rgb != nullptr && layout == HOC_LAYOUT_RAW)
         hoc_store_interleaved<3>(s_stage, col, rgb + ((long)b * npix + pix0) * 3, left * 3);
-    if (weight_map != nullptr)
+    if (weight_map != nullptr && !sparse_saved)
         hoc_store_interleaved<3>(s_stage, w, weight_map + ((long)b * npix + pix0) * 3, left * 3);
     if (face_inv_map != nullptr)
         hoc_store_interleaved<9>(s_stage, inv, face_inv_map + ((long)b * npix + pix0) * 9, left * 9);
@@ -355,7 +361,8 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_forward: image_size %d outside [1, 2048]", S);
     const bool keys_cleared = (layout & HOC_LAYOUT_KEYS_CLEARED) != 0; /* the caller filled the workspace with 0xff */
     const int tex_vertex = (layout & HOC_LAYOUT_TEX_VERTEX) ? 1 : 0;   /* textures = [B,F,3,3] vertex values */
-    layout &= ~(HOC_LAYOUT_KEYS_CLEARED | HOC_LAYOUT_TEX_VERTEX);
+    const int sparse_saved = (layout & HOC_LAYOUT_SPARSE_SAVED) ? 1 : 0; /* depth / weight_map at covered pixels only */
+    layout &= ~(HOC_LAYOUT_KEYS_CLEARED | HOC_LAYOUT_TEX_VERTEX | HOC_LAYOUT_SPARSE_SAVED);
     HOC_CHECK_ARG(!tex_vertex || ts == 2, "hoc_raster_forward: vertex textures need texture_size 2, got %d", ts);
     HOC_CHECK_ARG(layout == HOC_LAYOUT_RAW || layout == HOC_LAYOUT_IMAGE, "hoc_raster_forward: bad layout %d", layout);
     HOC_CHECK_ARG(face_index_map != nullptr, "hoc_raster_forward: face_index_map is required");
@@ -397,8 +404,8 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
                (hoc_raster_resolve_kernel<<<grid2, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
                                                                         bg[0], bg[1], bg[2], background_dev, layout,
-                                                                        tex_vertex, rgb, alpha, depth, face_index_map,
-                                                                        weight_map, face_inv_map)));
+                                                                        tex_vertex, sparse_saved, rgb, alpha, depth,
+                                                                        face_index_map, weight_map, face_inv_map)));
     HOC_CHECK_LAUNCH("hoc_raster_resolve_kernel");
     return HOC_OK;
 }

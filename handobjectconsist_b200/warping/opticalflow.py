@@ -62,10 +62,13 @@ class _MeshRasterFunction(Function):
             alpha = torch.empty((B, S, S), dtype=torch.float32, device=dev)
             depth = torch.empty((B, S, S), dtype=torch.float32, device=dev)
             idx = torch.empty((B, S, S), dtype=torch.int32, device=dev)
-            wmap = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)  # saved for the backward
+            # depth and wmap are saved for the backward, which reads them at covered pixels: the forward writes them
+            # there only (HOC_LAYOUT_SPARSE_SAVED) -- the depth this Function returns is NOT a full depth map
+            wmap = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev)
             _lib.check(L.hoc_raster_forward(_lib.ptr(faces), _lib.ptr(tex), B, Fo, S, 2, float(near), float(far),
                                             float(eps), bg, None,
-                                            _lib.HOC_LAYOUT_IMAGE | _lib.HOC_LAYOUT_KEYS_CLEARED | _lib.HOC_LAYOUT_TEX_VERTEX,
+                                            _lib.HOC_LAYOUT_IMAGE | _lib.HOC_LAYOUT_KEYS_CLEARED | _lib.HOC_LAYOUT_TEX_VERTEX
+                                            | _lib.HOC_LAYOUT_SPARSE_SAVED,
                                             _lib.ptr(rgb),
                                             _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx), _lib.ptr(wmap), None,
                                             _lib.ptr(ws), ws_bytes, st), "hoc_raster_forward")

@@ -52,6 +52,10 @@ extern "C" {
  * stands for the cube T[i,j,k] = i c0 + j c1 + k c2 (texture_size 2), whose texels the forward evaluates on the fly
  * with hoc_mesh_gather's expression: same bits as sampling the materialised cube, 36 instead of 96 bytes per face */
 #define HOC_LAYOUT_TEX_VERTEX 0x200
+/* OR-ed into `layout` of hoc_raster_forward: `depth` and `weight_map` are only kept for hoc_raster_backward, which
+ * reads them at covered pixels -- write them there only (background pixels stay uninitialised): 16 of the 36 bytes per
+ * pixel the forward writes are not written for the 90+ % of the pixels no face covers */
+#define HOC_LAYOUT_SPARSE_SAVED 0x400
 
 int hoc_abi_version(void);
 const char *hoc_last_error(void);
