@@ -48,7 +48,8 @@
  *   cov_count  int    [B]            covered pixels listed per sample                      (zero-filled)
  *   line_count int    [B][2][S]      outward scans queued on each line (axis 0: column x, axis 1: row y)  (zero-filled)
  *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
- *   cov_list   int    [B][S*S]       the covered pixels (yi * S + xi) that have work, in tile order
+ *   cov_list   int2   [B][S*S]       the covered pixels that have work, in tile order: (yi * S + xi, owning face) --
+ *                                    the face rides along so that the cover pass starts one dependent load earlier
  *   emitters   ushort [B][2][S][3S]  the queues: position on the line | edge << 11.  3S is a hard bound: a scan is
  *                                    keyed by its inside pixel on the line, which is owned by exactly one face with
  *                                    3 edges; only the used part is ever touched */
@@ -57,7 +58,7 @@ struct HocBwdWorkspace {
     int *cov_count;
     int *line_count;
     float *acc_d;
-    int *cov_list;
+    int2 *cov_list;
     unsigned short *emitters;
     size_t count_bytes, acc_bytes; /* ext + cov_count + line_count, then acc_d: one contiguous zero-fill */
     size_t total;
@@ -80,8 +81,8 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     w.acc_d = (float *)(p + off); /* directly after the counters: one memset covers both */
     w.acc_bytes = sizeof(float) * 3 * (size_t)B * F;
     off = up(off + w.acc_bytes);
-    w.cov_list = (int *)(p + off);
-    off = up(off + sizeof(int) * (size_t)B * S * S);
+    w.cov_list = (int2 *)(p + off);
+    off = up(off + sizeof(int2) * (size_t)B * S * S);
     w.emitters = (unsigned short *)(p + off);
     off = up(off + sizeof(unsigned short) * 2 * (size_t)B * S * 3 * (size_t)S);
     w.total = off;
@@ -183,7 +184,7 @@ template <bool K4>
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int S, int layout, int list_all, int *__restrict__ ext,
-                           int *__restrict__ cov_count, int *__restrict__ cov_list, float *__restrict__ zero_a,
+                           int *__restrict__ cov_count, int2 *__restrict__ cov_list, float *__restrict__ zero_a,
                            long n_a, float *__restrict__ zero_b, long n_b)
 {
     { /* zero-fill of the two gradient outputs (accumulated with atomics by the later passes), spread over the grid */
@@ -273,13 +274,13 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         }
     }
     __syncthreads();
-    int *list = cov_list + (long)b * S * S + s_cnt[32];
+    int2 *list = cov_list + (long)b * S * S + s_cnt[32];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int lr = r * 8 + ty;
         const int yi = blockIdx.y * 32 + lr;
         if ((want[r] >> tx) & 1u)
-            list[s_cnt[lr] + __popc(want[r] & ((1u << tx) - 1u))] = yi * S + xi;
+            list[s_cnt[lr] + __popc(want[r] & ((1u << tx) - 1u))] = make_int2(yi * S + xi, fis[r]);
     }
 }
 
@@ -403,21 +404,21 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                             const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
                             const float *__restrict__ g_alpha, const float *__restrict__ g_depth, int F, int S, int ts,
                             float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
-                            const int *__restrict__ cov_count, const int *__restrict__ cov_list,
+                            const int *__restrict__ cov_count, const int2 *__restrict__ cov_list,
                             float *__restrict__ acc_d, int *__restrict__ line_count,
                             unsigned short *__restrict__ emitters, float *__restrict__ grad_faces,
                             float *__restrict__ grad_textures)
 {
     const int b = blockIdx.y;
     const int count = min(cov_count[b], S * S);
-    const int *list = cov_list + (long)b * S * S;
+    const int2 *list = cov_list + (long)b * S * S;
     const int32_t *idx = face_index_map + (long)b * S * S;
     if (!K4) {
         for (int i = blockIdx.x * CV_THREADS + threadIdx.x; i < count; i += gridDim.x * CV_THREADS) {
-            const int p = list[i];
-            const int yi = p / S, xi = p - yi * S;
-            hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, idx[p], xi, yi, F, S, ts, near_,
-                                     far_, eps, layout, tex_mode, acc_d, grad_textures);
+            const int2 e = list[i];
+            const int yi = e.x / S, xi = e.x - yi * S;
+            hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, e.y, xi, yi, F, S, ts, near_, far_,
+                                     eps, layout, tex_mode, acc_d, grad_textures);
         }
         return;
     }
@@ -435,9 +436,9 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
     for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {
         const int i = base + lane;
         const bool live = i < count;
-        const int p = live ? list[i] : 0;
+        const int2 e = live ? list[i] : make_int2(0, -1);
+        const int p = e.x, fi = e.y;
         const int yi = p / S, xi = p - yi * S;
-        const int fi = live ? idx[p] : -1;
         if (wid == 6) {
             if (fi >= 0)
                 hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, fi, xi, yi, F, S, ts, near_,

@@ -187,7 +187,9 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
     }
 }
 
+#ifndef RS_THREADS
 #define RS_THREADS 256
+#endif
 
 /* Stage `n_per` floats per thread in shared memory and store them as one contiguous, coalesced
  * run of RS_THREADS*n_per floats starting at dst (bounded by `limit` floats). */
