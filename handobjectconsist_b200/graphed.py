@@ -34,6 +34,7 @@ class GraphedConsistStep:
                        use_backward=use_backward, detach_renders=detach_renders)
         self.hand_face = hand_face.to(dev)
         self._u8_stage = {}
+        self._one = torch.ones((), dtype=torch.float32, device=dev)  # d loss / d loss, created once (not per replay)
         # static inputs
         def static(k, v):
             if not torch.is_tensor(v):
@@ -70,7 +71,7 @@ class GraphedConsistStep:
     def _run(self):
         loss, _ = warpbranch.forward(self.samples, self.results, self.hand_face, self.renderer, self.image_size,
                                      self.criterion, **self.kw)
-        gh, go = torch.autograd.grad(loss, [self.hand, self.obj], allow_unused=True)
+        gh, go = torch.autograd.grad(loss, [self.hand, self.obj], grad_outputs=self._one, allow_unused=True)
         if gh is None:
             gh = torch.zeros_like(self.hand)
         if go is None:
