@@ -1,12 +1,14 @@
-"""``batch_masked_mean_loss`` -- /root/reference/meshreg/optim/lossutils.py:1-8 (torch ops; the fused L1
-path of pair_consist computes the same quantity inside hoc_warp_photo_forward)."""
+"""``batch_masked_mean_loss`` -- same contract as /root/reference/meshreg/optim/lossutils.py:1-8: the mean of a
+per-element distance over the elements a mask selects, one value per sample, 0 for a sample whose mask is empty.
+(Element-wise torch ops for the generic criteria; the fused L1 path of ``pair_consist`` computes the same quantity
+inside ``hoc_warp_photo_forward`` / ``hoc_pair_loss``.)"""
 
 
 def batch_masked_mean_loss(dists, mask):
-    mask = mask.float()
-    batch_sum = (mask * dists).sum(dim=list(range(1, dists.dim())))
-    batch_valid_vals = mask.sum(dim=list(range(1, dists.dim())))
-    # Don't divide by 0
-    batch_valid_vals[(batch_valid_vals == 0)] = 1
-    batch_losses = batch_sum / batch_valid_vals
-    return batch_losses
+    """dists, mask: [B, ...] of the same shape (mask boolean or 0/1).  Returns [B]."""
+    weights = mask.float()
+    per_sample = weights.flatten(1)
+    selected_sum = (per_sample * dists.flatten(1)).sum(dim=1)
+    selected_count = per_sample.sum(dim=1)
+    # an empty mask would divide 0 by 0: its count is replaced by 1, which makes the sample's loss exactly 0
+    return selected_sum / selected_count.clamp(min=1.0)
