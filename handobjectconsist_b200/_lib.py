@@ -72,7 +72,8 @@ SIGNATURES = {
 KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_backward": 3, "warp_photo_fwd": 4,
               "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8, "mesh_gather": 9, "mesh_scatter": 10,
               "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16, "mano_fwd": 17,
-              "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22, "unpack_u8": 23}
+              "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22, "unpack_u8": 23,
+              "hand_head_fwd": 24, "hand_head_bwd": 25, "recover_points_fwd": 26, "recover_points_bwd": 27}
 
 
 
@@ -88,6 +89,12 @@ SIGNATURES["hoc_mano_forward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp
 SIGNATURES["hoc_mano_backward_workspace_bytes"] = (_sz, [_i])
 SIGNATURES["hoc_mano_backward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                                         _vp, _sz, _vp])
+
+_GH_CAM = [_vp, _i, _vp, _vp] + [_f] * 5  # camintr, camintr_batched, scale, trans, factors / off_z / input_res
+SIGNATURES["hoc_hand_head_forward"] = (_i, [_vp] * 3 + [_i] * 4 + _GH_CAM + [_vp] * 7 + [_vp])
+SIGNATURES["hoc_hand_head_backward"] = (_i, [_vp] * 3 + [_i] * 4 + _GH_CAM + [_vp] * 7 + [_vp] * 5 + [_vp])
+SIGNATURES["hoc_recover_points_forward"] = (_i, [_vp] * 2 + [_i] * 2 + _GH_CAM + [_vp] * 4 + [_vp])
+SIGNATURES["hoc_recover_points_backward"] = (_i, [_vp] * 2 + [_i] * 2 + _GH_CAM + [_vp] * 4 + [_vp] * 4 + [_vp])
 
 _LIB = None
 

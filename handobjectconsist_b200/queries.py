@@ -1,5 +1,5 @@
 """Sample-dictionary keys -- the members of /root/reference/meshreg/datasets/queries.py:4-46 that
-``warpbranch.forward`` reads (same names, so a reference batch dict works unchanged)."""
+``warpbranch.forward`` and ``ObjBranch.forward`` read (same names, so a reference batch dict works unchanged)."""
 from enum import Enum, auto
 
 
@@ -9,6 +9,9 @@ class BaseQueries(Enum):
     OBJVERTS3D = auto()
     HANDVERTS3D = auto()
     IMAGE = auto()
+    OBJCANVERTS = auto()
+    OBJCANCORNERS = auto()
+    OBJCORNERS3D = auto()
 
 
 class TransQueries(Enum):

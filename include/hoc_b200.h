@@ -85,7 +85,11 @@ const char *hoc_last_error(void);
 #define HOC_K_CAT_MESHES 21
 #define HOC_K_PAIR_LOSS 22
 #define HOC_K_UNPACK_U8 23
-#define HOC_KERNEL_COUNT 24
+#define HOC_K_HAND_HEAD_FWD 24
+#define HOC_K_HAND_HEAD_BWD 25
+#define HOC_K_RECOVER_POINTS_FWD 26
+#define HOC_K_RECOVER_POINTS_BWD 27
+#define HOC_KERNEL_COUNT 28
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
@@ -322,6 +326,54 @@ size_t hoc_mano_backward_workspace_bytes(int B);
 int hoc_mano_backward(const hoc_mano_model *model, const float *pose, const float *betas, const float *trans,
                       const float *grad_verts, const float *grad_joints, int B, float *grad_pose, float *grad_betas,
                       float *grad_trans, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- geometry head: network outputs -> camera-space meshes ---------------
+ * Shared camera arguments (recover_3d_proj, /root/reference/meshreg/models/project.py:5-23):
+ *   camintr [B,3,3] (or [1,3,3] with camintr_batched = 0), scale [B], trans [B,2] = the predicted pixel-space
+ *   scale / translation BEFORE the factors (meshregnet.py:220-221, objbranch.py:50-51), scale_factor / trans_factor,
+ *   off_z (0.4), input_res (res_w, res_h).
+ *     Z0 = camintr[b,0,0] * scale * scale_factor + off_z
+ *     XY0 = (trans * trans_factor + input_res / 2 - camintr[b,:2,2]) * Z0 / camintr[b,0,0];  center3d = (XY0, Z0)
+ *
+ * hoc_hand_head_forward replaces the geometry of MeshRegNet.recover_mano (meshregnet.py:191-229): ManoAdaptor
+ * (bias-free Linear 778 -> 21, `adaptor` [J,V]; meshregnet.py:23-51), centring on adapted joint `center_idx`,
+ * recover_3d_proj, recov_joints3d / recov_handverts3d and both batch_proj2d.  One launch.
+ *   verts [B,V,3] (V <= 1024);  adaptor [J,V] or NULL (then joints_in [B,J,3] are the joints and nothing is
+ *   re-derived from the vertices);  center_idx -1 = no centring (the no-adaptor branch of the reference);
+ *   outputs (any may be NULL): joints3d [B,J,3], verts3d [B,V,3] (centred), recov_joints3d, recov_verts3d
+ *   (+ center3d), joints2d [B,J,2], verts2d [B,V,2] (pixels), center3d [B,3]. */
+int hoc_hand_head_forward(const float *verts, const float *joints_in, const float *adaptor, int B, int V, int J,
+                          int center_idx, const float *camintr, int camintr_batched, const float *scale,
+                          const float *trans, float scale_factor, float trans_factor, float off_z, float res_w,
+                          float res_h, float *joints3d, float *verts3d, float *recov_joints3d, float *recov_verts3d,
+                          float *joints2d, float *verts2d, float *center3d, void *stream);
+/* Adjoint.  recov_verts3d / recov_joints3d: the forward's outputs (needed when a 2-D gradient is given);
+ * g_*: gradients of the seven outputs (any may be NULL = zero);  results (any may be NULL; fully overwritten):
+ * grad_verts [B,V,3], grad_joints_in [B,J,3] (adaptor == NULL) or grad_adapt [B,J,3] (d L / d adapted joints, from
+ * which the caller forms a weight gradient if the adaptor is not frozen), grad_scale [B], grad_trans [B,2]. */
+int hoc_hand_head_backward(const float *recov_verts3d, const float *recov_joints3d, const float *adaptor, int B, int V,
+                           int J, int center_idx, const float *camintr, int camintr_batched, const float *scale,
+                           const float *trans, float scale_factor, float trans_factor, float off_z, float res_w,
+                           float res_h, const float *g_joints3d, const float *g_verts3d,
+                           const float *g_recov_joints3d, const float *g_recov_verts3d, const float *g_joints2d,
+                           const float *g_verts2d, const float *g_center3d, float *grad_verts, float *grad_joints_in,
+                           float *grad_adapt, float *grad_scale, float *grad_trans, void *stream);
+/* hoc_recover_points_forward replaces ObjBranch.forward's geometry (objbranch.py:46-77): batch_rodrigues of
+ * rotaxisang [B,3] (manopth rodrigues_layer; NULL = no rotation, which makes the call recover_3d_proj itself),
+ * rot_points = R . points, recov_points = rot_points + center3d, points2d = batch_proj2d(recov_points).
+ * points [B,N,3]; outputs (any may be NULL): rot_points [B,N,3], recov_points [B,N,3], points2d [B,N,2], center3d [B,3]. */
+int hoc_recover_points_forward(const float *points, const float *rotaxisang, int B, int N, const float *camintr,
+                               int camintr_batched, const float *scale, const float *trans, float scale_factor,
+                               float trans_factor, float off_z, float res_w, float res_h, float *rot_points,
+                               float *recov_points, float *points2d, float *center3d, void *stream);
+/* Adjoint: g_* any may be NULL;  grad_points [B,N,3], grad_rot [B,3], grad_scale [B], grad_trans [B,2]
+ * (any may be NULL; fully overwritten).  Deterministic (sums are reduced inside one CTA per sample). */
+int hoc_recover_points_backward(const float *points, const float *rotaxisang, int B, int N, const float *camintr,
+                                int camintr_batched, const float *scale, const float *trans, float scale_factor,
+                                float trans_factor, float off_z, float res_w, float res_h, const float *g_rot_points,
+                                const float *g_recov_points, const float *g_points2d, const float *g_center3d,
+                                float *grad_points, float *grad_rot, float *grad_scale, float *grad_trans,
+                                void *stream);
 
 #ifdef __cplusplus
 }

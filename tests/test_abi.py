@@ -67,6 +67,21 @@ def test_argument_errors_are_codes_not_crashes():
     assert L.hoc_raster_forward(None, None, 1, 0, 16, 3, 0.1, 100.0, 1e-3, bg, None, 0x200, None, None, None, None, None,
                                 None, None, 0, None) == -1      # vertex textures need texture_size 2
     assert b"texture_size 2" in L.hoc_last_error()
+    # geometry head (geom_head.cu)
+    cam = (None, 1, None, None, 1.0, 1.0, 0.4, 256.0, 256.0)
+    assert L.hoc_hand_head_forward(None, None, None, 0, 778, 21, 9, *cam, *([None] * 8)) == 0       # empty batch
+    assert L.hoc_hand_head_forward(None, None, None, 2, 778, 21, 9, *cam, *([None] * 8)) == -1
+    assert b"camintr" in L.hoc_last_error()
+    assert L.hoc_hand_head_forward(None, None, None, 0, 5000, 21, 9, *cam, *([None] * 8)) == -1
+    assert b"vertices" in L.hoc_last_error()
+    assert L.hoc_hand_head_forward(None, None, None, 0, 778, 21, 21, *cam, *([None] * 8)) == -1
+    assert b"center_idx" in L.hoc_last_error()
+    assert L.hoc_hand_head_backward(None, None, None, 0, 778, 40, 9, *cam, *([None] * 13)) == -1
+    assert b"joints" in L.hoc_last_error()
+    assert L.hoc_recover_points_forward(None, None, 0, 10, *cam, *([None] * 5)) == 0
+    assert L.hoc_recover_points_forward(None, None, 1, -1, *cam, *([None] * 5)) == -1
+    assert L.hoc_recover_points_backward(None, None, 3, 10, *cam, *([None] * 9)) == -1
+    assert b"hoc_recover_points_backward" in L.hoc_last_error()
 
 
 def test_pixel_centre_float_equals_reference_double_formula():
@@ -89,3 +104,6 @@ def test_cpu_tensors_are_rejected_loudly():
         rasterize_rgbad(torch.zeros(1, 1, 3, 3), torch.zeros(1, 1, 2, 2, 2, 3))
     with pytest.raises(TypeError):
         warp(torch.zeros(1, 3, 4, 4), torch.zeros(1, 2, 4, 4))
+    from handobjectconsist_b200.project import recover_3d_proj
+    with pytest.raises(TypeError):
+        recover_3d_proj(torch.zeros(1, 4, 3), torch.eye(3)[None], torch.zeros(1, 1, 1), torch.zeros(1, 1, 2))

@@ -1,0 +1,127 @@
+"""CPU: the geometry-head oracle (oracle/geom.py) against the golden vectors generated from the REFERENCE's own
+meshreg/models/project.py (tests/golden/make_geom_golden.py, run where /root/reference exists) -- bit for bit, values
+and gradients -- and the hand-derived adjoint of the kernels (tests/emul/geom_emul.py, the decomposition
+csrc/geom_head.cu uses) against float64 autograd of the oracle."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers  # noqa: F401  (sys.path)
+from oracle import geom as ogeom
+from oracle import mano as omano
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_mk = _load("make_geom_golden", os.path.join(GOLD, "make_geom_golden.py"))
+_emul = _load("geom_emul", os.path.join(HERE, "emul", "geom_emul.py"))
+
+
+@pytest.mark.parametrize("name", sorted(_mk.CASES))
+def test_oracle_recover_3d_proj_matches_reference_golden(name):
+    gold = np.load(os.path.join(GOLD, "geom_recover3d.npz"))
+    B, N, seed, res = _mk.CASES[name]
+    pts, K, scale, trans, w_rec, w_c = _mk.inputs(B, N, seed, res)
+    pts, scale, trans = [t.clone().requires_grad_(True) for t in (pts, scale, trans)]
+    rec, c3d = ogeom.recover_3d_proj(pts, K, scale, trans, input_res=res)
+    ((rec * w_rec).sum() + (c3d * w_c).sum()).backward()
+    np.testing.assert_array_equal(rec.detach().numpy(), gold[f"{name}_recons3d"])
+    np.testing.assert_array_equal(c3d.detach().numpy(), gold[f"{name}_c3d"])
+    np.testing.assert_array_equal(pts.grad.numpy(), gold[f"{name}_g_pts"])
+    np.testing.assert_array_equal(scale.grad.numpy(), gold[f"{name}_g_scale"])
+    np.testing.assert_array_equal(trans.grad.numpy(), gold[f"{name}_g_trans"])
+
+
+def _camera(B, g, res=(256, 256)):
+    f = 300.0 + 400.0 * torch.rand(B, generator=g, dtype=torch.float64)
+    K = torch.zeros(B, 3, 3, dtype=torch.float64)
+    K[:, 0, 0], K[:, 1, 1], K[:, 2, 2] = f, f * 1.01, 1
+    K[:, 0, 1] = 0.3  # a skew term: the kernels use the full matrix
+    K[:, 0, 2] = res[0] / 2 + 10 * torch.randn(B, generator=g, dtype=torch.float64)
+    K[:, 1, 2] = res[1] / 2 + 10 * torch.randn(B, generator=g, dtype=torch.float64)
+    scale = (torch.randn(B, 1, generator=g, dtype=torch.float64) * 2e-4).requires_grad_(True)
+    trans = (torch.randn(B, 2, generator=g, dtype=torch.float64) * 30).requires_grad_(True)
+    return K, scale, trans
+
+
+@pytest.mark.parametrize("with_adaptor", [True, False])
+def test_hand_head_adjoint_decomposition(with_adaptor):
+    g = torch.Generator().manual_seed(3)
+    B, V, J, ci, res = 3, 50, 21, 9, (256, 192)
+    verts = (torch.randn(B, V, 3, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    joints = (torch.randn(B, J, 3, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    W = torch.rand(J, V, generator=g, dtype=torch.float64) / V if with_adaptor else None
+    K, scale, trans = _camera(B, g, res)
+    out = ogeom.recover_mano_geometry(verts, joints, K, scale, trans, adaptor_weight=W, center_idx=ci,
+                                      trans_factor=100.0, scale_factor=1e-4, input_res=res)
+    keys = {"joints3d": "joints3d", "verts3d": "verts3d", "recov_joints3d": "recov_joints3d",
+            "recov_verts3d": "recov_handverts3d", "joints2d": "joints2d", "verts2d": "verts2d", "center3d": "center3d"}
+    gr = {k: torch.randn(out[o].shape, generator=g, dtype=torch.float64) for k, o in keys.items()}
+    sum((out[o] * gr[k]).sum() for k, o in keys.items()).backward()
+    gnp = {k: v.numpy().reshape(B, 3) if k == "center3d" else v.numpy() for k, v in gr.items()}
+    gv, ga, gs, gt = _emul.hand_head_backward(
+        out["recov_handverts3d"].detach().numpy(), out["recov_joints3d"].detach().numpy(),
+        None if W is None else W.numpy(), ci if with_adaptor else -1, K.numpy(), scale.detach().numpy().reshape(B),
+        trans.detach().numpy(), 1e-4, 100.0, 0.4, res, gnp)
+    np.testing.assert_allclose(gv, verts.grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(gs, scale.grad.numpy().reshape(B), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(gt, trans.grad.numpy(), rtol=1e-9, atol=1e-9)
+    if not with_adaptor:
+        np.testing.assert_allclose(ga, joints.grad.numpy(), rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("with_rot", [True, False])
+def test_recover_points_adjoint_decomposition(with_rot):
+    g = torch.Generator().manual_seed(5)
+    B, N, res = 2, 40, (256, 256)
+    pts = (torch.randn(B, N, 3, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    rot = (torch.randn(B, 3, generator=g, dtype=torch.float64) * 0.8).requires_grad_(True)
+    K, scale, trans = _camera(B, g, res)
+    if with_rot:
+        out = ogeom.obj_branch(pts, K, scale, trans, rot, trans_factor=100.0, scale_factor=1e-4, input_res=res)
+        outs = {"rot_points": out["obj_verts3d"], "recov_points": out["recov_objverts3d"],
+                "points2d": out["obj_verts2d"], "center3d": out["center3d"]}
+    else:
+        rec, c3d = ogeom.recover_3d_proj(pts, K, scale * 1e-4, trans * 100.0, input_res=res)
+        outs = {"recov_points": rec, "center3d": c3d}
+    gr = {k: torch.randn(v.shape, generator=g, dtype=torch.float64) for k, v in outs.items()}
+    sum((outs[k] * gr[k]).sum() for k in outs).backward()
+    gnp = {k: v.numpy().reshape(B, 3) if k == "center3d" else v.numpy() for k, v in gr.items()}
+    R = dR = None
+    if with_rot:
+        R = omano.batch_rodrigues(rot.detach()).reshape(B, 3, 3).numpy()
+        jac = torch.autograd.functional.jacobian(lambda r: omano.batch_rodrigues(r).reshape(B, 3, 3), rot.detach())
+        dR = np.stack([jac[b, :, :, b].permute(2, 0, 1).numpy() for b in range(B)])  # [B,k,3,3]
+    gp, grot, gs, gt = _emul.recover_points_backward(pts.detach().numpy(), R, dR, K.numpy(),
+                                                      scale.detach().numpy().reshape(B), trans.detach().numpy(), 1e-4,
+                                                      100.0, 0.4, res, gnp)
+    np.testing.assert_allclose(gp, pts.grad.numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(gs, scale.grad.numpy().reshape(B), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(gt, trans.grad.numpy(), rtol=1e-9, atol=1e-9)
+    if with_rot:
+        np.testing.assert_allclose(grot, rot.grad.numpy(), rtol=1e-9, atol=1e-9)
+
+
+def test_oracle_geometry_gradcheck():
+    g = torch.Generator().manual_seed(7)
+    B, N = 2, 6
+    pts = (torch.randn(B, N, 3, generator=g, dtype=torch.float64) * 0.05).requires_grad_(True)
+    rot = (torch.randn(B, 3, generator=g, dtype=torch.float64) * 0.8).requires_grad_(True)
+    K, scale, trans = _camera(B, g)
+
+    def f(p, r, s, t):
+        o = ogeom.obj_branch(p, K, s, t, r, trans_factor=100.0, scale_factor=1e-4)
+        return o["obj_verts2d"], o["recov_objverts3d"], o["obj_verts3d"]
+
+    assert torch.autograd.gradcheck(f, (pts, rot, scale, trans), eps=1e-7, atol=1e-5)
