@@ -490,6 +490,81 @@ def gpu_ref_equiv(steps=3, warmup=1):
                     "with ATen grid_sample, on this GPU, same workload; NOT the upstream binary (not installable)"}
 
 
+def geom_head_leg(samples=None, iters=50):
+    """the geometry head in front of the path -- ManoAdaptor + centring + recover_3d_proj + both
+    projections of the hand (hoc_hand_head_*), Rodrigues + rotation + recover_3d_proj + projection of the object
+    (hoc_recover_points_*) -- forward + backward on one hand and one 1502-vertex object per rendered frame, inputs
+    resident, CUDA-event timed; beside it the reference's op-by-op ATen composition of the same (restated:
+    baseline/ref_equiv/geomhead.py).  Not part of `value`."""
+    import torch
+
+    from baseline.ref_equiv import geomhead as ref_head
+    from handobjectconsist_b200 import _lib, synth
+    from handobjectconsist_b200._geomhead import _HandHeadFunction, _RecoverPointsFunction
+
+    n = 2 * PAIRS if samples is None else samples
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator().manual_seed(0)
+    res, sf, tf = (float(SIZE), float(SIZE)), 1e-4, 100.0
+    K = synth.camera_intrinsics(n, SIZE, SIZE, dev)
+    verts = (torch.randn(n, 778, 3, generator=g) * 0.05).to(dev).requires_grad_(True)
+    can = (torch.randn(n, 1502, 3, generator=g) * 0.05).to(dev)
+    W = torch.rand(21, 778, generator=g)
+    W = (W / W.sum(1, keepdim=True)).to(dev)
+    lin = torch.nn.Linear(778, 21, bias=False).to(dev)
+    lin.weight.data = W
+    lin.weight.requires_grad_(False)
+    hst = (torch.randn(n, 3, generator=g) * 0.3).to(dev).requires_grad_(True)
+    ost = (torch.randn(n, 6, generator=g) * 0.3).to(dev).requires_grad_(True)
+    wv = torch.randn(n, 778, 3, generator=g).to(dev)
+    w2 = torch.randn(n, 778, 2, generator=g).to(dev)
+    wo = torch.randn(n, 1502, 3, generator=g).to(dev)
+    wo2 = torch.randn(n, 1502, 2, generator=g).to(dev)
+
+    def ours():
+        out = _HandHeadFunction.apply(verts, None, W, K, hst[:, 0], hst[:, 1:], 9, sf, tf, 0.4, *res)
+        obj = _RecoverPointsFunction.apply(can, ost[:, 3:], K, ost[:, 0], ost[:, 1:3], sf, tf, 0.4, *res)
+        loss = (out[3] * wv).sum() + (out[5] * w2).sum() + out[4].sum() + (obj[1] * wo).sum() + (obj[2] * wo2).sum()
+        torch.autograd.grad(loss, [verts, hst, ost])
+
+    def reference():
+        rj, rv, j2, v2 = ref_head.hand_head(verts, lin, 9, K, hst[:, :1], hst[:, 1:], sf, tf, res)
+        _, ov, o2 = ref_head.obj_head(can, K, ost[:, :1], ost[:, 1:3], ost[:, 3:], sf, tf, res)
+        loss = (rv * wv).sum() + (v2 * w2).sum() + j2.sum() + (ov * wo).sum() + (o2 * wo2).sum()
+        torch.autograd.grad(loss, [verts, hst, ost])
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(iters):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / iters * 1e3
+
+    us_ours, us_ref = timed(ours), timed(reference)
+    L = _lib.lib()
+    ids = _lib.KERNEL_IDS
+    names = ("hand_head_fwd", "hand_head_bwd", "recover_points_fwd", "recover_points_bwd")
+    L.hoc_timer_begin(sum(1 << ids[k] for k in names))
+    for _ in range(10):
+        ours()
+    torch.cuda.synchronize()
+    buf, kid = (ctypes.c_float * 64)(), (ctypes.c_int * 64)()
+    cnt = L.hoc_timer_end(buf, kid, 64)
+    k_us = {}
+    for j in range(cnt):
+        k_us.setdefault(kid[j], []).append(buf[j] * 1e3)
+    return {"samples": n, "fwd_bwd_us": us_ours, "ref_op_by_op_us": us_ref, "speedup": us_ref / us_ours,
+            "kernel_us": {k: (sum(k_us[ids[k]]) / len(k_us[ids[k]]) if k_us.get(ids[k]) else None) for k in names},
+            "note": "hand head (adaptor, centring, recover_3d_proj, 2 projections) + object head (Rodrigues, rotation, "
+                    "recover_3d_proj, projection), forward + backward, eager: 4 launches of this library against the "
+                    "reference's op-by-op ATen composition (restated, baseline/ref_equiv/geomhead.py); both launch-bound"}
+
+
 def mano_leg(hands=None, iters=50):
     """ManoLayer forward + backward (hoc_mano_forward / hoc_mano_backward) on one hand per rendered
     frame of the workload, inputs resident, CUDA-event timed.  Not part of `value` (the metric is render + warp +
@@ -632,6 +707,10 @@ def main():
                 out["mano"] = mano_leg()
             except Exception as exc:
                 out["mano"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            try:
+                out["geom_head"] = geom_head_leg()
+            except Exception as exc:
+                out["geom_head"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         _emit(out)

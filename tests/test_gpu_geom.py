@@ -195,3 +195,89 @@ def test_geometry_head_rejects_cpu_tensors_and_bad_shapes():
         recover_mano_geometry({"verts3d": torch.zeros(1, 10, 3).cuda(), "joints3d": torch.zeros(1, 21, 3).cuda()},
                               K.cuda(), torch.zeros(1, 1).cuda(), torch.zeros(1, 2).cuda(),
                               adaptor=torch.zeros(21, 778).cuda())
+
+
+def test_network_outputs_to_photometric_loss_and_back():
+    """Rows f1 -> a1 -> a14 chained: pose / shape -> ManoLayer -> ManoAdaptor + recover_3d_proj (hand head), object
+    scale / translation / rotation -> ObjBranch, both meshes -> warpbranch's consist step -> masked L1, and back to
+    every network output.  Checked in two links: (1) loss and the gradient that reaches the mesh vertices against the
+    oracle's pipeline run on the same vertices; (2) that vertex gradient pushed through the oracle's float64 front end
+    (MANO, adaptor, recover_3d_proj, Rodrigues) against the gradients the kernels return for the network outputs."""
+    from handobjectconsist_b200 import synth, warpbranch
+    from handobjectconsist_b200.mano.manolayer import ManoLayer
+    from handobjectconsist_b200.meshregnet import ManoAdaptor, recover_mano_geometry
+    from handobjectconsist_b200.neurender.renderer import Renderer
+    from handobjectconsist_b200.objbranch import ObjBranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+    from oracle import mano as omano
+    from oracle import pipeline as opipe
+
+    S, B, hv, sf, tf = 64, 2, 778, 1e-4, 100.0
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, S, seed=7)
+    model = synth.mano_model(seed=3)
+    layer = ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=15, use_pca=True, model=model).to(dev)
+    adaptor = ManoAdaptor(layer).to(dev)
+    for p_ in adaptor.parameters():
+        p_.requires_grad_(False)  # rec_freeze(self.adaptor), meshregnet.py:147
+    g = torch.Generator().manual_seed(5)
+    pose = torch.randn(B, 18, generator=g) * 0.4
+    betas = torch.randn(B, 10, generator=g) * 0.5
+    K = sc["K"]
+
+    def head_inputs(centre):
+        """scale / translation (network units) that put est_c3d at `centre` (inverse of project.py:15-20)."""
+        f, cc = K[:, 0, 0], K[:, :2, 2]
+        s = (centre[:, 2] - 0.4) / (f * sf)
+        t = (centre[:, :2] * (f / centre[:, 2])[:, None] - S / 2.0 + cc) / tf
+        return torch.cat([s[:, None], t], 1)
+
+    hand_st = head_inputs(sc["verts1"][:, :hv].mean(1))
+    obj_centre = sc["verts1"][:, hv:].mean(1)
+    can = sc["verts1"][:, hv:] - obj_centre[:, None]
+    obj_st = torch.cat([head_inputs(obj_centre), torch.randn(B, 3, generator=g) * 0.2], 1)
+
+    p, b, hs, os_ = [t.to(dev).requires_grad_(True) for t in (pose, betas, hand_st, obj_st)]
+    verts_mm, joints_mm = layer(p, th_betas=b)
+    mano_results = recover_mano_geometry({"verts3d": verts_mm / 1000, "joints3d": joints_mm / 1000}, K.to(dev),
+                                         hs[:, :1], hs[:, 1:], adaptor=adaptor, mano_center_idx=9, trans_factor=tf,
+                                         scale_factor=sf, input_res=(S, S))
+    sample = {BaseQueries.OBJCANVERTS: can, TransQueries.IMAGE: sc["image"], TransQueries.CAMINTR: K}
+    obj_results = ObjBranch(trans_factor=tf, scale_factor=sf)(sample, os_)
+    v1 = torch.cat([mano_results["recov_handverts3d"], obj_results["recov_objverts3d"]], 1)
+    v1.retain_grad()
+    gsc = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    renderer = Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                        K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True, near=0.1,
+                        no_light=True)
+    loss, _ = warpbranch.consist_step(v1, gsc["verts2"], gsc["faces"], gsc["K"], gsc["image_ref"], gsc["image"],
+                                      gsc["jitter_mask_ref"], gsc["jitter_mask"], renderer, PyramidCriterion("l1"),
+                                      (S, S), sc["hand_ignore_faces"], detach_renders=False, use_backward=True)
+    loss.backward()
+
+    # link 1: same vertices into the oracle's pipeline
+    c1 = v1.detach().cpu().clone().requires_grad_(True)
+    loss_o, _ = opipe.consist_step(c1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                   sc["jitter_mask_ref"], sc["jitter_mask"], S, (S, S), sc["hand_ignore_faces"],
+                                   detach_renders=False, use_backward=True, grad_dtype=np.float32, warp_device=dev)
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) <= 1e-4
+    gv = v1.grad.cpu()
+    assert gv[:, :hv].abs().max().item() > 0 and gv[:, hv:].abs().max().item() > 0
+    assert (gv - c1.grad).abs().max().item() <= 1e-3 * c1.grad.abs().max().item()
+
+    # link 2: the kernels' vertex gradient through the oracle's front end, float64
+    dbl = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in model.items()}
+    po, bo, hso, oso = [t.double().requires_grad_(True) for t in (pose, betas, hand_st, obj_st)]
+    vo, jo = omano.mano_forward(dbl, po, bo, None, True, 9)
+    ref_h = ogeom.recover_mano_geometry(vo / 1000, jo / 1000, K.double(), hso[:, :1], hso[:, 1:],
+                                        adaptor_weight=adaptor.J_regressor.double().cpu(), center_idx=9,
+                                        trans_factor=tf, scale_factor=sf, input_res=(S, S))
+    ref_o = ogeom.obj_branch(can.double(), K.double(), oso[:, :1], oso[:, 1:3], oso[:, 3:], trans_factor=tf,
+                             scale_factor=sf, input_res=(S, S))
+    vref = torch.cat([ref_h["recov_handverts3d"], ref_o["recov_objverts3d"]], 1)
+    _close(v1, vref, 2e-5)  # the MANO kernels' bar (test_gpu_mano.py: 1e-4 of the hand size in mm)
+    (vref * gv.double()).sum().backward()
+    for got, want in ((p, po), (b, bo), (hs, hso), (os_, oso)):
+        assert helpers.rel_err(got.grad.cpu().numpy(), want.grad.numpy()) < 1e-3
