@@ -203,17 +203,26 @@ hoc_hand_head_forward_kernel(const float *__restrict__ verts, const float *__res
             s_a[i] = joints_in[(long)b * J * 3 + i];
     __syncthreads();
     if (adaptor != nullptr) {
-        /* adapted joints = W . verts: a warp per output coordinate, lanes stride the vertices
-         * (W rows are contiguous over v: coalesced; s_v stride 3 words: conflict-free) */
-        for (int o = warp; o < J * 3; o += GH_WARPS) {
-            const int j = o / 3, c = o - 3 * j;
+        /* adapted joints = W . verts: a warp per joint, lanes stride the vertices (the row of W is read once,
+         * coalesced, and feeds three accumulators; s_v with a stride of 3 words: conflict-free) */
+        for (int j = warp; j < J; j += GH_WARPS) {
             const float *w = adaptor + (long)j * V;
-            float acc = 0.0f;
-            for (int v = lane; v < V; v += 32)
-                acc = __fmaf_rn(w[v], s_v[v * 3 + c], acc);
-            acc = hoc_warp_sum(acc);
-            if (lane == 0)
-                s_a[o] = acc;
+            float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 5
+            for (int v = lane; v < V; v += 32) {
+                const float wv = __ldg(w + v);
+                ax = __fmaf_rn(wv, s_v[v * 3], ax);
+                ay = __fmaf_rn(wv, s_v[v * 3 + 1], ay);
+                az = __fmaf_rn(wv, s_v[v * 3 + 2], az);
+            }
+            ax = hoc_warp_sum(ax);
+            ay = hoc_warp_sum(ay);
+            az = hoc_warp_sum(az);
+            if (lane == 0) {
+                s_a[j * 3] = ax;
+                s_a[j * 3 + 1] = ay;
+                s_a[j * 3 + 2] = az;
+            }
         }
         __syncthreads();
     }
@@ -375,12 +384,13 @@ hoc_hand_head_backward_kernel(const float *__restrict__ recov_verts, const float
             grad_adapt[(long)b * J * 3 + i] = s_ga[i];
     }
     if (grad_verts != nullptr) {
-        /* d verts = G_v3d + W^T d adapted: thread per vertex (W columns: coalesced over v), 8-byte... */
+        /* d verts = G_v3d + W^T d adapted: thread per vertex (W columns: coalesced over v) */
         for (int v = tid; v < V; v += GH_THREADS) {
             float ax = 0.f, ay = 0.f, az = 0.f;
             if (adaptor != nullptr)
+#pragma unroll 7
                 for (int j = 0; j < J; j++) {
-                    const float w = adaptor[(long)j * V + v];
+                    const float w = __ldg(adaptor + (long)j * V + v);
                     ax = __fmaf_rn(w, s_ga[j * 3], ax);
                     ay = __fmaf_rn(w, s_ga[j * 3 + 1], ay);
                     az = __fmaf_rn(w, s_ga[j * 3 + 2], az);
