@@ -66,7 +66,8 @@ class GraphedConsistStep:
         # fills in around it instead of delaying it
         self.capture_stream = torch.cuda.Stream(device=dev, priority=-1)
         with torch.cuda.graph(self.graph, stream=self.capture_stream):
-            self.loss, self.grad_hand, self.grad_obj = self._run()
+            self._captured = self._run()
+        self.loss, self.grad_hand, self.grad_obj = self._captured[:3]
 
     def _run(self):
         loss, _ = warpbranch.forward(self.samples, self.results, self.hand_face, self.renderer, self.image_size,
@@ -135,3 +136,52 @@ class _GraphedConsistFunction(Function):
     def backward(ctx, grad_loss):
         gh, go = ctx.saved_tensors
         return gh * grad_loss, go * grad_loss, None, None, None
+
+
+class GraphedHeadConsistStep(GraphedConsistStep):
+    """The captured step with the geometry head (and whatever else ``head`` runs: MANO skinning, ManoAdaptor,
+    recover_3d_proj, ObjBranch) INSIDE the graph: network outputs -> loss -> gradients of the network outputs in
+    one replay, instead of a launch-bound eager front end (~1 ms of Python for ~0.1 ms of kernels) in front of it.
+
+    ``head(inputs)`` maps a dict of device tensors (pose, shape, scale / translation / rotation heads, canonical object
+    vertices ...) to ``(recov_handverts3d, recov_objverts3d)`` of the first frame -- what MeshRegNet.recover_mano /
+    recover_object produce (/root/reference/meshreg/models/meshregnet.py:179-272) -- using capturable operators only
+    (no host synchronisation, no host-to-device copies: everything it reads lives on the device).
+    ``head_inputs`` is an example dict that fixes shapes; every floating-point entry gets a gradient
+    (``head_grads[name]``), other entries are constants of the step.  ``all_results[0]`` must hold example
+    ``recov_handverts3d`` / ``recov_objverts3d`` at construction (shapes); batches loaded later need not."""
+
+    def __init__(self, head, head_inputs, renderer, criterion, image_size, hand_face, samples, all_results, **kw):
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.head = head
+        self.head_inputs = {k: v.detach().to(dev).clone().requires_grad_(v.is_floating_point())
+                            for k, v in head_inputs.items()}
+        self._grad_keys = [k for k, v in self.head_inputs.items() if v.requires_grad]
+        super().__init__(renderer, criterion, image_size, hand_face, samples, all_results, **kw)
+        self.head_grads = dict(zip(self._grad_keys, self._captured[3:]))
+        # the first frame's vertices now come from the head: later batches need not carry them
+        for key in ("recov_handverts3d", "recov_objverts3d"):
+            self.results[0].pop(key, None)
+
+    def _run(self):
+        hand, obj = self.head(self.head_inputs)
+        results = [dict(self.results[0], recov_handverts3d=hand, recov_objverts3d=obj)] + self.results[1:]
+        loss, _ = warpbranch.forward(self.samples, results, self.hand_face, self.renderer, self.image_size,
+                                     self.criterion, **self.kw)
+        wrt = [hand, obj] + [self.head_inputs[k] for k in self._grad_keys]
+        grads = torch.autograd.grad(loss, wrt, grad_outputs=self._one, allow_unused=True)
+        return (loss.detach(),) + tuple(torch.zeros_like(w) if g is None else g for g, w in zip(grads, wrt))
+
+    def load(self, samples, all_results, head_inputs=None):
+        super().load(samples, all_results)
+        if head_inputs is not None:
+            with torch.no_grad():
+                for k, buf in self.head_inputs.items():
+                    buf.copy_(head_inputs[k].detach(), non_blocking=True)
+
+    def __call__(self, samples, all_results, head_inputs=None):
+        """Returns the static ``(loss, head_grads)``; ``grad_hand`` / ``grad_obj`` (gradients that reach the mesh
+        vertices) stay available as attributes."""
+        self.load(samples, all_results, head_inputs)
+        self.graph.replay()
+        return self.loss, self.head_grads

@@ -281,3 +281,95 @@ def test_network_outputs_to_photometric_loss_and_back():
     (vref * gv.double()).sum().backward()
     for got, want in ((p, po), (b, bo), (hs, hso), (os_, oso)):
         assert helpers.rel_err(got.grad.cpu().numpy(), want.grad.numpy()) < 1e-3
+
+
+def test_graphed_step_with_the_head_inside_matches_eager():
+    """GraphedHeadConsistStep: MANO + ManoAdaptor + recover_3d_proj + ObjBranch + the consistency step, forward and
+    backward, captured in ONE CUDA graph -- same loss and the same gradients of the network outputs as the eager
+    chain, also after loading other network outputs into its static buffers."""
+    from handobjectconsist_b200 import synth, warpbranch
+    from handobjectconsist_b200.graphed import GraphedHeadConsistStep
+    from handobjectconsist_b200.mano.manolayer import ManoLayer
+    from handobjectconsist_b200.meshregnet import recover_mano_geometry
+    from handobjectconsist_b200.neurender.renderer import Renderer
+    from handobjectconsist_b200.objbranch import ObjBranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+
+    S, B, hv, sf, tf = 64, 2, 778, 1e-4, 100.0
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, S, seed=20)
+    layer = ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=15, use_pca=True, model=synth.mano_model(seed=3)).to(dev)
+    g = torch.Generator().manual_seed(9)
+    W = torch.rand(21, hv, generator=g) * (torch.rand(21, hv, generator=g) > 0.9).float()
+    W = (W / W.sum(1, keepdim=True)).to(dev)
+    K = sc["K"]
+    f, cc = K[:, 0, 0], K[:, :2, 2]
+
+    def head_units(centre):
+        s = (centre[:, 2] - 0.4) / (f * sf)
+        t = (centre[:, :2] * (f / centre[:, 2])[:, None] - S / 2.0 + cc) / tf
+        return torch.cat([s[:, None], t], 1)
+
+    obj_centre = sc["verts1"][:, hv:].mean(1)
+    can = (sc["verts1"][:, hv:] - obj_centre[:, None]).to(dev)
+    Kd = K.to(dev)
+    obj_branch = ObjBranch(trans_factor=tf, scale_factor=sf)
+    shape_only = torch.empty(0, 0, S, S)
+
+    def head(inp):
+        verts_mm, joints_mm = layer(inp["pose"], th_betas=inp["betas"])
+        hand = recover_mano_geometry({"verts3d": verts_mm / 1000, "joints3d": joints_mm / 1000}, Kd,
+                                     inp["hand_st"][:, :1], inp["hand_st"][:, 1:], adaptor=W, mano_center_idx=9,
+                                     trans_factor=tf, scale_factor=sf, input_res=(S, S))["recov_handverts3d"]
+        sample = {BaseQueries.OBJCANVERTS: can, TransQueries.IMAGE: shape_only, TransQueries.CAMINTR: Kd}
+        return hand, obj_branch(sample, inp["obj_st"])["recov_objverts3d"]
+
+    def net_outputs(seed):
+        gg = torch.Generator().manual_seed(seed)
+        return {"pose": torch.randn(B, 18, generator=gg) * 0.4, "betas": torch.randn(B, 10, generator=gg) * 0.5,
+                "hand_st": head_units(sc["verts1"][:, :hv].mean(1)) + torch.randn(B, 3, generator=gg) * 0.02,
+                "obj_st": torch.cat([head_units(obj_centre), torch.randn(B, 3, generator=gg) * 0.2], 1)}
+
+    mv = lambda t: t.to(dev)
+    obj_faces = mv(sc["faces"][:, 1552:] - hv)
+    samples = []
+    for verts, img, jit in ((sc["verts1"], sc["image_ref"], sc["jitter_mask_ref"]),
+                            (sc["verts2"], sc["image"], sc["jitter_mask"])):
+        samples.append({TransQueries.IMAGE: mv(img), TransQueries.JITTERMASK: mv(jit), TransQueries.CAMINTR: Kd,
+                        BaseQueries.OBJFACES: obj_faces, BaseQueries.OBJVERTS3D: mv(verts[:, hv:]),
+                        BaseQueries.HANDVERTS3D: mv(verts[:, :hv])})
+    hand_face = sc["faces"][0, :1552].to(dev)
+    crit = PyramidCriterion("l1")
+    # the second frame's entry is read and then replaced by ground truth (gt_refs, warpbranch.py:38-44)
+    second = {"recov_handverts3d": mv(sc["verts2"][:, :hv]), "recov_objverts3d": mv(sc["verts2"][:, hv:])}
+
+    def renderer():
+        return Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                        K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True, near=0.1,
+                        no_light=True)
+
+    def eager(outs):
+        inp = {k: v.to(dev).requires_grad_(True) for k, v in outs.items()}
+        hand, obj = head(inp)
+        loss, _ = warpbranch.forward(samples, [{"recov_handverts3d": hand, "recov_objverts3d": obj}, second], hand_face,
+                                     renderer(), (S, S), crit, hand_ignore_faces=sc["hand_ignore_faces"],
+                                     detach_renders=False)
+        loss.backward()
+        return loss.detach(), {k: v.grad for k, v in inp.items()}, hand.detach(), obj.detach()
+
+    first = net_outputs(1)
+    _, _, hand0, obj0 = eager(first)
+    gstep = GraphedHeadConsistStep(head, first, renderer(), crit, (S, S), hand_face, samples,
+                                   [{"recov_handverts3d": hand0, "recov_objverts3d": obj0}, second],
+                                   hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)
+    for seed in (1, 2, 3):
+        outs = net_outputs(seed)
+        loss_g, grads_g = gstep(samples, [{}, second], outs)
+        loss_g, grads_g = loss_g.clone(), {k: v.clone() for k, v in grads_g.items()}
+        loss_e, grads_e, _, _ = eager(outs)
+        assert loss_e.item() > 0 and abs(loss_g.item() - loss_e.item()) <= 1e-6
+        assert set(grads_g) == {"pose", "betas", "hand_st", "obj_st"}
+        for k in grads_g:
+            assert grads_e[k].abs().max().item() > 0
+            assert helpers.rel_err(grads_g[k].cpu().numpy(), grads_e[k].cpu().numpy()) < 1e-4, k
