@@ -565,6 +565,107 @@ def geom_head_leg(samples=None, iters=50):
                     "reference's op-by-op ATen composition (restated, baseline/ref_equiv/geomhead.py); both launch-bound"}
 
 
+def head_graph_leg(iters=30):
+    """Network outputs -> MANO -> geometry head -> consistency step -> gradients of the network outputs, three ways on
+    the bench workload: ONE captured graph (graphed.GraphedHeadConsistStep), the eager front end around the captured
+    consistency step (GraphedConsistStep.apply: what a training loop did before the head could be captured), and
+    everything eager.  Not part of `value` (the metric is render + warp + photometric from camera-space meshes)."""
+    import torch
+
+    from handobjectconsist_b200 import synth, warpbranch
+    from handobjectconsist_b200.graphed import GraphedConsistStep, GraphedHeadConsistStep
+    from handobjectconsist_b200.mano.manolayer import ManoLayer
+    from handobjectconsist_b200.meshregnet import recover_mano_geometry
+    from handobjectconsist_b200.neurender.renderer import Renderer
+    from handobjectconsist_b200.objbranch import ObjBranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, S, hv, sf, tf = PAIRS, SIZE, 778, 1e-4, 100.0
+    sc = _make_sets(1, B, S, dev)[0]
+    samples, results = _samples_from_scene(sc)
+    hand_face, ignore = sc["faces"][0, :1552].clone(), sc["hand_ignore_faces"]
+    layer = ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=15, use_pca=True, model=synth.mano_model(seed=3)).to(dev)
+    g = torch.Generator().manual_seed(0)
+    W = torch.rand(21, hv, generator=g) * (torch.rand(21, hv, generator=g) > 0.9).float()
+    W = (W / W.sum(1, keepdim=True)).to(dev)
+    K = sc["K"]
+    f, cc = K[:, 0, 0], K[:, :2, 2]
+
+    def units(centre):  # scale / translation heads that put est_c3d at `centre` (inverse of project.py:15-20)
+        s = (centre[:, 2] - 0.4) / (f * sf)
+        t = (centre[:, :2] * (f / centre[:, 2])[:, None] - S / 2.0 + cc) / tf
+        return torch.cat([s[:, None], t], 1)
+
+    obj_centre = sc["verts1"][:, hv:].mean(1)
+    can = (sc["verts1"][:, hv:] - obj_centre[:, None]).contiguous()
+    obj_branch = ObjBranch(trans_factor=tf, scale_factor=sf)
+    shape_only = torch.empty(0, 0, S, S)
+    inputs = {"pose": (torch.randn(B, 18, generator=g) * 0.4).to(dev), "betas": (torch.randn(B, 10, generator=g) * 0.5).to(dev),
+              "hand_st": units(sc["verts1"][:, :hv].mean(1)),
+              "obj_st": torch.cat([units(obj_centre), (torch.randn(B, 3, generator=g) * 0.2).to(dev)], 1)}
+
+    def head(inp):
+        verts_mm, joints_mm = layer(inp["pose"], th_betas=inp["betas"])
+        hand = recover_mano_geometry({"verts3d": verts_mm / 1000, "joints3d": joints_mm / 1000}, K, inp["hand_st"][:, :1],
+                                     inp["hand_st"][:, 1:], adaptor=W, mano_center_idx=9, trans_factor=tf,
+                                     scale_factor=sf, input_res=(S, S))["recov_handverts3d"]
+        sample = {BaseQueries.OBJCANVERTS: can, TransQueries.IMAGE: shape_only, TransQueries.CAMINTR: K}
+        return hand, obj_branch(sample, inp["obj_st"])["recov_objverts3d"]
+
+    def renderer():
+        return Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                        K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True, near=0.1,
+                        no_light=True)
+
+    crit = PyramidCriterion("l1")
+    kw = dict(hand_ignore_faces=ignore, gt_refs=True, first_only=True, use_backward=True, detach_renders=False)
+    with torch.no_grad():
+        hand0, obj0 = head(inputs)
+    example = [{"recov_handverts3d": hand0, "recov_objverts3d": obj0}, results[1]]
+    full = GraphedHeadConsistStep(head, inputs, renderer(), crit, (S, S), hand_face, samples, example, warmup=1, **kw)
+    part = GraphedConsistStep(renderer(), crit, (S, S), hand_face, samples, example, warmup=1, **kw)
+    rend = renderer()
+
+    def leaves():
+        return {k: v.detach().requires_grad_(True) for k, v in inputs.items()}
+
+    def eager_head_graphed_step():
+        inp = leaves()
+        hand, obj = head(inp)
+        part.apply(samples, [{"recov_handverts3d": hand, "recov_objverts3d": obj}, results[1]]).backward()
+
+    def all_eager():
+        inp = leaves()
+        hand, obj = head(inp)
+        loss, _ = warpbranch.forward(samples, [{"recov_handverts3d": hand, "recov_objverts3d": obj}, results[1]],
+                                     hand_face, rend, (S, S), crit, **kw)
+        loss.backward()
+
+    def timed(fn):
+        for _ in range(5):
+            fn()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0.record()
+        for _ in range(iters):
+            fn()
+        t1.record()
+        torch.cuda.synchronize()
+        return t0.elapsed_time(t1) / iters
+
+    ms_full = timed(full.graph.replay)
+    ms_part = timed(eager_head_graphed_step)
+    ms_eager = timed(all_eager)
+    return {"pairs": B, "graphed_with_head_ms": ms_full, "eager_head_plus_graphed_step_ms": ms_part,
+            "all_eager_ms": ms_eager, "frames_per_s_graphed_with_head": 2 * B / (ms_full / 1e3),
+            "loss": float(full.loss),
+            "note": "network outputs (pose, shape, scale / translation / rotation heads) -> ManoLayer -> ManoAdaptor + "
+                    "recover_3d_proj -> ObjBranch -> consistency step -> gradients of the network outputs; "
+                    "GraphedHeadConsistStep replays all of it as one CUDA graph"}
+
+
 def mano_leg(hands=None, iters=50):
     """ManoLayer forward + backward (hoc_mano_forward / hoc_mano_backward) on one hand per rendered
     frame of the workload, inputs resident, CUDA-event timed.  Not part of `value` (the metric is render + warp +
@@ -711,6 +812,10 @@ def main():
                 out["geom_head"] = geom_head_leg()
             except Exception as exc:
                 out["geom_head"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+            try:
+                out["head_graph"] = head_graph_leg()
+            except Exception as exc:
+                out["head_graph"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         _emit(out)
