@@ -125,3 +125,43 @@ def test_oracle_geometry_gradcheck():
         return o["obj_verts2d"], o["recov_objverts3d"], o["obj_verts3d"]
 
     assert torch.autograd.gradcheck(f, (pts, rot, scale, trans), eps=1e-7, atol=1e-5)
+
+
+def test_mano_adaptor_initialisation_follows_the_reference():
+    """ManoAdaptor built from a ManoLayer (meshregnet.py:34-45): the 16 regressor rows + 5 one-hot fingertip rows in
+    the reference's 21-joint order; built from a pickle (meshregnet.py:27-33): the stored [21,778] matrix."""
+    import pickle
+    import tempfile
+
+    from handobjectconsist_b200 import synth
+    from handobjectconsist_b200.mano.manolayer import ManoLayer
+    from handobjectconsist_b200.meshregnet import ManoAdaptor
+
+    model = synth.mano_model(seed=3)
+    layer = ManoLayer(center_idx=9, flat_hand_mean=False, ncomps=15, use_pca=True, model=model)
+    ad = ManoAdaptor(layer)
+    reg = ad.J_regressor
+    assert reg.shape == (21, 778) and ad.adaptor.weight.shape == (21, 778)
+    for pos, vert in zip((4, 8, 12, 16, 20), (745, 317, 444, 556, 673)):
+        row = torch.zeros(778)
+        row[vert] = 1
+        assert torch.equal(reg[pos], row)
+    order = [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]
+    for pos, src in enumerate(order):
+        if src < 16:
+            assert torch.equal(reg[pos], model["j_regressor"][src])
+    assert torch.equal(ad.pinned_weight().detach(), reg)
+    # drifted wrist / fingertip rows are reset by pinned_weight (meshregnet.py:48-50), the others are kept
+    with torch.no_grad():
+        ad.adaptor.weight.add_(0.5)
+    w = ad.pinned_weight().detach()
+    assert torch.equal(w[[0, 4, 8, 12, 16, 20]], reg[[0, 4, 8, 12, 16, 20]])
+    assert torch.allclose(w[1], reg[1] + 0.5)
+    with tempfile.NamedTemporaryFile(suffix=".pkl") as fh:
+        stored = np.random.default_rng(0).random((21, 778)).astype(np.float32)
+        pickle.dump({"adaptor": stored, "shape": np.zeros(10)}, fh)
+        fh.flush()
+        ad2 = ManoAdaptor(None, load_path=fh.name)
+    assert torch.equal(ad2.J_regressor, torch.from_numpy(stored)) and torch.equal(ad2.adaptor.weight.detach(), ad2.J_regressor)
+    with pytest.raises(TypeError):
+        ad2(torch.zeros(1, 778, 3))  # CPU tensor: no CPU path
