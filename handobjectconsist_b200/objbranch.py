@@ -1,11 +1,12 @@
 """``ObjBranch`` with the interface of /root/reference/meshreg/models/objbranch.py:10-81: predicted scale /
 2-D translation / axis-angle rotation + the canonical object vertices of the sample -> object vertices in the
 camera frame and their projections.  batch_rodrigues, the rotation, recover_3d_proj and batch_proj2d are ONE
-launch per direction (``hoc_recover_points_forward/backward``)."""
+launch per direction (``hoc_recover_points_forward/backward``).  Like ``warpbranch.forward`` the sample may be keyed by
+the reference's own ``BaseQueries`` / ``TransQueries`` enums or by ours: the lookup goes by member NAME."""
 from torch import nn
 
 from ._geomhead import _RecoverPointsFunction
-from .queries import BaseQueries, TransQueries
+from .warpbranch import _base, _trans
 
 
 class ObjBranch(nn.Module):
@@ -28,8 +29,8 @@ class ObjBranch(nn.Module):
         if rotaxisang is None:
             rotaxisang = scaletrans[:, 3:]
         dev = rotaxisang.device
-        height, width = tuple(sample[TransQueries.IMAGE].shape[2:])
-        camintr = sample[TransQueries.CAMINTR].to(dev)
+        height, width = tuple(_trans(sample, "IMAGE").shape[2:])
+        camintr = _trans(sample, "CAMINTR").to(dev)
         consts = (float(self.scale_factor), float(self.trans_factor), 0.4, float(width), float(height))
         flat_scale, flat_trans = scale.reshape(batch_size), trans.reshape(batch_size, 2)
 
@@ -37,9 +38,9 @@ class ObjBranch(nn.Module):
             return _RecoverPointsFunction.apply(points.to(dev).float(), rotaxisang, camintr, flat_scale, flat_trans,
                                                 *consts)
 
-        rotobjverts, objverts3d, pred_objverts2d, center3d = head(sample[BaseQueries.OBJCANVERTS])
-        if BaseQueries.OBJCORNERS3D in sample:
-            rotobjcorners, recov_objcorners3d, pred_objcorners2d, _ = head(sample[BaseQueries.OBJCANCORNERS])
+        rotobjverts, objverts3d, pred_objverts2d, center3d = head(_base(sample, "OBJCANVERTS"))
+        if any(getattr(key, "name", key) == "OBJCORNERS3D" and type(key).__name__ == "BaseQueries" for key in sample):
+            rotobjcorners, recov_objcorners3d, pred_objcorners2d, _ = head(_base(sample, "OBJCANCORNERS"))
         else:
             pred_objcorners2d = recov_objcorners3d = rotobjcorners = None
         return {

@@ -165,3 +165,103 @@ def test_mano_adaptor_initialisation_follows_the_reference():
     assert torch.equal(ad2.J_regressor, torch.from_numpy(stored)) and torch.equal(ad2.adaptor.weight.detach(), ad2.J_regressor)
     with pytest.raises(TypeError):
         ad2(torch.zeros(1, 778, 3))  # CPU tensor: no CPU path
+
+
+def test_obj_branch_host_logic_with_foreign_query_enums(monkeypatch):
+    """ObjBranch's host side (argument handling, sample lookup by member NAME so that a batch keyed by the reference's
+    own enums works, result dict) with the kernel call replaced by the oracle -- no GPU involved."""
+    from enum import Enum, auto
+
+    from handobjectconsist_b200 import objbranch
+
+    class BaseQueries(Enum):  # stands for meshreg.datasets.queries.BaseQueries: same member names, another class
+        OBJCANVERTS = auto()
+        OBJCANCORNERS = auto()
+        OBJCORNERS3D = auto()
+
+    class TransQueries(Enum):
+        IMAGE = auto()
+        CAMINTR = auto()
+
+    class FakeFunction:
+        @staticmethod
+        def apply(points, rot, camintr, scale, trans, scale_factor, trans_factor, off_z, res_w, res_h):
+            assert off_z == 0.4 and scale.shape == (points.shape[0],) and trans.shape == (points.shape[0], 2)
+            o = ogeom.obj_branch(points, camintr, scale, trans, rot, trans_factor=trans_factor,
+                                 scale_factor=scale_factor, input_res=(res_w, res_h))
+            return o["obj_verts3d"], o["recov_objverts3d"], o["obj_verts2d"], o["center3d"].reshape(-1, 3)
+
+    monkeypatch.setattr(objbranch, "_RecoverPointsFunction", FakeFunction)
+    g = torch.Generator().manual_seed(2)
+    B = 3
+    can = torch.randn(B, 12, 3, generator=g) * 0.05
+    corners = torch.randn(B, 8, 3, generator=g) * 0.05
+    K = torch.tensor([[[400.0, 0, 128], [0, 400.0, 96], [0, 0, 1]]]).repeat(B, 1, 1)
+    st = torch.cat([torch.randn(B, 1, generator=g), torch.randn(B, 2, generator=g) * 0.3,
+                    torch.randn(B, 3, generator=g)], 1)
+    sample = {BaseQueries.OBJCANVERTS: can.double(), BaseQueries.OBJCANCORNERS: corners, BaseQueries.OBJCORNERS3D: corners,
+              TransQueries.IMAGE: torch.zeros(B, 3, 192, 256), TransQueries.CAMINTR: K}
+    branch = objbranch.ObjBranch(trans_factor=100, scale_factor=0.0001)
+    want = ogeom.obj_branch(can, K, st[:, :1], st[:, 1:3], st[:, 3:], corners, trans_factor=100, scale_factor=0.0001,
+                            input_res=(256, 192))
+    for out in (branch(sample, st), branch(sample, None, scale=st[:, :1], trans=st[:, 1:3], rotaxisang=st[:, 3:])):
+        assert set(out) == {"obj_verts2d", "obj_verts3d", "recov_objverts3d", "recov_objcorners3d", "obj_scale",
+                            "obj_prescale", "obj_prerot", "obj_trans", "obj_pretrans", "obj_corners2d", "obj_corners3d"}
+        for k in ("obj_verts2d", "obj_verts3d", "recov_objverts3d", "recov_objcorners3d", "obj_corners2d",
+                  "obj_corners3d", "obj_scale", "obj_trans"):
+            assert out[k].shape == want[k].shape and torch.allclose(out[k], want[k]), k
+        assert out["obj_prescale"].shape == (B, 1) and out["obj_pretrans"].shape == (B, 2) and out["obj_prerot"].shape == (B, 3)
+    del sample[BaseQueries.OBJCORNERS3D]
+    out = branch(sample, st)
+    assert out["obj_corners2d"] is None and out["recov_objcorners3d"] is None and out["obj_corners3d"] is None
+
+
+@pytest.mark.parametrize("with_adaptor", [True, False])
+def test_recover_mano_geometry_host_logic(monkeypatch, with_adaptor):
+    """recover_mano_geometry / recover_3d_proj host side (shapes handed to the kernels, centring switch, result keys)
+    with the kernel calls replaced by the oracle -- no GPU involved."""
+    from handobjectconsist_b200 import meshregnet, project
+
+    class FakeHandHead:
+        @staticmethod
+        def apply(verts, joints_in, weight, camintr, scale, trans, center_idx, scale_factor, trans_factor, off_z, res_w,
+                  res_h):
+            B = verts.shape[0]
+            assert off_z == 0.4 and scale.shape == (B,) and trans.shape == (B, 2)
+            assert (joints_in is None) == (weight is not None) and (center_idx == -1) == (weight is None)
+            o = ogeom.recover_mano_geometry(verts, joints_in, camintr, scale, trans, adaptor_weight=weight,
+                                            center_idx=center_idx, trans_factor=trans_factor, scale_factor=scale_factor,
+                                            input_res=(res_w, res_h))
+            return (o["joints3d"], o["verts3d"], o["recov_joints3d"], o["recov_handverts3d"], o["joints2d"],
+                    o["verts2d"], o["center3d"].reshape(B, 3))
+
+    class FakeRecover:
+        @staticmethod
+        def apply(points, rot, camintr, scale, trans, scale_factor, trans_factor, off_z, res_w, res_h):
+            assert rot is None and scale_factor == 1.0 and trans_factor == 1.0
+            rec, c3d = ogeom.recover_3d_proj(points, camintr, scale, trans, off_z=off_z, input_res=(res_w, res_h))
+            return None, rec, None, c3d.reshape(-1, 3)
+
+    monkeypatch.setattr(meshregnet, "_HandHeadFunction", FakeHandHead)
+    monkeypatch.setattr(project, "_RecoverPointsFunction", FakeRecover)
+    g = torch.Generator().manual_seed(4)
+    B = 2
+    verts = torch.randn(B, 778, 3, generator=g) * 0.05
+    joints = torch.randn(B, 21, 3, generator=g) * 0.05
+    W = torch.rand(21, 778, generator=g) / 778 if with_adaptor else None
+    K = torch.tensor([[[400.0, 0, 128], [0, 400.0, 96], [0, 0, 1]]]).repeat(B, 1, 1)
+    scale, trans = torch.randn(B, 1, generator=g), torch.randn(B, 2, generator=g) * 0.3
+    out = meshregnet.recover_mano_geometry({"verts3d": verts, "joints3d": joints, "shape": "kept"}, K, scale, trans,
+                                           adaptor=W, mano_center_idx=9, trans_factor=100, scale_factor=0.0001,
+                                           input_res=(256, 192))
+    want = ogeom.recover_mano_geometry(verts, joints, K, scale, trans, adaptor_weight=W, center_idx=9, trans_factor=100,
+                                       scale_factor=0.0001, input_res=(256, 192))
+    assert out["shape"] == "kept" and out["hand_pretrans"] is trans and out["hand_prescale"] is scale
+    for k in ("joints3d", "verts3d", "joints2d", "recov_joints3d", "recov_handverts3d", "verts2d", "hand_trans",
+              "hand_scale"):
+        assert out[k].shape == want[k].shape and torch.allclose(out[k], want[k]), k
+    # recover_3d_proj: the reference's argument shapes ([B,1,1] scale, [B,1,2] translation) and return shapes
+    rec, c3d = project.recover_3d_proj(joints, K, scale.view(B, 1, 1) * 1e-4, trans.unsqueeze(1) * 100, input_res=(256, 192))
+    wrec, wc3d = ogeom.recover_3d_proj(joints, K, scale.view(B, 1, 1) * 1e-4, trans.unsqueeze(1) * 100, input_res=(256, 192))
+    assert rec.shape == (B, 21, 3) and c3d.shape == (B, 1, 3)
+    assert torch.allclose(rec, wrec) and torch.allclose(c3d, wc3d)
