@@ -17,6 +17,9 @@ HOC_LAYOUT_TEX_VERTEX = 0x200
 HOC_LAYOUT_SPARSE_SAVED = 0x400
 HOC_TEX_GRAD_CUBE = 0
 HOC_TEX_GRAD_VERTEX = 1
+HOC_TUNE_LINE_THREADS = 1
+HOC_TUNE_LINE_SEGMENT = 2
+HOC_TUNE_DETERMINISTIC = 3
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
 _vp = ctypes.c_void_p
@@ -42,6 +45,9 @@ SIGNATURES = {
     "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "hoc_raster_backward_workspace_bytes_ex": (_sz, [_i, _i, _i, _i, _i]),
+    "hoc_mesh_scatter_workspace_bytes": (_sz, [_i, _i]),
+    "hoc_mesh_scatter_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "hoc_set_tuning": (_i, [_i, _i]),
     "hoc_unpack_u8": (_i, [_vp, _vp, ctypes.c_longlong, _f, _f, _vp]),
     "hoc_flow_finalize_backward_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -115,6 +121,23 @@ def lib():
             fn.argtypes = args
         _LIB = L
     return _LIB
+
+
+class deterministic:
+    """Context manager / switch of the library's reproducible mode (``HOC_TUNE_DETERMINISTIC``, include/hoc_b200.h):
+    gradient sums are accumulated in 128-bit fixed point with integer atomics, so that two runs -- or a captured
+    graph and the eager path -- give the same bits.  Slower; meant for tests and debugging.  Process-wide."""
+
+    def __init__(self, on=True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        check(lib().hoc_set_tuning(HOC_TUNE_DETERMINISTIC, int(self.on)), "hoc_set_tuning")
+        return self
+
+    def __exit__(self, *exc):
+        check(lib().hoc_set_tuning(HOC_TUNE_DETERMINISTIC, 0), "hoc_set_tuning")
+        return False
 
 
 def check(code, what):

@@ -17,6 +17,7 @@
  *   hoc_flow_finalize_backward   grad of the flows -> grad of the rendered rgb maps
  */
 #include "hoc_common.cuh"
+#include "hoc_det.cuh"
 
 #define FP_THREADS 256
 
@@ -51,7 +52,9 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
             i0 = i2;
             i2 = t;
         }
-        const long long iv[3] = {i0, i1, i2};
+        /* precondition 0 <= index < V (include/hoc_b200.h); a bad table must not read out of bounds */
+        const long long iv[3] = {(i0 >= 0 && i0 < V) ? i0 : 0, (i1 >= 0 && i1 < V) ? i1 : 0,
+                                 (i2 >= 0 && i2 < V) ? i2 : 0};
         float c[3][3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -105,7 +108,8 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
 __global__ void __launch_bounds__(FP_THREADS)
 hoc_mesh_scatter_kernel(const float *__restrict__ grad_faces, const float *__restrict__ grad_tex,
                         const long long *__restrict__ faces_idx, int V, int F, int fill_back, int tex_grad_mode,
-                        float *__restrict__ grad_verts, float *__restrict__ grad_attrs)
+                        float *__restrict__ grad_verts, float *__restrict__ grad_attrs,
+                        unsigned long long *__restrict__ det_v, unsigned long long *__restrict__ det_a)
 {
     const int Fo = fill_back ? 2 * F : F;
     const int fo = blockIdx.x * FP_THREADS + threadIdx.x;
@@ -169,19 +173,20 @@ hoc_mesh_scatter_kernel(const float *__restrict__ grad_faces, const float *__res
     const long long iv[3] = {i0, i1, i2};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
+        if (iv[k] < 0 || iv[k] >= V)
+            continue; /* precondition violated: skip instead of writing out of bounds */
+        const long dst = ((long)b * V + iv[k]) * 3;
         if (any) {
-            float *dst = grad_verts + ((long)b * V + iv[k]) * 3;
 #pragma unroll
             for (int d = 0; d < 3; d++)
                 if (gf[3 * k + d] != 0.0f)
-                    atomicAdd(dst + d, gf[3 * k + d]);
+                    hoc_accum(grad_verts, dst + d, gf[3 * k + d], det_v);
         }
         if (any_t) {
-            float *dst = grad_attrs + ((long)b * V + iv[k]) * 3;
 #pragma unroll
             for (int ch = 0; ch < 3; ch++)
                 if (gc[k][ch] != 0.0f)
-                    atomicAdd(dst + ch, gc[k][ch]);
+                    hoc_accum(grad_attrs, dst + ch, gc[k][ch], det_a);
         }
     }
 }
@@ -609,9 +614,26 @@ extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, con
     return HOC_OK;
 }
 
+extern "C" size_t hoc_mesh_scatter_workspace_bytes(int B, int V)
+{
+    return (g_hoc_deterministic != 0 && B > 0 && V > 0) ? 2 * 16 * 3 * (size_t)B * V : 0;
+}
+
+extern "C" int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx,
+                                   int B, int V, int F, int fill_back, int tex_grad_mode, float *grad_verts,
+                                   float *grad_attrs, void *workspace, size_t workspace_bytes, void *stream);
+
 extern "C" int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B,
                                 int V, int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs,
                                 void *stream)
+{
+    return hoc_mesh_scatter_ws(grad_faces, grad_textures, faces_idx, B, V, F, fill_back, tex_grad_mode, grad_verts,
+                               grad_attrs, nullptr, 0, stream);
+}
+
+extern "C" int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx,
+                                   int B, int V, int F, int fill_back, int tex_grad_mode, float *grad_verts,
+                                   float *grad_attrs, void *workspace, size_t workspace_bytes, void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && V >= 0 && F >= 0, "hoc_mesh_scatter: bad shape B=%d V=%d F=%d", B, V, F);
     HOC_CHECK_ARG(B <= 65535, "hoc_mesh_scatter: batch %d exceeds 65535", B);
@@ -635,12 +657,36 @@ extern "C" int hoc_mesh_scatter(const float *grad_faces, const float *grad_textu
     if (F == 0)
         return HOC_OK;
     HOC_CHECK_ARG(faces_idx != nullptr, "hoc_mesh_scatter: faces_idx NULL");
+    unsigned long long *det_v = nullptr, *det_a = nullptr;
+    const size_t need = hoc_mesh_scatter_workspace_bytes(B, V);
+    if (need > 0) { /* reproducible mode */
+        if (workspace == nullptr || workspace_bytes < need) {
+            hoc_set_error("hoc_mesh_scatter: reproducible mode needs a workspace of %zu bytes (hoc_mesh_scatter_ws), %zu given",
+                          need, workspace_bytes);
+            return HOC_ERR_WORKSPACE;
+        }
+        if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) {
+            hoc_set_error("hoc_mesh_scatter: memset of the accumulators failed");
+            return HOC_ERR_CUDA;
+        }
+        det_v = (unsigned long long *)workspace;
+        det_a = det_v + 2 * 3 * (size_t)B * V;
+    }
     const int Fo = fill_back ? 2 * F : F;
     dim3 grid((Fo + FP_THREADS - 1) / FP_THREADS, B);
     HOC_LAUNCH(HOC_K_MESH_SCATTER, st,
                (hoc_mesh_scatter_kernel<<<grid, FP_THREADS, 0, st>>>(grad_faces, grad_textures, faces_idx, V, F,
-                                                                     fill_back, tex_grad_mode, grad_verts, grad_attrs)));
+                                                                     fill_back, tex_grad_mode, grad_verts, grad_attrs,
+                                                                     det_v, det_a)));
     HOC_CHECK_LAUNCH("hoc_mesh_scatter_kernel");
+    if (need > 0) {
+        const long n = 3l * B * V;
+        if ((grad_verts != nullptr && hoc_det_flush(det_v, n, grad_verts, 0, st) != cudaSuccess) ||
+            (grad_attrs != nullptr && hoc_det_flush(det_a, n, grad_attrs, 0, st) != cudaSuccess)) {
+            hoc_set_error("hoc_mesh_scatter: flush of the accumulators failed");
+            return HOC_ERR_CUDA;
+        }
+    }
     return HOC_OK;
 }
 

@@ -393,8 +393,9 @@ __device__ __forceinline__ void mano_grad_centre(const float *g_verts, const flo
 /*
  * Backward, kernel A.  grid (ceil(V / MN_VS), B): the vertex-parallel part for one slice of one sample -- skinning
  * adjoint (dL/dA_j, 192 sums), dL/d v_posed = T_v^T g_v, and its products with the pose / shape blend shapes
- * (dL/d pose_map, 135 sums; direct part of dL/d betas, 10 sums) -- reduced over the slice in the CTA and added to
- * the sample's accumulators [MN_ACC] with one atomic per sum.
+ * (dL/d pose_map, 135 sums; direct part of dL/d betas, 10 sums) -- reduced over the slice in the CTA and stored in
+ * the slice's own row of partial sums [B][slices][MN_ACC]; kernel B adds the rows in slice order.  No atomics: the
+ * MANO gradient is reproducible bit for bit.
  */
 __global__ void __launch_bounds__(MN_THREADS)
 hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
@@ -449,15 +450,14 @@ hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose,
             s_g[3 * tid + k] = g[k];
     }
     __syncthreads();
-    float *A = acc + (long)b * MN_ACC;
+    float *A = acc + ((long)b * gridDim.x + blockIdx.x) * MN_ACC;
     if (tid < 192) { /* dL/dA_j = sum_v w_vj g_v (x) [v_posed; 1] */
         const int j = tid / 12, e = tid % 12; /* e < 9: rotation entry (r, c); e >= 9: translation r */
         const int r = e < 9 ? e / 3 : e - 9, c = e < 9 ? e % 3 : -1;
         float a = 0.0f;
         for (int v = 0; v < nv; v++)
             a += s_w[v * 16 + j] * s_g[3 * v + r] * (c >= 0 ? s_vp[3 * v + c] : 1.0f);
-        if (a != 0.0f)
-            atomicAdd(A + tid, a);
+        A[tid] = a;
     } else if (tid < 192 + 10) { /* direct part of dL/d betas = shapedirs^T dL/d v_posed */
         const int k = tid - 192;
         float a = 0.0f, a2 = 0.0f;
@@ -477,8 +477,7 @@ hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose,
         for (; i < 3 * nv; i++)
             a += __ldg(sd + (long)i * 10) * s_gvp[i];
         a += a2;
-        if (a != 0.0f)
-            atomicAdd(A + 192 + 135 + k, a);
+        A[192 + 135 + k] = a;
     }
     if (tid < 135) { /* dL/d pose_map[k] = sum_i posedirs[i][k] dL/d v_posed[i]  (coalesced across threads) */
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -500,8 +499,7 @@ hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose,
         for (; i < 3 * nv; i++)
             a0 += __ldg(pd + (long)i * 135) * s_gvp[i];
         a0 = (a0 + a1) + (a2 + a3);
-        if (a0 != 0.0f)
-            atomicAdd(A + 192 + tid, a0);
+        A[192 + tid] = a0;
     }
 }
 
@@ -514,16 +512,23 @@ hoc_mano_backward_verts_kernel(hoc_mano_model M, const float *__restrict__ pose,
 __global__ void __launch_bounds__(MN_THREADS_B)
 hoc_mano_backward_pose_kernel(hoc_mano_model M, const float *__restrict__ pose, const float *__restrict__ betas,
                               const float *__restrict__ trans, const float *__restrict__ g_verts,
-                              const float *__restrict__ g_joints, const float *__restrict__ acc,
+                              const float *__restrict__ g_joints, const float *__restrict__ acc, int n_slices,
                               float *__restrict__ g_pose, float *__restrict__ g_betas, float *__restrict__ g_trans)
 {
     __shared__ ManoPose P;
-    __shared__ float gAR[16][9], gAt[16][3], gGt[16][3], gpm[135], gfull[48], gJ[48];
+    __shared__ float gAR[16][9], gAt[16][3], gGt[16][3], gpm[135], gfull[48], gJ[48], s_A[MN_ACC];
     __shared__ float s_red[(MN_THREADS_B / 32) * 3], s_gc[3];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int npose = 3 + M.ncomps;
     mano_pose_setup(M, pose, betas, b, P);
-    const float *A = acc + (long)b * MN_ACC;
+    for (int i = tid; i < 192 + 135 + 10; i += MN_THREADS_B) { /* the slices' partial sums, in slice order */
+        float a = 0.0f;
+        for (int sl = 0; sl < n_slices; sl++)
+            a += acc[((long)b * n_slices + sl) * MN_ACC + i];
+        s_A[i] = a;
+    }
+    __syncthreads();
+    const float *A = s_A;
     for (int i = tid; i < 192; i += MN_THREADS_B) {
         const int j = i / 12, e = i % 12;
         if (e < 9)
@@ -663,7 +668,8 @@ extern "C" int hoc_mano_forward(const hoc_mano_model *model, const float *pose, 
 
 extern "C" size_t hoc_mano_backward_workspace_bytes(int B)
 {
-    return B > 0 ? sizeof(float) * MN_ACC * (size_t)B : 0;
+    /* one row of partial sums per (sample, 64-vertex slice); sized for the largest model the kernels accept */
+    return B > 0 ? sizeof(float) * MN_ACC * (size_t)B * ((MN_MAXV + MN_VS - 1) / MN_VS) : 0;
 }
 
 extern "C" int hoc_mano_backward(const hoc_mano_model *model, const float *pose, const float *betas,
@@ -683,11 +689,7 @@ extern "C" int hoc_mano_backward(const hoc_mano_model *model, const float *pose,
         return HOC_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (cudaMemsetAsync(workspace, 0, need, st) != cudaSuccess) {
-        hoc_set_error("hoc_mano_backward: memset failed");
-        return HOC_ERR_CUDA;
-    }
-    float *acc = (float *)workspace;
+    float *acc = (float *)workspace; /* every (sample, slice) row is fully written by kernel A: no zero-fill */
     dim3 grid((model->num_verts + MN_VS - 1) / MN_VS, B);
     HOC_LAUNCH(HOC_K_MANO_BWD, st,
                (hoc_mano_backward_verts_kernel<<<grid, MN_THREADS, 0, st>>>(*model, pose, betas, trans, grad_verts,
@@ -695,8 +697,8 @@ extern "C" int hoc_mano_backward(const hoc_mano_model *model, const float *pose,
     HOC_CHECK_LAUNCH("hoc_mano_backward_verts_kernel");
     HOC_LAUNCH(HOC_K_MANO_BWD, st,
                (hoc_mano_backward_pose_kernel<<<B, MN_THREADS_B, 0, st>>>(*model, pose, betas, trans, grad_verts,
-                                                                          grad_joints, acc, grad_pose, grad_betas,
-                                                                          grad_trans)));
+                                                                          grad_joints, acc, (int)grid.x, grad_pose,
+                                                                          grad_betas, grad_trans)));
     HOC_CHECK_LAUNCH("hoc_mano_backward_pose_kernel");
     return HOC_OK;
 }

@@ -35,6 +35,7 @@
  * 548 us (one warp per face) -> 245 -> 121 -> 93 (pixel / face / line passes) -> 55 us (this decomposition).
  */
 #include "hoc_common.cuh"
+#include "hoc_det.cuh"
 #include "raster_math.h"
 
 #define EXT_ROW_LO 0
@@ -60,11 +61,15 @@ struct HocBwdWorkspace {
     float *acc_d;
     int2 *cov_list;
     unsigned short *emitters;
+    /* reproducible mode only (hoc_det.cuh): fixed-point accumulators of grad_faces / grad_textures / acc_d,
+     * two 64-bit words per float, one contiguous zero-fill */
+    unsigned long long *det_gf, *det_gt, *det_ad;
+    size_t det_bytes;
     size_t count_bytes, acc_bytes; /* ext + cov_count + line_count, then acc_d: one contiguous zero-fill */
     size_t total;
 };
 
-static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
+static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S, int tex_n = 0, bool det = false)
 {
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     HocBwdWorkspace w;
@@ -85,6 +90,18 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S)
     off = up(off + sizeof(int2) * (size_t)B * S * S);
     w.emitters = (unsigned short *)(p + off);
     off = up(off + sizeof(unsigned short) * 2 * (size_t)B * S * 3 * (size_t)S);
+    w.det_gf = w.det_gt = w.det_ad = nullptr;
+    w.det_bytes = 0;
+    if (det) {
+        const size_t nf = (size_t)B * F, begin = off;
+        w.det_gf = (unsigned long long *)(p + off);
+        off += 16 * 9 * nf;
+        w.det_gt = (unsigned long long *)(p + off);
+        off += 16 * (size_t)tex_n * nf;
+        w.det_ad = (unsigned long long *)(p + off);
+        off = up(off + 16 * 3 * nf);
+        w.det_bytes = off - begin;
+    }
     w.total = off;
     return w;
 }
@@ -123,14 +140,15 @@ __device__ __forceinline__ float hoc_rcp_approx(float x)
 
 /* One (edge, axis) of the face owning pixel (xi, yi): the pixel's term of the inward scan of the column it
  * lies on (added to grad_faces) and, when it is the pixel just inside the edge, the queued outward scan.
- * (ax..cy) are the face's vertices in NDC rotated so that A is the first vertex of the edge; gfA / gfB point
- * at the x component of vertex A / B in grad_faces.  I / g: (alpha, r, g, b) of the pixel and its incoming
+ * (ax..cy) are the face's vertices in NDC rotated so that A is the first vertex of the edge; gfA / gfB index
+ * the x component of vertex A / B in grad_faces.  I / g: (alpha, r, g, b) of the pixel and its incoming
  * gradient. */
 __device__ __forceinline__ void hoc_k4_pixel_combo(float ax, float ay, float bx, float by, float cx, float cy,
                                                    int edge, int axis, int xi, int yi, const HocBwdMaps &M,
                                                    const float *I, const float *g, float eps,
                                                    int *__restrict__ line_count, unsigned short *__restrict__ emitters,
-                                                   float *__restrict__ gfA, float *__restrict__ gfB)
+                                                   float *__restrict__ grad_faces, long gfA, long gfB,
+                                                   unsigned long long *__restrict__ det_gf)
 {
     HocK4Edge E;
     hoc_k4_edge_pts(ax, ay, bx, by, cx, cy, M.S, axis, &E);
@@ -167,9 +185,9 @@ __device__ __forceinline__ void hoc_k4_pixel_combo(float ax, float ay, float bx,
             float gA = 0.0f, gB = 0.0f;
             hoc_k4_accum_col(&C, d1p, eps, delta, &gA, &gB);
             if (gA != 0.0f)
-                atomicAdd(gfA + (1 - axis), gA);
+                hoc_accum(grad_faces, gfA + (1 - axis), gA, det_gf);
             if (gB != 0.0f)
-                atomicAdd(gfB + (1 - axis), gB);
+                hoc_accum(grad_faces, gfB + (1 - axis), gB, det_gf);
         }
     }
 }
@@ -293,7 +311,9 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
                                                     const float *__restrict__ g_depth, int b, int fi, int xi, int yi,
                                                     int F, int S, int ts, float near_, float far_, float eps, int layout,
                                                     int tex_mode, float *__restrict__ acc_d,
-                                                    float *__restrict__ grad_textures)
+                                                    float *__restrict__ grad_textures,
+                                                    unsigned long long *__restrict__ det_ad,
+                                                    unsigned long long *__restrict__ det_gt)
 {
     const bool want_tex = (grad_textures != nullptr) && (g_rgb != nullptr);
     const bool want_depth = (acc_d != nullptr) && (g_depth != nullptr);
@@ -330,16 +350,16 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
     if (want_depth) {
         const float gz = g_depth[hoc_plane_off(layout, S, b, yi, xi)] * zp * zp;
         if (gz != 0.0f) {
-            float *ad = acc_d + ((long)b * F + fi) * 3;
+            const long ad = ((long)b * F + fi) * 3;
 #pragma unroll
             for (int k = 0; k < 3; k++)
-                atomicAdd(ad + k, gz * w[k]);
+                hoc_accum(acc_d, ad + k, gz * w[k], det_ad);
         }
     }
     if (want_tex && nz && tex_mode == HOC_TEX_GRAD_VERTEX) {
         /* textures are the multilinear extension of three vertex values (T[i,j,k] = i c0 + j c1 + k c2, ts == 2):
          * d rgb / d c_k = t_k, so nine sums per face instead of twenty-four */
-        float *gt = grad_textures + ((long)b * F + fi) * 9;
+        const long gt = ((long)b * F + fi) * 9;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const float t = hoc_tex_coord(w[k], f[3 * k + 2], zp, 2, eps);
@@ -347,11 +367,11 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
             for (int c = 0; c < 3; c++) {
                 const float v = t * gr[c];
                 if (v != 0.0f)
-                    atomicAdd(gt + 3 * k + c, v);
+                    hoc_accum(grad_textures, gt + 3 * k + c, v, det_gt);
             }
         }
     } else if (want_tex && nz) {
-        float *gt = grad_textures + ((long)b * F + fi) * tex_n;
+        const long gt = ((long)b * F + fi) * tex_n;
         float tf[3];
         int ti[3];
 #pragma unroll
@@ -381,7 +401,7 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
                 for (int c = 0; c < 3; c++) {
                     const float v = ww * gr[c];
                     if (v != 0.0f)
-                        atomicAdd(gt + isc * 3 + c, v);
+                        hoc_accum(grad_textures, gt + isc * 3 + c, v, det_gt);
                 }
             }
         }
@@ -407,7 +427,8 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                             const int *__restrict__ cov_count, const int2 *__restrict__ cov_list,
                             float *__restrict__ acc_d, int *__restrict__ line_count,
                             unsigned short *__restrict__ emitters, float *__restrict__ grad_faces,
-                            float *__restrict__ grad_textures)
+                            float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gf,
+                            unsigned long long *__restrict__ det_gt, unsigned long long *__restrict__ det_ad)
 {
     const int b = blockIdx.y;
     const int count = min(cov_count[b], S * S);
@@ -418,7 +439,7 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
             const int2 e = list[i];
             const int yi = e.x / S, xi = e.x - yi * S;
             hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, e.y, xi, yi, F, S, ts, near_, far_,
-                                     eps, layout, tex_mode, acc_d, grad_textures);
+                                     eps, layout, tex_mode, acc_d, grad_textures, det_ad, det_gt);
         }
         return;
     }
@@ -442,7 +463,7 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
         if (wid == 6) {
             if (fi >= 0)
                 hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, fi, xi, yi, F, S, ts, near_,
-                                         far_, eps, layout, tex_mode, acc_d, grad_textures);
+                                         far_, eps, layout, tex_mode, acc_d, grad_textures, det_ad, det_gt);
         } else if (fi >= 0) {
             const int edge = wid >> 1, axis = wid & 1;
             const int ia = edge, ib = (edge == 2) ? 0 : edge + 1, ic = (edge == 0) ? 2 : edge - 1;
@@ -473,9 +494,9 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
             f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
             f[2] = f[5] = f[8] = 0.0f;
             if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
-                float *gf = grad_faces + ((long)b * F + fi) * 9;
+                const long gf = ((long)b * F + fi) * 9;
                 hoc_k4_pixel_combo(ax, ay, bx, by, cx, cy, edge, axis, xi, yi, M, I, g, eps, line_count, emitters,
-                                   gf + 3 * ia, gf + 3 * ib);
+                                   grad_faces, gf + 3 * ia, gf + 3 * ib, det_gf);
             }
         }
     }
@@ -529,7 +550,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
                            const int *__restrict__ ext, const int *__restrict__ line_count,
-                           const unsigned short *__restrict__ emitters, float *__restrict__ grad_faces)
+                           const unsigned short *__restrict__ emitters, float *__restrict__ grad_faces,
+                           unsigned long long *__restrict__ det_gf)
 {
     /* dynamic shared memory: float4 s_line4[S + 16]
      * per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (the inside pixel of a scan
@@ -672,9 +694,9 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 gB = __fmaf_rn(-delta, hoc_rcp_approx(dB), gB);
             }
             if (gA != 0.0f)
-                atomicAdd(grad_faces + gfA, gA);
+                hoc_accum(grad_faces, gfA, gA, det_gf);
             if (gB != 0.0f)
-                atomicAdd(grad_faces + gfB, gB);
+                hoc_accum(grad_faces, gfB, gB, det_gf);
         }
     }
 }
@@ -688,6 +710,8 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_line_threads = value;
     else if (key == HOC_TUNE_LINE_SEGMENT && (value == 8 || value == 16))
         g_line_seg = value;
+    else if (key == HOC_TUNE_DETERMINISTIC && (value == 0 || value == 1))
+        g_hoc_deterministic = value;
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -706,7 +730,7 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
                (hoc_raster_bwd_line_kernel<CH><<<grid, g_line_threads, smem, st>>>(
                    faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,
-                   w.emitters, grad_faces)));
+                   w.emitters, grad_faces, w.det_gf)));
     return cudaSuccess;
 }
 
@@ -715,6 +739,16 @@ extern "C" size_t hoc_raster_backward_workspace_bytes(int B, int F, int S)
     if (B <= 0 || S <= 0 || F < 0)
         return 0;
     return hoc_bwd_workspace(nullptr, B, F, S).total;
+}
+
+/* Workspace of hoc_raster_backward for a given texture size: in the reproducible mode (HOC_TUNE_DETERMINISTIC) the
+ * fixed-point accumulators of grad_textures ([B,F,ts^3,3] or, in HOC_TEX_GRAD_VERTEX mode, [B,F,3,3]) live in it. */
+extern "C" size_t hoc_raster_backward_workspace_bytes_ex(int B, int F, int S, int ts, int tex_grad_mode)
+{
+    if (B <= 0 || S <= 0 || F < 0)
+        return 0;
+    const int tex_n = (tex_grad_mode == HOC_TEX_GRAD_VERTEX) ? 9 : 3 * ts * ts * ts;
+    return hoc_bwd_workspace(nullptr, B, F, S, tex_n, g_hoc_deterministic != 0).total;
 }
 
 extern "C" int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
@@ -741,9 +775,12 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     if (grad_faces == nullptr && grad_textures == nullptr)
         return HOC_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const HocBwdWorkspace w = hoc_bwd_workspace(workspace, B, F, S);
+    const bool det = g_hoc_deterministic != 0;
+    const int tex_n = (tex_grad_mode == HOC_TEX_GRAD_VERTEX) ? 9 : 3 * ts * ts * ts;
+    const HocBwdWorkspace w = hoc_bwd_workspace(workspace, B, F, S, tex_n, det);
     if (workspace == nullptr || workspace_bytes < w.total) {
-        hoc_set_error("hoc_raster_backward: workspace of %zu bytes needed, %zu given", w.total, workspace_bytes);
+        hoc_set_error("hoc_raster_backward: workspace of %zu bytes needed%s, %zu given", w.total,
+                      det ? " (reproducible mode: query hoc_raster_backward_workspace_bytes_ex)" : "", workspace_bytes);
         return HOC_ERR_WORKSPACE;
     }
     const float *g_alpha = use_alpha ? grad_alpha : nullptr;
@@ -756,6 +793,8 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     /* spans, counters and (directly behind them) acc_d are zero-filled by ONE memset; the gradient outputs are
      * zero-filled by the scan pass */
     cudaError_t e = cudaMemsetAsync(w.ext, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
+    if (e == cudaSuccess && det)
+        e = cudaMemsetAsync(w.det_gf, 0, w.det_bytes, st);
     if (e != cudaSuccess) {
         hoc_set_error("hoc_raster_backward: memset failed: %s", cudaGetErrorString(e));
         return HOC_ERR_CUDA;
@@ -789,7 +828,7 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                (hoc_raster_bwd_cover_kernel<TS2, K4><<<cg, K4 ? CV_THREADS_K4 : CV_THREADS, 0, st>>>(                 \
                    faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
                    eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
-                   w.line_count, w.emitters, grad_faces, gt)))
+                   w.line_count, w.emitters, grad_faces, gt, w.det_gf, w.det_gt, w.det_ad)))
         if (ts == 2 && k4)
             HOC_COVER_LAUNCH(true, true);
         else if (ts == 2)
@@ -801,9 +840,19 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
 #undef HOC_COVER_LAUNCH
         HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
     }
+    const long nfaces = (long)B * F;
+    if (det && gt != nullptr && hoc_det_flush(w.det_gt, nfaces * tex_n, gt, 0, st) != cudaSuccess) {
+        hoc_set_error("hoc_raster_backward: flush of the texture accumulators failed");
+        return HOC_ERR_CUDA;
+    }
     if (grad_faces == nullptr)
         return HOC_OK;
-    if (want_depth) {
+    if (det && want_depth && hoc_det_flush(w.det_ad, nfaces * 3, w.acc_d, 0, st) != cudaSuccess) {
+        hoc_set_error("hoc_raster_backward: flush of the depth accumulators failed");
+        return HOC_ERR_CUDA;
+    }
+    /* reproducible mode: the per-face depth epilogue (a plain `+=`) runs after the flush of grad_faces below */
+    if (want_depth && !det) {
         const long nf = (long)B * F;
         HOC_LAUNCH(HOC_K_RASTER_BACKWARD, st,
                    (hoc_raster_bwd_depth_kernel<<<(unsigned)((nf + 255) / 256), 256, 0, st>>>(faces, w.acc_d, nf, S,
@@ -823,6 +872,18 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
             return HOC_ERR_CUDA;
         }
         HOC_CHECK_LAUNCH("hoc_raster_bwd_line_kernel");
+    }
+    if (det) {
+        if (k4 && hoc_det_flush(w.det_gf, nfaces * 9, grad_faces, 0, st) != cudaSuccess) {
+            hoc_set_error("hoc_raster_backward: flush of the face accumulators failed");
+            return HOC_ERR_CUDA;
+        }
+        if (want_depth) {
+            HOC_LAUNCH(HOC_K_RASTER_BACKWARD, st,
+                       (hoc_raster_bwd_depth_kernel<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(faces, w.acc_d, nfaces,
+                                                                                                  S, grad_faces)));
+            HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
+        }
     }
     return HOC_OK;
 }

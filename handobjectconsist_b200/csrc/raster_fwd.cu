@@ -352,7 +352,9 @@ extern "C" size_t hoc_raster_forward_workspace_bytes(int B, int F, int S)
     (void)F;
     if (B <= 0 || S <= 0)
         return 0;
-    return (size_t)B * S * S * sizeof(unsigned long long);
+    /* rounded up to 256 bytes: hoc_mesh_gather_clear fills the keys with 16-byte stores (odd B * S * S otherwise
+     * left an 8-byte tail it had to reject) */
+    return ((size_t)B * S * S * sizeof(unsigned long long) + 255) & ~(size_t)255;
 }
 
 extern "C" int hoc_raster_forward(const float *faces, const float *textures, int B, int F, int S, int ts,

@@ -153,6 +153,12 @@ __device__ __forceinline__ float hoc_threshold_mask(float m, float thresh)
 
 #define WP_THREADS 256
 #define WP_MAXC 4
+/* The per-sample sum of |diff| is accumulated over the CTAs with double atomics.  Every CTA's partial sum is first
+ * rounded to an integer multiple of 2^-28: integer-valued doubles add exactly (below 2^53), so the total does not
+ * depend on the order in which the CTAs arrive -- the loss is reproducible bit for bit.  (A partial sum >= 2^-4 has no
+ * bits below 2^-28: nothing is lost; smaller ones are rounded by < 2e-9.) */
+#define WP_SUM_SCALE 268435456.0
+#define WP_SUM_INV (1.0 / 268435456.0)
 
 template <int CT, int CJT> /* compile-time channel counts (0 = use the run-time values, any count) */
 __global__ void __launch_bounds__(WP_THREADS)
@@ -289,7 +295,7 @@ hoc_warp_photo_forward_kernel(const float *__restrict__ src, const float *__rest
         a = hoc_warp_sum(a);
         n = hoc_warp_sum(n);
         if (lane == 0 && n > 0.0f) {
-            atomicAdd(&sums[2 * b + 0], (double)a);
+            atomicAdd(&sums[2 * b + 0], rint((double)a * WP_SUM_SCALE));
             atomicAdd(&sums[2 * b + 1], (double)n);
         }
     }
@@ -300,7 +306,7 @@ __global__ void hoc_masked_mean_kernel(const double *__restrict__ sums, int B, f
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B)
-        loss[b] = (float)(sums[2 * b] / fmax(sums[2 * b + 1], 1.0));
+        loss[b] = (float)(sums[2 * b] * WP_SUM_INV / fmax(sums[2 * b + 1], 1.0));
 }
 
 /* pair_consist's loss of one frame pair (imgflowarp.py:108-114): loss_bwd + loss_fwd (that order) or loss_fwd. */
@@ -309,8 +315,10 @@ __global__ void hoc_pair_loss_kernel(const double *__restrict__ sums_fwd, const 
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < B) {
-        const float lf = (float)(sums_fwd[2 * b] / fmax(sums_fwd[2 * b + 1], 1.0));
-        loss[b] = (sums_bwd != nullptr) ? (float)(sums_bwd[2 * b] / fmax(sums_bwd[2 * b + 1], 1.0)) + lf : lf;
+        const float lf = (float)(sums_fwd[2 * b] * WP_SUM_INV / fmax(sums_fwd[2 * b + 1], 1.0));
+        loss[b] = (sums_bwd != nullptr)
+                      ? (float)(sums_bwd[2 * b] * WP_SUM_INV / fmax(sums_bwd[2 * b + 1], 1.0)) + lf
+                      : lf;
     }
 }
 

@@ -88,10 +88,11 @@ class GraphedConsistStep:
         stage = self._u8_stage.get(key)
         if stage is None or stage.shape != src.shape:
             stage = self._u8_stage[key] = torch.empty(src.shape, dtype=torch.uint8, device=self.device)
-        stage.copy_(src, non_blocking=True)
         sub = 0.5 if name == "IMAGE" else 0.0
-        _lib.check(_lib.lib().hoc_unpack_u8(_lib.ptr(stage), _lib.ptr(buf), buf.numel(), 255.0, sub,
-                                            _lib.stream_ptr()), "hoc_unpack_u8")
+        with torch.cuda.device(self.device):  # the launch goes to THIS step's device, whatever the caller's current one
+            stage.copy_(src, non_blocking=True)
+            _lib.check(_lib.lib().hoc_unpack_u8(_lib.ptr(stage), _lib.ptr(buf), buf.numel(), 255.0, sub,
+                                                _lib.stream_ptr()), "hoc_unpack_u8")
 
     def load(self, samples, all_results):
         """Copy a new batch into the static buffers (stream-ordered; pinned host tensors copy asynchronously).

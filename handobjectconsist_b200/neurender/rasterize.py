@@ -134,7 +134,7 @@ def _backward_impl(ctx, grad_rgb, grad_alpha, grad_depth):
     with torch.cuda.device(dev):
         grad_faces = torch.empty_like(faces) if need_faces else None
         grad_textures = torch.empty_like(textures) if need_tex else None
-        ws_bytes = L.hoc_raster_backward_workspace_bytes(B, Fn, S)
+        ws_bytes = L.hoc_raster_backward_workspace_bytes_ex(B, Fn, S, max(int(ctx.texture_size), 1), _lib.HOC_TEX_GRAD_CUBE)
         ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
         code = L.hoc_raster_backward(
             _lib.ptr(faces), _lib.ptr(textures), _lib.ptr(face_index_map), _lib.ptr(rgb), _lib.ptr(weight_map),

@@ -2,13 +2,17 @@
 per-element distance over the elements a mask selects, one value per sample, 0 for a sample whose mask is empty.
 (Element-wise torch ops for the generic criteria; the fused L1 path of ``pair_consist`` computes the same quantity
 inside ``hoc_warp_photo_forward`` / ``hoc_pair_loss``.)"""
+import torch
 
 
 def batch_masked_mean_loss(dists, mask):
-    """dists, mask: [B, ...] of the same shape (mask boolean or 0/1).  Returns [B]."""
+    """dists [B, ...]; mask broadcastable against it over the same number of dimensions (e.g. [B,1,H,W] against
+    [B,3,H,W], like the reference), boolean, 0/1 or soft weights.  Returns [B]: sum(mask * dists) / sum(mask),
+    both over every axis but the first; the denominator counts the mask's OWN elements (a broadcast mask is not
+    re-counted per channel) and only an exactly-zero denominator is replaced by 1."""
     weights = mask.float()
-    per_sample = weights.flatten(1)
-    selected_sum = (per_sample * dists.flatten(1)).sum(dim=1)
-    selected_count = per_sample.sum(dim=1)
-    # an empty mask would divide 0 by 0: its count is replaced by 1, which makes the sample's loss exactly 0
-    return selected_sum / selected_count.clamp(min=1.0)
+    axes = list(range(1, dists.dim()))
+    selected_sum = (weights * dists).sum(dim=axes)
+    selected_count = weights.sum(dim=axes)
+    selected_count = torch.where(selected_count == 0, torch.ones_like(selected_count), selected_count)
+    return selected_sum / selected_count

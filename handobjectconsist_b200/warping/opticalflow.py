@@ -94,7 +94,7 @@ class _MeshRasterFunction(Function):
             grad_faces = torch.empty_like(faces) if need_v else None
             # the cubes come from three vertex values per face: ask for d loss / d vertex value directly
             grad_tex = torch.empty((B, Fo, 3, 3), dtype=torch.float32, device=dev) if need_a else None
-            ws_bytes = L.hoc_raster_backward_workspace_bytes(B, Fo, S)
+            ws_bytes = L.hoc_raster_backward_workspace_bytes_ex(B, Fo, S, 2, _lib.HOC_TEX_GRAD_VERTEX)
             ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
             _lib.check(L.hoc_raster_backward(_lib.ptr(faces), None, _lib.ptr(idx), _lib.ptr(rgb), _lib.ptr(wmap),
                                              _lib.ptr(depth), _lib.ptr(g_rgb),
@@ -107,9 +107,11 @@ class _MeshRasterFunction(Function):
             else:
                 grad_verts = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_v else None
                 grad_attrs = torch.empty((B, V, 3), dtype=torch.float32, device=dev) if need_a else None
-            _lib.check(L.hoc_mesh_scatter(_lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(fi), B, V, Fn,
-                                          int(fill_back), _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_verts),
-                                          _lib.ptr(grad_attrs), st),
+            sc_bytes = L.hoc_mesh_scatter_workspace_bytes(B, V)  # 0 unless the reproducible mode is on
+            sc_ws = torch.empty(sc_bytes, dtype=torch.uint8, device=dev) if sc_bytes else None
+            _lib.check(L.hoc_mesh_scatter_ws(_lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(fi), B, V, Fn,
+                                             int(fill_back), _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_verts),
+                                             _lib.ptr(grad_attrs), _lib.ptr(sc_ws), sc_bytes, st),
                        "hoc_mesh_scatter")
         return (grad_verts, grad_attrs) + (None,) * 7
 

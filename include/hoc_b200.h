@@ -93,9 +93,17 @@ const char *hoc_last_error(void);
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
- *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan (8 or 16) */
+ *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan (8 or 16)
+ *   HOC_TUNE_DETERMINISTIC 0 (default) / 1: reproducible mode.  The gradient sums that production accumulates with
+ *                          float atomics (like the reference's backward_textures / backward_depth_map /
+ *                          index_put(accumulate)) are accumulated in 128-bit fixed point with integer atomics
+ *                          instead (csrc/hoc_det.cuh): the result no longer depends on the order of the additions,
+ *                          so two runs -- or a captured graph and the eager path -- give the same bits.  Needs the
+ *                          larger workspaces reported by hoc_raster_backward_workspace_bytes_ex /
+ *                          hoc_mesh_scatter_workspace_bytes.  Slower; for tests and debugging. */
 #define HOC_TUNE_LINE_THREADS 1
 #define HOC_TUNE_LINE_SEGMENT 2
+#define HOC_TUNE_DETERMINISTIC 3
 int hoc_set_tuning(int key, int value);
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
@@ -157,6 +165,8 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
 #define HOC_TEX_GRAD_CUBE 0
 #define HOC_TEX_GRAD_VERTEX 1
 size_t hoc_raster_backward_workspace_bytes(int B, int F, int S);
+/* the same, plus (reproducible mode only) the fixed-point accumulators for this texture size / gradient mode */
+size_t hoc_raster_backward_workspace_bytes_ex(int B, int F, int S, int ts, int tex_grad_mode);
 int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
                         const float *rgb, const float *weight_map, const float *depth, const float *grad_rgb,
                         const float *grad_alpha,
@@ -177,8 +187,10 @@ int hoc_raster_backward(const float *faces, const float *textures, const int32_t
  *   valid_mask [B,H,W] uint8 (0/1)   warp_mask[:,0] & (flow[...,0] != 0) & (jitter[:,0] == 1)
  *   flow_mask  [B,H,W,2] uint8 (0/1) ~(flow == 0)
  *   diff       [B,C,H,W]  |warped - target|
- *   sums       [B,2] DOUBLE (sum of diff over valid elements, number of valid elements); zero-filled by the call
- *   loss       [B] = sums[b,0] / max(sums[b,1], 1)  (batch_masked_mean_loss; second tiny launch; may be NULL)
+ *   sums       [B,2] DOUBLE, zero-filled by the call; consumed by hoc_pair_loss / hoc_warp_photo_backward:
+ *              (sum of diff over valid elements in units of 2^-28, number of valid elements) -- both integer-valued,
+ *              so that the double atomics that accumulate them commute and the loss is reproducible bit for bit
+ *   loss       [B] = sum / max(count, 1)  (batch_masked_mean_loss; second tiny launch; may be NULL)
  */
 int hoc_warp_photo_forward(const float *src, const float *target, const float *flow, const float *jitter, int B,
                            int C, int Cj, int H, int W, float thresh, float *warped, float *warp_mask,
@@ -251,6 +263,14 @@ int hoc_cat_meshes(const float *hand_a, const float *obj_a, const float *hand_b,
  * tex_grad_mode as in hoc_raster_backward: CUBE = grad_textures [B,F',2,2,2,3], VERTEX = [B,F',3,3]. */
 int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B, int V,
                      int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs, void *stream);
+/* The same with a workspace: 0 bytes in production, the fixed-point accumulators of both outputs in the
+ * reproducible mode (HOC_TUNE_DETERMINISTIC), where hoc_mesh_scatter itself fails with HOC_ERR_WORKSPACE.
+ * Precondition of both (and of hoc_mesh_gather): 0 <= faces_idx < V; indices outside that range are skipped
+ * (gather: read as vertex 0) instead of touching memory out of bounds. */
+size_t hoc_mesh_scatter_workspace_bytes(int B, int V);
+int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B, int V,
+                        int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs,
+                        void *workspace, size_t workspace_bytes, void *stream);
 /* hoc_flow_finalize: everything get_opticalflow does after its two renders (opticalflow.py:109-154): alpha
  * threshold, ignore-face mask, flow = rgb * mask, forward-backward occlusion check, mask products, channel
  * slice, crop.  rgb [B,3,S,S] / alpha [B,S,S] in HOC_LAYOUT_IMAGE, idx [B,S,S] raster order;

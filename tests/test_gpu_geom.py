@@ -283,7 +283,7 @@ def test_network_outputs_to_photometric_loss_and_back():
         assert helpers.rel_err(got.grad.cpu().numpy(), want.grad.numpy()) < 1e-3
 
 
-def test_graphed_step_with_the_head_inside_matches_eager():
+def test_graphed_step_with_the_head_inside_matches_eager(det_mode):
     """GraphedHeadConsistStep: MANO + ManoAdaptor + recover_3d_proj + ObjBranch + the consistency step, forward and
     backward, captured in ONE CUDA graph -- same loss and the same gradients of the network outputs as the eager
     chain, also after loading other network outputs into its static buffers."""
@@ -372,5 +372,5 @@ def test_graphed_step_with_the_head_inside_matches_eager():
         assert set(grads_g) == {"pose", "betas", "hand_st", "obj_st"}
         for k in grads_g:
             assert grads_e[k].abs().max().item() > 0
-            # same kernels on both sides; what differs is the order of the float atomics (rasterizer / MANO backward)
-            assert helpers.rel_err(grads_g[k].cpu().numpy(), grads_e[k].cpu().numpy()) < 5e-4, k
+            # same kernels on both sides, reproducible mode (order-independent sums): bit-level agreement
+            assert helpers.rel_err(grads_g[k].cpu().numpy(), grads_e[k].cpu().numpy()) < 1e-6, k

@@ -56,6 +56,32 @@ def test_consist_step_matches_oracle(S, crop, detach, use_bwd, seed):
     assert helpers.rel_err(v1.grad.cpu().numpy(), go) < 1e-3
 
 
+@pytest.mark.parametrize("B,S", [(1, 63), (3, 33)])
+def test_odd_batch_and_image_size(B, S):
+    """B * S * S odd (last-batch remainder at an odd image size): the z-buffer key fill of the fused gather used to
+    reject the 8-byte tail."""
+    from handobjectconsist_b200 import warpbranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, S, seed=9)
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    v1 = g["verts1"].clone().requires_grad_(True)
+    loss, res = warpbranch.consist_step(v1, g["verts2"], g["faces"], g["K"], g["image_ref"], g["image"],
+                                        g["jitter_mask_ref"], g["jitter_mask"], _renderer(S, dev),
+                                        PyramidCriterion("l1"), (S, S), sc["hand_ignore_faces"], detach_renders=False,
+                                        use_backward=True)
+    loss.backward()
+    c1 = sc["verts1"].clone().requires_grad_(True)
+    loss_o, res_o = opipe.consist_step(c1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                       sc["jitter_mask_ref"], sc["jitter_mask"], S, (S, S), sc["hand_ignore_faces"],
+                                       detach_renders=False, use_backward=True, warp_device=dev)
+    loss_o.backward()
+    for i in range(2):
+        assert (res["flows"][i].detach() - res_o["flows"][i].detach()).abs().max().item() <= 1e-4
+    assert abs(loss.item() - loss_o.item()) <= 1e-4
+    assert np.abs(v1.grad.cpu().numpy() - c1.grad.numpy()).max() <= 1e-3 * np.abs(c1.grad.numpy()).max()
+
+
 def test_warpbranch_forward_batch_dicts():
     """The reference's calling convention: sample dicts keyed by TransQueries/BaseQueries + result dicts."""
     from handobjectconsist_b200 import warpbranch
@@ -121,9 +147,10 @@ def test_fused_flow_path_equals_op_by_op_path(detach):
         assert np.abs(a - b).max() <= 1e-3 * np.abs(b).max()
 
 
-def test_graphed_step_matches_eager():
+def test_graphed_step_matches_eager(det_mode):
     """CUDA-graph capture of forward+backward (handobjectconsist_b200.graphed) reproduces the eager step,
-    also after loading a different batch into its static buffers, from pinned host memory."""
+    also after loading a different batch into its static buffers, from pinned host memory.  Reproducible mode:
+    the graph and the eager path launch the same kernels, so their gradients must agree to the last bit."""
     from handobjectconsist_b200 import warpbranch
     from handobjectconsist_b200.graphed import GraphedConsistStep
     from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
@@ -158,14 +185,13 @@ def test_graphed_step_matches_eager():
         loss_e, _ = warpbranch.forward(samples, dres, hand_face, _renderer(S, dev), (S, S), crit,
                                        hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)
         loss_e.backward()
-        assert abs(loss_g.item() - loss_e.item()) <= 1e-6
-        assert helpers.rel_err(gh_g.cpu().numpy(), h.grad.cpu().numpy()) < 1e-4
-        assert helpers.rel_err(go_g.cpu().numpy(), o.grad.cpu().numpy()) < 1e-4
+        assert loss_g.item() == loss_e.item()
+        assert torch.equal(gh_g, h.grad) and torch.equal(go_g, o.grad)
     # autograd entry: loss as a differentiable function of the predicted vertices
     h2 = dres[0]["recov_handverts3d"].detach().clone().requires_grad_(True)
     dres[0] = {"recov_handverts3d": h2, "recov_objverts3d": dres[0]["recov_objverts3d"].detach()}
     (gstep.apply(samples, dres) * 3.0).backward()
-    assert helpers.rel_err(h2.grad.cpu().numpy(), 3.0 * h.grad.cpu().numpy()) < 1e-4
+    assert helpers.rel_err(h2.grad.cpu().numpy(), 3.0 * h.grad.cpu().numpy()) < 1e-6
 
 
 def test_vertex_texture_mode_is_bit_identical_to_cubes():
@@ -216,7 +242,7 @@ def test_vertex_texture_mode_is_bit_identical_to_cubes():
         assert torch.equal(a, b)
 
 
-def test_graphed_step_accepts_uint8_frames():
+def test_graphed_step_accepts_uint8_frames(det_mode):
     """GraphedConsistStep.load with uint8 IMAGE / JITTERMASK (pinned host memory) gives what the equivalent fp32
     tensors (x / 255 - 0.5, x / 255, computed on the CPU like the reference's dataset workers do) give."""
     from handobjectconsist_b200.graphed import GraphedConsistStep
@@ -251,8 +277,8 @@ def test_graphed_step_accepts_uint8_frames():
     got = [t.clone() for t in gstep(us, ur)]
     assert ref[0].item() > 0
     assert abs(ref[0].item() - got[0].item()) <= 1e-6
-    for a, b in zip(ref[1:], got[1:]):  # float atomics: two replays of the same inputs agree to rounding, not bit for bit
-        assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item()
+    for a, b in zip(ref[1:], got[1:]):  # reproducible mode: the widened frames are bit-identical, so are the sums
+        assert (a - b).abs().max().item() <= 1e-6 * a.abs().max().item()
     # and a step captured from a uint8 example batch
     gstep2 = GraphedConsistStep(_renderer(S, dev), PyramidCriterion("l1"), (S, S), sc["faces"][0, :1552].to(dev), us, ur,
                                 hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=False)

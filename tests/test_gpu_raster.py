@@ -127,10 +127,33 @@ def test_backward_matches_oracle(dense, S, B):
     gf, gt = f.grad.cpu().numpy(), t.grad.cpu().numpy()
     _check_grads(gt, gt32, gt64)
     _check_grads(gf, gf32, gf64)
-    # a second run reproduces the gradients to rounding (float atomics reorder the sums)
+    # a second run reproduces the gradients to rounding (float atomics reorder the sums): bounded against the
+    # gradient scale here, bit for bit in the reproducible mode (test_backward_reproducible_mode)
     f2, t2, (rgb2, alpha2, depth2, _, _, _) = _run_function(faces, tex, S)
     ((rgb2 * _cuda(g_rgb)).sum() + (alpha2 * _cuda(g_alpha)).sum() + (depth2 * _cuda(g_depth)).sum()).backward()
-    assert helpers.rel_err(f2.grad.cpu().numpy(), gf) < 1e-4 and helpers.rel_err(t2.grad.cpu().numpy(), gt) < 1e-4
+    assert np.abs(f2.grad.cpu().numpy() - gf).max() <= 1e-3 * np.abs(gf).max()
+    assert np.abs(t2.grad.cpu().numpy() - gt).max() <= 1e-3 * np.abs(gt).max()
+
+
+@pytest.mark.parametrize("S,B", [(48, 2), (96, 2)])
+def test_backward_reproducible_mode(det_mode, S, B):
+    """HOC_TUNE_DETERMINISTIC: same parity bar against the oracle, and two runs give the same bits."""
+    faces, tex, _ = helpers.scene_faces(B, S, seed=1)
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    rng = np.random.default_rng(0)
+    g_rgb = rng.normal(size=ora["rgb_map"].shape).astype(np.float32)
+    g_alpha = rng.normal(size=ora["alpha_map"].shape).astype(np.float32)
+    g_depth = rng.normal(size=ora["depth_map"].shape).astype(np.float32)
+    gf32, gt32 = onmr.rasterize_backward(ora, g_rgb, g_alpha, g_depth)
+    runs = []
+    for _ in range(3):
+        f, t, (rgb, alpha, depth, _, _, _) = _run_function(faces, tex, S)
+        ((rgb * _cuda(g_rgb)).sum() + (alpha * _cuda(g_alpha)).sum() + (depth * _cuda(g_depth)).sum()).backward()
+        runs.append((f.grad.clone(), t.grad.clone()))
+    _check_grads(runs[0][0].cpu().numpy(), gf32)
+    _check_grads(runs[0][1].cpu().numpy(), gt32)
+    for gf, gt in runs[1:]:
+        assert torch.equal(gf, runs[0][0]) and torch.equal(gt, runs[0][1])
 
 
 def test_backward_partial_outputs():
@@ -179,9 +202,9 @@ def test_rasterize_rgbad_matches_oracle(aa):
     np.testing.assert_array_equal(out["face_inv_map"].cpu().numpy(), ora["face_inv_map"])
 
 
-def test_image_layout_backward_matches_raw_layout():
+def test_image_layout_backward_matches_raw_layout(det_mode):
     """The fused NCHW/flipped output path gives the same gradients as the reference-shaped path
-    followed by permute + flip."""
+    followed by permute + flip.  (Reproducible mode: both layouts add the same terms, only in another order.)"""
     from handobjectconsist_b200.neurender.rasterize import rasterize_rgbad
     S = 48
     faces, tex, _ = helpers.scene_faces(2, S, seed=8)
@@ -197,5 +220,5 @@ def test_image_layout_backward_matches_raw_layout():
     rgb = rgb.permute(0, 3, 1, 2).flip(2)
     assert torch.equal(rgb, o["rgb"])
     ((rgb * g_rgb).sum() + (alpha.flip(1) * g_a).sum() + (depth.flip(1) * g_d).sum()).backward()
-    assert helpers.rel_err(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-4
-    assert helpers.rel_err(t1.grad.cpu().numpy(), t2.grad.cpu().numpy()) < 1e-4
+    assert helpers.rel_err(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) < 1e-6
+    assert helpers.rel_err(t1.grad.cpu().numpy(), t2.grad.cpu().numpy()) < 1e-6
