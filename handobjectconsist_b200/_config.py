@@ -5,6 +5,10 @@
 # instrumented graph it uses to time kernels one at a time.
 overlap_streams = True
 
+# warpbranch.forward takes the fused frame-pair path (consist.py) when the configuration allows it; False forces the
+# operator-by-operator path (get_opticalflow + pair_consist), e.g. to compare the two in tests.
+fused_pair = True
+
 
 _SIDE_STREAMS = {}
 

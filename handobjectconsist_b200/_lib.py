@@ -56,6 +56,14 @@ SIGNATURES = {
     "hoc_cat_meshes": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
                                  _vp, _vp, _vp, _sz, _vp]),
+    "hoc_raster_backward_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
+                                    _i, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_warp_photo_forward_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp]),
+    "hoc_warp_photo_backward_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,
+                                          _vp, _vp]),
+    "hoc_pair_front": (_i, [_vp] * 5 + [_i, _vp] + [_vp, _i] * 5 + [_f] + [_i] * 6 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_pair_back": (_i, [_vp] * 4 + [_vp, _i] * 5 + [_f] + [_i] * 3 + [_vp, _vp] + [_i] * 4 + [_vp, _vp, _vp]),
     "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp]),
     "hoc_warp_photo_forward_acc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
@@ -79,7 +87,8 @@ KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_b
               "warp_photo_bwd": 5, "warp": 6, "warp_bwd": 7, "occlusion": 8, "mesh_gather": 9, "mesh_scatter": 10,
               "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16, "mano_fwd": 17,
               "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22, "unpack_u8": 23,
-              "hand_head_fwd": 24, "hand_head_bwd": 25, "recover_points_fwd": 26, "recover_points_bwd": 27}
+              "hand_head_fwd": 24, "hand_head_bwd": 25, "recover_points_fwd": 26, "recover_points_bwd": 27,
+              "pair_front": 28, "pair_back": 29}
 
 
 
@@ -144,6 +153,14 @@ def check(code, what):
     if code != 0:
         msg = lib().hoc_last_error().decode("utf-8", "replace")
         raise HocLibraryError(f"{what} failed with code {code}: {msg}")
+
+
+def ptr_pair(a, b):
+    """C array of two device pointers (per-direction outputs of the frame-pair kernels); None -> NULL entries."""
+    arr = (ctypes.c_void_p * 2)()
+    arr[0] = None if a is None else a.data_ptr()
+    arr[1] = None if b is None else b.data_ptr()
+    return arr
 
 
 def ptr(t):

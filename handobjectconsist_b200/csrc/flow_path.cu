@@ -573,6 +573,150 @@ extern "C" int hoc_cat_meshes(const float *hand_a, const float *obj_a, const flo
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* Frame-pair front end in ONE launch: what warpbranch.forward + get_opticalflow + Renderer.render do between the
+ * network's vertices and the rasterizer (warpbranch.py:50-52 batch_cat_meshes; opticalflow.py:98-103,121-123
+ * batch_proj2d x2, displacements, batch_vertex_textures; renderer.py:250-252,282 fill_back, nr.projection,
+ * vertices_to_faces), for BOTH renders of the pair, plus the 0xff fill of the z-buffer keys.  Face-parallel: a thread
+ * owns one face of one sample, projects its three vertices in both frames (the per-vertex arithmetic is a few dozen
+ * flops, recomputing it per corner is cheaper than a round trip of four [B,V,3] arrays through L2 and two more
+ * launches) and emits the face's records of both renders, both windings:
+ *   faces [2B,F',3,3]  rows 0..B-1: mesh 1 in NDC (render 1),  rows B..2B-1: mesh 2 (render 2)
+ *   tex   [2B,F',3,3]  vertex values [dx, dy, 1]: locs2 - locs1 for render 1, locs1 - locs2 for render 2
+ * Same device functions as hoc_flow_vertices / hoc_mesh_gather: bit-identical records.  Also writes the concatenated
+ * face table [2B,F,3] (hand first, object indices offset by Vh; rows B..2B-1 repeat rows 0..B-1) that the adjoint
+ * scatter of the stacked batch walks. */
+#define PF_THREADS 128
+__global__ void __launch_bounds__(PF_THREADS)
+hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__ obj1, const float *__restrict__ hand2,
+                      const float *__restrict__ obj2, const long long *__restrict__ hand_faces, int hand_faces_batched,
+                      const long long *__restrict__ obj_faces, HocCam C, int B, int Vh, int Vo, int Fh, int Fo,
+                      int fill_back, float *__restrict__ faces_out, float *__restrict__ tex_out,
+                      long long *__restrict__ face_table, uint4 *__restrict__ clear, long n_clear)
+{
+    if (clear != nullptr) {
+        const long nthreads = (long)gridDim.x * gridDim.y * PF_THREADS;
+        for (long i = ((long)blockIdx.y * gridDim.x + blockIdx.x) * PF_THREADS + threadIdx.x; i < n_clear; i += nthreads)
+            clear[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    }
+    /* staged records of this CTA's faces: [kind][thread][9], kind = faces1, tex1, faces2, tex2 */
+    __shared__ float s_rec[4][PF_THREADS * 9];
+    const int F = Fh + Fo, V = Vh + Vo;
+    const int Fout = fill_back ? 2 * F : F;
+    const int f0 = blockIdx.x * PF_THREADS;
+    const int f = f0 + threadIdx.x;
+    const int b = blockIdx.y;
+    if (f < F) {
+        long long iv[3];
+        if (f < Fh) {
+            const long long *fi = hand_faces + (hand_faces_batched ? (long)b * Fh * 3 : 0) + (long)f * 3;
+            iv[0] = fi[0]; iv[1] = fi[1]; iv[2] = fi[2];
+        } else {
+            const long long *fi = obj_faces + ((long)b * Fo + (f - Fh)) * 3;
+            iv[0] = fi[0] + Vh; iv[1] = fi[1] + Vh; iv[2] = fi[2] + Vh;
+        }
+        if (face_table != nullptr) { /* [2B,F,3]: the same table for both renders of sample b */
+            long long *ft = face_table + ((long)b * F + f) * 3;
+            ft[0] = iv[0]; ft[1] = iv[1]; ft[2] = iv[2];
+            ft += (long)B * F * 3;
+            ft[0] = iv[0]; ft[1] = iv[1]; ft[2] = iv[2];
+        }
+        const float *K1 = C.K1 + (long)b * C.K1_bs, *K2 = C.K2 + (long)b * C.K2_bs;
+        const float *R = C.R + (long)b * C.R_bs, *t = C.t + (long)b * C.t_bs, *d = C.dist + (long)b * C.dist_bs;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const long long i = (iv[k] >= 0 && iv[k] < V) ? iv[k] : 0; /* precondition 0 <= index < V */
+            const float *p1 = (i < Vh) ? hand1 + ((long)b * Vh + i) * 3 : obj1 + ((long)b * Vo + (i - Vh)) * 3;
+            const float *p2 = (i < Vh) ? hand2 + ((long)b * Vh + i) * 3 : obj2 + ((long)b * Vo + (i - Vh)) * 3;
+            const float v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+            float u1, w1, u2, w2, hz;
+            hoc_proj2d(K1, v1, &u1, &w1, &hz);
+            hoc_proj2d(K2, v2, &u2, &w2, &hz);
+            HocProj P;
+            hoc_ndc_project(K1, R, t, d, C.orig_size, v1, &P);
+            float *r = &s_rec[0][threadIdx.x * 9 + 3 * k];
+            r[0] = P.ndc[0]; r[1] = P.ndc[1]; r[2] = P.ndc[2];
+            r = &s_rec[1][threadIdx.x * 9 + 3 * k];
+            r[0] = u2 - u1; r[1] = w2 - w1; r[2] = 1.0f;
+            hoc_ndc_project(K2, R, t, d, C.orig_size, v2, &P);
+            r = &s_rec[2][threadIdx.x * 9 + 3 * k];
+            r[0] = P.ndc[0]; r[1] = P.ndc[1]; r[2] = P.ndc[2];
+            r = &s_rec[3][threadIdx.x * 9 + 3 * k];
+            r[0] = u1 - u2; r[1] = w1 - w2; r[2] = 1.0f;
+        }
+    }
+    __syncthreads();
+    const int nf = min(PF_THREADS, F - f0);
+    if (nf <= 0)
+        return;
+#pragma unroll
+    for (int kind = 0; kind < 4; kind++) {
+        float *base = (kind & 1) ? tex_out : faces_out;
+        const long row = (kind >= 2) ? (long)B + b : (long)b; /* render 2 lives in the second half of the batch */
+        float *front = base + (row * Fout + f0) * 9;
+        for (int i = threadIdx.x; i < nf * 9; i += PF_THREADS)
+            front[i] = s_rec[kind][i];
+        if (fill_back) { /* reversed winding (v2, v1, v0): vertices 0 and 2 of the record swap */
+            float *back = base + (row * Fout + F + f0) * 9;
+            for (int i = threadIdx.x; i < nf * 9; i += PF_THREADS) {
+                const int fl = i / 9, j = i - fl * 9;
+                const int src = (j < 3) ? j + 6 : ((j < 6) ? j : j - 6);
+                back[i] = s_rec[kind][fl * 9 + src];
+            }
+        }
+    }
+}
+
+/* Adjoint of the per-vertex part of hoc_pair_front: gradients of the NDC vertices / vertex attributes of both renders
+ * (what hoc_mesh_scatter produces from grad_faces / grad_textures of the stacked [2B] batch) -> gradients of the
+ * camera-space vertices of frame 1 (and of frame 2 when asked), written as [B,Vh+Vo,3] (hand first). */
+__global__ void __launch_bounds__(FP_THREADS)
+hoc_pair_back_kernel(const float *__restrict__ hand1, const float *__restrict__ obj1, const float *__restrict__ hand2,
+                     const float *__restrict__ obj2, HocCam C, int B, int Vh, int Vo,
+                     const float *__restrict__ g_ndc, const float *__restrict__ g_attr, int has_ndc1, int has_ndc2,
+                     int has_a12, int has_a21, float *__restrict__ grad_v1, float *__restrict__ grad_v2)
+{
+    const int b = blockIdx.y;
+    const int vi = blockIdx.x * FP_THREADS + threadIdx.x;
+    const int V = Vh + Vo;
+    if (vi >= V)
+        return;
+    const float *p1 = (vi < Vh) ? hand1 + ((long)b * Vh + vi) * 3 : obj1 + ((long)b * Vo + (vi - Vh)) * 3;
+    const float *p2 = (vi < Vh) ? hand2 + ((long)b * Vh + vi) * 3 : obj2 + ((long)b * Vo + (vi - Vh)) * 3;
+    const float v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+    const float *K1 = C.K1 + (long)b * C.K1_bs, *K2 = C.K2 + (long)b * C.K2_bs;
+    const float *R = C.R + (long)b * C.R_bs, *t = C.t + (long)b * C.t_bs, *d = C.dist + (long)b * C.dist_bs;
+    const long o1 = ((long)b * V + vi) * 3, o2 = (((long)B + b) * V + vi) * 3;
+    /* attrs12 = loc2 - loc1 (render 1, rows 0..B-1), attrs21 = loc1 - loc2 (render 2, rows B..2B-1) */
+    float gu1 = 0.f, gw1 = 0.f;
+    if (has_a12) {
+        gu1 -= g_attr[o1];
+        gw1 -= g_attr[o1 + 1];
+    }
+    if (has_a21) {
+        gu1 += g_attr[o2];
+        gw1 += g_attr[o2 + 1];
+    }
+    if (grad_v1 != nullptr) {
+        float gv[3] = {0.f, 0.f, 0.f};
+        hoc_proj2d_bwd(K1, v1, gu1, gw1, gv);
+        if (has_ndc1) {
+            const float g[3] = {g_ndc[o1], g_ndc[o1 + 1], g_ndc[o1 + 2]};
+            hoc_ndc_project_bwd(K1, R, t, d, C.orig_size, v1, g, gv);
+        }
+        grad_v1[o1] = gv[0]; grad_v1[o1 + 1] = gv[1]; grad_v1[o1 + 2] = gv[2];
+    }
+    if (grad_v2 != nullptr) {
+        float gv[3] = {0.f, 0.f, 0.f};
+        hoc_proj2d_bwd(K2, v2, -gu1, -gw1, gv);
+        if (has_ndc2) {
+            const float g[3] = {g_ndc[o2], g_ndc[o2 + 1], g_ndc[o2 + 2]};
+            hoc_ndc_project_bwd(K2, R, t, d, C.orig_size, v2, g, gv);
+        }
+        grad_v2[o1] = gv[0]; grad_v2[o1 + 1] = gv[1]; grad_v2[o1 + 2] = gv[2];
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 extern "C" int hoc_mesh_gather_clear(const float *verts, const float *attrs, const long long *faces_idx, int B, int V,
                                      int F, int fill_back, int tex_mode, float *faces_out, float *textures_out,
                                      void *clear, size_t clear_bytes, void *stream);
@@ -807,5 +951,63 @@ extern "C" int hoc_flow_vertices_backward(const float *verts1, const float *vert
                (hoc_flow_vertices_backward_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
                    verts1, verts2, C, V, grad_ndc1, grad_ndc2, grad_attrs12, grad_attrs21, grad_verts1, grad_verts2)));
     HOC_CHECK_LAUNCH("hoc_flow_vertices_backward_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_pair_front(const float *hand1, const float *obj1, const float *hand2, const float *obj2,
+                              const long long *hand_faces, int hand_faces_batched, const long long *obj_faces,
+                              const float *K1, int K1_batched, const float *K2, int K2_batched, const float *R,
+                              int R_batched, const float *t, int t_batched, const float *dist_coeffs, int dist_batched,
+                              float orig_size, int B, int Vh, int Vo, int Fh, int Fo, int fill_back, float *faces_out,
+                              float *textures_out, long long *face_table, void *clear, size_t clear_bytes, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && Vh >= 0 && Vo >= 0 && Fh >= 0 && Fo >= 0 && B <= 32767, "hoc_pair_front: bad shape");
+    HOC_CHECK_ARG(clear == nullptr || (clear_bytes % 16 == 0 && ((uintptr_t)clear & 15) == 0),
+                  "hoc_pair_front: clear buffer must be 16-byte aligned with a size multiple of 16");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B == 0 || Fh + Fo == 0) {
+        if (clear != nullptr && cudaMemsetAsync(clear, 0xff, clear_bytes, st) != cudaSuccess) {
+            hoc_set_error("hoc_pair_front: memset failed");
+            return HOC_ERR_CUDA;
+        }
+        return HOC_OK;
+    }
+    HOC_CHECK_ARG((Vh == 0 || (hand1 && hand2)) && (Vo == 0 || (obj1 && obj2)), "hoc_pair_front: NULL vertices");
+    HOC_CHECK_ARG((Fh == 0 || hand_faces) && (Fo == 0 || obj_faces), "hoc_pair_front: NULL face table");
+    HOC_CHECK_ARG(K1 && K2 && R && t && dist_coeffs && faces_out && textures_out, "hoc_pair_front: NULL argument");
+    HocCam C = hoc_make_cam(K1, K1_batched, K2, K2_batched, R, R_batched, t, t_batched, dist_coeffs, dist_batched,
+                            orig_size);
+    dim3 grid((Fh + Fo + PF_THREADS - 1) / PF_THREADS, B);
+    HOC_LAUNCH(HOC_K_PAIR_FRONT, st,
+               (hoc_pair_front_kernel<<<grid, PF_THREADS, 0, st>>>(hand1, obj1, hand2, obj2, hand_faces,
+                                                                   hand_faces_batched, obj_faces, C, B, Vh, Vo, Fh, Fo,
+                                                                   fill_back, faces_out, textures_out, face_table,
+                                                                   (uint4 *)clear, (long)(clear_bytes / 16))));
+    HOC_CHECK_LAUNCH("hoc_pair_front_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_pair_back(const float *hand1, const float *obj1, const float *hand2, const float *obj2,
+                             const float *K1, int K1_batched, const float *K2, int K2_batched, const float *R,
+                             int R_batched, const float *t, int t_batched, const float *dist_coeffs, int dist_batched,
+                             float orig_size, int B, int Vh, int Vo, const float *grad_ndc, const float *grad_attrs,
+                             int has_ndc1, int has_ndc2, int has_attrs12, int has_attrs21, float *grad_verts1,
+                             float *grad_verts2, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && Vh >= 0 && Vo >= 0 && B <= 32767, "hoc_pair_back: bad shape");
+    if (B == 0 || Vh + Vo == 0 || (grad_verts1 == nullptr && grad_verts2 == nullptr))
+        return HOC_OK;
+    HOC_CHECK_ARG((Vh == 0 || (hand1 && hand2)) && (Vo == 0 || (obj1 && obj2)) && K1 && K2 && R && t && dist_coeffs,
+                  "hoc_pair_back: NULL argument");
+    HOC_CHECK_ARG((!(has_ndc1 || has_ndc2) || grad_ndc) && (!(has_attrs12 || has_attrs21) || grad_attrs),
+                  "hoc_pair_back: gradient flagged but NULL");
+    HocCam C = hoc_make_cam(K1, K1_batched, K2, K2_batched, R, R_batched, t, t_batched, dist_coeffs, dist_batched,
+                            orig_size);
+    dim3 grid((Vh + Vo + FP_THREADS - 1) / FP_THREADS, B);
+    HOC_LAUNCH(HOC_K_PAIR_BACK, (cudaStream_t)stream,
+               (hoc_pair_back_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   hand1, obj1, hand2, obj2, C, B, Vh, Vo, grad_ndc, grad_attrs, has_ndc1, has_ndc2, has_attrs12,
+                   has_attrs21, grad_verts1, grad_verts2)));
+    HOC_CHECK_LAUNCH("hoc_pair_back_kernel");
     return HOC_OK;
 }

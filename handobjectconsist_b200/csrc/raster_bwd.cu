@@ -198,13 +198,19 @@ __device__ __forceinline__ void hoc_k4_pixel_combo(float ax, float ay, float bx,
  * work (all of them when the pseudo-gradient is wanted, else those with a texture / depth gradient).  One global
  * atomic per CTA reserves the tile's list slots.
  */
-template <bool K4>
 __global__ void __launch_bounds__(256)
-hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb,
-                           const float *__restrict__ g_alpha, int S, int layout, int list_all, int *__restrict__ ext,
-                           int *__restrict__ cov_count, int2 *__restrict__ cov_list, float *__restrict__ zero_a,
-                           long n_a, float *__restrict__ zero_b, long n_b)
+hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
+                           const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S, int layout,
+                           int k4_samples, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
+                           int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
+                           float *__restrict__ zero_b, long n_b)
 {
+    /* samples [0, k4_samples) get the pseudo-gradient (spans + every covered pixel listed); the others only list the
+     * pixels that have a texture (non-zero dL/drgb) or depth gradient */
+    const bool K4 = (int)blockIdx.z < k4_samples;
+    const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
+    const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
+    const int list_all = K4 ? 1 : list_all_rest;
     { /* zero-fill of the two gradient outputs (accumulated with atomics by the later passes), spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 32 +
@@ -410,15 +416,15 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
 
 /*
  * Cover pass: the work of the covered pixels, spread evenly over the GPU (the scan pass listed them).
- * K4 = false: 128 threads, one listed pixel each -> texture / depth gradient.
+ * K4 (per sample: b < k4_samples) = false: one listed pixel per thread -> texture / depth gradient.
  * K4 = true:  224 threads work on 32 listed pixels at a time: warp c < 6 runs (edge c >> 1, axis c & 1) of the
  *             pseudo-gradient for the 32 pixels (uniform edge / axis per warp: inward-scan terms into grad_faces,
  *             outward scans queued on their lines), warp 6 their texture / depth gradient.  Warps are independent.
  */
 #define CV_THREADS_K4 224
 #define CV_THREADS 128
-template <bool TS2, bool K4>
-__global__ void __launch_bounds__(K4 ? CV_THREADS_K4 : CV_THREADS)
+template <bool TS2>
+__global__ void __launch_bounds__(CV_THREADS_K4)
 hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                             const float *__restrict__ rgb, const float *__restrict__ weight_map,
                             const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
@@ -428,14 +434,16 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                             float *__restrict__ acc_d, int *__restrict__ line_count,
                             unsigned short *__restrict__ emitters, float *__restrict__ grad_faces,
                             float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gf,
-                            unsigned long long *__restrict__ det_gt, unsigned long long *__restrict__ det_ad)
+                            unsigned long long *__restrict__ det_gt, unsigned long long *__restrict__ det_ad,
+                            int k4_samples)
 {
     const int b = blockIdx.y;
     const int count = min(cov_count[b], S * S);
     const int2 *list = cov_list + (long)b * S * S;
     const int32_t *idx = face_index_map + (long)b * S * S;
+    const bool K4 = b < k4_samples; /* uniform per CTA */
     if (!K4) {
-        for (int i = blockIdx.x * CV_THREADS + threadIdx.x; i < count; i += gridDim.x * CV_THREADS) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
             const int2 e = list[i];
             const int yi = e.x / S, xi = e.x - yi * S;
             hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, e.y, xi, yi, F, S, ts, near_, far_,
@@ -751,6 +759,13 @@ extern "C" size_t hoc_raster_backward_workspace_bytes_ex(int B, int F, int S, in
     return hoc_bwd_workspace(nullptr, B, F, S, tex_n, g_hoc_deterministic != 0).total;
 }
 
+extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures, const int32_t *face_index_map,
+                                      const float *rgb, const float *weight_map, const float *depth,
+                                      const float *grad_rgb, const float *grad_alpha, const float *grad_depth, int B,
+                                      int F, int S, int ts, float near_, float far_, float eps, int layout,
+                                      int use_alpha, int tex_grad_mode, int geom_samples, float *grad_faces,
+                                      float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
+
 extern "C" int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
                                    const float *rgb, const float *weight_map, const float *depth,
                                    const float *grad_rgb, const float *grad_alpha,
@@ -758,7 +773,24 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                    float eps, int layout, int use_alpha, int tex_grad_mode, float *grad_faces,
                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
 {
+    return hoc_raster_backward_ex(faces, textures, face_index_map, rgb, weight_map, depth, grad_rgb, grad_alpha,
+                                  grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode, B,
+                                  grad_faces, grad_textures, workspace, workspace_bytes, stream);
+}
+
+/* geom_samples: the pseudo-gradient (backward_pixel_map) is computed for samples [0, geom_samples) only; the rows of
+ * grad_faces of the other samples receive the depth gradient alone (zero without grad_depth).  The frame-pair path
+ * stacks both renders of a pair in one batch and needs the geometry gradient of the first one only. */
+extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures, const int32_t *face_index_map,
+                                      const float *rgb, const float *weight_map, const float *depth,
+                                      const float *grad_rgb, const float *grad_alpha, const float *grad_depth, int B,
+                                      int F, int S, int ts, float near_, float far_, float eps, int layout,
+                                      int use_alpha, int tex_grad_mode, int geom_samples, float *grad_faces,
+                                      float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
+{
     (void)textures;
+    HOC_CHECK_ARG(geom_samples >= 0 && geom_samples <= B, "hoc_raster_backward: geom_samples %d outside [0, %d]",
+                  geom_samples, B);
     HOC_CHECK_ARG(tex_grad_mode == HOC_TEX_GRAD_CUBE || (tex_grad_mode == HOC_TEX_GRAD_VERTEX && ts == 2),
                   "hoc_raster_backward: tex_grad_mode %d (vertex mode needs texture_size 2, got %d)", tex_grad_mode, ts);
     HOC_CHECK_ARG(B >= 0 && F >= 0, "hoc_raster_backward: negative batch (%d) or face count (%d)", B, F);
@@ -784,7 +816,8 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         return HOC_ERR_WORKSPACE;
     }
     const float *g_alpha = use_alpha ? grad_alpha : nullptr;
-    const bool k4 = grad_faces != nullptr && (grad_rgb != nullptr || g_alpha != nullptr);
+    const int k4_samples = (grad_faces != nullptr && (grad_rgb != nullptr || g_alpha != nullptr)) ? geom_samples : 0;
+    const bool k4 = k4_samples > 0;
     const bool want_depth = grad_faces != nullptr && grad_depth != nullptr;
     const size_t tex_bytes = (tex_grad_mode == HOC_TEX_GRAD_VERTEX)
                                  ? sizeof(float) * 9 * (size_t)B * F
@@ -806,37 +839,26 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
         /* without the pseudo-gradient only pixels with a texture gradient (non-zero dL/drgb) or a depth
          * gradient have work */
         dim3 pg((S + 31) / 32, (S + 31) / 32, B);
-        const int list_all = (k4 || want_depth) ? 1 : 0;
-        if (k4)
-            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
-                       (hoc_raster_bwd_scan_kernel<true><<<pg, dim3(32, 8), 0, st>>>(
-                           face_index_map, grad_rgb, g_alpha, S, layout, list_all, w.ext, w.cov_count, w.cov_list, grad_faces,
-                           n_gf, grad_textures, n_gt)));
-        else
-            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
-                       (hoc_raster_bwd_scan_kernel<false><<<pg, dim3(32, 8), 0, st>>>(
-                           face_index_map, gt != nullptr ? grad_rgb : nullptr, nullptr, S, layout, list_all, w.ext,
-                           w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt)));
+        HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
+                   (hoc_raster_bwd_scan_kernel<<<pg, dim3(32, 8), 0, st>>>(
+                       face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples,
+                       want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
     }
     {
         const long npix = (long)S * S;
         const int per = k4 ? 32 : CV_THREADS;
         dim3 cg((unsigned)((npix + per - 1) / per < 296 ? (npix + per - 1) / per : 296), B);
-#define HOC_COVER_LAUNCH(TS2, K4)                                                                                    \
-    HOC_LAUNCH(K4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, st,                                      \
-               (hoc_raster_bwd_cover_kernel<TS2, K4><<<cg, K4 ? CV_THREADS_K4 : CV_THREADS, 0, st>>>(                 \
+#define HOC_COVER_LAUNCH(TS2)                                                                                        \
+    HOC_LAUNCH(k4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, st,                                      \
+               (hoc_raster_bwd_cover_kernel<TS2><<<cg, k4 ? CV_THREADS_K4 : CV_THREADS, 0, st>>>(                     \
                    faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
                    eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
-                   w.line_count, w.emitters, grad_faces, gt, w.det_gf, w.det_gt, w.det_ad)))
-        if (ts == 2 && k4)
-            HOC_COVER_LAUNCH(true, true);
-        else if (ts == 2)
-            HOC_COVER_LAUNCH(true, false);
-        else if (k4)
-            HOC_COVER_LAUNCH(false, true);
+                   w.line_count, w.emitters, grad_faces, gt, w.det_gf, w.det_gt, w.det_ad, k4_samples)))
+        if (ts == 2)
+            HOC_COVER_LAUNCH(true);
         else
-            HOC_COVER_LAUNCH(false, false);
+            HOC_COVER_LAUNCH(false);
 #undef HOC_COVER_LAUNCH
         HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
     }
@@ -861,11 +883,11 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     }
     if (k4) {
         if (g_line_seg >= 16)
-            e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w,
-                                    grad_faces, st);
+            e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
+                                    use_alpha, w, grad_faces, st);
         else
-            e = hoc_launch_line<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, B, F, S, eps, layout, use_alpha, w,
-                                   grad_faces, st);
+            e = hoc_launch_line<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
+                                   use_alpha, w, grad_faces, st);
         if (e != cudaSuccess) {
             hoc_set_error("hoc_raster_backward: line pass: %s",
                           cudaGetErrorString(e));

@@ -381,6 +381,273 @@ hoc_warp_photo_backward_kernel(const float *__restrict__ src, const float *__res
     *reinterpret_cast<float2 *>(grad_flow + ((long)b * npix + pix) * 2) = g;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Both directions of pair_consist in ONE launch, four pixels per thread (the frame-pair fast path).
+ *
+ * blockIdx.z = direction k (imgflowarp.py:80-107): k = 0 warps image_ref with flow21 against image (jitter mask of
+ * frame 2), k = 1 warps image with flow12 against image_ref (jitter mask of the reference frame).  A thread owns four
+ * consecutive pixels of a row: flows, targets, the centre jitter value and every dense output move as 16-byte
+ * accesses; only the bilinear taps (data-dependent addresses) stay scalar.
+ *
+ * VIS = false (training): the visualisation returns of pair_consist (`warps`, `diffs`, `warp_mask`) are not
+ * produced.  What is left per pixel is the loss term and the valid mask, and both vanish where the rendered flow is
+ * zero (valid = ... & (flow_x != 0), imgflowarp.py:93-101) -- 93-95 % of a frame: such a pixel costs its 8-byte flow
+ * and 3 bytes of masks, nothing else.  VIS = true produces everything the reference returns. */
+struct HocPairDir {
+    const float *src, *target, *flow, *jitter;
+    float *warped, *warp_mask, *diff;
+    uint8_t *valid_mask, *flow_mask;
+    double *sums;
+};
+
+/* one pixel of one direction: sample position -> masks -> |warp - target|; v / d / wm get the three channel values
+ * when VIS.  Arithmetic identical to hoc_warp_photo_forward_kernel<3, 3> (same helpers, same order). */
+template <bool VIS>
+__device__ __forceinline__ bool hoc_pair_pixel(const float *__restrict__ sb, const float *__restrict__ jb,
+                                               const float *tv, float jc, int x, int y, float fx, float fy, int H,
+                                               int W, int npix, float inv_w, float inv_h, float thresh, float *v,
+                                               float *d, float *wm, float *sum_d)
+{
+    HocTaps T;
+    hoc_bilinear_taps_inv(x, y, fx, fy, H, W, inv_w, inv_h, T);
+    const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
+    HocTapsFlat F;
+    hoc_flatten_taps(T, H, W, F);
+    float sv[3][4], jv[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            sv[c][k] = __ldg(sb + (size_t)c * npix + F.o[k]);
+    float wm0 = m;
+    if (jb != nullptr) {
+#pragma unroll
+        for (int c = 0; c < (VIS ? 3 : 1); c++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                jv[c][k] = __ldg(jb + (size_t)c * npix + F.o[k]);
+#pragma unroll
+        for (int c = 0; c < (VIS ? 3 : 1); c++) {
+            const float wj = __fmul_rn(hoc_flat_combine(jv[c], F), m);
+            const float w = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
+            if (VIS)
+                wm[c] = w;
+            if (c == 0)
+                wm0 = w;
+        }
+    } else if (VIS) {
+        wm[0] = wm[1] = wm[2] = m;
+    }
+    const bool valid = (jb != nullptr) ? ((wm0 != 0.0f) && !(fx == 0.0f) && (jc == 1.0f)) : ((m != 0.0f) && !(fx == 0.0f));
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float val = __fmul_rn(hoc_flat_combine(sv[c], F), m);
+        const float dd = fabsf(__fsub_rn(val, tv[c]));
+        if (VIS) {
+            v[c] = val;
+            d[c] = dd;
+        }
+        acc += dd; /* channel order r, g, b like the single-direction kernel */
+    }
+    *sum_d = acc;
+    return valid;
+}
+
+template <bool VIS>
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_warp_photo_pair_forward_kernel(HocPairDir D0, HocPairDir D1, int H, int W, float inv_w, float inv_h, float thresh)
+{
+    __shared__ float s_sum[WP_THREADS / 32];
+    __shared__ float s_cnt[WP_THREADS / 32];
+    const HocPairDir &D = blockIdx.z ? D1 : D0;
+    const int b = blockIdx.y;
+    const int npix = H * W, W4 = W >> 2;
+    const int q = blockIdx.x * WP_THREADS + threadIdx.x; /* group of four pixels */
+    float my_sum = 0.0f, my_cnt = 0.0f;
+    if (q < H * W4) {
+        const int y = q / W4, x0 = (q - y * W4) << 2;
+        const size_t pix = (size_t)y * W + x0;
+        const float4 f01 = *reinterpret_cast<const float4 *>(D.flow + ((size_t)b * npix + pix) * 2);
+        const float4 f23 = *reinterpret_cast<const float4 *>(D.flow + ((size_t)b * npix + pix) * 2 + 4);
+        const float fx[4] = {f01.x, f01.z, f23.x, f23.z}, fy[4] = {f01.y, f01.w, f23.y, f23.w};
+        unsigned vbits = 0;
+        const bool any = VIS || !(fx[0] == 0.0f) || !(fx[1] == 0.0f) || !(fx[2] == 0.0f) || !(fx[3] == 0.0f);
+        if (any) {
+            const float *sb = D.src + (size_t)b * 3 * npix;
+            const float *jb = (D.jitter != nullptr) ? D.jitter + (size_t)b * 3 * npix : nullptr;
+            const float *tb = D.target + (size_t)b * 3 * npix + pix;
+            const float4 t0 = *reinterpret_cast<const float4 *>(tb), t1 = *reinterpret_cast<const float4 *>(tb + npix),
+                         t2 = *reinterpret_cast<const float4 *>(tb + 2 * (size_t)npix);
+            const float4 jc4 = (jb != nullptr) ? *reinterpret_cast<const float4 *>(jb + pix)
+                                               : make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            const float tr[4] = {t0.x, t0.y, t0.z, t0.w}, tg[4] = {t1.x, t1.y, t1.z, t1.w},
+                        tbl[4] = {t2.x, t2.y, t2.z, t2.w}, jc[4] = {jc4.x, jc4.y, jc4.z, jc4.w};
+            float ov[3][4], od[3][4], om[3][4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (VIS || !(fx[j] == 0.0f)) {
+                    const float tv[3] = {tr[j], tg[j], tbl[j]};
+                    float v[3], d[3], wm[3], sd;
+                    const bool valid = hoc_pair_pixel<VIS>(sb, jb, tv, jc[j], x0 + j, y, fx[j], fy[j], H, W, npix, inv_w,
+                                                           inv_h, thresh, v, d, wm, &sd);
+                    if (VIS) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            ov[c][j] = v[c];
+                            od[c][j] = d[c];
+                            om[c][j] = wm[c];
+                        }
+                    }
+                    if (valid) {
+                        vbits |= 1u << (8 * j);
+                        my_sum += sd;
+                        my_cnt += 3.0f;
+                    }
+                }
+            }
+            if (VIS) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const size_t o = ((size_t)b * 3 + c) * npix + pix;
+                    if (D.warped != nullptr)
+                        *reinterpret_cast<float4 *>(D.warped + o) = make_float4(ov[c][0], ov[c][1], ov[c][2], ov[c][3]);
+                    if (D.diff != nullptr)
+                        *reinterpret_cast<float4 *>(D.diff + o) = make_float4(od[c][0], od[c][1], od[c][2], od[c][3]);
+                    if (D.warp_mask != nullptr)
+                        *reinterpret_cast<float4 *>(D.warp_mask + o) = make_float4(om[c][0], om[c][1], om[c][2], om[c][3]);
+                }
+            }
+        }
+        if (D.valid_mask != nullptr)
+            *reinterpret_cast<unsigned *>(D.valid_mask + (size_t)b * npix + pix) = vbits;
+        if (D.flow_mask != nullptr) { /* ~(flow == 0), both components (imgflowarp.py:93,99) */
+            uint2 fm;
+            fm.x = (!(fx[0] == 0.0f) ? 1u : 0u) | (!(fy[0] == 0.0f) ? 0x100u : 0u) | (!(fx[1] == 0.0f) ? 0x10000u : 0u) |
+                   (!(fy[1] == 0.0f) ? 0x1000000u : 0u);
+            fm.y = (!(fx[2] == 0.0f) ? 1u : 0u) | (!(fy[2] == 0.0f) ? 0x100u : 0u) | (!(fx[3] == 0.0f) ? 0x10000u : 0u) |
+                   (!(fy[3] == 0.0f) ? 0x1000000u : 0u);
+            *reinterpret_cast<uint2 *>(D.flow_mask + ((size_t)b * npix + pix) * 2) = fm;
+        }
+    }
+    my_sum = hoc_warp_sum(my_sum);
+    my_cnt = hoc_warp_sum(my_cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_sum[warp] = my_sum;
+        s_cnt[warp] = my_cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float a = (lane < WP_THREADS / 32) ? s_sum[lane] : 0.0f;
+        float n = (lane < WP_THREADS / 32) ? s_cnt[lane] : 0.0f;
+        a = hoc_warp_sum(a);
+        n = hoc_warp_sum(n);
+        if (lane == 0 && n > 0.0f) {
+            atomicAdd(&D.sums[2 * b + 0], rint((double)a * WP_SUM_SCALE));
+            atomicAdd(&D.sums[2 * b + 1], (double)n);
+        }
+    }
+}
+
+/* Backward of both directions, fused with hoc_flow_finalize_backward: d loss / d flow (hoc_warp_photo_backward_kernel's
+ * arithmetic) times mult = d flow / d rgb, written straight into the incoming gradient of the two renders' rgb maps
+ * ([B,3,S,S], image layout; zero outside the H x W crop and in the third channel).  blockIdx.z = direction k: k = 0
+ * differentiates flow21 (render 2), k = 1 flow12 (render 1).  Four pixels of a raster row per thread. */
+struct HocPairBwdDir {
+    const float *src, *target, *flow, *mult;
+    const uint8_t *valid_mask;
+    const double *sums;
+    float *grad_rgb;  /* [B,3,S,S] or NULL (direction skipped) */
+    float *grad_flow; /* [B,H,W,2] or NULL: the flow gradient itself, for callers that want it */
+    int active;       /* 0: this direction carries no loss (use_backward = False): zeros */
+};
+
+__global__ void __launch_bounds__(WP_THREADS)
+hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const float *__restrict__ grad_loss, int S, int H,
+                                    int W, float inv_w, float inv_h)
+{
+    const HocPairBwdDir &D = blockIdx.z ? D1 : D0;
+    if (D.grad_rgb == nullptr && D.grad_flow == nullptr)
+        return;
+    const int b = blockIdx.y;
+    const int S4 = S >> 2;
+    const int q = blockIdx.x * WP_THREADS + threadIdx.x;
+    if (q >= S * S4)
+        return;
+    const int y = q / S4, x0 = (q - y * S4) << 2;
+    float gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
+    float gfx[4] = {0.f, 0.f, 0.f, 0.f}, gfy[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool inside = y < H && x0 < W; /* W % 4 == 0: a group is inside or outside as a whole */
+    const long npix = (long)H * W;
+    if (inside && D.active) {
+        const long pix = (long)y * W + x0;
+        const unsigned vb = *reinterpret_cast<const unsigned *>(D.valid_mask + (long)b * npix + pix);
+        if (vb != 0u) {
+            const float4 f01 = *reinterpret_cast<const float4 *>(D.flow + ((long)b * npix + pix) * 2);
+            const float4 f23 = *reinterpret_cast<const float4 *>(D.flow + ((long)b * npix + pix) * 2 + 4);
+            const float4 mu = *reinterpret_cast<const float4 *>(D.mult + (long)b * npix + pix);
+            const float fx[4] = {f01.x, f01.z, f23.x, f23.z}, fy[4] = {f01.y, f01.w, f23.y, f23.w};
+            const float mm[4] = {mu.x, mu.y, mu.z, mu.w};
+            const float cnt = (float)D.sums[2 * b + 1];
+            const float scale = grad_loss[b] / fmaxf(cnt, 1.0f);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!((vb >> (8 * j)) & 0xffu))
+                    continue;
+                HocTaps T;
+                hoc_bilinear_taps_inv(x0 + j, y, fx[j], fy[j], H, W, inv_w, inv_h, T);
+                const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
+                float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float *plane = D.src + ((long)b * 3 + c) * npix;
+                    const float v = hoc_plane_sample(plane, W, T); /* valid => in-bounds mask is 1 */
+                    const float d = v - D.target[((long)b * 3 + c) * npix + pix + j];
+                    const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+                    const float go = scale * sgn;
+                    const float *p = plane + (long)T.y0 * W + T.x0;
+                    if (T.b_nw) {
+                        const float v0 = __ldg(p);
+                        gix -= v0 * (y_se - T.iy) * go;
+                        giy -= v0 * (x_se - T.ix) * go;
+                    }
+                    if (T.b_ne) {
+                        const float v1 = __ldg(p + 1);
+                        gix += v1 * (y_se - T.iy) * go;
+                        giy -= v1 * (T.ix - x_nw) * go;
+                    }
+                    if (T.b_sw) {
+                        const float v2 = __ldg(p + W);
+                        gix -= v2 * (T.iy - y_nw) * go;
+                        giy += v2 * (x_se - T.ix) * go;
+                    }
+                    if (T.b_se) {
+                        const float v3 = __ldg(p + W + 1);
+                        gix += v3 * (T.iy - y_nw) * go;
+                        giy += v3 * (T.ix - x_nw) * go;
+                    }
+                }
+                gfx[j] = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
+                gfy[j] = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
+                gx[j] = gfx[j] * mm[j]; /* hoc_flow_finalize_backward_kernel */
+                gy[j] = gfy[j] * mm[j];
+            }
+        }
+    }
+    if (D.grad_rgb != nullptr) {
+        float *dst = D.grad_rgb + (long)b * 3 * S * S + (long)y * S + x0;
+        *reinterpret_cast<float4 *>(dst) = make_float4(gx[0], gx[1], gx[2], gx[3]);
+        *reinterpret_cast<float4 *>(dst + (long)S * S) = make_float4(gy[0], gy[1], gy[2], gy[3]);
+        *reinterpret_cast<float4 *>(dst + 2l * S * S) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (D.grad_flow != nullptr && inside) {
+        float *dst = D.grad_flow + ((long)b * npix + (long)y * W + x0) * 2;
+        *reinterpret_cast<float4 *>(dst) = make_float4(gfx[0], gfy[0], gfx[1], gfy[1]);
+        *reinterpret_cast<float4 *>(dst + 4) = make_float4(gfx[2], gfy[2], gfx[3], gfy[3]);
+    }
+}
+
 /* Plain warp(): out = grid_sample(x, grid(flow)) * mask.  flow is NCHW [B,2,H,W] like the
  * reference's argument.  mode 0 = bilinear, 1 = nearest. */
 __global__ void __launch_bounds__(WP_THREADS)
@@ -669,6 +936,98 @@ extern "C" int hoc_warp_backward(const float *x, const float *flow_nchw, const f
                (hoc_warp_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(x, flow_nchw, grad_out, C, H, W,
                                                                                         thresh, grad_flow_nchw)));
     HOC_CHECK_LAUNCH("hoc_warp_backward_kernel");
+    return HOC_OK;
+}
+
+
+/* ---- frame-pair entry points (both directions, one launch each way) ----------------------------------------- */
+static bool hoc_aligned16(const void *p) { return (((uintptr_t)p) & 15) == 0; }
+
+extern "C" int hoc_warp_photo_forward_pair(const float *image_ref, const float *image, const float *flow12,
+                                           const float *flow21, const float *jitter_ref, const float *jitter, int B,
+                                           int H, int W, float thresh, int visuals, float *const *warped,
+                                           float *const *warp_mask, float *const *diff, uint8_t *const *valid_mask,
+                                           uint8_t *const *flow_mask, double *sums, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && H >= 1 && W >= 4 && (W % 4) == 0 && (long)H * W < (1l << 29),
+                  "hoc_warp_photo_forward_pair: bad shape B=%d H=%d W=%d (W must be a multiple of 4)", B, H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_warp_photo_forward_pair: batch %d exceeds 65535", B);
+    HOC_CHECK_ARG(sums != nullptr && valid_mask != nullptr, "hoc_warp_photo_forward_pair: sums / valid_mask are required");
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(image_ref && image && flow12 && flow21 && valid_mask[0] && valid_mask[1],
+                  "hoc_warp_photo_forward_pair: NULL input");
+    HOC_CHECK_ARG((jitter_ref == nullptr) == (jitter == nullptr), "hoc_warp_photo_forward_pair: one jitter mask missing");
+    HocPairDir D[2];
+    for (int k = 0; k < 2; k++) {
+        D[k].src = k == 0 ? image_ref : image;
+        D[k].target = k == 0 ? image : image_ref;
+        D[k].flow = k == 0 ? flow21 : flow12;
+        D[k].jitter = k == 0 ? jitter : jitter_ref;
+        D[k].warped = (visuals && warped) ? warped[k] : nullptr;
+        D[k].warp_mask = (visuals && warp_mask) ? warp_mask[k] : nullptr;
+        D[k].diff = (visuals && diff) ? diff[k] : nullptr;
+        D[k].valid_mask = valid_mask[k];
+        D[k].flow_mask = flow_mask ? flow_mask[k] : nullptr;
+        D[k].sums = sums + 2 * (size_t)B * k;
+        HOC_CHECK_ARG(hoc_aligned16(D[k].src) && hoc_aligned16(D[k].target) && hoc_aligned16(D[k].flow) &&
+                          hoc_aligned16(D[k].jitter) && hoc_aligned16(D[k].warped) && hoc_aligned16(D[k].warp_mask) &&
+                          hoc_aligned16(D[k].diff) && (((uintptr_t)D[k].valid_mask) & 3) == 0 &&
+                          (((uintptr_t)D[k].flow_mask) & 7) == 0,
+                      "hoc_warp_photo_forward_pair: tensors must be 16-byte aligned");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(sums, 0, sizeof(double) * 4 * (size_t)B, st) != cudaSuccess) {
+        hoc_set_error("hoc_warp_photo_forward_pair: memset failed");
+        return HOC_ERR_CUDA;
+    }
+    const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1), inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
+    const long groups = (long)H * (W / 4);
+    dim3 grid((unsigned)((groups + WP_THREADS - 1) / WP_THREADS), B, 2);
+    if (visuals)
+        HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
+                   (hoc_warp_photo_pair_forward_kernel<true><<<grid, WP_THREADS, 0, st>>>(D[0], D[1], H, W, inv_w, inv_h, thresh)));
+    else
+        HOC_LAUNCH(HOC_K_WARP_PHOTO_FWD, st,
+                   (hoc_warp_photo_pair_forward_kernel<false><<<grid, WP_THREADS, 0, st>>>(D[0], D[1], H, W, inv_w, inv_h, thresh)));
+    HOC_CHECK_LAUNCH("hoc_warp_photo_pair_forward_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float *image, const float *flow12,
+                                            const float *flow21, const uint8_t *const *valid_mask, const double *sums,
+                                            const float *mult1, const float *mult2, const float *grad_loss, int B, int S,
+                                            int H, int W, int use_backward, float *grad_rgb1, float *grad_rgb2,
+                                            float *grad_flow12, float *grad_flow21, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && S >= 4 && (S % 4) == 0 && H >= 1 && H <= S && W >= 4 && W <= S && (W % 4) == 0,
+                  "hoc_warp_photo_backward_pair: bad shape B=%d S=%d H=%d W=%d (S, W multiples of 4)", B, S, H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_warp_photo_backward_pair: batch %d exceeds 65535", B);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(image_ref && image && flow12 && flow21 && valid_mask && valid_mask[0] && valid_mask[1] && sums &&
+                      grad_loss,
+                  "hoc_warp_photo_backward_pair: NULL argument");
+    HOC_CHECK_ARG((grad_rgb1 == nullptr || mult1 != nullptr) && (grad_rgb2 == nullptr || mult2 != nullptr),
+                  "hoc_warp_photo_backward_pair: grad_rgb requested without mult");
+    HocPairBwdDir D[2];
+    /* direction 0: warp(image_ref, flow21) vs image -> d / d flow21 -> render 2; direction 1: the reverse */
+    D[0].src = image_ref; D[0].target = image; D[0].flow = flow21; D[0].mult = mult2; D[0].valid_mask = valid_mask[0];
+    D[0].sums = sums; D[0].grad_rgb = grad_rgb2; D[0].grad_flow = grad_flow21; D[0].active = 1;
+    D[1].src = image; D[1].target = image_ref; D[1].flow = flow12; D[1].mult = mult1; D[1].valid_mask = valid_mask[1];
+    D[1].sums = sums + 2 * (size_t)B; D[1].grad_rgb = grad_rgb1; D[1].grad_flow = grad_flow12;
+    D[1].active = use_backward ? 1 : 0;
+    for (int k = 0; k < 2; k++)
+        HOC_CHECK_ARG(hoc_aligned16(D[k].flow) && hoc_aligned16(D[k].mult) && hoc_aligned16(D[k].grad_rgb) &&
+                          hoc_aligned16(D[k].grad_flow) && (((uintptr_t)D[k].valid_mask) & 3) == 0,
+                      "hoc_warp_photo_backward_pair: tensors must be 16-byte aligned");
+    const long groups = (long)S * (S / 4);
+    dim3 grid((unsigned)((groups + WP_THREADS - 1) / WP_THREADS), B, 2);
+    HOC_LAUNCH(HOC_K_WARP_PHOTO_BWD, (cudaStream_t)stream,
+               (hoc_warp_photo_pair_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
+                   D[0], D[1], grad_loss, S, H, W, 1.0f / (float)(W - 1 > 1 ? W - 1 : 1),
+                   1.0f / (float)(H - 1 > 1 ? H - 1 : 1))));
+    HOC_CHECK_LAUNCH("hoc_warp_photo_pair_backward_kernel");
     return HOC_OK;
 }
 

@@ -30,8 +30,10 @@ class GraphedConsistStep:
         self.device = torch.device("cuda", torch.cuda.current_device())
         dev = self.device
         self.renderer, self.criterion, self.image_size = renderer, criterion, image_size
+        # the captured step returns the loss and its gradients only: the visualisation entries of pair_results
+        # (warps / diffs / warp_mask) would be dead stores inside the graph
         self.kw = dict(gt_refs=gt_refs, first_only=first_only, hand_ignore_faces=hand_ignore_faces,
-                       use_backward=use_backward, detach_renders=detach_renders)
+                       use_backward=use_backward, detach_renders=detach_renders, return_visuals=False)
         self.hand_face = hand_face.to(dev)
         self._u8_stage = {}
         self._one = torch.ones((), dtype=torch.float32, device=dev)  # d loss / d loss, created once (not per replay)

@@ -8,6 +8,7 @@ lookup goes by member NAME.
 """
 import torch
 
+from . import _config, consist
 from .meshutils import batch_cat_meshes, cat_hand_object_pair
 from .warping import imgflowarp, opticalflow
 
@@ -36,12 +37,14 @@ def _base(sample, name):
 
 
 def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt_refs=True, first_only=True,
-            hand_ignore_faces=None, use_backward=True, detach_renders=True):
+            hand_ignore_faces=None, use_backward=True, detach_renders=True, return_visuals=True):
     """
     Args:
         use_backward: also compare the warp from the first to the other frame (warpbranch.py:21-25)
         detach_renders: extension -- the reference hard-codes True (warpbranch.py:66); False lets the
             NMR geometry gradient flow as well
+        return_visuals: extension -- False skips the visualisation entries of ``pair_results`` (``warps``, ``diffs``
+            and the masks' ``warp_mask`` are None): nothing the loss or its gradient depends on
     Returns (full_loss, pair_results) like the reference.
     """
     # Put inputs on GPU (stream-ordered copies when the host tensors are pinned)
@@ -58,6 +61,20 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
             hand_verts[sample_idx] = _base(samples[sample_idx], "HANDVERTS3D").cuda(non_blocking=True)
     verts_world = []
     last = len(samples) - 1
+    if (len(samples) == 2 and _config.fused_pair and hand_face.dim() in (2, 3)
+            and consist.pair_path_ok(renderer, criterion, images, jitter_masks, image_size)):
+        # one frame pair, the renderer WarpRegNet builds, L1: the whole step behind one autograd node
+        # (consist.py: 6 launches forward, 5 backward, both renders stacked along the batch)
+        hand2, obj2 = (hand_verts[1].detach(), obj_verts[1].detach()) if first_only else (hand_verts[1], obj_verts[1])
+        warp_loss, flows, masks, warps, diffs = consist.pair_consist_step(
+            hand_verts[0], obj_verts[0], hand2, obj2, hand_face.cuda(non_blocking=True), obj_faces[last], camintrs[0],
+            camintrs[1], images[0], images[1], jitter_masks[0], jitter_masks[1], renderer, image_size,
+            hand_ignore_faces=hand_ignore_faces, detach_renders=detach_renders, use_backward=use_backward,
+            return_visuals=return_visuals)
+        stack_losses = warp_loss.unsqueeze(0)
+        pair_results = {"masks": [masks], "warps": [warps], "recons_flows": [flows], "diffs": [diffs],
+                        "diff_losses": stack_losses}
+        return stack_losses.mean(), pair_results
     if len(samples) == 2 and hand_face.dim() in (2, 3) and (hand_face.dim() == 2 or hand_face.shape[0] == 1):
         # one frame pair (the training setting): both concatenations and the face table in one launch
         verts_a, verts_b, all_faces = cat_hand_object_pair(hand_verts[0], obj_verts[0], hand_verts[1], obj_verts[1],
@@ -100,8 +117,9 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
 
 def consist_step(verts1, verts2, faces, K, image_ref, image, jitter_mask_ref, jitter_mask, renderer, criterion,
                  orig_img_size, ignore_face_idxs=None, detach_renders=True, use_backward=True):
-    """One frame pair given already-concatenated meshes: flows -> pair_consist -> batch mean.
-    (What ``forward`` does after its gather / concat glue; used by bench.py and the tests.)"""
+    """One frame pair given already-concatenated meshes: flows -> pair_consist -> batch mean, through the
+    operator-by-operator surface (get_opticalflow, pair_consist).  (``forward`` takes the fused pair path of
+    consist.py when it can; this entry keeps exercising the reference-shaped operators.)"""
     flows = opticalflow.get_opticalflow([verts1, verts2], faces, [K, K], renderer, orig_img_size,
                                         detach_textures=False, detach_renders=detach_renders,
                                         ignore_face_idxs=ignore_face_idxs)

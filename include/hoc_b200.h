@@ -89,7 +89,9 @@ const char *hoc_last_error(void);
 #define HOC_K_HAND_HEAD_BWD 25
 #define HOC_K_RECOVER_POINTS_FWD 26
 #define HOC_K_RECOVER_POINTS_BWD 27
-#define HOC_KERNEL_COUNT 28
+#define HOC_K_PAIR_FRONT 28
+#define HOC_K_PAIR_BACK 29
+#define HOC_KERNEL_COUNT 30
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
@@ -174,6 +176,16 @@ int hoc_raster_backward(const float *faces, const float *textures, const int32_t
                         float eps, int layout, int use_alpha, int tex_grad_mode, float *grad_faces,
                         float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same for a batch of which only the first `geom_samples` samples need the pseudo-gradient
+ * (backward_pixel_map); the rows of grad_faces of the others hold the depth gradient alone.  Used by the frame-pair
+ * path, which stacks the two renders of a pair ([2B]) and differentiates the geometry of the first one only. */
+int hoc_raster_backward_ex(const float *faces, const float *textures, const int32_t *face_index_map,
+                           const float *rgb, const float *weight_map, const float *depth, const float *grad_rgb,
+                           const float *grad_alpha, const float *grad_depth, int B, int F, int S, int ts,
+                           float near_, float far_, float eps, int layout, int use_alpha, int tex_grad_mode,
+                           int geom_samples, float *grad_faces, float *grad_textures, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
 /* ---- flow-guided warp + masked photometric L1 ---------------------------------------------
  * ONE direction of pair_consist (imgflowarp.py:80-107) in one launch: warp(src, flow),
  * warp(jitter, flow), the valid-mask algebra and criterion.compute / batch_masked_mean_loss
@@ -208,6 +220,29 @@ int hoc_warp_photo_forward_acc(const float *src, const float *target, const floa
  * followed by `normalize(mean, 1)` (/root/reference/meshreg/datasets/handobjset.py:368-372: div = 255, sub = 0.5);
  * div = 255, sub = 0 for the jitter masks, `to_tensor` of a warped white image (handobjset.py:375-379). */
 int hoc_unpack_u8(const uint8_t *src, float *dst, long long n, float div, float sub, void *stream);
+
+/* BOTH directions of pair_consist (imgflowarp.py:80-107) in one launch, four pixels per thread (W % 4 == 0, C = 3,
+ * 3-channel jitter masks or none; 16-byte aligned tensors).  Direction 0 warps image_ref with flow21 against image
+ * (jitter mask of the second frame), direction 1 warps image with flow12 against image_ref; per-direction outputs are
+ * passed as arrays of two pointers [direction 0, direction 1].
+ *   visuals = 1  everything pair_consist returns: warped / warp_mask / diff [B,3,H,W] (any may be NULL)
+ *   visuals = 0  training: only what the loss and its gradient need -- valid_mask, flow_mask, sums.  A pixel whose
+ *                rendered flow is zero is invalid whatever it samples (imgflowarp.py:93-101), so it costs its flow
+ *                and mask bytes only.
+ *   sums [2,B,2] DOUBLE (direction-major), zero-filled by the call; feed hoc_pair_loss(sums, sums + 2 B, ...). */
+int hoc_warp_photo_forward_pair(const float *image_ref, const float *image, const float *flow12, const float *flow21,
+                                const float *jitter_ref, const float *jitter, int B, int H, int W, float thresh,
+                                int visuals, float *const *warped, float *const *warp_mask, float *const *diff,
+                                uint8_t *const *valid_mask, uint8_t *const *flow_mask, double *sums, void *stream);
+/* Backward of both directions fused with hoc_flow_finalize_backward: grad_rgb1 / grad_rgb2 [B,3,S,S] (image layout,
+ * fully overwritten: d loss / d flow x mult inside the H x W crop, zero elsewhere and in the third channel) are the
+ * incoming gradients of the two renders; grad_flow12 / grad_flow21 [B,H,W,2] optionally receive d loss / d flow
+ * itself.  Any output may be NULL.  use_backward = 0: direction 1 carries no loss (zeros). */
+int hoc_warp_photo_backward_pair(const float *image_ref, const float *image, const float *flow12, const float *flow21,
+                                 const uint8_t *const *valid_mask, const double *sums, const float *mult1,
+                                 const float *mult2, const float *grad_loss, int B, int S, int H, int W,
+                                 int use_backward, float *grad_rgb1, float *grad_rgb2, float *grad_flow12,
+                                 float *grad_flow21, void *stream);
 
 /* pair_consist's per-sample loss from the sums of its two directions (imgflowarp.py:108-114):
  * loss[b] = masked_mean(bwd) + masked_mean(fwd) (that order, float) when sums_bwd is given, else masked_mean(fwd). */
@@ -271,6 +306,27 @@ size_t hoc_mesh_scatter_workspace_bytes(int B, int V);
 int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B, int V,
                         int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs,
                         void *workspace, size_t workspace_bytes, void *stream);
+/* Frame-pair front end in ONE launch (replaces hoc_cat_meshes + hoc_flow_vertices + 2 x hoc_mesh_gather_clear):
+ * hand / object vertices of both frames [B,Vh,3] / [B,Vo,3] (camera space), hand_faces [Fh,3] (or [B,Fh,3]),
+ * obj_faces [B,Fo,3] (object-local indices) and the cameras -> the rasterizer inputs of BOTH renders stacked along the
+ * batch: faces_out / textures_out [2B,F',3,3] (F' = 2 (Fh + Fo) with fill_back; textures are the three vertex values
+ * [dx, dy, 1] of HOC_LAYOUT_TEX_VERTEX), rows 0..B-1 = render of mesh 1 with flow 1->2, rows B..2B-1 = render of
+ * mesh 2 with flow 2->1.  face_table [2B,Fh+Fo,3] (optional) receives the concatenated table the adjoint walks;
+ * `clear` as in hoc_mesh_gather_clear (the z-buffer keys of the [2B] forward that follows).
+ * Replaces warpbranch.py:50-52, opticalflow.py:98-103,121-123, renderer.py:250-252,282. */
+int hoc_pair_front(const float *hand1, const float *obj1, const float *hand2, const float *obj2,
+                   const long long *hand_faces, int hand_faces_batched, const long long *obj_faces, const float *K1,
+                   int K1_batched, const float *K2, int K2_batched, const float *R, int R_batched, const float *t,
+                   int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B, int Vh, int Vo,
+                   int Fh, int Fo, int fill_back, float *faces_out, float *textures_out, long long *face_table,
+                   void *clear, size_t clear_bytes, void *stream);
+/* Its per-vertex adjoint: grad_ndc / grad_attrs [2B,Vh+Vo,3] (hoc_mesh_scatter's outputs for the stacked batch; the
+ * has_* flags say which halves carry a gradient) -> grad_verts1 / grad_verts2 [B,Vh+Vo,3] (either may be NULL). */
+int hoc_pair_back(const float *hand1, const float *obj1, const float *hand2, const float *obj2, const float *K1,
+                  int K1_batched, const float *K2, int K2_batched, const float *R, int R_batched, const float *t,
+                  int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B, int Vh, int Vo,
+                  const float *grad_ndc, const float *grad_attrs, int has_ndc1, int has_ndc2, int has_attrs12,
+                  int has_attrs21, float *grad_verts1, float *grad_verts2, void *stream);
 /* hoc_flow_finalize: everything get_opticalflow does after its two renders (opticalflow.py:109-154): alpha
  * threshold, ignore-face mask, flow = rgb * mask, forward-backward occlusion check, mask products, channel
  * slice, crop.  rgb [B,3,S,S] / alpha [B,S,S] in HOC_LAYOUT_IMAGE, idx [B,S,S] raster order;

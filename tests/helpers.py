@@ -42,3 +42,27 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-30)
     return float((np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * scale)).max())
+
+
+HAND_VERTS, HAND_FACES = 778, 1552
+
+
+def pair_step(sc, S, crop, dev, detach_renders, use_backward, return_visuals=True):
+    """The fused frame-pair path (handobjectconsist_b200.consist) on a synth scene: hand / object split like
+    warpbranch.forward receives them.  Returns (mean loss, dict like warpbranch.consist_step's, leaf vertices)."""
+    from handobjectconsist_b200 import consist
+    from handobjectconsist_b200.neurender.renderer import Renderer
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    r = Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                 K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True, near=0.1,
+                 no_light=True)
+    v1 = g["verts1"].clone().requires_grad_(True)
+    hv = HAND_VERTS
+    hand_faces = g["faces"][0, :HAND_FACES]
+    obj_faces = g["faces"][:, HAND_FACES:] - hv
+    loss, flows, masks, warps, diffs = consist.pair_consist_step(
+        v1[:, :hv], v1[:, hv:], g["verts2"][:, :hv], g["verts2"][:, hv:], hand_faces, obj_faces, g["K"], g["K"],
+        g["image_ref"], g["image"], g["jitter_mask_ref"], g["jitter_mask"], r, crop,
+        hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=detach_renders, use_backward=use_backward,
+        return_visuals=return_visuals)
+    return loss.mean(), dict(flows=flows, loss=loss, masks=masks, warps=warps, diffs=diffs), v1

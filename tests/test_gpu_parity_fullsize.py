@@ -104,6 +104,9 @@ def _consist_both(sc, S, crop, detach, use_bwd, dev):
     loss, res, grad = run()
     with _lib.deterministic(True):
         _, _, grad_d = run()
+        # the fused frame-pair path (consist.py), which warpbranch.forward / the captured step take
+        loss_p, res_p, v1_p = helpers.pair_step(sc, S, crop, dev, detach, use_bwd, return_visuals=False)
+        loss_p.backward()
     c1 = sc["verts1"].clone().requires_grad_(True)
     loss_o, res_o = opipe.consist_step(c1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
                                        sc["jitter_mask_ref"], sc["jitter_mask"], S, crop, sc["hand_ignore_faces"],
@@ -120,6 +123,11 @@ def _consist_both(sc, S, crop, detach, use_bwd, dev):
     assert np.abs(go).max() > 0
     assert _max_rel(grad, go) <= 1e-3
     assert helpers.rel_err(grad_d, go) < 1e-3
+    for i in range(2):
+        assert torch.equal(res_p["flows"][i], res["flows"][i].detach())
+        assert torch.equal(res_p["masks"][i]["full_mask"], res_o["masks"][i]["full_mask"])
+    assert abs(loss_p.item() - loss_o.item()) <= 1e-4
+    assert helpers.rel_err(v1_p.grad.cpu().numpy(), go) < 1e-3
 
 
 @pytest.mark.parametrize("detach,use_bwd", [(False, True), (True, False)])

@@ -56,6 +56,75 @@ def test_consist_step_matches_oracle(S, crop, detach, use_bwd, seed):
     assert helpers.rel_err(v1.grad.cpu().numpy(), go) < 1e-3
 
 
+@pytest.mark.parametrize("S,crop,detach,use_bwd,visuals,seed", [
+    (64, (64, 64), False, True, True, 0),
+    (64, (64, 64), True, False, True, 1),    # the reference's training setting
+    (96, (96, 52), True, True, False, 2),    # rectangular crop, no visualisation returns
+    (128, (128, 128), False, True, False, 3),
+    (64, (64, 64), False, False, True, 4),   # geometry gradient without the backward direction
+])
+def test_pair_path_matches_oracle(S, crop, detach, use_bwd, visuals, seed):
+    """The fused frame-pair path (consist.py: both renders stacked along the batch, one autograd node) against the
+    oracle pipeline: flows / loss 1e-4, every mask exact, warps / diffs 1e-6, vertex gradients 1e-3."""
+    B = 2
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, crop[0], crop[1], seed=seed)
+    sc["K"] = synth.camera_intrinsics(B, S, S)
+    loss, res, v1 = helpers.pair_step(sc, S, crop, dev, detach, use_bwd, visuals)
+    loss.backward()
+    c1 = sc["verts1"].clone().requires_grad_(True)
+    loss_o, res_o = opipe.consist_step(c1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
+                                       sc["jitter_mask_ref"], sc["jitter_mask"], S, crop, sc["hand_ignore_faces"],
+                                       detach_renders=detach, use_backward=use_bwd, warp_device=dev)
+    loss_o.backward()
+    for i in range(2):
+        assert res["flows"][i].shape == (B, crop[1], crop[0], 2)
+        assert (res["flows"][i].detach() - res_o["flows"][i].detach()).abs().max().item() <= 1e-4
+        assert torch.equal(res["masks"][i]["full_mask"], res_o["masks"][i]["full_mask"])
+        assert torch.equal(res["masks"][i]["flow_mask"], res_o["masks"][i]["flow_mask"])
+        if visuals:
+            assert torch.equal(res["masks"][i]["warp_mask"], res_o["masks"][i]["warp_mask"])
+            assert (res["warps"][i] - res_o["warps"][i].detach()).abs().max().item() <= 1e-6
+            assert (res["diffs"][i] - res_o["diffs"][i].detach()).abs().max().item() <= 1e-6
+        else:
+            assert res["warps"][i] is None and res["diffs"][i] is None and res["masks"][i]["warp_mask"] is None
+    assert res_o["masks"][0]["full_mask"].float().mean().item() > 0.005
+    assert (res["loss"].detach() - res_o["loss"].detach()).abs().max().item() <= 1e-4
+    go = c1.grad.numpy()
+    assert np.abs(go).max() > 0
+    assert helpers.rel_err(v1.grad.cpu().numpy(), go) < 1e-3
+
+
+def test_pair_path_equals_operator_path(det_mode):
+    """consist.py against the operator-by-operator surface (get_opticalflow + pair_consist): same device functions,
+    so flows and masks are bit-identical; losses to rounding of the partial sums; gradients (reproducible mode: the
+    same terms in another order, through different kernels on the vertex side) to 1e-6."""
+    from handobjectconsist_b200 import warpbranch
+    from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
+    S, B = 96, 3
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, 64, seed=13)
+    sc["K"] = synth.camera_intrinsics(B, S, S)
+    g = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items()}
+    for detach, use_bwd in ((False, True), (True, False)):
+        loss, res, v1 = helpers.pair_step(sc, S, (S, 64), dev, detach, use_bwd, True)
+        loss.backward()
+        w1 = g["verts1"].clone().requires_grad_(True)
+        loss_m, res_m = warpbranch.consist_step(w1, g["verts2"], g["faces"], g["K"], g["image_ref"], g["image"],
+                                                g["jitter_mask_ref"], g["jitter_mask"], _renderer(S, dev),
+                                                PyramidCriterion("l1"), (S, 64), sc["hand_ignore_faces"],
+                                                detach_renders=detach, use_backward=use_bwd)
+        loss_m.backward()
+        for i in range(2):
+            assert torch.equal(res["flows"][i], res_m["flows"][i].detach())
+            for key in ("full_mask", "flow_mask", "warp_mask"):
+                assert torch.equal(res["masks"][i][key], res_m["masks"][i][key])
+            assert torch.equal(res["warps"][i], res_m["warps"][i].detach())
+            assert torch.equal(res["diffs"][i], res_m["diffs"][i].detach())
+        assert (res["loss"].detach() - res_m["loss"].detach()).abs().max().item() <= 1e-6
+        assert helpers.rel_err(v1.grad.cpu().numpy(), w1.grad.cpu().numpy()) < 1e-5
+
+
 @pytest.mark.parametrize("B,S", [(1, 63), (3, 33)])
 def test_odd_batch_and_image_size(B, S):
     """B * S * S odd (last-batch remainder at an odd image size): the z-buffer key fill of the fused gather used to
