@@ -20,6 +20,7 @@ HOC_TEX_GRAD_VERTEX = 1
 HOC_TUNE_LINE_THREADS = 1
 HOC_TUNE_LINE_SEGMENT = 2
 HOC_TUNE_DETERMINISTIC = 3
+HOC_BWD_WORKSPACE_ZEROED = 1
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
 _vp = ctypes.c_void_p
@@ -47,7 +48,7 @@ SIGNATURES = {
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_backward_workspace_bytes_ex": (_sz, [_i, _i, _i, _i, _i]),
     "hoc_mesh_scatter_workspace_bytes": (_sz, [_i, _i]),
-    "hoc_mesh_scatter_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_mesh_scatter_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _sz, _vp]),
     "hoc_set_tuning": (_i, [_i, _i]),
     "hoc_unpack_u8": (_i, [_vp, _vp, ctypes.c_longlong, _f, _f, _vp]),
     "hoc_flow_finalize_backward_pair": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -57,12 +58,15 @@ SIGNATURES = {
     "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
                                  _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
-                                    _i, _vp, _vp, _vp, _sz, _vp]),
+                                    _i, _i, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_raster_backward_zero_bytes": (_sz, [_i, _i, _i]),
+    "hoc_flow_finalize_warp": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 8),
+    "hoc_pair_loss_mean": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "hoc_warp_photo_forward_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp]),
-    "hoc_warp_photo_backward_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp,
-                                          _vp, _vp]),
-    "hoc_pair_front": (_i, [_vp] * 5 + [_i, _vp] + [_vp, _i] * 5 + [_f] + [_i] * 6 + [_vp, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_warp_photo_backward_pair": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_pair_front": (_i, [_vp] * 5 + [_i, _vp] + [_vp, _i] * 5 + [_f] + [_i] * 6
+                       + [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
     "hoc_pair_back": (_i, [_vp] * 4 + [_vp, _i] * 5 + [_f] + [_i] * 3 + [_vp, _vp] + [_i] * 4 + [_vp, _vp, _vp]),
     "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp]),

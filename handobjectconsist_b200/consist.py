@@ -10,13 +10,19 @@ of the pair stacked along the batch ([2B]) so that every rasterizer kernel runs 
 
     forward   hoc_pair_front                 vertices of both frames -> faces / vertex textures of both renders, key fill
               hoc_raster_forward  [2B]       z-buffer pass + resolve pass
-              hoc_flow_finalize              masks, ignore faces, occlusion check, crop -> flow12, flow21
-              hoc_warp_photo_forward_pair    both warp directions, valid masks, |warp - target| sums
-              hoc_pair_loss                  masked means -> loss [B]
+              hoc_flow_finalize_warp         masks, ignore faces, occlusion check, crop -> flow12, flow21, and -- same
+                                             pixel, same pass -- both warp directions, valid masks, |warp - target| sums
+                                             (with visuals: hoc_flow_finalize, then hoc_warp_photo_forward_pair)
+              hoc_pair_loss_mean             masked means -> loss [B] and its batch mean
     backward  hoc_warp_photo_backward_pair   d loss / d flow x d flow / d rgb -> incoming gradients of both renders
               hoc_raster_backward_ex [2B]    scan / cover / line passes (pseudo-gradient for the first render only)
               hoc_mesh_scatter       [2B]    faces -> vertices
               hoc_pair_back                  projection adjoints -> d loss / d (hand, object vertices)
+
+No memset and no ATen kernel in between: every zero-fill a kernel needs is done by the kernel before it (the loss
+sums by hoc_pair_front, the rasterizer backward's counters by the warp backward, the scatter's outputs by the
+rasterizer backward's streaming pass), and the batch mean and its adjoint live inside hoc_pair_loss_mean / the warp
+backward.
 
 ``return_visuals=False`` (what ``GraphedConsistStep`` asks for) skips the three visualisation returns of pair_consist
 (``warps``, ``diffs``, ``warp_mask``): nothing the loss or its gradient depends on.
@@ -29,6 +35,18 @@ from torch.autograd import Function
 from . import _lib
 from .warping.opticalflow import _fused_path_ok, _ignore_tensor
 from .warping.imgflowarp import _criterion_is_fused_l1
+
+_CAM_DEFAULTS = {}
+
+
+def _default_cams(device):
+    """R = I, t = 0, no distortion (what WarpRegNet's renderer uses), created once per device -- not per step."""
+    key = str(device)
+    if key not in _CAM_DEFAULTS:
+        _CAM_DEFAULTS[key] = (torch.eye(3, dtype=torch.float32, device=device)[None].contiguous(),
+                              torch.zeros(1, 3, dtype=torch.float32, device=device),
+                              torch.zeros(1, 5, dtype=torch.float32, device=device))
+    return _CAM_DEFAULTS[key]
 
 
 def pair_path_ok(renderer, criterion, images, jitter_masks, image_size):
@@ -70,9 +88,10 @@ class _PairConsistFunction(Function):
         W, H = cfg["wh"]
         dev = h1.device
         dt = torch.float32
-        R = c(r.R) if r.R is not None else torch.eye(3, dtype=dt, device=dev)[None]
-        t = c(r.t) if r.t is not None else torch.zeros(1, 3, dtype=dt, device=dev)
-        dist = c(r.dist_coeffs) if r.dist_coeffs is not None else torch.zeros(1, 5, dtype=dt, device=dev)
+        dR, dtr, ddist = _default_cams(dev)
+        R = c(r.R) if r.R is not None else dR
+        t = c(r.t) if r.t is not None else dtr
+        dist = c(r.dist_coeffs) if r.dist_coeffs is not None else ddist
         cams = (c(K1).reshape(-1, 9), c(K2).reshape(-1, 9), R.reshape(-1, 9), t.reshape(-1, 3), dist.reshape(-1, 5))
         for cam in cams:
             if cam.shape[0] not in (1, B):
@@ -92,10 +111,11 @@ class _PairConsistFunction(Function):
             table = e(2 * B, Fn, 3, dtype=torch.int64)
             ws_bytes = L.hoc_raster_forward_workspace_bytes(2 * B, Fr, S)
             ws = e(max(ws_bytes, 16), dtype=torch.uint8)
+            sums = e(2, B, 2, dtype=torch.float64)  # 32 B bytes: a multiple of 16; zero-filled by the front kernel
             _lib.check(L.hoc_pair_front(_lib.ptr(h1), _lib.ptr(o1), _lib.ptr(h2), _lib.ptr(o2), _lib.ptr(hf),
                                         int(hf.dim() == 3), _lib.ptr(of), *cam_args, float(r.orig_size), B, Vh, Vo, Fh,
                                         Fo, int(fill_back), _lib.ptr(faces), _lib.ptr(tex), _lib.ptr(table),
-                                        _lib.ptr(ws), ws_bytes, st), "hoc_pair_front")
+                                        _lib.ptr(ws), ws_bytes, _lib.ptr(sums), sums.numel() * 8, st), "hoc_pair_front")
             rgb, alpha, idx = e(2 * B, 3, S, S), e(2 * B, S, S), e(2 * B, S, S, dtype=torch.int32)
             # depth / weight_map only feed the backward, at covered pixels (HOC_LAYOUT_SPARSE_SAVED)
             depth, wmap = e(2 * B, S, S), e(2 * B, S, S, 3)
@@ -106,41 +126,47 @@ class _PairConsistFunction(Function):
                                             _lib.ptr(wmap), None, _lib.ptr(ws), ws_bytes, st), "hoc_raster_forward")
             flow12, flow21 = e(B, H, W, 2), e(B, H, W, 2)
             mult = e(2, B, H, W)
-            _lib.check(L.hoc_flow_finalize(_lib.ptr(rgb[:B]), _lib.ptr(alpha[:B]), _lib.ptr(idx[:B]), _lib.ptr(rgb[B:]),
-                                           _lib.ptr(alpha[B:]), _lib.ptr(idx[B:]), B, S, H, W, _lib.ptr(ignore), n_ign,
-                                           1, 0.03, _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr(mult[0]),
-                                           _lib.ptr(mult[1]), st), "hoc_flow_finalize")
             valid = e(2, B, H, W, dtype=torch.bool)
             flow_mask = e(2, B, H, W, 2, dtype=torch.bool)
-            sums = e(2, B, 2, dtype=torch.float64)
-            vis = e(6, B, 3, H, W) if visuals else None  # warped, warp_mask, diff of direction 0, then of direction 1
             pp = _lib.ptr_pair
-            _lib.check(L.hoc_warp_photo_forward_pair(
-                _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr(jr), _lib.ptr(jm), B, H, W,
-                float(cfg["thresh"]), int(visuals),
-                pp(vis[0], vis[3]) if visuals else None, pp(vis[1], vis[4]) if visuals else None,
-                pp(vis[2], vis[5]) if visuals else None, pp(valid[0], valid[1]), pp(flow_mask[0], flow_mask[1]),
-                _lib.ptr(sums), st), "hoc_warp_photo_forward_pair")
-            loss = e(B)
-            _lib.check(L.hoc_pair_loss(_lib.ptr(sums[0]), _lib.ptr(sums[1]) if cfg["use_backward"] else None, B,
-                                       _lib.ptr(loss), st), "hoc_pair_loss")
+            renders = (_lib.ptr(rgb[:B]), _lib.ptr(alpha[:B]), _lib.ptr(idx[:B]), _lib.ptr(rgb[B:]), _lib.ptr(alpha[B:]),
+                       _lib.ptr(idx[B:]))
+            vis = None
+            if not visuals:
+                _lib.check(L.hoc_flow_finalize_warp(
+                    *renders, _lib.ptr(ir), _lib.ptr(im), _lib.ptr(jr), _lib.ptr(jm), B, S, H, W, _lib.ptr(ignore), n_ign,
+                    0.03, float(cfg["thresh"]), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr(mult[0]), _lib.ptr(mult[1]),
+                    pp(valid[0], valid[1]), pp(flow_mask[0], flow_mask[1]), _lib.ptr(sums), st), "hoc_flow_finalize_warp")
+            else:
+                _lib.check(L.hoc_flow_finalize(*renders, B, S, H, W, _lib.ptr(ignore), n_ign, 1, 0.03, _lib.ptr(flow12),
+                                               _lib.ptr(flow21), _lib.ptr(mult[0]), _lib.ptr(mult[1]), st),
+                           "hoc_flow_finalize")
+                vis = e(6, B, 3, H, W)  # warped, warp_mask, diff of direction 0, then of direction 1
+                _lib.check(L.hoc_warp_photo_forward_pair(
+                    _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr(jr), _lib.ptr(jm), B, H, W,
+                    float(cfg["thresh"]), 1, pp(vis[0], vis[3]), pp(vis[1], vis[4]), pp(vis[2], vis[5]),
+                    pp(valid[0], valid[1]), pp(flow_mask[0], flow_mask[1]), _lib.ptr(sums), st),
+                    "hoc_warp_photo_forward_pair")
+            loss, mean = e(B), e()
+            _lib.check(L.hoc_pair_loss_mean(_lib.ptr(sums[0]), _lib.ptr(sums[1]) if cfg["use_backward"] else None, B,
+                                            _lib.ptr(loss), _lib.ptr(mean), st), "hoc_pair_loss_mean")
         ctx.save_for_backward(h1, o1, h2, o2, faces, table, idx, rgb, wmap, depth, ir, im, flow12, flow21, valid, sums,
                               mult, *cams)
         ctx.cfg = dict(B=B, Vh=Vh, Vo=Vo, Fn=Fn, Fr=Fr, S=S, H=H, W=W, near=near, far=far, eps=eps, fill_back=fill_back,
                        orig_size=float(r.orig_size), detach_renders=bool(cfg["detach_renders"]),
                        use_backward=bool(cfg["use_backward"]), cam_flags=[a for a in cam_args[1::2]])
-        outs = (loss, flow12, flow21, valid[0], valid[1], flow_mask[0], flow_mask[1])
+        outs = (loss, mean, flow12, flow21, valid[0], valid[1], flow_mask[0], flow_mask[1])
         if visuals:
             outs = outs + tuple(vis[k] for k in range(6))
-        ctx.mark_non_differentiable(*outs[1:])
+        ctx.mark_non_differentiable(*outs[2:])
         ctx.set_materialize_grads(False)
         return outs
 
     @staticmethod
-    def backward(ctx, g_loss, *unused):
+    def backward(ctx, g_loss, g_mean, *unused):
         need = ctx.needs_input_grad
         need1, need2 = need[0] or need[1], need[2] or need[3]
-        if g_loss is None or not (need1 or need2):
+        if (g_loss is None and g_mean is None) or not (need1 or need2):
             return (None,) * 13
         (h1, o1, h2, o2, faces, table, idx, rgb, wmap, depth, ir, im, flow12, flow21, valid, sums, mult, K1, K2, R, t,
          dist) = ctx.saved_tensors
@@ -149,7 +175,8 @@ class _PairConsistFunction(Function):
         V = Vh + Vo
         L = _lib.lib()
         dev = h1.device
-        gl = g_loss.contiguous().float()
+        gl = None if g_loss is None else g_loss.contiguous().float()
+        gm = None if g_mean is None else g_mean.contiguous().float()
         use_backward = k["use_backward"]
         # rows of the stacked batch that receive a gradient: without the backward direction the render of mesh 1
         # (rows 0..B-1) has none (imgflowarp.py:108-114)
@@ -168,32 +195,33 @@ class _PairConsistFunction(Function):
             st = _lib.stream_ptr()
             e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
             grad_rgb = e(2 * B, 3, S, S)
+            ws_bytes = L.hoc_raster_backward_workspace_bytes_ex(n, Fr, S, 2, _lib.HOC_TEX_GRAD_VERTEX)
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            # the warp backward also zero-fills the counters of the rasterizer backward that follows
+            ws_zero = L.hoc_raster_backward_zero_bytes(n, Fr, S)
             _lib.check(L.hoc_warp_photo_backward_pair(
                 _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr_pair(valid[0], valid[1]),
-                _lib.ptr(sums), _lib.ptr(mult[0]), _lib.ptr(mult[1]), _lib.ptr(gl), B, S, H, W, int(use_backward),
-                _lib.ptr(grad_rgb[:B]) if use_backward else None, _lib.ptr(grad_rgb[B:]), None, None, st),
-                "hoc_warp_photo_backward_pair")
+                _lib.ptr(sums), _lib.ptr(mult[0]), _lib.ptr(mult[1]), _lib.ptr(gl), _lib.ptr(gm), B, S, H, W,
+                int(use_backward), _lib.ptr(grad_rgb[:B]) if use_backward else None, _lib.ptr(grad_rgb[B:]), None, None,
+                _lib.ptr(ws), ws_zero, st), "hoc_warp_photo_backward_pair")
             grad_faces = e(n, Fr, 3, 3) if geom > 0 else None
             grad_tex = e(n, Fr, 3, 3)
-            ws_bytes = L.hoc_raster_backward_workspace_bytes_ex(n, Fr, S, 2, _lib.HOC_TEX_GRAD_VERTEX)
-            ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+            # grad of the NDC vertices, grad of the vertex attributes: zero-filled by the rasterizer backward's
+            # streaming pass, accumulated by the scatter after it
+            both = e(2, 2 * B, V, 3)
             _lib.check(L.hoc_raster_backward_ex(
                 _lib.ptr(faces[lo:]), None, _lib.ptr(idx[lo:]), _lib.ptr(rgb[lo:]), _lib.ptr(wmap[lo:]),
                 _lib.ptr(depth[lo:]), _lib.ptr(grad_rgb[lo:]), None, None, n, Fr, S, 2, k["near"], k["far"], k["eps"],
-                _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, geom, _lib.ptr(grad_faces), _lib.ptr(grad_tex),
-                _lib.ptr(ws), ws_bytes, st), "hoc_raster_backward_ex")
-            both = e(2, 2 * B, V, 3)  # grad of the NDC vertices, grad of the vertex attributes (one zero-fill)
+                _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, geom, _lib.HOC_BWD_WORKSPACE_ZEROED, _lib.ptr(both),
+                both.numel() * 4, _lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st),
+                "hoc_raster_backward_ex")
             g_ndc, g_attr = (both[0] if geom > 0 else None), both[1]
             sc_bytes = L.hoc_mesh_scatter_workspace_bytes(n, V)
             sc_ws = torch.empty(sc_bytes, dtype=torch.uint8, device=dev) if sc_bytes else None
-            if geom > 0:
-                gv_arg, ga_arg = _lib.ptr(both[0, lo:]), _lib.ptr(both[1, lo:])
-                if lo:  # (rows 0..B-1 of g_ndc are never read in that case: has_ndc1 = 0)
-                    pass
-            else:
-                gv_arg, ga_arg = None, _lib.ptr(both[1, lo:])
+            gv_arg = _lib.ptr(both[0, lo:]) if geom > 0 else None
+            ga_arg = _lib.ptr(both[1, lo:])
             _lib.check(L.hoc_mesh_scatter_ws(_lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(table[lo:]), n, V, Fn,
-                                             int(k["fill_back"]), _lib.HOC_TEX_GRAD_VERTEX, gv_arg, ga_arg,
+                                             int(k["fill_back"]), _lib.HOC_TEX_GRAD_VERTEX, gv_arg, ga_arg, 1,
                                              _lib.ptr(sc_ws), sc_bytes, st), "hoc_mesh_scatter")
             gv1 = e(B, V, 3) if need1 else None
             gv2 = e(B, V, 3) if need2 else None
@@ -214,9 +242,10 @@ def pair_consist_step(hand1, obj1, hand2, obj2, hand_faces, obj_faces, K1, K2, i
                       return_visuals=True, thresh=0.99999):
     """Loss [B] of one frame pair and the reference's result structures.
 
-    Returns ``(loss, flows, masks, warps, diffs)``: ``flows = [flow12, flow21]`` ([B,H,W,2]); ``masks`` the two dicts
+    Returns ``((loss, mean), flows, masks, warps, diffs)``: ``loss`` [B] and its batch mean (scalar, computed by the
+    same launch); ``flows = [flow12, flow21]`` ([B,H,W,2]); ``masks`` the two dicts
     of pair_consist (``warp_mask`` is None without visuals); ``warps`` / ``diffs`` lists of two tensors (None entries
-    without visuals).  Only ``loss`` is differentiable -- w.r.t. the four vertex tensors."""
+    without visuals).  Only ``loss`` / ``mean`` are differentiable -- w.r.t. the four vertex tensors."""
     S = int(renderer.image_size)
     wh = (min(int(image_size[0]), S), min(int(image_size[1]), S)) if image_size is not None else (S, S)
     ignore = None if hand_ignore_faces is None else _ignore_tensor(hand_ignore_faces, hand1.device)
@@ -224,8 +253,8 @@ def pair_consist_step(hand1, obj1, hand2, obj2, hand_faces, obj_faces, K1, K2, i
                visuals=return_visuals, thresh=thresh)
     outs = _PairConsistFunction.apply(hand1, obj1, hand2, obj2, hand_faces, obj_faces, K1, K2, image_ref, image,
                                       jitter_mask_ref, jitter_mask, cfg)
-    loss, flow12, flow21, valid1, valid2, fmask1, fmask2 = outs[:7]
-    vis = outs[7:] if return_visuals else (None,) * 6
+    loss, mean, flow12, flow21, valid1, valid2, fmask1, fmask2 = outs[:8]
+    vis = outs[8:] if return_visuals else (None,) * 6
     masks = [{"warp_mask": vis[1], "full_mask": valid1, "flow_mask": fmask1},
              {"warp_mask": vis[4], "full_mask": valid2, "flow_mask": fmask2}]
-    return loss, [flow12, flow21], masks, [vis[0], vis[3]], [vis[2], vis[5]]
+    return (loss, mean), [flow12, flow21], masks, [vis[0], vis[3]], [vis[2], vis[5]]

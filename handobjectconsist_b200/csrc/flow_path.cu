@@ -18,6 +18,7 @@
  */
 #include "hoc_common.cuh"
 #include "hoc_det.cuh"
+#include "warp_math.cuh"
 
 #define FP_THREADS 256
 
@@ -253,32 +254,29 @@ __device__ __forceinline__ void hoc_fp_flow(const HocRender &R, int b, int S, in
  *   mask_a' = mask_a * occl_a  (render 2: alpha * occl_2);   flow_a = pf_a * mask_a'   (:146-150)
  * Output: flow [B,H,W,2] (cropped to H x W) and mult [B,H,W] = d flow / d rgb = mask_a * mask_a'.
  */
-__global__ void __launch_bounds__(FP_THREADS)
-hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const int *__restrict__ ignore, int n_ignore,
-                         int mask_occlusions, float distance_thresh, float *__restrict__ flow12,
-                         float *__restrict__ flow21, float *__restrict__ mult1, float *__restrict__ mult2)
+/* One pixel r = (rx, ry) of direction a -> b (see the comment above): `alpha_r`, `rgb0`, `rgb1` are render a's alpha and
+ * first two colour channels at r (loaded by the caller, scalar or vectorised).  Returns the final flow and
+ * mult = d flow / d rgb. */
+__device__ __forceinline__ void hoc_finalize_pixel(const HocRender &Ra, const HocRender &Rb, bool second, int b, int S,
+                                                   int rx, int ry, float alpha_r, float rgb0, float rgb1,
+                                                   const int *__restrict__ ignore, int n_ignore, int mask_occlusions,
+                                                   float distance_thresh, float *fx_out, float *fy_out, float *mult_out)
 {
-    const int b = blockIdx.y;
-    const bool second = blockIdx.z != 0;
-    const long pix = (long)blockIdx.x * FP_THREADS + threadIdx.x;
-    if (pix >= (long)H * W)
-        return;
-    const int ry = (int)((unsigned)pix / (unsigned)W), rx = (int)pix - ry * W;
-    const HocRender &Ra = second ? R2 : R1;
-    const HocRender &Rb = second ? R1 : R2;
-
-    float alpha_r;
-    const float mt_r = hoc_fp_mask(Ra, b, S, rx, ry, ignore, n_ignore, &alpha_r); /* thresholded * keep */
-    float fx, fy;
-    hoc_fp_flow(Ra, b, S, rx, ry, mt_r, &fx, &fy);
+    float mt_r = (alpha_r > 0.99999f) ? 1.0f : 0.0f; /* thresholded alpha x keep-mask (hoc_fp_mask on preloaded alpha) */
+    if (n_ignore > 0 && mt_r != 0.0f) {
+        const int fidx = Ra.idx[((long)b * S + (S - 1 - ry)) * S + rx];
+        bool keep = true;
+        for (int k = 0; k < n_ignore; k++)
+            keep = keep && (fidx != ignore[k]);
+        mt_r = __fmul_rn(mt_r, keep ? 1.0f : 0.0f);
+    }
+    float fx = __fmul_rn(rgb0, mt_r), fy = __fmul_rn(rgb1, mt_r);
     float mfinal = mt_r;
-    float *flow = second ? flow21 : flow12;
-    float *mult = second ? mult2 : mult1;
-    const long o = ((long)b * H + ry) * W + rx;
     if (mask_occlusions && (second ? alpha_r : mt_r) == 0.0f && fx == fx && fy == fy) {
         /* the pixel's own mask is zero (93 % of a typical frame): every product below is zero */
-        *reinterpret_cast<float2 *>(flow + o * 2) = make_float2(0.0f, 0.0f);
-        mult[o] = 0.0f;
+        *fx_out = 0.0f;
+        *fy_out = 0.0f;
+        *mult_out = 0.0f;
         return;
     }
     if (mask_occlusions) {
@@ -318,8 +316,152 @@ hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const 
         fx = __fmul_rn(fx, mfinal);
         fy = __fmul_rn(fy, mfinal);
     }
-    *reinterpret_cast<float2 *>(flow + o * 2) = make_float2(fx, fy);
-    mult[o] = mask_occlusions ? __fmul_rn(mt_r, mfinal) : mt_r;
+    *fx_out = fx;
+    *fy_out = fy;
+    *mult_out = mask_occlusions ? __fmul_rn(mt_r, mfinal) : mt_r;
+}
+
+__global__ void __launch_bounds__(FP_THREADS)
+hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const int *__restrict__ ignore, int n_ignore,
+                         int mask_occlusions, float distance_thresh, float *__restrict__ flow12,
+                         float *__restrict__ flow21, float *__restrict__ mult1, float *__restrict__ mult2)
+{
+    const int b = blockIdx.y;
+    const bool second = blockIdx.z != 0;
+    const long pix = (long)blockIdx.x * FP_THREADS + threadIdx.x;
+    if (pix >= (long)H * W)
+        return;
+    const int ry = (int)((unsigned)pix / (unsigned)W), rx = (int)pix - ry * W;
+    const HocRender &Ra = second ? R2 : R1;
+    const HocRender &Rb = second ? R1 : R2;
+    const long po = ((long)b * S + ry) * S + rx, co = (((long)b * 3) * S + ry) * S + rx;
+    float fx, fy, mu;
+    hoc_finalize_pixel(Ra, Rb, second, b, S, rx, ry, Ra.alpha[po], Ra.rgb[co], Ra.rgb[co + (long)S * S], ignore, n_ignore,
+                       mask_occlusions, distance_thresh, &fx, &fy, &mu);
+    const long o = ((long)b * H + ry) * W + rx;
+    *reinterpret_cast<float2 *>((second ? flow21 : flow12) + o * 2) = make_float2(fx, fy);
+    (second ? mult2 : mult1)[o] = mu;
+}
+
+/*
+ * hoc_flow_finalize + the training half of hoc_warp_photo_forward_pair in one pass (frame-pair path without the
+ * visualisation returns): the pixel that has just produced its flow vector is the pixel whose warp sample that flow
+ * drives (pair_consist warps at p with flow(p), imgflowarp.py:80-101), so the flow never makes a round trip through
+ * memory before the warp and the two dense passes become one.  Four consecutive pixels per thread: alpha, the two
+ * colour planes, flows, mult and the masks move as 16-byte (8- / 4-byte for the byte masks) accesses; the occlusion
+ * gathers and the bilinear taps run only on the few per cent of pixels a mesh covers.
+ * blockIdx.z = 0: flow12 (render 1) -> pair_consist direction 1 (warp image against image_ref, jitter_mask_ref);
+ * blockIdx.z = 1: flow21 (render 2) -> direction 0 (warp image_ref against image, jitter_mask).
+ */
+struct HocFinWarpDir {
+    float *flow, *mult;
+    const float *src, *target, *jitter;
+    uint8_t *valid_mask, *flow_mask;
+    double *sums;
+};
+
+__global__ void __launch_bounds__(FP_THREADS)
+hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocFinWarpDir D1, int S, int H, int W,
+                              const int *__restrict__ ignore, int n_ignore, float distance_thresh, float inv_w,
+                              float inv_h, float thresh)
+{
+    /* Two phases per CTA (1024 pixels).  A: every thread streams its four pixels -- 16-byte loads of alpha and the two
+     * colour planes, 16-byte stores of the (zero) outputs -- and notes the pixels a mesh covers in a shared list.
+     * B: the listed pixels (a few per cent, clustered in a few CTAs) are dealt ONE PER THREAD: each carries a chain of
+     * dependent gathers (ignore table, two occlusion look-ups, 24 bilinear taps), and a thread that ran its own four
+     * covered pixels one after the other would be the tail of the whole launch. */
+    __shared__ unsigned short s_list[FP_THREADS * 4];
+    __shared__ int s_n;
+    __shared__ float s_sum[FP_THREADS / 32];
+    __shared__ float s_cnt[FP_THREADS / 32];
+    const int b = blockIdx.y;
+    const bool second = blockIdx.z != 0;
+    const HocRender &Ra = second ? R2 : R1;
+    const HocRender &Rb = second ? R1 : R2;
+    const HocFinWarpDir &D = second ? D1 : D0;
+    const int W4 = W >> 2, npix = H * W;
+    const int q = blockIdx.x * FP_THREADS + threadIdx.x;
+    if (threadIdx.x == 0)
+        s_n = 0;
+    __syncthreads();
+    if (q < H * W4) {
+        const int ry = q / W4, x0 = (q - ry * W4) << 2;
+        const long po = ((long)b * S + ry) * S + x0, co = (((long)b * 3) * S + ry) * S + x0;
+        const float4 a4 = *reinterpret_cast<const float4 *>(Ra.alpha + po);
+        const float4 r4 = *reinterpret_cast<const float4 *>(Ra.rgb + co);
+        const float4 g4 = *reinterpret_cast<const float4 *>(Ra.rgb + co + (long)S * S);
+        const float al[4] = {a4.x, a4.y, a4.z, a4.w}, c0[4] = {r4.x, r4.y, r4.z, r4.w}, c1[4] = {g4.x, g4.y, g4.z, g4.w};
+        const long o = (long)b * npix + (long)ry * W + x0;
+        const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        *reinterpret_cast<float4 *>(D.flow + o * 2) = z4;
+        *reinterpret_cast<float4 *>(D.flow + o * 2 + 4) = z4;
+        *reinterpret_cast<float4 *>(D.mult + o) = z4;
+        *reinterpret_cast<unsigned *>(D.valid_mask + o) = 0u;
+        if (D.flow_mask != nullptr)
+            *reinterpret_cast<uint2 *>(D.flow_mask + o * 2) = make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 4; j++) /* (alpha 0 and finite colour: every output of the pixel is zero) */
+            if (al[j] != 0.0f || !(c0[j] == c0[j]) || !(c1[j] == c1[j]))
+                s_list[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + j);
+    }
+    __syncthreads(); /* orders phase A's zero stores before phase B's stores to the same addresses */
+    const int n = s_n;
+    if (n == 0)
+        return;
+    float my_sum = 0.0f, my_cnt = 0.0f;
+    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
+        const int loc = s_list[i];
+        const int qq = blockIdx.x * FP_THREADS + (loc >> 2);
+        const int ry = qq / W4, rx = ((qq - ry * W4) << 2) + (loc & 3);
+        const long po = ((long)b * S + ry) * S + rx, co = (((long)b * 3) * S + ry) * S + rx;
+        float fx, fy, mu;
+        hoc_finalize_pixel(Ra, Rb, second, b, S, rx, ry, Ra.alpha[po], Ra.rgb[co], Ra.rgb[co + (long)S * S], ignore,
+                           n_ignore, 1, distance_thresh, &fx, &fy, &mu);
+        const long pix = (long)ry * W + rx;
+        const long o = (long)b * npix + pix;
+        *reinterpret_cast<float2 *>(D.flow + o * 2) = make_float2(fx, fy);
+        D.mult[o] = mu;
+        if (D.flow_mask != nullptr) {
+            uchar2 fm;
+            fm.x = !(fx == 0.0f) ? 1 : 0;
+            fm.y = !(fy == 0.0f) ? 1 : 0;
+            *reinterpret_cast<uchar2 *>(D.flow_mask + o * 2) = fm;
+        }
+        if (fx == 0.0f)
+            continue; /* valid = ... & (flow_x != 0): nothing of this pixel reaches the loss (NaN flows go on) */
+        const float *sb = D.src + (size_t)b * 3 * npix;
+        const float *jb = (D.jitter != nullptr) ? D.jitter + (size_t)b * 3 * npix : nullptr;
+        const float *tb = D.target + (size_t)b * 3 * npix + pix;
+        const float tv[3] = {__ldg(tb), __ldg(tb + npix), __ldg(tb + 2 * (size_t)npix)};
+        const float jc = (jb != nullptr) ? __ldg(jb + pix) : 1.0f;
+        float v[3], d[3], wm[3], sd;
+        if (hoc_pair_pixel<false>(sb, jb, tv, jc, rx, ry, fx, fy, H, W, npix, inv_w, inv_h, thresh, v, d, wm, &sd)) {
+            D.valid_mask[o] = 1;
+            my_sum += sd;
+            my_cnt += 3.0f;
+        }
+    }
+    /* per-sample (sum, count) */
+    if (!__syncthreads_or(my_cnt > 0.0f))
+        return;
+    my_sum = hoc_warp_sum(my_sum);
+    my_cnt = hoc_warp_sum(my_cnt);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_sum[warp] = my_sum;
+        s_cnt[warp] = my_cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float a = (lane < FP_THREADS / 32) ? s_sum[lane] : 0.0f;
+        float nn = (lane < FP_THREADS / 32) ? s_cnt[lane] : 0.0f;
+        a = hoc_warp_sum(a);
+        nn = hoc_warp_sum(nn);
+        if (lane == 0 && nn > 0.0f) {
+            atomicAdd(&D.sums[2 * b + 0], rint((double)a * WP_SUM_SCALE));
+            atomicAdd(&D.sums[2 * b + 1], (double)nn);
+        }
+    }
 }
 
 /* grad_rgb [B,3,S,S] (image layout) = grad_flow [B,H,W,2] * mult inside the crop, 0 elsewhere / channel 2 */
@@ -591,12 +733,16 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
                       const float *__restrict__ obj2, const long long *__restrict__ hand_faces, int hand_faces_batched,
                       const long long *__restrict__ obj_faces, HocCam C, int B, int Vh, int Vo, int Fh, int Fo,
                       int fill_back, float *__restrict__ faces_out, float *__restrict__ tex_out,
-                      long long *__restrict__ face_table, uint4 *__restrict__ clear, long n_clear)
+                      long long *__restrict__ face_table, uint4 *__restrict__ clear, long n_clear,
+                      uint4 *__restrict__ zero, long n_zero)
 {
-    if (clear != nullptr) {
+    {
         const long nthreads = (long)gridDim.x * gridDim.y * PF_THREADS;
-        for (long i = ((long)blockIdx.y * gridDim.x + blockIdx.x) * PF_THREADS + threadIdx.x; i < n_clear; i += nthreads)
+        const long t0 = ((long)blockIdx.y * gridDim.x + blockIdx.x) * PF_THREADS + threadIdx.x;
+        for (long i = t0; i < n_clear; i += nthreads) /* z-buffer keys of the forward that follows */
             clear[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        for (long i = t0; i < n_zero; i += nthreads) /* small accumulators of later kernels (the loss sums) */
+            zero[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     /* staged records of this CTA's faces: [kind][thread][9], kind = faces1, tex1, faces2, tex2 */
     __shared__ float s_rec[4][PF_THREADS * 9];
@@ -765,19 +911,21 @@ extern "C" size_t hoc_mesh_scatter_workspace_bytes(int B, int V)
 
 extern "C" int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx,
                                    int B, int V, int F, int fill_back, int tex_grad_mode, float *grad_verts,
-                                   float *grad_attrs, void *workspace, size_t workspace_bytes, void *stream);
+                                   float *grad_attrs, int outputs_zeroed, void *workspace, size_t workspace_bytes,
+                                   void *stream);
 
 extern "C" int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B,
                                 int V, int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs,
                                 void *stream)
 {
     return hoc_mesh_scatter_ws(grad_faces, grad_textures, faces_idx, B, V, F, fill_back, tex_grad_mode, grad_verts,
-                               grad_attrs, nullptr, 0, stream);
+                               grad_attrs, 0, nullptr, 0, stream);
 }
 
 extern "C" int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx,
                                    int B, int V, int F, int fill_back, int tex_grad_mode, float *grad_verts,
-                                   float *grad_attrs, void *workspace, size_t workspace_bytes, void *stream)
+                                   float *grad_attrs, int outputs_zeroed, void *workspace, size_t workspace_bytes,
+                                   void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && V >= 0 && F >= 0, "hoc_mesh_scatter: bad shape B=%d V=%d F=%d", B, V, F);
     HOC_CHECK_ARG(B <= 65535, "hoc_mesh_scatter: batch %d exceeds 65535", B);
@@ -786,7 +934,9 @@ extern "C" int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_te
         return HOC_OK;
     cudaError_t e = cudaSuccess;
     const size_t nbytes = sizeof(float) * 3 * (size_t)B * V;
-    if (grad_verts != nullptr && grad_attrs == grad_verts + 3 * (size_t)B * V) {
+    if (outputs_zeroed) {
+        /* an earlier kernel of the caller's sequence filled both outputs with zeros (one graph node less) */
+    } else if (grad_verts != nullptr && grad_attrs == grad_verts + 3 * (size_t)B * V) {
         e = cudaMemsetAsync(grad_verts, 0, 2 * nbytes, st); /* adjacent outputs: one fill */
     } else {
         if (grad_verts != nullptr)
@@ -959,14 +1109,22 @@ extern "C" int hoc_pair_front(const float *hand1, const float *obj1, const float
                               const float *K1, int K1_batched, const float *K2, int K2_batched, const float *R,
                               int R_batched, const float *t, int t_batched, const float *dist_coeffs, int dist_batched,
                               float orig_size, int B, int Vh, int Vo, int Fh, int Fo, int fill_back, float *faces_out,
-                              float *textures_out, long long *face_table, void *clear, size_t clear_bytes, void *stream)
+                              float *textures_out, long long *face_table, void *clear, size_t clear_bytes, void *zero,
+                              size_t zero_bytes, void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && Vh >= 0 && Vo >= 0 && Fh >= 0 && Fo >= 0 && B <= 32767, "hoc_pair_front: bad shape");
     HOC_CHECK_ARG(clear == nullptr || (clear_bytes % 16 == 0 && ((uintptr_t)clear & 15) == 0),
                   "hoc_pair_front: clear buffer must be 16-byte aligned with a size multiple of 16");
+    HOC_CHECK_ARG(zero == nullptr || (zero_bytes % 16 == 0 && ((uintptr_t)zero & 15) == 0),
+                  "hoc_pair_front: zero buffer must be 16-byte aligned with a size multiple of 16");
     cudaStream_t st = (cudaStream_t)stream;
+    if (clear == nullptr)
+        clear_bytes = 0;
+    if (zero == nullptr)
+        zero_bytes = 0;
     if (B == 0 || Fh + Fo == 0) {
-        if (clear != nullptr && cudaMemsetAsync(clear, 0xff, clear_bytes, st) != cudaSuccess) {
+        if ((clear_bytes && cudaMemsetAsync(clear, 0xff, clear_bytes, st) != cudaSuccess) ||
+            (zero_bytes && cudaMemsetAsync(zero, 0, zero_bytes, st) != cudaSuccess)) {
             hoc_set_error("hoc_pair_front: memset failed");
             return HOC_ERR_CUDA;
         }
@@ -982,7 +1140,8 @@ extern "C" int hoc_pair_front(const float *hand1, const float *obj1, const float
                (hoc_pair_front_kernel<<<grid, PF_THREADS, 0, st>>>(hand1, obj1, hand2, obj2, hand_faces,
                                                                    hand_faces_batched, obj_faces, C, B, Vh, Vo, Fh, Fo,
                                                                    fill_back, faces_out, textures_out, face_table,
-                                                                   (uint4 *)clear, (long)(clear_bytes / 16))));
+                                                                   (uint4 *)clear, (long)(clear_bytes / 16),
+                                                                   (uint4 *)zero, (long)(zero_bytes / 16))));
     HOC_CHECK_LAUNCH("hoc_pair_front_kernel");
     return HOC_OK;
 }
@@ -1009,5 +1168,43 @@ extern "C" int hoc_pair_back(const float *hand1, const float *obj1, const float 
                    hand1, obj1, hand2, obj2, C, B, Vh, Vo, grad_ndc, grad_attrs, has_ndc1, has_ndc2, has_attrs12,
                    has_attrs21, grad_verts1, grad_verts2)));
     HOC_CHECK_LAUNCH("hoc_pair_back_kernel");
+    return HOC_OK;
+}
+
+extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
+                                      const float *alpha2, const int32_t *idx2, const float *image_ref,
+                                      const float *image, const float *jitter_ref, const float *jitter, int B, int S,
+                                      int H, int W, const int *ignore_faces, int n_ignore, float distance_thresh,
+                                      float thresh, float *flow12, float *flow21, float *mult1, float *mult2,
+                                      uint8_t *const *valid_mask, uint8_t *const *flow_mask, double *sums, void *stream)
+{
+    HOC_CHECK_ARG(B >= 0 && S >= 4 && (S % 4) == 0 && H >= 1 && W >= 4 && (W % 4) == 0 && H <= S && W <= S,
+                  "hoc_flow_finalize_warp: bad shape B=%d S=%d H=%d W=%d (S, W multiples of 4)", B, S, H, W);
+    HOC_CHECK_ARG(B <= 65535, "hoc_flow_finalize_warp: batch %d exceeds 65535", B);
+    HOC_CHECK_ARG(n_ignore >= 0 && n_ignore <= 64, "hoc_flow_finalize_warp: at most 64 ignored faces (got %d)", n_ignore);
+    if (B == 0)
+        return HOC_OK;
+    HOC_CHECK_ARG(rgb1 && alpha1 && idx1 && rgb2 && alpha2 && idx2 && image_ref && image && flow12 && flow21 && mult1 &&
+                      mult2 && valid_mask && valid_mask[0] && valid_mask[1] && sums,
+                  "hoc_flow_finalize_warp: NULL argument");
+    HOC_CHECK_ARG((jitter_ref == nullptr) == (jitter == nullptr), "hoc_flow_finalize_warp: one jitter mask missing");
+    HOC_CHECK_ARG(n_ignore == 0 || ignore_faces != nullptr, "hoc_flow_finalize_warp: ignore_faces NULL");
+    HocRender R1 = {rgb1, alpha1, idx1}, R2 = {rgb2, alpha2, idx2};
+    /* finalize direction 0 produces flow12, which pair_consist's direction 1 consumes (and vice versa) */
+    HocFinWarpDir D0 = {flow12, mult1, image, image_ref, jitter_ref, valid_mask[1], flow_mask ? flow_mask[1] : nullptr,
+                        sums + 2 * (size_t)B};
+    HocFinWarpDir D1 = {flow21, mult2, image_ref, image, jitter, valid_mask[0], flow_mask ? flow_mask[0] : nullptr, sums};
+    const uintptr_t al16 = (uintptr_t)rgb1 | (uintptr_t)alpha1 | (uintptr_t)rgb2 | (uintptr_t)alpha2 | (uintptr_t)flow12 |
+                           (uintptr_t)flow21 | (uintptr_t)mult1 | (uintptr_t)mult2;
+    HOC_CHECK_ARG((al16 & 15) == 0 && (((uintptr_t)valid_mask[0] | (uintptr_t)valid_mask[1]) & 3) == 0 &&
+                      (flow_mask == nullptr || (((uintptr_t)flow_mask[0] | (uintptr_t)flow_mask[1]) & 7) == 0),
+                  "hoc_flow_finalize_warp: tensors must be 16-byte aligned");
+    const long groups = (long)H * (W / 4);
+    dim3 grid((unsigned)((groups + FP_THREADS - 1) / FP_THREADS), B, 2);
+    HOC_LAUNCH(HOC_K_FLOW_FINALIZE, (cudaStream_t)stream,
+               (hoc_flow_finalize_warp_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+                   R1, R2, D0, D1, S, H, W, ignore_faces, n_ignore, distance_thresh,
+                   1.0f / (float)(W - 1 > 1 ? W - 1 : 1), 1.0f / (float)(H - 1 > 1 ? H - 1 : 1), thresh)));
+    HOC_CHECK_LAUNCH("hoc_flow_finalize_warp_kernel");
     return HOC_OK;
 }

@@ -203,7 +203,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
                            const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S, int layout,
                            int k4_samples, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
                            int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
-                           float *__restrict__ zero_b, long n_b)
+                           float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c)
 {
     /* samples [0, k4_samples) get the pseudo-gradient (spans + every covered pixel listed); the others only list the
      * pixels that have a texture (non-zero dL/drgb) or depth gradient */
@@ -219,6 +219,8 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
             zero_a[i] = 0.0f;
         for (long i = t0; i < n_b; i += nthreads)
             zero_b[i] = 0.0f;
+        for (long i = t0; i < n_c; i += nthreads) /* a buffer of the caller's NEXT kernel (hoc_mesh_scatter's outputs) */
+            zero_c[i] = 0.0f;
     }
     __shared__ int s_lo[8][32];
     __shared__ int s_hi[8][32];
@@ -749,6 +751,16 @@ extern "C" size_t hoc_raster_backward_workspace_bytes(int B, int F, int S)
     return hoc_bwd_workspace(nullptr, B, F, S).total;
 }
 
+/* Leading bytes of the workspace that must be zero when hoc_raster_backward_ex is told HOC_BWD_WORKSPACE_ZEROED
+ * (line spans, counters, per-face depth sums). */
+extern "C" size_t hoc_raster_backward_zero_bytes(int B, int F, int S)
+{
+    if (B <= 0 || S <= 0 || F < 0)
+        return 0;
+    const HocBwdWorkspace w = hoc_bwd_workspace(nullptr, B, F, S);
+    return (w.count_bytes + w.acc_bytes + 15) & ~(size_t)15;
+}
+
 /* Workspace of hoc_raster_backward for a given texture size: in the reproducible mode (HOC_TUNE_DETERMINISTIC) the
  * fixed-point accumulators of grad_textures ([B,F,ts^3,3] or, in HOC_TEX_GRAD_VERTEX mode, [B,F,3,3]) live in it. */
 extern "C" size_t hoc_raster_backward_workspace_bytes_ex(int B, int F, int S, int ts, int tex_grad_mode)
@@ -763,8 +775,9 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
                                       const float *rgb, const float *weight_map, const float *depth,
                                       const float *grad_rgb, const float *grad_alpha, const float *grad_depth, int B,
                                       int F, int S, int ts, float near_, float far_, float eps, int layout,
-                                      int use_alpha, int tex_grad_mode, int geom_samples, float *grad_faces,
-                                      float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
+                                      int use_alpha, int tex_grad_mode, int geom_samples, int flags, void *extra_zero,
+                                      size_t extra_zero_bytes, float *grad_faces, float *grad_textures, void *workspace,
+                                      size_t workspace_bytes, void *stream);
 
 extern "C" int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
                                    const float *rgb, const float *weight_map, const float *depth,
@@ -774,8 +787,8 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
 {
     return hoc_raster_backward_ex(faces, textures, face_index_map, rgb, weight_map, depth, grad_rgb, grad_alpha,
-                                  grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode, B,
-                                  grad_faces, grad_textures, workspace, workspace_bytes, stream);
+                                  grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode, B, 0,
+                                  nullptr, 0, grad_faces, grad_textures, workspace, workspace_bytes, stream);
 }
 
 /* geom_samples: the pseudo-gradient (backward_pixel_map) is computed for samples [0, geom_samples) only; the rows of
@@ -785,10 +798,15 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
                                       const float *rgb, const float *weight_map, const float *depth,
                                       const float *grad_rgb, const float *grad_alpha, const float *grad_depth, int B,
                                       int F, int S, int ts, float near_, float far_, float eps, int layout,
-                                      int use_alpha, int tex_grad_mode, int geom_samples, float *grad_faces,
-                                      float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
+                                      int use_alpha, int tex_grad_mode, int geom_samples, int flags, void *extra_zero,
+                                      size_t extra_zero_bytes, float *grad_faces, float *grad_textures, void *workspace,
+                                      size_t workspace_bytes, void *stream)
 {
     (void)textures;
+    HOC_CHECK_ARG(extra_zero == nullptr || (extra_zero_bytes % 4 == 0 && ((uintptr_t)extra_zero & 3) == 0),
+                  "hoc_raster_backward: extra_zero must be a float buffer");
+    if (extra_zero == nullptr)
+        extra_zero_bytes = 0;
     HOC_CHECK_ARG(geom_samples >= 0 && geom_samples <= B, "hoc_raster_backward: geom_samples %d outside [0, %d]",
                   geom_samples, B);
     HOC_CHECK_ARG(tex_grad_mode == HOC_TEX_GRAD_CUBE || (tex_grad_mode == HOC_TEX_GRAD_VERTEX && ts == 2),
@@ -825,7 +843,10 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
 
     /* spans, counters and (directly behind them) acc_d are zero-filled by ONE memset; the gradient outputs are
      * zero-filled by the scan pass */
-    cudaError_t e = cudaMemsetAsync(w.ext, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
+    /* (HOC_BWD_WORKSPACE_ZEROED: an earlier kernel of the caller's sequence did it -- one graph node less) */
+    cudaError_t e = (flags & HOC_BWD_WORKSPACE_ZEROED)
+                        ? cudaSuccess
+                        : cudaMemsetAsync(w.ext, 0, w.count_bytes + (want_depth ? w.acc_bytes : 0), st);
     if (e == cudaSuccess && det)
         e = cudaMemsetAsync(w.det_gf, 0, w.det_bytes, st);
     if (e != cudaSuccess) {
@@ -842,7 +863,8 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
         HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                    (hoc_raster_bwd_scan_kernel<<<pg, dim3(32, 8), 0, st>>>(
                        face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples,
-                       want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt)));
+                       want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
+                       (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)))));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
     }
     {

@@ -347,6 +347,94 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
         hoc_store_interleaved<9>(s_stage, inv, face_inv_map + ((long)b * npix + pix0) * 9, left * 9);
 }
 
+/*
+ * Resolve pass, image layout, four pixels per thread (S % 4 == 0, no face_inv_map, weight_map sparse or absent): what the
+ * flow path and rasterize_rgbad's default outputs need.  Two phases per CTA (1024 pixels of one sample).  A: every thread
+ * streams its four pixels -- two 16-byte loads of the keys, 16-byte stores of face_index_map, alpha, the background
+ * colour and (dense mode) the background depth -- and notes the covered ones in a shared list.  B: the covered pixels
+ * (a few per cent of a frame, clustered in a few CTAs) are dealt one per thread: barycentric matrix, weights, depth and
+ * texture sample of the winning face are a chain of dependent loads and IEEE divisions, and a thread that ran its own
+ * four covered pixels one after the other would be the tail of the launch (measured in round 1: 19.6 us against 15.8).
+ */
+__global__ void __launch_bounds__(RS_THREADS)
+hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
+                           const unsigned long long *__restrict__ zbuf, int F, int S, int ts, float near_, float far_,
+                           float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int tex_vertex,
+                           int sparse_saved, float *__restrict__ rgb, float *__restrict__ alpha,
+                           float *__restrict__ depth, int32_t *__restrict__ face_index_map,
+                           float *__restrict__ weight_map)
+{
+    __shared__ unsigned short s_list[RS_THREADS * 4];
+    __shared__ int s_n;
+    const int b = blockIdx.y;
+    const int S4 = S >> 2;
+    const long npix = (long)S * S;
+    const int q = blockIdx.x * RS_THREADS + threadIdx.x;
+    if (threadIdx.x == 0)
+        s_n = 0;
+    __syncthreads();
+    float col[3];
+    if (bg_dev != nullptr) {
+        col[0] = __ldg(bg_dev + b * 3 + 0);
+        col[1] = __ldg(bg_dev + b * 3 + 1);
+        col[2] = __ldg(bg_dev + b * 3 + 2);
+    } else {
+        col[0] = bg0;
+        col[1] = bg1;
+        col[2] = bg2;
+    }
+    if (q < S * S4) {
+        const int yi = q / S4, x0 = (q - yi * S4) << 2;
+        const long pix = (long)yi * S + x0;
+        const uint4 k01 = *reinterpret_cast<const uint4 *>(zbuf + (long)b * npix + pix);
+        const uint4 k23 = *reinterpret_cast<const uint4 *>(zbuf + (long)b * npix + pix + 2);
+        const int f4[4] = {(int)k01.x, (int)k01.z, (int)k23.x, (int)k23.z}; /* low words: the face (-1 = empty key) */
+        *reinterpret_cast<int4 *>(face_index_map + (long)b * npix + pix) = make_int4(f4[0], f4[1], f4[2], f4[3]);
+        const long po = ((long)b * S + (S - 1 - yi)) * S + x0; /* image layout: rows flipped */
+        if (alpha != nullptr)
+            *reinterpret_cast<float4 *>(alpha + po) = make_float4(f4[0] >= 0 ? 1.0f : 0.0f, f4[1] >= 0 ? 1.0f : 0.0f,
+                                                                  f4[2] >= 0 ? 1.0f : 0.0f, f4[3] >= 0 ? 1.0f : 0.0f);
+        if (depth != nullptr && !sparse_saved)
+            *reinterpret_cast<float4 *>(depth + po) = make_float4(far_, far_, far_, far_);
+        if (rgb != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                *reinterpret_cast<float4 *>(rgb + (((long)b * 3 + c) * S + (S - 1 - yi)) * S + x0) =
+                    make_float4(col[c], col[c], col[c], col[c]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (f4[j] >= 0)
+                s_list[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + j);
+    }
+    __syncthreads(); /* orders phase A's background stores before phase B's stores to the same addresses */
+    const int n = s_n;
+    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+        const int loc = s_list[i];
+        const int qq = blockIdx.x * RS_THREADS + (loc >> 2);
+        const int yi = qq / S4, xi = ((qq - yi * S4) << 2) + (loc & 3);
+        const long pix = (long)yi * S + xi;
+        const int fidx = (int)(unsigned)(zbuf[(long)b * npix + pix] & 0xffffffffull);
+        float w[3], inv[9], zp = far_, cc[3] = {col[0], col[1], col[2]};
+        hoc_resolve_covered(faces, textures, b, F, S, ts, near_, far_, eps, tex_vertex, rgb != nullptr, fidx, xi, yi, w,
+                            inv, &zp, cc);
+        const long po = ((long)b * S + (S - 1 - yi)) * S + xi;
+        if (depth != nullptr)
+            depth[po] = zp;
+        if (weight_map != nullptr) {
+            float *wd = weight_map + ((long)b * npix + pix) * 3;
+            wd[0] = w[0];
+            wd[1] = w[1];
+            wd[2] = w[2];
+        }
+        if (rgb != nullptr) {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                rgb[(((long)b * 3 + c) * S + (S - 1 - yi)) * S + xi] = cc[c];
+        }
+    }
+}
+
 extern "C" size_t hoc_raster_forward_workspace_bytes(int B, int F, int S)
 {
     (void)F;
@@ -406,6 +494,18 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
     const long npix = (long)S * S;
     /* (four pixels per thread with 16-byte stores and no staging was measured: 19.6 us against 15.8 -- the pass is
      * bound by the dependent chain of the covered pixels, key -> face -> texture, which a thread then runs four times) */
+    if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && face_inv_map == nullptr && (weight_map == nullptr || sparse_saved) &&
+        ((((uintptr_t)zbuf | (uintptr_t)rgb | (uintptr_t)alpha | (uintptr_t)depth | (uintptr_t)face_index_map) & 15) == 0)) {
+        const long groups = npix / 4;
+        dim3 grid4((unsigned)((groups + RS_THREADS - 1) / RS_THREADS), B);
+        HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
+                   (hoc_raster_resolve4_kernel<<<grid4, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
+                                                                           bg[0], bg[1], bg[2], background_dev, tex_vertex,
+                                                                           sparse_saved, rgb, alpha, depth,
+                                                                           face_index_map, weight_map)));
+        HOC_CHECK_LAUNCH("hoc_raster_resolve4_kernel");
+        return HOC_OK;
+    }
     dim3 grid2((unsigned)((npix + RS_THREADS - 1) / RS_THREADS), B);
     HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
                (hoc_raster_resolve_kernel<<<grid2, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,

@@ -25,140 +25,7 @@
  */
 #include "hoc_common.cuh"
 
-struct HocTaps {
-    float ix, iy;
-    int x0, y0;          /* north-west tap */
-    float nw, ne, sw, se;
-    bool b_nw, b_ne, b_sw, b_se; /* tap inside the image */
-};
-
-/* 1 / max(size - 1, 1) as torch's div-by-scalar kernel computes it (IEEE float divide); evaluated once per
- * thread by the kernels below and passed down, not once per coordinate */
-__device__ __forceinline__ float hoc_inv_extent(int size) { return __fdiv_rn(1.0f, (float)max(size - 1, 1)); }
-
-__device__ __forceinline__ float hoc_norm_coord_inv(int p, float flow, float inv)
-{
-    const float v = __fadd_rn((float)p, flow);
-    return __fadd_rn(__fmul_rn(__fmul_rn(2.0f, v), inv), -1.0f);
-}
-
-__device__ __forceinline__ float hoc_norm_coord(int p, float flow, int size)
-{
-    return hoc_norm_coord_inv(p, flow, hoc_inv_extent(size));
-}
-
-__device__ __forceinline__ float hoc_unnormalize(float coord, int size)
-{
-    /* ((coord + 1.f) * size - 1) / 2 with the multiply-subtract contracted */
-    return __fmul_rn(__fmaf_rn(__fadd_rn(coord, 1.0f), (float)size, -1.0f), 0.5f);
-}
-
-__device__ __forceinline__ void hoc_bilinear_taps_inv(int x, int y, float fx, float fy, int H, int W, float inv_w,
-                                                      float inv_h, HocTaps &T);
-
-__device__ __forceinline__ void hoc_bilinear_taps(int x, int y, float fx, float fy, int H, int W, HocTaps &T)
-{
-    hoc_bilinear_taps_inv(x, y, fx, fy, H, W, hoc_inv_extent(W), hoc_inv_extent(H), T);
-}
-
-__device__ __forceinline__ void hoc_bilinear_taps_inv(int x, int y, float fx, float fy, int H, int W, float inv_w,
-                                                      float inv_h, HocTaps &T)
-{
-    const float ix = hoc_unnormalize(hoc_norm_coord_inv(x, fx, inv_w), W);
-    const float iy = hoc_unnormalize(hoc_norm_coord_inv(y, fy, inv_h), H);
-    T.ix = ix;
-    T.iy = iy;
-    /* clamp before the conversion only to keep it defined; far-away taps are out of bounds anyway */
-    const float fxn = floorf(fminf(fmaxf(ix, -4.0f), (float)W + 4.0f));
-    const float fyn = floorf(fminf(fmaxf(iy, -4.0f), (float)H + 4.0f));
-    const int x0 = (int)fxn, y0 = (int)fyn;
-    T.x0 = x0;
-    T.y0 = y0;
-    const float x_nw = (float)x0, y_nw = (float)y0;
-    const float x_se = (float)(x0 + 1), y_se = (float)(y0 + 1);
-    T.nw = __fmul_rn(__fsub_rn(x_se, ix), __fsub_rn(y_se, iy));
-    T.ne = __fmul_rn(__fsub_rn(ix, x_nw), __fsub_rn(y_se, iy));
-    T.sw = __fmul_rn(__fsub_rn(x_se, ix), __fsub_rn(iy, y_nw));
-    T.se = __fmul_rn(__fsub_rn(ix, x_nw), __fsub_rn(iy, y_nw));
-    const bool xin0 = x0 >= 0 && x0 < W, xin1 = x0 + 1 >= 0 && x0 + 1 < W;
-    const bool yin0 = y0 >= 0 && y0 < H, yin1 = y0 + 1 >= 0 && y0 + 1 < H;
-    /* NaN coordinates: every comparison above is false in ATen as well -> no tap */
-    const bool ok = (ix == ix) && (iy == iy);
-    T.b_nw = ok && xin0 && yin0;
-    T.b_ne = ok && xin1 && yin0;
-    T.b_sw = ok && xin0 && yin1;
-    T.b_se = ok && xin1 && yin1;
-}
-
-/* grid_sample of an all-ones image: sum of the in-bounds weights in tap order. */
-__device__ __forceinline__ float hoc_ones_sample(const HocTaps &T)
-{
-    float acc = 0.0f;
-    if (T.b_nw) acc = __fmaf_rn(1.0f, T.nw, acc);
-    if (T.b_ne) acc = __fmaf_rn(1.0f, T.ne, acc);
-    if (T.b_sw) acc = __fmaf_rn(1.0f, T.sw, acc);
-    if (T.b_se) acc = __fmaf_rn(1.0f, T.se, acc);
-    return acc;
-}
-
-/* grid_sample of one channel plane (zeros padding). */
-__device__ __forceinline__ float hoc_plane_sample(const float *__restrict__ plane, int W, const HocTaps &T)
-{
-    float acc = 0.0f;
-    const float *p = plane + (long)T.y0 * W + T.x0;
-
-    if (T.b_nw) acc = __fmaf_rn(__ldg(p), T.nw, acc);
-    if (T.b_ne) acc = __fmaf_rn(__ldg(p + 1), T.ne, acc);
-    if (T.b_sw) acc = __fmaf_rn(__ldg(p + W), T.sw, acc);
-    if (T.b_se) acc = __fmaf_rn(__ldg(p + W + 1), T.se, acc);
-    return acc;
-}
-
-/* Branch-free form of hoc_plane_sample for the streaming kernels: out-of-bounds taps are read from a clamped
- * (valid) address and enter the same FMA chain with weight 0 -- fma(v, 0, acc) == acc for every finite v -- so
- * that all loads of all planes can be issued before the first one is consumed. */
-struct HocTapsFlat {
-    int o[4];   /* offsets of nw, ne, sw, se inside a plane (clamped into the image) */
-    float w[4]; /* their weights, 0 for taps outside the image */
-};
-
-__device__ __forceinline__ void hoc_flatten_taps(const HocTaps &T, int H, int W, HocTapsFlat &F)
-{
-    const int x0 = min(max(T.x0, 0), W - 1), x1 = min(max(T.x0 + 1, 0), W - 1);
-    const int y0 = min(max(T.y0, 0), H - 1), y1 = min(max(T.y0 + 1, 0), H - 1);
-    F.o[0] = y0 * W + x0;
-    F.o[1] = y0 * W + x1;
-    F.o[2] = y1 * W + x0;
-    F.o[3] = y1 * W + x1;
-    F.w[0] = T.b_nw ? T.nw : 0.0f;
-    F.w[1] = T.b_ne ? T.ne : 0.0f;
-    F.w[2] = T.b_sw ? T.sw : 0.0f;
-    F.w[3] = T.b_se ? T.se : 0.0f;
-}
-
-__device__ __forceinline__ float hoc_flat_combine(const float *v, const HocTapsFlat &F)
-{
-    return __fmaf_rn(v[3], F.w[3], __fmaf_rn(v[2], F.w[2], __fmaf_rn(v[1], F.w[1], __fmaf_rn(v[0], F.w[0], 0.0f))));
-}
-
-/* mask[mask < thresh] = 0; mask[mask > 0] = 1 */
-__device__ __forceinline__ float hoc_threshold_mask(float m, float thresh)
-{
-    if (m < thresh)
-        m = 0.0f;
-    if (m > 0.0f)
-        m = 1.0f;
-    return m;
-}
-
-#define WP_THREADS 256
-#define WP_MAXC 4
-/* The per-sample sum of |diff| is accumulated over the CTAs with double atomics.  Every CTA's partial sum is first
- * rounded to an integer multiple of 2^-28: integer-valued doubles add exactly (below 2^53), so the total does not
- * depend on the order in which the CTAs arrive -- the loss is reproducible bit for bit.  (A partial sum >= 2^-4 has no
- * bits below 2^-28: nothing is lost; smaller ones are rounded by < 2e-9.) */
-#define WP_SUM_SCALE 268435456.0
-#define WP_SUM_INV (1.0 / 268435456.0)
+#include "warp_math.cuh"
 
 template <int CT, int CJT> /* compile-time channel counts (0 = use the run-time values, any count) */
 __global__ void __launch_bounds__(WP_THREADS)
@@ -322,6 +189,25 @@ __global__ void hoc_pair_loss_kernel(const double *__restrict__ sums_fwd, const 
     }
 }
 
+/* The same plus the batch mean (warpbranch.py:88: the mean over the single pair's per-sample losses), one warp:
+ * no separate reduction kernel, and its adjoint (d mean / d loss[b] = 1 / B) is folded into the backward kernel. */
+__global__ void hoc_pair_loss_mean_kernel(const double *__restrict__ sums_fwd, const double *__restrict__ sums_bwd, int B,
+                                          float *__restrict__ loss, float *__restrict__ mean)
+{
+    float acc = 0.0f;
+    for (int b = threadIdx.x; b < B; b += 32) {
+        const float lf = (float)(sums_fwd[2 * b] * WP_SUM_INV / fmax(sums_fwd[2 * b + 1], 1.0));
+        const float l = (sums_bwd != nullptr)
+                            ? (float)(sums_bwd[2 * b] * WP_SUM_INV / fmax(sums_bwd[2 * b + 1], 1.0)) + lf
+                            : lf;
+        loss[b] = l;
+        acc += l;
+    }
+    acc = hoc_warp_sum(acc);
+    if (threadIdx.x == 0)
+        *mean = acc / (float)B;
+}
+
 /* d loss[b] / d flow.  loss[b] = sum_valid |warp - target| / max(count, 1); the thresholded masks
  * carry no gradient, so only the bilinear taps of `src` depend on the flow. */
 __global__ void __launch_bounds__(WP_THREADS)
@@ -399,60 +285,6 @@ struct HocPairDir {
     uint8_t *valid_mask, *flow_mask;
     double *sums;
 };
-
-/* one pixel of one direction: sample position -> masks -> |warp - target|; v / d / wm get the three channel values
- * when VIS.  Arithmetic identical to hoc_warp_photo_forward_kernel<3, 3> (same helpers, same order). */
-template <bool VIS>
-__device__ __forceinline__ bool hoc_pair_pixel(const float *__restrict__ sb, const float *__restrict__ jb,
-                                               const float *tv, float jc, int x, int y, float fx, float fy, int H,
-                                               int W, int npix, float inv_w, float inv_h, float thresh, float *v,
-                                               float *d, float *wm, float *sum_d)
-{
-    HocTaps T;
-    hoc_bilinear_taps_inv(x, y, fx, fy, H, W, inv_w, inv_h, T);
-    const float m = hoc_threshold_mask(hoc_ones_sample(T), thresh);
-    HocTapsFlat F;
-    hoc_flatten_taps(T, H, W, F);
-    float sv[3][4], jv[3][4];
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            sv[c][k] = __ldg(sb + (size_t)c * npix + F.o[k]);
-    float wm0 = m;
-    if (jb != nullptr) {
-#pragma unroll
-        for (int c = 0; c < (VIS ? 3 : 1); c++)
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                jv[c][k] = __ldg(jb + (size_t)c * npix + F.o[k]);
-#pragma unroll
-        for (int c = 0; c < (VIS ? 3 : 1); c++) {
-            const float wj = __fmul_rn(hoc_flat_combine(jv[c], F), m);
-            const float w = __fmul_rn(m, (wj == 1.0f) ? 1.0f : 0.0f);
-            if (VIS)
-                wm[c] = w;
-            if (c == 0)
-                wm0 = w;
-        }
-    } else if (VIS) {
-        wm[0] = wm[1] = wm[2] = m;
-    }
-    const bool valid = (jb != nullptr) ? ((wm0 != 0.0f) && !(fx == 0.0f) && (jc == 1.0f)) : ((m != 0.0f) && !(fx == 0.0f));
-    float acc = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const float val = __fmul_rn(hoc_flat_combine(sv[c], F), m);
-        const float dd = fabsf(__fsub_rn(val, tv[c]));
-        if (VIS) {
-            v[c] = val;
-            d[c] = dd;
-        }
-        acc += dd; /* channel order r, g, b like the single-direction kernel */
-    }
-    *sum_d = acc;
-    return valid;
-}
 
 template <bool VIS>
 __global__ void __launch_bounds__(WP_THREADS)
@@ -564,87 +396,115 @@ struct HocPairBwdDir {
 };
 
 __global__ void __launch_bounds__(WP_THREADS)
-hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const float *__restrict__ grad_loss, int S, int H,
-                                    int W, float inv_w, float inv_h)
+hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const float *__restrict__ grad_loss,
+                                    const float *__restrict__ grad_mean, int B, int S, int H, int W, float inv_w,
+                                    float inv_h, uint4 *__restrict__ zero, long n_zero)
 {
+    if (n_zero > 0) { /* zero-fill for the kernels that follow (counters of the rasterizer backward), spread over the grid */
+        const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * WP_THREADS;
+        for (long i = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WP_THREADS + threadIdx.x;
+             i < n_zero; i += nthreads)
+            zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     const HocPairBwdDir &D = blockIdx.z ? D1 : D0;
     if (D.grad_rgb == nullptr && D.grad_flow == nullptr)
         return;
+    /* Two phases per CTA (1024 raster pixels).  A: 16-byte zero stores of the gradient planes, the valid pixels noted
+     * in a shared list.  B: the listed pixels (a few per cent) one per thread: 12 taps + the gradient of the bilinear
+     * weights, scalar stores over the zeros. */
+    __shared__ unsigned short s_list[WP_THREADS * 4];
+    __shared__ int s_n;
     const int b = blockIdx.y;
     const int S4 = S >> 2;
     const int q = blockIdx.x * WP_THREADS + threadIdx.x;
-    if (q >= S * S4)
-        return;
-    const int y = q / S4, x0 = (q - y * S4) << 2;
-    float gx[4] = {0.f, 0.f, 0.f, 0.f}, gy[4] = {0.f, 0.f, 0.f, 0.f};
-    float gfx[4] = {0.f, 0.f, 0.f, 0.f}, gfy[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool inside = y < H && x0 < W; /* W % 4 == 0: a group is inside or outside as a whole */
     const long npix = (long)H * W;
-    if (inside && D.active) {
-        const long pix = (long)y * W + x0;
-        const unsigned vb = *reinterpret_cast<const unsigned *>(D.valid_mask + (long)b * npix + pix);
-        if (vb != 0u) {
-            const float4 f01 = *reinterpret_cast<const float4 *>(D.flow + ((long)b * npix + pix) * 2);
-            const float4 f23 = *reinterpret_cast<const float4 *>(D.flow + ((long)b * npix + pix) * 2 + 4);
-            const float4 mu = *reinterpret_cast<const float4 *>(D.mult + (long)b * npix + pix);
-            const float fx[4] = {f01.x, f01.z, f23.x, f23.z}, fy[4] = {f01.y, f01.w, f23.y, f23.w};
-            const float mm[4] = {mu.x, mu.y, mu.z, mu.w};
-            const float cnt = (float)D.sums[2 * b + 1];
-            const float scale = grad_loss[b] / fmaxf(cnt, 1.0f);
+    if (threadIdx.x == 0)
+        s_n = 0;
+    __syncthreads();
+    if (q < S * S4) {
+        const int y = q / S4, x0 = (q - y * S4) << 2;
+        const bool inside = y < H && x0 < W; /* W % 4 == 0: a group is inside or outside as a whole */
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (D.grad_rgb != nullptr) {
+            float *dst = D.grad_rgb + (long)b * 3 * S * S + (long)y * S + x0;
+            *reinterpret_cast<float4 *>(dst) = z4;
+            *reinterpret_cast<float4 *>(dst + (long)S * S) = z4;
+            *reinterpret_cast<float4 *>(dst + 2l * S * S) = z4;
+        }
+        if (inside) {
+            const long pix = (long)y * W + x0;
+            if (D.grad_flow != nullptr) {
+                float *dst = D.grad_flow + ((long)b * npix + pix) * 2;
+                *reinterpret_cast<float4 *>(dst) = z4;
+                *reinterpret_cast<float4 *>(dst + 4) = z4;
+            }
+            if (D.active) {
+                const unsigned vb = *reinterpret_cast<const unsigned *>(D.valid_mask + (long)b * npix + pix);
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                if (!((vb >> (8 * j)) & 0xffu))
-                    continue;
-                HocTaps T;
-                hoc_bilinear_taps_inv(x0 + j, y, fx[j], fy[j], H, W, inv_w, inv_h, T);
-                const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
-                float gix = 0.0f, giy = 0.0f;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    const float *plane = D.src + ((long)b * 3 + c) * npix;
-                    const float v = hoc_plane_sample(plane, W, T); /* valid => in-bounds mask is 1 */
-                    const float d = v - D.target[((long)b * 3 + c) * npix + pix + j];
-                    const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-                    const float go = scale * sgn;
-                    const float *p = plane + (long)T.y0 * W + T.x0;
-                    if (T.b_nw) {
-                        const float v0 = __ldg(p);
-                        gix -= v0 * (y_se - T.iy) * go;
-                        giy -= v0 * (x_se - T.ix) * go;
-                    }
-                    if (T.b_ne) {
-                        const float v1 = __ldg(p + 1);
-                        gix += v1 * (y_se - T.iy) * go;
-                        giy -= v1 * (T.ix - x_nw) * go;
-                    }
-                    if (T.b_sw) {
-                        const float v2 = __ldg(p + W);
-                        gix -= v2 * (T.iy - y_nw) * go;
-                        giy += v2 * (x_se - T.ix) * go;
-                    }
-                    if (T.b_se) {
-                        const float v3 = __ldg(p + W + 1);
-                        gix += v3 * (T.iy - y_nw) * go;
-                        giy += v3 * (T.ix - x_nw) * go;
-                    }
-                }
-                gfx[j] = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
-                gfy[j] = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
-                gx[j] = gfx[j] * mm[j]; /* hoc_flow_finalize_backward_kernel */
-                gy[j] = gfy[j] * mm[j];
+                for (int j = 0; j < 4; j++)
+                    if ((vb >> (8 * j)) & 0xffu)
+                        s_list[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + j);
             }
         }
     }
-    if (D.grad_rgb != nullptr) {
-        float *dst = D.grad_rgb + (long)b * 3 * S * S + (long)y * S + x0;
-        *reinterpret_cast<float4 *>(dst) = make_float4(gx[0], gx[1], gx[2], gx[3]);
-        *reinterpret_cast<float4 *>(dst + (long)S * S) = make_float4(gy[0], gy[1], gy[2], gy[3]);
-        *reinterpret_cast<float4 *>(dst + 2l * S * S) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (D.grad_flow != nullptr && inside) {
-        float *dst = D.grad_flow + ((long)b * npix + (long)y * W + x0) * 2;
-        *reinterpret_cast<float4 *>(dst) = make_float4(gfx[0], gfy[0], gfx[1], gfy[1]);
-        *reinterpret_cast<float4 *>(dst + 4) = make_float4(gfx[2], gfy[2], gfx[3], gfy[3]);
+    __syncthreads(); /* orders phase A's zero stores before phase B's stores to the same addresses */
+    const int n = s_n;
+    if (n == 0)
+        return;
+    const float cnt = (float)D.sums[2 * b + 1];
+    /* d L / d loss[b]: given directly, and / or through the batch mean (d mean / d loss[b] = 1 / B) */
+    const float gl = ((grad_loss != nullptr) ? grad_loss[b] : 0.0f) +
+                     ((grad_mean != nullptr) ? __fdiv_rn(grad_mean[0], (float)B) : 0.0f);
+    const float scale = gl / fmaxf(cnt, 1.0f);
+    for (int i = threadIdx.x; i < n; i += WP_THREADS) {
+        const int loc = s_list[i];
+        const int qq = blockIdx.x * WP_THREADS + (loc >> 2);
+        const int y = qq / S4, x = ((qq - y * S4) << 2) + (loc & 3);
+        const long pix = (long)y * W + x;
+        const float2 fl = *reinterpret_cast<const float2 *>(D.flow + ((long)b * npix + pix) * 2);
+        HocTaps T;
+        hoc_bilinear_taps_inv(x, y, fl.x, fl.y, H, W, inv_w, inv_h, T);
+        const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
+        float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float *plane = D.src + ((long)b * 3 + c) * npix;
+            const float v = hoc_plane_sample(plane, W, T); /* valid => in-bounds mask is 1 */
+            const float d = v - D.target[((long)b * 3 + c) * npix + pix];
+            const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+            const float go = scale * sgn;
+            const float *p = plane + (long)T.y0 * W + T.x0;
+            if (T.b_nw) {
+                const float v0 = __ldg(p);
+                gix -= v0 * (y_se - T.iy) * go;
+                giy -= v0 * (x_se - T.ix) * go;
+            }
+            if (T.b_ne) {
+                const float v1 = __ldg(p + 1);
+                gix += v1 * (y_se - T.iy) * go;
+                giy -= v1 * (T.ix - x_nw) * go;
+            }
+            if (T.b_sw) {
+                const float v2 = __ldg(p + W);
+                gix -= v2 * (T.iy - y_nw) * go;
+                giy += v2 * (x_se - T.ix) * go;
+            }
+            if (T.b_se) {
+                const float v3 = __ldg(p + W + 1);
+                gix += v3 * (T.iy - y_nw) * go;
+                giy += v3 * (T.ix - x_nw) * go;
+            }
+        }
+        const float gfx = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
+        const float gfy = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
+        if (D.grad_rgb != nullptr) {
+            const float m = D.mult[(long)b * npix + pix]; /* hoc_flow_finalize_backward_kernel */
+            float *dst = D.grad_rgb + (long)b * 3 * S * S + (long)y * S + x;
+            dst[0] = gfx * m;
+            dst[(long)S * S] = gfy * m;
+        }
+        if (D.grad_flow != nullptr)
+            *reinterpret_cast<float2 *>(D.grad_flow + ((long)b * npix + pix) * 2) = make_float2(gfx, gfy);
     }
 }
 
@@ -883,6 +743,17 @@ extern "C" int hoc_pair_loss(const double *sums_fwd, const double *sums_bwd, int
     return HOC_OK;
 }
 
+extern "C" int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, float *loss, float *mean,
+                                  void *stream)
+{
+    HOC_CHECK_ARG(B >= 1, "hoc_pair_loss_mean: batch %d", B);
+    HOC_CHECK_ARG(sums_fwd && loss && mean, "hoc_pair_loss_mean: NULL argument");
+    HOC_LAUNCH(HOC_K_PAIR_LOSS, (cudaStream_t)stream,
+               (hoc_pair_loss_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums_fwd, sums_bwd, B, loss, mean)));
+    HOC_CHECK_LAUNCH("hoc_pair_loss_mean_kernel");
+    return HOC_OK;
+}
+
 extern "C" int hoc_warp_photo_backward(const float *src, const float *target, const float *flow,
                                        const uint8_t *valid_mask, const double *sums, const float *grad_loss, int B,
                                        int C, int H, int W, float thresh, float *grad_flow, void *stream)
@@ -996,9 +867,10 @@ extern "C" int hoc_warp_photo_forward_pair(const float *image_ref, const float *
 
 extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float *image, const float *flow12,
                                             const float *flow21, const uint8_t *const *valid_mask, const double *sums,
-                                            const float *mult1, const float *mult2, const float *grad_loss, int B, int S,
-                                            int H, int W, int use_backward, float *grad_rgb1, float *grad_rgb2,
-                                            float *grad_flow12, float *grad_flow21, void *stream)
+                                            const float *mult1, const float *mult2, const float *grad_loss,
+                                            const float *grad_mean, int B, int S, int H, int W, int use_backward,
+                                            float *grad_rgb1, float *grad_rgb2, float *grad_flow12, float *grad_flow21,
+                                            void *zero, size_t zero_bytes, void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && S >= 4 && (S % 4) == 0 && H >= 1 && H <= S && W >= 4 && W <= S && (W % 4) == 0,
                   "hoc_warp_photo_backward_pair: bad shape B=%d S=%d H=%d W=%d (S, W multiples of 4)", B, S, H, W);
@@ -1006,8 +878,10 @@ extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float 
     if (B == 0)
         return HOC_OK;
     HOC_CHECK_ARG(image_ref && image && flow12 && flow21 && valid_mask && valid_mask[0] && valid_mask[1] && sums &&
-                      grad_loss,
+                      (grad_loss || grad_mean),
                   "hoc_warp_photo_backward_pair: NULL argument");
+    HOC_CHECK_ARG(zero == nullptr || (zero_bytes % 16 == 0 && ((uintptr_t)zero & 15) == 0),
+                  "hoc_warp_photo_backward_pair: zero buffer must be 16-byte aligned with a size multiple of 16");
     HOC_CHECK_ARG((grad_rgb1 == nullptr || mult1 != nullptr) && (grad_rgb2 == nullptr || mult2 != nullptr),
                   "hoc_warp_photo_backward_pair: grad_rgb requested without mult");
     HocPairBwdDir D[2];
@@ -1025,8 +899,8 @@ extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float 
     dim3 grid((unsigned)((groups + WP_THREADS - 1) / WP_THREADS), B, 2);
     HOC_LAUNCH(HOC_K_WARP_PHOTO_BWD, (cudaStream_t)stream,
                (hoc_warp_photo_pair_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
-                   D[0], D[1], grad_loss, S, H, W, 1.0f / (float)(W - 1 > 1 ? W - 1 : 1),
-                   1.0f / (float)(H - 1 > 1 ? H - 1 : 1))));
+                   D[0], D[1], grad_loss, grad_mean, B, S, H, W, 1.0f / (float)(W - 1 > 1 ? W - 1 : 1),
+                   1.0f / (float)(H - 1 > 1 ? H - 1 : 1), (uint4 *)zero, zero ? (long)(zero_bytes / 16) : 0l)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_pair_backward_kernel");
     return HOC_OK;
 }

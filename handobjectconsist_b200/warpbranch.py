@@ -66,15 +66,15 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
         # one frame pair, the renderer WarpRegNet builds, L1: the whole step behind one autograd node
         # (consist.py: 6 launches forward, 5 backward, both renders stacked along the batch)
         hand2, obj2 = (hand_verts[1].detach(), obj_verts[1].detach()) if first_only else (hand_verts[1], obj_verts[1])
-        warp_loss, flows, masks, warps, diffs = consist.pair_consist_step(
+        (warp_loss, warp_mean), flows, masks, warps, diffs = consist.pair_consist_step(
             hand_verts[0], obj_verts[0], hand2, obj2, hand_face.cuda(non_blocking=True), obj_faces[last], camintrs[0],
             camintrs[1], images[0], images[1], jitter_masks[0], jitter_masks[1], renderer, image_size,
             hand_ignore_faces=hand_ignore_faces, detach_renders=detach_renders, use_backward=use_backward,
             return_visuals=return_visuals)
-        stack_losses = warp_loss.unsqueeze(0)
+        # the mean over the single pair's per-sample losses (warpbranch.py:88) comes out of the same launch
         pair_results = {"masks": [masks], "warps": [warps], "recons_flows": [flows], "diffs": [diffs],
-                        "diff_losses": stack_losses}
-        return stack_losses.mean(), pair_results
+                        "diff_losses": warp_loss.unsqueeze(0)}
+        return warp_mean, pair_results
     if len(samples) == 2 and hand_face.dim() in (2, 3) and (hand_face.dim() == 2 or hand_face.shape[0] == 1):
         # one frame pair (the training setting): both concatenations and the face table in one launch
         verts_a, verts_b, all_faces = cat_hand_object_pair(hand_verts[0], obj_verts[0], hand_verts[1], obj_verts[1],

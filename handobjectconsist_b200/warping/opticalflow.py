@@ -111,7 +111,7 @@ class _MeshRasterFunction(Function):
             sc_ws = torch.empty(sc_bytes, dtype=torch.uint8, device=dev) if sc_bytes else None
             _lib.check(L.hoc_mesh_scatter_ws(_lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(fi), B, V, Fn,
                                              int(fill_back), _lib.HOC_TEX_GRAD_VERTEX, _lib.ptr(grad_verts),
-                                             _lib.ptr(grad_attrs), _lib.ptr(sc_ws), sc_bytes, st),
+                                             _lib.ptr(grad_attrs), 0, _lib.ptr(sc_ws), sc_bytes, st),
                        "hoc_mesh_scatter")
         return (grad_verts, grad_attrs) + (None,) * 7
 

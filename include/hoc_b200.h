@@ -178,13 +178,18 @@ int hoc_raster_backward(const float *faces, const float *textures, const int32_t
 
 /* The same for a batch of which only the first `geom_samples` samples need the pseudo-gradient
  * (backward_pixel_map); the rows of grad_faces of the others hold the depth gradient alone.  Used by the frame-pair
- * path, which stacks the two renders of a pair ([2B]) and differentiates the geometry of the first one only. */
+ * path, which stacks the two renders of a pair ([2B]) and differentiates the geometry of the first one only.
+ * flags: HOC_BWD_WORKSPACE_ZEROED = the first hoc_raster_backward_zero_bytes(B,F,S) bytes of the workspace are
+ * already zero (an earlier kernel of the caller's sequence filled them: one memset node less in a captured step).
+ * extra_zero: a float buffer the streaming pass also zero-fills (the outputs of the hoc_mesh_scatter that follows). */
+#define HOC_BWD_WORKSPACE_ZEROED 1
+size_t hoc_raster_backward_zero_bytes(int B, int F, int S);
 int hoc_raster_backward_ex(const float *faces, const float *textures, const int32_t *face_index_map,
                            const float *rgb, const float *weight_map, const float *depth, const float *grad_rgb,
                            const float *grad_alpha, const float *grad_depth, int B, int F, int S, int ts,
                            float near_, float far_, float eps, int layout, int use_alpha, int tex_grad_mode,
-                           int geom_samples, float *grad_faces, float *grad_textures, void *workspace,
-                           size_t workspace_bytes, void *stream);
+                           int geom_samples, int flags, void *extra_zero, size_t extra_zero_bytes, float *grad_faces,
+                           float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- flow-guided warp + masked photometric L1 ---------------------------------------------
  * ONE direction of pair_consist (imgflowarp.py:80-107) in one launch: warp(src, flow),
@@ -237,12 +242,27 @@ int hoc_warp_photo_forward_pair(const float *image_ref, const float *image, cons
 /* Backward of both directions fused with hoc_flow_finalize_backward: grad_rgb1 / grad_rgb2 [B,3,S,S] (image layout,
  * fully overwritten: d loss / d flow x mult inside the H x W crop, zero elsewhere and in the third channel) are the
  * incoming gradients of the two renders; grad_flow12 / grad_flow21 [B,H,W,2] optionally receive d loss / d flow
- * itself.  Any output may be NULL.  use_backward = 0: direction 1 carries no loss (zeros). */
+ * itself.  Any output may be NULL.  use_backward = 0: direction 1 carries no loss (zeros).
+ * grad_loss [B] and / or grad_mean [1]: d L / d loss[b] = grad_loss[b] + grad_mean / B (the adjoint of the batch mean
+ * hoc_pair_loss_mean emits).  zero: an optional buffer the kernel also zero-fills (the counters of the
+ * hoc_raster_backward_ex that follows, see HOC_BWD_WORKSPACE_ZEROED). */
 int hoc_warp_photo_backward_pair(const float *image_ref, const float *image, const float *flow12, const float *flow21,
                                  const uint8_t *const *valid_mask, const double *sums, const float *mult1,
-                                 const float *mult2, const float *grad_loss, int B, int S, int H, int W,
-                                 int use_backward, float *grad_rgb1, float *grad_rgb2, float *grad_flow12,
-                                 float *grad_flow21, void *stream);
+                                 const float *mult2, const float *grad_loss, const float *grad_mean, int B, int S,
+                                 int H, int W, int use_backward, float *grad_rgb1, float *grad_rgb2,
+                                 float *grad_flow12, float *grad_flow21, void *zero, size_t zero_bytes, void *stream);
+/* hoc_flow_finalize and the training half of hoc_warp_photo_forward_pair (visuals = 0) in ONE pass: the pixel that
+ * has just produced its flow vector is the pixel whose warp that flow drives.  Same arguments as the two calls
+ * (valid_mask / flow_mask / sums indexed by pair_consist's direction); `sums` must be zero on entry
+ * (hoc_pair_front's zero region). */
+int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
+                           const float *alpha2, const int32_t *idx2, const float *image_ref, const float *image,
+                           const float *jitter_ref, const float *jitter, int B, int S, int H, int W,
+                           const int *ignore_faces, int n_ignore, float distance_thresh, float thresh, float *flow12,
+                           float *flow21, float *mult1, float *mult2, uint8_t *const *valid_mask,
+                           uint8_t *const *flow_mask, double *sums, void *stream);
+/* hoc_pair_loss plus the mean over the batch (warpbranch.py:88 for one pair), one launch. */
+int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, float *loss, float *mean, void *stream);
 
 /* pair_consist's per-sample loss from the sums of its two directions (imgflowarp.py:108-114):
  * loss[b] = masked_mean(bwd) + masked_mean(fwd) (that order, float) when sums_bwd is given, else masked_mean(fwd). */
@@ -300,26 +320,28 @@ int hoc_mesh_scatter(const float *grad_faces, const float *grad_textures, const 
                      int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs, void *stream);
 /* The same with a workspace: 0 bytes in production, the fixed-point accumulators of both outputs in the
  * reproducible mode (HOC_TUNE_DETERMINISTIC), where hoc_mesh_scatter itself fails with HOC_ERR_WORKSPACE.
+ * outputs_zeroed = 1: the caller (an earlier kernel of its sequence) already filled both outputs with zeros.
  * Precondition of both (and of hoc_mesh_gather): 0 <= faces_idx < V; indices outside that range are skipped
  * (gather: read as vertex 0) instead of touching memory out of bounds. */
 size_t hoc_mesh_scatter_workspace_bytes(int B, int V);
 int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, const long long *faces_idx, int B, int V,
                         int F, int fill_back, int tex_grad_mode, float *grad_verts, float *grad_attrs,
-                        void *workspace, size_t workspace_bytes, void *stream);
+                        int outputs_zeroed, void *workspace, size_t workspace_bytes, void *stream);
 /* Frame-pair front end in ONE launch (replaces hoc_cat_meshes + hoc_flow_vertices + 2 x hoc_mesh_gather_clear):
  * hand / object vertices of both frames [B,Vh,3] / [B,Vo,3] (camera space), hand_faces [Fh,3] (or [B,Fh,3]),
  * obj_faces [B,Fo,3] (object-local indices) and the cameras -> the rasterizer inputs of BOTH renders stacked along the
  * batch: faces_out / textures_out [2B,F',3,3] (F' = 2 (Fh + Fo) with fill_back; textures are the three vertex values
  * [dx, dy, 1] of HOC_LAYOUT_TEX_VERTEX), rows 0..B-1 = render of mesh 1 with flow 1->2, rows B..2B-1 = render of
  * mesh 2 with flow 2->1.  face_table [2B,Fh+Fo,3] (optional) receives the concatenated table the adjoint walks;
- * `clear` as in hoc_mesh_gather_clear (the z-buffer keys of the [2B] forward that follows).
+ * `clear` as in hoc_mesh_gather_clear (the z-buffer keys of the [2B] forward that follows); `zero` an optional buffer
+ * filled with zeros (the loss sums of hoc_flow_finalize_warp).
  * Replaces warpbranch.py:50-52, opticalflow.py:98-103,121-123, renderer.py:250-252,282. */
 int hoc_pair_front(const float *hand1, const float *obj1, const float *hand2, const float *obj2,
                    const long long *hand_faces, int hand_faces_batched, const long long *obj_faces, const float *K1,
                    int K1_batched, const float *K2, int K2_batched, const float *R, int R_batched, const float *t,
                    int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B, int Vh, int Vo,
                    int Fh, int Fo, int fill_back, float *faces_out, float *textures_out, long long *face_table,
-                   void *clear, size_t clear_bytes, void *stream);
+                   void *clear, size_t clear_bytes, void *zero, size_t zero_bytes, void *stream);
 /* Its per-vertex adjoint: grad_ndc / grad_attrs [2B,Vh+Vo,3] (hoc_mesh_scatter's outputs for the stacked batch; the
  * has_* flags say which halves carry a gradient) -> grad_verts1 / grad_verts2 [B,Vh+Vo,3] (either may be NULL). */
 int hoc_pair_back(const float *hand1, const float *obj1, const float *hand2, const float *obj2, const float *K1,

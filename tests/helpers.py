@@ -60,9 +60,9 @@ def pair_step(sc, S, crop, dev, detach_renders, use_backward, return_visuals=Tru
     hv = HAND_VERTS
     hand_faces = g["faces"][0, :HAND_FACES]
     obj_faces = g["faces"][:, HAND_FACES:] - hv
-    loss, flows, masks, warps, diffs = consist.pair_consist_step(
+    (loss, mean), flows, masks, warps, diffs = consist.pair_consist_step(
         v1[:, :hv], v1[:, hv:], g["verts2"][:, :hv], g["verts2"][:, hv:], hand_faces, obj_faces, g["K"], g["K"],
         g["image_ref"], g["image"], g["jitter_mask_ref"], g["jitter_mask"], r, crop,
         hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=detach_renders, use_backward=use_backward,
         return_visuals=return_visuals)
-    return loss.mean(), dict(flows=flows, loss=loss, masks=masks, warps=warps, diffs=diffs), v1
+    return mean, dict(flows=flows, loss=loss, masks=masks, warps=warps, diffs=diffs), v1

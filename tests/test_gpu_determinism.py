@@ -76,7 +76,7 @@ def test_reproducible_mode_needs_its_workspace():
         outs = []
         for _ in range(2):
             _lib.check(L.hoc_mesh_scatter_ws(_lib.ptr(gf), None, _lib.ptr(fi), B, V, F, 1, _lib.HOC_TEX_GRAD_VERTEX,
-                                             _lib.ptr(gv), None, _lib.ptr(ws), need, st), "scatter")
+                                             _lib.ptr(gv), None, 0, _lib.ptr(ws), need, st), "scatter")
             outs.append(gv.clone())
     assert torch.equal(outs[0], outs[1])
     # against index_add in float64
