@@ -30,7 +30,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 PAIRS = 16          # frame pairs per rank and step (configs[2])
-SIZE = 256          # raster / image side
+SIZE = 256          # raster side of configs[2] (square frames); WIDTH / HEIGHT are the frame size
+WIDTH, HEIGHT = 256, 256
+CONFIG = 2
 N_SETS = 3          # distinct input sets cycled between steps (> L2 between reuse)
 METRIC = "render+warp+photometric fwd+bwd frames/sec @256x256"
 UNIT = "frames/s"
@@ -88,13 +90,15 @@ class ClockSampler(threading.Thread):
 
 def _make_sets(n_sets, pairs, size, device, pin=False, rank=0, world=1):
     """`n_sets` input sets for this rank: the GLOBAL batch of pairs*world frame pairs is generated identically on
-    every rank (same seed) and rank r keeps its shard [r*pairs, (r+1)*pairs) -- sharding.shard_range."""
+    every rank (same seed) and rank r keeps its shard [r*pairs, (r+1)*pairs) -- sharding.shard_range.
+    `size`: int (square frames) or (width, height)."""
     import torch
     from handobjectconsist_b200 import sharding, synth
 
+    width, height = (size, size) if isinstance(size, int) else size
     sets = []
     for i in range(n_sets):
-        sc = synth.make_scene(pairs * world, size, size, seed=1000 + i)
+        sc = synth.make_scene(pairs * world, width, height, seed=1000 + i)
         lo, hi = sharding.shard_range(pairs * world, rank, world)
         sc = {k: (v[lo:hi].contiguous() if torch.is_tensor(v) else v) for k, v in sc.items()}
         if device is not None:
@@ -126,36 +130,59 @@ def _samples_from_scene(sc, hand_v=778):
     return samples, results
 
 
+def _bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and so its later pinned-host allocations, first touch) to the CPUs of the NUMA node its GPU
+    hangs off: with 8 ranks streaming frames over PCIe, a rank whose staging buffers live on the other socket pays the
+    inter-socket hop on every copy.  Best effort -- returns a description or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:  # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+
+
 def run_native(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
 
-    from handobjectconsist_b200 import _lib, warpbranch
+    from handobjectconsist_b200 import _config, _lib, sharding, warpbranch
+    from handobjectconsist_b200.graphed import GraphedConsistStep
     from handobjectconsist_b200.neurender.renderer import Renderer
     from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native arm) needs a CUDA device: the product path has no CPU fallback")
+    numa = _bind_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     L = _lib.lib()
-    renderer = Renderer(image_size=SIZE, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
-                        K=torch.ones(1, 3, 3, device=dev), orig_size=SIZE, anti_aliasing=False, fill_back=True,
+    W, H = WIDTH, HEIGHT
+    S = max(W, H)  # the reference renders on the square that contains the frame (warpreg.py:29,40-45)
+    renderer = Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
+                        K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True,
                         near=0.1, no_light=True)
     criterion = PyramidCriterion("l1")
-    hand_face = None
-
-    def step(samples, results, hand_face, ignore):
-        hv = results[0]["recov_handverts3d"].detach().requires_grad_(True)
-        ov = results[0]["recov_objverts3d"].detach().requires_grad_(True)
-        res = [{"recov_handverts3d": hv, "recov_objverts3d": ov}, results[1]]
-        loss, _ = warpbranch.forward(samples, res, hand_face, renderer, (SIZE, SIZE), criterion, gt_refs=True,
-                                     first_only=True, hand_ignore_faces=ignore, use_backward=True,
-                                     detach_renders=False)
-        loss.backward()
-        return loss, hv.grad, ov.grad
-
-    from handobjectconsist_b200.graphed import GraphedConsistStep
+    step_kw = dict(gt_refs=True, first_only=True, use_backward=True, detach_renders=False)
 
     def barrier():
         torch.cuda.synchronize()
@@ -173,16 +200,44 @@ def run_native(args, rank, world, local_rank):
         barrier()
         return t0.elapsed_time(t1)
 
-    dsets = _make_sets(N_SETS, PAIRS, SIZE, dev, rank=rank, world=world)
+    def timed_blocks(fn, steps, min_total_ms, max_blocks=300):
+        """The K-step block above, repeated until ~min_total_ms of device time has been timed (a 5 ms region moves by
+        per cent on one hiccup).  Every block is max-reduced over the ranks; returns the per-block times."""
+        first = sharding.max_over_ranks([timed(fn, steps)], device=dev)[0]
+        n = int(min(max_blocks, max(1, -(-min_total_ms // max(first, 1e-3)))))
+        blocks = [first] + [timed(fn, steps) for _ in range(n - 1)]
+        return sharding.max_over_ranks(blocks, device=dev)
+
+    def median(v):
+        v = sorted(v)
+        return v[len(v) // 2]
+
+    dsets = _make_sets(N_SETS, PAIRS, (W, H), dev, rank=rank, world=world)
     hand_face = dsets[0]["faces"][0, :1552].clone()
     ignore = dsets[0]["hand_ignore_faces"]
     dbatches = [_samples_from_scene(sc) for sc in dsets]
 
-    # ---- eager arm (every launch issued from python): per-kernel device times for the roofline ----
-    for i in range(args.warmup):
-        step(*dbatches[i % N_SETS], hand_face, ignore)
-    eager_ms = timed(lambda i: step(*dbatches[i % N_SETS], hand_face, ignore), args.steps)
+    def eager_step(samples, results, visuals=False):
+        hv = results[0]["recov_handverts3d"].detach().requires_grad_(True)
+        ov = results[0]["recov_objverts3d"].detach().requires_grad_(True)
+        res = [{"recov_handverts3d": hv, "recov_objverts3d": ov}, results[1]]
+        loss, _ = warpbranch.forward(samples, res, hand_face, renderer, (W, H), criterion, hand_ignore_faces=ignore,
+                                     return_visuals=visuals, **step_kw)
+        loss.backward()
+        return loss
 
+    # ---- measured coverage of the synthetic scene (the algorithmic-byte formulas below use it) ----
+    from handobjectconsist_b200 import consist
+    stats = {}
+    consist.STATS = stats
+    eager_step(*dbatches[0])
+    consist.STATS = None
+    coverage = float(stats.get("coverage", 0.0))
+
+    # ---- eager arm: every launch issued from python (CPU-launch-bound), for reference ----
+    for i in range(args.warmup):
+        eager_step(*dbatches[i % N_SETS])
+    eager_ms = timed(lambda i: eager_step(*dbatches[i % N_SETS]), args.steps)
     if args.eager_only:
         if rank == 0:
             _emit({"eager_ms_per_step": eager_ms / args.steps})
@@ -193,9 +248,9 @@ def run_native(args, rank, world, local_rank):
     # exactly one graph replay (no copies); the sets rotate so that consecutive steps touch different data
     launches0 = L.hoc_launch_count(-1)
 
-    def capture(k):
-        return GraphedConsistStep(renderer, criterion, (SIZE, SIZE), hand_face, *dbatches[k], hand_ignore_faces=ignore,
-                                  gt_refs=True, first_only=True, use_backward=True, detach_renders=False, warmup=1)
+    def capture(k, **kw):
+        return GraphedConsistStep(renderer, criterion, (W, H), hand_face, *dbatches[k], hand_ignore_faces=ignore,
+                                  warmup=1, **step_kw, **kw)
 
     gsteps_dev = [capture(0)]
     launches_per_step = int(L.hoc_launch_count(-1) - launches0) // 2  # one warm-up run + the captured run
@@ -209,26 +264,33 @@ def run_native(args, rank, world, local_rank):
         graphed_step(i)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms = timed(graphed_step, args.steps)
+    blocks = timed_blocks(graphed_step, args.steps, min_total_ms=1000.0)
     clocks = sampler.finish()
+    ms = median(blocks)
     launches = launches_per_step * args.steps
+
+    # ---- the same step WITH the visualisation returns of pair_consist (warps / diffs / warp_mask), for transparency:
+    # `value` times the training step, which does not produce them ----
+    vis_ms = None
+    if world == 1:
+        gvis = capture(0, return_visuals=True)
+        for _ in range(args.warmup):
+            gvis.replay()
+        vis_ms = median(timed_blocks(lambda i: gvis.replay(), args.steps, min_total_ms=200.0))
+        del gvis
 
     # ---- per-kernel device times, measured where the kernels run in production: inside the graph.  A separate,
     # instrumented capture brackets every launch of this library with external event nodes (hoc_timer_*); it is
     # replayed after the timed region so that the event nodes do not perturb `value`.
-    from handobjectconsist_b200 import _config
     timed_mask = sum(1 << v for k, v in _lib.KERNEL_IDS.items() if k != "grad_extent")
-    _config.overlap_streams = False  # one stream: every kernel is timed alone, not sharing the GPU with its twin
-    probe = GraphedConsistStep(renderer, criterion, (SIZE, SIZE), hand_face, *dbatches[0], hand_ignore_faces=ignore,
-                               gt_refs=True, first_only=True, use_backward=True, detach_renders=False, warmup=1,
-                               before_capture=lambda: L.hoc_timer_begin(timed_mask))  # arm right before the capture
+    probe = capture(0, before_capture=lambda: L.hoc_timer_begin(timed_mask))  # arm right before the capture
     L.hoc_timer_pause()
-    _config.overlap_streams = True
     buf = (ctypes.c_float * 8192)()
     ids = (ctypes.c_int * 8192)()
     id2name = {v: k for k, v in _lib.KERNEL_IDS.items()}
     per_kernel = {}
-    for i in range(max(args.steps, 5)):
+    probe_steps = max(min(args.steps, 50), 5)
+    for i in range(probe_steps):
         probe.load(*dbatches[i % N_SETS])
         probe.replay()
         torch.cuda.synchronize()
@@ -236,57 +298,63 @@ def run_native(args, rank, world, local_rank):
         for j in range(n_k):
             if buf[j] >= 0:
                 per_kernel.setdefault(id2name[ids[j]], []).append(buf[j])
-    probe_steps = max(args.steps, 5)
     L.hoc_timer_begin(0)
 
     # ---- end-to-end arm: pinned host buffers -> static device buffers -> graph -> host ----
-    hsets = _make_sets(N_SETS, PAIRS, SIZE, None, pin=True, rank=rank, world=world)
+    # A ring of RING captured steps with their own static buffers and their own pinned result slots.  While step i
+    # replays, the inputs of steps i+1 .. i+RING-1 are in flight on the copy stream; the host never waits for the step
+    # it has just issued: it reads the loss of step i-1 (event wait, one step behind) and goes on issuing.  Every timed
+    # step pays exactly one H2D of its inputs and one D2H of its results.
+    RING = 3
+    hsets = _make_sets(N_SETS, PAIRS, (W, H), None, pin=True, rank=rank, world=world)
     hbatches = [_samples_from_scene(sc) for sc in hsets]
-    grad_host = [torch.empty(PAIRS, 778, 3).pin_memory(), torch.empty(PAIRS, 1502, 3).pin_memory()]
-    loss_host = torch.empty(()).pin_memory()
-
-    # two captured steps with their own static buffers: while step i replays, the inputs of step i+1 are
-    # copied host -> device on a second stream (every timed step still pays exactly one H2D of its inputs
-    # and one D2H of its results)
-    gsteps = gsteps_dev[:2]
+    gsteps = gsteps_dev[:RING] if len(gsteps_dev) >= RING else gsteps_dev + [capture(0) for _ in range(RING - len(gsteps_dev))]
+    grad_host = [[torch.empty(PAIRS, 778, 3).pin_memory(), torch.empty(PAIRS, 1502, 3).pin_memory()] for _ in range(RING)]
+    loss_host = [torch.empty(()).pin_memory() for _ in range(RING)]
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
-    def run_e2e(batches):
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
+    def run_e2e(batches, min_total_ms):
+        ready = [torch.cuda.Event() for _ in range(RING)]
+        done = [torch.cuda.Event() for _ in range(RING)]
+        state = {"issued": 0, "loaded": 0, "losses": 0.0}
         for ev in done:
             ev.record(main_stream)
 
         def prefetch(i):
-            slot = i % 2
+            slot = i % RING
             with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[slot])
+                copy_stream.wait_event(done[slot])  # the slot's previous step has consumed its inputs
                 gsteps[slot].load(*batches[i % N_SETS])
                 ready[slot].record(copy_stream)
 
-        def e2e_step(i):
-            slot = i % 2
-            prefetch(i + 1)
+        def e2e_step(_):
+            i = state["issued"]
+            while state["loaded"] < i + RING - 1 + 1:  # keep RING-1 steps of inputs in flight ahead of the replay
+                prefetch(state["loaded"])
+                state["loaded"] += 1
+            slot = i % RING
             main_stream.wait_event(ready[slot])
             loss, gh, go = gsteps[slot].replay()
-            grad_host[0].copy_(gh, non_blocking=True)
-            grad_host[1].copy_(go, non_blocking=True)
-            loss_host.copy_(loss, non_blocking=True)
+            grad_host[slot][0].copy_(gh, non_blocking=True)
+            grad_host[slot][1].copy_(go, non_blocking=True)
+            loss_host[slot].copy_(loss, non_blocking=True)
             done[slot].record(main_stream)
-            main_stream.synchronize()  # the caller reads the loss every step
+            if i > 0:  # the caller reads the loss of the PREVIOUS step: one step behind, no stall of the one in flight
+                done[(i - 1) % RING].synchronize()
+                state["losses"] += float(loss_host[(i - 1) % RING])
+            state["issued"] = i + 1
 
         nbytes = sum(v.numel() * v.element_size() for s_ in batches[0][0] for v in s_.values() if torch.is_tensor(v))
         nbytes += sum(v.numel() * v.element_size() for r in batches[0][1] for v in r.values())
-        prefetch(0)
         for i in range(args.warmup):
             e2e_step(i)
-        t = timed(lambda i: e2e_step(i + args.warmup), args.steps)
+        t = timed_blocks(e2e_step, args.steps, min_total_ms=min_total_ms, max_blocks=40)
         torch.cuda.synchronize()
-        return t, nbytes
+        return median(t), nbytes
 
-    e2e_ms, h2d = run_e2e(hbatches)
-    d2h = grad_host[0].numel() * 4 + grad_host[1].numel() * 4 + 4
+    e2e_ms, h2d = run_e2e(hbatches, 500.0)
+    d2h = grad_host[0][0].numel() * 4 + grad_host[0][1].numel() * 4 + 4
 
     # the same with the frames and jitter masks as uint8 in host memory (what an image decoder produces; widened and
     # normalised on the device by hoc_unpack_u8 inside GraphedConsistStep.load): a quarter of the image bytes cross PCIe
@@ -307,10 +375,9 @@ def run_native(args, rank, world, local_rank):
         return out, results
 
     u8batches = [to_u8(bt) for bt in hbatches]
-    e2e_u8_ms, h2d_u8 = run_e2e(u8batches)
+    e2e_u8_ms, h2d_u8 = run_e2e(u8batches, 300.0)
 
-    from handobjectconsist_b200 import sharding
-    ms, e2e_ms, eager_ms, e2e_u8_ms = sharding.max_over_ranks([ms, e2e_ms, eager_ms, e2e_u8_ms], device=dev)
+    e2e_ms, eager_ms, e2e_u8_ms = sharding.max_over_ranks([e2e_ms, eager_ms, e2e_u8_ms], device=dev)
     global_loss = float(sharding.global_mean_loss(gstep.loss))  # the one scalar exchange of the path
     if rank != 0:
         return None
@@ -318,102 +385,311 @@ def run_native(args, rank, world, local_rank):
     frames = 2 * PAIRS * world * args.steps
     value = frames / (ms / 1e3)
     peak, peak_src = _peaks()
-    F2, npx = 2 * 4552, PAIRS * SIZE * SIZE
-    # ALGORITHMIC bytes per launch: every datum the kernel needs crosses HBM once.
+    Bp, V, Fh, Fo = PAIRS, 2280, 1552, 3000
+    Fm = Fh + Fo
+    F2 = 2 * Fm                      # faces the rasterizer sees per mesh (fill_back)
+    npx, ncrop = Bp * S * S, Bp * H * W
+    npx2, nf, nf2 = 2 * npx, Bp * F2, 2 * Bp * F2
+    c = coverage
+    # ALGORITHMIC bytes per launch: every datum the kernel needs crosses HBM once.  The frame-pair
+    # path stacks both renders of a pair along the batch, so the rasterizer kernels run once over 2 * pairs samples.
     algo = {
-        "raster_zbuf": PAIRS * F2 * 36 + npx * 8,                       # faces in, 8-byte depth/face key per pixel
-        # key in; faces + vertex values in; rgb12 + alpha4 + idx4 out, depth4 + weights12 out at the covered 7 % only
-        "raster_resolve": npx * 8 + PAIRS * F2 * (36 + 36) + npx * 20 + int(0.07 * npx) * 16,
-        # scan pass (streaming): idx + grad_rgb in; list of covered pixels (4 B per listed pixel, bounded by npx * 4,
-        # counted at the measured 7 % coverage) and the zero-fill of grad_faces + grad of the 9 vertex values out
-        "raster_bwd_pixel": npx * (4 + 12) + int(0.07 * npx) * 4 + PAIRS * F2 * (36 + 36),
-        # cover pass, texture gradient only: per listed pixel idx, grad_rgb, weights, depth; faces in; 9 sums per face out
-        "raster_bwd_cover": int(0.07 * npx) * (4 + 4 + 12 + 12 + 4) + PAIRS * F2 * (36 + 36),
-        # cover pass with the pseudo-gradient: + rgb in, scan records out, grad_faces update
-        "raster_bwd_pixel_k4": int(0.07 * npx) * (4 + 4 + 12 + 12 + 4 + 12 + 2) + PAIRS * F2 * (36 + 36 + 36),
-        "raster_backward": PAIRS * F2 * (36 + 12 + 36),                  # depth epilogue (only with dL/ddepth)
-        # line pass: rgb, grad_rgb, idx once (both axes read the same maps); faces of the queued scans, grad_faces update
-        "raster_bwd_line": npx * (12 + 12 + 4) + PAIRS * F2 * (36 + 36),
-        "warp_photo_fwd": npx * (12 + 8 + 12 + 4 + 4 + 12 + 12 + 12 + 1),
-        "warp_photo_bwd": npx * (12 + 8 + 12 + 1 + 8),
-        "flow_finalize": 2 * npx * (2 * (8 + 4 + 4) + 8 + 4),
-        "flow_finalize_bwd": npx * (8 + 4 + 12),
-        "mesh_gather": PAIRS * (2280 * 24 + 4552 * 24 + F2 * (36 + 36)) + npx * 8,  # + the z-buffer key fill
-        "mesh_scatter": PAIRS * (F2 * (36 + 36) + 4552 * 24 + 2280 * 24),  # grad_faces + grad of the 9 vertex values in
+        # hand / object vertices of both frames + face tables in; faces + vertex values of both renders, the stacked
+        # face table and the z-buffer key fill out
+        "pair_front": Bp * 2 * V * 12 + (Fh + Bp * Fo) * 24 + nf2 * 72 + 2 * Bp * Fm * 24 + npx2 * 8,
+        "raster_zbuf": nf2 * 36 + npx2 * 8,                       # faces in, 8-byte depth/face key per pixel
+        # key in; idx4 + alpha4 + rgb12 out; at the covered pixels face + vertex values in, depth4 + weights12 out
+        "raster_resolve": npx2 * (8 + 20) + int(c * npx2) * (36 + 36 + 16),
+        # finalize + warp, both directions: alpha4 + rgb8 in, flow8 + mult4 + valid1 + flow_mask2 out per pixel; at
+        # covered pixels the ignore / occlusion look-ups (idx4 + 2 x (alpha4 + rgb8 + idx4)) and the warp's operands
+        # (source 12, target 12, jitter 4 + 4)
+        "flow_finalize": 2 * ncrop * (12 + 15) + int(c * 2 * ncrop) * (4 + 32 + 32),
+        # warp backward fused with the finalize backward: valid1 in, grad_rgb 12 out per raster pixel; flow8 + mult4 +
+        # source 12 + target 12 at the valid pixels
+        "warp_photo_bwd": 2 * ncrop * 1 + npx2 * 12 + int(c * 2 * ncrop) * 36,
+        # scan pass over both renders: idx4 + grad_rgb12 in, list entries (8 B per covered pixel) out, zero-fill of
+        # grad_faces (one render) + grad of the vertex values (both) + the scatter's outputs
+        "raster_bwd_pixel": npx2 * 16 + int(c * npx2) * 8 + nf * 36 + nf2 * 36 + 2 * 2 * Bp * V * 12,
+        # cover pass over both renders: per listed pixel entry8 + grad_rgb12 + weights12 + depth4 (+ rgb12 and a 2-byte
+        # scan record for the render with the pseudo-gradient); faces in; 9 sums per face out (+ grad_faces update)
+        "raster_bwd_pixel_k4": int(c * npx2) * 36 + int(c * npx) * 14 + nf2 * 72 + nf * 36,
+        "raster_bwd_cover": int(c * npx2) * 36 + nf2 * 72,
+        "raster_backward": nf * (36 + 12 + 36),                    # depth epilogue (only with dL/ddepth)
+        # line pass (one render): rgb, grad_rgb, idx once (both axes read the same maps); faces of the queued scans,
+        # grad_faces update
+        "raster_bwd_line": npx * (12 + 12 + 4) + nf * (36 + 36),
+        "mesh_scatter": nf * 36 + nf2 * 36 + 2 * Bp * Fm * 24 + 2 * 2 * Bp * V * 12,
+        "pair_back": 2 * 2 * Bp * V * 12 + 2 * Bp * V * 12 + Bp * V * 12,
     }
     table = []
+    step_ms = ms / args.steps
     for name, v in per_kernel.items():
         avg = sum(v) / len(v)
         ab = algo.get(name)
         table.append({"kernel": name, "launches_per_step": len(v) / probe_steps, "avg_ms": avg,
-                      "share_of_step": sum(v) / probe_steps / (ms / args.steps),
+                      "share_of_step": sum(v) / probe_steps / step_ms,
                       "algorithmic_bytes_per_launch": ab,
                       "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
     table.sort(key=lambda r: -r["share_of_step"])
-    kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve_kernel",
-             "raster_bwd_pixel": "hoc_raster_bwd_scan_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel<K4>",
+    kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve4_kernel",
+             "raster_bwd_pixel": "hoc_raster_bwd_scan_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel",
              "raster_bwd_cover": "hoc_raster_bwd_cover_kernel", "raster_backward": "hoc_raster_bwd_depth_kernel",
-             "raster_bwd_line": "hoc_raster_bwd_line_kernel", "warp_photo_fwd": "hoc_warp_photo_forward_kernel",
-             "warp_photo_bwd": "hoc_warp_photo_backward_kernel", "flow_finalize": "hoc_flow_finalize_kernel",
-             "flow_finalize_bwd": "hoc_flow_finalize_backward_kernel", "mesh_gather": "hoc_mesh_gather_kernel",
-             "mesh_scatter": "hoc_mesh_scatter_kernel", "flow_vertices": "hoc_flow_vertices_kernel",
-             "flow_vertices_bwd": "hoc_flow_vertices_backward_kernel"}
+             "raster_bwd_line": "hoc_raster_bwd_line_kernel", "warp_photo_bwd": "hoc_warp_photo_pair_backward_kernel",
+             "flow_finalize": "hoc_flow_finalize_warp_kernel", "mesh_scatter": "hoc_mesh_scatter_kernel",
+             "pair_front": "hoc_pair_front_kernel", "pair_back": "hoc_pair_back_kernel",
+             "pair_loss": "hoc_pair_loss_mean_kernel"}
     traffic_tab = {}
-    tpath = os.path.join(ROOT, "profiles", "raster_backward_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic_r2.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic_tab = json.load(f)
-    # `roofline`: the kernel with the largest share of the step (table[0]); `roofline_raster_backward`: the kernel
-    # BASELINE.json's north_star names -- three launches here (scan, cover, line pass), reported together with the
-    # bytes of the whole backward of one render counted once
+    # `roofline`: the kernel BASELINE.json's north_star names, the rasterizer backward -- three launches here (scan,
+    # cover, line pass) over the stacked batch, reported together with the bytes of the backward of both renders counted
+    # once: the render whose geometry gradient is needed (H*W*28 + 2F*108 per sample) and the render that only
+    # needs its texture gradient (H*W*16 + 2F*72).  `roofline_dominant`: the kernel with the largest share of the step.
     dom = next((r for r in table if r["algorithmic_bytes_per_launch"]), None)
-    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel", "raster_bwd_pixel_k4", "raster_backward",
-                                               "raster_bwd_line")]
-    bwd_bytes = npx * (4 + 12 + 12) + PAIRS * F2 * (36 + 36 + 36)
-    bwd_ms = sum(r["avg_ms"] for r in bwd)
-    traffic = traffic_tab.get(kname[dom["kernel"]].split("<")[0]) if dom else None
+    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel", "raster_bwd_pixel_k4", "raster_bwd_cover",
+                                               "raster_backward", "raster_bwd_line")]
+    bwd_bytes = (npx * 28 + nf * 108) + (npx * 16 + nf * 72)
+    bwd_ms = sum(r["avg_ms"] * r["launches_per_step"] for r in bwd)
+    bwd_traffic = sum(traffic_tab.get(kname[r["kernel"]], 0) for r in bwd) or None
+    timing_note = ("CUDA events (external event nodes) around every launch inside an instrumented copy of the captured "
+                   "graph; the event nodes add ~3-4 us per kernel, so fractions are slightly pessimistic "
+                   "(profiles/timeline_r2.txt holds CUPTI durations of an un-instrumented replay)")
+
+    def roof(r):
+        if r is None:
+            return None
+        return {"kernel": kname.get(r["kernel"], r["kernel"]), "bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": r["achieved_gbs"] / peak, "traffic": traffic_tab.get(kname.get(r["kernel"])),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"],
+                "avg_launch_ms": r["avg_ms"], "launches_timed": int(r["launches_per_step"] * probe_steps),
+                "share_of_step": r["share_of_step"], "timing": timing_note}
+
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[2]: {PAIRS} frame pairs/rank (= {2 * PAIRS} mesh renders of configs[1] shape, "
-                               f"9104 faces after fill_back) render->flow->occlusion->warp->masked L1 fwd+bwd at "
-                               f"{SIZE}x{SIZE}, full geometry+texture backward (detach_renders=False), use_backward=True",
-                   "pairs_per_rank": PAIRS, "image_size": SIZE, "faces_per_mesh": F2, "parallelism": f"dp{world}",
+        "config": {"workload": f"configs[{CONFIG}]: {PAIRS} frame pairs/rank (= {2 * PAIRS} mesh renders of configs[1] "
+                               f"shape, 9104 faces after fill_back) render->flow->occlusion->warp->masked L1 fwd+bwd, "
+                               f"{W}x{H} frames on a {S}x{S} raster, full geometry+texture backward "
+                               f"(detach_renders=False), use_backward=True; training step: the visualisation returns of "
+                               f"pair_consist (warps / diffs / warp_mask) are not produced",
+                   "pairs_per_rank": PAIRS, "image_size": [W, H], "raster_size": S, "faces_per_mesh": F2,
+                   "parallelism": f"dp{world}", "measured_coverage": c,
                    "l2": f"{N_SETS} resident input sets rotate (one captured graph each); a step touches ~250 MB > 126 MB L2"},
+        "timed_region": {"blocks": len(blocks), "steps_per_block": args.steps, "total_ms": sum(blocks),
+                         "block_ms_median": ms, "block_ms_min": min(blocks), "block_ms_max": max(blocks),
+                         "note": "the contract's K-step region (barrier + synchronize on both sides, CUDA events, max "
+                                 "over ranks), repeated; `value` is the median block"},
         "e2e": {"value": frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps, "ring": RING, "numa": numa,
+                "note": "GraphedConsistStep.load + replay from pinned fp32 host buffers (the reference's formats), "
+                        "results to pinned host memory, loss read one step behind"},
         "e2e_u8": {"value": frames / (e2e_u8_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_u8),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_u8_ms / args.steps,
                    "note": "same call with the frames and jitter masks as uint8 host tensors (widened + normalised on the "
                            "device, hoc_unpack_u8); `e2e` above is the reference's fp32 host format"},
         "gpu_launches": launches,
+        "launches_per_step": launches_per_step,
         "loss_global_mean": global_loss,
-        "execution": "forward+backward captured once in a CUDA graph (handobjectconsist_b200.graphed), replayed per step",
+        "execution": "forward+backward captured once in a CUDA graph (handobjectconsist_b200.graphed), replayed per step; "
+                     "the frame-pair path of consist.py: 11 kernel nodes, no memset / ATen node",
+        "with_visuals": ({"value": 2 * PAIRS * args.steps / (vis_ms / 1e3), "ms_per_step": vis_ms / args.steps,
+                          "note": "the same captured step when it also produces pair_consist's visualisation returns"}
+                         if vis_ms else None),
         "eager": {"value": frames / (eager_ms / 1e3), "ms_per_step": eager_ms / args.steps,
                   "note": "same step with every launch issued from python (CPU-launch-bound)"},
         "clocks": clocks,
-        "roofline": {"kernel": kname[dom["kernel"]] if dom else None, "bound": "hbm",
-                     "achieved": dom["achieved_gbs"] if dom else None, "peak": peak, "unit": "GB/s",
-                     "frac": (dom["achieved_gbs"] / peak if dom else None), "traffic": traffic,
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"] if dom else None,
-                     "avg_launch_ms": dom["avg_ms"] if dom else None,
-                     "launches_timed": int(dom["launches_per_step"] * probe_steps) if dom else 0,
-                     "share_of_step": dom["share_of_step"] if dom else None,
-                     "timing": "CUDA events (external event nodes) around every launch inside an instrumented, "
-                               "single-stream copy of the captured graph; `share_of_step` = launches x avg / step "
-                               "time of the two-stream graph, so shares add up to more than the overlap leaves"},
-        "roofline_raster_backward": {
-            "kernels": [kname[r["kernel"]] for r in bwd], "bound": "hbm",
-            "algorithmic_bytes_per_render": bwd_bytes, "ms_per_render": bwd_ms if bwd else None,
-            "achieved": (bwd_bytes / (bwd_ms * 1e-3) / 1e9) if bwd and bwd_ms > 0 else None, "peak": peak, "unit": "GB/s",
-            "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak) if bwd and bwd_ms > 0 else None,
-            "traffic": sum(traffic_tab.get(kname[r["kernel"]].split("<")[0], 0) for r in bwd) or None,
-            "note": "scan + cover + line pass of the render whose geometry gradient is needed (no per-face pass: the pseudo-gradient runs from the covered pixels)"},
+        "roofline": {
+            "kernel": "rasterizer backward: " + " + ".join(sorted({kname[r["kernel"]] for r in bwd})), "bound": "hbm",
+            "achieved": (bwd_bytes / (bwd_ms * 1e-3) / 1e9) if bwd_ms > 0 else None, "peak": peak, "unit": "GB/s",
+            "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak) if bwd_ms > 0 else None, "traffic": bwd_traffic,
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms,
+            "share_of_step": bwd_ms / step_ms if bwd_ms else None, "timing": timing_note,
+            "note": "scan + cover + line pass over the stacked batch of both renders (one launch each); bytes: the render "
+                    "with the pseudo-gradient (H*W*28 + 2F*108 per sample) + the texture-only render (H*W*16 + 2F*72)"},
+        "roofline_dominant": roof(dom),
         "kernels": table,
     }
     return out
+
+
+def run_config4(args, rank, world, local_rank):
+    """BASELINE.json configs[3]: the full trainmeshwarp optimisation step under DDP -- ResNet-18 backbone + MLP heads
+    (torch / cuDNN, bench_models.py) -> ManoLayer -> geometry head -> WarpRegNet's photometric consistency step (this
+    library, one CUDA-graph replay) -> backward -> NCCL all-reduce of the network gradients (DistributedDataParallel,
+    overlapped with the backward) -> Adam step (trainmeshwarp.py:181-255, epochpassconsist.py:56-68,
+    warpreg.py:81-127).  Weak scaling: PAIRS frame pairs per rank (8 -> global batch 64 on 8 GPUs)."""
+    import torch
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    import bench_models
+    from handobjectconsist_b200 import _lib, sharding, synth
+    from handobjectconsist_b200.queries import BaseQueries, TransQueries
+    from handobjectconsist_b200.warpreg import WarpRegNet
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: the product path has no CPU fallback")
+    numa = _bind_to_gpu_numa_node(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    W, H, B, hv = WIDTH, HEIGHT, PAIRS, 778
+    sf, tf = 1e-4, 100.0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            fn(i)
+        t1.record()
+        barrier()
+        return t0.elapsed_time(t1)
+
+    def median(v):
+        v = sorted(v)
+        return v[len(v) // 2]
+
+    def timed_blocks(fn, steps, min_total_ms, max_blocks=100):
+        first = sharding.max_over_ranks([timed(fn, steps)], device=dev)[0]
+        n = int(min(max_blocks, max(1, -(-min_total_ms // max(first, 1e-3)))))
+        return sharding.max_over_ranks([first] + [timed(fn, steps) for _ in range(n - 1)], device=dev)
+
+    def batches(device, pin):
+        out = []
+        for sc in _make_sets(N_SETS, B, (W, H), device, pin=pin, rank=rank, world=world):
+            obj_centre = sc["verts1"][:, hv:].mean(1)
+            can = (sc["verts1"][:, hv:] - obj_centre[:, None]).contiguous()
+            can = can.pin_memory() if (pin and not can.is_cuda) else can
+            samples, _ = _samples_from_scene(sc)
+            for s_ in samples:
+                s_[BaseQueries.OBJCANVERTS] = can
+            out.append(({"data": samples, "supervision": ["consist"]}, sc))
+        return out
+
+    dbatches = batches(dev, False)
+    sc0 = dbatches[0][1]
+    torch.manual_seed(0)
+    model = bench_models.BenchMeshRegNet(trans_factor=tf, scale_factor=sf).to(dev)
+    model.train()
+    model.freeze_batchnorm()
+    K = sc0["K"]
+    f, cc = K[:, 0, 0], K[:, :2, 2]
+
+    def units(centre):  # scale / translation head outputs that put est_c3d at `centre` (inverse of project.py:15-20)
+        s_ = (centre[:, 2] - 0.4) / (f * sf)
+        t_ = (centre[:, :2] * (f / centre[:, 2])[:, None] - torch.tensor([W / 2.0, H / 2.0], device=dev) + cc) / tf
+        return torch.cat([s_[:, None], t_], 1)
+
+    obj_st = torch.cat([units(sc0["verts1"][:, hv:].mean(1)), torch.zeros(B, 3, device=dev)], 1)
+    model.set_head_bias(units(sc0["verts1"][:, :hv].mean(1)), obj_st)
+    net = WarpRegNet((W, H), model, mano_faces=sc0["faces"][0, :1538].cpu(), use_backward=True, lambda_data=1,
+                     lambda_consist=1, progressive_consist=True, progressive_steps=1000, detach_renders=True,
+                     graphed=True).to(dev)
+    # the synthetic hand is a closed 1552-face template whose own last 14 faces play the wrist cap (SURVEY 8d): use its
+    # table instead of MANO's wrist fan, which indexes the real MANO topology
+    net.mano_layer.register_buffer("th_faces", sc0["faces"][0, :1552].clone())
+    net.step_count = 500  # mid-schedule: both loss terms weighted (warpreg.py:102-110)
+    params = [p for p in net.parameters() if p.requires_grad]
+    n_param = sum(p.numel() for p in params)
+    ddp = DDP(net, device_ids=[local_rank], broadcast_buffers=False, gradient_as_bucket_view=True) if world > 1 else net
+    opt = torch.optim.Adam(params, lr=5e-5)
+    state = {"loss": None}
+
+    def train_step(batch, sync=True):
+        import contextlib
+        ctx = ddp.no_sync() if (world > 1 and not sync) else contextlib.nullcontext()
+        with ctx:
+            loss, agg, _, _ = ddp(batch)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+        opt.step()
+        state["loss"] = loss.detach()
+
+    launches0 = L.hoc_launch_count(-1)
+    train_step(dbatches[0][0])  # captures the consistency step
+    for i in range(max(args.warmup, 3)):
+        train_step(dbatches[i % N_SETS][0])
+    torch.cuda.synchronize()
+    l0 = L.hoc_launch_count(-1)
+    train_step(dbatches[0][0])
+    torch.cuda.synchronize()
+    launches_per_step = int(L.hoc_launch_count(-1) - l0)
+    graph_nodes = int(l0 - launches0)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    blocks = timed_blocks(lambda i: train_step(dbatches[i % N_SETS][0]), args.steps, 1000.0)
+    clocks = sampler.finish()
+    ms = median(blocks) / args.steps
+    nosync_ms = None
+    if world > 1:
+        nosync_ms = median(timed_blocks(lambda i: train_step(dbatches[i % N_SETS][0], sync=False), args.steps, 300.0)) / args.steps
+    # the library's share: the captured consistency step replayed alone
+    gstep = net._graph_step
+    lib_ms = median(timed_blocks(lambda i: gstep.replay(), args.steps, 200.0)) / args.steps
+    # forward + backward of the network alone (no consistency term): data supervision only
+    def net_only(i):
+        import contextlib
+        batch = dict(dbatches[i % N_SETS][0], supervision=["data"])
+        with (ddp.no_sync() if world > 1 else contextlib.nullcontext()):
+            loss, _, _, _ = ddp(batch)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+    net_ms = median(timed_blocks(net_only, args.steps, 300.0)) / args.steps
+
+    # end to end: the batch dicts live in pinned host memory (frames, masks, intrinsics, GT meshes of the reference frame)
+    hbatches = batches(None, True)
+    h2d = sum(v.numel() * v.element_size() for s_ in hbatches[0][0]["data"] for v in s_.values() if torch.is_tensor(v))
+    for i in range(3):
+        train_step(hbatches[i % N_SETS][0])
+
+    def e2e_step(i):
+        train_step(hbatches[i % N_SETS][0])
+        float(state["loss"])  # the training loop logs the loss every step (D2H + sync)
+
+    e2e_ms = median(timed_blocks(e2e_step, args.steps, 500.0)) / args.steps
+    loss_val = float(sharding.global_mean_loss(state["loss"]))
+    if rank != 0:
+        return None
+    frames = 2 * B * world
+    return {
+        "metric": METRIC, "value": frames / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"configs[3]: full trainmeshwarp optimisation step, {B} frame pairs/rank (global {B * world}), "
+                               f"{W}x{H}: ResNet-18 (random init, frozen BN) + MLP heads on both frames of every pair -> "
+                               f"ManoLayer + geometry head -> WarpRegNet consistency step (CUDA-graph replay of this "
+                               f"library, use_backward=True, detach_renders=True like the reference) -> backward -> "
+                               f"DDP all-reduce -> Adam",
+                   "pairs_per_rank": B, "global_batch": B * world, "image_size": [W, H], "parallelism": f"ddp{world}",
+                   "l2": f"{N_SETS} resident batches rotate"},
+        "timed_region": {"blocks": len(blocks), "steps_per_block": args.steps, "block_ms_median": median(blocks),
+                         "block_ms_min": min(blocks), "block_ms_max": max(blocks)},
+        "breakdown_ms": {"step": ms, "network_fwd_bwd_only": net_ms, "consistency_step_library_replay": lib_ms,
+                         "library_share_of_step": lib_ms / ms,
+                         "step_without_allreduce": nosync_ms,
+                         "allreduce_exposed": (ms - nosync_ms) if nosync_ms is not None else None},
+        "allreduce": {"params": n_param, "bytes": n_param * 4, "backend": "nccl" if world > 1 else None,
+                      "note": "one bucketed all-reduce of the network gradients per step (DistributedDataParallel), "
+                              "overlapped with the backward; nothing inside the render / warp kernels communicates"},
+        "e2e": {"value": frames / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms, "numa": numa,
+                "note": "the same step fed from pinned host batch dicts, loss read back every step"},
+        "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
+        "graph_kernel_nodes_at_capture": graph_nodes,
+        "loss_global_mean": loss_val, "clocks": clocks,
+        "execution": "eager torch network + one CUDA-graph replay of the consistency step (GraphedConsistStep.apply) per "
+                     "optimisation step",
+    }
 
 
 def _reference_pairs_per_second(pairs, steps, warmup, threads):
@@ -430,11 +706,11 @@ def _reference_pairs_per_second(pairs, steps, warmup, threads):
     onmr.set_threads(threads)
     times = []
     for i in range(warmup + steps):
-        sc = synth.make_scene(pairs, SIZE, SIZE, seed=i)
+        sc = synth.make_scene(pairs, WIDTH, HEIGHT, seed=i)
         t0 = time.perf_counter()
         v1 = sc["verts1"].clone().requires_grad_(True)
         loss, _ = opipe.consist_step(v1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
-                                     sc["jitter_mask_ref"], sc["jitter_mask"], SIZE, (SIZE, SIZE),
+                                     sc["jitter_mask_ref"], sc["jitter_mask"], max(WIDTH, HEIGHT), (WIDTH, HEIGHT),
                                      sc["hand_ignore_faces"], detach_renders=False, use_backward=True,
                                      grad_dtype=np.float32)
         loss.backward()
@@ -448,7 +724,7 @@ def cpu_baseline(sample_pairs=4, steps=4, warmup=1):
     threads = os.cpu_count() or 1
     total, n = _reference_pairs_per_second(sample_pairs, steps, warmup, threads)
     return {"value": 2 * sample_pairs * n / total, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} step(s) of {sample_pairs} frame pairs (of the {PAIRS}-pair workload) at {SIZE}x{SIZE}, "
+            "sample": f"{n} step(s) of {sample_pairs} frame pairs (of the {PAIRS}-pair workload) at {WIDTH}x{HEIGHT}, "
                       f"oracle/ C restatement (pthreads over pixels/faces) + torch CPU warp/loss"}
 
 
@@ -462,14 +738,14 @@ def gpu_ref_equiv(steps=3, warmup=1):
     from baseline import ref_equiv  # benchmark baseline; never on the product path
 
     dev = torch.device("cuda", torch.cuda.current_device())
-    sets = _make_sets(2, PAIRS, SIZE, dev)
+    sets = _make_sets(2, PAIRS, (WIDTH, HEIGHT), dev)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def one(i):
         sc = sets[i % 2]
         v1 = sc["verts1"].clone().requires_grad_(True)
         loss, _ = ref_equiv.consist_step(v1, sc["verts2"], sc["faces"], sc["K"], sc["image_ref"], sc["image"],
-                                         sc["jitter_mask_ref"], sc["jitter_mask"], SIZE, (SIZE, SIZE),
+                                         sc["jitter_mask_ref"], sc["jitter_mask"], max(WIDTH, HEIGHT), (WIDTH, HEIGHT),
                                          sc["hand_ignore_faces"], detach_renders=False, use_backward=True)
         loss.backward()
         return loss
@@ -732,9 +1008,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": warmup, "ms_per_step": total / n * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[2] on host cores: bounded sample of {pairs} frame pairs/step at {SIZE}x{SIZE} "
-                               f"(same scene generator, full backward, use_backward=True)",
-                   "pairs_per_step": pairs, "image_size": SIZE, "faces_per_mesh": 2 * 4552},
+        "config": {"workload": f"configs[{CONFIG}] on host cores: bounded sample of {pairs} frame pairs/step at "
+                               f"{WIDTH}x{HEIGHT} (same scene generator, full backward, use_backward=True)",
+                   "pairs_per_step": pairs, "image_size": SIZE if WIDTH == HEIGHT else [WIDTH, HEIGHT],
+                   "faces_per_mesh": 2 * 4552},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} timed step(s) of {pairs} frame pairs; the reference has no CPU renderer and "
                                    f"its CUDA extension is absent, so this is the oracle/ restatement"},
@@ -771,11 +1048,27 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-equiv", action="store_true", help="skip the GPU reference-equivalent baseline leg")
     ap.add_argument("--eager-only", action="store_true", help="profiling aid: run only the eager arm (ncu)")
-    ap.add_argument("--pairs", type=int, default=PAIRS, help="frame pairs per rank and step (default: configs[2])")
-    ap.add_argument("--size", type=int, default=SIZE, help="raster / image side (default: configs[2])")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.json workload: 2 (default, the metric's own: 16 pairs/rank at 256x256), 4 (configs[3]: "
+                         "full trainmeshwarp step under DDP, 8 pairs/rank), 5 (configs[4]: 32 pairs/rank at 480x270)")
+    ap.add_argument("--pairs", type=int, default=None, help="frame pairs per rank and step (default: the config's)")
+    ap.add_argument("--size", type=int, default=None, help="square frame / raster side (default: the config's)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
     args = ap.parse_args()
     _claim_stdout()
-    globals()["PAIRS"], globals()["SIZE"] = args.pairs, args.size
+    pairs, width, height = {2: (16, 256, 256), 4: (8, 256, 256), 5: (32, 480, 270)}[args.config]
+    if args.size is not None:
+        width = height = args.size
+    width = args.width if args.width is not None else width
+    height = args.height if args.height is not None else height
+    g = globals()
+    g["PAIRS"], g["WIDTH"], g["HEIGHT"], g["CONFIG"] = (args.pairs if args.pairs is not None else pairs), width, height, args.config
+    g["SIZE"] = max(width, height)
+    if args.config == 5:
+        g["METRIC"] = "render+warp+photometric fwd+bwd frames/sec @480x270 (480x480 raster)"
+    elif args.config == 4:
+        g["METRIC"] = "full trainmeshwarp step (ResNet-18 + MANO + render + warp) frames/sec @256x256"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -795,15 +1088,23 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     args.warmup = max(args.warmup, 3)
+    if args.config == 4:
+        out = run_config4(args, rank, world, local_rank)
+        if out is not None:
+            _emit(out)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     out = run_native(args, rank, world, local_rank)
+    legs = args.config == 2 and WIDTH == HEIGHT
     if out is not None:
-        if world == 1 and not args.no_ref_equiv:
+        if world == 1 and not args.no_ref_equiv and legs:
             try:
                 out["gpu_ref_equiv"] = gpu_ref_equiv()
                 out["gpu_ref_equiv"]["speedup_of_value"] = out["value"] / out["gpu_ref_equiv"]["value"]
             except Exception as exc:  # a baseline leg must never cost the bench line
                 out["gpu_ref_equiv"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
-        if world == 1:
+        if world == 1 and legs:
             try:
                 out["mano"] = mano_leg()
             except Exception as exc:

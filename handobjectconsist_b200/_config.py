@@ -23,3 +23,8 @@ def side_stream(device):
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
     return _SIDE_STREAMS[key]
+
+# The frame-pair path rasterises only the rows of the square raster that can matter for the (cropped) frame: the crop,
+# the reach of the occlusion check below it and -- when the geometry gradient is wanted -- the rows of the meshes
+# (hoc_pair_front computes the window on the device; include/hoc_b200.h).  False = the reference's full square.
+raster_window = True

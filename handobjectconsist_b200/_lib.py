@@ -45,6 +45,8 @@ SIGNATURES = {
     "hoc_raster_forward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_forward": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_raster_forward_ex": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _f, _f, ctypes.POINTER(ctypes.c_float), _vp, _i, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "hoc_raster_backward_workspace_bytes_ex": (_sz, [_i, _i, _i, _i, _i]),
     "hoc_mesh_scatter_workspace_bytes": (_sz, [_i, _i]),
@@ -58,15 +60,15 @@ SIGNATURES = {
     "hoc_raster_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
                                  _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i, _i,
-                                    _i, _i, _vp, _sz, _vp, _vp, _vp, _sz, _vp]),
+                                    _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_zero_bytes": (_sz, [_i, _i, _i]),
     "hoc_flow_finalize_warp": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 8),
     "hoc_pair_loss_mean": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "hoc_warp_photo_forward_pair": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp]),
-    "hoc_warp_photo_backward_pair": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "hoc_warp_photo_backward_pair": (_i, [_vp] * 10 + [_i] * 5 + [_vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "hoc_pair_front": (_i, [_vp] * 5 + [_i, _vp] + [_vp, _i] * 5 + [_f] + [_i] * 6
-                       + [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp]),
+                       + [_vp, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _i, _i, _i, _vp]),
     "hoc_pair_back": (_i, [_vp] * 4 + [_vp, _i] * 5 + [_f] + [_i] * 3 + [_vp, _vp] + [_i] * 4 + [_vp, _vp, _vp]),
     "hoc_warp_photo_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp]),

@@ -32,11 +32,15 @@ import ctypes
 import torch
 from torch.autograd import Function
 
-from . import _lib
+from . import _config, _lib
 from .warping.opticalflow import _fused_path_ok, _ignore_tensor
 from .warping.imgflowarp import _criterion_is_fused_l1
 
 _CAM_DEFAULTS = {}
+
+# benchmarking hook: a dict here receives the measured coverage of the last forward (a device -> host read: never set
+# inside a captured step)
+STATS = None
 
 
 def _default_cams(device):
@@ -112,18 +116,27 @@ class _PairConsistFunction(Function):
             ws_bytes = L.hoc_raster_forward_workspace_bytes(2 * B, Fr, S)
             ws = e(max(ws_bytes, 16), dtype=torch.uint8)
             sums = e(2, B, 2, dtype=torch.float64)  # 32 B bytes: a multiple of 16; zero-filled by the front kernel
+            # raster row window: only when the frame is lower than the square raster; the geometry gradient
+            # (if any input can ask for it) extends it to the rows of the meshes
+            want_geom = (not cfg["detach_renders"]) and any(ctx.needs_input_grad[:4])
+            row_lo = e(2 * B, dtype=torch.int32) if (_config.raster_window and H < S) else None
             _lib.check(L.hoc_pair_front(_lib.ptr(h1), _lib.ptr(o1), _lib.ptr(h2), _lib.ptr(o2), _lib.ptr(hf),
                                         int(hf.dim() == 3), _lib.ptr(of), *cam_args, float(r.orig_size), B, Vh, Vo, Fh,
                                         Fo, int(fill_back), _lib.ptr(faces), _lib.ptr(tex), _lib.ptr(table),
-                                        _lib.ptr(ws), ws_bytes, _lib.ptr(sums), sums.numel() * 8, st), "hoc_pair_front")
+                                        _lib.ptr(ws), ws_bytes, _lib.ptr(sums), sums.numel() * 8, _lib.ptr(row_lo), S, H,
+                                        int(want_geom), st), "hoc_pair_front")
             rgb, alpha, idx = e(2 * B, 3, S, S), e(2 * B, S, S), e(2 * B, S, S, dtype=torch.int32)
             # depth / weight_map only feed the backward, at covered pixels (HOC_LAYOUT_SPARSE_SAVED)
             depth, wmap = e(2 * B, S, S), e(2 * B, S, S, 3)
             layout = (_lib.HOC_LAYOUT_IMAGE | _lib.HOC_LAYOUT_KEYS_CLEARED | _lib.HOC_LAYOUT_TEX_VERTEX
                       | _lib.HOC_LAYOUT_SPARSE_SAVED)
-            _lib.check(L.hoc_raster_forward(_lib.ptr(faces), _lib.ptr(tex), 2 * B, Fr, S, 2, near, far, eps, bg, None,
-                                            layout, _lib.ptr(rgb), _lib.ptr(alpha), _lib.ptr(depth), _lib.ptr(idx),
-                                            _lib.ptr(wmap), None, _lib.ptr(ws), ws_bytes, st), "hoc_raster_forward")
+            _lib.check(L.hoc_raster_forward_ex(_lib.ptr(faces), _lib.ptr(tex), 2 * B, Fr, S, 2, near, far, eps, bg, None,
+                                               layout, _lib.ptr(row_lo), _lib.ptr(rgb), _lib.ptr(alpha), _lib.ptr(depth),
+                                               _lib.ptr(idx), _lib.ptr(wmap), None, _lib.ptr(ws), ws_bytes, st),
+                       "hoc_raster_forward")
+            if STATS is not None:  # (rows below the window are undefined: counted through the z-buffer keys instead)
+                keys = ws[: 2 * B * S * S * 8].view(torch.int64)
+                STATS["coverage"] = float((keys != -1).float().mean())
             flow12, flow21 = e(B, H, W, 2), e(B, H, W, 2)
             mult = e(2, B, H, W)
             valid = e(2, B, H, W, dtype=torch.bool)
@@ -150,6 +163,7 @@ class _PairConsistFunction(Function):
             loss, mean = e(B), e()
             _lib.check(L.hoc_pair_loss_mean(_lib.ptr(sums[0]), _lib.ptr(sums[1]) if cfg["use_backward"] else None, B,
                                             _lib.ptr(loss), _lib.ptr(mean), st), "hoc_pair_loss_mean")
+        ctx.row_lo = row_lo
         ctx.save_for_backward(h1, o1, h2, o2, faces, table, idx, rgb, wmap, depth, ir, im, flow12, flow21, valid, sums,
                               mult, *cams)
         ctx.cfg = dict(B=B, Vh=Vh, Vo=Vo, Fn=Fn, Fr=Fr, S=S, H=H, W=W, near=near, far=far, eps=eps, fill_back=fill_back,
@@ -175,6 +189,8 @@ class _PairConsistFunction(Function):
         V = Vh + Vo
         L = _lib.lib()
         dev = h1.device
+        row_lo = ctx.row_lo
+        rl = (lambda off: None) if row_lo is None else (lambda off: _lib.ptr(row_lo[off:]))
         gl = None if g_loss is None else g_loss.contiguous().float()
         gm = None if g_mean is None else g_mean.contiguous().float()
         use_backward = k["use_backward"]
@@ -203,7 +219,7 @@ class _PairConsistFunction(Function):
                 _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr_pair(valid[0], valid[1]),
                 _lib.ptr(sums), _lib.ptr(mult[0]), _lib.ptr(mult[1]), _lib.ptr(gl), _lib.ptr(gm), B, S, H, W,
                 int(use_backward), _lib.ptr(grad_rgb[:B]) if use_backward else None, _lib.ptr(grad_rgb[B:]), None, None,
-                _lib.ptr(ws), ws_zero, st), "hoc_warp_photo_backward_pair")
+                _lib.ptr(ws), ws_zero, rl(0), rl(B), st), "hoc_warp_photo_backward_pair")
             grad_faces = e(n, Fr, 3, 3) if geom > 0 else None
             grad_tex = e(n, Fr, 3, 3)
             # grad of the NDC vertices, grad of the vertex attributes: zero-filled by the rasterizer backward's
@@ -213,7 +229,7 @@ class _PairConsistFunction(Function):
                 _lib.ptr(faces[lo:]), None, _lib.ptr(idx[lo:]), _lib.ptr(rgb[lo:]), _lib.ptr(wmap[lo:]),
                 _lib.ptr(depth[lo:]), _lib.ptr(grad_rgb[lo:]), None, None, n, Fr, S, 2, k["near"], k["far"], k["eps"],
                 _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, geom, _lib.HOC_BWD_WORKSPACE_ZEROED, _lib.ptr(both),
-                both.numel() * 4, _lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st),
+                both.numel() * 4, rl(lo), _lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st),
                 "hoc_raster_backward_ex")
             g_ndc, g_attr = (both[0] if geom > 0 else None), both[1]
             sc_bytes = L.hoc_mesh_scatter_workspace_bytes(n, V)

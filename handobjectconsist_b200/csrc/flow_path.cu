@@ -734,7 +734,8 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
                       const long long *__restrict__ obj_faces, HocCam C, int B, int Vh, int Vo, int Fh, int Fo,
                       int fill_back, float *__restrict__ faces_out, float *__restrict__ tex_out,
                       long long *__restrict__ face_table, uint4 *__restrict__ clear, long n_clear,
-                      uint4 *__restrict__ zero, long n_zero)
+                      uint4 *__restrict__ zero, long n_zero, int *__restrict__ row_lo, int S, int crop_h,
+                      int geom_window)
 {
     {
         const long nthreads = (long)gridDim.x * gridDim.y * PF_THREADS;
@@ -744,6 +745,64 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
         for (long i = t0; i < n_zero; i += nthreads) /* small accumulators of later kernels (the loss sums) */
             zero[i] = make_uint4(0u, 0u, 0u, 0u);
     }
+    if (blockIdx.x == gridDim.x - 1 && row_lo != nullptr) {
+        /* The last CTA of every sample computes the pair's RASTER ROW WINDOW (the reference rasterises the
+         * square that contains the frame and crops afterwards; 44 % of the pixels of a 480 x 270 frame are thrown
+         * away).  Rows yi < row_lo (raster rows count from the bottom; the crop keeps the top crop_h rows) are skipped
+         * by every pixel pass.  The window is EXACT, not a heuristic: the only readers outside the crop are
+         *   (a) the forward-backward occlusion check, which looks one flow vector away and then another one
+         *       (imgflowarp.py:118-146).  A rendered flow value is a convex combination of the vertex displacements of
+         *       its face, so |flow_y| <= D = max_v |dy_v|; the nearest-sample position of warp() is
+         *       (y + f) S / (S - 1) - 0.5 rounded, at most |f| S / (S - 1) + 1 rows away: two hops reach
+         *       2 (D S / (S - 1) + 1) rows below the crop;
+         *   (b) the pseudo-gradient (only when the geometry gradient is wanted), which needs every covered pixel of the
+         *       mesh: the window then starts below the lowest vertex of both meshes. */
+        __shared__ float s_red[2][PF_THREADS / 32];
+        const int b = blockIdx.y, V = Vh + Vo;
+        const float *K1 = C.K1 + (long)b * C.K1_bs, *K2 = C.K2 + (long)b * C.K2_bs;
+        const float *R = C.R + (long)b * C.R_bs, *t = C.t + (long)b * C.t_bs, *d = C.dist + (long)b * C.dist_bs;
+        float dmax = 0.0f, ymin = 3.0e38f;
+        for (int i = threadIdx.x; i < V; i += PF_THREADS) {
+            const float *p1 = (i < Vh) ? hand1 + ((long)b * Vh + i) * 3 : obj1 + ((long)b * Vo + (i - Vh)) * 3;
+            const float *p2 = (i < Vh) ? hand2 + ((long)b * Vh + i) * 3 : obj2 + ((long)b * Vo + (i - Vh)) * 3;
+            const float v1[3] = {p1[0], p1[1], p1[2]}, v2[3] = {p2[0], p2[1], p2[2]};
+            float u1, w1, u2, w2, hz;
+            hoc_proj2d(K1, v1, &u1, &w1, &hz);
+            hoc_proj2d(K2, v2, &u2, &w2, &hz);
+            dmax = fmaxf(dmax, fabsf(w2 - w1)); /* (fmaxf / fminf drop NaNs) */
+            if (geom_window) {
+                HocProj P;
+                hoc_ndc_project(K1, R, t, d, C.orig_size, v1, &P);
+                ymin = fminf(ymin, 0.5f * (P.ndc[1] * (float)S + (float)S - 1.0f));
+                hoc_ndc_project(K2, R, t, d, C.orig_size, v2, &P);
+                ymin = fminf(ymin, 0.5f * (P.ndc[1] * (float)S + (float)S - 1.0f));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            dmax = fmaxf(dmax, __shfl_xor_sync(HOC_FULL_MASK, dmax, o));
+            ymin = fminf(ymin, __shfl_xor_sync(HOC_FULL_MASK, ymin, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_red[0][threadIdx.x >> 5] = dmax;
+            s_red[1][threadIdx.x >> 5] = ymin;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < PF_THREADS / 32; w++) {
+                dmax = fmaxf(dmax, s_red[0][w]);
+                ymin = fminf(ymin, s_red[1][w]);
+            }
+            const float hop = ceilf(dmax * (float)S / (float)max(S - 1, 1)) + 1.0f;
+            float lo = (float)(S - crop_h) - 2.0f * hop - 2.0f; /* (two rows of slack) */
+            if (geom_window)
+                lo = fminf(lo, floorf(ymin) - 2.0f);
+            const int r = (lo > 0.0f && lo == lo) ? min((int)lo, S - crop_h) : 0; /* huge / NaN displacement: no window */
+            row_lo[b] = max(r, 0);
+            row_lo[B + b] = max(r, 0);
+        }
+        return;
+    }
     /* staged records of this CTA's faces: [kind][thread][9], kind = faces1, tex1, faces2, tex2 */
     __shared__ float s_rec[4][PF_THREADS * 9];
     const int F = Fh + Fo, V = Vh + Vo;
@@ -751,6 +810,8 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
     const int f0 = blockIdx.x * PF_THREADS;
     const int f = f0 + threadIdx.x;
     const int b = blockIdx.y;
+    if (f0 >= F)
+        return; /* (the window CTA when no window is wanted) */
     if (f < F) {
         long long iv[3];
         if (f < Fh) {
@@ -1110,8 +1171,10 @@ extern "C" int hoc_pair_front(const float *hand1, const float *obj1, const float
                               int R_batched, const float *t, int t_batched, const float *dist_coeffs, int dist_batched,
                               float orig_size, int B, int Vh, int Vo, int Fh, int Fo, int fill_back, float *faces_out,
                               float *textures_out, long long *face_table, void *clear, size_t clear_bytes, void *zero,
-                              size_t zero_bytes, void *stream)
+                              size_t zero_bytes, int *row_lo, int S, int crop_h, int geom_window, void *stream)
 {
+    HOC_CHECK_ARG(row_lo == nullptr || (S >= 1 && crop_h >= 1 && crop_h <= S),
+                  "hoc_pair_front: row window needs 1 <= crop_h <= S (got %d, %d)", crop_h, S);
     HOC_CHECK_ARG(B >= 0 && Vh >= 0 && Vo >= 0 && Fh >= 0 && Fo >= 0 && B <= 32767, "hoc_pair_front: bad shape");
     HOC_CHECK_ARG(clear == nullptr || (clear_bytes % 16 == 0 && ((uintptr_t)clear & 15) == 0),
                   "hoc_pair_front: clear buffer must be 16-byte aligned with a size multiple of 16");
@@ -1135,13 +1198,14 @@ extern "C" int hoc_pair_front(const float *hand1, const float *obj1, const float
     HOC_CHECK_ARG(K1 && K2 && R && t && dist_coeffs && faces_out && textures_out, "hoc_pair_front: NULL argument");
     HocCam C = hoc_make_cam(K1, K1_batched, K2, K2_batched, R, R_batched, t, t_batched, dist_coeffs, dist_batched,
                             orig_size);
-    dim3 grid((Fh + Fo + PF_THREADS - 1) / PF_THREADS, B);
+    dim3 grid((Fh + Fo + PF_THREADS - 1) / PF_THREADS + 1, B); /* + the row-window CTA of every sample */
     HOC_LAUNCH(HOC_K_PAIR_FRONT, st,
                (hoc_pair_front_kernel<<<grid, PF_THREADS, 0, st>>>(hand1, obj1, hand2, obj2, hand_faces,
                                                                    hand_faces_batched, obj_faces, C, B, Vh, Vo, Fh, Fo,
                                                                    fill_back, faces_out, textures_out, face_table,
                                                                    (uint4 *)clear, (long)(clear_bytes / 16),
-                                                                   (uint4 *)zero, (long)(zero_bytes / 16))));
+                                                                   (uint4 *)zero, (long)(zero_bytes / 16), row_lo, S,
+                                                                   crop_h, geom_window)));
     HOC_CHECK_LAUNCH("hoc_pair_front_kernel");
     return HOC_OK;
 }

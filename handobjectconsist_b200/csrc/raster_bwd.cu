@@ -203,7 +203,8 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
                            const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S, int layout,
                            int k4_samples, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
                            int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
-                           float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c)
+                           float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
+                           const int *__restrict__ row_lo)
 {
     /* samples [0, k4_samples) get the pseudo-gradient (spans + every covered pixel listed); the others only list the
      * pixels that have a texture (non-zero dL/drgb) or depth gradient */
@@ -228,6 +229,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int b = blockIdx.z;
     const int xi = blockIdx.x * 32 + tx;
+    const int y_first = (row_lo != nullptr) ? row_lo[b] : 0; /* rows below the sample's window hold nothing (undefined maps) */
     int *e = ext + (long)b * 4 * S;
     int c_lo = 0x7f7f7f7f, c_hi = -1;
     float gr[4][3], ga[4];
@@ -235,7 +237,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
 #pragma unroll
     for (int r = 0; r < 4; r++) {
         const int yi = blockIdx.y * 32 + r * 8 + ty;
-        const bool in = xi < S && yi < S;
+        const bool in = xi < S && yi < S && yi >= y_first;
         gr[r][0] = gr[r][1] = gr[r][2] = 0.0f;
         ga[r] = 0.0f;
         fis[r] = -1;
@@ -776,8 +778,8 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
                                       const float *grad_rgb, const float *grad_alpha, const float *grad_depth, int B,
                                       int F, int S, int ts, float near_, float far_, float eps, int layout,
                                       int use_alpha, int tex_grad_mode, int geom_samples, int flags, void *extra_zero,
-                                      size_t extra_zero_bytes, float *grad_faces, float *grad_textures, void *workspace,
-                                      size_t workspace_bytes, void *stream);
+                                      size_t extra_zero_bytes, const int *row_lo, float *grad_faces,
+                                      float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
 
 extern "C" int hoc_raster_backward(const float *faces, const float *textures, const int32_t *face_index_map,
                                    const float *rgb, const float *weight_map, const float *depth,
@@ -788,7 +790,7 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
 {
     return hoc_raster_backward_ex(faces, textures, face_index_map, rgb, weight_map, depth, grad_rgb, grad_alpha,
                                   grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode, B, 0,
-                                  nullptr, 0, grad_faces, grad_textures, workspace, workspace_bytes, stream);
+                                  nullptr, 0, nullptr, grad_faces, grad_textures, workspace, workspace_bytes, stream);
 }
 
 /* geom_samples: the pseudo-gradient (backward_pixel_map) is computed for samples [0, geom_samples) only; the rows of
@@ -799,8 +801,8 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
                                       const float *grad_rgb, const float *grad_alpha, const float *grad_depth, int B,
                                       int F, int S, int ts, float near_, float far_, float eps, int layout,
                                       int use_alpha, int tex_grad_mode, int geom_samples, int flags, void *extra_zero,
-                                      size_t extra_zero_bytes, float *grad_faces, float *grad_textures, void *workspace,
-                                      size_t workspace_bytes, void *stream)
+                                      size_t extra_zero_bytes, const int *row_lo, float *grad_faces,
+                                      float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
 {
     (void)textures;
     HOC_CHECK_ARG(extra_zero == nullptr || (extra_zero_bytes % 4 == 0 && ((uintptr_t)extra_zero & 3) == 0),
@@ -864,7 +866,7 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
                    (hoc_raster_bwd_scan_kernel<<<pg, dim3(32, 8), 0, st>>>(
                        face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples,
                        want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
-                       (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)))));
+                       (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
     }
     {

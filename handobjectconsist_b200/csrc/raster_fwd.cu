@@ -64,7 +64,7 @@ __device__ __forceinline__ bool hoc_face_bbox(const float *f, int S, int *x0, in
  */
 __global__ void __launch_bounds__(ZB_THREADS)
 hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__restrict__ zbuf, int F, int S,
-                       float near_, float far_)
+                       float near_, float far_, const int *__restrict__ row_lo)
 {
     extern __shared__ float s_centre[]; /* [S] pixel-centre NDC coordinate of index i */
     __shared__ float s_rec[ZB_WARPS][ZB_FACES_PER_WARP][ZB_REC];
@@ -74,6 +74,7 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
+    const int y_first = (row_lo != nullptr) ? row_lo[b] : 0; /* raster rows below the sample's window are not drawn */
 
     for (int i = threadIdx.x; i < S; i += ZB_THREADS)
         s_centre[i] = hoc_pix_centre(i, S);
@@ -96,6 +97,10 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
             for (int k = 0; k < 9; k++)
                 f[k] = __ldg(src + k);
             keep = hoc_face_xy_finite(f) && !hoc_face_back(f) && hoc_face_bbox(f, S, &x0, &y0, &x1, &y1);
+            if (keep && y0 < y_first) {
+                y0 = y_first;
+                keep = y0 <= y1;
+            }
         }
         const unsigned m = __ballot_sync(HOC_FULL_MASK, keep);
         const int cnt = keep ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0;
@@ -362,7 +367,7 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
                            float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int tex_vertex,
                            int sparse_saved, float *__restrict__ rgb, float *__restrict__ alpha,
                            float *__restrict__ depth, int32_t *__restrict__ face_index_map,
-                           float *__restrict__ weight_map)
+                           float *__restrict__ weight_map, const int *__restrict__ row_lo)
 {
     __shared__ unsigned short s_list[RS_THREADS * 4];
     __shared__ int s_n;
@@ -383,7 +388,8 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
         col[1] = bg1;
         col[2] = bg2;
     }
-    if (q < S * S4) {
+    const int y_first = (row_lo != nullptr) ? row_lo[b] : 0; /* rows below the window: nothing is read or written */
+    if (q < S * S4 && q / S4 >= y_first) {
         const int yi = q / S4, x0 = (q - yi * S4) << 2;
         const long pix = (long)yi * S + x0;
         const uint4 k01 = *reinterpret_cast<const uint4 *>(zbuf + (long)b * npix + pix);
@@ -445,11 +451,32 @@ extern "C" size_t hoc_raster_forward_workspace_bytes(int B, int F, int S)
     return ((size_t)B * S * S * sizeof(unsigned long long) + 255) & ~(size_t)255;
 }
 
+extern "C" int hoc_raster_forward_ex(const float *faces, const float *textures, int B, int F, int S, int ts,
+                                     float near_, float far_, float eps, const float *background_host,
+                                     const float *background_dev, int layout, const int *row_lo, float *rgb,
+                                     float *alpha, float *depth, int32_t *face_index_map, float *weight_map,
+                                     float *face_inv_map, void *workspace, size_t workspace_bytes, void *stream);
+
 extern "C" int hoc_raster_forward(const float *faces, const float *textures, int B, int F, int S, int ts,
                                   float near_, float far_, float eps, const float *background_host,
                                   const float *background_dev, int layout, float *rgb, float *alpha, float *depth,
                                   int32_t *face_index_map, float *weight_map, float *face_inv_map, void *workspace,
                                   size_t workspace_bytes, void *stream)
+{
+    return hoc_raster_forward_ex(faces, textures, B, F, S, ts, near_, far_, eps, background_host, background_dev, layout,
+                                 nullptr, rgb, alpha, depth, face_index_map, weight_map, face_inv_map, workspace,
+                                 workspace_bytes, stream);
+}
+
+/* row_lo: device int [B] or NULL.  Raster rows yi < row_lo[b] of sample b (rows count from the bottom) are outside the
+ * sample's window: no face is drawn there and the output maps are NOT written there (their content is undefined).
+ * Honoured by the 4-pixel image-layout resolve pass (what the frame-pair path uses); with any other output
+ * configuration the rows are resolved as background. */
+extern "C" int hoc_raster_forward_ex(const float *faces, const float *textures, int B, int F, int S, int ts,
+                                     float near_, float far_, float eps, const float *background_host,
+                                     const float *background_dev, int layout, const int *row_lo, float *rgb,
+                                     float *alpha, float *depth, int32_t *face_index_map, float *weight_map,
+                                     float *face_inv_map, void *workspace, size_t workspace_bytes, void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && F >= 0, "hoc_raster_forward: negative batch (%d) or face count (%d)", B, F);
     HOC_CHECK_ARG(S >= 1 && S <= 2048, "hoc_raster_forward: image_size %d outside [1, 2048]", S);
@@ -482,7 +509,8 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
         const int per_cta = ZB_WARPS * ZB_FACES_PER_WARP;
         dim3 grid((F + per_cta - 1) / per_cta, B);
         HOC_LAUNCH(HOC_K_RASTER_ZBUF, st,
-                   (hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_)));
+                   (hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_,
+                                                                                        row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_zbuf_kernel");
     }
     float bg[3] = {0.f, 0.f, 0.f};
@@ -502,7 +530,7 @@ extern "C" int hoc_raster_forward(const float *faces, const float *textures, int
                    (hoc_raster_resolve4_kernel<<<grid4, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
                                                                            bg[0], bg[1], bg[2], background_dev, tex_vertex,
                                                                            sparse_saved, rgb, alpha, depth,
-                                                                           face_index_map, weight_map)));
+                                                                           face_index_map, weight_map, row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_resolve4_kernel");
         return HOC_OK;
     }

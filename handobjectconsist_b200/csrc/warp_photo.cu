@@ -398,7 +398,8 @@ struct HocPairBwdDir {
 __global__ void __launch_bounds__(WP_THREADS)
 hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const float *__restrict__ grad_loss,
                                     const float *__restrict__ grad_mean, int B, int S, int H, int W, float inv_w,
-                                    float inv_h, uint4 *__restrict__ zero, long n_zero)
+                                    float inv_h, uint4 *__restrict__ zero, long n_zero,
+                                    const int *__restrict__ row_lo1, const int *__restrict__ row_lo2)
 {
     if (n_zero > 0) { /* zero-fill for the kernels that follow (counters of the rasterizer backward), spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * WP_THREADS;
@@ -421,7 +422,11 @@ hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const fl
     if (threadIdx.x == 0)
         s_n = 0;
     __syncthreads();
-    if (q < S * S4) {
+    /* rows of the render below its raster window (raster rows count from the bottom, this layout from the top) are
+     * never read by the rasterizer backward: not written */
+    const int *row_lo = blockIdx.z ? row_lo1 : row_lo2; /* direction 0 -> render 2, direction 1 -> render 1 */
+    const int y_last = (row_lo != nullptr) ? S - 1 - row_lo[b] : S - 1;
+    if (q < S * S4 && q / S4 <= y_last) {
         const int y = q / S4, x0 = (q - y * S4) << 2;
         const bool inside = y < H && x0 < W; /* W % 4 == 0: a group is inside or outside as a whole */
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -870,7 +875,8 @@ extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float 
                                             const float *mult1, const float *mult2, const float *grad_loss,
                                             const float *grad_mean, int B, int S, int H, int W, int use_backward,
                                             float *grad_rgb1, float *grad_rgb2, float *grad_flow12, float *grad_flow21,
-                                            void *zero, size_t zero_bytes, void *stream)
+                                            void *zero, size_t zero_bytes, const int *row_lo1, const int *row_lo2,
+                                            void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && S >= 4 && (S % 4) == 0 && H >= 1 && H <= S && W >= 4 && W <= S && (W % 4) == 0,
                   "hoc_warp_photo_backward_pair: bad shape B=%d S=%d H=%d W=%d (S, W multiples of 4)", B, S, H, W);
@@ -900,7 +906,8 @@ extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float 
     HOC_LAUNCH(HOC_K_WARP_PHOTO_BWD, (cudaStream_t)stream,
                (hoc_warp_photo_pair_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
                    D[0], D[1], grad_loss, grad_mean, B, S, H, W, 1.0f / (float)(W - 1 > 1 ? W - 1 : 1),
-                   1.0f / (float)(H - 1 > 1 ? H - 1 : 1), (uint4 *)zero, zero ? (long)(zero_bytes / 16) : 0l)));
+                   1.0f / (float)(H - 1 > 1 ? H - 1 : 1), (uint4 *)zero, zero ? (long)(zero_bytes / 16) : 0l, row_lo1,
+                   row_lo2)));
     HOC_CHECK_LAUNCH("hoc_warp_photo_pair_backward_kernel");
     return HOC_OK;
 }

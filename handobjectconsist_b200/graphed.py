@@ -22,7 +22,7 @@ def _name(key):
 class GraphedConsistStep:
     def __init__(self, renderer, criterion, image_size, hand_face, samples, all_results, hand_ignore_faces=None,
                  gt_refs=True, first_only=True, use_backward=True, detach_renders=True, warmup=3,
-                 before_capture=None):
+                 before_capture=None, return_visuals=False):
         """``samples`` / ``all_results``: one example batch (reference layout, warpbranch.py:27-44) that fixes
         shapes and dtypes; their values are only used for the warm-up iterations."""
         if len(samples) != 2:
@@ -31,9 +31,10 @@ class GraphedConsistStep:
         dev = self.device
         self.renderer, self.criterion, self.image_size = renderer, criterion, image_size
         # the captured step returns the loss and its gradients only: the visualisation entries of pair_results
-        # (warps / diffs / warp_mask) would be dead stores inside the graph
+        # (warps / diffs / warp_mask) would be dead stores inside the graph (return_visuals=True keeps them, for
+        # benchmarking the difference)
         self.kw = dict(gt_refs=gt_refs, first_only=first_only, hand_ignore_faces=hand_ignore_faces,
-                       use_backward=use_backward, detach_renders=detach_renders, return_visuals=False)
+                       use_backward=use_backward, detach_renders=detach_renders, return_visuals=return_visuals)
         self.hand_face = hand_face.to(dev)
         self._u8_stage = {}
         self._one = torch.ones((), dtype=torch.float32, device=dev)  # d loss / d loss, created once (not per replay)

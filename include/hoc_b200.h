@@ -141,6 +141,13 @@ int hoc_raster_forward(const float *faces, const float *textures, int B, int F, 
                        int layout, float *rgb, float *alpha, float *depth, int32_t *face_index_map,
                        float *weight_map, float *face_inv_map, void *workspace, size_t workspace_bytes,
                        void *stream);
+/* The same with a raster row window (device int [B] or NULL, see hoc_pair_front): rows yi < row_lo[b] of sample b are
+ * not drawn and -- by the 4-pixel image-layout resolve pass the frame-pair path uses -- not written (undefined). */
+int hoc_raster_forward_ex(const float *faces, const float *textures, int B, int F, int S, int ts, float near_,
+                          float far_, float eps, const float *background_host, const float *background_dev,
+                          int layout, const int *row_lo, float *rgb, float *alpha, float *depth,
+                          int32_t *face_index_map, float *weight_map, float *face_inv_map, void *workspace,
+                          size_t workspace_bytes, void *stream);
 
 /* ---- rasterizer backward ------------------------------------------------------------------
  * Replaces backward_pixel_map + backward_textures + backward_depth_map
@@ -181,15 +188,17 @@ int hoc_raster_backward(const float *faces, const float *textures, const int32_t
  * path, which stacks the two renders of a pair ([2B]) and differentiates the geometry of the first one only.
  * flags: HOC_BWD_WORKSPACE_ZEROED = the first hoc_raster_backward_zero_bytes(B,F,S) bytes of the workspace are
  * already zero (an earlier kernel of the caller's sequence filled them: one memset node less in a captured step).
- * extra_zero: a float buffer the streaming pass also zero-fills (the outputs of the hoc_mesh_scatter that follows). */
+ * extra_zero: a float buffer the streaming pass also zero-fills (the outputs of the hoc_mesh_scatter that follows).
+ * row_lo: device int [B] or NULL -- the raster row window of hoc_pair_front (rows below it are not read). */
 #define HOC_BWD_WORKSPACE_ZEROED 1
 size_t hoc_raster_backward_zero_bytes(int B, int F, int S);
 int hoc_raster_backward_ex(const float *faces, const float *textures, const int32_t *face_index_map,
                            const float *rgb, const float *weight_map, const float *depth, const float *grad_rgb,
                            const float *grad_alpha, const float *grad_depth, int B, int F, int S, int ts,
                            float near_, float far_, float eps, int layout, int use_alpha, int tex_grad_mode,
-                           int geom_samples, int flags, void *extra_zero, size_t extra_zero_bytes, float *grad_faces,
-                           float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
+                           int geom_samples, int flags, void *extra_zero, size_t extra_zero_bytes, const int *row_lo,
+                           float *grad_faces, float *grad_textures, void *workspace, size_t workspace_bytes,
+                           void *stream);
 
 /* ---- flow-guided warp + masked photometric L1 ---------------------------------------------
  * ONE direction of pair_consist (imgflowarp.py:80-107) in one launch: warp(src, flow),
@@ -245,12 +254,14 @@ int hoc_warp_photo_forward_pair(const float *image_ref, const float *image, cons
  * itself.  Any output may be NULL.  use_backward = 0: direction 1 carries no loss (zeros).
  * grad_loss [B] and / or grad_mean [1]: d L / d loss[b] = grad_loss[b] + grad_mean / B (the adjoint of the batch mean
  * hoc_pair_loss_mean emits).  zero: an optional buffer the kernel also zero-fills (the counters of the
- * hoc_raster_backward_ex that follows, see HOC_BWD_WORKSPACE_ZEROED). */
+ * hoc_raster_backward_ex that follows, see HOC_BWD_WORKSPACE_ZEROED).  row_lo1 / row_lo2: raster row windows of the
+ * two renders (device int [B] each, or NULL): rows of grad_rgb below them are not written. */
 int hoc_warp_photo_backward_pair(const float *image_ref, const float *image, const float *flow12, const float *flow21,
                                  const uint8_t *const *valid_mask, const double *sums, const float *mult1,
                                  const float *mult2, const float *grad_loss, const float *grad_mean, int B, int S,
                                  int H, int W, int use_backward, float *grad_rgb1, float *grad_rgb2,
-                                 float *grad_flow12, float *grad_flow21, void *zero, size_t zero_bytes, void *stream);
+                                 float *grad_flow12, float *grad_flow21, void *zero, size_t zero_bytes,
+                                 const int *row_lo1, const int *row_lo2, void *stream);
 /* hoc_flow_finalize and the training half of hoc_warp_photo_forward_pair (visuals = 0) in ONE pass: the pixel that
  * has just produced its flow vector is the pixel whose warp that flow drives.  Same arguments as the two calls
  * (valid_mask / flow_mask / sums indexed by pair_consist's direction); `sums` must be zero on entry
@@ -335,13 +346,21 @@ int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_textures, con
  * mesh 2 with flow 2->1.  face_table [2B,Fh+Fo,3] (optional) receives the concatenated table the adjoint walks;
  * `clear` as in hoc_mesh_gather_clear (the z-buffer keys of the [2B] forward that follows); `zero` an optional buffer
  * filled with zeros (the loss sums of hoc_flow_finalize_warp).
+ * row_lo (device int [2B], optional): the RASTER ROW WINDOW of every pair (warpreg.py:29,40-45 renders
+ * the square that contains the frame, opticalflow.py:152-154 crops afterwards).  Raster rows yi < row_lo[b] (rows count
+ * from the bottom; the crop keeps the top crop_h rows of the S x S raster) are skipped by hoc_raster_forward_ex,
+ * hoc_warp_photo_backward_pair and hoc_raster_backward_ex when they are handed the same array.  The window is exact,
+ * computed on the device from the pair itself: it extends below the crop by what the forward-backward occlusion check
+ * can reach (two hops of the largest vertex displacement) and, with geom_window = 1 (the pseudo-gradient is wanted), down
+ * to the lowest vertex of both meshes.
  * Replaces warpbranch.py:50-52, opticalflow.py:98-103,121-123, renderer.py:250-252,282. */
 int hoc_pair_front(const float *hand1, const float *obj1, const float *hand2, const float *obj2,
                    const long long *hand_faces, int hand_faces_batched, const long long *obj_faces, const float *K1,
                    int K1_batched, const float *K2, int K2_batched, const float *R, int R_batched, const float *t,
                    int t_batched, const float *dist_coeffs, int dist_batched, float orig_size, int B, int Vh, int Vo,
                    int Fh, int Fo, int fill_back, float *faces_out, float *textures_out, long long *face_table,
-                   void *clear, size_t clear_bytes, void *zero, size_t zero_bytes, void *stream);
+                   void *clear, size_t clear_bytes, void *zero, size_t zero_bytes, int *row_lo, int S, int crop_h,
+                   int geom_window, void *stream);
 /* Its per-vertex adjoint: grad_ndc / grad_attrs [2B,Vh+Vo,3] (hoc_mesh_scatter's outputs for the stacked batch; the
  * has_* flags say which halves carry a gradient) -> grad_verts1 / grad_verts2 [B,Vh+Vo,3] (either may be NULL). */
 int hoc_pair_back(const float *hand1, const float *obj1, const float *hand2, const float *obj2, const float *K1,

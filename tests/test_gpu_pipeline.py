@@ -62,6 +62,8 @@ def test_consist_step_matches_oracle(S, crop, detach, use_bwd, seed):
     (96, (96, 52), True, True, False, 2),    # rectangular crop, no visualisation returns
     (128, (128, 128), False, True, False, 3),
     (64, (64, 64), False, False, True, 4),   # geometry gradient without the backward direction
+    (96, (96, 52), False, True, True, 5),    # raster row window + geometry gradient: the meshes reach below the crop
+    (128, (128, 72), False, True, False, 6),
 ])
 def test_pair_path_matches_oracle(S, crop, detach, use_bwd, visuals, seed):
     """The fused frame-pair path (consist.py: both renders stacked along the batch, one autograd node) against the
@@ -93,6 +95,36 @@ def test_pair_path_matches_oracle(S, crop, detach, use_bwd, visuals, seed):
     go = c1.grad.numpy()
     assert np.abs(go).max() > 0
     assert helpers.rel_err(v1.grad.cpu().numpy(), go) < 1e-3
+
+
+@pytest.mark.parametrize("detach", [False, True])
+def test_raster_row_window_is_exact(det_mode, detach):
+    """the frame-pair path rasterises only the rows that can matter for the cropped frame (the crop, the
+    reach of the occlusion check, and with the geometry gradient the rows of the meshes).  Same bits as the reference's
+    full square followed by the crop -- flows, masks, loss and (reproducible mode) gradients."""
+    from handobjectconsist_b200 import _config
+    S, B, crop = 160, 3, (160, 88)
+    dev = torch.device("cuda:0")
+    outs = []
+    for seed, K_square in ((21, True), (22, False)):  # meshes centred in the square (half below the crop) / in the frame
+        sc = synth.make_scene(B, crop[0], crop[1], seed=seed)
+        if K_square:
+            sc["K"] = synth.camera_intrinsics(B, S, S)
+        res = []
+        for window in (False, True):
+            _config.raster_window = window
+            try:
+                loss, r, v1 = helpers.pair_step(sc, S, crop, dev, detach, True, False)
+                loss.backward()
+            finally:
+                _config.raster_window = True
+            res.append((loss.detach(), r, v1.grad.clone()))
+        (l0, r0, g0), (l1, r1, g1) = res
+        assert l0.item() > 0 and torch.equal(l0, l1)
+        for i in range(2):
+            assert torch.equal(r0["flows"][i], r1["flows"][i])
+            assert torch.equal(r0["masks"][i]["full_mask"], r1["masks"][i]["full_mask"])
+        assert g0.abs().max().item() > 0 and torch.equal(g0, g1)
 
 
 def test_pair_path_equals_operator_path(det_mode):
