@@ -94,7 +94,7 @@ KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_b
               "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16, "mano_fwd": 17,
               "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22, "unpack_u8": 23,
               "hand_head_fwd": 24, "hand_head_bwd": 25, "recover_points_fwd": 26, "recover_points_bwd": 27,
-              "pair_front": 28, "pair_back": 29}
+              "pair_front": 28, "pair_back": 29, "augment_stats": 30, "augment_frames": 31}
 
 
 
@@ -110,6 +110,10 @@ SIGNATURES["hoc_mano_forward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp
 SIGNATURES["hoc_mano_backward_workspace_bytes"] = (_sz, [_i])
 SIGNATURES["hoc_mano_backward"] = (_i, [ctypes.POINTER(ManoModelStruct), _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp,
                                         _vp, _sz, _vp])
+
+SIGNATURES["hoc_augment_frame_pair_workspace_bytes"] = (_sz, [_i])
+SIGNATURES["hoc_augment_frame_pair"] = (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz,
+                                             _vp])
 
 _GH_CAM = [_vp, _i, _vp, _vp] + [_f] * 5  # camintr, camintr_batched, scale, trans, factors / off_z / input_res
 SIGNATURES["hoc_hand_head_forward"] = (_i, [_vp] * 3 + [_i] * 4 + _GH_CAM + [_vp] * 7 + [_vp])

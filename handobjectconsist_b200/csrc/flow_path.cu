@@ -372,8 +372,6 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
      * covered pixels one after the other would be the tail of the whole launch. */
     __shared__ unsigned short s_list[FP_THREADS * 4];
     __shared__ int s_n;
-    __shared__ float s_sum[FP_THREADS / 32];
-    __shared__ float s_cnt[FP_THREADS / 32];
     const int b = blockIdx.y;
     const bool second = blockIdx.z != 0;
     const HocRender &Ra = second ? R2 : R1;
@@ -408,7 +406,11 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
     const int n = s_n;
     if (n == 0)
         return;
-    float my_sum = 0.0f, my_cnt = 0.0f;
+    /* The listed pixels reach the threads in the order of the shared-memory atomics, which changes from run to run:
+     * a float sum per thread would make the loss depend on that order.  Every pixel's term is therefore rounded to a
+     * multiple of 2^-28 FIRST and the terms are added as integers (associative): same bits every run. */
+    unsigned long long my_fix = 0ull;
+    int my_cnt = 0;
     for (int i = threadIdx.x; i < n; i += FP_THREADS) {
         const int loc = s_list[i];
         const int qq = blockIdx.x * FP_THREADS + (loc >> 2);
@@ -437,28 +439,35 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
         float v[3], d[3], wm[3], sd;
         if (hoc_pair_pixel<false>(sb, jb, tv, jc, rx, ry, fx, fy, H, W, npix, inv_w, inv_h, thresh, v, d, wm, &sd)) {
             D.valid_mask[o] = 1;
-            my_sum += sd;
-            my_cnt += 3.0f;
+            my_fix += (unsigned long long)__double2ll_rn((double)sd * WP_SUM_SCALE); /* sd >= 0 */
+            my_cnt += 3;
         }
     }
     /* per-sample (sum, count) */
-    if (!__syncthreads_or(my_cnt > 0.0f))
+    if (!__syncthreads_or(my_cnt > 0))
         return;
-    my_sum = hoc_warp_sum(my_sum);
-    my_cnt = hoc_warp_sum(my_cnt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_fix += __shfl_xor_sync(HOC_FULL_MASK, my_fix, o);
+        my_cnt += __shfl_xor_sync(HOC_FULL_MASK, my_cnt, o);
+    }
+    __shared__ unsigned long long s_fix[FP_THREADS / 32];
+    __shared__ int s_cn[FP_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
-        s_sum[warp] = my_sum;
-        s_cnt[warp] = my_cnt;
+        s_fix[warp] = my_fix;
+        s_cn[warp] = my_cnt;
     }
     __syncthreads();
-    if (warp == 0) {
-        float a = (lane < FP_THREADS / 32) ? s_sum[lane] : 0.0f;
-        float nn = (lane < FP_THREADS / 32) ? s_cnt[lane] : 0.0f;
-        a = hoc_warp_sum(a);
-        nn = hoc_warp_sum(nn);
-        if (lane == 0 && nn > 0.0f) {
-            atomicAdd(&D.sums[2 * b + 0], rint((double)a * WP_SUM_SCALE));
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0ull;
+        int nn = 0;
+        for (int w = 0; w < FP_THREADS / 32; w++) {
+            a += s_fix[w];
+            nn += s_cn[w];
+        }
+        if (nn > 0) { /* integer-valued doubles: exact below 2^53, so the atomics commute */
+            atomicAdd(&D.sums[2 * b + 0], (double)a);
             atomicAdd(&D.sums[2 * b + 1], (double)nn);
         }
     }

@@ -114,6 +114,26 @@ class GraphedConsistStep:
                 for k, buf in dst.items():
                     buf.copy_(src[k].detach(), non_blocking=True)
 
+    def load_frames(self, frames, affinetrans, color=None, orders=None):
+        """The image side of a new batch straight from the DECODED frames: two uint8 tensors [B,Hs,Ws,3] (pinned host
+        memory: a quarter of the bytes of the float tensors) are colour-jittered, cropped / rotated to ``image_size``,
+        normalised and masked on the device (``inputpipe.augment_frame_pair``, two launches, bit-compatible with the
+        PIL calls of handobjset.py:336-379) directly into this step's static IMAGE / JITTERMASK buffers.  The other
+        sample entries (intrinsics, faces, reference meshes, predicted vertices) still go through ``load``."""
+        from . import inputpipe
+
+        def buf(sample, name):
+            for k, v in sample.items():
+                if _name(k) == name and torch.is_tensor(v) and v.dim() == 4:
+                    return v
+            raise KeyError(name)
+
+        images = [buf(s, "IMAGE") for s in self.samples]
+        masks = [buf(s, "JITTERMASK") for s in self.samples]
+        with torch.cuda.device(self.device):
+            inputpipe.augment_frame_pair(frames, affinetrans, self.image_size, color=color, orders=orders,
+                                         out=(images, masks))
+
     def replay(self):
         """Run the captured forward + backward; returns the static (loss, grad_hand, grad_obj) tensors."""
         self.graph.replay()

@@ -91,7 +91,9 @@ const char *hoc_last_error(void);
 #define HOC_K_RECOVER_POINTS_BWD 27
 #define HOC_K_PAIR_FRONT 28
 #define HOC_K_PAIR_BACK 29
-#define HOC_KERNEL_COUNT 30
+#define HOC_K_AUGMENT_STATS 30
+#define HOC_K_AUGMENT_FRAMES 31
+#define HOC_KERNEL_COUNT 32
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
@@ -491,6 +493,28 @@ int hoc_recover_points_backward(const float *points, const float *rotaxisang, in
                                 const float *g_recov_points, const float *g_points2d, const float *g_center3d,
                                 float *grad_points, float *grad_rot, float *grad_scale, float *grad_trans,
                                 void *stream);
+
+/* ---- frame-pair input pipeline ---------------------------------------------------------------
+ * The image side of HandObjSet.get_sample for the two frames of a pair
+ * (/root/reference/meshreg/datasets/handobjset.py:336-379: colortrans.apply_jitter, handutils.transform_img, to_tensor,
+ * normalize, the jitter mask), bit-compatible with the PIL / torchvision calls those helpers make (csrc/input_pipe.cu).
+ *   frame0 / frame1  [B,Hs,Ws,3] uint8, the decoded source frames (HWC, as PIL holds them)
+ *   coef_fix16       [B,6] int32: PIL's 16.16 fixed-point coefficients of the output -> input affine map (shared by the
+ *                    two frames of a sample: the same space augmentation, handobjset.py:417-421): with
+ *                    (a, b, c, d, e, f) = inv(affinetrans)[:2] they are floor(v * 65536 + 0.5) of
+ *                    a, b, c + a / 2 + b / 2, d, e, f + d / 2 + e / 2
+ *   color            [B,3] float: brightness, saturation, contrast factors;  hue_shift [B] int32: uint8(hue * 255)
+ *   order            [B,2,4] int32: per (sample, frame) the order of the adjustments (0 brightness, 1 saturation, 2 hue,
+ *                    3 contrast, -1 none); NULL = no colour jitter (evaluation mode)
+ *   image0 / image1  [B,3,H,W] float out: x / 255 - 0.5;  mask0 / mask1 [B,3,H,W] float out (or both NULL): 1 where the
+ *                    source pixel exists
+ *   workspace        hoc_augment_frame_pair_workspace_bytes(B) bytes (the grey sums of the contrast adjustment)
+ * Two launches (one without colour jitter). */
+size_t hoc_augment_frame_pair_workspace_bytes(int B);
+int hoc_augment_frame_pair(const uint8_t *frame0, const uint8_t *frame1, int B, int Hs, int Ws, const int *coef_fix16,
+                           const float *color, const int *hue_shift, const int *order, int H, int W, float *image0,
+                           float *image1, float *mask0, float *mask1, void *workspace, size_t workspace_bytes,
+                           void *stream);
 
 #ifdef __cplusplus
 }

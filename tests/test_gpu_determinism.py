@@ -52,6 +52,32 @@ def test_reproducible_mode_is_bit_exact_at_bench_size():
     assert worst <= 1e-3
 
 
+def test_pair_path_is_reproducible_at_bench_size():
+    """The fused frame-pair path (consist.py): its two-phase kernels deal the covered pixels to threads in the order of
+    shared-memory atomics, which changes from run to run -- the loss must not (its terms are added as integers), and
+    in the reproducible mode neither must the gradients.  Freed NaN-filled blocks poison the allocator's cache between
+    runs, so that nothing can lean on stale contents of `torch.empty` buffers (rows outside the raster window)."""
+    import helpers
+    S, B = 256, 16
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, 144, seed=0)   # 256 x 144 frames on a 256 x 256 raster: the row window is active
+    runs = []
+    with _lib.deterministic(True):
+        for i in range(4):
+            junk = torch.full((48, 1024, 1024), float("nan"), device=dev)
+            del junk
+            loss, res, v1 = helpers.pair_step(sc, S, (S, 144), dev, False, True, False)
+            loss.backward()
+            runs.append((loss.detach().clone(), res["loss"].detach().clone(), v1.grad.clone()))
+    for mean, per_sample, grad in runs[1:]:
+        assert torch.equal(mean, runs[0][0]) and torch.equal(per_sample, runs[0][1])
+        assert torch.equal(grad, runs[0][2])
+    assert runs[0][0].item() > 0 and torch.isfinite(runs[0][2]).all()
+    # production mode: the loss is still bit-identical
+    loss, res, _ = helpers.pair_step(sc, S, (S, 144), dev, False, True, False)
+    assert torch.equal(loss.detach(), runs[0][0])
+
+
 def test_reproducible_mode_needs_its_workspace():
     """In the reproducible mode the plain hoc_mesh_scatter (no workspace) refuses to run instead of silently falling
     back to float atomics, and the rasterizer backward asks for the larger workspace."""
