@@ -314,7 +314,7 @@ def run_native(args, rank, world, local_rank):
     copy_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream(dev)
 
-    def run_e2e(batches, min_total_ms):
+    def run_e2e(batches, min_total_ms, frames=None):
         ready = [torch.cuda.Event() for _ in range(RING)]
         done = [torch.cuda.Event() for _ in range(RING)]
         state = {"issued": 0, "loaded": 0, "losses": 0.0}
@@ -325,7 +325,12 @@ def run_native(args, rank, world, local_rank):
             slot = i % RING
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[slot])  # the slot's previous step has consumed its inputs
-                gsteps[slot].load(*batches[i % N_SETS])
+                if frames is None:
+                    gsteps[slot].load(*batches[i % N_SETS])
+                else:  # decoded uint8 frames: colour jitter + affine crop + normalise + jitter mask on the device
+                    fr = frames[i % N_SETS]
+                    gsteps[slot].load(*batches[i % N_SETS], skip_images=True)
+                    gsteps[slot].load_frames(fr["frames"], fr["affine"], color=fr["color"], orders=fr["orders"])
                 ready[slot].record(copy_stream)
 
         def e2e_step(_):
@@ -345,8 +350,12 @@ def run_native(args, rank, world, local_rank):
                 state["losses"] += float(loss_host[(i - 1) % RING])
             state["issued"] = i + 1
 
-        nbytes = sum(v.numel() * v.element_size() for s_ in batches[0][0] for v in s_.values() if torch.is_tensor(v))
+        is_img = lambda k: getattr(k, "name", k) in ("IMAGE", "JITTERMASK")
+        nbytes = sum(v.numel() * v.element_size() for s_ in batches[0][0] for k, v in s_.items()
+                     if torch.is_tensor(v) and not (frames is not None and is_img(k)))
         nbytes += sum(v.numel() * v.element_size() for r in batches[0][1] for v in r.values())
+        if frames is not None:
+            nbytes += sum(f.numel() for f in frames[0]["frames"]) + PAIRS * (6 * 4 + 3 * 4 + 4 + 8 * 4)
         for i in range(args.warmup):
             e2e_step(i)
         t = timed_blocks(e2e_step, args.steps, min_total_ms=min_total_ms, max_blocks=40)
@@ -377,7 +386,26 @@ def run_native(args, rank, world, local_rank):
     u8batches = [to_u8(bt) for bt in hbatches]
     e2e_u8_ms, h2d_u8 = run_e2e(u8batches, 300.0)
 
-    e2e_ms, eager_ms, e2e_u8_ms = sharding.max_over_ranks([e2e_ms, eager_ms, e2e_u8_ms], device=dev)
+    # and from the DECODED source frames: uint8 [B,270,480,3] frames of FPHAB's quarter size cross PCIe;
+    # colour jitter, the shared affine crop / rotation to the input resolution, normalisation and the jitter masks run on
+    # the device (inputpipe.augment_frame_pair, bit-compatible with the PIL calls of handobjset.py:336-379)
+    from handobjectconsist_b200 import inputpipe
+    import numpy as np
+    rng = np.random.default_rng(7)
+    Hs, Ws = 270, 480
+    raw = []
+    for k in range(N_SETS):
+        affine = np.stack([inputpipe.get_affine_transform((Ws / 2 + rng.uniform(-20, 20), Hs / 2 + rng.uniform(-10, 10)),
+                                                          rng.uniform(0.9, 1.2) * Hs, (W, H), rot=rng.uniform(-0.3, 0.3))[0]
+                           for _ in range(PAIRS)])
+        raw.append({"frames": [torch.randint(0, 256, (PAIRS, Hs, Ws, 3), dtype=torch.uint8).pin_memory() for _ in range(2)],
+                    "affine": affine,
+                    "color": dict(brightness=rng.uniform(0.5, 1.5, PAIRS), saturation=rng.uniform(0.5, 1.5, PAIRS),
+                                  hue=rng.uniform(-0.15, 0.15, PAIRS), contrast=rng.uniform(0.5, 1.5, PAIRS)),
+                    "orders": np.stack([[rng.permutation(4) for _ in range(2)] for _ in range(PAIRS)])})
+    e2e_raw_ms, h2d_raw = run_e2e(hbatches, 300.0, frames=raw)
+
+    e2e_ms, eager_ms, e2e_u8_ms, e2e_raw_ms = sharding.max_over_ranks([e2e_ms, eager_ms, e2e_u8_ms, e2e_raw_ms], device=dev)
     global_loss = float(sharding.global_mean_loss(gstep.loss))  # the one scalar exchange of the path
     if rank != 0:
         return None
@@ -490,6 +518,12 @@ def run_native(args, rank, world, local_rank):
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_u8_ms / args.steps,
                    "note": "same call with the frames and jitter masks as uint8 host tensors (widened + normalised on the "
                            "device, hoc_unpack_u8); `e2e` above is the reference's fp32 host format"},
+        "e2e_frames": {"value": frames / (e2e_raw_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_raw),
+                       "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_raw_ms / args.steps,
+                       "note": "the same call fed with DECODED uint8 source frames (480x270): colour jitter, the pair's shared "
+                               "affine crop / rotation, normalisation and the jitter masks run on the device "
+                               "(GraphedConsistStep.load_frames -> hoc_augment_frame_pair, SURVEY 8f row f3); includes the "
+                               "host-side inversion of the affine transforms"},
         "gpu_launches": launches,
         "launches_per_step": launches_per_step,
         "loss_global_mean": global_loss,

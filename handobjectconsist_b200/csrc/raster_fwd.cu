@@ -33,8 +33,11 @@
 #define ZB_FACES_PER_WARP 32 /* one face per lane before culling */
 #define ZB_REC 24            /* floats per surviving face: 9 coordinates, 9 inverse, x0, y0, width, 1/width, id */
 
-/* clipped pixel bounding box of a face: inside => pmin <= xi <= pmax in exact arithmetic; half a
- * pixel of slack absorbs fp32 rounding of the edge tests.  false when empty. */
+/* clipped pixel bounding box of a face: inside => pmin <= xi <= pmax in exact arithmetic; 1/16 pixel of slack absorbs
+ * the fp32 rounding of the NDC -> pixel map (~1e-4 px at S = 2048) and of the edge tests (a pixel centre further than
+ * ~1e-4 px outside the exact triangle cannot pass them).  Half a pixel of slack, as in round 1, made a sub-pixel face
+ * -- the common case for a 9k-triangle mesh at 256 x 256 -- test 4-9 pixels where 0-2 can be inside.  false when empty. */
+#define ZB_SLACK 0.0625f
 __device__ __forceinline__ bool hoc_face_bbox(const float *f, int S, int *x0, int *y0, int *x1, int *y1)
 {
     const float pxmin = hoc_ndc_to_pix(fminf(f[0], fminf(f[3], f[6])), S);
@@ -42,10 +45,10 @@ __device__ __forceinline__ bool hoc_face_bbox(const float *f, int S, int *x0, in
     const float pymin = hoc_ndc_to_pix(fminf(f[1], fminf(f[4], f[7])), S);
     const float pymax = hoc_ndc_to_pix(fmaxf(f[1], fmaxf(f[4], f[7])), S);
     const float fS1 = (float)(S - 1);
-    const float x_lo = fmaxf(ceilf(pxmin - 0.5f), 0.0f);
-    const float x_hi = fminf(floorf(pxmax + 0.5f), fS1);
-    const float y_lo = fmaxf(ceilf(pymin - 0.5f), 0.0f);
-    const float y_hi = fminf(floorf(pymax + 0.5f), fS1);
+    const float x_lo = fmaxf(ceilf(pxmin - ZB_SLACK), 0.0f);
+    const float x_hi = fminf(floorf(pxmax + ZB_SLACK), fS1);
+    const float y_lo = fmaxf(ceilf(pymin - ZB_SLACK), 0.0f);
+    const float y_hi = fminf(floorf(pymax + ZB_SLACK), fS1);
     if (!(x_lo <= x_hi && y_lo <= y_hi))
         return false;
     *x0 = (int)x_lo;

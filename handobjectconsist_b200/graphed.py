@@ -97,13 +97,16 @@ class GraphedConsistStep:
             _lib.check(_lib.lib().hoc_unpack_u8(_lib.ptr(stage), _lib.ptr(buf), buf.numel(), 255.0, sub,
                                                 _lib.stream_ptr()), "hoc_unpack_u8")
 
-    def load(self, samples, all_results):
+    def load(self, samples, all_results, skip_images=False):
         """Copy a new batch into the static buffers (stream-ordered; pinned host tensors copy asynchronously).
-        IMAGE / JITTERMASK may be given as uint8 tensors (0..255): see ``_load_u8``."""
+        IMAGE / JITTERMASK may be given as uint8 tensors (0..255): see ``_load_u8``; ``skip_images=True`` leaves them
+        alone (they come from ``load_frames``)."""
         with torch.no_grad():
             for dst, src in zip(self.samples, samples):
                 by_name = {(_name(k), type(k).__name__): v for k, v in src.items()}
                 for k, buf in dst.items():
+                    if skip_images and _name(k) in ("IMAGE", "JITTERMASK"):
+                        continue
                     if torch.is_tensor(buf):
                         val = by_name[(_name(k), type(k).__name__)]
                         if val.dtype == torch.uint8 and buf.dtype == torch.float32 and _name(k) in ("IMAGE", "JITTERMASK"):

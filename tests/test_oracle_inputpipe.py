@@ -79,3 +79,18 @@ def test_whole_frame_matches_the_reference_sequence():
     crop = Image.fromarray(a).transform(res, Image.AFFINE, oip.transform_coefficients(affine))
     assert torch.equal(torch.from_numpy(img), F.normalize(F.to_tensor(crop).float(), [0.5] * 3, [1] * 3))
     assert 0.2 < mask.mean() < 1.0
+
+
+def test_batched_coefficients_equal_the_per_sample_computation():
+    """inputpipe.affine_fixed_coefficients inverts the whole batch at once; the reference inverts one matrix at a time
+    (handutils.transform_img): same integers."""
+    from handobjectconsist_b200 import inputpipe
+    rng = np.random.default_rng(4)
+    aff = np.stack([oip.get_affine_transform((rng.uniform(100, 300), rng.uniform(50, 200)), rng.uniform(100, 400),
+                                             (256, 256), rot=rng.uniform(-3, 3))[0] for _ in range(64)])
+    got = inputpipe.affine_fixed_coefficients(aff).numpy()
+    ref = np.array([oip.affine_fixed_coeffs(oip.transform_coefficients(a)) for a in aff])
+    np.testing.assert_array_equal(got, ref)
+    a1, a2 = inputpipe.get_affine_transform((120.0, 80.0), 200.0, (256, 192), 0.3), oip.get_affine_transform((120.0, 80.0), 200.0, (256, 192), 0.3)
+    np.testing.assert_array_equal(a1[0], a2[0])
+    np.testing.assert_array_equal(a1[1], a2[1])
