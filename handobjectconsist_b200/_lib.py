@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhoc_b200.so")
+# HOC_B200_LIB: another build of the same library (A/B sweeps of compile-time knobs); default: the in-tree build
+LIB_PATH = os.environ.get("HOC_B200_LIB") or os.path.join(_HERE, "libhoc_b200.so")
 
 HOC_LAYOUT_RAW = 0
 HOC_LAYOUT_IMAGE = 1

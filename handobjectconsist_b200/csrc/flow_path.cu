@@ -360,7 +360,10 @@ struct HocFinWarpDir {
     double *sums;
 };
 
-__global__ void __launch_bounds__(FP_THREADS)
+#ifndef FW_THREADS
+#define FW_THREADS 128 /* (128 vs 256 vs 64: 20.6 / 21.3 / 24.6 us at 16 pairs of 256 x 256) */
+#endif
+__global__ void __launch_bounds__(FW_THREADS)
 hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocFinWarpDir D1, int S, int H, int W,
                               const int *__restrict__ ignore, int n_ignore, float distance_thresh, float inv_w,
                               float inv_h, float thresh)
@@ -370,7 +373,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
      * B: the listed pixels (a few per cent, clustered in a few CTAs) are dealt ONE PER THREAD: each carries a chain of
      * dependent gathers (ignore table, two occlusion look-ups, 24 bilinear taps), and a thread that ran its own four
      * covered pixels one after the other would be the tail of the whole launch. */
-    __shared__ unsigned short s_list[FP_THREADS * 4];
+    __shared__ unsigned short s_list[FW_THREADS * 4];
     __shared__ int s_n;
     const int b = blockIdx.y;
     const bool second = blockIdx.z != 0;
@@ -378,7 +381,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
     const HocRender &Rb = second ? R1 : R2;
     const HocFinWarpDir &D = second ? D1 : D0;
     const int W4 = W >> 2, npix = H * W;
-    const int q = blockIdx.x * FP_THREADS + threadIdx.x;
+    const int q = blockIdx.x * FW_THREADS + threadIdx.x;
     if (threadIdx.x == 0)
         s_n = 0;
     __syncthreads();
@@ -411,9 +414,9 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
      * multiple of 2^-28 FIRST and the terms are added as integers (associative): same bits every run. */
     unsigned long long my_fix = 0ull;
     int my_cnt = 0;
-    for (int i = threadIdx.x; i < n; i += FP_THREADS) {
+    for (int i = threadIdx.x; i < n; i += FW_THREADS) {
         const int loc = s_list[i];
-        const int qq = blockIdx.x * FP_THREADS + (loc >> 2);
+        const int qq = blockIdx.x * FW_THREADS + (loc >> 2);
         const int ry = qq / W4, rx = ((qq - ry * W4) << 2) + (loc & 3);
         const long po = ((long)b * S + ry) * S + rx, co = (((long)b * 3) * S + ry) * S + rx;
         float fx, fy, mu;
@@ -451,8 +454,8 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
         my_fix += __shfl_xor_sync(HOC_FULL_MASK, my_fix, o);
         my_cnt += __shfl_xor_sync(HOC_FULL_MASK, my_cnt, o);
     }
-    __shared__ unsigned long long s_fix[FP_THREADS / 32];
-    __shared__ int s_cn[FP_THREADS / 32];
+    __shared__ unsigned long long s_fix[FW_THREADS / 32];
+    __shared__ int s_cn[FW_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (lane == 0) {
         s_fix[warp] = my_fix;
@@ -462,7 +465,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
     if (threadIdx.x == 0) {
         unsigned long long a = 0ull;
         int nn = 0;
-        for (int w = 0; w < FP_THREADS / 32; w++) {
+        for (int w = 0; w < FW_THREADS / 32; w++) {
             a += s_fix[w];
             nn += s_cn[w];
         }
@@ -1273,9 +1276,9 @@ extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, co
                       (flow_mask == nullptr || (((uintptr_t)flow_mask[0] | (uintptr_t)flow_mask[1]) & 7) == 0),
                   "hoc_flow_finalize_warp: tensors must be 16-byte aligned");
     const long groups = (long)H * (W / 4);
-    dim3 grid((unsigned)((groups + FP_THREADS - 1) / FP_THREADS), B, 2);
+    dim3 grid((unsigned)((groups + FW_THREADS - 1) / FW_THREADS), B, 2);
     HOC_LAUNCH(HOC_K_FLOW_FINALIZE, (cudaStream_t)stream,
-               (hoc_flow_finalize_warp_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+               (hoc_flow_finalize_warp_kernel<<<grid, FW_THREADS, 0, (cudaStream_t)stream>>>(
                    R1, R2, D0, D1, S, H, W, ignore_faces, n_ignore, distance_thresh,
                    1.0f / (float)(W - 1 > 1 ? W - 1 : 1), 1.0f / (float)(H - 1 > 1 ? H - 1 : 1), thresh)));
     HOC_CHECK_LAUNCH("hoc_flow_finalize_warp_kernel");

@@ -364,7 +364,10 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
  * texture sample of the winning face are a chain of dependent loads and IEEE divisions, and a thread that ran its own
  * four covered pixels one after the other would be the tail of the launch (measured in round 1: 19.6 us against 15.8).
  */
-__global__ void __launch_bounds__(RS_THREADS)
+#ifndef RS4_THREADS
+#define RS4_THREADS 128 /* (128 vs 256: 14.6 / 15.7 us) */
+#endif
+__global__ void __launch_bounds__(RS4_THREADS)
 hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
                            const unsigned long long *__restrict__ zbuf, int F, int S, int ts, float near_, float far_,
                            float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int tex_vertex,
@@ -372,12 +375,12 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
                            float *__restrict__ depth, int32_t *__restrict__ face_index_map,
                            float *__restrict__ weight_map, const int *__restrict__ row_lo)
 {
-    __shared__ unsigned short s_list[RS_THREADS * 4];
+    __shared__ unsigned short s_list[RS4_THREADS * 4];
     __shared__ int s_n;
     const int b = blockIdx.y;
     const int S4 = S >> 2;
     const long npix = (long)S * S;
-    const int q = blockIdx.x * RS_THREADS + threadIdx.x;
+    const int q = blockIdx.x * RS4_THREADS + threadIdx.x;
     if (threadIdx.x == 0)
         s_n = 0;
     __syncthreads();
@@ -418,9 +421,9 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
     }
     __syncthreads(); /* orders phase A's background stores before phase B's stores to the same addresses */
     const int n = s_n;
-    for (int i = threadIdx.x; i < n; i += RS_THREADS) {
+    for (int i = threadIdx.x; i < n; i += RS4_THREADS) {
         const int loc = s_list[i];
-        const int qq = blockIdx.x * RS_THREADS + (loc >> 2);
+        const int qq = blockIdx.x * RS4_THREADS + (loc >> 2);
         const int yi = qq / S4, xi = ((qq - yi * S4) << 2) + (loc & 3);
         const long pix = (long)yi * S + xi;
         const int fidx = (int)(unsigned)(zbuf[(long)b * npix + pix] & 0xffffffffull);
@@ -528,9 +531,9 @@ extern "C" int hoc_raster_forward_ex(const float *faces, const float *textures, 
     if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && face_inv_map == nullptr && (weight_map == nullptr || sparse_saved) &&
         ((((uintptr_t)zbuf | (uintptr_t)rgb | (uintptr_t)alpha | (uintptr_t)depth | (uintptr_t)face_index_map) & 15) == 0)) {
         const long groups = npix / 4;
-        dim3 grid4((unsigned)((groups + RS_THREADS - 1) / RS_THREADS), B);
+        dim3 grid4((unsigned)((groups + RS4_THREADS - 1) / RS4_THREADS), B);
         HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
-                   (hoc_raster_resolve4_kernel<<<grid4, RS_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
+                   (hoc_raster_resolve4_kernel<<<grid4, RS4_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
                                                                            bg[0], bg[1], bg[2], background_dev, tex_vertex,
                                                                            sparse_saved, rgb, alpha, depth,
                                                                            face_index_map, weight_map, row_lo)));

@@ -395,15 +395,18 @@ struct HocPairBwdDir {
     int active;       /* 0: this direction carries no loss (use_backward = False): zeros */
 };
 
-__global__ void __launch_bounds__(WP_THREADS)
+#ifndef WPB_THREADS
+#define WPB_THREADS 128 /* (128 vs 256: 11.2 / 11.9 us) */
+#endif
+__global__ void __launch_bounds__(WPB_THREADS)
 hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const float *__restrict__ grad_loss,
                                     const float *__restrict__ grad_mean, int B, int S, int H, int W, float inv_w,
                                     float inv_h, uint4 *__restrict__ zero, long n_zero,
                                     const int *__restrict__ row_lo1, const int *__restrict__ row_lo2)
 {
     if (n_zero > 0) { /* zero-fill for the kernels that follow (counters of the rasterizer backward), spread over the grid */
-        const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * WP_THREADS;
-        for (long i = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WP_THREADS + threadIdx.x;
+        const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * WPB_THREADS;
+        for (long i = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WPB_THREADS + threadIdx.x;
              i < n_zero; i += nthreads)
             zero[i] = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -413,11 +416,11 @@ hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const fl
     /* Two phases per CTA (1024 raster pixels).  A: 16-byte zero stores of the gradient planes, the valid pixels noted
      * in a shared list.  B: the listed pixels (a few per cent) one per thread: 12 taps + the gradient of the bilinear
      * weights, scalar stores over the zeros. */
-    __shared__ unsigned short s_list[WP_THREADS * 4];
+    __shared__ unsigned short s_list[WPB_THREADS * 4];
     __shared__ int s_n;
     const int b = blockIdx.y;
     const int S4 = S >> 2;
-    const int q = blockIdx.x * WP_THREADS + threadIdx.x;
+    const int q = blockIdx.x * WPB_THREADS + threadIdx.x;
     const long npix = (long)H * W;
     if (threadIdx.x == 0)
         s_n = 0;
@@ -461,9 +464,9 @@ hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const fl
     const float gl = ((grad_loss != nullptr) ? grad_loss[b] : 0.0f) +
                      ((grad_mean != nullptr) ? __fdiv_rn(grad_mean[0], (float)B) : 0.0f);
     const float scale = gl / fmaxf(cnt, 1.0f);
-    for (int i = threadIdx.x; i < n; i += WP_THREADS) {
+    for (int i = threadIdx.x; i < n; i += WPB_THREADS) {
         const int loc = s_list[i];
-        const int qq = blockIdx.x * WP_THREADS + (loc >> 2);
+        const int qq = blockIdx.x * WPB_THREADS + (loc >> 2);
         const int y = qq / S4, x = ((qq - y * S4) << 2) + (loc & 3);
         const long pix = (long)y * W + x;
         const float2 fl = *reinterpret_cast<const float2 *>(D.flow + ((long)b * npix + pix) * 2);
@@ -902,9 +905,9 @@ extern "C" int hoc_warp_photo_backward_pair(const float *image_ref, const float 
                           hoc_aligned16(D[k].grad_flow) && (((uintptr_t)D[k].valid_mask) & 3) == 0,
                       "hoc_warp_photo_backward_pair: tensors must be 16-byte aligned");
     const long groups = (long)S * (S / 4);
-    dim3 grid((unsigned)((groups + WP_THREADS - 1) / WP_THREADS), B, 2);
+    dim3 grid((unsigned)((groups + WPB_THREADS - 1) / WPB_THREADS), B, 2);
     HOC_LAUNCH(HOC_K_WARP_PHOTO_BWD, (cudaStream_t)stream,
-               (hoc_warp_photo_pair_backward_kernel<<<grid, WP_THREADS, 0, (cudaStream_t)stream>>>(
+               (hoc_warp_photo_pair_backward_kernel<<<grid, WPB_THREADS, 0, (cudaStream_t)stream>>>(
                    D[0], D[1], grad_loss, grad_mean, B, S, H, W, 1.0f / (float)(W - 1 > 1 ? W - 1 : 1),
                    1.0f / (float)(H - 1 > 1 ? H - 1 : 1), (uint4 *)zero, zero ? (long)(zero_bytes / 16) : 0l, row_lo1,
                    row_lo2)));

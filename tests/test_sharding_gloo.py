@@ -64,3 +64,72 @@ def test_shard_range_rejects_ragged_batches():
     with pytest.raises(ValueError):
         sharding.shard_range(10, 0, 4)
     assert sharding.max_over_ranks([1.5]) == [1.5]  # no process group: identity
+
+
+class _TinyNet(torch.nn.Module):
+    """Stands in for MeshRegNet under DDP: a per-sample regression loss and 'vertices' that depend on the weights."""
+
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(3, 3)
+
+    def forward(self, sample):
+        x = sample["x"]
+        verts = self.lin(x)
+        reg = (verts ** 2).mean()
+        return reg.reshape(1), {"recov_handverts3d": verts}, {"mano_reg_loss": 0.1 * reg}
+
+
+def _ddp_worker(rank, world, port, out):
+    """WarpRegNet (warpreg.py:81-127) wrapped in DistributedDataParallel over gloo, the consistency term replaced by a
+    per-sample function of the predicted vertices (no kernels on a CPU box): every rank sees its shard of the global
+    batch, the all-reduced gradients equal the gradients of the global-batch loss, step_count advances in lock step."""
+    from torch.nn.parallel import DistributedDataParallel as DDP
+
+    from handobjectconsist_b200 import synth, warpreg
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        hv, hf = synth.hand_template()
+
+        def make():
+            net = warpreg.WarpRegNet((32, 32), _TinyNet(), mano_faces=torch.from_numpy(hf[:1538]), lambda_data=1,
+                                     lambda_consist=0.5, progressive_steps=2)
+            net.warp_forward = lambda samples, results: ((results[0]["recov_handverts3d"] - samples[1]["x"]).abs().mean(), None)
+            return net
+
+        g = torch.Generator().manual_seed(1)
+        x0, x1 = torch.rand(8, 5, 3, generator=g), torch.rand(8, 5, 3, generator=g)
+        lo, hi = sharding.shard_range(8, rank, world)
+        net = make()
+        ddp = DDP(net, broadcast_buffers=False)
+        single = make()
+        single.load_state_dict(net.state_dict())
+        for step in range(3):
+            batch = {"data": [{"x": x0[lo:hi]}, {"x": x1[lo:hi]}], "supervision": ["consist"]}
+            loss, agg, _, _ = ddp(batch)
+            ddp.zero_grad()
+            loss.backward()
+            # the same step on the global batch, one process
+            loss_s, _, _, _ = single({"data": [{"x": x0}, {"x": x1}], "supervision": ["consist"]})
+            single.zero_grad()
+            loss_s.backward()
+            for (n, p), (_, q) in zip(net.named_parameters(), single.named_parameters()):
+                assert torch.allclose(p.grad, q.grad, atol=1e-6), n
+            assert net.step_count == single.step_count == step + 1
+            assert abs(float(sharding.global_mean_loss(loss)) - float(loss_s)) < 1e-6
+        out[rank] = net.step_count
+    finally:
+        dist.destroy_process_group()
+
+
+def test_warpregnet_under_ddp_over_gloo():
+    world = 2
+    port = 29300 + os.getpid() % 250
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_ddp_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: 3, 1: 3}
