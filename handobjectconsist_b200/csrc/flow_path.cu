@@ -368,7 +368,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
                               const int *__restrict__ ignore, int n_ignore, float distance_thresh, float inv_w,
                               float inv_h, float thresh)
 {
-    /* Two phases per CTA (1024 pixels).  A: every thread streams its four pixels -- 16-byte loads of alpha and the two
+    /* Two phases per CTA (4 pixels per thread).  A: every thread streams its four pixels -- 16-byte loads of alpha and the two
      * colour planes, 16-byte stores of the (zero) outputs -- and notes the pixels a mesh covers in a shared list.
      * B: the listed pixels (a few per cent, clustered in a few CTAs) are dealt ONE PER THREAD: each carries a chain of
      * dependent gathers (ignore table, two occlusion look-ups, 24 bilinear taps), and a thread that ran its own four

@@ -357,7 +357,7 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
 
 /*
  * Resolve pass, image layout, four pixels per thread (S % 4 == 0, no face_inv_map, weight_map sparse or absent): what the
- * flow path and rasterize_rgbad's default outputs need.  Two phases per CTA (1024 pixels of one sample).  A: every thread
+ * flow path and rasterize_rgbad's default outputs need.  Two phases per CTA (4 pixels per thread, one sample).  A: every thread
  * streams its four pixels -- two 16-byte loads of the keys, 16-byte stores of face_index_map, alpha, the background
  * colour and (dense mode) the background depth -- and notes the covered ones in a shared list.  B: the covered pixels
  * (a few per cent of a frame, clustered in a few CTAs) are dealt one per thread: barycentric matrix, weights, depth and

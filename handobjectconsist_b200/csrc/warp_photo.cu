@@ -413,7 +413,7 @@ hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const fl
     const HocPairBwdDir &D = blockIdx.z ? D1 : D0;
     if (D.grad_rgb == nullptr && D.grad_flow == nullptr)
         return;
-    /* Two phases per CTA (1024 raster pixels).  A: 16-byte zero stores of the gradient planes, the valid pixels noted
+    /* Two phases per CTA (4 raster pixels per thread).  A: 16-byte zero stores of the gradient planes, the valid pixels noted
      * in a shared list.  B: the listed pixels (a few per cent) one per thread: 12 taps + the gradient of the bilinear
      * weights, scalar stores over the zeros. */
     __shared__ unsigned short s_list[WPB_THREADS * 4];

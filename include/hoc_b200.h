@@ -108,6 +108,7 @@ const char *hoc_last_error(void);
 #define HOC_TUNE_LINE_THREADS 1
 #define HOC_TUNE_LINE_SEGMENT 2
 #define HOC_TUNE_DETERMINISTIC 3
+#define HOC_TUNE_LINE_CTAS 4 /* line pass: 0 (default) one CTA per line, centre-out; n > 0: n CTAs walk the list of non-empty lines */
 int hoc_set_tuning(int key, int value);
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
