@@ -95,7 +95,8 @@ KERNEL_IDS = {"raster_zbuf": 0, "raster_resolve": 1, "grad_extent": 2, "raster_b
               "flow_finalize": 11, "flow_finalize_bwd": 12, "raster_bwd_pixel": 13, "raster_bwd_line": 14, "flow_vertices": 15, "flow_vertices_bwd": 16, "mano_fwd": 17,
               "mano_bwd": 18, "raster_bwd_pixel_k4": 19, "raster_bwd_cover": 20, "cat_meshes": 21, "pair_loss": 22, "unpack_u8": 23,
               "hand_head_fwd": 24, "hand_head_bwd": 25, "recover_points_fwd": 26, "recover_points_bwd": 27,
-              "pair_front": 28, "pair_back": 29, "augment_stats": 30, "augment_frames": 31}
+              "pair_front": 28, "pair_back": 29, "augment_stats": 30, "augment_frames": 31,
+              "raster_bwd_group": 32}
 
 
 

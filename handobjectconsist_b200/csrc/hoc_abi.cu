@@ -51,7 +51,8 @@ extern "C" const char *hoc_last_error(void) { return g_hoc_error; }
 static std::atomic<unsigned long long> g_launches[HOC_KERNEL_COUNT];
 static std::atomic<unsigned long long> g_timer_mask{0};
 static std::mutex g_timer_mutex;
-static thread_local int g_timer_slot = -1; /* slot reserved by phase 0 of this thread's launch in flight */
+static thread_local int g_timer_slot[2] = {-1, -1}; /* slot reserved by phase 0 of this thread's launch in flight
+                                                       ([1]: a group id bracketing several launches, nested around [0]) */
 static int g_timer_n = 0;
 static cudaEvent_t g_timer_ev[HOC_TIMER_CAP][2];
 static int g_timer_id[HOC_TIMER_CAP];
@@ -70,10 +71,11 @@ static void hoc_timer_record(cudaEvent_t ev, cudaStream_t st)
 
 void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
 {
-    if (phase == 0)
+    const int lvl = kernel_id >= HOC_K_RASTER_BWD_GROUP ? 1 : 0;
+    if (phase == 0 && lvl == 0)
         g_launches[kernel_id].fetch_add(1, std::memory_order_relaxed);
     if (phase == 0) {
-        g_timer_slot = -1;
+        g_timer_slot[lvl] = -1;
         if (!((g_timer_mask.load(std::memory_order_relaxed) >> kernel_id) & 1ull))
             return;
         std::lock_guard<std::mutex> lock(g_timer_mutex);
@@ -86,11 +88,11 @@ void hoc_note_launch(int kernel_id, cudaStream_t st, int phase)
             g_timer_created++;
         }
         g_timer_id[slot] = kernel_id;
-        g_timer_slot = slot;
+        g_timer_slot[lvl] = slot;
         hoc_timer_record(g_timer_ev[slot][0], st);
-    } else if (g_timer_slot >= 0) {
-        hoc_timer_record(g_timer_ev[g_timer_slot][1], st);
-        g_timer_slot = -1;
+    } else if (g_timer_slot[lvl] >= 0) {
+        hoc_timer_record(g_timer_ev[g_timer_slot[lvl]][1], st);
+        g_timer_slot[lvl] = -1;
     }
 }
 

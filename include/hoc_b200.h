@@ -93,7 +93,9 @@ const char *hoc_last_error(void);
 #define HOC_K_PAIR_BACK 29
 #define HOC_K_AUGMENT_STATS 30
 #define HOC_K_AUGMENT_FRAMES 31
-#define HOC_KERNEL_COUNT 32
+#define HOC_K_RASTER_BWD_GROUP 32 /* not a kernel: the whole hoc_raster_backward(_ex) call (scan + cover + line [+ depth]) timed
+                                     with ONE event pair -- per-kernel event nodes add ~4 us each inside a captured graph */
+#define HOC_KERNEL_COUNT 33
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)

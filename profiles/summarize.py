@@ -24,8 +24,10 @@ def launches(src, dst):
     own = sum(a[1] for k, a in agg.items() if "hoc_" in k)
     with open(dst, "w") as f:
         f.write(f"# ncu launch list ({src})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over "
-                f"`python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (all arms: eager, graph capture + replays, "
-                f"e2e).  Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n"
+                f"`python bench.py --eager-only --steps 2 --warmup 3` (the eager arm of the frame-pair path: coverage probe, "
+                f"warm-up and timed steps issued from Python; the ATen kernels are bench.py's own cloning of its inputs "
+                f"into fresh leaf tensors and the one-off measured-coverage reduction, not part of a captured step).  "
+                f"Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n\n"
                 f"{len(rows)} launches, {tot:.0f} us of kernel time, of which this library's kernels: {own:.0f} us "
                 f"({own / tot * 100:.1f} %).\n\n| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -63,7 +65,7 @@ def full(rep, dst, traffic_json=None):
     traffic = {}
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary ({rep})\n\n`ncu --set full --clock-control none --import-source on -k regex:hoc_` "
-                f"over the eager arm of bench.py (16 pairs, 256x256).  Values are the mean over the captured launches of "
+                f"over the eager arm of bench.py (16 frame pairs, 256x256: both renders of a pair stacked, 32 samples per rasterizer launch).  Values are the mean over the captured launches of "
                 f"each kernel.\n\n")
         for k, rs in per.items():
             f.write(f"## `{k}`  ({len(rs)} launches, grid {rs[0][hdr.index('Grid Size')]}, block {rs[0][hdr.index('Block Size')]})\n\n"

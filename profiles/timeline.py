@@ -1,6 +1,6 @@
 """Kernel timeline of ONE replay of the captured consist step (torch.profiler / CUPTI), bench.py's workload.
 
-    python profiles/timeline.py > profiles/timeline_rN.txt
+    python profiles/timeline.py [pairs width height] > profiles/timeline_rN.txt      (default: configs[2], 16 256 256)
 
 Columns: start (us, relative to the first kernel of the replay), duration (us), kernel name.  Unlike ncu's per-launch
 numbers these are warm-cache and overlapped exactly as in production (two streams inside the graph)."""
@@ -16,15 +16,16 @@ from handobjectconsist_b200.graphed import GraphedConsistStep  # noqa: E402
 from handobjectconsist_b200.neurender.renderer import Renderer  # noqa: E402
 from handobjectconsist_b200.optim.pyramidloss import PyramidCriterion  # noqa: E402
 
-S, P = bench.SIZE, bench.PAIRS
+P, W, H = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (bench.PAIRS, bench.WIDTH, bench.HEIGHT)
+S = max(W, H)
 dev = torch.device("cuda:0")
 renderer = Renderer(image_size=S, R=torch.eye(3, device=dev)[None], t=torch.zeros(1, 3, device=dev),
                     K=torch.ones(1, 3, 3, device=dev), orig_size=S, anti_aliasing=False, fill_back=True, near=0.1,
                     no_light=True)
-sets = bench._make_sets(2, P, S, dev)
+sets = bench._make_sets(2, P, (W, H), dev)
 hand_face = sets[0]["faces"][0, :1552].clone()
 batches = [bench._samples_from_scene(sc) for sc in sets]
-g = GraphedConsistStep(renderer, PyramidCriterion("l1"), (S, S), hand_face, *batches[0],
+g = GraphedConsistStep(renderer, PyramidCriterion("l1"), (W, H), hand_face, *batches[0],
                        hand_ignore_faces=sets[0]["hand_ignore_faces"], gt_refs=True, first_only=True, use_backward=True,
                        detach_renders=False, warmup=2)
 for _ in range(5):
@@ -41,7 +42,7 @@ cut = max(i for i, e in enumerate(ev) if "Memcpy" in e.name)
 ev = ev[cut + 1:]
 t0 = ev[0].time_range.start
 span = max(e.time_range.end for e in ev) - t0
-print(f"kernels in replay {len(ev)} span us {span:.3f}")
+print(f"{P} frame pairs of {W}x{H} on a {S}x{S} raster: kernels in replay {len(ev)} span us {span:.3f}")
 agg = {}
 for e in ev:
     d = e.time_range.end - e.time_range.start
