@@ -5,7 +5,7 @@ occlusion check) -> pair_consist (four warps, mask algebra, two masked L1 means)
 (/root/reference/meshreg/models/warpbranch.py:45-88, meshreg/warping/opticalflow.py:51-156,
 meshreg/warping/imgflowarp.py:58-115).  The operator-by-operator mirrors of those functions live in
 ``warping/opticalflow.py`` and ``warping/imgflowarp.py``; this module is the training fast path: the same arithmetic
-(same device functions, bit-identical flows / masks) as SIX launches forward and FIVE backward, with the two renders
+(same device functions, bit-identical flows / masks) as FIVE launches forward and FIVE backward, with the two renders
 of the pair stacked along the batch ([2B]) so that every rasterizer kernel runs once:
 
     forward   hoc_pair_front                 vertices of both frames -> faces / vertex textures of both renders, key fill
@@ -14,13 +14,14 @@ of the pair stacked along the batch ([2B]) so that every rasterizer kernel runs 
                                              pixel, same pass -- both warp directions, valid masks, |warp - target| sums
                                              (with visuals: hoc_flow_finalize, then hoc_warp_photo_forward_pair)
               hoc_pair_loss_mean             masked means -> loss [B] and its batch mean
-    backward  hoc_warp_photo_backward_pair   d loss / d flow x d flow / d rgb -> incoming gradients of both renders
-              hoc_raster_backward_ex [2B]    scan / cover / line passes (pseudo-gradient for the first render only)
+    backward  hoc_pair_backward_raster [2B]  scan pass FUSED with the backward of pair_consist (d loss / d flow x d flow /
+                                             d rgb computed from the valid masks), then the cover / line passes
+                                             (pseudo-gradient for the first render only)
               hoc_mesh_scatter       [2B]    faces -> vertices
               hoc_pair_back                  projection adjoints -> d loss / d (hand, object vertices)
 
 No memset and no ATen kernel in between: every zero-fill a kernel needs is done by the kernel before it (the loss
-sums by hoc_pair_front, the rasterizer backward's counters by the warp backward, the scatter's outputs by the
+sums by hoc_pair_front, the rasterizer backward's counters by hoc_pair_loss_mean, the scatter's outputs by the
 rasterizer backward's streaming pass), and the batch mean and its adjoint live inside hoc_pair_loss_mean / the warp
 backward.
 
@@ -161,8 +162,18 @@ class _PairConsistFunction(Function):
                     pp(valid[0], valid[1]), pp(flow_mask[0], flow_mask[1]), _lib.ptr(sums), st),
                     "hoc_warp_photo_forward_pair")
             loss, mean = e(B), e()
+            # the workspace of the step's backward is allocated here, so that this launch can zero-fill its counters
+            # (one memset node less in a captured step); a second backward over the same graph falls back to a memset
+            bws = bws_zero = None
+            if any(ctx.needs_input_grad[:4]):
+                n_b = 2 * B if cfg["use_backward"] else B
+                bws_bytes = L.hoc_raster_backward_workspace_bytes_ex(n_b, Fr, S, 2, _lib.HOC_TEX_GRAD_VERTEX)
+                bws = e(max(bws_bytes, 16), dtype=torch.uint8)
+                bws_zero = L.hoc_raster_backward_zero_bytes(n_b, Fr, S)
             _lib.check(L.hoc_pair_loss_mean(_lib.ptr(sums[0]), _lib.ptr(sums[1]) if cfg["use_backward"] else None, B,
-                                            _lib.ptr(loss), _lib.ptr(mean), st), "hoc_pair_loss_mean")
+                                            _lib.ptr(loss), _lib.ptr(mean), _lib.ptr(bws), bws_zero or 0, st),
+                       "hoc_pair_loss_mean")
+            ctx.bws, ctx.bws_clean = bws, bws is not None
         ctx.row_lo = row_lo
         ctx.save_for_backward(h1, o1, h2, o2, faces, table, idx, rgb, wmap, depth, ir, im, flow12, flow21, valid, sums,
                               mult, *cams)
@@ -210,27 +221,25 @@ class _PairConsistFunction(Function):
         with torch.cuda.device(dev):
             st = _lib.stream_ptr()
             e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
-            grad_rgb = e(2 * B, 3, S, S)
             ws_bytes = L.hoc_raster_backward_workspace_bytes_ex(n, Fr, S, 2, _lib.HOC_TEX_GRAD_VERTEX)
-            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-            # the warp backward also zero-fills the counters of the rasterizer backward that follows
-            ws_zero = L.hoc_raster_backward_zero_bytes(n, Fr, S)
-            _lib.check(L.hoc_warp_photo_backward_pair(
-                _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr_pair(valid[0], valid[1]),
-                _lib.ptr(sums), _lib.ptr(mult[0]), _lib.ptr(mult[1]), _lib.ptr(gl), _lib.ptr(gm), B, S, H, W,
-                int(use_backward), _lib.ptr(grad_rgb[:B]) if use_backward else None, _lib.ptr(grad_rgb[B:]), None, None,
-                _lib.ptr(ws), ws_zero, rl(0), rl(B), st), "hoc_warp_photo_backward_pair")
+            ws = ctx.bws
+            clean = ctx.bws_clean and ws is not None and ws.numel() >= ws_bytes
+            if not clean:  # (a second backward over the same graph, or the reproducible mode switched on in between)
+                ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+            ctx.bws_clean = False
+            grad_rgb = e(n, 3, S, S)  # scratch of the fused scan pass: the incoming gradient of the renders' rgb maps
             grad_faces = e(n, Fr, 3, 3) if geom > 0 else None
             grad_tex = e(n, Fr, 3, 3)
             # grad of the NDC vertices, grad of the vertex attributes: zero-filled by the rasterizer backward's
             # streaming pass, accumulated by the scatter after it
             both = e(2, 2 * B, V, 3)
-            _lib.check(L.hoc_raster_backward_ex(
-                _lib.ptr(faces[lo:]), None, _lib.ptr(idx[lo:]), _lib.ptr(rgb[lo:]), _lib.ptr(wmap[lo:]),
-                _lib.ptr(depth[lo:]), _lib.ptr(grad_rgb[lo:]), None, None, n, Fr, S, 2, k["near"], k["far"], k["eps"],
-                _lib.HOC_LAYOUT_IMAGE, 1, _lib.HOC_TEX_GRAD_VERTEX, geom, _lib.HOC_BWD_WORKSPACE_ZEROED, _lib.ptr(both),
-                both.numel() * 4, rl(lo), _lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(ws), ws_bytes, st),
-                "hoc_raster_backward_ex")
+            _lib.check(L.hoc_pair_backward_raster(
+                _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr_pair(valid[0], valid[1]),
+                _lib.ptr(sums), _lib.ptr(mult[0]), _lib.ptr(mult[1]), _lib.ptr(gl), _lib.ptr(gm), B, H, W,
+                int(use_backward), lo, _lib.ptr(faces[lo:]), _lib.ptr(idx[lo:]), _lib.ptr(rgb[lo:]), _lib.ptr(wmap[lo:]),
+                _lib.ptr(depth[lo:]), _lib.ptr(grad_rgb), n, Fr, S, k["near"], k["far"], k["eps"], geom,
+                _lib.HOC_BWD_WORKSPACE_ZEROED if clean else 0, _lib.ptr(both), both.numel() * 4, rl(lo),
+                _lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(ws), ws.numel(), st), "hoc_pair_backward_raster")
             g_ndc, g_attr = (both[0] if geom > 0 else None), both[1]
             sc_bytes = L.hoc_mesh_scatter_workspace_bytes(n, V)
             sc_ws = torch.empty(sc_bytes, dtype=torch.uint8, device=dev) if sc_bytes else None

@@ -37,6 +37,7 @@
 #include "hoc_common.cuh"
 #include "hoc_det.cuh"
 #include "raster_math.h"
+#include "warp_math.cuh"
 
 #define EXT_ROW_LO 0
 #define EXT_ROW_HI 1
@@ -460,6 +461,176 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     if (lane == 31)
         s_wcnt[ty] = incl;
     __syncthreads(); /* warp totals and the column spans are complete */
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const int c = s_wcnt[w];
+            s_wcnt[w] = tot;
+            tot += c;
+        }
+        s_base = (tot > 0) ? atomicAdd(cov_count + b, tot) : 0;
+    }
+    if (K4 && threadIdx.x < 128) {
+        const int xi = blockIdx.x * 128 + threadIdx.x;
+        if (xi < S && s_chi[threadIdx.x] >= 0) {
+            int *e = ext + (long)b * 4 * S;
+            atomicMax(&e[EXT_COL_LO * S + xi], S - s_clo[threadIdx.x]);
+            atomicMax(&e[EXT_COL_HI * S + xi], s_chi[threadIdx.x] + 1);
+        }
+    }
+    __syncthreads();
+    if (want) {
+        int2 *list = cov_list + (long)b * S * S + s_base + s_wcnt[ty] + (incl - mine);
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((want >> j) & 1u)
+                list[k++] = make_int2(yi * S + x0 + j, fis[j]);
+    }
+}
+
+/*
+ * Frame-pair path: the scan pass FUSED with the backward of pair_consist (hoc_warp_photo_backward_pair).  The incoming
+ * gradient of a render's rgb map is d loss / d flow x mult at the few valid pixels of the crop and zero everywhere
+ * else, so instead of one pass that writes it (12 B/px) and another that reads it back, this pass reads the valid mask
+ * (1 B/px), computes the gradient of the valid pixels (phase B of the two-phase pattern: 12 bilinear taps each, one
+ * pixel per thread) into a shared tile, and goes on as hoc_raster_bwd_scan4_kernel from there -- spans, covered-pixel
+ * list, zero-fills -- writing the gradient planes once for the cover and line passes.  One launch and 12 B/px less.
+ * Stacked row b of the launch is render (b + row_offset) / pairs of pair (b + row_offset) % pairs; render 1's flow is
+ * consumed by pair_consist's direction 1, render 2's by direction 0.
+ */
+struct HocPairGradSrc {
+    HocPairBwdDir dir[2]; /* by pair_consist direction (warp_math.cuh); grad_rgb / grad_flow unused here */
+    const float *grad_loss, *grad_mean;
+    int pairs, H, W, row_offset;
+    float inv_w, inv_h;
+};
+
+__global__ void __launch_bounds__(256)
+hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocPairGradSrc G, float *__restrict__ g_rgb,
+                                int S, int k4_samples, int list_all_rest, int *__restrict__ ext,
+                                int *__restrict__ cov_count, int2 *__restrict__ cov_list, float *__restrict__ zero_a,
+                                long n_a, float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
+                                const int *__restrict__ row_lo)
+{
+    {
+        const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
+        const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        for (long i = t0; i < n_a; i += nthreads)
+            zero_a[i] = 0.0f;
+        for (long i = t0; i < n_b; i += nthreads)
+            zero_b[i] = 0.0f;
+        for (long i = t0; i < n_c; i += nthreads)
+            zero_c[i] = 0.0f;
+    }
+    __shared__ int s_clo[128], s_chi[128];
+    __shared__ int s_wcnt[8], s_base, s_n;
+    __shared__ unsigned short s_list[1024];
+    __shared__ __align__(16) float s_gx[1024];
+    __shared__ __align__(16) float s_gy[1024];
+    const int b = blockIdx.z;
+    const bool K4 = b < k4_samples;
+    const int list_all = K4 ? 1 : list_all_rest;
+    const int r = b + G.row_offset;
+    const int bp = r % G.pairs;                       /* the pair */
+    const HocPairBwdDir &D = G.dir[r < G.pairs ? 1 : 0]; /* render 1 <- direction 1, render 2 <- direction 0 */
+    const int H = G.H, W = G.W;
+    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int y_img = blockIdx.y * 8 + ty; /* image row (rows flipped): raster row yi = S - 1 - y_img */
+    const int yi = S - 1 - y_img;
+    const int x0 = blockIdx.x * 128 + lane * 4;
+    const int y_first = (row_lo != nullptr) ? row_lo[b] : 0;
+    const bool in = y_img < S && x0 < S && yi >= y_first;
+    if (threadIdx.x < 128) {
+        s_clo[threadIdx.x] = 0x7fffffff;
+        s_chi[threadIdx.x] = -1;
+    }
+    if (threadIdx.x == 0)
+        s_n = 0;
+    *reinterpret_cast<float4 *>(s_gx + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4 *>(s_gy + threadIdx.x * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    /* phase A: face indices of the four pixels; the valid pixels of the crop are noted in the shared list */
+    int fis[4] = {-1, -1, -1, -1};
+    const long npix = (long)H * W;
+    if (in) {
+        const int4 f4 = *reinterpret_cast<const int4 *>(face_index_map + ((long)b * S + yi) * S + x0);
+        fis[0] = f4.x; fis[1] = f4.y; fis[2] = f4.z; fis[3] = f4.w;
+        if (D.active && y_img < H && x0 < W) {
+            const unsigned vb = *reinterpret_cast<const unsigned *>(D.valid_mask + (long)bp * npix + (long)y_img * W + x0);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if ((vb >> (8 * j)) & 0xffu)
+                    s_list[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + j);
+        }
+    }
+    __syncthreads();
+    /* phase B: d loss / d flow x mult of the listed pixels, one per thread (hoc_warp_photo_pair_backward_kernel) */
+    const int n_valid = s_n;
+    if (n_valid > 0) {
+        const float cnt = (float)D.sums[2 * bp + 1];
+        const float gl = ((G.grad_loss != nullptr) ? G.grad_loss[bp] : 0.0f) +
+                         ((G.grad_mean != nullptr) ? __fdiv_rn(G.grad_mean[0], (float)G.pairs) : 0.0f);
+        const float scale = gl / fmaxf(cnt, 1.0f);
+        for (int i = threadIdx.x; i < n_valid; i += 256) {
+            const int loc = s_list[i];
+            const int t = loc >> 2, j = loc & 3;
+            const int y = blockIdx.y * 8 + (t >> 5), x = blockIdx.x * 128 + (t & 31) * 4 + j;
+            float gfx, gfy;
+            hoc_pair_bwd_pixel(D, bp, x, y, H, W, G.inv_w, G.inv_h, scale, &gfx, &gfy);
+            const float m = D.mult[(long)bp * npix + (long)y * W + x]; /* hoc_flow_finalize_backward_kernel */
+            s_gx[loc] = gfx * m;
+            s_gy[loc] = gfy * m;
+        }
+    }
+    __syncthreads();
+    /* phase C: the gradient planes (written once, for the cover and line passes) and the scan pass proper */
+    unsigned nzm = 0;
+    if (in) {
+        const float4 gx = *reinterpret_cast<const float4 *>(s_gx + threadIdx.x * 4);
+        const float4 gy = *reinterpret_cast<const float4 *>(s_gy + threadIdx.x * 4);
+        float *dst = g_rgb + (((long)b * 3) * S + y_img) * S + x0;
+        *reinterpret_cast<float4 *>(dst) = gx;
+        *reinterpret_cast<float4 *>(dst + (long)S * S) = gy;
+        *reinterpret_cast<float4 *>(dst + 2l * S * S) = make_float4(0.f, 0.f, 0.f, 0.f);
+        nzm = ((!(gx.x == 0.0f) || !(gy.x == 0.0f)) ? 1u : 0u) | ((!(gx.y == 0.0f) || !(gy.y == 0.0f)) ? 2u : 0u) |
+              ((!(gx.z == 0.0f) || !(gy.z == 0.0f)) ? 4u : 0u) | ((!(gx.w == 0.0f) || !(gy.w == 0.0f)) ? 8u : 0u);
+    }
+    unsigned want = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (fis[j] >= 0 && (list_all || ((nzm >> j) & 1u)))
+            want |= 1u << j;
+    if (K4) {
+        int lo = nzm ? x0 + (__ffs(nzm) - 1) : 0x7fffffff, hi = nzm ? x0 + (31 - __clz(nzm)) : -1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(HOC_FULL_MASK, lo, o));
+            hi = max(hi, __shfl_xor_sync(HOC_FULL_MASK, hi, o));
+        }
+        int *e = ext + (long)b * 4 * S;
+        if (lane == 0 && hi >= 0) {
+            atomicMax(&e[EXT_ROW_LO * S + yi], S - lo);
+            atomicMax(&e[EXT_ROW_HI * S + yi], hi + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if ((nzm >> j) & 1u) {
+                atomicMin(&s_clo[lane * 4 + j], yi);
+                atomicMax(&s_chi[lane * 4 + j], yi);
+            }
+    }
+    const int mine = __popc(want);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s_wcnt[ty] = incl;
+    __syncthreads();
     if (threadIdx.x == 0) {
         int tot = 0;
         for (int w = 0; w < 8; w++) {
@@ -1021,7 +1192,8 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
                                     int F, int S, int ts, float near_, float far_, float eps, int layout,
                                     int use_alpha, int tex_grad_mode, int geom_samples, int flags, void *extra_zero,
                                     size_t extra_zero_bytes, const int *row_lo, float *grad_faces,
-                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream);
+                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream,
+                                    const HocPairGradSrc *pair_src, float *grad_rgb_out);
 
 extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures, const int32_t *face_index_map,
                                       const float *rgb, const float *weight_map, const float *depth,
@@ -1036,7 +1208,54 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
     const int rc = hoc_raster_backward_impl(faces, textures, face_index_map, rgb, weight_map, depth, grad_rgb, grad_alpha,
                                             grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode,
                                             geom_samples, flags, extra_zero, extra_zero_bytes, row_lo, grad_faces,
-                                            grad_textures, workspace, workspace_bytes, stream);
+                                            grad_textures, workspace, workspace_bytes, stream, nullptr, nullptr);
+    hoc_note_launch(HOC_K_RASTER_BWD_GROUP, (cudaStream_t)stream, 1);
+    return rc;
+}
+
+/* The backward of the frame-pair step from the loss to grad_faces / grad_textures in one call: the backward of
+ * pair_consist (hoc_warp_photo_backward_pair) fused into the rasterizer backward's scan pass
+ * (hoc_raster_bwd_scan_pair_kernel), then the cover and line passes.  grad_rgb [n,3,S,S] is scratch the call fills.
+ * The stacked batch holds rows [row_offset, row_offset + n) of (render 1 of every pair, render 2 of every pair). */
+extern "C" int hoc_pair_backward_raster(const float *image_ref, const float *image, const float *flow12,
+                                        const float *flow21, const uint8_t *const *valid_mask, const double *sums,
+                                        const float *mult1, const float *mult2, const float *grad_loss,
+                                        const float *grad_mean, int pairs, int H, int W, int use_backward,
+                                        int row_offset, const float *faces, const int32_t *face_index_map,
+                                        const float *rgb, const float *weight_map, const float *depth, float *grad_rgb,
+                                        int n, int F, int S, float near_, float far_, float eps, int geom_samples,
+                                        int flags, void *extra_zero, size_t extra_zero_bytes, const int *row_lo,
+                                        float *grad_faces, float *grad_textures, void *workspace,
+                                        size_t workspace_bytes, void *stream)
+{
+    HOC_CHECK_ARG(pairs >= 1 && n >= 1 && row_offset >= 0 && row_offset + n <= 2 * pairs,
+                  "hoc_pair_backward_raster: rows [%d, %d) outside the stacked batch of %d pairs", row_offset,
+                  row_offset + n, pairs);
+    HOC_CHECK_ARG(S >= 4 && (S % 4) == 0 && H >= 1 && H <= S && W >= 4 && W <= S && (W % 4) == 0,
+                  "hoc_pair_backward_raster: bad shape S=%d H=%d W=%d (S, W multiples of 4)", S, H, W);
+    HOC_CHECK_ARG(image_ref && image && flow12 && flow21 && valid_mask && valid_mask[0] && valid_mask[1] && sums && mult1 &&
+                      mult2 && (grad_loss || grad_mean) && grad_rgb && rgb,
+                  "hoc_pair_backward_raster: NULL argument");
+    HOC_CHECK_ARG((((uintptr_t)grad_rgb | (uintptr_t)face_index_map) & 15) == 0 &&
+                      ((((uintptr_t)valid_mask[0] | (uintptr_t)valid_mask[1]) & 3) == 0),
+                  "hoc_pair_backward_raster: tensors must be 16-byte aligned");
+    HocPairGradSrc G;
+    /* direction 0: warp(image_ref, flow21) vs image -> d / d flow21 -> render 2; direction 1: the reverse */
+    G.dir[0].src = image_ref; G.dir[0].target = image; G.dir[0].flow = flow21; G.dir[0].mult = mult2;
+    G.dir[0].valid_mask = valid_mask[0]; G.dir[0].sums = sums; G.dir[0].grad_rgb = nullptr; G.dir[0].grad_flow = nullptr;
+    G.dir[0].active = 1;
+    G.dir[1].src = image; G.dir[1].target = image_ref; G.dir[1].flow = flow12; G.dir[1].mult = mult1;
+    G.dir[1].valid_mask = valid_mask[1]; G.dir[1].sums = sums + 2 * (size_t)pairs; G.dir[1].grad_rgb = nullptr;
+    G.dir[1].grad_flow = nullptr; G.dir[1].active = use_backward ? 1 : 0;
+    G.grad_loss = grad_loss; G.grad_mean = grad_mean;
+    G.pairs = pairs; G.H = H; G.W = W; G.row_offset = row_offset;
+    G.inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);
+    G.inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
+    hoc_note_launch(HOC_K_RASTER_BWD_GROUP, (cudaStream_t)stream, 0);
+    const int rc = hoc_raster_backward_impl(faces, nullptr, face_index_map, rgb, weight_map, depth, grad_rgb, nullptr,
+                                            nullptr, n, F, S, 2, near_, far_, eps, HOC_LAYOUT_IMAGE, 1, HOC_TEX_GRAD_VERTEX,
+                                            geom_samples, flags, extra_zero, extra_zero_bytes, row_lo, grad_faces,
+                                            grad_textures, workspace, workspace_bytes, stream, &G, grad_rgb);
     hoc_note_launch(HOC_K_RASTER_BWD_GROUP, (cudaStream_t)stream, 1);
     return rc;
 }
@@ -1047,7 +1266,8 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
                                     int F, int S, int ts, float near_, float far_, float eps, int layout,
                                     int use_alpha, int tex_grad_mode, int geom_samples, int flags, void *extra_zero,
                                     size_t extra_zero_bytes, const int *row_lo, float *grad_faces,
-                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream)
+                                    float *grad_textures, void *workspace, size_t workspace_bytes, void *stream,
+                                    const HocPairGradSrc *pair_src, float *grad_rgb_out)
 {
     (void)textures;
     HOC_CHECK_ARG(extra_zero == nullptr || (extra_zero_bytes % 4 == 0 && ((uintptr_t)extra_zero & 3) == 0),
@@ -1107,7 +1327,15 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         /* without the pseudo-gradient only pixels with a texture gradient (non-zero dL/drgb) or a depth
          * gradient have work */
         const uintptr_t al = (uintptr_t)face_index_map | (uintptr_t)grad_rgb | (uintptr_t)g_alpha;
-        if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && (al & 15) == 0) {
+        if (pair_src != nullptr) { /* frame-pair path: the incoming gradient is computed by the scan pass itself */
+            dim3 pg4((S + 127) / 128, (S + 7) / 8, B);
+            HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
+                       (hoc_raster_bwd_scan_pair_kernel<<<pg4, 256, 0, st>>>(
+                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, want_depth ? 1 : 0, w.ext, w.cov_count,
+                           w.cov_list, grad_faces, n_gf, grad_textures, n_gt, (float *)extra_zero,
+                           (long)(extra_zero_bytes / sizeof(float)), row_lo)));
+            HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_pair_kernel");
+        } else if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && (al & 15) == 0) {
             dim3 pg4((S + 127) / 128, (S + 7) / 8, B);
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan4_kernel<<<pg4, 256, 0, st>>>(

@@ -193,3 +193,61 @@ __device__ __forceinline__ bool hoc_pair_pixel(const float *__restrict__ sb, con
     return valid;
 }
 
+
+/* ---- backward of one direction of pair_consist -------------------------------------------------------------------- */
+struct HocPairBwdDir {
+    const float *src, *target, *flow, *mult;
+    const uint8_t *valid_mask;
+    const double *sums;
+    float *grad_rgb;  /* [B,3,S,S] or NULL (direction skipped) */
+    float *grad_flow; /* [B,H,W,2] or NULL: the flow gradient itself, for callers that want it */
+    int active;       /* 0: this direction carries no loss (use_backward = False): zeros */
+};
+
+
+/* d loss[b] / d flow at one VALID pixel (x, y) of direction D (valid => the in-bounds mask of the sample is 1):
+ * loss[b] = sum_valid |warp - target| / max(count, 1); `scale` = d L / d loss[b] / max(count, 1).  The thresholded
+ * masks carry no gradient, so only the bilinear taps of the source depend on the flow (imgflowarp.py:52-53). */
+__device__ __forceinline__ void hoc_pair_bwd_pixel(const HocPairBwdDir &D, int b, int x, int y, int H, int W, float inv_w,
+                                                   float inv_h, float scale, float *gfx, float *gfy)
+{
+    const long npix = (long)H * W;
+    const long pix = (long)y * W + x;
+    const float2 fl = *reinterpret_cast<const float2 *>(D.flow + ((long)b * npix + pix) * 2);
+    HocTaps T;
+    hoc_bilinear_taps_inv(x, y, fl.x, fl.y, H, W, inv_w, inv_h, T);
+    const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
+    float gix = 0.0f, giy = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const float *plane = D.src + ((long)b * 3 + c) * npix;
+        const float v = hoc_plane_sample(plane, W, T);
+        const float d = v - D.target[((long)b * 3 + c) * npix + pix];
+        const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
+        const float go = scale * sgn;
+        const float *p = plane + (long)T.y0 * W + T.x0;
+        if (T.b_nw) {
+            const float v0 = __ldg(p);
+            gix -= v0 * (y_se - T.iy) * go;
+            giy -= v0 * (x_se - T.ix) * go;
+        }
+        if (T.b_ne) {
+            const float v1 = __ldg(p + 1);
+            gix += v1 * (y_se - T.iy) * go;
+            giy -= v1 * (T.ix - x_nw) * go;
+        }
+        if (T.b_sw) {
+            const float v2 = __ldg(p + W);
+            gix -= v2 * (T.iy - y_nw) * go;
+            giy += v2 * (x_se - T.ix) * go;
+        }
+        if (T.b_se) {
+            const float v3 = __ldg(p + W + 1);
+            gix += v3 * (T.iy - y_nw) * go;
+            giy += v3 * (T.ix - x_nw) * go;
+        }
+    }
+    /* d ix / d x_norm = W / 2 ; d x_norm / d flow = 2 / (W - 1) */
+    *gfx = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
+    *gfy = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
+}

@@ -192,8 +192,16 @@ __global__ void hoc_pair_loss_kernel(const double *__restrict__ sums_fwd, const 
 /* The same plus the batch mean (warpbranch.py:88: the mean over the single pair's per-sample losses), one warp:
  * no separate reduction kernel, and its adjoint (d mean / d loss[b] = 1 / B) is folded into the backward kernel. */
 __global__ void hoc_pair_loss_mean_kernel(const double *__restrict__ sums_fwd, const double *__restrict__ sums_bwd, int B,
-                                          float *__restrict__ loss, float *__restrict__ mean)
+                                          float *__restrict__ loss, float *__restrict__ mean, uint4 *__restrict__ zero,
+                                          long n_zero)
 {
+    if (blockIdx.x > 0) { /* the other CTAs zero-fill a buffer of the step's BACKWARD (its rasterizer's counters) */
+        for (long i = (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < n_zero; i += (long)(gridDim.x - 1) * blockDim.x)
+            zero[i] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    if (threadIdx.x >= 32)
+        return;
     float acc = 0.0f;
     for (int b = threadIdx.x; b < B; b += 32) {
         const float lf = (float)(sums_fwd[2 * b] * WP_SUM_INV / fmax(sums_fwd[2 * b + 1], 1.0));
@@ -386,15 +394,6 @@ hoc_warp_photo_pair_forward_kernel(HocPairDir D0, HocPairDir D1, int H, int W, f
  * arithmetic) times mult = d flow / d rgb, written straight into the incoming gradient of the two renders' rgb maps
  * ([B,3,S,S], image layout; zero outside the H x W crop and in the third channel).  blockIdx.z = direction k: k = 0
  * differentiates flow21 (render 2), k = 1 flow12 (render 1).  Four pixels of a raster row per thread. */
-struct HocPairBwdDir {
-    const float *src, *target, *flow, *mult;
-    const uint8_t *valid_mask;
-    const double *sums;
-    float *grad_rgb;  /* [B,3,S,S] or NULL (direction skipped) */
-    float *grad_flow; /* [B,H,W,2] or NULL: the flow gradient itself, for callers that want it */
-    int active;       /* 0: this direction carries no loss (use_backward = False): zeros */
-};
-
 #ifndef WPB_THREADS
 #define WPB_THREADS 128 /* (128 vs 256: 11.2 / 11.9 us) */
 #endif
@@ -469,42 +468,8 @@ hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const fl
         const int qq = blockIdx.x * WPB_THREADS + (loc >> 2);
         const int y = qq / S4, x = ((qq - y * S4) << 2) + (loc & 3);
         const long pix = (long)y * W + x;
-        const float2 fl = *reinterpret_cast<const float2 *>(D.flow + ((long)b * npix + pix) * 2);
-        HocTaps T;
-        hoc_bilinear_taps_inv(x, y, fl.x, fl.y, H, W, inv_w, inv_h, T);
-        const float x_nw = (float)T.x0, y_nw = (float)T.y0, x_se = (float)(T.x0 + 1), y_se = (float)(T.y0 + 1);
-        float gix = 0.0f, giy = 0.0f;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float *plane = D.src + ((long)b * 3 + c) * npix;
-            const float v = hoc_plane_sample(plane, W, T); /* valid => in-bounds mask is 1 */
-            const float d = v - D.target[((long)b * 3 + c) * npix + pix];
-            const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-            const float go = scale * sgn;
-            const float *p = plane + (long)T.y0 * W + T.x0;
-            if (T.b_nw) {
-                const float v0 = __ldg(p);
-                gix -= v0 * (y_se - T.iy) * go;
-                giy -= v0 * (x_se - T.ix) * go;
-            }
-            if (T.b_ne) {
-                const float v1 = __ldg(p + 1);
-                gix += v1 * (y_se - T.iy) * go;
-                giy -= v1 * (T.ix - x_nw) * go;
-            }
-            if (T.b_sw) {
-                const float v2 = __ldg(p + W);
-                gix -= v2 * (T.iy - y_nw) * go;
-                giy += v2 * (x_se - T.ix) * go;
-            }
-            if (T.b_se) {
-                const float v3 = __ldg(p + W + 1);
-                gix += v3 * (T.iy - y_nw) * go;
-                giy += v3 * (T.ix - x_nw) * go;
-            }
-        }
-        const float gfx = (0.5f * (float)W) * gix * 2.0f / (float)max(W - 1, 1);
-        const float gfy = (0.5f * (float)H) * giy * 2.0f / (float)max(H - 1, 1);
+        float gfx, gfy;
+        hoc_pair_bwd_pixel(D, b, x, y, H, W, inv_w, inv_h, scale, &gfx, &gfy);
         if (D.grad_rgb != nullptr) {
             const float m = D.mult[(long)b * npix + pix]; /* hoc_flow_finalize_backward_kernel */
             float *dst = D.grad_rgb + (long)b * 3 * S * S + (long)y * S + x;
@@ -752,12 +717,17 @@ extern "C" int hoc_pair_loss(const double *sums_fwd, const double *sums_bwd, int
 }
 
 extern "C" int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, float *loss, float *mean,
-                                  void *stream)
+                                  void *zero, size_t zero_bytes, void *stream)
 {
     HOC_CHECK_ARG(B >= 1, "hoc_pair_loss_mean: batch %d", B);
     HOC_CHECK_ARG(sums_fwd && loss && mean, "hoc_pair_loss_mean: NULL argument");
+    HOC_CHECK_ARG(zero == nullptr || (zero_bytes % 16 == 0 && ((uintptr_t)zero & 15) == 0),
+                  "hoc_pair_loss_mean: zero buffer must be 16-byte aligned with a size multiple of 16");
+    const long n_zero = zero ? (long)(zero_bytes / 16) : 0;
+    const unsigned extra = n_zero ? (unsigned)((n_zero + 1023) / 1024 < 64 ? (n_zero + 1023) / 1024 : 64) : 0;
     HOC_LAUNCH(HOC_K_PAIR_LOSS, (cudaStream_t)stream,
-               (hoc_pair_loss_mean_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sums_fwd, sums_bwd, B, loss, mean)));
+               (hoc_pair_loss_mean_kernel<<<1 + extra, 128, 0, (cudaStream_t)stream>>>(sums_fwd, sums_bwd, B, loss, mean,
+                                                                                        (uint4 *)zero, n_zero)));
     HOC_CHECK_LAUNCH("hoc_pair_loss_mean_kernel");
     return HOC_OK;
 }

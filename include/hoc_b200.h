@@ -277,8 +277,24 @@ int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, const int32_t
                            const int *ignore_faces, int n_ignore, float distance_thresh, float thresh, float *flow12,
                            float *flow21, float *mult1, float *mult2, uint8_t *const *valid_mask,
                            uint8_t *const *flow_mask, double *sums, void *stream);
-/* hoc_pair_loss plus the mean over the batch (warpbranch.py:88 for one pair), one launch. */
-int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, float *loss, float *mean, void *stream);
+/* hoc_pair_loss plus the mean over the batch (warpbranch.py:88 for one pair), one launch.  zero: an optional buffer the
+ * launch also zero-fills (the counters of the step's rasterizer backward, HOC_BWD_WORKSPACE_ZEROED). */
+int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, float *loss, float *mean, void *zero,
+                       size_t zero_bytes, void *stream);
+/* The backward of the frame-pair step from d loss to grad_faces / grad_textures in ONE call: the backward of pair_consist
+ * fused into the rasterizer backward's scan pass (the incoming gradient of the renders' rgb maps is computed from the
+ * valid masks instead of being written by one pass and read back by the next), then the cover and line passes.
+ * Arguments: those of hoc_warp_photo_backward_pair (pairs = B of the pair kernels) and of hoc_raster_backward_ex for the
+ * stacked rows [row_offset, row_offset + n) of (render 1 of every pair, render 2 of every pair); image layout, vertex
+ * texture gradients; grad_rgb [n,3,S,S] is scratch the call fills (rows inside the raster window). */
+int hoc_pair_backward_raster(const float *image_ref, const float *image, const float *flow12, const float *flow21,
+                             const uint8_t *const *valid_mask, const double *sums, const float *mult1,
+                             const float *mult2, const float *grad_loss, const float *grad_mean, int pairs, int H, int W,
+                             int use_backward, int row_offset, const float *faces, const int32_t *face_index_map,
+                             const float *rgb, const float *weight_map, const float *depth, float *grad_rgb, int n, int F,
+                             int S, float near_, float far_, float eps, int geom_samples, int flags, void *extra_zero,
+                             size_t extra_zero_bytes, const int *row_lo, float *grad_faces, float *grad_textures,
+                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* pair_consist's per-sample loss from the sums of its two directions (imgflowarp.py:108-114):
  * loss[b] = masked_mean(bwd) + masked_mean(fwd) (that order, float) when sums_bwd is given, else masked_mean(fwd). */
