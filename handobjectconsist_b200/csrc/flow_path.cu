@@ -375,13 +375,14 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
      * covered pixels one after the other would be the tail of the whole launch. */
     __shared__ unsigned short s_list[FW_THREADS * 4];
     __shared__ int s_n;
-    const int b = blockIdx.y;
-    const bool second = blockIdx.z != 0;
+    const int b = blockIdx.x >> 1; /* (sample, direction) fastest, chunks of rows from the image centre outwards */
+    const bool second = (blockIdx.x & 1) != 0;
+    const int chunk = hoc_centre_out(blockIdx.y, gridDim.y);
     const HocRender &Ra = second ? R2 : R1;
     const HocRender &Rb = second ? R1 : R2;
     const HocFinWarpDir &D = second ? D1 : D0;
     const int W4 = W >> 2, npix = H * W;
-    const int q = blockIdx.x * FW_THREADS + threadIdx.x;
+    const int q = chunk * FW_THREADS + threadIdx.x;
     if (threadIdx.x == 0)
         s_n = 0;
     __syncthreads();
@@ -416,7 +417,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
     int my_cnt = 0;
     for (int i = threadIdx.x; i < n; i += FW_THREADS) {
         const int loc = s_list[i];
-        const int qq = blockIdx.x * FW_THREADS + (loc >> 2);
+        const int qq = chunk * FW_THREADS + (loc >> 2);
         const int ry = qq / W4, rx = ((qq - ry * W4) << 2) + (loc & 3);
         const long po = ((long)b * S + ry) * S + rx, co = (((long)b * 3) * S + ry) * S + rx;
         float fx, fy, mu;
@@ -1276,7 +1277,7 @@ extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, co
                       (flow_mask == nullptr || (((uintptr_t)flow_mask[0] | (uintptr_t)flow_mask[1]) & 7) == 0),
                   "hoc_flow_finalize_warp: tensors must be 16-byte aligned");
     const long groups = (long)H * (W / 4);
-    dim3 grid((unsigned)((groups + FW_THREADS - 1) / FW_THREADS), B, 2);
+    dim3 grid(2 * B, (unsigned)((groups + FW_THREADS - 1) / FW_THREADS));
     HOC_LAUNCH(HOC_K_FLOW_FINALIZE, (cudaStream_t)stream,
                (hoc_flow_finalize_warp_kernel<<<grid, FW_THREADS, 0, (cudaStream_t)stream>>>(
                    R1, R2, D0, D1, S, H, W, ignore_faces, n_ignore, distance_thresh,

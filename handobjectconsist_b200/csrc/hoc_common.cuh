@@ -55,6 +55,14 @@ __device__ __forceinline__ long hoc_rgb_off(int layout, int S, int b, int yi, in
     return (((long)b * S + yi) * S + xi) * 3 + c;
 }
 
+/* k-th element of the centre-out order of [0, n): c, c-1, c+1, c-2, ... (a bijection).  Pixel passes hand their tiles
+ * to CTAs in this order, sample fastest: the tiles that hold the meshes (centred by the crop) carry the heavy work and
+ * start first, the empty border tiles drain last -- instead of the last sample's mesh tiles being the tail. */
+__device__ __forceinline__ int hoc_centre_out(int k, int n)
+{
+    return (n >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1));
+}
+
 __device__ __forceinline__ float hoc_warp_sum(float v)
 {
 #pragma unroll

@@ -516,6 +516,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     {
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
+        /* (grid = (samples, column tiles, row tiles): sample fastest, row tiles from the image centre outwards) */
         for (long i = t0; i < n_a; i += nthreads)
             zero_a[i] = 0.0f;
         for (long i = t0; i < n_b; i += nthreads)
@@ -528,7 +529,8 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     __shared__ unsigned short s_list[1024];
     __shared__ __align__(16) float s_gx[1024];
     __shared__ __align__(16) float s_gy[1024];
-    const int b = blockIdx.z;
+    const int b = blockIdx.x;
+    const int tile_x = blockIdx.y, tile_y = hoc_centre_out(blockIdx.z, gridDim.z);
     const bool K4 = b < k4_samples;
     const int list_all = K4 ? 1 : list_all_rest;
     const int r = b + G.row_offset;
@@ -536,9 +538,9 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     const HocPairBwdDir &D = G.dir[r < G.pairs ? 1 : 0]; /* render 1 <- direction 1, render 2 <- direction 0 */
     const int H = G.H, W = G.W;
     const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int y_img = blockIdx.y * 8 + ty; /* image row (rows flipped): raster row yi = S - 1 - y_img */
+    const int y_img = tile_y * 8 + ty; /* image row (rows flipped): raster row yi = S - 1 - y_img */
     const int yi = S - 1 - y_img;
-    const int x0 = blockIdx.x * 128 + lane * 4;
+    const int x0 = tile_x * 128 + lane * 4;
     const int y_first = (row_lo != nullptr) ? row_lo[b] : 0;
     const bool in = y_img < S && x0 < S && yi >= y_first;
     if (threadIdx.x < 128) {
@@ -575,7 +577,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         for (int i = threadIdx.x; i < n_valid; i += 256) {
             const int loc = s_list[i];
             const int t = loc >> 2, j = loc & 3;
-            const int y = blockIdx.y * 8 + (t >> 5), x = blockIdx.x * 128 + (t & 31) * 4 + j;
+            const int y = tile_y * 8 + (t >> 5), x = tile_x * 128 + (t & 31) * 4 + j;
             float gfx, gfy;
             hoc_pair_bwd_pixel(D, bp, x, y, H, W, G.inv_w, G.inv_h, scale, &gfx, &gfy);
             const float m = D.mult[(long)bp * npix + (long)y * W + x]; /* hoc_flow_finalize_backward_kernel */
@@ -641,7 +643,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         s_base = (tot > 0) ? atomicAdd(cov_count + b, tot) : 0;
     }
     if (K4 && threadIdx.x < 128) {
-        const int xi = blockIdx.x * 128 + threadIdx.x;
+        const int xi = tile_x * 128 + threadIdx.x;
         if (xi < S && s_chi[threadIdx.x] >= 0) {
             int *e = ext + (long)b * 4 * S;
             atomicMax(&e[EXT_COL_LO * S + xi], S - s_clo[threadIdx.x]);
@@ -1328,7 +1330,7 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
          * gradient have work */
         const uintptr_t al = (uintptr_t)face_index_map | (uintptr_t)grad_rgb | (uintptr_t)g_alpha;
         if (pair_src != nullptr) { /* frame-pair path: the incoming gradient is computed by the scan pass itself */
-            dim3 pg4((S + 127) / 128, (S + 7) / 8, B);
+            dim3 pg4(B, (S + 127) / 128, (S + 7) / 8);
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan_pair_kernel<<<pg4, 256, 0, st>>>(
                            face_index_map, *pair_src, grad_rgb_out, S, k4_samples, want_depth ? 1 : 0, w.ext, w.cov_count,

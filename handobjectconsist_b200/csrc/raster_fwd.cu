@@ -377,10 +377,11 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
 {
     __shared__ unsigned short s_list[RS4_THREADS * 4];
     __shared__ int s_n;
-    const int b = blockIdx.y;
+    const int b = blockIdx.x; /* sample fastest, chunks of rows from the image centre outwards (hoc_centre_out) */
+    const int chunk = hoc_centre_out(blockIdx.y, gridDim.y);
     const int S4 = S >> 2;
     const long npix = (long)S * S;
-    const int q = blockIdx.x * RS4_THREADS + threadIdx.x;
+    const int q = chunk * RS4_THREADS + threadIdx.x;
     if (threadIdx.x == 0)
         s_n = 0;
     __syncthreads();
@@ -423,7 +424,7 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
     const int n = s_n;
     for (int i = threadIdx.x; i < n; i += RS4_THREADS) {
         const int loc = s_list[i];
-        const int qq = blockIdx.x * RS4_THREADS + (loc >> 2);
+        const int qq = chunk * RS4_THREADS + (loc >> 2);
         const int yi = qq / S4, xi = ((qq - yi * S4) << 2) + (loc & 3);
         const long pix = (long)yi * S + xi;
         const int fidx = (int)(unsigned)(zbuf[(long)b * npix + pix] & 0xffffffffull);
@@ -531,7 +532,7 @@ extern "C" int hoc_raster_forward_ex(const float *faces, const float *textures, 
     if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && face_inv_map == nullptr && (weight_map == nullptr || sparse_saved) &&
         ((((uintptr_t)zbuf | (uintptr_t)rgb | (uintptr_t)alpha | (uintptr_t)depth | (uintptr_t)face_index_map) & 15) == 0)) {
         const long groups = npix / 4;
-        dim3 grid4((unsigned)((groups + RS4_THREADS - 1) / RS4_THREADS), B);
+        dim3 grid4(B, (unsigned)((groups + RS4_THREADS - 1) / RS4_THREADS));
         HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
                    (hoc_raster_resolve4_kernel<<<grid4, RS4_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
                                                                            bg[0], bg[1], bg[2], background_dev, tex_vertex,
