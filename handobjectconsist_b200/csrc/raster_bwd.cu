@@ -56,9 +56,10 @@
  *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
  *   cov_list   int2   [B][S*S]       the covered pixels that have work, in tile order: (yi * S + xi, owning face) --
  *                                    the face rides along so that the cover pass starts one dependent load earlier
- *   emitters   ushort [B][2][S][3S]  the queues: position on the line | edge << 11.  3S is a hard bound: a scan is
- *                                    keyed by its inside pixel on the line, which is owned by exactly one face with
- *                                    3 edges; only the used part is ever touched */
+ *   emitters   uint   [B][2][S][3S]  the queues: position on the line | edge << 11 | owning face << 13 (the face rides
+ *                                    along so that the line pass starts one dependent load earlier).  3S is a hard
+ *                                    bound: a scan is keyed by its inside pixel on the line, which is owned by exactly
+ *                                    one face with 3 edges; only the used part is ever touched */
 struct HocBwdWorkspace {
     int *ext;
     int *cov_count;
@@ -67,7 +68,7 @@ struct HocBwdWorkspace {
     int *line_list;
     float *acc_d;
     int2 *cov_list;
-    unsigned short *emitters;
+    unsigned int *emitters;
     /* reproducible mode only (hoc_det.cuh): fixed-point accumulators of grad_faces / grad_textures / acc_d,
      * two 64-bit words per float, one contiguous zero-fill */
     unsigned long long *det_gf, *det_gt, *det_ad;
@@ -99,8 +100,8 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S, int te
     off = up(off + sizeof(int) * 2 * (size_t)B * S);
     w.cov_list = (int2 *)(p + off);
     off = up(off + sizeof(int2) * (size_t)B * S * S);
-    w.emitters = (unsigned short *)(p + off);
-    off = up(off + sizeof(unsigned short) * 2 * (size_t)B * S * 3 * (size_t)S);
+    w.emitters = (unsigned int *)(p + off);
+    off = up(off + sizeof(unsigned int) * 2 * (size_t)B * S * 3 * (size_t)S);
     w.det_gf = w.det_gt = w.det_ad = nullptr;
     w.det_bytes = 0;
     if (det) {
@@ -192,14 +193,14 @@ __device__ __forceinline__ void hoc_k4_stage_a(float ax, float ay, float bx, flo
     }
 }
 
-/* Queue the outward scans of a warp's pixels on their lines (2-byte record: position on the line | edge << 11).  Called
+/* Queue the outward scans of a warp's pixels on their lines (4-byte record: position on the line | edge << 11 | face << 13).  Called
  * by ALL 32 lanes.  Pixels that are neighbours in the list are neighbours in the image, so many lanes push on the same
  * line (a row, for axis 1): lanes are grouped by line with one MATCH, the group's leader reserves the slots with ONE
  * atomic and the first scan ever queued on a line also appends the line to the list the line pass walks.  (One atomic
  * with return per pixel was the hottest stall of the pass: 5 of its 23 us.) */
-__device__ __forceinline__ void hoc_k4_queue_push(bool push, int line, int d1p, int edge, int S,
+__device__ __forceinline__ void hoc_k4_queue_push(bool push, int line, int d1p, int edge, int fi, int S,
                                                   int *__restrict__ line_count, int *__restrict__ n_lines,
-                                                  int *__restrict__ line_list, unsigned short *__restrict__ emitters)
+                                                  int *__restrict__ line_list, unsigned int *__restrict__ emitters)
 {
     const int lane = threadIdx.x & 31;
     const unsigned grp = __match_any_sync(HOC_FULL_MASK, push ? line : -1 - lane);
@@ -214,7 +215,7 @@ __device__ __forceinline__ void hoc_k4_queue_push(bool push, int line, int d1p, 
     if (push) {
         const int pos = base + __popc(grp & ((1u << lane) - 1u));
         if (pos < 3 * S) /* cannot fail (see HocBwdWorkspace); keeps a corrupted map from overrunning */
-            emitters[(long)line * 3 * S + pos] = (unsigned short)(d1p | (edge << 11));
+            emitters[(long)line * 3 * S + pos] = (unsigned)d1p | ((unsigned)edge << 11) | ((unsigned)fi << 13);
     }
 }
 
@@ -788,7 +789,7 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                             float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
                             const int *__restrict__ cov_count, const int2 *__restrict__ cov_list,
                             float *__restrict__ acc_d, int *__restrict__ line_count, int *__restrict__ n_lines,
-                            int *__restrict__ line_list, unsigned short *__restrict__ emitters,
+                            int *__restrict__ line_list, unsigned int *__restrict__ emitters,
                             float *__restrict__ grad_faces,
                             float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gf,
                             unsigned long long *__restrict__ det_gt, unsigned long long *__restrict__ det_ad,
@@ -869,8 +870,10 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                 hoc_k4_stage_a(ax, ay, bx, by, cx, cy, edge, 1, xi, yi, M, T1);
             }
         }
-        hoc_k4_queue_push(T0.push, (b * 2 + 0) * S + T0.d0, T0.d1p, edge, S, line_count, n_lines, line_list, emitters);
-        hoc_k4_queue_push(T1.push, (b * 2 + 1) * S + T1.d0, T1.d1p, edge, S, line_count, n_lines, line_list, emitters);
+        hoc_k4_queue_push(T0.push, (b * 2 + 0) * S + T0.d0, T0.d1p, edge, fi, S, line_count, n_lines, line_list,
+                          emitters);
+        hoc_k4_queue_push(T1.push, (b * 2 + 1) * S + T1.d0, T1.d1p, edge, fi, S, line_count, n_lines, line_list,
+                          emitters);
         float O0[4] = {0.f, 0.f, 0.f, 0.f}, O1[4] = {0.f, 0.f, 0.f, 0.f};
         if (T0.need)
             hoc_load_I(M, T0.ox, T0.oy, O0);
@@ -917,13 +920,85 @@ hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__rest
     }
 }
 
+/* One queued outward scan, set up by one lane: everything the chunk loop needs. */
+struct HocLineScan {
+    float cA, cB;     /* dist to vertex A / B = c * (d1 - cross) + e: c already times 2 / S; 0 for a vertex without term */
+    float eA, eB;     /* +-eps with the sign of c * (d1 - cross), which is the same for every pixel of an outward scan
+                       * (they all lie strictly on the outside of the crossing); 1 for a vertex without term */
+    float cross;
+    float I1, I2, I3; /* colour of the inside pixel */
+    int from, to;     /* range on the line, clipped to the span of non-zero gradient */
+    int gfA, gfB;     /* element of grad_faces, -1 for a vertex without term */
+    int nchunk;
+};
+
+template <int CH>
+__device__ __forceinline__ void hoc_line_scan_setup(unsigned rec, bool valid, const float *__restrict__ faces,
+                                                    const float *__restrict__ rgb, bool has_rgb, int b, int F, int S,
+                                                    int layout, int axis, int d0, int lo, int hi, float eps,
+                                                    HocLineScan &sc)
+{
+    sc.cA = sc.cB = 0.0f;
+    sc.eA = sc.eB = 1.0f;
+    sc.cross = 0.0f;
+    sc.I1 = sc.I2 = sc.I3 = 0.0f;
+    sc.from = 0;
+    sc.to = -1;
+    sc.gfA = sc.gfB = -1;
+    sc.nchunk = 0;
+    if (!valid)
+        return;
+    const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3, fi = (int)(rec >> 13);
+    if (edge > 2 || fi >= F)
+        return; /* cannot happen (the cover pass wrote the record); keeps a corrupted queue inside the arrays */
+    const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
+    const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
+    const float *src = faces + ((long)b * F + fi) * 9;
+    const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
+    const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
+    if (has_rgb) { /* rgb of the inside pixel (its alpha is 1: folded into P) */
+        sc.I1 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 0)];
+        sc.I2 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 1)];
+        sc.I3 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 2)];
+    }
+    HocK4Edge E;
+    hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
+    int d1_chk, d1_out;
+    /* always true: the cover pass queued this column because it passed the same test */
+    if (!hoc_k4_column(&E, S, d0, &sc.cross, &d1_chk, &d1_out))
+        return;
+    sc.from = (0 < E.dir) ? max(d1_out, lo) : lo;
+    sc.to = (0 < E.dir) ? hi : min(d1_out, hi);
+    if (sc.to < sc.from)
+        return;
+    HocK4Col C;
+    hoc_k4_col(&E, S, d0, sc.cross, &C);
+    /* d1_out lies strictly outside the crossing (floor / ceil in hoc_k4_column) and the scan runs away from it: t has
+     * the sign of E.dir on the whole scan, so the reference's `dist > 0 ? dist + eps : dist - eps` is one constant */
+    const float t_first = (float)d1_out - sc.cross;
+    const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
+    if (C.hasA) {
+        sc.cA = C.cA * C.scale;
+        sc.eA = (0.0f < sc.cA * t_first) ? eps : -eps;
+        sc.gfA = gbase + ia * 3;
+    }
+    if (C.hasB) {
+        sc.cB = C.cB * C.scale;
+        sc.eB = (0.0f < sc.cB * t_first) ? eps : -eps;
+        sc.gfB = gbase + ib * 3;
+    }
+    sc.nchunk = (sc.to - sc.from + CH) / CH;
+}
+
 /*
- * Line pass.  grid (B, 2, S): one CTA per image column (axis 0) or row (axis 1) of one sample, sample fastest and
- * lines ordered from the image centre outwards: the lines that carry the most scans (meshes are centred by the crop)
- * are dispatched first, the empty border lines last.  One line per CTA is the measured optimum on B200: several
- * lines per CTA lengthen the CTA's dependent chain (count -> queue record -> face_index_map -> face -> scan), which is
- * what bounds this pass; a persistent grid walking the lines and splitting a line's scans over several CTAs were
- * measured too and lost.
+ * Line pass.  One CTA per image column (axis 0) or row (axis 1) of one sample, sample fastest and lines ordered from
+ * the image centre outwards: the lines that carry the most scans (meshes are centred by the crop) are dispatched
+ * first, the empty border lines last.  One line per CTA is the measured optimum on B200: the pass is bound by the
+ * CTA's chain of dependent loads, not by arithmetic, so the chain is kept at three levels -- (1) the line's scan count
+ * and gradient span, (2) the queue records of the first 32 scans of every warp AND the line's pixels (staged in shared
+ * memory), (3) the faces and inside pixels of those scans (the record carries the face) -- and the scans' geometry is
+ * set up while the staging of other warps is still in flight; a persistent grid walking the lines and splitting a
+ * line's scans over several CTAs were measured too and lost.
  */
 #define LN_THREADS 256
 template <int CH>
@@ -933,7 +1008,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
                            const int *__restrict__ ext, const int *__restrict__ line_count,
                            const int *__restrict__ n_lines, const int *__restrict__ line_list, int max_lines,
-                           int walk_list, int n_samples, const unsigned short *__restrict__ emitters,
+                           int walk_list, int n_samples, const unsigned int *__restrict__ emitters,
                            float *__restrict__ grad_faces,
                            unsigned long long *__restrict__ det_gf)
 {
@@ -944,160 +1019,139 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
      * gradients carry 1e-3) */
     extern __shared__ float4 s_line4[];
     /* Two ways to hand lines to CTAs (HOC_TUNE_LINE_CTAS).  walk_list = 0 (default): one CTA per line of every sample,
-     * sample fastest and lines ordered from the image centre outwards, so that the lines that carry the most scans
-     * (meshes are centred by the crop) are dispatched first and the empty border lines last; an empty line costs its
-     * CTA one load.  walk_list = 1: a fixed grid walks the list of non-empty lines the cover pass built (in the order
+     * sample fastest and lines ordered from the image centre outwards; an empty line costs its CTA one round of
+     * loads.  walk_list = 1: a fixed grid walks the list of non-empty lines the cover pass built (in the order
      * of their first scan): no empty CTAs, but no heavy-first order either -- measured 25.4 us against 23.0 at 16
      * samples of 256 x 256, where one wave holds every non-empty line anyway. */
-    const int n_list = walk_list ? min(*n_lines, max_lines) : max_lines;
-    for (int li = blockIdx.x; li < n_list; li += gridDim.x) { /* (body not re-indented: one line per turn) */
-    if (li != (int)blockIdx.x)
-        __syncthreads(); /* every warp is done with the previous line's staged span */
-    long line;
-    if (walk_list) {
-        line = line_list[li];
-    } else { /* li = (k * 2 + axis) * B + b with k the centre-out rank of the line */
-        const int bb = li % n_samples, ax_ = (li / n_samples) & 1, k = li / (2 * n_samples);
-        const int dd = (S >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1)); /* c, c-1, c+1, c-2, ...: a bijection of [0, S) */
-        line = ((long)bb * 2 + ax_) * S + dd;
-    }
-    const int d0 = (int)(line % S), axis = (int)((line / S) & 1), b = (int)(line / (2 * S));
-    const int n = min(line_count[line], 3 * S);
-    if (n == 0)
-        continue;
-    const int *e = ext + (long)b * 4 * S;
-    const int lo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
-    const int hi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0] - 1;
-    if (lo > hi)
-        continue; /* no incoming gradient anywhere on this line: every outward scan sums zeros */
-    const int len = hi - lo + 1;
+    /* (default mode: grid (samples, 2, S) -- x is dispatched fastest -- so that the CTA's line costs no division: the
+     * prologue runs in all 4 warps of all 2 B S CTAs and was HALF of the pass's instructions when it decoded a linear
+     * index with 64-bit divisions) */
+    const int n_list = walk_list ? min(*n_lines, max_lines) : 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    const unsigned short *queue = emitters + line * 3 * S;
-    const int32_t *idx = face_index_map + (long)b * S * S;
-
-    /* 1. stage the span of non-zero gradient */
-    for (int i = tid; i < len; i += T) {
-        const int d1 = lo + i;
-        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-        float4 pg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (has_rgb) {
-            const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
-                       o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
-            pg.y = g_rgb[o0];
-            pg.z = g_rgb[o1];
-            pg.w = g_rgb[o2];
-            pg.x = rgb[o0] * pg.y + rgb[o1] * pg.z + rgb[o2] * pg.w;
+    for (int li = walk_list ? (int)blockIdx.x : 0; li < n_list; li += gridDim.x) {
+        int b, axis, d0;
+        if (walk_list) {
+            if (li != (int)blockIdx.x)
+                __syncthreads(); /* every warp is done with the previous line's staged span */
+            const int l = line_list[li];
+            d0 = l % S;
+            axis = (l / S) & 1;
+            b = l / (2 * S);
+        } else {
+            b = blockIdx.x;
+            axis = blockIdx.y;
+            d0 = hoc_centre_out(blockIdx.z, S);
         }
-        if (has_alpha) {
-            const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
-            const float a = (idx[(long)yi * S + xi] >= 0) ? 1.0f : 0.0f;
-            pg.x += a * ga - ga;
-        }
-        s_line4[i] = pg;
-    }
-    __syncthreads();
+        const int line = (b * 2 + axis) * S + d0;
+        /* level 1: three independent loads */
+        const int *e = ext + (long)b * 4 * S;
+        const int n_raw = line_count[line];
+        const int lo_raw = e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
+        const int hi_raw = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0];
+        const int n = min(n_raw, 3 * S);
+        const int lo = S - lo_raw, hi = hi_raw - 1;
+        if (n == 0 || lo > hi)
+            continue; /* no scan, or no incoming gradient anywhere on this line: every outward scan sums zeros */
+        const int len = hi - lo + 1;
+        const unsigned int *queue = emitters + (long)line * 3 * S;
+        const int32_t *idx = face_index_map + (long)b * S * S;
 
-    /* 2. the scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane sets up one
-     *    scan (edge geometry, colour of the inside pixel, range) in registers; (b) the warp's scans are cut into
-     *    chunks of CH pixels and every lane sums one chunk -- it finds its scan with a 5-step search over the warp's
-     *    prefix sums and fetches the scan's constants with shuffles -- so that the lanes finish together however
-     *    different the scan lengths are.  The chunk loop is fully unrolled and branch-free: a pixel beyond the end
-     *    of the scan, or with delta <= 0, adds 0 * (1 / dist); 1 / dist is one MUFU.RCP (2 ulp: the pseudo-gradient
-     *    carries a 1e-3 tolerance and this quotient is the hot instruction of the pass).  Each chunk adds its two
-     *    vertex contributions to grad_faces. */
-    const float scale = 2.0f / (float)S;
-    const float peps = eps, neps = -eps;
-    for (int q0 = wid * 32; q0 < n; q0 += T) {
-        const int q = q0 + lane;
-        float r_cA = 0.0f, r_cB = 0.0f, r_cross = 0.0f, r_I1 = 0.0f, r_I2 = 0.0f, r_I3 = 0.0f;
-        int r_from = 0, r_to = -1, r_gfA = 0, r_gfB = 0, nchunk = 0;
-        if (q < n) {
-            const int rec = queue[q];
-            const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3;
-            const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
-            const int fi = idx[(long)yin * S + xin];
-            if (has_rgb) { /* rgb of the inside pixel (its alpha is 1: folded into P) */
-                r_I1 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 0)];
-                r_I2 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 1)];
-                r_I3 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 2)];
+        /* level 2: the records of the first round of scans, and the span of non-zero gradient into shared memory */
+        const int q_first = wid * 32 + lane;
+        const unsigned rec_first = (q_first < n) ? queue[q_first] : 0u;
+        for (int i = tid; i < len; i += T) {
+            const int d1 = lo + i;
+            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+            float4 pg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (has_rgb) {
+                const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
+                           o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
+                pg.y = g_rgb[o0];
+                pg.z = g_rgb[o1];
+                pg.w = g_rgb[o2];
+                pg.x = rgb[o0] * pg.y + rgb[o1] * pg.z + rgb[o2] * pg.w;
             }
-            if (fi >= 0) { /* always: the cover pass queues owned pixels only */
-                const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
-                const float *src = faces + ((long)b * F + fi) * 9;
-                const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
-                const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
-                HocK4Edge E;
-                hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
-                int d1_chk, d1_out;
-                /* always true: the cover pass queued this column because it passed the same test */
-                if (hoc_k4_column(&E, S, d0, &r_cross, &d1_chk, &d1_out)) {
-                    r_from = (0 < E.dir) ? max(d1_out, lo) : lo;
-                    r_to = (0 < E.dir) ? hi : min(d1_out, hi);
-                    HocK4Col C;
-                    hoc_k4_col(&E, S, d0, r_cross, &C);
-                    /* a vertex that gets no contribution: infinite distance -> 1 / dist = 0 (d1 - cross != 0) */
-                    r_cA = C.hasA ? C.cA * scale : __int_as_float(0x7f800000);
-                    r_cB = C.hasB ? C.cB * scale : __int_as_float(0x7f800000);
-                    const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
-                    r_gfA = gbase + ia * 3;
-                    r_gfB = gbase + ib * 3;
-                    if (r_to >= r_from)
-                        nchunk = (r_to - r_from + CH) / CH;
+            if (has_alpha) {
+                const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+                const float a = (idx[(long)yi * S + xi] >= 0) ? 1.0f : 0.0f;
+                pg.x += a * ga - ga;
+            }
+            s_line4[i] = pg;
+        }
+        /* level 3: faces and inside pixels of the first round, set up before the barrier */
+        HocLineScan sc;
+        hoc_line_scan_setup<CH>(rec_first, q_first < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo, hi, eps, sc);
+        __syncthreads();
+
+        /* The scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane has set up one
+         * scan in registers; (b) the warp's scans are cut into chunks of CH pixels and every lane sums one chunk -- it
+         * finds its scan with a 5-step search over the warp's prefix sums and fetches the scan's constants with
+         * shuffles -- so that the lanes finish together however different the scan lengths are.  The chunk loop is
+         * fully unrolled and branch-free: per pixel one 16-byte shared load, delta (3 FMA), both distances (one FMA
+         * each: c * kk + (c * u0 + e)) and ONE MUFU.RCP of their product (1 / dA = dB * r, 1 / dB = dA * r; 3 ulp: the
+         * pseudo-gradient carries a 1e-3 tolerance and the reciprocals were the busiest pipe of the pass).  A pixel
+         * beyond the end of the scan, or with delta <= 0, adds nothing.  Each chunk adds its two vertex
+         * contributions to grad_faces. */
+        for (int q0 = wid * 32; q0 < n; q0 += T) {
+            if (q0 != wid * 32) {
+                const int q = q0 + lane;
+                hoc_line_scan_setup<CH>(q < n ? queue[q] : 0u, q < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo,
+                                        hi, eps, sc);
+            }
+            int incl = sc.nchunk;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            const int pre = incl - sc.nchunk;
+            const int total = __shfl_sync(HOC_FULL_MASK, incl, 31);
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = min(j0 + lane, total - 1);
+                const bool live = j0 + lane < total;
+                int a = 0; /* last scan with pre <= j */
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) {
+                    const int pv = __shfl_sync(HOC_FULL_MASK, pre, (a + st) & 31);
+                    if (a + st < 32 && pv <= j)
+                        a += st;
                 }
+                /* (every shuffle stays outside any lane-dependent branch: a predicated shuffle desynchronises the warp) */
+                const int c0 = (j - __shfl_sync(HOC_FULL_MASK, pre, a)) * CH;
+                const int d1_from = __shfl_sync(HOC_FULL_MASK, sc.from, a) + c0;
+                const int to_a = __shfl_sync(HOC_FULL_MASK, sc.to, a);
+                const int left = live ? to_a - d1_from : -1; /* pixels beyond the first */
+                const float cA = __shfl_sync(HOC_FULL_MASK, sc.cA, a), cB = __shfl_sync(HOC_FULL_MASK, sc.cB, a);
+                const float eA = __shfl_sync(HOC_FULL_MASK, sc.eA, a), eB = __shfl_sync(HOC_FULL_MASK, sc.eB, a);
+                const float I1 = __shfl_sync(HOC_FULL_MASK, sc.I1, a), I2 = __shfl_sync(HOC_FULL_MASK, sc.I2, a),
+                            I3 = __shfl_sync(HOC_FULL_MASK, sc.I3, a);
+                const float u0 = (float)d1_from - __shfl_sync(HOC_FULL_MASK, sc.cross, a);
+                const int gfA = __shfl_sync(HOC_FULL_MASK, sc.gfA, a), gfB = __shfl_sync(HOC_FULL_MASK, sc.gfB, a);
+                const float dA0 = __fmaf_rn(cA, u0, eA), dB0 = __fmaf_rn(cB, u0, eB);
+                const float4 *sp = s_line4 + (d1_from - lo);
+                float gA = 0.0f, gB = 0.0f;
+#pragma unroll
+                for (int kk = 0; kk < CH; kk++) {
+                    const float4 pg = sp[kk]; /* at most CH - 1 entries past the staged span: the buffer is padded */
+                    const float delta = __fmaf_rn(-I3, pg.w, __fmaf_rn(-I2, pg.z, __fmaf_rn(-I1, pg.y, pg.x)));
+                    const float dA = __fmaf_rn(cA, (float)kk, dA0), dB = __fmaf_rn(cB, (float)kk, dB0);
+                    float t = delta * hoc_rcp_approx(dA * dB);
+                    /* (past the scan's end the product may be 0: selected away; a NaN delta propagates like the
+                     * reference's `if (!(delta <= 0))`) */
+                    t = (delta <= 0.0f || kk > left) ? 0.0f : t;
+                    gA = __fmaf_rn(-t, dB, gA);
+                    gB = __fmaf_rn(-t, dA, gB);
+                }
+                if (gA != 0.0f && gfA >= 0)
+                    hoc_accum(grad_faces, gfA, gA, det_gf);
+                if (gB != 0.0f && gfB >= 0)
+                    hoc_accum(grad_faces, gfB, gB, det_gf);
             }
         }
-        int incl = nchunk;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        const int pre = incl - nchunk;
-        const int total = __shfl_sync(HOC_FULL_MASK, incl, 31);
-        for (int j0 = 0; j0 < total; j0 += 32) {
-            const int j = min(j0 + lane, total - 1);
-            const bool live = j0 + lane < total;
-            int a = 0; /* last scan with pre <= j */
-#pragma unroll
-            for (int st = 16; st >= 1; st >>= 1) {
-                const int pv = __shfl_sync(HOC_FULL_MASK, pre, (a + st) & 31);
-                if (a + st < 32 && pv <= j)
-                    a += st;
-            }
-            /* (every shuffle stays outside any lane-dependent branch: a predicated shuffle desynchronises the warp) */
-            const int c0 = (j - __shfl_sync(HOC_FULL_MASK, pre, a)) * CH;
-            const int d1_from = __shfl_sync(HOC_FULL_MASK, r_from, a) + c0;
-            const int to_a = __shfl_sync(HOC_FULL_MASK, r_to, a);
-            const int left = live ? to_a - d1_from : -1; /* pixels beyond the first */
-            const float cA = __shfl_sync(HOC_FULL_MASK, r_cA, a), cB = __shfl_sync(HOC_FULL_MASK, r_cB, a);
-            const float I1 = __shfl_sync(HOC_FULL_MASK, r_I1, a), I2 = __shfl_sync(HOC_FULL_MASK, r_I2, a),
-                        I3 = __shfl_sync(HOC_FULL_MASK, r_I3, a);
-            const float u0 = (float)d1_from - __shfl_sync(HOC_FULL_MASK, r_cross, a);
-            const int gfA = __shfl_sync(HOC_FULL_MASK, r_gfA, a), gfB = __shfl_sync(HOC_FULL_MASK, r_gfB, a);
-            const float4 *sp = s_line4 + (d1_from - lo);
-            float gA = 0.0f, gB = 0.0f;
-#pragma unroll
-            for (int kk = 0; kk < CH; kk++) {
-                const float4 pg = sp[kk]; /* at most CH - 1 entries past the staged span: the buffer is padded */
-                float delta = pg.x - __fmaf_rn(I3, pg.w, __fmaf_rn(I2, pg.z, I1 * pg.y));
-                delta = (delta <= 0.0f || kk > left) ? 0.0f : delta;
-                const float u = u0 + (float)kk;
-                float dA = cA * u, dB = cB * u;
-                dA += (0.0f < dA) ? peps : neps;
-                dB += (0.0f < dB) ? peps : neps;
-                gA = __fmaf_rn(-delta, hoc_rcp_approx(dA), gA);
-                gB = __fmaf_rn(-delta, hoc_rcp_approx(dB), gB);
-            }
-            if (gA != 0.0f)
-                hoc_accum(grad_faces, gfA, gA, det_gf);
-            if (gB != 0.0f)
-                hoc_accum(grad_faces, gfB, gB, det_gf);
-        }
-    }
     } /* lines of the list */
 }
 
@@ -1130,7 +1184,7 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
     const size_t smem = ((size_t)S + 16) * sizeof(float4); /* + padding for the unrolled chunk loop; <= 33 KB */
     const long max_lines = 2l * B * S;
     const int walk = g_line_ctas > 0 ? 1 : 0;
-    const unsigned grid = (unsigned)(walk ? (max_lines < g_line_ctas ? max_lines : g_line_ctas) : max_lines);
+    const dim3 grid = walk ? dim3((unsigned)(max_lines < g_line_ctas ? max_lines : g_line_ctas)) : dim3(B, 2, S);
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
                (hoc_raster_bwd_line_kernel<CH><<<grid, g_line_threads, smem, st>>>(
                    faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,
@@ -1286,6 +1340,9 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
                   layout);
     HOC_CHECK_ARG(B <= 65535, "hoc_raster_backward: batch %d exceeds 65535", B); /* grid.y / grid.z limits */
     HOC_CHECK_ARG(F < (1 << 29), "hoc_raster_backward: face count %d exceeds 2^29", F);
+    /* (the scan records of the pseudo-gradient carry the face in 19 bits) */
+    HOC_CHECK_ARG(F <= (1 << 19) || grad_faces == nullptr || geom_samples == 0 || (grad_rgb == nullptr && grad_alpha == nullptr),
+                  "hoc_raster_backward: face count %d exceeds 2^19 (limit with a geometry gradient)", F);
     HOC_CHECK_ARG(grad_textures == nullptr || ts >= 1, "hoc_raster_backward: texture_size %d", ts);
     HOC_CHECK_ARG(grad_rgb == nullptr || rgb != nullptr, "hoc_raster_backward: grad_rgb given without rgb");
     if (B == 0 || F == 0)
