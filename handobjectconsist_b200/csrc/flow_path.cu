@@ -34,8 +34,8 @@ hoc_mesh_gather_kernel(const float *__restrict__ verts, const float *__restrict_
 {
     if (clear != nullptr) { /* 0xff fill of the z-buffer keys of the forward that follows, spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * GA_THREADS;
-        for (long i = ((long)blockIdx.y * gridDim.x + blockIdx.x) * GA_THREADS + threadIdx.x; i < n_clear; i += nthreads)
-            clear[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        hoc_fill16(clear, n_clear, ((long)blockIdx.y * gridDim.x + blockIdx.x) * GA_THREADS + threadIdx.x, nthreads,
+                   0xffffffffu);
     }
     /* per-face records are staged in shared memory and written out as contiguous, coalesced runs */
     __shared__ __align__(16) float s_tex[GA_THREADS * 24];
@@ -218,20 +218,31 @@ struct HocRender {
 };
 
 /* thresholded alpha x keep-mask of the ignored faces at image pixel (x, y) (opticalflow.py:109-116) */
-__device__ __forceinline__ float hoc_fp_mask(const HocRender &R, int b, int S, int x, int y,
-                                             const int *__restrict__ ignore, int n_ignore, float *alpha_out)
+/* The ignored faces: list + the range [lo, hi] its entries lie in (a face outside the range is kept without a walk
+ * over the list: three mask evaluations per covered pixel times 14 ignored faces were 15 % of the finalize pass). */
+struct HocIgnore {
+    const int *list;
+    int n, lo, hi;
+};
+
+__device__ __forceinline__ bool hoc_fp_keep(const HocIgnore &G, int fidx)
+{
+    bool keep = true;
+    if (fidx >= G.lo && fidx <= G.hi)
+        for (int k = 0; k < G.n; k++)
+            keep = keep && (fidx != G.list[k]);
+    return keep;
+}
+
+__device__ __forceinline__ float hoc_fp_mask(const HocRender &R, int b, int S, int x, int y, const HocIgnore &G,
+                                             float *alpha_out)
 {
     const long po = ((long)b * S + y) * S + x;
     const float a = R.alpha[po];
     *alpha_out = a;
     float m = (a > 0.99999f) ? 1.0f : 0.0f;
-    if (n_ignore > 0 && m != 0.0f) { /* the keep-mask only matters where alpha passed the threshold */
-        const int fidx = R.idx[((long)b * S + (S - 1 - y)) * S + x];
-        bool keep = true;
-        for (int k = 0; k < n_ignore; k++)
-            keep = keep && (fidx != ignore[k]);
-        m = __fmul_rn(m, keep ? 1.0f : 0.0f);
-    }
+    if (G.n > 0 && m != 0.0f) /* the keep-mask only matters where alpha passed the threshold */
+        m = __fmul_rn(m, hoc_fp_keep(G, R.idx[((long)b * S + (S - 1 - y)) * S + x]) ? 1.0f : 0.0f);
     return m;
 }
 
@@ -259,17 +270,12 @@ __device__ __forceinline__ void hoc_fp_flow(const HocRender &R, int b, int S, in
  * mult = d flow / d rgb. */
 __device__ __forceinline__ void hoc_finalize_pixel(const HocRender &Ra, const HocRender &Rb, bool second, int b, int S,
                                                    int rx, int ry, float alpha_r, float rgb0, float rgb1,
-                                                   const int *__restrict__ ignore, int n_ignore, int mask_occlusions,
+                                                   const HocIgnore &G, int mask_occlusions,
                                                    float distance_thresh, float *fx_out, float *fy_out, float *mult_out)
 {
     float mt_r = (alpha_r > 0.99999f) ? 1.0f : 0.0f; /* thresholded alpha x keep-mask (hoc_fp_mask on preloaded alpha) */
-    if (n_ignore > 0 && mt_r != 0.0f) {
-        const int fidx = Ra.idx[((long)b * S + (S - 1 - ry)) * S + rx];
-        bool keep = true;
-        for (int k = 0; k < n_ignore; k++)
-            keep = keep && (fidx != ignore[k]);
-        mt_r = __fmul_rn(mt_r, keep ? 1.0f : 0.0f);
-    }
+    if (G.n > 0 && mt_r != 0.0f)
+        mt_r = __fmul_rn(mt_r, hoc_fp_keep(G, Ra.idx[((long)b * S + (S - 1 - ry)) * S + rx]) ? 1.0f : 0.0f);
     float fx = __fmul_rn(rgb0, mt_r), fy = __fmul_rn(rgb1, mt_r);
     float mfinal = mt_r;
     if (mask_occlusions && (second ? alpha_r : mt_r) == 0.0f && fx == fx && fy == fy) {
@@ -287,7 +293,7 @@ __device__ __forceinline__ void hoc_finalize_pixel(const HocRender &Ra, const Ho
         int sx, sy;
         if (hoc_fp_nearest(rx, ry, fx, fy, S, &sx, &sy)) {
             float alpha_s;
-            const float mt_s = hoc_fp_mask(Rb, b, S, sx, sy, ignore, n_ignore, &alpha_s);
+            const float mt_s = hoc_fp_mask(Rb, b, S, sx, sy, G, &alpha_s);
             float sfx, sfy;
             hoc_fp_flow(Rb, b, S, sx, sy, mt_s, &sfx, &sfy);
             const float m_s = second ? mt_s : alpha_s; /* mask of the OTHER render in the check */
@@ -295,7 +301,7 @@ __device__ __forceinline__ void hoc_finalize_pixel(const HocRender &Ra, const Ho
             int qx, qy;
             if (hoc_fp_nearest(sx, sy, sfx, sfy, S, &qx, &qy)) {
                 float alpha_q;
-                const float mt_q = hoc_fp_mask(Ra, b, S, qx, qy, ignore, n_ignore, &alpha_q);
+                const float mt_q = hoc_fp_mask(Ra, b, S, qx, qy, G, &alpha_q);
                 g0 = __fmul_rn((float)qx, inv_s);
                 g1 = __fmul_rn((float)qy, inv_s);
                 g2 = second ? alpha_q : mt_q;
@@ -336,7 +342,9 @@ hoc_flow_finalize_kernel(HocRender R1, HocRender R2, int S, int H, int W, const 
     const HocRender &Rb = second ? R1 : R2;
     const long po = ((long)b * S + ry) * S + rx, co = (((long)b * 3) * S + ry) * S + rx;
     float fx, fy, mu;
-    hoc_finalize_pixel(Ra, Rb, second, b, S, rx, ry, Ra.alpha[po], Ra.rgb[co], Ra.rgb[co + (long)S * S], ignore, n_ignore,
+    HocIgnore G; /* (this one-pixel-per-thread kernel walks the list for every covered pixel) */
+    G.list = ignore; G.n = n_ignore; G.lo = -0x7fffffff - 1; G.hi = 0x7fffffff;
+    hoc_finalize_pixel(Ra, Rb, second, b, S, rx, ry, Ra.alpha[po], Ra.rgb[co], Ra.rgb[co + (long)S * S], G,
                        mask_occlusions, distance_thresh, &fx, &fy, &mu);
     const long o = ((long)b * H + ry) * W + rx;
     *reinterpret_cast<float2 *>((second ? flow21 : flow12) + o * 2) = make_float2(fx, fy);
@@ -374,7 +382,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
      * dependent gathers (ignore table, two occlusion look-ups, 24 bilinear taps), and a thread that ran its own four
      * covered pixels one after the other would be the tail of the whole launch. */
     __shared__ unsigned short s_list[FW_THREADS * 4];
-    __shared__ int s_n;
+    __shared__ int s_n, s_ig_lo, s_ig_hi;
     const int b = blockIdx.x >> 1; /* (sample, direction) fastest, chunks of rows from the image centre outwards */
     const bool second = (blockIdx.x & 1) != 0;
     const int chunk = hoc_centre_out(blockIdx.y, gridDim.y);
@@ -383,11 +391,20 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
     const HocFinWarpDir &D = second ? D1 : D0;
     const int W4 = W >> 2, npix = H * W;
     const int q = chunk * FW_THREADS + threadIdx.x;
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
         s_n = 0;
+        s_ig_lo = 0x7fffffff;
+        s_ig_hi = -0x7fffffff - 1;
+    }
     __syncthreads();
+    for (int k = threadIdx.x; k < n_ignore; k += FW_THREADS) { /* range of the ignored faces, for phase B */
+        const int f = ignore[k];
+        atomicMin(&s_ig_lo, f);
+        atomicMax(&s_ig_hi, f);
+    }
     if (q < H * W4) {
-        const int ry = q / W4, x0 = (q - ry * W4) << 2;
+        int xq;
+        const int ry = hoc_div_small(q, W4, &xq), x0 = xq << 2;
         const long po = ((long)b * S + ry) * S + x0, co = (((long)b * 3) * S + ry) * S + x0;
         const float4 a4 = *reinterpret_cast<const float4 *>(Ra.alpha + po);
         const float4 r4 = *reinterpret_cast<const float4 *>(Ra.rgb + co);
@@ -415,14 +432,17 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
      * multiple of 2^-28 FIRST and the terms are added as integers (associative): same bits every run. */
     unsigned long long my_fix = 0ull;
     int my_cnt = 0;
+    HocIgnore G;
+    G.list = ignore; G.n = n_ignore; G.lo = s_ig_lo; G.hi = s_ig_hi;
     for (int i = threadIdx.x; i < n; i += FW_THREADS) {
         const int loc = s_list[i];
         const int qq = chunk * FW_THREADS + (loc >> 2);
-        const int ry = qq / W4, rx = ((qq - ry * W4) << 2) + (loc & 3);
+        int xq;
+        const int ry = hoc_div_small(qq, W4, &xq), rx = (xq << 2) + (loc & 3);
         const long po = ((long)b * S + ry) * S + rx, co = (((long)b * 3) * S + ry) * S + rx;
         float fx, fy, mu;
-        hoc_finalize_pixel(Ra, Rb, second, b, S, rx, ry, Ra.alpha[po], Ra.rgb[co], Ra.rgb[co + (long)S * S], ignore,
-                           n_ignore, 1, distance_thresh, &fx, &fy, &mu);
+        hoc_finalize_pixel(Ra, Rb, second, b, S, rx, ry, Ra.alpha[po], Ra.rgb[co], Ra.rgb[co + (long)S * S], G, 1,
+                           distance_thresh, &fx, &fy, &mu);
         const long pix = (long)ry * W + rx;
         const long o = (long)b * npix + pix;
         *reinterpret_cast<float2 *>(D.flow + o * 2) = make_float2(fx, fy);
@@ -753,10 +773,8 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
     {
         const long nthreads = (long)gridDim.x * gridDim.y * PF_THREADS;
         const long t0 = ((long)blockIdx.y * gridDim.x + blockIdx.x) * PF_THREADS + threadIdx.x;
-        for (long i = t0; i < n_clear; i += nthreads) /* z-buffer keys of the forward that follows */
-            clear[i] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        for (long i = t0; i < n_zero; i += nthreads) /* small accumulators of later kernels (the loss sums) */
-            zero[i] = make_uint4(0u, 0u, 0u, 0u);
+        hoc_fill16(clear, n_clear, t0, nthreads, 0xffffffffu); /* z-buffer keys of the forward that follows */
+        hoc_fill16(zero, n_zero, t0, nthreads, 0u);           /* small accumulators of later kernels (the loss sums) */
     }
     if (blockIdx.x == gridDim.x - 1 && row_lo != nullptr) {
         /* The last CTA of every sample computes the pair's RASTER ROW WINDOW (the reference rasterises the
@@ -817,7 +835,10 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
         return;
     }
     /* staged records of this CTA's faces: [kind][thread][9], kind = faces1, tex1, faces2, tex2 */
-    __shared__ float s_rec[4][PF_THREADS * 9];
+    /* records of (faces 1, textures 1, faces 2, textures 2), in stored winding [0..3] and reversed winding [4..7]: every
+     * output run is then a plain copy with 16-byte stores (a shared copy loop that un-permuted the reversed records
+     * with a division by 9 per float was 45 % of this kernel's instructions) */
+    __shared__ __align__(16) float s_rec[8][PF_THREADS * 9];
     const int F = Fh + Fo, V = Vh + Vo;
     const int Fout = fill_back ? 2 * F : F;
     const int f0 = blockIdx.x * PF_THREADS;
@@ -853,35 +874,42 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
             hoc_proj2d(K2, v2, &u2, &w2, &hz);
             HocProj P;
             hoc_ndc_project(K1, R, t, d, C.orig_size, v1, &P);
-            float *r = &s_rec[0][threadIdx.x * 9 + 3 * k];
-            r[0] = P.ndc[0]; r[1] = P.ndc[1]; r[2] = P.ndc[2];
-            r = &s_rec[1][threadIdx.x * 9 + 3 * k];
-            r[0] = u2 - u1; r[1] = w2 - w1; r[2] = 1.0f;
+            const int at = threadIdx.x * 9 + 3 * k, rt = threadIdx.x * 9 + 3 * (2 - k);
+            const float t12[3] = {u2 - u1, w2 - w1, 1.0f}, t21[3] = {u1 - u2, w1 - w2, 1.0f};
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                s_rec[0][at + c] = s_rec[4][rt + c] = P.ndc[c];
+                s_rec[1][at + c] = s_rec[5][rt + c] = t12[c];
+                s_rec[3][at + c] = s_rec[7][rt + c] = t21[c];
+            }
             hoc_ndc_project(K2, R, t, d, C.orig_size, v2, &P);
-            r = &s_rec[2][threadIdx.x * 9 + 3 * k];
-            r[0] = P.ndc[0]; r[1] = P.ndc[1]; r[2] = P.ndc[2];
-            r = &s_rec[3][threadIdx.x * 9 + 3 * k];
-            r[0] = u1 - u2; r[1] = w1 - w2; r[2] = 1.0f;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                s_rec[2][at + c] = s_rec[6][rt + c] = P.ndc[c];
         }
     }
     __syncthreads();
     const int nf = min(PF_THREADS, F - f0);
     if (nf <= 0)
         return;
+    const int nfl = nf * 9;
 #pragma unroll
-    for (int kind = 0; kind < 4; kind++) {
+    for (int kind = 0; kind < 8; kind++) {
+        if (kind >= 4 && !fill_back)
+            break;
         float *base = (kind & 1) ? tex_out : faces_out;
-        const long row = (kind >= 2) ? (long)B + b : (long)b; /* render 2 lives in the second half of the batch */
-        float *front = base + (row * Fout + f0) * 9;
-        for (int i = threadIdx.x; i < nf * 9; i += PF_THREADS)
-            front[i] = s_rec[kind][i];
-        if (fill_back) { /* reversed winding (v2, v1, v0): vertices 0 and 2 of the record swap */
-            float *back = base + (row * Fout + F + f0) * 9;
-            for (int i = threadIdx.x; i < nf * 9; i += PF_THREADS) {
-                const int fl = i / 9, j = i - fl * 9;
-                const int src = (j < 3) ? j + 6 : ((j < 6) ? j : j - 6);
-                back[i] = s_rec[kind][fl * 9 + src];
-            }
+        const long row = (kind & 2) ? (long)B + b : (long)b; /* render 2 lives in the second half of the batch */
+        /* reversed winding (v2, v1, v0) in the second half of the faces */
+        float *dst = base + (row * Fout + (kind >= 4 ? F : 0) + f0) * 9;
+        const float *src = s_rec[kind];
+        if ((((uintptr_t)dst) & 15) == 0) {
+            for (int i = threadIdx.x; i < (nfl >> 2); i += PF_THREADS)
+                reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(src)[i];
+            if ((int)threadIdx.x < (nfl & 3))
+                dst[(nfl & ~3) + threadIdx.x] = src[(nfl & ~3) + threadIdx.x];
+        } else {
+            for (int i = threadIdx.x; i < nfl; i += PF_THREADS)
+                dst[i] = src[i];
         }
     }
 }

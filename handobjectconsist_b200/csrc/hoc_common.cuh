@@ -63,6 +63,59 @@ __device__ __forceinline__ int hoc_centre_out(int k, int n)
     return (n >> 1) + ((k & 1) ? -((k + 1) >> 1) : (k >> 1));
 }
 
+/* q / d (remainder in *rem) for 0 <= q < 2^22, 1 <= d <= 2^11 without the ~20-instruction integer division: a float
+ * estimate (one MUFU.RCP) and one correction step (the estimate is off by at most one). */
+__device__ __forceinline__ int hoc_div_small(int q, int d, int *rem)
+{
+    float inv;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"((float)d));
+    int k = (int)(((float)q + 0.5f) * inv);
+    int r = q - k * d;
+    if (r < 0) {
+        k--;
+        r += d;
+    } else if (r >= d) {
+        k++;
+        r -= d;
+    }
+    *rem = r;
+    return k;
+}
+
+/* Grid-wide fill of n 16-byte words with the 32-bit pattern v, spread over nthreads threads (t0: this thread's linear
+ * id).  The loop is controlled in 32 bits whenever the sizes allow: the 64-bit form of these loops (compare chains of
+ * the unrolled body) was 35 % of the scan pass's instructions. */
+__device__ __forceinline__ void hoc_fill16(uint4 *__restrict__ p, long n, long t0, long nthreads, unsigned v)
+{
+    const uint4 w = make_uint4(v, v, v, v);
+    if (n < 0x7fffffffl && nthreads < 0x3fffffffl) {
+        const unsigned n32 = (unsigned)(n > 0 ? n : 0), step = (unsigned)nthreads;
+#pragma unroll 1
+        for (unsigned i = (unsigned)t0; i < n32; i += step)
+            p[i] = w;
+    } else {
+#pragma unroll 1
+        for (long i = t0; i < n; i += nthreads)
+            p[i] = w;
+    }
+}
+
+/* Grid-wide zero-fill of n floats (any 4-byte alignment): scalar head and tail, 16-byte stores in between. */
+__device__ __forceinline__ void hoc_zero_floats(float *__restrict__ p, long n, long t0, long nthreads)
+{
+    if (n <= 0)
+        return;
+    long head = (long)(((16u - (unsigned)((uintptr_t)p & 15u)) & 15u) >> 2);
+    head = head < n ? head : n;
+    if (t0 < head)
+        p[t0] = 0.0f;
+    float *q = p + head;
+    const long m = n - head, m4 = m >> 2;
+    hoc_fill16(reinterpret_cast<uint4 *>(q), m4, t0, nthreads, 0u);
+    if (t0 < (m & 3))
+        q[(m4 << 2) + t0] = 0.0f;
+}
+
 __device__ __forceinline__ float hoc_warp_sum(float v)
 {
 #pragma unroll

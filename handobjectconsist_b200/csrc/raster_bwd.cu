@@ -268,12 +268,9 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 32 +
                         threadIdx.x;
-        for (long i = t0; i < n_a; i += nthreads)
-            zero_a[i] = 0.0f;
-        for (long i = t0; i < n_b; i += nthreads)
-            zero_b[i] = 0.0f;
-        for (long i = t0; i < n_c; i += nthreads) /* a buffer of the caller's NEXT kernel (hoc_mesh_scatter's outputs) */
-            zero_c[i] = 0.0f;
+        hoc_zero_floats(zero_a, n_a, t0, nthreads);
+        hoc_zero_floats(zero_b, n_b, t0, nthreads);
+        hoc_zero_floats(zero_c, n_c, t0, nthreads); /* (a buffer of the caller's NEXT kernel: hoc_mesh_scatter's outputs) */
     }
     __shared__ int s_lo[8][32];
     __shared__ int s_hi[8][32];
@@ -381,12 +378,9 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     {
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
-        for (long i = t0; i < n_a; i += nthreads)
-            zero_a[i] = 0.0f;
-        for (long i = t0; i < n_b; i += nthreads)
-            zero_b[i] = 0.0f;
-        for (long i = t0; i < n_c; i += nthreads)
-            zero_c[i] = 0.0f;
+        hoc_zero_floats(zero_a, n_a, t0, nthreads);
+        hoc_zero_floats(zero_b, n_b, t0, nthreads);
+        hoc_zero_floats(zero_c, n_c, t0, nthreads); /* (a buffer of the caller's NEXT kernel: hoc_mesh_scatter's outputs) */
     }
     __shared__ int s_clo[128], s_chi[128];
     __shared__ int s_wcnt[8], s_base;
@@ -518,12 +512,9 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
         /* (grid = (samples, column tiles, row tiles): sample fastest, row tiles from the image centre outwards) */
-        for (long i = t0; i < n_a; i += nthreads)
-            zero_a[i] = 0.0f;
-        for (long i = t0; i < n_b; i += nthreads)
-            zero_b[i] = 0.0f;
-        for (long i = t0; i < n_c; i += nthreads)
-            zero_c[i] = 0.0f;
+        hoc_zero_floats(zero_a, n_a, t0, nthreads);
+        hoc_zero_floats(zero_b, n_b, t0, nthreads);
+        hoc_zero_floats(zero_c, n_c, t0, nthreads); /* (a buffer of the caller's NEXT kernel: hoc_mesh_scatter's outputs) */
     }
     __shared__ int s_clo[128], s_chi[128];
     __shared__ int s_wcnt[8], s_base, s_n;
@@ -535,7 +526,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     const bool K4 = b < k4_samples;
     const int list_all = K4 ? 1 : list_all_rest;
     const int r = b + G.row_offset;
-    const int bp = r % G.pairs;                       /* the pair */
+    const int bp = r < G.pairs ? r : r - G.pairs;     /* the pair (r < 2 pairs) */
     const HocPairBwdDir &D = G.dir[r < G.pairs ? 1 : 0]; /* render 1 <- direction 1, render 2 <- direction 0 */
     const int H = G.H, W = G.W;
     const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -936,7 +927,7 @@ template <int CH>
 __device__ __forceinline__ void hoc_line_scan_setup(unsigned rec, bool valid, const float *__restrict__ faces,
                                                     const float *__restrict__ rgb, bool has_rgb, int b, int F, int S,
                                                     int layout, int axis, int d0, int lo, int hi, float eps,
-                                                    HocLineScan &sc)
+                                                    float scale, HocLineScan &sc)
 {
     sc.cA = sc.cB = 0.0f;
     sc.eA = sc.eB = 1.0f;
@@ -978,12 +969,12 @@ __device__ __forceinline__ void hoc_line_scan_setup(unsigned rec, bool valid, co
     const float t_first = (float)d1_out - sc.cross;
     const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
     if (C.hasA) {
-        sc.cA = C.cA * C.scale;
+        sc.cA = C.cA * scale; /* scale = 2 / S, divided on the host (the same IEEE quotient) */
         sc.eA = (0.0f < sc.cA * t_first) ? eps : -eps;
         sc.gfA = gbase + ia * 3;
     }
     if (C.hasB) {
-        sc.cB = C.cB * C.scale;
+        sc.cB = C.cB * scale;
         sc.eB = (0.0f < sc.cB * t_first) ? eps : -eps;
         sc.gfB = gbase + ib * 3;
     }
@@ -1001,14 +992,14 @@ __device__ __forceinline__ void hoc_line_scan_setup(unsigned rec, bool valid, co
  * line's scans over several CTAs were measured too and lost.
  */
 #define LN_THREADS 256
-template <int CH>
+template <int CH, bool WALK>
 __global__ void __launch_bounds__(LN_THREADS)
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
                            const int *__restrict__ ext, const int *__restrict__ line_count,
                            const int *__restrict__ n_lines, const int *__restrict__ line_list, int max_lines,
-                           int walk_list, int n_samples, const unsigned int *__restrict__ emitters,
+                           float scale, const unsigned int *__restrict__ emitters,
                            float *__restrict__ grad_faces,
                            unsigned long long *__restrict__ det_gf)
 {
@@ -1018,22 +1009,22 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
      * shared load and three FMAs per scanned pixel (<= 1 ulp of |P| from the reference's summation order,
      * gradients carry 1e-3) */
     extern __shared__ float4 s_line4[];
-    /* Two ways to hand lines to CTAs (HOC_TUNE_LINE_CTAS).  walk_list = 0 (default): one CTA per line of every sample,
+    /* Two ways to hand lines to CTAs (HOC_TUNE_LINE_CTAS), two instances of the kernel.  WALK = false (default): one CTA per line of every sample,
      * sample fastest and lines ordered from the image centre outwards; an empty line costs its CTA one round of
-     * loads.  walk_list = 1: a fixed grid walks the list of non-empty lines the cover pass built (in the order
+     * loads.  WALK = true: a fixed grid walks the list of non-empty lines the cover pass built (in the order
      * of their first scan): no empty CTAs, but no heavy-first order either -- measured 25.4 us against 23.0 at 16
      * samples of 256 x 256, where one wave holds every non-empty line anyway. */
     /* (default mode: grid (samples, 2, S) -- x is dispatched fastest -- so that the CTA's line costs no division: the
      * prologue runs in all 4 warps of all 2 B S CTAs and was HALF of the pass's instructions when it decoded a linear
      * index with 64-bit divisions) */
-    const int n_list = walk_list ? min(*n_lines, max_lines) : 1;
+    const int n_list = WALK ? min(*n_lines, max_lines) : 1;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    for (int li = walk_list ? (int)blockIdx.x : 0; li < n_list; li += gridDim.x) {
+    for (int li = WALK ? (int)blockIdx.x : 0; li < n_list; li += gridDim.x) {
         int b, axis, d0;
-        if (walk_list) {
+        if (WALK) {
             if (li != (int)blockIdx.x)
                 __syncthreads(); /* every warp is done with the previous line's staged span */
             const int l = line_list[li];
@@ -1083,7 +1074,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         }
         /* level 3: faces and inside pixels of the first round, set up before the barrier */
         HocLineScan sc;
-        hoc_line_scan_setup<CH>(rec_first, q_first < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo, hi, eps, sc);
+        hoc_line_scan_setup<CH>(rec_first, q_first < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo, hi, eps, scale,
+                                sc);
         __syncthreads();
 
         /* The scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane has set up one
@@ -1099,7 +1091,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
             if (q0 != wid * 32) {
                 const int q = q0 + lane;
                 hoc_line_scan_setup<CH>(q < n ? queue[q] : 0u, q < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo,
-                                        hi, eps, sc);
+                                        hi, eps, scale, sc);
             }
             int incl = sc.nchunk;
 #pragma unroll
@@ -1185,10 +1177,16 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
     const long max_lines = 2l * B * S;
     const int walk = g_line_ctas > 0 ? 1 : 0;
     const dim3 grid = walk ? dim3((unsigned)(max_lines < g_line_ctas ? max_lines : g_line_ctas)) : dim3(B, 2, S);
-    HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_raster_bwd_line_kernel<CH><<<grid, g_line_threads, smem, st>>>(
-                   faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,
-                   w.n_lines, w.line_list, (int)max_lines, walk, B, w.emitters, grad_faces, w.det_gf)));
+#define HOC_LINE_LAUNCH(WALK)                                                                                         \
+    HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,                                                                             \
+               (hoc_raster_bwd_line_kernel<CH, WALK><<<grid, g_line_threads, smem, st>>>(                             \
+                   faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,  \
+                   w.n_lines, w.line_list, (int)max_lines, 2.0f / (float)S, w.emitters, grad_faces, w.det_gf)))
+    if (walk)
+        HOC_LINE_LAUNCH(true);
+    else
+        HOC_LINE_LAUNCH(false);
+#undef HOC_LINE_LAUNCH
     return cudaSuccess;
 }
 

@@ -396,8 +396,10 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
         col[2] = bg2;
     }
     const int y_first = (row_lo != nullptr) ? row_lo[b] : 0; /* rows below the window: nothing is read or written */
-    if (q < S * S4 && q / S4 >= y_first) {
-        const int yi = q / S4, x0 = (q - yi * S4) << 2;
+    int xq = 0;
+    const int yq = (q < S * S4) ? hoc_div_small(q, S4, &xq) : 0;
+    if (q < S * S4 && yq >= y_first) {
+        const int yi = yq, x0 = xq << 2;
         const long pix = (long)yi * S + x0;
         const uint4 k01 = *reinterpret_cast<const uint4 *>(zbuf + (long)b * npix + pix);
         const uint4 k23 = *reinterpret_cast<const uint4 *>(zbuf + (long)b * npix + pix + 2);
@@ -425,7 +427,8 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
     for (int i = threadIdx.x; i < n; i += RS4_THREADS) {
         const int loc = s_list[i];
         const int qq = chunk * RS4_THREADS + (loc >> 2);
-        const int yi = qq / S4, xi = ((qq - yi * S4) << 2) + (loc & 3);
+        int xr;
+        const int yi = hoc_div_small(qq, S4, &xr), xi = (xr << 2) + (loc & 3);
         const long pix = (long)yi * S + xi;
         const int fidx = (int)(unsigned)(zbuf[(long)b * npix + pix] & 0xffffffffull);
         float w[3], inv[9], zp = far_, cc[3] = {col[0], col[1], col[2]};

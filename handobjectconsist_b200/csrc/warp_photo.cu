@@ -196,8 +196,7 @@ __global__ void hoc_pair_loss_mean_kernel(const double *__restrict__ sums_fwd, c
                                           long n_zero)
 {
     if (blockIdx.x > 0) { /* the other CTAs zero-fill a buffer of the step's BACKWARD (its rasterizer's counters) */
-        for (long i = (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < n_zero; i += (long)(gridDim.x - 1) * blockDim.x)
-            zero[i] = make_uint4(0u, 0u, 0u, 0u);
+        hoc_fill16(zero, n_zero, (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x, (long)(gridDim.x - 1) * blockDim.x, 0u);
         return;
     }
     if (threadIdx.x >= 32)
@@ -405,9 +404,9 @@ hoc_warp_photo_pair_backward_kernel(HocPairBwdDir D0, HocPairBwdDir D1, const fl
 {
     if (n_zero > 0) { /* zero-fill for the kernels that follow (counters of the rasterizer backward), spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * WPB_THREADS;
-        for (long i = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WPB_THREADS + threadIdx.x;
-             i < n_zero; i += nthreads)
-            zero[i] = make_uint4(0u, 0u, 0u, 0u);
+        hoc_fill16(zero, n_zero,
+                   (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * WPB_THREADS + threadIdx.x,
+                   nthreads, 0u);
     }
     const HocPairBwdDir &D = blockIdx.z ? D1 : D0;
     if (D.grad_rgb == nullptr && D.grad_flow == nullptr)

@@ -31,12 +31,17 @@ g = GraphedConsistStep(renderer, PyramidCriterion("l1"), (W, H), hand_face, *bat
 for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
+REPLAYS = 40
 with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
-    for i in range(3):
+    for i in range(REPLAYS):
         g.load(*batches[i % 2])
         g.replay()
     torch.cuda.synchronize()
 ev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+every = {}
+for e in ev:
+    if "Memcpy" not in e.name and "Memset" not in e.name:
+        every.setdefault(e.name.split("(")[0][:60], []).append(e.time_range.end - e.time_range.start)
 # last replay = everything after the last input copy of g.load()
 cut = max(i for i, e in enumerate(ev) if "Memcpy" in e.name)
 ev = ev[cut + 1:]
@@ -53,3 +58,11 @@ for e in ev:
 print("\nsum of kernel durations by name (overlapped streams: sums exceed the span)")
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{a[1]:8.1f} us  x{a[0]:<3d} {k}")
+
+print(f"\nmean / min duration over {REPLAYS} replays (us)")
+tot = 0.0
+for k, v in sorted(every.items(), key=lambda kv: -sum(kv[1])):
+    per = len(v) / REPLAYS
+    tot += sum(v) / REPLAYS
+    print(f"{sum(v) / len(v):8.2f} {min(v):8.2f}  x{per:<4.1f} {k}")
+print(f"{tot:8.2f}           sum of the means")
