@@ -135,8 +135,11 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
         n_surv += __popc(m);
         n_pix += __shfl_sync(HOC_FULL_MASK, incl, 31);
     }
+    static_assert(ZB_FACES_PER_WARP == 32, "one prefix-sum entry per lane");
+    if (lane >= n_surv)
+        s_pre[warp][lane] = (lane == n_surv) ? n_pix : 0x7fffffff; /* sentinels: the slot search below needs no bound */
     if (lane == 0)
-        s_pre[warp][n_surv] = n_pix;
+        s_pre[warp][ZB_FACES_PER_WARP] = (n_surv == ZB_FACES_PER_WARP) ? n_pix : 0x7fffffff;
     __syncthreads(); /* s_centre ready; orders the record writes */
 
     unsigned long long *zb = zbuf + (long)b * S * S;
@@ -152,14 +155,11 @@ hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__re
         bool hit = false;
         int packed = 0;
         if (item < n_pix) {
-            int lo = 0, hi = n_surv; /* last slot with pre[slot] <= item */
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (pre[mid] <= item)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
+            int lo = 0; /* last slot with pre[slot] <= item: branch-free descent over the padded prefix sums */
+#pragma unroll
+            for (int st = ZB_FACES_PER_WARP / 2; st >= 1; st >>= 1)
+                if (pre[lo + st] <= item)
+                    lo += st;
             const float *rec = s_rec[warp][lo];
             const int p = item - pre[lo];
             const int bw = __float_as_int(rec[20]);
