@@ -21,6 +21,9 @@ HOC_TEX_GRAD_VERTEX = 1
 HOC_TUNE_LINE_THREADS = 1
 HOC_TUNE_LINE_SEGMENT = 2
 HOC_TUNE_DETERMINISTIC = 3
+HOC_TUNE_LINE_CTAS = 4
+HOC_TUNE_PDL = 5
+HOC_TUNE_COVER_CTAS = 6
 HOC_BWD_WORKSPACE_ZEROED = 1
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers
@@ -143,6 +146,11 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _LIB = L
+        # measurement switch: HOC_B200_TUNE="key=value,key=value" (hoc_set_tuning keys of include/hoc_b200.h)
+        for item in filter(None, os.environ.get("HOC_B200_TUNE", "").split(",")):
+            key, value = item.split("=")
+            if L.hoc_set_tuning(int(key), int(value)) != 0:
+                raise HocLibraryError(f"HOC_B200_TUNE: {item}: {L.hoc_last_error().decode()}")
     return _LIB
 
 

@@ -228,11 +228,15 @@ class _PairConsistFunction(Function):
                 ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
             ctx.bws_clean = False
             grad_rgb = e(n, 3, S, S)  # scratch of the fused scan pass: the incoming gradient of the renders' rgb maps
-            grad_faces = e(n, Fr, 3, 3) if geom > 0 else None
-            grad_tex = e(n, Fr, 3, 3)
-            # grad of the NDC vertices, grad of the vertex attributes: zero-filled by the rasterizer backward's
-            # streaming pass, accumulated by the scatter after it
-            both = e(2, 2 * B, V, 3)
+            # grad_faces | grad_textures | (grad of the NDC vertices, grad of the vertex attributes), back to back: ONE
+            # region for the zero-fill of the rasterizer backward's streaming pass (the last one is accumulated by the
+            # scatter after it)
+            n_f = n * Fr * 9
+            flat = e((n_f if geom > 0 else 0) + n_f + 2 * 2 * B * V * 3)
+            o = n_f if geom > 0 else 0
+            grad_faces = flat[:n_f].view(n, Fr, 3, 3) if geom > 0 else None
+            grad_tex = flat[o:o + n_f].view(n, Fr, 3, 3)
+            both = flat[o + n_f:].view(2, 2 * B, V, 3)
             _lib.check(L.hoc_pair_backward_raster(
                 _lib.ptr(ir), _lib.ptr(im), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr_pair(valid[0], valid[1]),
                 _lib.ptr(sums), _lib.ptr(mult[0]), _lib.ptr(mult[1]), _lib.ptr(gl), _lib.ptr(gm), B, H, W,

@@ -112,6 +112,7 @@ hoc_mesh_scatter_kernel(const float *__restrict__ grad_faces, const float *__res
                         float *__restrict__ grad_verts, float *__restrict__ grad_attrs,
                         unsigned long long *__restrict__ det_v, unsigned long long *__restrict__ det_a)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     const int Fo = fill_back ? 2 * F : F;
     const int fo = blockIdx.x * FP_THREADS + threadIdx.x;
     const int b = blockIdx.y;
@@ -376,6 +377,7 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
                               const int *__restrict__ ignore, int n_ignore, float distance_thresh, float inv_w,
                               float inv_h, float thresh)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     /* Two phases per CTA (4 pixels per thread).  A: every thread streams its four pixels -- 16-byte loads of alpha and the two
      * colour planes, 16-byte stores of the (zero) outputs -- and notes the pixels a mesh covers in a shared list.
      * B: the listed pixels (a few per cent, clustered in a few CTAs) are dealt ONE PER THREAD: each carries a chain of
@@ -770,6 +772,7 @@ hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__
                       uint4 *__restrict__ zero, long n_zero, int *__restrict__ row_lo, int S, int crop_h,
                       int geom_window)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     {
         const long nthreads = (long)gridDim.x * gridDim.y * PF_THREADS;
         const long t0 = ((long)blockIdx.y * gridDim.x + blockIdx.x) * PF_THREADS + threadIdx.x;
@@ -923,6 +926,7 @@ hoc_pair_back_kernel(const float *__restrict__ hand1, const float *__restrict__ 
                      const float *__restrict__ g_ndc, const float *__restrict__ g_attr, int has_ndc1, int has_ndc2,
                      int has_a12, int has_a21, float *__restrict__ grad_v1, float *__restrict__ grad_v2)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     const int b = blockIdx.y;
     const int vi = blockIdx.x * FP_THREADS + threadIdx.x;
     const int V = Vh + Vo;
@@ -1071,7 +1075,7 @@ extern "C" int hoc_mesh_scatter_ws(const float *grad_faces, const float *grad_te
     const int Fo = fill_back ? 2 * F : F;
     dim3 grid((Fo + FP_THREADS - 1) / FP_THREADS, B);
     HOC_LAUNCH(HOC_K_MESH_SCATTER, st,
-               (hoc_mesh_scatter_kernel<<<grid, FP_THREADS, 0, st>>>(grad_faces, grad_textures, faces_idx, V, F,
+               (hoc_launch_pdl((hoc_mesh_scatter_kernel), grid, FP_THREADS, 0, st, grad_faces, grad_textures, faces_idx, V, F,
                                                                      fill_back, tex_grad_mode, grad_verts, grad_attrs,
                                                                      det_v, det_a)));
     HOC_CHECK_LAUNCH("hoc_mesh_scatter_kernel");
@@ -1241,7 +1245,7 @@ extern "C" int hoc_pair_front(const float *hand1, const float *obj1, const float
                             orig_size);
     dim3 grid((Fh + Fo + PF_THREADS - 1) / PF_THREADS + 1, B); /* + the row-window CTA of every sample */
     HOC_LAUNCH(HOC_K_PAIR_FRONT, st,
-               (hoc_pair_front_kernel<<<grid, PF_THREADS, 0, st>>>(hand1, obj1, hand2, obj2, hand_faces,
+               (hoc_launch_pdl((hoc_pair_front_kernel), grid, PF_THREADS, 0, st, hand1, obj1, hand2, obj2, hand_faces,
                                                                    hand_faces_batched, obj_faces, C, B, Vh, Vo, Fh, Fo,
                                                                    fill_back, faces_out, textures_out, face_table,
                                                                    (uint4 *)clear, (long)(clear_bytes / 16),
@@ -1269,7 +1273,7 @@ extern "C" int hoc_pair_back(const float *hand1, const float *obj1, const float 
                             orig_size);
     dim3 grid((Vh + Vo + FP_THREADS - 1) / FP_THREADS, B);
     HOC_LAUNCH(HOC_K_PAIR_BACK, (cudaStream_t)stream,
-               (hoc_pair_back_kernel<<<grid, FP_THREADS, 0, (cudaStream_t)stream>>>(
+               (hoc_launch_pdl((hoc_pair_back_kernel), grid, FP_THREADS, 0, (cudaStream_t)stream, 
                    hand1, obj1, hand2, obj2, C, B, Vh, Vo, grad_ndc, grad_attrs, has_ndc1, has_ndc2, has_attrs12,
                    has_attrs21, grad_verts1, grad_verts2)));
     HOC_CHECK_LAUNCH("hoc_pair_back_kernel");
@@ -1307,7 +1311,7 @@ extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, co
     const long groups = (long)H * (W / 4);
     dim3 grid(2 * B, (unsigned)((groups + FW_THREADS - 1) / FW_THREADS));
     HOC_LAUNCH(HOC_K_FLOW_FINALIZE, (cudaStream_t)stream,
-               (hoc_flow_finalize_warp_kernel<<<grid, FW_THREADS, 0, (cudaStream_t)stream>>>(
+               (hoc_launch_pdl((hoc_flow_finalize_warp_kernel), grid, FW_THREADS, 0, (cudaStream_t)stream, 
                    R1, R2, D0, D1, S, H, W, ignore_faces, n_ignore, distance_thresh,
                    1.0f / (float)(W - 1 > 1 ? W - 1 : 1), 1.0f / (float)(H - 1 > 1 ? H - 1 : 1), thresh)));
     HOC_CHECK_LAUNCH("hoc_flow_finalize_warp_kernel");

@@ -10,6 +10,7 @@
 
 /* reproducible accumulation (hoc_det.cuh): set by hoc_set_tuning(HOC_TUNE_DETERMINISTIC, 0 / 1) */
 int g_hoc_deterministic = 0;
+int g_hoc_pdl = 0; /* programmatic dependent launch of the frame-pair kernels (HOC_TUNE_PDL) */
 
 __global__ void __launch_bounds__(256)
 hoc_det_flush_kernel(const unsigned long long *__restrict__ det, long n, float *__restrict__ dst, int add)

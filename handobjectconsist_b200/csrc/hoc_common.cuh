@@ -22,6 +22,40 @@ void hoc_note_launch(int kernel_id, cudaStream_t st, int phase);
         hoc_note_launch(kernel_id, st, 1); \
     } while (0)
 
+/* Programmatic dependent launch (sm_90+): the kernels of the frame-pair step are launched with the "programmatic
+ * stream serialization" attribute and start with hoc_pdl_sync() -- `griddepcontrol.launch_dependents` (the NEXT kernel
+ * of the stream may be scheduled as soon as every CTA of this one has started) then `griddepcontrol.wait` (blocks until
+ * the PREVIOUS kernel has completed and its writes are visible).  No kernel touches global memory before its wait, so
+ * the stream's semantics are unchanged; what overlaps is the launch, the CTA scheduling and the prologue of kernel
+ * N + 1 with the tail of kernel N (a captured graph keeps the edges as programmatic dependencies).  Without the
+ * attribute both instructions are no-ops.  hoc_set_tuning(HOC_TUNE_PDL, 0) switches the attribute off. */
+extern int g_hoc_pdl;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void hoc_pdl_sync()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t hoc_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                         Args &&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_hoc_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #define HOC_CHECK_ARG(cond, ...)        \
     do {                                \
         if (!(cond)) {                  \

@@ -508,6 +508,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
                                 long n_a, float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                                 const int *__restrict__ row_lo)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     {
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.x;
@@ -546,19 +547,30 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     __syncthreads();
     /* phase A: face indices of the four pixels; the valid pixels of the crop are noted in the shared list */
     int fis[4] = {-1, -1, -1, -1};
+    unsigned vb = 0u;
     const long npix = (long)H * W;
     if (in) {
         const int4 f4 = *reinterpret_cast<const int4 *>(face_index_map + ((long)b * S + yi) * S + x0);
         fis[0] = f4.x; fis[1] = f4.y; fis[2] = f4.z; fis[3] = f4.w;
         if (D.active && y_img < H && x0 < W) {
-            const unsigned vb = *reinterpret_cast<const unsigned *>(D.valid_mask + (long)bp * npix + (long)y_img * W + x0);
+            vb = *reinterpret_cast<const unsigned *>(D.valid_mask + (long)bp * npix + (long)y_img * W + x0);
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 if ((vb >> (8 * j)) & 0xffu)
                     s_list[atomicAdd(&s_n, 1)] = (unsigned short)(threadIdx.x * 4 + j);
         }
     }
-    __syncthreads();
+    /* a tile no mesh covers (most of them) has nothing to list, no span and no gradient: zero planes and out */
+    if (!__syncthreads_or((fis[0] & fis[1] & fis[2] & fis[3]) >= 0 || vb != 0u)) {
+        if (in) {
+            float *dst = g_rgb + (((long)b * 3) * S + y_img) * S + x0;
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4 *>(dst) = z4;
+            *reinterpret_cast<float4 *>(dst + (long)S * S) = z4;
+            *reinterpret_cast<float4 *>(dst + 2l * S * S) = z4;
+        }
+        return;
+    }
     /* phase B: d loss / d flow x mult of the listed pixels, one per thread (hoc_warp_photo_pair_backward_kernel) */
     const int n_valid = s_n;
     if (n_valid > 0) {
@@ -786,6 +798,7 @@ hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__re
                             unsigned long long *__restrict__ det_gt, unsigned long long *__restrict__ det_ad,
                             int k4_samples)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     const int b = blockIdx.y;
     const int count = min(cov_count[b], S * S);
     const int2 *list = cov_list + (long)b * S * S;
@@ -1003,6 +1016,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                            float *__restrict__ grad_faces,
                            unsigned long long *__restrict__ det_gf)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     /* dynamic shared memory: float4 s_line4[S + 16]
      * per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (the inside pixel of a scan
      * is covered, its alpha is 1): delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_rgb Iin_ch g_ch -- one 16-byte
@@ -1148,6 +1162,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
 }
 
 /* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
+static int g_cover_ctas = 296;
 static int g_line_threads = 128, g_line_seg = 16, g_line_ctas = 0; /* 0: one CTA per line; > 0: that many CTAs walk the list */
 
 extern "C" int hoc_set_tuning(int key, int value)
@@ -1160,6 +1175,10 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_hoc_deterministic = value;
     else if (key == HOC_TUNE_LINE_CTAS && value >= 0 && value <= (1 << 20))
         g_line_ctas = value;
+    else if (key == HOC_TUNE_PDL && (value == 0 || value == 1))
+        g_hoc_pdl = value;
+    else if (key == HOC_TUNE_COVER_CTAS && value >= 1 && value <= 65535)
+        g_cover_ctas = value;
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -1179,7 +1198,7 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
     const dim3 grid = walk ? dim3((unsigned)(max_lines < g_line_ctas ? max_lines : g_line_ctas)) : dim3(B, 2, S);
 #define HOC_LINE_LAUNCH(WALK)                                                                                         \
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,                                                                             \
-               (hoc_raster_bwd_line_kernel<CH, WALK><<<grid, g_line_threads, smem, st>>>(                             \
+               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH, WALK>), grid, g_line_threads, smem, st,                              \
                    faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,  \
                    w.n_lines, w.line_list, (int)max_lines, 2.0f / (float)S, w.emitters, grad_faces, w.det_gf)))
     if (walk)
@@ -1386,11 +1405,21 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         const uintptr_t al = (uintptr_t)face_index_map | (uintptr_t)grad_rgb | (uintptr_t)g_alpha;
         if (pair_src != nullptr) { /* frame-pair path: the incoming gradient is computed by the scan pass itself */
             dim3 pg4(B, (S + 127) / 128, (S + 7) / 8);
+            /* the three zero-filled outputs as one region when the caller laid them out back to back */
+            float *za = grad_faces, *zb = grad_textures, *zc = (float *)extra_zero;
+            long na = n_gf, nb = n_gt, nc = (long)(extra_zero_bytes / sizeof(float));
+            if (zb != nullptr && zc == zb + nb) {
+                nb += nc;
+                nc = 0;
+            }
+            if (za != nullptr && zb == za + na) {
+                na += nb;
+                nb = 0;
+            }
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
-                       (hoc_raster_bwd_scan_pair_kernel<<<pg4, 256, 0, st>>>(
+                       (hoc_launch_pdl((hoc_raster_bwd_scan_pair_kernel), pg4, 256, 0, st, 
                            face_index_map, *pair_src, grad_rgb_out, S, k4_samples, want_depth ? 1 : 0, w.ext, w.cov_count,
-                           w.cov_list, grad_faces, n_gf, grad_textures, n_gt, (float *)extra_zero,
-                           (long)(extra_zero_bytes / sizeof(float)), row_lo)));
+                           w.cov_list, za, na, zb, nb, zc, nc, row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_pair_kernel");
         } else if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && (al & 15) == 0) {
             dim3 pg4((S + 127) / 128, (S + 7) / 8, B);
@@ -1413,10 +1442,10 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     {
         const long npix = (long)S * S;
         const int per = k4 ? 32 : CV_THREADS;
-        dim3 cg((unsigned)((npix + per - 1) / per < 296 ? (npix + per - 1) / per : 296), B);
+        dim3 cg((unsigned)((npix + per - 1) / per < g_cover_ctas ? (npix + per - 1) / per : g_cover_ctas), B);
 #define HOC_COVER_LAUNCH(TS2)                                                                                        \
     HOC_LAUNCH(k4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, st,                                      \
-               (hoc_raster_bwd_cover_kernel<TS2><<<cg, CV_THREADS, 0, st>>>(                                          \
+               (hoc_launch_pdl((hoc_raster_bwd_cover_kernel<TS2>), cg, CV_THREADS, 0, st,                                           \
                    faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
                    eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
                    w.line_count, w.n_lines, w.line_list, w.emitters, grad_faces, gt, w.det_gf, w.det_gt, w.det_ad,   \

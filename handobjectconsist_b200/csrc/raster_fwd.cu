@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(ZB_THREADS)
 hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__restrict__ zbuf, int F, int S,
                        float near_, float far_, const int *__restrict__ row_lo)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     extern __shared__ float s_centre[]; /* [S] pixel-centre NDC coordinate of index i */
     __shared__ float s_rec[ZB_WARPS][ZB_FACES_PER_WARP][ZB_REC];
     __shared__ int s_pre[ZB_WARPS][ZB_FACES_PER_WARP + 1];
@@ -375,6 +376,7 @@ hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restr
                            float *__restrict__ depth, int32_t *__restrict__ face_index_map,
                            float *__restrict__ weight_map, const int *__restrict__ row_lo)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     __shared__ unsigned short s_list[RS4_THREADS * 4];
     __shared__ int s_n;
     const int b = blockIdx.x; /* sample fastest, chunks of rows from the image centre outwards (hoc_centre_out) */
@@ -519,7 +521,7 @@ extern "C" int hoc_raster_forward_ex(const float *faces, const float *textures, 
         const int per_cta = ZB_WARPS * ZB_FACES_PER_WARP;
         dim3 grid((F + per_cta - 1) / per_cta, B);
         HOC_LAUNCH(HOC_K_RASTER_ZBUF, st,
-                   (hoc_raster_zbuf_kernel<<<grid, ZB_THREADS, S * sizeof(float), st>>>(faces, zbuf, F, S, near_, far_,
+                   (hoc_launch_pdl((hoc_raster_zbuf_kernel), grid, ZB_THREADS, S * sizeof(float), st, faces, zbuf, F, S, near_, far_,
                                                                                         row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_zbuf_kernel");
     }
@@ -537,7 +539,7 @@ extern "C" int hoc_raster_forward_ex(const float *faces, const float *textures, 
         const long groups = npix / 4;
         dim3 grid4(B, (unsigned)((groups + RS4_THREADS - 1) / RS4_THREADS));
         HOC_LAUNCH(HOC_K_RASTER_RESOLVE, st,
-                   (hoc_raster_resolve4_kernel<<<grid4, RS4_THREADS, 0, st>>>(faces, textures, zbuf, F, S, ts, near_, far_, eps,
+                   (hoc_launch_pdl((hoc_raster_resolve4_kernel), grid4, RS4_THREADS, 0, st, faces, textures, zbuf, F, S, ts, near_, far_, eps,
                                                                            bg[0], bg[1], bg[2], background_dev, tex_vertex,
                                                                            sparse_saved, rgb, alpha, depth,
                                                                            face_index_map, weight_map, row_lo)));

@@ -195,6 +195,7 @@ __global__ void hoc_pair_loss_mean_kernel(const double *__restrict__ sums_fwd, c
                                           float *__restrict__ loss, float *__restrict__ mean, uint4 *__restrict__ zero,
                                           long n_zero)
 {
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     if (blockIdx.x > 0) { /* the other CTAs zero-fill a buffer of the step's BACKWARD (its rasterizer's counters) */
         hoc_fill16(zero, n_zero, (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x, (long)(gridDim.x - 1) * blockDim.x, 0u);
         return;
@@ -725,7 +726,7 @@ extern "C" int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd
     const long n_zero = zero ? (long)(zero_bytes / 16) : 0;
     const unsigned extra = n_zero ? (unsigned)((n_zero + 1023) / 1024 < 64 ? (n_zero + 1023) / 1024 : 64) : 0;
     HOC_LAUNCH(HOC_K_PAIR_LOSS, (cudaStream_t)stream,
-               (hoc_pair_loss_mean_kernel<<<1 + extra, 128, 0, (cudaStream_t)stream>>>(sums_fwd, sums_bwd, B, loss, mean,
+               (hoc_launch_pdl((hoc_pair_loss_mean_kernel), 1 + extra, 128, 0, (cudaStream_t)stream, sums_fwd, sums_bwd, B, loss, mean,
                                                                                         (uint4 *)zero, n_zero)));
     HOC_CHECK_LAUNCH("hoc_pair_loss_mean_kernel");
     return HOC_OK;

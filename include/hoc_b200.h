@@ -111,6 +111,10 @@ const char *hoc_last_error(void);
 #define HOC_TUNE_LINE_SEGMENT 2
 #define HOC_TUNE_DETERMINISTIC 3
 #define HOC_TUNE_LINE_CTAS 4 /* line pass: 0 (default) one CTA per line, centre-out; n > 0: n CTAs walk the list of non-empty lines */
+#define HOC_TUNE_PDL 5       /* 0 (default) / 1: programmatic dependent launch of the frame-pair step's kernels (launch,
+                              * CTA scheduling and prologue of kernel N + 1 overlap the tail of kernel N; results are
+                              * identical either way).  Measured: no gain inside the captured graph */
+#define HOC_TUNE_COVER_CTAS 6 /* CTAs per sample of the rasterizer backward's cover pass (grid-stride over the listed pixels) */
 int hoc_set_tuning(int key, int value);
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */
