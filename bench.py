@@ -448,9 +448,12 @@ def run_native(args, rank, world, local_rank):
         # warp backward fused with the finalize backward: valid1 in, grad_rgb 12 out per raster pixel; flow8 + mult4 +
         # source 12 + target 12 at the valid pixels
         "warp_photo_bwd": 2 * ncrop * 1 + npx2 * 12 + int(c * 2 * ncrop) * 36,
-        # scan pass over both renders: idx4 + grad_rgb12 in, list entries (8 B per covered pixel) out, zero-fill of
-        # grad_faces (one render) + grad of the vertex values (both) + the scatter's outputs
-        "raster_bwd_pixel": npx2 * 16 + int(c * npx2) * 8 + nf * 36 + nf2 * 36 + 2 * 2 * Bp * V * 12,
+        # scan pass over both renders with the backward of pair_consist fused in (hoc_raster_bwd_scan_pair_kernel): idx4 +
+        # valid1 in, grad_rgb12 out per pixel; flow8 + mult4 + source 12 + target 12 at the valid pixels; list entries
+        # (8 B per covered pixel) out; zero-fill of grad_faces (one render) + grad of the vertex values (both) + the
+        # scatter's outputs
+        "raster_bwd_pixel": (npx2 * 16 + 2 * ncrop * 1 + int(c * 2 * ncrop) * 36 + int(c * npx2) * 8 + nf * 36 + nf2 * 36
+                             + 2 * 2 * Bp * V * 12),
         # cover pass over both renders: per listed pixel entry8 + grad_rgb12 + weights12 + depth4 (+ rgb12 and a 2-byte
         # scan record for the render with the pseudo-gradient); faces in; 9 sums per face out (+ grad_faces update)
         "raster_bwd_pixel_k4": int(c * npx2) * 36 + int(c * npx) * 14 + nf2 * 72 + nf * 36,
@@ -473,7 +476,7 @@ def run_native(args, rank, world, local_rank):
                       "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
     table.sort(key=lambda r: -r["share_of_step"])
     kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve4_kernel",
-             "raster_bwd_pixel": "hoc_raster_bwd_scan4_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel",
+             "raster_bwd_pixel": "hoc_raster_bwd_scan_pair_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel",
              "raster_bwd_cover": "hoc_raster_bwd_cover_kernel", "raster_backward": "hoc_raster_bwd_depth_kernel",
              "raster_bwd_line": "hoc_raster_bwd_line_kernel", "warp_photo_bwd": "hoc_warp_photo_pair_backward_kernel",
              "flow_finalize": "hoc_flow_finalize_warp_kernel", "mesh_scatter": "hoc_mesh_scatter_kernel",
@@ -542,7 +545,7 @@ def run_native(args, rank, world, local_rank):
         "launches_per_step": launches_per_step,
         "loss_global_mean": global_loss,
         "execution": "forward+backward captured once in a CUDA graph (handobjectconsist_b200.graphed), replayed per step; "
-                     "the frame-pair path of consist.py: 11 kernel nodes, no memset / ATen node",
+                     "the frame-pair path of consist.py: 10 kernel nodes, no memset / ATen node",
         "with_visuals": ({"value": 2 * PAIRS * args.steps / (vis_ms / 1e3), "ms_per_step": vis_ms / args.steps,
                           "note": "the same captured step when it also produces pair_consist's visualisation returns"}
                          if vis_ms else None),
@@ -557,10 +560,12 @@ def run_native(args, rank, world, local_rank):
             "share_of_step": bwd_ms / step_ms if bwd_ms else None,
             "launches_timed": len(group_ms), "sum_of_per_kernel_brackets_ms": bwd_ms_kernels,
             "timing": "ONE pair of CUDA events (external event nodes of an instrumented copy of the captured graph) around the "
-                      "three launches of hoc_raster_backward_ex; the pair adds ~4 us (profiles/timeline_r2.txt holds the "
+                      "three launches of hoc_pair_backward_raster; the pair adds ~4 us (profiles/timeline_r2.txt holds the "
                       "CUPTI durations of an un-instrumented replay)",
             "note": "scan + cover + line pass over the stacked batch of both renders (one launch each); bytes: the render "
-                    "with the pseudo-gradient (H*W*28 + 2F*108 per sample) + the texture-only render (H*W*16 + 2F*72)"},
+                    "with the pseudo-gradient (H*W*28 + 2F*108 per sample) + the texture-only render (H*W*16 + 2F*72).  "
+                    "The scan pass also computes the backward of pair_consist (fused in; its own operand bytes are NOT "
+                    "added to the numerator), so the fraction is a lower bound for the rasterizer backward alone"},
         "roofline_dominant": roof(dom),
         "kernels": table,
     }

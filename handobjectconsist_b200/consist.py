@@ -169,7 +169,7 @@ class _PairConsistFunction(Function):
                 n_b = 2 * B if cfg["use_backward"] else B
                 bws_bytes = L.hoc_raster_backward_workspace_bytes_ex(n_b, Fr, S, 2, _lib.HOC_TEX_GRAD_VERTEX)
                 bws = e(max(bws_bytes, 16), dtype=torch.uint8)
-                bws_zero = L.hoc_raster_backward_zero_bytes(n_b, Fr, S)
+                bws_zero = L.hoc_pair_backward_zero_bytes(n_b, Fr, S)  # (no depth gradient: spans and counters only)
             _lib.check(L.hoc_pair_loss_mean(_lib.ptr(sums[0]), _lib.ptr(sums[1]) if cfg["use_backward"] else None, B,
                                             _lib.ptr(loss), _lib.ptr(mean), _lib.ptr(bws), bws_zero or 0, st),
                        "hoc_pair_loss_mean")

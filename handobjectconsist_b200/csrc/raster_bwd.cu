@@ -1226,6 +1226,14 @@ extern "C" size_t hoc_raster_backward_zero_bytes(int B, int F, int S)
     return (w.count_bytes + w.acc_bytes + 15) & ~(size_t)15;
 }
 
+/* The same for hoc_pair_backward_raster, which never has a depth gradient: the line spans and counters only. */
+extern "C" size_t hoc_pair_backward_zero_bytes(int n, int F, int S)
+{
+    if (n <= 0 || S <= 0 || F < 0)
+        return 0;
+    return (hoc_bwd_workspace(nullptr, n, F, S).count_bytes + 15) & ~(size_t)15;
+}
+
 /* Workspace of hoc_raster_backward for a given texture size: in the reproducible mode (HOC_TUNE_DETERMINISTIC) the
  * fixed-point accumulators of grad_textures ([B,F,ts^3,3] or, in HOC_TEX_GRAD_VERTEX mode, [B,F,3,3]) live in it. */
 extern "C" size_t hoc_raster_backward_workspace_bytes_ex(int B, int F, int S, int ts, int tex_grad_mode)

@@ -291,6 +291,7 @@ int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, fl
  * Arguments: those of hoc_warp_photo_backward_pair (pairs = B of the pair kernels) and of hoc_raster_backward_ex for the
  * stacked rows [row_offset, row_offset + n) of (render 1 of every pair, render 2 of every pair); image layout, vertex
  * texture gradients; grad_rgb [n,3,S,S] is scratch the call fills (rows inside the raster window). */
+size_t hoc_pair_backward_zero_bytes(int n, int F, int S); /* leading workspace bytes HOC_BWD_WORKSPACE_ZEROED vouches for */
 int hoc_pair_backward_raster(const float *image_ref, const float *image, const float *flow12, const float *flow21,
                              const uint8_t *const *valid_mask, const double *sums, const float *mult1,
                              const float *mult2, const float *grad_loss, const float *grad_mean, int pairs, int H, int W,
