@@ -372,7 +372,11 @@ struct HocFinWarpDir {
 #ifndef FW_THREADS
 #define FW_THREADS 128 /* (128 vs 256 vs 64: 20.6 / 21.3 / 24.6 us at 16 pairs of 256 x 256) */
 #endif
-__global__ void __launch_bounds__(FW_THREADS)
+#ifndef FW_MINB
+#define FW_MINB 8 /* 64 registers, no spill: 16.5 -> 16.0 us against the compiler's own choice of 72 */
+#endif
+#define FW_BOUNDS __launch_bounds__(FW_THREADS, FW_MINB)
+__global__ void FW_BOUNDS
 hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocFinWarpDir D1, int S, int H, int W,
                               const int *__restrict__ ignore, int n_ignore, float distance_thresh, float inv_w,
                               float inv_h, float thresh)
@@ -763,7 +767,12 @@ extern "C" int hoc_cat_meshes(const float *hand_a, const float *obj_a, const flo
  * face table [2B,F,3] (hand first, object indices offset by Vh; rows B..2B-1 repeat rows 0..B-1) that the adjoint
  * scatter of the stacked batch walks. */
 #define PF_THREADS 128
-__global__ void __launch_bounds__(PF_THREADS)
+#ifdef PF_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
+#define PF_BOUNDS __launch_bounds__(PF_THREADS, PF_MINB)
+#else
+#define PF_BOUNDS __launch_bounds__(PF_THREADS)
+#endif
+__global__ void PF_BOUNDS
 hoc_pair_front_kernel(const float *__restrict__ hand1, const float *__restrict__ obj1, const float *__restrict__ hand2,
                       const float *__restrict__ obj2, const long long *__restrict__ hand_faces, int hand_faces_batched,
                       const long long *__restrict__ obj_faces, HocCam C, int B, int Vh, int Vo, int Fh, int Fo,

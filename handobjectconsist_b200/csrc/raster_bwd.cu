@@ -784,7 +784,12 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
  */
 #define CV_THREADS 128
 template <bool TS2>
-__global__ void __launch_bounds__(CV_THREADS)
+#ifdef CV_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
+#define CV_BOUNDS __launch_bounds__(CV_THREADS, CV_MINB)
+#else
+#define CV_BOUNDS __launch_bounds__(CV_THREADS)
+#endif
+__global__ void CV_BOUNDS
 hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                             const float *__restrict__ rgb, const float *__restrict__ weight_map,
                             const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
@@ -1006,7 +1011,12 @@ __device__ __forceinline__ void hoc_line_scan_setup(unsigned rec, bool valid, co
  */
 #define LN_THREADS 256
 template <int CH, bool WALK>
-__global__ void __launch_bounds__(LN_THREADS)
+#ifdef LN_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
+#define LN_BOUNDS __launch_bounds__(LN_THREADS, LN_MINB)
+#else
+#define LN_BOUNDS __launch_bounds__(LN_THREADS)
+#endif
+__global__ void LN_BOUNDS
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,

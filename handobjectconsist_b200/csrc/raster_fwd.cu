@@ -65,7 +65,12 @@ __device__ __forceinline__ bool hoc_face_bbox(const float *f, int S, int *x0, in
  * whatever the sizes of the individual faces (a 9k-triangle mesh at 256x256 has faces of 2-30 pixels,
  * a silhouette test has two triangles of 30 000).
  */
-__global__ void __launch_bounds__(ZB_THREADS)
+#ifdef ZB_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
+#define ZB_BOUNDS __launch_bounds__(ZB_THREADS, ZB_MINB)
+#else
+#define ZB_BOUNDS __launch_bounds__(ZB_THREADS)
+#endif
+__global__ void ZB_BOUNDS
 hoc_raster_zbuf_kernel(const float *__restrict__ faces, unsigned long long *__restrict__ zbuf, int F, int S,
                        float near_, float far_, const int *__restrict__ row_lo)
 {
@@ -368,7 +373,12 @@ hoc_raster_resolve_kernel(const float *__restrict__ faces, const float *__restri
 #ifndef RS4_THREADS
 #define RS4_THREADS 128 /* (128 vs 256: 14.6 / 15.7 us) */
 #endif
-__global__ void __launch_bounds__(RS4_THREADS)
+#ifdef RS4_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
+#define RS4_BOUNDS __launch_bounds__(RS4_THREADS, RS4_MINB)
+#else
+#define RS4_BOUNDS __launch_bounds__(RS4_THREADS)
+#endif
+__global__ void RS4_BOUNDS
 hoc_raster_resolve4_kernel(const float *__restrict__ faces, const float *__restrict__ textures,
                            const unsigned long long *__restrict__ zbuf, int F, int S, int ts, float near_, float far_,
                            float eps, float bg0, float bg1, float bg2, const float *__restrict__ bg_dev, int tex_vertex,
