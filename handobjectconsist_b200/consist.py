@@ -22,8 +22,8 @@ of the pair stacked along the batch ([2B]) so that every rasterizer kernel runs 
 
 No memset and no ATen kernel in between: every zero-fill a kernel needs is done by the kernel before it (the loss
 sums by hoc_pair_front, the rasterizer backward's counters by hoc_pair_loss_mean, the scatter's outputs by the
-rasterizer backward's streaming pass), and the batch mean and its adjoint live inside hoc_pair_loss_mean / the warp
-backward.
+rasterizer backward's streaming pass), and the batch mean and its adjoint live inside hoc_pair_loss_mean / the
+rasterizer backward's streaming pass.
 
 ``return_visuals=False`` (what ``GraphedConsistStep`` asks for) skips the three visualisation returns of pair_consist
 (``warps``, ``diffs``, ``warp_mask``): nothing the loss or its gradient depends on.
