@@ -34,6 +34,8 @@
  * Measured progression on bench.py's workload (B = 16 renders of 9104 faces at 256 x 256, B200, in-graph):
  * 548 us (one warp per face) -> 245 -> 121 -> 93 (pixel / face / line passes) -> 55 us (this decomposition).
  */
+#include <mutex>
+
 #include "hoc_common.cuh"
 #include "hoc_det.cuh"
 #include "raster_math.h"
@@ -253,7 +255,7 @@ __device__ __forceinline__ void hoc_k4_stage_b(const HocK4Stage &T, int axis, co
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
                            const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S, int layout,
-                           int k4_samples, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
+                           int k4_samples, int list_all_k4, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
                            int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
                            float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                            const int *__restrict__ row_lo)
@@ -263,7 +265,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
     const bool K4 = (int)blockIdx.z < k4_samples;
     const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
     const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
-    const int list_all = K4 ? 1 : list_all_rest;
+    const int list_all = K4 ? list_all_k4 : list_all_rest;
     { /* zero-fill of the two gradient outputs (accumulated with atomics by the later passes), spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 32 +
@@ -310,12 +312,15 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         if (tx == 0)
             s_cnt[r * 8 + ty] = __popc(want[r]);
         if (K4) {
-            const unsigned m = __ballot_sync(HOC_FULL_MASK, nz);
+            /* span of the pixels the line pass has to look at: covered ones (they own the scans) and those with an
+             * incoming gradient (the only ones a scan gets a term from) */
+            const bool sp = nz || fis[r] >= 0;
+            const unsigned m = __ballot_sync(HOC_FULL_MASK, sp);
             if (m != 0 && tx == 0) {
                 atomicMax(&e[EXT_ROW_LO * S + yi], S - (blockIdx.x * 32 + (__ffs(m) - 1)));
                 atomicMax(&e[EXT_ROW_HI * S + yi], blockIdx.x * 32 + (31 - __clz(m)) + 1);
             }
-            if (nz) {
+            if (sp) {
                 c_lo = min(c_lo, yi);
                 c_hi = max(c_hi, yi);
             }
@@ -370,7 +375,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
                             const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S,
-                            int k4_samples, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
+                            int k4_samples, int list_all_k4, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
                             int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
                             float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                             const int *__restrict__ row_lo)
@@ -388,7 +393,7 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     const bool K4 = b < k4_samples;
     const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
     const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
-    const int list_all = K4 ? 1 : list_all_rest;
+    const int list_all = K4 ? list_all_k4 : list_all_rest;
     const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int y_img = blockIdx.y * 8 + ty;  /* image row (rows flipped): raster row yi = S - 1 - y_img */
     const int yi = S - 1 - y_img;
@@ -426,7 +431,11 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     __syncthreads(); /* s_clo / s_chi initialised */
     if (K4) {
         /* span of non-zero incoming gradient of this row (the warp's) and of the tile's columns */
-        int lo = nzm ? x0 + (__ffs(nzm) - 1) : 0x7fffffff, hi = nzm ? x0 + (31 - __clz(nzm)) : -1;
+        /* (pixels the line pass has to look at: those with an incoming gradient -- the only ones a scan gets a term
+         * from -- and the covered ones, which own the scans) */
+        const unsigned spm = nzm | (fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
+                             (fis[3] >= 0 ? 8u : 0u);
+        int lo = spm ? x0 + (__ffs(spm) - 1) : 0x7fffffff, hi = spm ? x0 + (31 - __clz(spm)) : -1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = min(lo, __shfl_xor_sync(HOC_FULL_MASK, lo, o));
@@ -439,7 +448,7 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
         }
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if ((nzm >> j) & 1u) {
+            if ((spm >> j) & 1u) {
                 atomicMin(&s_clo[lane * 4 + j], yi);
                 atomicMax(&s_chi[lane * 4 + j], yi);
             }
@@ -503,7 +512,7 @@ struct HocPairGradSrc {
 
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocPairGradSrc G, float *__restrict__ g_rgb,
-                                int S, int k4_samples, int list_all_rest, int *__restrict__ ext,
+                                int S, int k4_samples, int list_all_k4, int list_all_rest, int *__restrict__ ext,
                                 int *__restrict__ cov_count, int2 *__restrict__ cov_list, float *__restrict__ zero_a,
                                 long n_a, float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                                 const int *__restrict__ row_lo)
@@ -525,7 +534,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     const int b = blockIdx.x;
     const int tile_x = blockIdx.y, tile_y = hoc_centre_out(blockIdx.z, gridDim.z);
     const bool K4 = b < k4_samples;
-    const int list_all = K4 ? 1 : list_all_rest;
+    const int list_all = K4 ? list_all_k4 : list_all_rest;
     const int r = b + G.row_offset;
     const int bp = r < G.pairs ? r : r - G.pairs;     /* the pair (r < 2 pairs) */
     const HocPairBwdDir &D = G.dir[r < G.pairs ? 1 : 0]; /* render 1 <- direction 1, render 2 <- direction 0 */
@@ -608,7 +617,11 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         if (fis[j] >= 0 && (list_all || ((nzm >> j) & 1u)))
             want |= 1u << j;
     if (K4) {
-        int lo = nzm ? x0 + (__ffs(nzm) - 1) : 0x7fffffff, hi = nzm ? x0 + (31 - __clz(nzm)) : -1;
+        /* (pixels the line pass has to look at: those with an incoming gradient -- the only ones a scan gets a term
+         * from -- and the covered ones, which own the scans) */
+        const unsigned spm = nzm | (fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
+                             (fis[3] >= 0 ? 8u : 0u);
+        int lo = spm ? x0 + (__ffs(spm) - 1) : 0x7fffffff, hi = spm ? x0 + (31 - __clz(spm)) : -1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             lo = min(lo, __shfl_xor_sync(HOC_FULL_MASK, lo, o));
@@ -621,7 +634,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         }
 #pragma unroll
         for (int j = 0; j < 4; j++)
-            if ((nzm >> j) & 1u) {
+            if ((spm >> j) & 1u) {
                 atomicMin(&s_clo[lane * 4 + j], yi);
                 atomicMax(&s_chi[lane * 4 + j], yi);
             }
@@ -1171,8 +1184,227 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     } /* lines of the list */
 }
 
+/*
+ * Line pass, fused form (HOC_TUNE_LINE_MODE 1): the pseudo-gradient of one image column / row in ONE kernel, without the
+ * cover pass's per-pixel edge work, its scan queues and their round trip.  Every term of backward_pixel_map lives on one
+ * line: for (face f, edge, axis, d0) the inside pixel, the outside pixel, the inward scan and the outward scan all have
+ * walk coordinate d0.  So the CTA of line (axis, d0) stages the line's span once -- owning face, colour, incoming
+ * gradient of every pixel -- and then runs, from shared memory, one CANDIDATE per (covered pixel of the line, edge of its
+ * face): the face's vertices are loaded (three lanes share a face), that column of the edge is evaluated once
+ * (hoc_k4_column), the pixel adds its own term of the inward scan (colour of the outside pixel: from the staged line),
+ * and if it is the pixel just inside the edge the lane holds the outward scan in registers; the warp then cuts its
+ * scans into 16-pixel chunks exactly as the queued form does.  Chain of dependent loads per CTA: span -> line -> faces.
+ */
+template <int CH>
+__global__ void LN_BOUNDS
+hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
+                            const float *__restrict__ rgb, const float *__restrict__ g_rgb,
+                            const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
+                            const int *__restrict__ ext, float scale, float *__restrict__ grad_faces,
+                            unsigned long long *__restrict__ det_gf)
+{
+    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
+    /* dynamic shared memory, per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (see the
+     * queued kernel), float4 (I_r, I_g, I_b, g_alpha), int owning face */
+    extern __shared__ float4 s_line4[];
+    float4 *s_pg = s_line4, *s_ia = s_line4 + (S + 16);
+    int *s_fi = reinterpret_cast<int *>(s_line4 + 2 * (S + 16));
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
+    const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
+    const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
+    const int b = blockIdx.x, axis = blockIdx.y, d0 = hoc_centre_out(blockIdx.z, S);
+    /* level 1: the span of the pixels that matter on this line (covered or with an incoming gradient: the scan pass) */
+    const int *e = ext + (long)b * 4 * S;
+    const int lo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
+    const int hi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0] - 1;
+    if (lo > hi)
+        return;
+    const int len = hi - lo + 1;
+    const int32_t *idx = face_index_map + (long)b * S * S;
+
+    /* level 2: the line */
+    for (int i = tid; i < len; i += T) {
+        const int d1 = lo + i;
+        const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
+        float4 pg = make_float4(0.0f, 0.0f, 0.0f, 0.0f), ia = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int fi = idx[(long)yi * S + xi];
+        if (has_rgb) {
+            const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
+                       o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
+            ia.x = rgb[o0];
+            ia.y = rgb[o1];
+            ia.z = rgb[o2];
+            pg.y = g_rgb[o0];
+            pg.z = g_rgb[o1];
+            pg.w = g_rgb[o2];
+            pg.x = ia.x * pg.y + ia.y * pg.z + ia.z * pg.w;
+        }
+        if (has_alpha) {
+            const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
+            const float a = (fi >= 0) ? 1.0f : 0.0f;
+            pg.x += a * ga - ga;
+            ia.w = ga;
+        }
+        s_pg[i] = pg;
+        s_ia[i] = ia;
+        s_fi[i] = fi;
+    }
+    __syncthreads();
+
+    HocBwdMaps M; /* (for the outside pixel of an inward term that lies beyond the staged span) */
+    M.idx = idx;
+    M.rgb = rgb;
+    M.g_rgb = g_rgb;
+    M.g_alpha = g_alpha;
+    M.S = S;
+    M.layout = layout;
+    M.b = b;
+    M.use_alpha = has_alpha;
+    M.use_rgb = has_rgb;
+    /* level 3: the candidates, 32 per warp at a time; the warps of the CTA no longer synchronise */
+    const int ncand = 3 * len;
+    for (int c0 = wid * 32; c0 < ncand; c0 += T) {
+        const int c = c0 + lane;
+        HocLineScan sc;
+        sc.cA = sc.cB = 0.0f;
+        sc.eA = sc.eB = 1.0f;
+        sc.cross = 0.0f;
+        sc.I1 = sc.I2 = sc.I3 = 0.0f;
+        sc.from = 0;
+        sc.to = -1;
+        sc.gfA = sc.gfB = -1;
+        sc.nchunk = 0;
+        const int i = (int)(((unsigned)min(c, ncand - 1) * 43691u) >> 17); /* c / 3 (exact below 98 304) */
+        const int edge = min(c, ncand - 1) - 3 * i;
+        const int fi = (c < ncand) ? s_fi[i] : -1;
+        if (fi >= 0 && fi < F) {
+            const int d1p = lo + i;
+            const int ia_ = edge, ib_ = (edge == 2) ? 0 : edge + 1, ic_ = (edge == 0) ? 2 : edge - 1;
+            const float *src = faces + ((long)b * F + fi) * 9;
+            const float ax = __ldg(src + 3 * ia_), ay = __ldg(src + 3 * ia_ + 1);
+            const float bx = __ldg(src + 3 * ib_), by = __ldg(src + 3 * ib_ + 1);
+            const float cx = __ldg(src + 3 * ic_), cy = __ldg(src + 3 * ic_ + 1);
+            /* the owner of a pixel is front-facing with finite xy (the forward's tests); re-checked, in the face's
+             * stored vertex order (hoc_face_back on the rotated vertices is NOT bit-identical) */
+            float f[9];
+            f[0] = (edge == 0) ? ax : ((edge == 1) ? cx : bx);
+            f[1] = (edge == 0) ? ay : ((edge == 1) ? cy : by);
+            f[3] = (edge == 0) ? bx : ((edge == 1) ? ax : cx);
+            f[4] = (edge == 0) ? by : ((edge == 1) ? ay : cy);
+            f[6] = (edge == 0) ? cx : ((edge == 1) ? bx : ax);
+            f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
+            f[2] = f[5] = f[8] = 0.0f;
+            HocK4Stage K;
+            K.need = K.push = false;
+            hoc_k4_edge_pts(ax, ay, bx, by, cx, cy, S, axis, &K.E);
+            int d1_in = 0, d1_out = 0;
+            if (hoc_face_xy_finite(f) && !hoc_face_back(f) && d0 >= K.E.d0_from && d0 <= K.E.d0_to &&
+                hoc_k4_column(&K.E, S, d0, &K.d1_cross, &d1_in, &d1_out)) {
+                const float4 pa = s_ia[i], pp = s_pg[i];
+                const long gf = ((long)b * F + fi) * 9;
+                /* (a) the pixel's own term of the inward scan (the owned pixels between the edge and the opposite edge) */
+                const int lim = hoc_k4_inward_limit(&K.E, d0);
+                if (max(min(d1_in, lim), 0) <= d1p && d1p <= min(max(d1_in, lim), S - 1)) {
+                    const float I[4] = {1.0f, pa.x, pa.y, pa.z}, g[4] = {pa.w, pp.y, pp.z, pp.w};
+                    float O[4];
+                    const int j = d1_out - lo;
+                    if (j >= 0 && j < len) {
+                        const float4 oa = s_ia[j];
+                        O[0] = (has_alpha && s_fi[j] >= 0) ? 1.0f : 0.0f;
+                        O[1] = oa.x;
+                        O[2] = oa.y;
+                        O[3] = oa.z;
+                    } else {
+                        hoc_load_I(M, axis == 0 ? d0 : d1_out, axis == 0 ? d1_out : d0, O);
+                    }
+                    K.d0 = d0;
+                    K.d1p = d1p;
+                    hoc_k4_stage_b(K, axis, M, I, O, g, eps, grad_faces, gf + 3 * ia_, gf + 3 * ib_, det_gf);
+                }
+                /* (b) the pixel just inside the edge: the outward scan starts here, clipped to the span */
+                if (d1_in == d1p) {
+                    sc.from = (0 < K.E.dir) ? max(d1_out, lo) : lo;
+                    sc.to = (0 < K.E.dir) ? hi : min(d1_out, hi);
+                    if (sc.to >= sc.from) {
+                        HocK4Col C;
+                        hoc_k4_col(&K.E, S, d0, K.d1_cross, &C);
+                        const float t_first = (float)d1_out - K.d1_cross; /* sign of (d1 - cross) on the whole scan */
+                        const int gbase = (int)gf + (1 - axis);
+                        sc.cross = K.d1_cross;
+                        if (C.hasA) {
+                            sc.cA = C.cA * scale;
+                            sc.eA = (0.0f < sc.cA * t_first) ? eps : -eps;
+                            sc.gfA = gbase + ia_ * 3;
+                        }
+                        if (C.hasB) {
+                            sc.cB = C.cB * scale;
+                            sc.eB = (0.0f < sc.cB * t_first) ? eps : -eps;
+                            sc.gfB = gbase + ib_ * 3;
+                        }
+                        sc.I1 = pa.x;
+                        sc.I2 = pa.y;
+                        sc.I3 = pa.z;
+                        sc.nchunk = (sc.to - sc.from + CH) / CH;
+                    }
+                }
+            }
+        }
+        /* the warp's scans, cut into chunks of CH pixels, one chunk per lane (see the queued kernel) */
+        int incl = sc.nchunk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const int pre = incl - sc.nchunk;
+        const int total = __shfl_sync(HOC_FULL_MASK, incl, 31);
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = min(j0 + lane, total - 1);
+            const bool live = j0 + lane < total;
+            int a = 0; /* last scan with pre <= j */
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) {
+                const int pv = __shfl_sync(HOC_FULL_MASK, pre, (a + st) & 31);
+                if (a + st < 32 && pv <= j)
+                    a += st;
+            }
+            const int cc = (j - __shfl_sync(HOC_FULL_MASK, pre, a)) * CH;
+            const int d1_from = __shfl_sync(HOC_FULL_MASK, sc.from, a) + cc;
+            const int to_a = __shfl_sync(HOC_FULL_MASK, sc.to, a);
+            const int left = live ? to_a - d1_from : -1; /* pixels beyond the first */
+            const float cA = __shfl_sync(HOC_FULL_MASK, sc.cA, a), cB = __shfl_sync(HOC_FULL_MASK, sc.cB, a);
+            const float eA = __shfl_sync(HOC_FULL_MASK, sc.eA, a), eB = __shfl_sync(HOC_FULL_MASK, sc.eB, a);
+            const float I1 = __shfl_sync(HOC_FULL_MASK, sc.I1, a), I2 = __shfl_sync(HOC_FULL_MASK, sc.I2, a),
+                        I3 = __shfl_sync(HOC_FULL_MASK, sc.I3, a);
+            const float u0 = (float)d1_from - __shfl_sync(HOC_FULL_MASK, sc.cross, a);
+            const int gfA = __shfl_sync(HOC_FULL_MASK, sc.gfA, a), gfB = __shfl_sync(HOC_FULL_MASK, sc.gfB, a);
+            const float dA0 = __fmaf_rn(cA, u0, eA), dB0 = __fmaf_rn(cB, u0, eB);
+            const float4 *sp = s_pg + (d1_from - lo);
+            float gA = 0.0f, gB = 0.0f;
+#pragma unroll
+            for (int kk = 0; kk < CH; kk++) {
+                const float4 pg = sp[kk]; /* at most CH - 1 entries past the staged span: the buffer is padded */
+                const float delta = __fmaf_rn(-I3, pg.w, __fmaf_rn(-I2, pg.z, __fmaf_rn(-I1, pg.y, pg.x)));
+                const float dA = __fmaf_rn(cA, (float)kk, dA0), dB = __fmaf_rn(cB, (float)kk, dB0);
+                float t = delta * hoc_rcp_approx(dA * dB);
+                t = (delta <= 0.0f || kk > left) ? 0.0f : t;
+                gA = __fmaf_rn(-t, dB, gA);
+                gB = __fmaf_rn(-t, dA, gB);
+            }
+            if (gA != 0.0f && gfA >= 0)
+                hoc_accum(grad_faces, gfA, gA, det_gf);
+            if (gB != 0.0f && gfB >= 0)
+                hoc_accum(grad_faces, gfB, gB, det_gf);
+        }
+    }
+}
+
 /* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
 static int g_cover_ctas = 296;
+static int g_fork_cover = 1; /* fused line pass: cover pass on a second stream (HOC_TUNE_FORK_COVER) */
+static int g_line_mode = 1; /* 1: fused line pass (hoc_raster_bwd_line2_kernel); 0: cover pass queues the scans, queued line pass */
 static int g_line_threads = 128, g_line_seg = 16, g_line_ctas = 0; /* 0: one CTA per line; > 0: that many CTAs walk the list */
 
 extern "C" int hoc_set_tuning(int key, int value)
@@ -1189,6 +1421,10 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_hoc_pdl = value;
     else if (key == HOC_TUNE_COVER_CTAS && value >= 1 && value <= 65535)
         g_cover_ctas = value;
+    else if (key == HOC_TUNE_LINE_MODE && (value == 0 || value == 1))
+        g_line_mode = value;
+    else if (key == HOC_TUNE_FORK_COVER && (value == 0 || value == 1))
+        g_fork_cover = value;
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -1216,6 +1452,27 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
     else
         HOC_LINE_LAUNCH(false);
 #undef HOC_LINE_LAUNCH
+    return cudaSuccess;
+}
+
+template <int CH>
+static cudaError_t hoc_launch_line2(const float *faces, const int32_t *face_index_map, const float *rgb,
+                                    const float *grad_rgb, const float *g_alpha, int B, int F, int S, float eps,
+                                    int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
+                                    cudaStream_t st)
+{
+    /* two float4 and one int per staged pixel, + padding for the unrolled chunk loop: 9.8 KB at S = 256, 74 KB at 2048 */
+    const size_t smem = ((size_t)S + 16) * (2 * sizeof(float4) + sizeof(int));
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line2_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
+    HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
+               (hoc_launch_pdl((hoc_raster_bwd_line2_kernel<CH>), dim3(B, 2, S), g_line_threads, smem, st, faces,
+                               face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
+                               2.0f / (float)S, grad_faces, w.det_gf)));
     return cudaSuccess;
 }
 
@@ -1272,6 +1529,40 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     return hoc_raster_backward_ex(faces, textures, face_index_map, rgb, weight_map, depth, grad_rgb, grad_alpha,
                                   grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode, B, 0,
                                   nullptr, 0, nullptr, grad_faces, grad_textures, workspace, workspace_bytes, stream);
+}
+
+/* A second stream per device for the one fork of the path: with the fused line pass the cover pass (texture gradient,
+ * accumulates into grad_textures) and the line pass (pseudo-gradient, accumulates into grad_faces) are independent, and
+ * the light one hides in the latency-bound other.  Fork / join are event dependencies, so a stream capture records two
+ * parallel branches.  The mutex covers the record / wait pairs (the events are shared by the host threads of a device). */
+struct HocSideStream {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+    bool ready;
+};
+static std::mutex g_side_mutex;
+static HocSideStream g_side[64];
+
+static HocSideStream *hoc_side_stream_locked()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return nullptr;
+    HocSideStream *s = &g_side[dev];
+    if (!s->ready) {
+        /* highest priority: the forked pass is the short one -- it should start at once and be out of the way, not
+         * wait until the long pass has no CTA left to dispatch */
+        int pr_least = 0, pr_greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest);
+        if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, pr_greatest) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        s->ready = true;
+    }
+    return s;
 }
 
 /* geom_samples: the pseudo-gradient (backward_pixel_map) is computed for samples [0, geom_samples) only; the rows of
@@ -1398,6 +1689,13 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     const int k4_samples = (grad_faces != nullptr && (grad_rgb != nullptr || g_alpha != nullptr)) ? geom_samples : 0;
     const bool k4 = k4_samples > 0;
     const bool want_depth = grad_faces != nullptr && grad_depth != nullptr;
+    /* fused line pass: the cover pass has no pseudo-gradient work (k4_cover = 0: texture / depth gradient of every
+     * sample, one listed pixel per thread) and the scan pass lists only the pixels with such a gradient */
+    const bool fused_line = k4 && g_line_mode == 1;
+    const int k4_cover = fused_line ? 0 : k4_samples;
+    const int list_k4 = fused_line ? (want_depth ? 1 : 0) : 1;
+    HocSideStream *side = nullptr; /* non-NULL between the fork and the join of the cover pass */
+    std::unique_lock<std::mutex> side_lock(g_side_mutex, std::defer_lock);
     const size_t tex_bytes = (tex_grad_mode == HOC_TEX_GRAD_VERTEX)
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
@@ -1436,14 +1734,14 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
             }
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_launch_pdl((hoc_raster_bwd_scan_pair_kernel), pg4, 256, 0, st, 
-                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, want_depth ? 1 : 0, w.ext, w.cov_count,
+                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, list_k4, want_depth ? 1 : 0, w.ext, w.cov_count,
                            w.cov_list, za, na, zb, nb, zc, nc, row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_pair_kernel");
         } else if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && (al & 15) == 0) {
             dim3 pg4((S + 127) / 128, (S + 7) / 8, B);
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan4_kernel<<<pg4, 256, 0, st>>>(
-                           face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, k4_samples,
+                           face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, k4_samples, list_k4,
                            want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
                            (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan4_kernel");
@@ -1451,7 +1749,7 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         dim3 pg((S + 31) / 32, (S + 31) / 32, B);
         HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                    (hoc_raster_bwd_scan_kernel<<<pg, dim3(32, 8), 0, st>>>(
-                       face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples,
+                       face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples, list_k4,
                        want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
                        (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
@@ -1459,21 +1757,54 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     }
     {
         const long npix = (long)S * S;
-        const int per = k4 ? 32 : CV_THREADS;
-        dim3 cg((unsigned)((npix + per - 1) / per < g_cover_ctas ? (npix + per - 1) / per : g_cover_ctas), B);
+        const int per = k4_cover > 0 ? 32 : CV_THREADS;
+        /* (fused line pass: few CTAs that loop over the list -- the forked pass must be dispatched in one go, the
+         * block scheduler does not interleave the CTAs of two kernels that both have thousands pending) */
+        const int max_ctas = fused_line ? 32 : g_cover_ctas;
+        dim3 cg((unsigned)((npix + per - 1) / per < max_ctas ? (npix + per - 1) / per : max_ctas), B);
+        if (k4_cover > 0 || gt != nullptr || want_depth) {
+            /* fused line pass without depth gradient: the cover pass touches grad_textures only -- fork it */
+            cudaStream_t cst = st;
+            if (fused_line && !want_depth && !det && g_fork_cover) {
+                side_lock.lock();
+                side = hoc_side_stream_locked();
+                if (side != nullptr && cudaEventRecord(side->fork, st) == cudaSuccess &&
+                    cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
+                    cst = side->stream;
+                } else {
+                    cudaGetLastError();
+                    side = nullptr;
+                    side_lock.unlock();
+                }
+            }
 #define HOC_COVER_LAUNCH(TS2)                                                                                        \
-    HOC_LAUNCH(k4 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, st,                                      \
-               (hoc_launch_pdl((hoc_raster_bwd_cover_kernel<TS2>), cg, CV_THREADS, 0, st,                                           \
+    HOC_LAUNCH(k4_cover > 0 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, cst,                           \
+               (hoc_launch_pdl((hoc_raster_bwd_cover_kernel<TS2>), cg, CV_THREADS, 0, cst,                            \
                    faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
                    eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
                    w.line_count, w.n_lines, w.line_list, w.emitters, grad_faces, gt, w.det_gf, w.det_gt, w.det_ad,   \
-                   k4_samples)))
+                   k4_cover)))
         if (ts == 2)
             HOC_COVER_LAUNCH(true);
         else
             HOC_COVER_LAUNCH(false);
 #undef HOC_COVER_LAUNCH
-        HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
+            if (side != nullptr && cudaEventRecord(side->join, side->stream) != cudaSuccess) {
+                side_lock.unlock();
+                hoc_set_error("hoc_raster_backward: event record on the side stream failed: %s",
+                              cudaGetErrorString(cudaGetLastError()));
+                return HOC_ERR_CUDA;
+            }
+            if (side != nullptr && cudaGetLastError() != cudaSuccess) {
+                /* (join before reporting: a capture must not be left with a dangling branch) */
+                cudaStreamWaitEvent(st, side->join, 0);
+                side_lock.unlock();
+                hoc_set_error("hoc_raster_bwd_cover_kernel: launch failed");
+                return HOC_ERR_CUDA;
+            }
+            if (side == nullptr)
+                HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
+        }
     }
     const long nfaces = (long)B * F;
     if (det && gt != nullptr && hoc_det_flush(w.det_gt, nfaces * tex_n, gt, 0, st) != cudaSuccess) {
@@ -1494,7 +1825,28 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
                                                                                               grad_faces)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
     }
-    if (k4) {
+    if (fused_line) {
+        if (g_line_seg >= 16)
+            e = hoc_launch_line2<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
+                                     use_alpha, w, grad_faces, st);
+        else
+            e = hoc_launch_line2<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
+                                    use_alpha, w, grad_faces, st);
+        const cudaError_t le = cudaGetLastError(); /* (launch status of the line pass, before the join's calls) */
+        if (side != nullptr) { /* join -- whatever happened above: the caller's stream waits for the cover pass */
+            const cudaError_t je = cudaStreamWaitEvent(st, side->join, 0);
+            side = nullptr;
+            side_lock.unlock();
+            if (je != cudaSuccess) {
+                hoc_set_error("hoc_raster_backward: join of the side stream failed: %s", cudaGetErrorString(je));
+                return HOC_ERR_CUDA;
+            }
+        }
+        if (e != cudaSuccess || le != cudaSuccess) {
+            hoc_set_error("hoc_raster_backward: line pass: %s", cudaGetErrorString(e != cudaSuccess ? e : le));
+            return HOC_ERR_CUDA;
+        }
+    } else if (k4) {
         if (g_line_seg >= 16)
             e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
                                     use_alpha, w, grad_faces, st);

@@ -114,6 +114,8 @@ const char *hoc_last_error(void);
 #define HOC_TUNE_PDL 5       /* 0 (default) / 1: programmatic dependent launch of the frame-pair step's kernels (launch,
                               * CTA scheduling and prologue of kernel N + 1 overlap the tail of kernel N; results are
                               * identical either way).  Measured: no gain inside the captured graph */
+#define HOC_TUNE_LINE_MODE 7  /* 1 (default): the pseudo-gradient of a line in one fused pass; 0: cover pass queues the scans of a line, queued line pass */
+#define HOC_TUNE_FORK_COVER 8 /* 1 (default): with the fused line pass the cover pass (texture gradient) runs on a second stream beside it */
 #define HOC_TUNE_COVER_CTAS 6 /* CTAs per sample of the rasterizer backward's cover pass (grid-stride over the listed pixels) */
 int hoc_set_tuning(int key, int value);
 
