@@ -26,6 +26,7 @@ HOC_TUNE_PDL = 5
 HOC_TUNE_COVER_CTAS = 6
 HOC_TUNE_LINE_MODE = 7
 HOC_TUNE_FORK_COVER = 8
+HOC_TUNE_TEX_IN_LINE = 9
 HOC_BWD_WORKSPACE_ZEROED = 1
 
 _c_float_p = ctypes.c_void_p  # device pointers travel as integers

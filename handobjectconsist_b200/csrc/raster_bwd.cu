@@ -41,6 +41,8 @@
 #include "raster_math.h"
 #include "warp_math.cuh"
 
+#define HOC_SCAN_SPAN_ALL 1
+#define HOC_SCAN_NO_LIST 2
 #define EXT_ROW_LO 0
 #define EXT_ROW_HI 1
 #define EXT_COL_LO 2
@@ -255,7 +257,8 @@ __device__ __forceinline__ void hoc_k4_stage_b(const HocK4Stage &T, int axis, co
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
                            const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S, int layout,
-                           int k4_samples, int list_all_k4, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
+                           int k4_samples, int list_all_k4, int list_all_rest, int scan_flags, int *__restrict__ ext,
+                           int *__restrict__ cov_count,
                            int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
                            float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                            const int *__restrict__ row_lo)
@@ -266,6 +269,10 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
     const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
     const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
     const int list_all = K4 ? list_all_k4 : list_all_rest;
+    /* scan_flags: HOC_SCAN_SPAN_ALL = line spans for every sample (the fused line pass also runs the texture gradient of
+     * the samples without pseudo-gradient, row by row), HOC_SCAN_NO_LIST = nobody reads the list of covered pixels */
+    const bool SPAN = K4 || (scan_flags & HOC_SCAN_SPAN_ALL);
+    const bool NO_LIST = (scan_flags & HOC_SCAN_NO_LIST) != 0;
     { /* zero-fill of the two gradient outputs (accumulated with atomics by the later passes), spread over the grid */
         const long nthreads = (long)gridDim.x * gridDim.y * gridDim.z * 256;
         const long t0 = (((long)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 256 + threadIdx.y * 32 +
@@ -308,13 +315,13 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
     for (int r = 0; r < 4; r++) {
         const int yi = blockIdx.y * 32 + r * 8 + ty;
         const bool nz = !(gr[r][0] == 0.0f) || !(gr[r][1] == 0.0f) || !(gr[r][2] == 0.0f) || !(ga[r] == 0.0f);
-        want[r] = __ballot_sync(HOC_FULL_MASK, fis[r] >= 0 && (list_all || nz));
+        want[r] = __ballot_sync(HOC_FULL_MASK, !NO_LIST && fis[r] >= 0 && (list_all || nz));
         if (tx == 0)
             s_cnt[r * 8 + ty] = __popc(want[r]);
-        if (K4) {
+        if (SPAN) {
             /* span of the pixels the line pass has to look at: covered ones (they own the scans) and those with an
              * incoming gradient (the only ones a scan gets a term from) */
-            const bool sp = nz || fis[r] >= 0;
+            const bool sp = nz || (K4 && fis[r] >= 0);
             const unsigned m = __ballot_sync(HOC_FULL_MASK, sp);
             if (m != 0 && tx == 0) {
                 atomicMax(&e[EXT_ROW_LO * S + yi], S - (blockIdx.x * 32 + (__ffs(m) - 1)));
@@ -326,7 +333,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
             }
         }
     }
-    if (K4) {
+    if (SPAN) {
         s_lo[ty][tx] = c_lo;
         s_hi[ty][tx] = c_hi;
     }
@@ -343,7 +350,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
         s_cnt[tx] = incl - mine;
         if (tx == 31)
             s_cnt[32] = (incl > 0) ? atomicAdd(cov_count + b, incl) : 0;
-        if (K4 && xi < S) {
+        if (SPAN && xi < S) {
 #pragma unroll
             for (int r = 1; r < 8; r++) {
                 c_lo = min(c_lo, s_lo[r][tx]);
@@ -375,7 +382,8 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
                             const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S,
-                            int k4_samples, int list_all_k4, int list_all_rest, int *__restrict__ ext, int *__restrict__ cov_count,
+                            int k4_samples, int list_all_k4, int list_all_rest, int scan_flags, int *__restrict__ ext,
+                           int *__restrict__ cov_count,
                             int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
                             float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                             const int *__restrict__ row_lo)
@@ -394,6 +402,10 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
     const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
     const int list_all = K4 ? list_all_k4 : list_all_rest;
+    /* scan_flags: HOC_SCAN_SPAN_ALL = line spans for every sample (the fused line pass also runs the texture gradient of
+     * the samples without pseudo-gradient, row by row), HOC_SCAN_NO_LIST = nobody reads the list of covered pixels */
+    const bool SPAN = K4 || (scan_flags & HOC_SCAN_SPAN_ALL);
+    const bool NO_LIST = (scan_flags & HOC_SCAN_NO_LIST) != 0;
     const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int y_img = blockIdx.y * 8 + ty;  /* image row (rows flipped): raster row yi = S - 1 - y_img */
     const int yi = S - 1 - y_img;
@@ -426,15 +438,16 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     unsigned want = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if (fis[j] >= 0 && (list_all || ((nzm >> j) & 1u)))
+        if (!NO_LIST && fis[j] >= 0 && (list_all || ((nzm >> j) & 1u)))
             want |= 1u << j;
     __syncthreads(); /* s_clo / s_chi initialised */
-    if (K4) {
+    if (SPAN) {
         /* span of non-zero incoming gradient of this row (the warp's) and of the tile's columns */
         /* (pixels the line pass has to look at: those with an incoming gradient -- the only ones a scan gets a term
          * from -- and the covered ones, which own the scans) */
-        const unsigned spm = nzm | (fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
-                             (fis[3] >= 0 ? 8u : 0u);
+        const unsigned spm = nzm | (K4 ? ((fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
+                                          (fis[3] >= 0 ? 8u : 0u))
+                                       : 0u);
         int lo = spm ? x0 + (__ffs(spm) - 1) : 0x7fffffff, hi = spm ? x0 + (31 - __clz(spm)) : -1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -474,7 +487,7 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
         }
         s_base = (tot > 0) ? atomicAdd(cov_count + b, tot) : 0;
     }
-    if (K4 && threadIdx.x < 128) {
+    if (SPAN && threadIdx.x < 128) {
         const int xi = blockIdx.x * 128 + threadIdx.x;
         if (xi < S && s_chi[threadIdx.x] >= 0) {
             int *e = ext + (long)b * 4 * S;
@@ -512,7 +525,8 @@ struct HocPairGradSrc {
 
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocPairGradSrc G, float *__restrict__ g_rgb,
-                                int S, int k4_samples, int list_all_k4, int list_all_rest, int *__restrict__ ext,
+                                int S, int k4_samples, int list_all_k4, int list_all_rest, int scan_flags,
+                                int *__restrict__ ext,
                                 int *__restrict__ cov_count, int2 *__restrict__ cov_list, float *__restrict__ zero_a,
                                 long n_a, float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
                                 const int *__restrict__ row_lo)
@@ -535,6 +549,10 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     const int tile_x = blockIdx.y, tile_y = hoc_centre_out(blockIdx.z, gridDim.z);
     const bool K4 = b < k4_samples;
     const int list_all = K4 ? list_all_k4 : list_all_rest;
+    /* scan_flags: HOC_SCAN_SPAN_ALL = line spans for every sample (the fused line pass also runs the texture gradient of
+     * the samples without pseudo-gradient, row by row), HOC_SCAN_NO_LIST = nobody reads the list of covered pixels */
+    const bool SPAN = K4 || (scan_flags & HOC_SCAN_SPAN_ALL);
+    const bool NO_LIST = (scan_flags & HOC_SCAN_NO_LIST) != 0;
     const int r = b + G.row_offset;
     const int bp = r < G.pairs ? r : r - G.pairs;     /* the pair (r < 2 pairs) */
     const HocPairBwdDir &D = G.dir[r < G.pairs ? 1 : 0]; /* render 1 <- direction 1, render 2 <- direction 0 */
@@ -614,13 +632,14 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     unsigned want = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++)
-        if (fis[j] >= 0 && (list_all || ((nzm >> j) & 1u)))
+        if (!NO_LIST && fis[j] >= 0 && (list_all || ((nzm >> j) & 1u)))
             want |= 1u << j;
-    if (K4) {
+    if (SPAN) {
         /* (pixels the line pass has to look at: those with an incoming gradient -- the only ones a scan gets a term
          * from -- and the covered ones, which own the scans) */
-        const unsigned spm = nzm | (fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
-                             (fis[3] >= 0 ? 8u : 0u);
+        const unsigned spm = nzm | (K4 ? ((fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
+                                          (fis[3] >= 0 ? 8u : 0u))
+                                       : 0u);
         int lo = spm ? x0 + (__ffs(spm) - 1) : 0x7fffffff, hi = spm ? x0 + (31 - __clz(spm)) : -1;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -659,7 +678,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         }
         s_base = (tot > 0) ? atomicAdd(cov_count + b, tot) : 0;
     }
-    if (K4 && threadIdx.x < 128) {
+    if (SPAN && threadIdx.x < 128) {
         const int xi = tile_x * 128 + threadIdx.x;
         if (xi < S && s_chi[threadIdx.x] >= 0) {
             int *e = ext + (long)b * 4 * S;
@@ -1201,7 +1220,9 @@ hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__re
                             const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                             const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
                             const int *__restrict__ ext, float scale, float *__restrict__ grad_faces,
-                            unsigned long long *__restrict__ det_gf)
+                            unsigned long long *__restrict__ det_gf, int k4_samples,
+                            const float *__restrict__ weight_map, const float *__restrict__ depth_map,
+                            float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gt)
 {
     hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     /* dynamic shared memory, per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (see the
@@ -1214,6 +1235,13 @@ hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__re
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
     const int b = blockIdx.x, axis = blockIdx.y, d0 = hoc_centre_out(blockIdx.z, S);
+    /* samples [0, k4_samples) get the pseudo-gradient; with grad_textures given the ROW CTAs of every sample also run
+     * backward_textures for the pixels of their row (three vertex values per face, weights and depth saved by the
+     * forward): they have staged each pixel's owning face and incoming gradient anyway */
+    const bool K4 = b < k4_samples;
+    const bool TEX = grad_textures != nullptr && axis == 1 && has_rgb;
+    if (!K4 && !TEX)
+        return;
     /* level 1: the span of the pixels that matter on this line (covered or with an incoming gradient: the scan pass) */
     const int *e = ext + (long)b * 4 * S;
     const int lo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
@@ -1251,6 +1279,34 @@ hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__re
         s_fi[i] = fi;
     }
     __syncthreads();
+
+    if (TEX) { /* d rgb / d c_k = t_k for the three vertex values of the owning face (hoc_cover_tex_depth, vertex mode) */
+        for (int i = tid; i < len; i += T) {
+            const float4 pg = s_pg[i];
+            const int fi = s_fi[i];
+            if (fi < 0 || fi >= F || (pg.y == 0.0f && pg.z == 0.0f && pg.w == 0.0f))
+                continue;
+            const int xi = lo + i, yi = d0; /* (axis 1: the line is raster row d0) */
+            const float *wm = weight_map + (((long)b * S + yi) * S + xi) * 3;
+            const float w3[3] = {wm[0], wm[1], wm[2]};
+            const float zp = depth_map[hoc_plane_off(layout, S, b, yi, xi)];
+            const float *src = faces + ((long)b * F + fi) * 9;
+            const long gt = ((long)b * F + fi) * 9;
+            const float gr[3] = {pg.y, pg.z, pg.w};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float t = hoc_tex_coord(w3[k], __ldg(src + 3 * k + 2), zp, 2, eps);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float v = t * gr[c];
+                    if (v != 0.0f)
+                        hoc_accum(grad_textures, gt + 3 * k + c, v, det_gt);
+                }
+            }
+        }
+        if (!K4)
+            return;
+    }
 
     HocBwdMaps M; /* (for the outside pixel of an inward term that lies beyond the staged span) */
     M.idx = idx;
@@ -1403,6 +1459,7 @@ hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__re
 
 /* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
 static int g_cover_ctas = 296;
+static int g_tex_in_line = 1; /* fused line pass: its row CTAs also run the (vertex-value) texture gradient (HOC_TUNE_TEX_IN_LINE) */
 static int g_fork_cover = 1; /* fused line pass: cover pass on a second stream (HOC_TUNE_FORK_COVER) */
 static int g_line_mode = 1; /* 1: fused line pass (hoc_raster_bwd_line2_kernel); 0: cover pass queues the scans, queued line pass */
 static int g_line_threads = 128, g_line_seg = 16, g_line_ctas = 0; /* 0: one CTA per line; > 0: that many CTAs walk the list */
@@ -1425,6 +1482,8 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_line_mode = value;
     else if (key == HOC_TUNE_FORK_COVER && (value == 0 || value == 1))
         g_fork_cover = value;
+    else if (key == HOC_TUNE_TEX_IN_LINE && (value == 0 || value == 1))
+        g_tex_in_line = value;
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -1457,8 +1516,9 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
 
 template <int CH>
 static cudaError_t hoc_launch_line2(const float *faces, const int32_t *face_index_map, const float *rgb,
-                                    const float *grad_rgb, const float *g_alpha, int B, int F, int S, float eps,
-                                    int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
+                                    const float *grad_rgb, const float *g_alpha, int B, int k4_samples, int F, int S,
+                                    float eps, int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
+                                    const float *weight_map, const float *depth_map, float *grad_textures,
                                     cudaStream_t st)
 {
     /* two float4 and one int per staged pixel, + padding for the unrolled chunk loop: 9.8 KB at S = 256, 74 KB at 2048 */
@@ -1472,7 +1532,8 @@ static cudaError_t hoc_launch_line2(const float *faces, const int32_t *face_inde
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
                (hoc_launch_pdl((hoc_raster_bwd_line2_kernel<CH>), dim3(B, 2, S), g_line_threads, smem, st, faces,
                                face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
-                               2.0f / (float)S, grad_faces, w.det_gf)));
+                               2.0f / (float)S, grad_faces, w.det_gf, k4_samples, weight_map, depth_map, grad_textures,
+                               w.det_gt)));
     return cudaSuccess;
 }
 
@@ -1694,6 +1755,13 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     const bool fused_line = k4 && g_line_mode == 1;
     const int k4_cover = fused_line ? 0 : k4_samples;
     const int list_k4 = fused_line ? (want_depth ? 1 : 0) : 1;
+    /* ... and when the textures are three vertex values per face and the forward saved its weights and depth (the
+     * frame-pair path), the ROW CTAs of the fused line pass -- they stage every pixel's gradient anyway -- run
+     * backward_textures too, for every sample: no cover pass at all, nobody reads the list of covered pixels */
+    const bool tex_in_line = fused_line && !want_depth && grad_rgb != nullptr && grad_textures != nullptr &&
+                             tex_grad_mode == HOC_TEX_GRAD_VERTEX && weight_map != nullptr && depth != nullptr &&
+                             g_tex_in_line;
+    const int scan_flags = tex_in_line ? (HOC_SCAN_SPAN_ALL | HOC_SCAN_NO_LIST) : 0;
     HocSideStream *side = nullptr; /* non-NULL between the fork and the join of the cover pass */
     std::unique_lock<std::mutex> side_lock(g_side_mutex, std::defer_lock);
     const size_t tex_bytes = (tex_grad_mode == HOC_TEX_GRAD_VERTEX)
@@ -1734,7 +1802,8 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
             }
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_launch_pdl((hoc_raster_bwd_scan_pair_kernel), pg4, 256, 0, st, 
-                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, list_k4, want_depth ? 1 : 0, w.ext, w.cov_count,
+                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, list_k4, want_depth ? 1 : 0, scan_flags, w.ext,
+                           w.cov_count,
                            w.cov_list, za, na, zb, nb, zc, nc, row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_pair_kernel");
         } else if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && (al & 15) == 0) {
@@ -1742,7 +1811,7 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan4_kernel<<<pg4, 256, 0, st>>>(
                            face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, k4_samples, list_k4,
-                           want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
+                           want_depth ? 1 : 0, scan_flags, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
                            (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan4_kernel");
         } else {
@@ -1750,7 +1819,7 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                    (hoc_raster_bwd_scan_kernel<<<pg, dim3(32, 8), 0, st>>>(
                        face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples, list_k4,
-                       want_depth ? 1 : 0, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
+                       want_depth ? 1 : 0, scan_flags, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
                        (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
         }
@@ -1762,7 +1831,7 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
          * block scheduler does not interleave the CTAs of two kernels that both have thousands pending) */
         const int max_ctas = fused_line ? 32 : g_cover_ctas;
         dim3 cg((unsigned)((npix + per - 1) / per < max_ctas ? (npix + per - 1) / per : max_ctas), B);
-        if (k4_cover > 0 || gt != nullptr || want_depth) {
+        if (!tex_in_line && (k4_cover > 0 || gt != nullptr || want_depth)) {
             /* fused line pass without depth gradient: the cover pass touches grad_textures only -- fork it */
             cudaStream_t cst = st;
             if (fused_line && !want_depth && !det && g_fork_cover) {
@@ -1807,7 +1876,7 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         }
     }
     const long nfaces = (long)B * F;
-    if (det && gt != nullptr && hoc_det_flush(w.det_gt, nfaces * tex_n, gt, 0, st) != cudaSuccess) {
+    if (det && gt != nullptr && !tex_in_line && hoc_det_flush(w.det_gt, nfaces * tex_n, gt, 0, st) != cudaSuccess) {
         hoc_set_error("hoc_raster_backward: flush of the texture accumulators failed");
         return HOC_ERR_CUDA;
     }
@@ -1827,11 +1896,13 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     }
     if (fused_line) {
         if (g_line_seg >= 16)
-            e = hoc_launch_line2<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
-                                     use_alpha, w, grad_faces, st);
+            e = hoc_launch_line2<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, tex_in_line ? B : k4_samples, k4_samples,
+                                     F, S, eps, layout, use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
+                                     tex_in_line ? gt : nullptr, st);
         else
-            e = hoc_launch_line2<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
-                                    use_alpha, w, grad_faces, st);
+            e = hoc_launch_line2<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, tex_in_line ? B : k4_samples, k4_samples,
+                                    F, S, eps, layout, use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
+                                    tex_in_line ? gt : nullptr, st);
         const cudaError_t le = cudaGetLastError(); /* (launch status of the line pass, before the join's calls) */
         if (side != nullptr) { /* join -- whatever happened above: the caller's stream waits for the cover pass */
             const cudaError_t je = cudaStreamWaitEvent(st, side->join, 0);
@@ -1859,6 +1930,10 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
             return HOC_ERR_CUDA;
         }
         HOC_CHECK_LAUNCH("hoc_raster_bwd_line_kernel");
+    }
+    if (det && tex_in_line && hoc_det_flush(w.det_gt, nfaces * tex_n, gt, 0, st) != cudaSuccess) {
+        hoc_set_error("hoc_raster_backward: flush of the texture accumulators failed");
+        return HOC_ERR_CUDA;
     }
     if (det) {
         if (k4 && hoc_det_flush(w.det_gf, nfaces * 9, grad_faces, 0, st) != cudaSuccess) {

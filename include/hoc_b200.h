@@ -116,6 +116,7 @@ const char *hoc_last_error(void);
                               * identical either way).  Measured: no gain inside the captured graph */
 #define HOC_TUNE_LINE_MODE 7  /* 1 (default): the pseudo-gradient of a line in one fused pass; 0: cover pass queues the scans of a line, queued line pass */
 #define HOC_TUNE_FORK_COVER 8 /* 1 (default): with the fused line pass the cover pass (texture gradient) runs on a second stream beside it */
+#define HOC_TUNE_TEX_IN_LINE 9 /* 1 (default): the fused line pass's row CTAs also run backward_textures (vertex-value textures, saved weights): no cover pass */
 #define HOC_TUNE_COVER_CTAS 6 /* CTAs per sample of the rasterizer backward's cover pass (grid-stride over the listed pixels) */
 int hoc_set_tuning(int key, int value);
 
