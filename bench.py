@@ -454,14 +454,13 @@ def run_native(args, rank, world, local_rank):
         # scatter's outputs
         "raster_bwd_pixel": (npx2 * 16 + 2 * ncrop * 1 + int(c * 2 * ncrop) * 36 + int(c * npx2) * 8 + nf * 36 + nf2 * 36
                              + 2 * 2 * Bp * V * 12),
-        # cover pass over both renders: per listed pixel entry8 + grad_rgb12 + weights12 + depth4 (+ rgb12 and a 2-byte
-        # scan record for the render with the pseudo-gradient); faces in; 9 sums per face out (+ grad_faces update)
-        "raster_bwd_pixel_k4": int(c * npx2) * 36 + int(c * npx) * 14 + nf2 * 72 + nf * 36,
+        # (cover pass: only in configurations whose texture gradient the line pass does not run; not in this workload)
         "raster_bwd_cover": int(c * npx2) * 36 + nf2 * 72,
         "raster_backward": nf * (36 + 12 + 36),                    # depth epilogue (only with dL/ddepth)
-        # line pass (one render): rgb, grad_rgb, idx once (both axes read the same maps); faces of the queued scans,
-        # grad_faces update
-        "raster_bwd_line": npx * (12 + 12 + 4) + nf * (36 + 36),
+        # line pass: rgb, grad_rgb, idx of the render with the pseudo-gradient once (both axes read the same maps), faces
+        # of its covered pixels, grad_faces update; texture gradient of both renders: grad_rgb12 (second render) +
+        # weights12 + depth4 at the valid pixels, 9 sums per face out
+        "raster_bwd_line": npx * (12 + 12 + 4) + nf * (36 + 36) + npx * 12 + int(c * npx2) * 16 + nf2 * 36,
         "mesh_scatter": nf * 36 + nf2 * 36 + 2 * Bp * Fm * 24 + 2 * 2 * Bp * V * 12,
         "pair_back": 2 * 2 * Bp * V * 12 + 2 * Bp * V * 12 + Bp * V * 12,
     }
@@ -476,7 +475,7 @@ def run_native(args, rank, world, local_rank):
                       "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
     table.sort(key=lambda r: -r["share_of_step"])
     kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve4_kernel",
-             "raster_bwd_pixel": "hoc_raster_bwd_scan_pair_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel",
+             "raster_bwd_pixel": "hoc_raster_bwd_scan_pair_kernel",
              "raster_bwd_cover": "hoc_raster_bwd_cover_kernel", "raster_backward": "hoc_raster_bwd_depth_kernel",
              "raster_bwd_line": "hoc_raster_bwd_line_kernel", "warp_photo_bwd": "hoc_warp_photo_pair_backward_kernel",
              "flow_finalize": "hoc_flow_finalize_warp_kernel", "mesh_scatter": "hoc_mesh_scatter_kernel",
@@ -492,7 +491,7 @@ def run_native(args, rank, world, local_rank):
     # once: the render whose geometry gradient is needed (H*W*28 + 2F*108 per sample) and the render that only
     # needs its texture gradient (H*W*16 + 2F*72).  `roofline_dominant`: the kernel with the largest share of the step.
     dom = next((r for r in table if r["algorithmic_bytes_per_launch"]), None)
-    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel", "raster_bwd_pixel_k4", "raster_bwd_cover",
+    bwd = [r for r in table if r["kernel"] in ("raster_bwd_pixel", "raster_bwd_cover",
                                                "raster_backward", "raster_bwd_line")]
     bwd_bytes = (npx * 28 + nf * 108) + (npx * 16 + nf * 72)
     bwd_ms_kernels = sum(r["avg_ms"] * r["launches_per_step"] for r in bwd)
@@ -545,7 +544,7 @@ def run_native(args, rank, world, local_rank):
         "launches_per_step": launches_per_step,
         "loss_global_mean": global_loss,
         "execution": "forward+backward captured once in a CUDA graph (handobjectconsist_b200.graphed), replayed per step; "
-                     "the frame-pair path of consist.py: 10 kernel nodes, no memset / ATen node",
+                     "the frame-pair path of consist.py: 9 kernel nodes, no memset / ATen node",
         "with_visuals": ({"value": 2 * PAIRS * args.steps / (vis_ms / 1e3), "ms_per_step": vis_ms / args.steps,
                           "note": "the same captured step when it also produces pair_consist's visualisation returns"}
                          if vis_ms else None),
@@ -560,9 +559,9 @@ def run_native(args, rank, world, local_rank):
             "share_of_step": bwd_ms / step_ms if bwd_ms else None,
             "launches_timed": len(group_ms), "sum_of_per_kernel_brackets_ms": bwd_ms_kernels,
             "timing": "ONE pair of CUDA events (external event nodes of an instrumented copy of the captured graph) around the "
-                      "three launches of hoc_pair_backward_raster; the pair adds ~4 us (profiles/timeline_r2.txt holds the "
+                      "two launches of hoc_pair_backward_raster; the pair adds ~4 us (profiles/timeline_r2.txt holds the "
                       "CUPTI durations of an un-instrumented replay)",
-            "note": "scan + cover + line pass over the stacked batch of both renders (one launch each); bytes: the render "
+            "note": "scan + line pass over the stacked batch of both renders (one launch each); bytes: the render "
                     "with the pseudo-gradient (H*W*28 + 2F*108 per sample) + the texture-only render (H*W*16 + 2F*72).  "
                     "The scan pass also computes the backward of pair_consist (fused in; its own operand bytes are NOT "
                     "added to the numerator), so the fraction is a lower bound for the rasterizer backward alone"},

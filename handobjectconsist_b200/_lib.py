@@ -21,11 +21,8 @@ HOC_TEX_GRAD_VERTEX = 1
 HOC_TUNE_LINE_THREADS = 1
 HOC_TUNE_LINE_SEGMENT = 2
 HOC_TUNE_DETERMINISTIC = 3
-HOC_TUNE_LINE_CTAS = 4
 HOC_TUNE_PDL = 5
 HOC_TUNE_COVER_CTAS = 6
-HOC_TUNE_LINE_MODE = 7
-HOC_TUNE_FORK_COVER = 8
 HOC_TUNE_TEX_IN_LINE = 9
 HOC_BWD_WORKSPACE_ZEROED = 1
 

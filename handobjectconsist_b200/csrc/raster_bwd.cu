@@ -10,32 +10,31 @@
  * passes over it) and scatters texture / depth gradients with one thread per pixel.  Here the work is
  * split by what it is parallel over:
  *
- *   hoc_raster_bwd_scan_kernel    pixel-parallel, pure streaming (one pass over face_index_map and the incoming
- *           gradients): per-line spans of non-zero incoming gradient (a pixel with zero incoming gradient
- *           contributes exactly nothing to any scan, so scans are clipped to the span), the list of covered
- *           pixels that have work (one global atomic per 32 x 32 tile), and the zero-fill of the two outputs.
- *   hoc_raster_bwd_cover_kernel   the work of the covered pixels, spread evenly over the GPU (covered pixels
- *           cluster in a few tiles, the list un-clusters them): texture / depth gradient of the owning face --
- *           weights and depth come from the forward's maps or are recomputed with the forward's functions
- *           (bit-identical); the reference's two sampling maps (64 B/px) are never stored -- and the
- *           pseudo-gradient run FROM THE PIXELS: a pixel owned by face f lies on column x and row y of f; for
- *           each of the 3 edges x 2 axes (one warp per combination, 32 pixels per warp) it evaluates that column
- *           of the edge once and (a) adds its own term of the short INWARD scan (the reference visits exactly
- *           the owned pixels between the edge and the opposite edge), (b) if it is the pixel just inside the
- *           edge, queues the long OUTWARD scan that starts there on the line it runs along (2-byte record).
- *           There is no per-face pass: a face that owns no pixel has no term in either scan.
+ *   hoc_raster_bwd_scan_kernel    pixel-parallel, streaming (one pass over face_index_map and the incoming gradients;
+ *   (_scan4_, _scan_pair_)        in the frame-pair path the pass COMPUTES the incoming gradient: the backward of
+ *           pair_consist is fused in): per-line spans of the pixels that matter -- covered ones, which own the scans,
+ *           and those with a non-zero incoming gradient, the only ones a scan gets a term from (scans are clipped to
+ *           the span: exact) --, the list of pixels with a texture / depth gradient when a cover pass follows, and the
+ *           zero-fill of the accumulated outputs.
+ *   hoc_raster_bwd_line_kernel    line-parallel, the pseudo-gradient run FROM THE PIXELS: every term of
+ *           backward_pixel_map lives on one image column or row, so a CTA stages its line once (owning face, colour,
+ *           incoming gradient) and runs one candidate per (covered pixel, edge of its face): that column of the edge
+ *           is evaluated once, the pixel adds its own term of the short INWARD scan (the reference visits exactly the
+ *           owned pixels between the edge and the opposite edge) and, if it is the pixel just inside the edge, the
+ *           lane holds the long OUTWARD scan that starts there; the warp's scans are cut into 16-pixel chunks summed
+ *           out of shared memory one per lane.  There is no per-face pass: a face that owns no pixel has no term in
+ *           either scan.  Its row CTAs also run backward_textures when the textures are three vertex values per
+ *           face and the forward saved weights and depth (the frame-pair path).
+ *   hoc_raster_bwd_cover_kernel   otherwise: texture / depth gradient of the listed pixels, spread evenly over the GPU
+ *           -- weights and depth come from the forward's maps or are recomputed with the forward's functions
+ *           (bit-identical); the reference's two sampling maps (64 B/px) are never stored.
  *   hoc_raster_bwd_depth_kernel   face-parallel epilogue of backward_depth_map (only when dL/ddepth exists).
- *   hoc_raster_bwd_line_kernel    line-parallel: a CTA owns one image row or column, stages the span of that line
- *           (P = sum_ch I_ch g_ch and g of every pixel) in shared memory ONCE; its warps then work independently:
- *           32 queued scans are set up one per lane, cut into 16-pixel chunks, and every lane sums one chunk out
- *           of shared memory (branch-free, MUFU.RCP) -- it finds its scan with a 5-step shuffle search over the
- *           warp's prefix sums -- and adds the chunk's two vertex contributions to grad_faces.
  *
- * Measured progression on bench.py's workload (B = 16 renders of 9104 faces at 256 x 256, B200, in-graph):
- * 548 us (one warp per face) -> 245 -> 121 -> 93 (pixel / face / line passes) -> 55 us (this decomposition).
+ * Measured progression on bench.py's workload (16 renders of 9104 faces at 256 x 256 with the pseudo-gradient + 16
+ * with the texture gradient only, B200, in-graph): 548 us (one warp per face, round 1) -> 245 -> 121 -> 93 (pixel /
+ * face / line passes) -> 55 + 25 us (scan, cover with scan queues, queued line pass; the two renders on two streams)
+ * -> 60 us for both renders in one batch -> 48 us (scan with the pair_consist backward inside + this line pass).
  */
-#include <mutex>
-
 #include "hoc_common.cuh"
 #include "hoc_det.cuh"
 #include "raster_math.h"
@@ -49,35 +48,23 @@
 #define EXT_COL_HI 3
 
 /* Workspace carved by hoc_raster_backward (256-byte aligned regions):
- *   ext        int    [B][4][S]      {row_nlo, row_hi, col_nlo, col_hi}: span of non-zero incoming gradient, stored as
- *                                    S - lo and hi + 1 so that both ends are max-reduced from 0      (zero-filled)
- *   cov_count  int    [B]            covered pixels listed per sample                      (zero-filled)
- *   line_count int    [B][2][S]      outward scans queued on each line (axis 0: column x, axis 1: row y)  (zero-filled)
- *   n_lines    int    [1]            lines that hold at least one scan                      (zero-filled)
- *   line_list  int    [B*2*S]        their ids ((b * 2 + axis) * S + d0), in the order of their first scan: the line
- *                                    pass walks this list instead of launching a CTA per line (5 us of empty CTAs at
- *                                    16 samples of 256 x 256)
- *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled)
- *   cov_list   int2   [B][S*S]       the covered pixels that have work, in tile order: (yi * S + xi, owning face) --
- *                                    the face rides along so that the cover pass starts one dependent load earlier
- *   emitters   uint   [B][2][S][3S]  the queues: position on the line | edge << 11 | owning face << 13 (the face rides
- *                                    along so that the line pass starts one dependent load earlier).  3S is a hard
- *                                    bound: a scan is keyed by its inside pixel on the line, which is owned by exactly
- *                                    one face with 3 edges; only the used part is ever touched */
+ *   ext        int    [B][4][S]      {row_nlo, row_hi, col_nlo, col_hi}: span of the pixels of a line that matter, stored
+ *                                    as S - lo and hi + 1 so that both ends are max-reduced from 0    (zero-filled)
+ *   cov_count  int    [B]            pixels listed per sample                                         (zero-filled)
+ *   acc_d      float  [B][F][3]      sum over owned pixels of dL/ddepth * depth^2 * w_k   (zero-filled, depth gradient only)
+ *   cov_list   int2   [B][S*S]       the pixels with a texture / depth gradient, in tile order: (yi * S + xi, owning
+ *                                    face) -- the face rides along so that the cover pass starts one dependent load
+ *                                    earlier; only the used part is ever touched */
 struct HocBwdWorkspace {
     int *ext;
     int *cov_count;
-    int *line_count;
-    int *n_lines;
-    int *line_list;
     float *acc_d;
     int2 *cov_list;
-    unsigned int *emitters;
     /* reproducible mode only (hoc_det.cuh): fixed-point accumulators of grad_faces / grad_textures / acc_d,
      * two 64-bit words per float, one contiguous zero-fill */
     unsigned long long *det_gf, *det_gt, *det_ad;
     size_t det_bytes;
-    size_t count_bytes, acc_bytes; /* ext + cov_count + line_count, then acc_d: one contiguous zero-fill */
+    size_t count_bytes, acc_bytes; /* ext + cov_count, then acc_d: one contiguous zero-fill */
     size_t total;
 };
 
@@ -92,20 +79,12 @@ static HocBwdWorkspace hoc_bwd_workspace(void *base, int B, int F, int S, int te
     off = up(off + sizeof(int) * 4 * (size_t)B * S);
     w.cov_count = (int *)(p + off);
     off = up(off + sizeof(int) * (size_t)B);
-    w.line_count = (int *)(p + off);
-    off = up(off + sizeof(int) * 2 * (size_t)B * S);
-    w.n_lines = (int *)(p + off);
-    off = up(off + sizeof(int));
     w.count_bytes = off - zero_begin;
     w.acc_d = (float *)(p + off); /* directly after the counters: one memset covers both */
     w.acc_bytes = sizeof(float) * 3 * (size_t)B * F;
     off = up(off + w.acc_bytes);
-    w.line_list = (int *)(p + off);
-    off = up(off + sizeof(int) * 2 * (size_t)B * S);
     w.cov_list = (int2 *)(p + off);
     off = up(off + sizeof(int2) * (size_t)B * S * S);
-    w.emitters = (unsigned int *)(p + off);
-    off = up(off + sizeof(unsigned int) * 2 * (size_t)B * S * 3 * (size_t)S);
     w.det_gf = w.det_gt = w.det_ad = nullptr;
     w.det_bytes = 0;
     if (det) {
@@ -154,74 +133,16 @@ __device__ __forceinline__ float hoc_rcp_approx(float x)
     return r;
 }
 
-/* One (edge, axis) of the face owning pixel (xi, yi), in two stages so that a thread can run both axes of its edge
- * with their dependent loads in flight together.
- * Stage A (geometry only): evaluates the pixel's column of the edge once; tells whether the pixel is the one just inside
- * the edge (an outward scan is then queued on the line it runs along, hoc_k4_queue_push) and whether it has a term in
- * the short INWARD scan
- * of that column (the reference visits exactly the owned pixels between the edge and the opposite edge) and, if so,
- * which pixel just outside the edge that term compares with.
- * Stage B: the term itself -- delta from the pixel and the outside pixel, -delta / dist to the two vertices of the edge.
- * (ax..cy) are the face's vertices in NDC rotated so that A is the first vertex of the edge; gfA / gfB index the x
- * component of vertex A / B in grad_faces.  I / g: (alpha, r, g, b) of the pixel and its incoming gradient. */
+/* One (edge, axis, column) of the face owning a pixel: what the line pass has evaluated for it (hoc_k4_edge_pts,
+ * hoc_k4_column) when it adds the pixel's own term of the short INWARD scan of that column (the reference visits
+ * exactly the owned pixels between the edge and the opposite edge): delta from the pixel and the pixel just outside the
+ * edge, -delta / dist to the two vertices of the edge.  gfA / gfB index the x component of vertex A / B in grad_faces;
+ * I / g: (alpha, r, g, b) of the pixel and its incoming gradient. */
 struct HocK4Stage {
     HocK4Edge E;
     float d1_cross;
-    int d0, d1p, ox, oy;
-    bool need; /* the pixel has a term in the inward scan of its column */
-    bool push; /* the pixel is the one just inside the edge: an outward scan starts here */
+    int d0, d1p;
 };
-
-__device__ __forceinline__ void hoc_k4_stage_a(float ax, float ay, float bx, float by, float cx, float cy, int edge,
-                                               int axis, int xi, int yi, const HocBwdMaps &M, HocK4Stage &T)
-{
-    T.need = false;
-    T.push = false;
-    hoc_k4_edge_pts(ax, ay, bx, by, cx, cy, M.S, axis, &T.E);
-    const int d0 = axis == 0 ? xi : yi, d1p = axis == 0 ? yi : xi;
-    T.d0 = d0;
-    T.d1p = d1p;
-    if (d0 < T.E.d0_from || d0 > T.E.d0_to)
-        return;
-    int d1_in, d1_out;
-    if (!hoc_k4_column(&T.E, M.S, d0, &T.d1_cross, &d1_in, &d1_out))
-        return;
-    T.push = d1_in == d1p;
-    const int lim = hoc_k4_inward_limit(&T.E, d0);
-    const int d1_from = max(min(d1_in, lim), 0);
-    const int d1_to = min(max(d1_in, lim), M.S - 1);
-    if (d1_from <= d1p && d1p <= d1_to) {
-        T.need = true;
-        T.ox = axis == 0 ? d0 : d1_out;
-        T.oy = axis == 0 ? d1_out : d0;
-    }
-}
-
-/* Queue the outward scans of a warp's pixels on their lines (4-byte record: position on the line | edge << 11 | face << 13).  Called
- * by ALL 32 lanes.  Pixels that are neighbours in the list are neighbours in the image, so many lanes push on the same
- * line (a row, for axis 1): lanes are grouped by line with one MATCH, the group's leader reserves the slots with ONE
- * atomic and the first scan ever queued on a line also appends the line to the list the line pass walks.  (One atomic
- * with return per pixel was the hottest stall of the pass: 5 of its 23 us.) */
-__device__ __forceinline__ void hoc_k4_queue_push(bool push, int line, int d1p, int edge, int fi, int S,
-                                                  int *__restrict__ line_count, int *__restrict__ n_lines,
-                                                  int *__restrict__ line_list, unsigned int *__restrict__ emitters)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned grp = __match_any_sync(HOC_FULL_MASK, push ? line : -1 - lane);
-    const int leader = __ffs(grp) - 1;
-    int base = 0;
-    if (push && lane == leader) {
-        base = atomicAdd(line_count + line, __popc(grp));
-        if (base == 0)
-            line_list[atomicAdd(n_lines, 1)] = line;
-    }
-    base = __shfl_sync(HOC_FULL_MASK, base, leader);
-    if (push) {
-        const int pos = base + __popc(grp & ((1u << lane) - 1u));
-        if (pos < 3 * S) /* cannot fail (see HocBwdWorkspace); keeps a corrupted map from overrunning */
-            emitters[(long)line * 3 * S + pos] = (unsigned)d1p | ((unsigned)edge << 11) | ((unsigned)fi << 13);
-    }
-}
 
 __device__ __forceinline__ void hoc_k4_stage_b(const HocK4Stage &T, int axis, const HocBwdMaps &M, const float *I,
                                                const float *I_out, const float *g, float eps,
@@ -257,7 +178,7 @@ __device__ __forceinline__ void hoc_k4_stage_b(const HocK4Stage &T, int axis, co
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
                            const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S, int layout,
-                           int k4_samples, int list_all_k4, int list_all_rest, int scan_flags, int *__restrict__ ext,
+                           int k4_samples, int list_all, int scan_flags, int *__restrict__ ext,
                            int *__restrict__ cov_count,
                            int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
                            float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
@@ -268,7 +189,6 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
     const bool K4 = (int)blockIdx.z < k4_samples;
     const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
     const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
-    const int list_all = K4 ? list_all_k4 : list_all_rest;
     /* scan_flags: HOC_SCAN_SPAN_ALL = line spans for every sample (the fused line pass also runs the texture gradient of
      * the samples without pseudo-gradient, row by row), HOC_SCAN_NO_LIST = nobody reads the list of covered pixels */
     const bool SPAN = K4 || (scan_flags & HOC_SCAN_SPAN_ALL);
@@ -382,7 +302,7 @@ hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const flo
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
                             const float *__restrict__ g_rgb_rest, const float *__restrict__ g_alpha_k4, int S,
-                            int k4_samples, int list_all_k4, int list_all_rest, int scan_flags, int *__restrict__ ext,
+                            int k4_samples, int list_all, int scan_flags, int *__restrict__ ext,
                            int *__restrict__ cov_count,
                             int2 *__restrict__ cov_list, float *__restrict__ zero_a, long n_a,
                             float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
@@ -401,7 +321,6 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
     const bool K4 = b < k4_samples;
     const float *g_rgb = K4 ? g_rgb_k4 : g_rgb_rest;
     const float *g_alpha = K4 ? g_alpha_k4 : nullptr;
-    const int list_all = K4 ? list_all_k4 : list_all_rest;
     /* scan_flags: HOC_SCAN_SPAN_ALL = line spans for every sample (the fused line pass also runs the texture gradient of
      * the samples without pseudo-gradient, row by row), HOC_SCAN_NO_LIST = nobody reads the list of covered pixels */
     const bool SPAN = K4 || (scan_flags & HOC_SCAN_SPAN_ALL);
@@ -525,7 +444,7 @@ struct HocPairGradSrc {
 
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocPairGradSrc G, float *__restrict__ g_rgb,
-                                int S, int k4_samples, int list_all_k4, int list_all_rest, int scan_flags,
+                                int S, int k4_samples, int list_all, int scan_flags,
                                 int *__restrict__ ext,
                                 int *__restrict__ cov_count, int2 *__restrict__ cov_list, float *__restrict__ zero_a,
                                 long n_a, float *__restrict__ zero_b, long n_b, float *__restrict__ zero_c, long n_c,
@@ -548,7 +467,6 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
     const int b = blockIdx.x;
     const int tile_x = blockIdx.y, tile_y = hoc_centre_out(blockIdx.z, gridDim.z);
     const bool K4 = b < k4_samples;
-    const int list_all = K4 ? list_all_k4 : list_all_rest;
     /* scan_flags: HOC_SCAN_SPAN_ALL = line spans for every sample (the fused line pass also runs the texture gradient of
      * the samples without pseudo-gradient, row by row), HOC_SCAN_NO_LIST = nobody reads the list of covered pixels */
     const bool SPAN = K4 || (scan_flags & HOC_SCAN_SPAN_ALL);
@@ -804,15 +722,10 @@ __device__ __forceinline__ void hoc_cover_tex_depth(const float *__restrict__ fa
 }
 
 /*
- * Cover pass: the work of the covered pixels, spread evenly over the GPU (the scan pass listed them).  128 threads.
- * K4 (per sample: b < k4_samples) = false: one listed pixel per thread -> texture / depth gradient.
- * K4 = true:  the CTA works on 32 listed pixels at a time: warp e < 3 runs EDGE e of the pseudo-gradient for the 32
- *             pixels -- both axes: the face, the pixel's colour and its incoming gradient are loaded once, the two
- *             columns are evaluated (stage A: inward-scan membership, outward scans queued on their lines), the two
- *             outside pixels are fetched together, the two terms added (stage B); warp 3 runs the pixels' texture /
- *             depth gradient.  Warps are independent.  (Round 1 gave every (edge, axis) its own warp: six warps loaded
- *             the same pixel and face, 3 000 CTAs of 224 threads at 40 % occupancy, each a chain of five dependent
- *             loads -- the pass was bound by occupancy x latency.)
+ * Cover pass: the texture / depth gradient of the pixels the scan pass listed (those with such a gradient), one pixel
+ * per thread, spread evenly over the GPU (covered pixels cluster in a few tiles, the list un-clusters them).  Not
+ * launched when the line pass runs the texture gradient itself (vertex-value textures, saved weights: the frame-pair
+ * path).
  */
 #define CV_THREADS 128
 template <bool TS2>
@@ -822,109 +735,23 @@ template <bool TS2>
 #define CV_BOUNDS __launch_bounds__(CV_THREADS)
 #endif
 __global__ void CV_BOUNDS
-hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
-                            const float *__restrict__ rgb, const float *__restrict__ weight_map,
+hoc_raster_bwd_cover_kernel(const float *__restrict__ faces, const float *__restrict__ weight_map,
                             const float *__restrict__ depth_map, const float *__restrict__ g_rgb,
-                            const float *__restrict__ g_alpha, const float *__restrict__ g_depth, int F, int S, int ts,
-                            float near_, float far_, float eps, int layout, int use_alpha, int tex_mode,
-                            const int *__restrict__ cov_count, const int2 *__restrict__ cov_list,
-                            float *__restrict__ acc_d, int *__restrict__ line_count, int *__restrict__ n_lines,
-                            int *__restrict__ line_list, unsigned int *__restrict__ emitters,
-                            float *__restrict__ grad_faces,
-                            float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gf,
-                            unsigned long long *__restrict__ det_gt, unsigned long long *__restrict__ det_ad,
-                            int k4_samples)
+                            const float *__restrict__ g_depth, int F, int S, int ts, float near_, float far_, float eps,
+                            int layout, int tex_mode, const int *__restrict__ cov_count,
+                            const int2 *__restrict__ cov_list, float *__restrict__ acc_d,
+                            float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gt,
+                            unsigned long long *__restrict__ det_ad)
 {
     hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     const int b = blockIdx.y;
     const int count = min(cov_count[b], S * S);
     const int2 *list = cov_list + (long)b * S * S;
-    const int32_t *idx = face_index_map + (long)b * S * S;
-    const bool K4 = b < k4_samples; /* uniform per CTA */
-    if (!K4) {
-        for (int i = blockIdx.x * CV_THREADS + threadIdx.x; i < count; i += gridDim.x * CV_THREADS) {
-            const int2 e = list[i];
-            const int yi = e.x / S, xi = e.x - yi * S;
-            hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, e.y, xi, yi, F, S, ts, near_, far_,
-                                     eps, layout, tex_mode, acc_d, grad_textures, det_ad, det_gt);
-        }
-        return;
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    HocBwdMaps M;
-    M.idx = idx;
-    M.rgb = rgb;
-    M.g_rgb = g_rgb;
-    M.g_alpha = g_alpha;
-    M.S = S;
-    M.layout = layout;
-    M.b = b;
-    M.use_alpha = (use_alpha != 0) && (g_alpha != nullptr);
-    M.use_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {
-        const int i = base + lane;
-        const bool live = i < count;
-        const int2 e = live ? list[i] : make_int2(0, -1);
-        const int p = e.x, fi = e.y;
-        const int yi = p / S, xi = p - yi * S;
-        if (wid == 3) {
-            if (fi >= 0)
-                hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, fi, xi, yi, F, S, ts, near_,
-                                         far_, eps, layout, tex_mode, acc_d, grad_textures, det_ad, det_gt);
-            continue;
-        }
-        /* (the 32 lanes of an edge warp stay converged up to the queue push: it is a warp-wide operation) */
-        const int edge = wid;
-        const int ia = edge, ib = (edge == 2) ? 0 : edge + 1, ic = (edge == 0) ? 2 : edge - 1;
-        float I[4] = {1.0f, 0.0f, 0.0f, 0.0f}, g[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        HocK4Stage T0, T1;
-        T0.need = T0.push = T1.need = T1.push = false;
-        T0.d0 = T1.d0 = T0.d1p = T1.d1p = 0;
-        if (fi >= 0) {
-            const float *src = faces + ((long)b * F + fi) * 9;
-            const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
-            const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
-            const float cx = __ldg(src + 3 * ic), cy = __ldg(src + 3 * ic + 1);
-            if (M.use_alpha)
-                g[0] = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
-            if (M.use_rgb) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const long o = hoc_rgb_off(layout, S, b, yi, xi, k);
-                    I[1 + k] = rgb[o];
-                    g[1 + k] = g_rgb[o];
-                }
-            }
-            /* the owner of a pixel is front-facing with finite xy (the forward's tests); re-checked so that a
-             * corrupted map cannot produce garbage.  hoc_face_back on the rotated vertices is NOT bit-identical,
-             * so the face is tested in its stored order. */
-            float f[9];
-            f[0] = (edge == 0) ? ax : ((edge == 1) ? cx : bx);
-            f[1] = (edge == 0) ? ay : ((edge == 1) ? cy : by);
-            f[3] = (edge == 0) ? bx : ((edge == 1) ? ax : cx);
-            f[4] = (edge == 0) ? by : ((edge == 1) ? ay : cy);
-            f[6] = (edge == 0) ? cx : ((edge == 1) ? bx : ax);
-            f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
-            f[2] = f[5] = f[8] = 0.0f;
-            if (hoc_face_xy_finite(f) && !hoc_face_back(f)) {
-                hoc_k4_stage_a(ax, ay, bx, by, cx, cy, edge, 0, xi, yi, M, T0);
-                hoc_k4_stage_a(ax, ay, bx, by, cx, cy, edge, 1, xi, yi, M, T1);
-            }
-        }
-        hoc_k4_queue_push(T0.push, (b * 2 + 0) * S + T0.d0, T0.d1p, edge, fi, S, line_count, n_lines, line_list,
-                          emitters);
-        hoc_k4_queue_push(T1.push, (b * 2 + 1) * S + T1.d0, T1.d1p, edge, fi, S, line_count, n_lines, line_list,
-                          emitters);
-        float O0[4] = {0.f, 0.f, 0.f, 0.f}, O1[4] = {0.f, 0.f, 0.f, 0.f};
-        if (T0.need)
-            hoc_load_I(M, T0.ox, T0.oy, O0);
-        if (T1.need)
-            hoc_load_I(M, T1.ox, T1.oy, O1);
-        const long gf = ((long)b * F + fi) * 9;
-        if (T0.need)
-            hoc_k4_stage_b(T0, 0, M, I, O0, g, eps, grad_faces, gf + 3 * ia, gf + 3 * ib, det_gf);
-        if (T1.need)
-            hoc_k4_stage_b(T1, 1, M, I, O1, g, eps, grad_faces, gf + 3 * ia, gf + 3 * ib, det_gf);
+    for (int i = blockIdx.x * CV_THREADS + threadIdx.x; i < count; i += gridDim.x * CV_THREADS) {
+        const int2 e = list[i];
+        const int yi = e.x / S, xi = e.x - yi * S;
+        hoc_cover_tex_depth<TS2>(faces, weight_map, depth_map, g_rgb, g_depth, b, e.y, xi, yi, F, S, ts, near_, far_, eps,
+                                 layout, tex_mode, acc_d, grad_textures, det_ad, det_gt);
     }
 }
 
@@ -961,7 +788,7 @@ hoc_raster_bwd_depth_kernel(const float *__restrict__ faces, const float *__rest
     }
 }
 
-/* One queued outward scan, set up by one lane: everything the chunk loop needs. */
+/* One outward scan, held by one lane: everything the chunk loop needs. */
 struct HocLineScan {
     float cA, cB;     /* dist to vertex A / B = c * (d1 - cross) + e: c already times 2 / S; 0 for a vertex without term */
     float eA, eB;     /* +-eps with the sign of c * (d1 - cross), which is the same for every pixel of an outward scan
@@ -973,250 +800,37 @@ struct HocLineScan {
     int nchunk;
 };
 
-template <int CH>
-__device__ __forceinline__ void hoc_line_scan_setup(unsigned rec, bool valid, const float *__restrict__ faces,
-                                                    const float *__restrict__ rgb, bool has_rgb, int b, int F, int S,
-                                                    int layout, int axis, int d0, int lo, int hi, float eps,
-                                                    float scale, HocLineScan &sc)
-{
-    sc.cA = sc.cB = 0.0f;
-    sc.eA = sc.eB = 1.0f;
-    sc.cross = 0.0f;
-    sc.I1 = sc.I2 = sc.I3 = 0.0f;
-    sc.from = 0;
-    sc.to = -1;
-    sc.gfA = sc.gfB = -1;
-    sc.nchunk = 0;
-    if (!valid)
-        return;
-    const int d1_in = rec & 0x7ff, edge = (rec >> 11) & 3, fi = (int)(rec >> 13);
-    if (edge > 2 || fi >= F)
-        return; /* cannot happen (the cover pass wrote the record); keeps a corrupted queue inside the arrays */
-    const int xin = axis == 0 ? d0 : d1_in, yin = axis == 0 ? d1_in : d0;
-    const int ia = edge, ib = (edge == 2) ? 0 : edge + 1;
-    const float *src = faces + ((long)b * F + fi) * 9;
-    const float ax = __ldg(src + 3 * ia), ay = __ldg(src + 3 * ia + 1);
-    const float bx = __ldg(src + 3 * ib), by = __ldg(src + 3 * ib + 1);
-    if (has_rgb) { /* rgb of the inside pixel (its alpha is 1: folded into P) */
-        sc.I1 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 0)];
-        sc.I2 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 1)];
-        sc.I3 = rgb[hoc_rgb_off(layout, S, b, yin, xin, 2)];
-    }
-    HocK4Edge E;
-    hoc_k4_edge_pts(ax, ay, bx, by, 0.0f, 0.0f, S, axis, &E);
-    int d1_chk, d1_out;
-    /* always true: the cover pass queued this column because it passed the same test */
-    if (!hoc_k4_column(&E, S, d0, &sc.cross, &d1_chk, &d1_out))
-        return;
-    sc.from = (0 < E.dir) ? max(d1_out, lo) : lo;
-    sc.to = (0 < E.dir) ? hi : min(d1_out, hi);
-    if (sc.to < sc.from)
-        return;
-    HocK4Col C;
-    hoc_k4_col(&E, S, d0, sc.cross, &C);
-    /* d1_out lies strictly outside the crossing (floor / ceil in hoc_k4_column) and the scan runs away from it: t has
-     * the sign of E.dir on the whole scan, so the reference's `dist > 0 ? dist + eps : dist - eps` is one constant */
-    const float t_first = (float)d1_out - sc.cross;
-    const int gbase = (int)(((long)b * F + fi) * 9) + (1 - axis);
-    if (C.hasA) {
-        sc.cA = C.cA * scale; /* scale = 2 / S, divided on the host (the same IEEE quotient) */
-        sc.eA = (0.0f < sc.cA * t_first) ? eps : -eps;
-        sc.gfA = gbase + ia * 3;
-    }
-    if (C.hasB) {
-        sc.cB = C.cB * scale;
-        sc.eB = (0.0f < sc.cB * t_first) ? eps : -eps;
-        sc.gfB = gbase + ib * 3;
-    }
-    sc.nchunk = (sc.to - sc.from + CH) / CH;
-}
-
-/*
- * Line pass.  One CTA per image column (axis 0) or row (axis 1) of one sample, sample fastest and lines ordered from
- * the image centre outwards: the lines that carry the most scans (meshes are centred by the crop) are dispatched
- * first, the empty border lines last.  One line per CTA is the measured optimum on B200: the pass is bound by the
- * CTA's chain of dependent loads, not by arithmetic, so the chain is kept at three levels -- (1) the line's scan count
- * and gradient span, (2) the queue records of the first 32 scans of every warp AND the line's pixels (staged in shared
- * memory), (3) the faces and inside pixels of those scans (the record carries the face) -- and the scans' geometry is
- * set up while the staging of other warps is still in flight; a persistent grid walking the lines and splitting a
- * line's scans over several CTAs were measured too and lost.
- */
 #define LN_THREADS 256
-template <int CH, bool WALK>
 #ifdef LN_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
 #define LN_BOUNDS __launch_bounds__(LN_THREADS, LN_MINB)
 #else
 #define LN_BOUNDS __launch_bounds__(LN_THREADS)
 #endif
-__global__ void LN_BOUNDS
-hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
-                           const float *__restrict__ rgb, const float *__restrict__ g_rgb,
-                           const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
-                           const int *__restrict__ ext, const int *__restrict__ line_count,
-                           const int *__restrict__ n_lines, const int *__restrict__ line_list, int max_lines,
-                           float scale, const unsigned int *__restrict__ emitters,
-                           float *__restrict__ grad_faces,
-                           unsigned long long *__restrict__ det_gf)
-{
-    hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
-    /* dynamic shared memory: float4 s_line4[S + 16]
-     * per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (the inside pixel of a scan
-     * is covered, its alpha is 1): delta = sum_ch (I_ch - Iin_ch) g_ch = P - sum_rgb Iin_ch g_ch -- one 16-byte
-     * shared load and three FMAs per scanned pixel (<= 1 ulp of |P| from the reference's summation order,
-     * gradients carry 1e-3) */
-    extern __shared__ float4 s_line4[];
-    /* Two ways to hand lines to CTAs (HOC_TUNE_LINE_CTAS), two instances of the kernel.  WALK = false (default): one CTA per line of every sample,
-     * sample fastest and lines ordered from the image centre outwards; an empty line costs its CTA one round of
-     * loads.  WALK = true: a fixed grid walks the list of non-empty lines the cover pass built (in the order
-     * of their first scan): no empty CTAs, but no heavy-first order either -- measured 25.4 us against 23.0 at 16
-     * samples of 256 x 256, where one wave holds every non-empty line anyway. */
-    /* (default mode: grid (samples, 2, S) -- x is dispatched fastest -- so that the CTA's line costs no division: the
-     * prologue runs in all 4 warps of all 2 B S CTAs and was HALF of the pass's instructions when it decoded a linear
-     * index with 64-bit divisions) */
-    const int n_list = WALK ? min(*n_lines, max_lines) : 1;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
-    const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
-    const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    for (int li = WALK ? (int)blockIdx.x : 0; li < n_list; li += gridDim.x) {
-        int b, axis, d0;
-        if (WALK) {
-            if (li != (int)blockIdx.x)
-                __syncthreads(); /* every warp is done with the previous line's staged span */
-            const int l = line_list[li];
-            d0 = l % S;
-            axis = (l / S) & 1;
-            b = l / (2 * S);
-        } else {
-            b = blockIdx.x;
-            axis = blockIdx.y;
-            d0 = hoc_centre_out(blockIdx.z, S);
-        }
-        const int line = (b * 2 + axis) * S + d0;
-        /* level 1: three independent loads */
-        const int *e = ext + (long)b * 4 * S;
-        const int n_raw = line_count[line];
-        const int lo_raw = e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
-        const int hi_raw = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0];
-        const int n = min(n_raw, 3 * S);
-        const int lo = S - lo_raw, hi = hi_raw - 1;
-        if (n == 0 || lo > hi)
-            continue; /* no scan, or no incoming gradient anywhere on this line: every outward scan sums zeros */
-        const int len = hi - lo + 1;
-        const unsigned int *queue = emitters + (long)line * 3 * S;
-        const int32_t *idx = face_index_map + (long)b * S * S;
-
-        /* level 2: the records of the first round of scans, and the span of non-zero gradient into shared memory */
-        const int q_first = wid * 32 + lane;
-        const unsigned rec_first = (q_first < n) ? queue[q_first] : 0u;
-        for (int i = tid; i < len; i += T) {
-            const int d1 = lo + i;
-            const int xi = axis == 0 ? d0 : d1, yi = axis == 0 ? d1 : d0;
-            float4 pg = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (has_rgb) {
-                const long o0 = hoc_rgb_off(layout, S, b, yi, xi, 0), o1 = hoc_rgb_off(layout, S, b, yi, xi, 1),
-                           o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
-                pg.y = g_rgb[o0];
-                pg.z = g_rgb[o1];
-                pg.w = g_rgb[o2];
-                pg.x = rgb[o0] * pg.y + rgb[o1] * pg.z + rgb[o2] * pg.w;
-            }
-            if (has_alpha) {
-                const float ga = g_alpha[hoc_plane_off(layout, S, b, yi, xi)];
-                const float a = (idx[(long)yi * S + xi] >= 0) ? 1.0f : 0.0f;
-                pg.x += a * ga - ga;
-            }
-            s_line4[i] = pg;
-        }
-        /* level 3: faces and inside pixels of the first round, set up before the barrier */
-        HocLineScan sc;
-        hoc_line_scan_setup<CH>(rec_first, q_first < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo, hi, eps, scale,
-                                sc);
-        __syncthreads();
-
-        /* The scans, 32 per warp at a time; the warps of the CTA no longer synchronise.  (a) Every lane has set up one
-         * scan in registers; (b) the warp's scans are cut into chunks of CH pixels and every lane sums one chunk -- it
-         * finds its scan with a 5-step search over the warp's prefix sums and fetches the scan's constants with
-         * shuffles -- so that the lanes finish together however different the scan lengths are.  The chunk loop is
-         * fully unrolled and branch-free: per pixel one 16-byte shared load, delta (3 FMA), both distances (one FMA
-         * each: c * kk + (c * u0 + e)) and ONE MUFU.RCP of their product (1 / dA = dB * r, 1 / dB = dA * r; 3 ulp: the
-         * pseudo-gradient carries a 1e-3 tolerance and the reciprocals were the busiest pipe of the pass).  A pixel
-         * beyond the end of the scan, or with delta <= 0, adds nothing.  Each chunk adds its two vertex
-         * contributions to grad_faces. */
-        for (int q0 = wid * 32; q0 < n; q0 += T) {
-            if (q0 != wid * 32) {
-                const int q = q0 + lane;
-                hoc_line_scan_setup<CH>(q < n ? queue[q] : 0u, q < n, faces, rgb, has_rgb, b, F, S, layout, axis, d0, lo,
-                                        hi, eps, scale, sc);
-            }
-            int incl = sc.nchunk;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(HOC_FULL_MASK, incl, o);
-                if (lane >= o)
-                    incl += t;
-            }
-            const int pre = incl - sc.nchunk;
-            const int total = __shfl_sync(HOC_FULL_MASK, incl, 31);
-            for (int j0 = 0; j0 < total; j0 += 32) {
-                const int j = min(j0 + lane, total - 1);
-                const bool live = j0 + lane < total;
-                int a = 0; /* last scan with pre <= j */
-#pragma unroll
-                for (int st = 16; st >= 1; st >>= 1) {
-                    const int pv = __shfl_sync(HOC_FULL_MASK, pre, (a + st) & 31);
-                    if (a + st < 32 && pv <= j)
-                        a += st;
-                }
-                /* (every shuffle stays outside any lane-dependent branch: a predicated shuffle desynchronises the warp) */
-                const int c0 = (j - __shfl_sync(HOC_FULL_MASK, pre, a)) * CH;
-                const int d1_from = __shfl_sync(HOC_FULL_MASK, sc.from, a) + c0;
-                const int to_a = __shfl_sync(HOC_FULL_MASK, sc.to, a);
-                const int left = live ? to_a - d1_from : -1; /* pixels beyond the first */
-                const float cA = __shfl_sync(HOC_FULL_MASK, sc.cA, a), cB = __shfl_sync(HOC_FULL_MASK, sc.cB, a);
-                const float eA = __shfl_sync(HOC_FULL_MASK, sc.eA, a), eB = __shfl_sync(HOC_FULL_MASK, sc.eB, a);
-                const float I1 = __shfl_sync(HOC_FULL_MASK, sc.I1, a), I2 = __shfl_sync(HOC_FULL_MASK, sc.I2, a),
-                            I3 = __shfl_sync(HOC_FULL_MASK, sc.I3, a);
-                const float u0 = (float)d1_from - __shfl_sync(HOC_FULL_MASK, sc.cross, a);
-                const int gfA = __shfl_sync(HOC_FULL_MASK, sc.gfA, a), gfB = __shfl_sync(HOC_FULL_MASK, sc.gfB, a);
-                const float dA0 = __fmaf_rn(cA, u0, eA), dB0 = __fmaf_rn(cB, u0, eB);
-                const float4 *sp = s_line4 + (d1_from - lo);
-                float gA = 0.0f, gB = 0.0f;
-#pragma unroll
-                for (int kk = 0; kk < CH; kk++) {
-                    const float4 pg = sp[kk]; /* at most CH - 1 entries past the staged span: the buffer is padded */
-                    const float delta = __fmaf_rn(-I3, pg.w, __fmaf_rn(-I2, pg.z, __fmaf_rn(-I1, pg.y, pg.x)));
-                    const float dA = __fmaf_rn(cA, (float)kk, dA0), dB = __fmaf_rn(cB, (float)kk, dB0);
-                    float t = delta * hoc_rcp_approx(dA * dB);
-                    /* (past the scan's end the product may be 0: selected away; a NaN delta propagates like the
-                     * reference's `if (!(delta <= 0))`) */
-                    t = (delta <= 0.0f || kk > left) ? 0.0f : t;
-                    gA = __fmaf_rn(-t, dB, gA);
-                    gB = __fmaf_rn(-t, dA, gB);
-                }
-                if (gA != 0.0f && gfA >= 0)
-                    hoc_accum(grad_faces, gfA, gA, det_gf);
-                if (gB != 0.0f && gfB >= 0)
-                    hoc_accum(grad_faces, gfB, gB, det_gf);
-            }
-        }
-    } /* lines of the list */
-}
 
 /*
- * Line pass, fused form (HOC_TUNE_LINE_MODE 1): the pseudo-gradient of one image column / row in ONE kernel, without the
- * cover pass's per-pixel edge work, its scan queues and their round trip.  Every term of backward_pixel_map lives on one
- * line: for (face f, edge, axis, d0) the inside pixel, the outside pixel, the inward scan and the outward scan all have
+ * Line pass: the pseudo-gradient (backward_pixel_map) of one image column / row of one sample per CTA -- grid (samples,
+ * 2, S), sample fastest and lines from the image centre outwards (the lines that carry the most work -- meshes are centred
+ * by the crop -- are dispatched first, the empty border lines last; an empty line costs its CTA ~50 instructions).
+ * Every term of backward_pixel_map lives on one line: for (face f, edge, axis, d0) the inside pixel, the outside pixel, the inward scan and the outward scan all have
  * walk coordinate d0.  So the CTA of line (axis, d0) stages the line's span once -- owning face, colour, incoming
  * gradient of every pixel -- and then runs, from shared memory, one CANDIDATE per (covered pixel of the line, edge of its
  * face): the face's vertices are loaded (three lanes share a face), that column of the edge is evaluated once
  * (hoc_k4_column), the pixel adds its own term of the inward scan (colour of the outside pixel: from the staged line),
- * and if it is the pixel just inside the edge the lane holds the outward scan in registers; the warp then cuts its
- * scans into 16-pixel chunks exactly as the queued form does.  Chain of dependent loads per CTA: span -> line -> faces.
+ * and if it is the pixel just inside the edge the lane holds the outward scan that starts there in registers (range
+ * clipped to the span, per-column constants, colour of the inside pixel).  The warp then cuts its <= 32 scans into
+ * chunks of CH pixels and every lane sums ONE chunk out of shared memory -- it finds its scan with a 5-step shuffle
+ * search over the warp's prefix sums and fetches the scan's constants with shuffles -- so that the lanes finish
+ * together however different the scan lengths are.  The chunk loop is fully unrolled and branch-free: per pixel one
+ * 16-byte shared load, delta (3 FMA), both distances (one FMA each: c * kk + (c * u0 + e); the reference's +-eps has a
+ * constant sign along an outward scan) and ONE MUFU.RCP of their product (1 / dA = dB * r, 1 / dB = dA * r; 3 ulp: the
+ * pseudo-gradient carries a 1e-3 tolerance).  A pixel beyond the end of the scan, or with delta <= 0, adds nothing.
+ * Chain of dependent loads per CTA: span -> line -> faces.  (Rounds 1-2 ran this as two passes -- a cover pass doing the
+ * per-pixel edge work and queueing the outward scans on their lines, a line pass draining the queues: six dependent
+ * loads, a 25 MB queue workspace and 40 us against 31.)
  */
 template <int CH>
 __global__ void LN_BOUNDS
-hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
+hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                             const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                             const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
                             const int *__restrict__ ext, float scale, float *__restrict__ grad_faces,
@@ -1352,7 +966,6 @@ hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__re
             f[7] = (edge == 0) ? cy : ((edge == 1) ? by : ay);
             f[2] = f[5] = f[8] = 0.0f;
             HocK4Stage K;
-            K.need = K.push = false;
             hoc_k4_edge_pts(ax, ay, bx, by, cx, cy, S, axis, &K.E);
             int d1_in = 0, d1_out = 0;
             if (hoc_face_xy_finite(f) && !hoc_face_back(f) && d0 >= K.E.d0_from && d0 <= K.E.d0_to &&
@@ -1459,10 +1072,8 @@ hoc_raster_bwd_line2_kernel(const float *__restrict__ faces, const int32_t *__re
 
 /* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
 static int g_cover_ctas = 296;
-static int g_tex_in_line = 1; /* fused line pass: its row CTAs also run the (vertex-value) texture gradient (HOC_TUNE_TEX_IN_LINE) */
-static int g_fork_cover = 1; /* fused line pass: cover pass on a second stream (HOC_TUNE_FORK_COVER) */
-static int g_line_mode = 1; /* 1: fused line pass (hoc_raster_bwd_line2_kernel); 0: cover pass queues the scans, queued line pass */
-static int g_line_threads = 128, g_line_seg = 16, g_line_ctas = 0; /* 0: one CTA per line; > 0: that many CTAs walk the list */
+static int g_tex_in_line = 1; /* the line pass's row CTAs also run the (vertex-value) texture gradient (HOC_TUNE_TEX_IN_LINE) */
+static int g_line_threads = 128, g_line_seg = 16;
 
 extern "C" int hoc_set_tuning(int key, int value)
 {
@@ -1472,16 +1083,10 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_line_seg = value;
     else if (key == HOC_TUNE_DETERMINISTIC && (value == 0 || value == 1))
         g_hoc_deterministic = value;
-    else if (key == HOC_TUNE_LINE_CTAS && value >= 0 && value <= (1 << 20))
-        g_line_ctas = value;
     else if (key == HOC_TUNE_PDL && (value == 0 || value == 1))
         g_hoc_pdl = value;
     else if (key == HOC_TUNE_COVER_CTAS && value >= 1 && value <= 65535)
         g_cover_ctas = value;
-    else if (key == HOC_TUNE_LINE_MODE && (value == 0 || value == 1))
-        g_line_mode = value;
-    else if (key == HOC_TUNE_FORK_COVER && (value == 0 || value == 1))
-        g_fork_cover = value;
     else if (key == HOC_TUNE_TEX_IN_LINE && (value == 0 || value == 1))
         g_tex_in_line = value;
     else {
@@ -1493,29 +1098,6 @@ extern "C" int hoc_set_tuning(int key, int value)
 
 template <int CH>
 static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index_map, const float *rgb,
-                                   const float *grad_rgb, const float *g_alpha, int B, int F, int S, float eps,
-                                   int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
-                                   cudaStream_t st)
-{
-    const size_t smem = ((size_t)S + 16) * sizeof(float4); /* + padding for the unrolled chunk loop; <= 33 KB */
-    const long max_lines = 2l * B * S;
-    const int walk = g_line_ctas > 0 ? 1 : 0;
-    const dim3 grid = walk ? dim3((unsigned)(max_lines < g_line_ctas ? max_lines : g_line_ctas)) : dim3(B, 2, S);
-#define HOC_LINE_LAUNCH(WALK)                                                                                         \
-    HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,                                                                             \
-               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH, WALK>), grid, g_line_threads, smem, st,                              \
-                   faces, face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext, w.line_count,  \
-                   w.n_lines, w.line_list, (int)max_lines, 2.0f / (float)S, w.emitters, grad_faces, w.det_gf)))
-    if (walk)
-        HOC_LINE_LAUNCH(true);
-    else
-        HOC_LINE_LAUNCH(false);
-#undef HOC_LINE_LAUNCH
-    return cudaSuccess;
-}
-
-template <int CH>
-static cudaError_t hoc_launch_line2(const float *faces, const int32_t *face_index_map, const float *rgb,
                                     const float *grad_rgb, const float *g_alpha, int B, int k4_samples, int F, int S,
                                     float eps, int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
                                     const float *weight_map, const float *depth_map, float *grad_textures,
@@ -1524,13 +1106,13 @@ static cudaError_t hoc_launch_line2(const float *faces, const int32_t *face_inde
     /* two float4 and one int per staged pixel, + padding for the unrolled chunk loop: 9.8 KB at S = 256, 74 KB at 2048 */
     const size_t smem = ((size_t)S + 16) * (2 * sizeof(float4) + sizeof(int));
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line2_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess)
             return e;
     }
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_launch_pdl((hoc_raster_bwd_line2_kernel<CH>), dim3(B, 2, S), g_line_threads, smem, st, faces,
+               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B, 2, S), g_line_threads, smem, st, faces,
                                face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
                                2.0f / (float)S, grad_faces, w.det_gf, k4_samples, weight_map, depth_map, grad_textures,
                                w.det_gt)));
@@ -1590,40 +1172,6 @@ extern "C" int hoc_raster_backward(const float *faces, const float *textures, co
     return hoc_raster_backward_ex(faces, textures, face_index_map, rgb, weight_map, depth, grad_rgb, grad_alpha,
                                   grad_depth, B, F, S, ts, near_, far_, eps, layout, use_alpha, tex_grad_mode, B, 0,
                                   nullptr, 0, nullptr, grad_faces, grad_textures, workspace, workspace_bytes, stream);
-}
-
-/* A second stream per device for the one fork of the path: with the fused line pass the cover pass (texture gradient,
- * accumulates into grad_textures) and the line pass (pseudo-gradient, accumulates into grad_faces) are independent, and
- * the light one hides in the latency-bound other.  Fork / join are event dependencies, so a stream capture records two
- * parallel branches.  The mutex covers the record / wait pairs (the events are shared by the host threads of a device). */
-struct HocSideStream {
-    cudaStream_t stream;
-    cudaEvent_t fork, join;
-    bool ready;
-};
-static std::mutex g_side_mutex;
-static HocSideStream g_side[64];
-
-static HocSideStream *hoc_side_stream_locked()
-{
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
-        return nullptr;
-    HocSideStream *s = &g_side[dev];
-    if (!s->ready) {
-        /* highest priority: the forked pass is the short one -- it should start at once and be out of the way, not
-         * wait until the long pass has no CTA left to dispatch */
-        int pr_least = 0, pr_greatest = 0;
-        cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest);
-        if (cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, pr_greatest) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
-            cudaGetLastError();
-            return nullptr;
-        }
-        s->ready = true;
-    }
-    return s;
 }
 
 /* geom_samples: the pseudo-gradient (backward_pixel_map) is computed for samples [0, geom_samples) only; the rows of
@@ -1727,9 +1275,6 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
                   layout);
     HOC_CHECK_ARG(B <= 65535, "hoc_raster_backward: batch %d exceeds 65535", B); /* grid.y / grid.z limits */
     HOC_CHECK_ARG(F < (1 << 29), "hoc_raster_backward: face count %d exceeds 2^29", F);
-    /* (the scan records of the pseudo-gradient carry the face in 19 bits) */
-    HOC_CHECK_ARG(F <= (1 << 19) || grad_faces == nullptr || geom_samples == 0 || (grad_rgb == nullptr && grad_alpha == nullptr),
-                  "hoc_raster_backward: face count %d exceeds 2^19 (limit with a geometry gradient)", F);
     HOC_CHECK_ARG(grad_textures == nullptr || ts >= 1, "hoc_raster_backward: texture_size %d", ts);
     HOC_CHECK_ARG(grad_rgb == nullptr || rgb != nullptr, "hoc_raster_backward: grad_rgb given without rgb");
     if (B == 0 || F == 0)
@@ -1750,20 +1295,13 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     const int k4_samples = (grad_faces != nullptr && (grad_rgb != nullptr || g_alpha != nullptr)) ? geom_samples : 0;
     const bool k4 = k4_samples > 0;
     const bool want_depth = grad_faces != nullptr && grad_depth != nullptr;
-    /* fused line pass: the cover pass has no pseudo-gradient work (k4_cover = 0: texture / depth gradient of every
-     * sample, one listed pixel per thread) and the scan pass lists only the pixels with such a gradient */
-    const bool fused_line = k4 && g_line_mode == 1;
-    const int k4_cover = fused_line ? 0 : k4_samples;
-    const int list_k4 = fused_line ? (want_depth ? 1 : 0) : 1;
-    /* ... and when the textures are three vertex values per face and the forward saved its weights and depth (the
-     * frame-pair path), the ROW CTAs of the fused line pass -- they stage every pixel's gradient anyway -- run
-     * backward_textures too, for every sample: no cover pass at all, nobody reads the list of covered pixels */
-    const bool tex_in_line = fused_line && !want_depth && grad_rgb != nullptr && grad_textures != nullptr &&
+    /* When the textures are three vertex values per face and the forward saved its weights and depth (the frame-pair
+     * path), the ROW CTAs of the line pass -- they stage every pixel's gradient anyway -- run backward_textures too,
+     * for every sample: no cover pass at all, nobody reads the list of covered pixels */
+    const bool tex_in_line = k4 && !want_depth && grad_rgb != nullptr && grad_textures != nullptr &&
                              tex_grad_mode == HOC_TEX_GRAD_VERTEX && weight_map != nullptr && depth != nullptr &&
                              g_tex_in_line;
     const int scan_flags = tex_in_line ? (HOC_SCAN_SPAN_ALL | HOC_SCAN_NO_LIST) : 0;
-    HocSideStream *side = nullptr; /* non-NULL between the fork and the join of the cover pass */
-    std::unique_lock<std::mutex> side_lock(g_side_mutex, std::defer_lock);
     const size_t tex_bytes = (tex_grad_mode == HOC_TEX_GRAD_VERTEX)
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
@@ -1802,15 +1340,14 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
             }
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_launch_pdl((hoc_raster_bwd_scan_pair_kernel), pg4, 256, 0, st, 
-                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, list_k4, want_depth ? 1 : 0, scan_flags, w.ext,
-                           w.cov_count,
-                           w.cov_list, za, na, zb, nb, zc, nc, row_lo)));
+                           face_index_map, *pair_src, grad_rgb_out, S, k4_samples, want_depth ? 1 : 0, scan_flags, w.ext,
+                           w.cov_count, w.cov_list, za, na, zb, nb, zc, nc, row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_pair_kernel");
         } else if (layout == HOC_LAYOUT_IMAGE && (S % 4) == 0 && (al & 15) == 0) {
             dim3 pg4((S + 127) / 128, (S + 7) / 8, B);
             HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                        (hoc_raster_bwd_scan4_kernel<<<pg4, 256, 0, st>>>(
-                           face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, k4_samples, list_k4,
+                           face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, k4_samples,
                            want_depth ? 1 : 0, scan_flags, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
                            (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
             HOC_CHECK_LAUNCH("hoc_raster_bwd_scan4_kernel");
@@ -1818,62 +1355,28 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         dim3 pg((S + 31) / 32, (S + 31) / 32, B);
         HOC_LAUNCH(HOC_K_RASTER_BWD_PIXEL, st,
                    (hoc_raster_bwd_scan_kernel<<<pg, dim3(32, 8), 0, st>>>(
-                       face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples, list_k4,
+                       face_index_map, grad_rgb, gt != nullptr ? grad_rgb : nullptr, g_alpha, S, layout, k4_samples,
                        want_depth ? 1 : 0, scan_flags, w.ext, w.cov_count, w.cov_list, grad_faces, n_gf, grad_textures, n_gt,
                        (float *)extra_zero, (long)(extra_zero_bytes / sizeof(float)), row_lo)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_scan_kernel");
         }
     }
-    {
+    if (!tex_in_line && (gt != nullptr || want_depth)) { /* cover pass: texture / depth gradient of the listed pixels */
         const long npix = (long)S * S;
-        const int per = k4_cover > 0 ? 32 : CV_THREADS;
-        /* (fused line pass: few CTAs that loop over the list -- the forked pass must be dispatched in one go, the
-         * block scheduler does not interleave the CTAs of two kernels that both have thousands pending) */
-        const int max_ctas = fused_line ? 32 : g_cover_ctas;
-        dim3 cg((unsigned)((npix + per - 1) / per < max_ctas ? (npix + per - 1) / per : max_ctas), B);
-        if (!tex_in_line && (k4_cover > 0 || gt != nullptr || want_depth)) {
-            /* fused line pass without depth gradient: the cover pass touches grad_textures only -- fork it */
-            cudaStream_t cst = st;
-            if (fused_line && !want_depth && !det && g_fork_cover) {
-                side_lock.lock();
-                side = hoc_side_stream_locked();
-                if (side != nullptr && cudaEventRecord(side->fork, st) == cudaSuccess &&
-                    cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
-                    cst = side->stream;
-                } else {
-                    cudaGetLastError();
-                    side = nullptr;
-                    side_lock.unlock();
-                }
-            }
+        dim3 cg((unsigned)((npix + CV_THREADS - 1) / CV_THREADS < g_cover_ctas ? (npix + CV_THREADS - 1) / CV_THREADS
+                                                                              : g_cover_ctas),
+                B);
 #define HOC_COVER_LAUNCH(TS2)                                                                                        \
-    HOC_LAUNCH(k4_cover > 0 ? HOC_K_RASTER_BWD_PIXEL_K4 : HOC_K_RASTER_BACKWARD_COVER, cst,                           \
-               (hoc_launch_pdl((hoc_raster_bwd_cover_kernel<TS2>), cg, CV_THREADS, 0, cst,                            \
-                   faces, face_index_map, rgb, weight_map, depth, grad_rgb, g_alpha, grad_depth, F, S, ts, near_, far_, \
-                   eps, layout, use_alpha, tex_grad_mode, w.cov_count, w.cov_list, want_depth ? w.acc_d : nullptr,     \
-                   w.line_count, w.n_lines, w.line_list, w.emitters, grad_faces, gt, w.det_gf, w.det_gt, w.det_ad,   \
-                   k4_cover)))
+    HOC_LAUNCH(HOC_K_RASTER_BACKWARD_COVER, st,                                                                      \
+               (hoc_launch_pdl((hoc_raster_bwd_cover_kernel<TS2>), cg, CV_THREADS, 0, st, faces, weight_map, depth,  \
+                               grad_rgb, grad_depth, F, S, ts, near_, far_, eps, layout, tex_grad_mode, w.cov_count, \
+                               w.cov_list, want_depth ? w.acc_d : nullptr, gt, w.det_gt, w.det_ad)))
         if (ts == 2)
             HOC_COVER_LAUNCH(true);
         else
             HOC_COVER_LAUNCH(false);
 #undef HOC_COVER_LAUNCH
-            if (side != nullptr && cudaEventRecord(side->join, side->stream) != cudaSuccess) {
-                side_lock.unlock();
-                hoc_set_error("hoc_raster_backward: event record on the side stream failed: %s",
-                              cudaGetErrorString(cudaGetLastError()));
-                return HOC_ERR_CUDA;
-            }
-            if (side != nullptr && cudaGetLastError() != cudaSuccess) {
-                /* (join before reporting: a capture must not be left with a dangling branch) */
-                cudaStreamWaitEvent(st, side->join, 0);
-                side_lock.unlock();
-                hoc_set_error("hoc_raster_bwd_cover_kernel: launch failed");
-                return HOC_ERR_CUDA;
-            }
-            if (side == nullptr)
-                HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
-        }
+        HOC_CHECK_LAUNCH("hoc_raster_bwd_cover_kernel");
     }
     const long nfaces = (long)B * F;
     if (det && gt != nullptr && !tex_in_line && hoc_det_flush(w.det_gt, nfaces * tex_n, gt, 0, st) != cudaSuccess) {
@@ -1894,39 +1397,18 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
                                                                                               grad_faces)));
         HOC_CHECK_LAUNCH("hoc_raster_bwd_depth_kernel");
     }
-    if (fused_line) {
+    if (k4) {
+        const int n_line = tex_in_line ? B : k4_samples; /* (texture gradient: row CTAs of every sample) */
         if (g_line_seg >= 16)
-            e = hoc_launch_line2<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, tex_in_line ? B : k4_samples, k4_samples,
-                                     F, S, eps, layout, use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
-                                     tex_in_line ? gt : nullptr, st);
-        else
-            e = hoc_launch_line2<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, tex_in_line ? B : k4_samples, k4_samples,
-                                    F, S, eps, layout, use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
+            e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, n_line, k4_samples, F, S, eps, layout,
+                                    use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
                                     tex_in_line ? gt : nullptr, st);
-        const cudaError_t le = cudaGetLastError(); /* (launch status of the line pass, before the join's calls) */
-        if (side != nullptr) { /* join -- whatever happened above: the caller's stream waits for the cover pass */
-            const cudaError_t je = cudaStreamWaitEvent(st, side->join, 0);
-            side = nullptr;
-            side_lock.unlock();
-            if (je != cudaSuccess) {
-                hoc_set_error("hoc_raster_backward: join of the side stream failed: %s", cudaGetErrorString(je));
-                return HOC_ERR_CUDA;
-            }
-        }
-        if (e != cudaSuccess || le != cudaSuccess) {
-            hoc_set_error("hoc_raster_backward: line pass: %s", cudaGetErrorString(e != cudaSuccess ? e : le));
-            return HOC_ERR_CUDA;
-        }
-    } else if (k4) {
-        if (g_line_seg >= 16)
-            e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
-                                    use_alpha, w, grad_faces, st);
         else
-            e = hoc_launch_line<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, k4_samples, F, S, eps, layout,
-                                   use_alpha, w, grad_faces, st);
+            e = hoc_launch_line<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, n_line, k4_samples, F, S, eps, layout,
+                                   use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
+                                   tex_in_line ? gt : nullptr, st);
         if (e != cudaSuccess) {
-            hoc_set_error("hoc_raster_backward: line pass: %s",
-                          cudaGetErrorString(e));
+            hoc_set_error("hoc_raster_backward: line pass: %s", cudaGetErrorString(e));
             return HOC_ERR_CUDA;
         }
         HOC_CHECK_LAUNCH("hoc_raster_bwd_line_kernel");

@@ -80,7 +80,7 @@ const char *hoc_last_error(void);
 #define HOC_K_FLOW_VERTICES_BWD 16
 #define HOC_K_MANO_FWD 17
 #define HOC_K_MANO_BWD 18
-#define HOC_K_RASTER_BWD_PIXEL_K4 19 /* hoc_raster_bwd_cover_kernel<.., true>: covered pixels incl. pseudo-gradient */
+#define HOC_K_RASTER_BWD_PIXEL_K4 19 /* (rounds 1-2: the cover pass with the pseudo-gradient's per-pixel work; unused) */
 #define HOC_K_RASTER_BACKWARD_COVER 20 /* hoc_raster_bwd_cover_kernel<.., false>: texture / depth gradient only */
 #define HOC_K_CAT_MESHES 21
 #define HOC_K_PAIR_LOSS 22
@@ -110,13 +110,11 @@ const char *hoc_last_error(void);
 #define HOC_TUNE_LINE_THREADS 1
 #define HOC_TUNE_LINE_SEGMENT 2
 #define HOC_TUNE_DETERMINISTIC 3
-#define HOC_TUNE_LINE_CTAS 4 /* line pass: 0 (default) one CTA per line, centre-out; n > 0: n CTAs walk the list of non-empty lines */
 #define HOC_TUNE_PDL 5       /* 0 (default) / 1: programmatic dependent launch of the frame-pair step's kernels (launch,
                               * CTA scheduling and prologue of kernel N + 1 overlap the tail of kernel N; results are
                               * identical either way).  Measured: no gain inside the captured graph */
-#define HOC_TUNE_LINE_MODE 7  /* 1 (default): the pseudo-gradient of a line in one fused pass; 0: cover pass queues the scans of a line, queued line pass */
-#define HOC_TUNE_FORK_COVER 8 /* 1 (default): with the fused line pass the cover pass (texture gradient) runs on a second stream beside it */
-#define HOC_TUNE_TEX_IN_LINE 9 /* 1 (default): the fused line pass's row CTAs also run backward_textures (vertex-value textures, saved weights): no cover pass */
+#define HOC_TUNE_TEX_IN_LINE 9 /* 1 (default) / 0: the line pass's row CTAs also run backward_textures (vertex-value
+                                * textures, saved weights: the frame-pair path); 0 = a cover pass does it */
 #define HOC_TUNE_COVER_CTAS 6 /* CTAs per sample of the rasterizer backward's cover pass (grid-stride over the listed pixels) */
 int hoc_set_tuning(int key, int value);
 

@@ -20,7 +20,7 @@ if len(sys.argv) > 3:
             cupti[m.group(3)] = float(m.group(1))
 peak = d["roofline"]["peak"]
 names = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve4_kernel",
-         "raster_bwd_pixel": "hoc_raster_bwd_scan_pair_kernel", "raster_bwd_pixel_k4": "hoc_raster_bwd_cover_kernel",
+         "raster_bwd_pixel": "hoc_raster_bwd_scan_pair_kernel",
          "raster_bwd_cover": "hoc_raster_bwd_cover_kernel", "raster_bwd_line": "hoc_raster_bwd_line_kernel",
          "warp_photo_bwd": "hoc_warp_photo_pair_backward_kernel", "flow_finalize": "hoc_flow_finalize_warp_kernel",
          "mesh_scatter": "hoc_mesh_scatter_kernel", "pair_front": "hoc_pair_front_kernel",
@@ -41,10 +41,10 @@ for k in d["kernels"]:
           f"{'' if gbs is None else f'{gbs:.0f}'} | {'' if gbs is None else f'{gbs / peak:.2f}'} | "
           f"{'' if t is None else f'{t / 1e6:.1f}'} |")
 r = d["roofline"]
-bw = [cupti.get(n) for n in ("hoc_raster_bwd_scan_pair_kernel", "hoc_raster_bwd_cover_kernel", "hoc_raster_bwd_line_kernel")]
+bw = [cupti.get(n) for n in ("hoc_raster_bwd_scan_pair_kernel", "hoc_raster_bwd_line_kernel")]
 cu_b = sum(bw) if all(bw) else None
 ab = r["algorithmic_bytes_per_launch"]
-print(f"| **rasterizer backward: scan + cover + line** | {ab / 1e6:.1f} | {r['avg_launch_ms'] * 1e3:.1f} | "
+print(f"| **rasterizer backward: scan + line** | {ab / 1e6:.1f} | {r['avg_launch_ms'] * 1e3:.1f} | "
       f"{'' if cu_b is None else f'{cu_b:.1f}'} | {'' if cu_b is None else f'{ab / (cu_b * 1e-6) / 1e9:.0f}'} | "
       f"**{r['frac']:.3f}** (events) / **{'' if cu_b is None else f'{ab / (cu_b * 1e-6) / 1e9 / peak:.3f}'}** (CUPTI) | "
       f"{'' if not r['traffic'] else f'{r['traffic'] / 1e6:.1f}'} |")

@@ -39,9 +39,8 @@ def test_every_entry_point_cites_the_reference():
 def test_argument_errors_are_codes_not_crashes():
     L = _lib.lib()
     assert L.hoc_raster_forward_workspace_bytes(2, 10, 16) == 2 * 16 * 16 * 8
-    # line spans (4 ints per line) + counters + per-face depth sums + list of covered pixels + 2-byte scan queues
-    assert L.hoc_raster_backward_workspace_bytes(2, 10, 16) >= (2 * 4 * 16 * 4 + 2 * 4 + 2 * 2 * 16 * 4 + 2 * 10 * 3 * 4 +
-                                                                2 * 16 * 16 * 4 + 2 * 2 * 16 * 48 * 2)
+    # line spans (4 ints per line) + counters + per-face depth sums + list of (pixel, face) pairs
+    assert L.hoc_raster_backward_workspace_bytes(2, 10, 16) >= (2 * 4 * 16 * 4 + 2 * 4 + 2 * 10 * 3 * 4 + 2 * 16 * 16 * 8)
     assert L.hoc_mano_backward_workspace_bytes(3) >= 3 * (192 + 135 + 10) * 4
     bg = (ctypes.c_float * 3)(0, 0, 0)
     # image size out of range / missing index map: rejected before anything touches the device
