@@ -42,6 +42,7 @@
 
 #define HOC_SCAN_SPAN_ALL 1
 #define HOC_SCAN_NO_LIST 2
+#define HOC_SCAN_TWO_CHANNELS 4 /* frame-pair path: the third gradient plane (always zero) is neither written nor read */
 #define EXT_ROW_LO 0
 #define EXT_ROW_HI 1
 #define EXT_COL_LO 2
@@ -512,7 +513,8 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
             *reinterpret_cast<float4 *>(dst) = z4;
             *reinterpret_cast<float4 *>(dst + (long)S * S) = z4;
-            *reinterpret_cast<float4 *>(dst + 2l * S * S) = z4;
+            if (!(scan_flags & HOC_SCAN_TWO_CHANNELS))
+                *reinterpret_cast<float4 *>(dst + 2l * S * S) = z4;
         }
         return;
     }
@@ -543,7 +545,8 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         float *dst = g_rgb + (((long)b * 3) * S + y_img) * S + x0;
         *reinterpret_cast<float4 *>(dst) = gx;
         *reinterpret_cast<float4 *>(dst + (long)S * S) = gy;
-        *reinterpret_cast<float4 *>(dst + 2l * S * S) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!(scan_flags & HOC_SCAN_TWO_CHANNELS))
+            *reinterpret_cast<float4 *>(dst + 2l * S * S) = make_float4(0.f, 0.f, 0.f, 0.f);
         nzm = ((!(gx.x == 0.0f) || !(gy.x == 0.0f)) ? 1u : 0u) | ((!(gx.y == 0.0f) || !(gy.y == 0.0f)) ? 2u : 0u) |
               ((!(gx.z == 0.0f) || !(gy.z == 0.0f)) ? 4u : 0u) | ((!(gx.w == 0.0f) || !(gy.w == 0.0f)) ? 8u : 0u);
     }
@@ -834,7 +837,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                             const float *__restrict__ rgb, const float *__restrict__ g_rgb,
                             const float *__restrict__ g_alpha, int F, int S, float eps, int layout, int use_alpha,
                             const int *__restrict__ ext, float scale, float *__restrict__ grad_faces,
-                            unsigned long long *__restrict__ det_gf, int k4_samples,
+                            unsigned long long *__restrict__ det_gf, int k4_samples, int g_channels,
                             const float *__restrict__ weight_map, const float *__restrict__ depth_map,
                             float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gt)
 {
@@ -876,10 +879,12 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                        o2 = hoc_rgb_off(layout, S, b, yi, xi, 2);
             ia.x = rgb[o0];
             ia.y = rgb[o1];
-            ia.z = rgb[o2];
             pg.y = g_rgb[o0];
             pg.z = g_rgb[o1];
-            pg.w = g_rgb[o2];
+            if (g_channels > 2) { /* (frame-pair path: the third channel carries no gradient -- the plane does not exist) */
+                ia.z = rgb[o2];
+                pg.w = g_rgb[o2];
+            }
             pg.x = ia.x * pg.y + ia.y * pg.z + ia.z * pg.w;
         }
         if (has_alpha) {
@@ -1101,7 +1106,7 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
                                     const float *grad_rgb, const float *g_alpha, int B, int k4_samples, int F, int S,
                                     float eps, int layout, int use_alpha, const HocBwdWorkspace &w, float *grad_faces,
                                     const float *weight_map, const float *depth_map, float *grad_textures,
-                                    cudaStream_t st)
+                                    int g_channels, cudaStream_t st)
 {
     /* two float4 and one int per staged pixel, + padding for the unrolled chunk loop: 9.8 KB at S = 256, 74 KB at 2048 */
     const size_t smem = ((size_t)S + 16) * (2 * sizeof(float4) + sizeof(int));
@@ -1114,8 +1119,8 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
                (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B, 2, S), g_line_threads, smem, st, faces,
                                face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
-                               2.0f / (float)S, grad_faces, w.det_gf, k4_samples, weight_map, depth_map, grad_textures,
-                               w.det_gt)));
+                               2.0f / (float)S, grad_faces, w.det_gf, k4_samples, g_channels, weight_map, depth_map,
+                               grad_textures, w.det_gt)));
     return cudaSuccess;
 }
 
@@ -1301,7 +1306,11 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     const bool tex_in_line = k4 && !want_depth && grad_rgb != nullptr && grad_textures != nullptr &&
                              tex_grad_mode == HOC_TEX_GRAD_VERTEX && weight_map != nullptr && depth != nullptr &&
                              g_tex_in_line;
-    const int scan_flags = tex_in_line ? (HOC_SCAN_SPAN_ALL | HOC_SCAN_NO_LIST) : 0;
+    /* frame-pair path: the rendered image is a 2-channel flow, the incoming gradient of the third channel is zero; when
+     * the line pass is the only reader of the gradient planes the third one is neither written nor read */
+    const int g_channels = (pair_src != nullptr && tex_in_line) ? 2 : 3;
+    const int scan_flags = (tex_in_line ? (HOC_SCAN_SPAN_ALL | HOC_SCAN_NO_LIST) : 0) |
+                           (g_channels == 2 ? HOC_SCAN_TWO_CHANNELS : 0);
     const size_t tex_bytes = (tex_grad_mode == HOC_TEX_GRAD_VERTEX)
                                  ? sizeof(float) * 9 * (size_t)B * F
                                  : sizeof(float) * 3 * (size_t)ts * ts * ts * (size_t)B * F;
@@ -1402,11 +1411,11 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
         if (g_line_seg >= 16)
             e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, n_line, k4_samples, F, S, eps, layout,
                                     use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
-                                    tex_in_line ? gt : nullptr, st);
+                                    tex_in_line ? gt : nullptr, g_channels, st);
         else
             e = hoc_launch_line<8>(faces, face_index_map, rgb, grad_rgb, g_alpha, n_line, k4_samples, F, S, eps, layout,
                                    use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
-                                   tex_in_line ? gt : nullptr, st);
+                                   tex_in_line ? gt : nullptr, g_channels, st);
         if (e != cudaSuccess) {
             hoc_set_error("hoc_raster_backward: line pass: %s", cudaGetErrorString(e));
             return HOC_ERR_CUDA;
