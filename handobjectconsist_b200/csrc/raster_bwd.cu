@@ -811,8 +811,8 @@ struct HocLineScan {
 #endif
 
 /*
- * Line pass: the pseudo-gradient (backward_pixel_map) of one image column / row of one sample per CTA -- grid (samples,
- * 2, S), sample fastest and lines from the image centre outwards (the lines that carry the most work -- meshes are centred
+ * Line pass: the pseudo-gradient (backward_pixel_map) of one image column / row of one sample per CTA -- grid ((sample,
+ * axis), S), sample fastest and lines from the image centre outwards (the lines that carry the most work -- meshes are centred
  * by the crop -- are dispatched first, the empty border lines last; an empty line costs its CTA ~50 instructions).
  * Every term of backward_pixel_map lives on one line: for (face f, edge, axis, d0) the inside pixel, the outside pixel, the inward scan and the outward scan all have
  * walk coordinate d0.  So the CTA of line (axis, d0) stages the line's span once -- owning face, colour, incoming
@@ -851,7 +851,11 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
     const bool has_rgb = (rgb != nullptr) && (g_rgb != nullptr);
-    const int b = blockIdx.x, axis = blockIdx.y, d0 = hoc_centre_out(blockIdx.z, S);
+    /* grid.x: (sample, axis) -- both axes of the samples with pseudo-gradient, then the rows of the others */
+    const int bx = blockIdx.x;
+    const int b = bx < 2 * k4_samples ? (bx >> 1) : bx - k4_samples;
+    const int axis = bx < 2 * k4_samples ? (bx & 1) : 1;
+    const int d0 = hoc_centre_out(blockIdx.y, S);
     /* samples [0, k4_samples) get the pseudo-gradient; with grad_textures given the ROW CTAs of every sample also run
      * backward_textures for the pixels of their row (three vertex values per face, weights and depth saved by the
      * forward): they have staged each pixel's owning face and incoming gradient anyway */
@@ -1117,7 +1121,7 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
             return e;
     }
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B, 2, S), g_line_threads, smem, st, faces,
+               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B + k4_samples, S), g_line_threads, smem, st, faces,
                                face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
                                2.0f / (float)S, grad_faces, w.det_gf, k4_samples, g_channels, weight_map, depth_map,
                                grad_textures, w.det_gt)));
