@@ -5,7 +5,7 @@ occlusion check) -> pair_consist (four warps, mask algebra, two masked L1 means)
 (/root/reference/meshreg/models/warpbranch.py:45-88, meshreg/warping/opticalflow.py:51-156,
 meshreg/warping/imgflowarp.py:58-115).  The operator-by-operator mirrors of those functions live in
 ``warping/opticalflow.py`` and ``warping/imgflowarp.py``; this module is the training fast path: the same arithmetic
-(same device functions, bit-identical flows / masks) as FIVE launches forward and FIVE backward, with the two renders
+(same device functions, bit-identical flows / masks) as FIVE launches forward and FOUR backward, with the two renders
 of the pair stacked along the batch ([2B]) so that every rasterizer kernel runs once:
 
     forward   hoc_pair_front                 vertices of both frames -> faces / vertex textures of both renders, key fill
@@ -15,8 +15,8 @@ of the pair stacked along the batch ([2B]) so that every rasterizer kernel runs 
                                              (with visuals: hoc_flow_finalize, then hoc_warp_photo_forward_pair)
               hoc_pair_loss_mean             masked means -> loss [B] and its batch mean
     backward  hoc_pair_backward_raster [2B]  scan pass FUSED with the backward of pair_consist (d loss / d flow x d flow /
-                                             d rgb computed from the valid masks), then the cover / line passes
-                                             (pseudo-gradient for the first render only)
+                                             d rgb computed from the valid masks), then the line pass (pseudo-gradient
+                                             of the first render, texture gradient of both)
               hoc_mesh_scatter       [2B]    faces -> vertices
               hoc_pair_back                  projection adjoints -> d loss / d (hand, object vertices)
 

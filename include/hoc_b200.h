@@ -288,10 +288,12 @@ int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, fl
                        size_t zero_bytes, void *stream);
 /* The backward of the frame-pair step from d loss to grad_faces / grad_textures in ONE call: the backward of pair_consist
  * fused into the rasterizer backward's scan pass (the incoming gradient of the renders' rgb maps is computed from the
- * valid masks instead of being written by one pass and read back by the next), then the cover and line passes.
+ * valid masks instead of being written by one pass and read back by the next), then the line pass (pseudo-gradient of
+ * the first geom_samples rows; texture gradient of all rows).  Two launches.
  * Arguments: those of hoc_warp_photo_backward_pair (pairs = B of the pair kernels) and of hoc_raster_backward_ex for the
  * stacked rows [row_offset, row_offset + n) of (render 1 of every pair, render 2 of every pair); image layout, vertex
- * texture gradients; grad_rgb [n,3,S,S] is scratch the call fills (rows inside the raster window). */
+ * texture gradients; grad_rgb [n,3,S,S] is scratch of the call (its third plane -- the rendered flow has two channels --
+ * is not touched). */
 size_t hoc_pair_backward_zero_bytes(int n, int F, int S); /* leading workspace bytes HOC_BWD_WORKSPACE_ZEROED vouches for */
 int hoc_pair_backward_raster(const float *image_ref, const float *image, const float *flow12, const float *flow21,
                              const uint8_t *const *valid_mask, const double *sums, const float *mult1,
