@@ -244,8 +244,6 @@ class _PairConsistFunction(Function):
                 _lib.ptr(depth[lo:]), _lib.ptr(grad_rgb), n, Fr, S, k["near"], k["far"], k["eps"], geom,
                 _lib.HOC_BWD_WORKSPACE_ZEROED if clean else 0, _lib.ptr(both), both.numel() * 4, rl(lo),
                 _lib.ptr(grad_faces), _lib.ptr(grad_tex), _lib.ptr(ws), ws.numel(), st), "hoc_pair_backward_raster")
-            if STATS is not None:  # (profiling scripts look at the counters the passes left in the workspace)
-                STATS["backward_workspace"] = (ws, n, Fr, S, geom)
             g_ndc, g_attr = (both[0] if geom > 0 else None), both[1]
             sc_bytes = L.hoc_mesh_scatter_workspace_bytes(n, V)
             sc_ws = torch.empty(sc_bytes, dtype=torch.uint8, device=dev) if sc_bytes else None

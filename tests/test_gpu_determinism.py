@@ -78,6 +78,36 @@ def test_pair_path_is_reproducible_at_bench_size():
     assert torch.equal(loss.detach(), runs[0][0])
 
 
+def test_tuning_switches_do_not_change_the_result():
+    """hoc_set_tuning switches that only change HOW the frame-pair step is executed must not change its result, bit
+    for bit in the reproducible mode: programmatic dependent launch of its kernels (HOC_TUNE_PDL), and the texture
+    gradient through the cover pass instead of the line pass's row CTAs (HOC_TUNE_TEX_IN_LINE = 0: scan pass lists the
+    pixels, three gradient planes, hoc_raster_bwd_cover_kernel)."""
+    import helpers
+    S, B = 128, 3
+    dev = torch.device("cuda:0")
+    sc = synth.make_scene(B, S, 96, seed=3)
+    L = _lib.lib()
+
+    def run():
+        loss, res, v1 = helpers.pair_step(sc, S, (S, 96), dev, False, True, False)
+        loss.backward()
+        return loss.detach().clone(), res["loss"].detach().clone(), v1.grad.clone()
+
+    with _lib.deterministic(True):
+        base = run()
+        for key, value, back in ((_lib.HOC_TUNE_PDL, 1, 0), (_lib.HOC_TUNE_TEX_IN_LINE, 0, 1)):
+            _lib.check(L.hoc_set_tuning(key, value), "hoc_set_tuning")
+            try:
+                other = run()
+            finally:
+                _lib.check(L.hoc_set_tuning(key, back), "hoc_set_tuning")
+            for a, b in zip(base, other):
+                assert torch.equal(a, b), (key, value)
+    assert base[0].item() > 0 and base[2].abs().max().item() > 0
+    assert L.hoc_set_tuning(4, 1) != 0 and b"hoc_set_tuning" in L.hoc_last_error()  # (a key of an earlier round: gone)
+
+
 def test_reproducible_mode_needs_its_workspace():
     """In the reproducible mode the plain hoc_mesh_scatter (no workspace) refuses to run instead of silently falling
     back to float atomics, and the rasterizer backward asks for the larger workspace."""
