@@ -162,9 +162,11 @@ int hoc_raster_forward_ex(const float *faces, const float *textures, int B, int 
 /* ---- rasterizer backward ------------------------------------------------------------------
  * Replaces backward_pixel_map + backward_textures + backward_depth_map
  * (rasterize.py:269-281,290-297,306-315) and the zero-fills around them (rasterize.py:151-181).
- * Three launches (pixel pass, face pass, line pass -- csrc/raster_bwd.cu).  Texture / depth gradients and
- * the outward-scan part of the pseudo-gradient are accumulated with float atomics, like the reference's
- * backward_textures / backward_depth_map: results are reproducible to rounding, not bit for bit.
+ * Two launches -- a streaming scan pass and a line pass that runs the pseudo-gradient of one image column / row per CTA
+ * (and the texture gradient, for vertex-value textures with saved weights) --, plus a cover pass for cube textures /
+ * depth gradients and a per-face epilogue for the depth gradient (csrc/raster_bwd.cu).  Texture / depth gradients and
+ * the pseudo-gradient are accumulated with float atomics, like the reference's backward_textures /
+ * backward_depth_map: results are reproducible to rounding, not bit for bit (HOC_TUNE_DETERMINISTIC: bit for bit).
  *   faces, textures, face_index_map   forward inputs / output
  *   rgb              forward output in `layout` (NULL when the forward had no rgb)
  *   weight_map, depth  forward outputs ([B,S,S,3] raster order / [B,S,S] in `layout`) or NULL: when both are
@@ -174,9 +176,9 @@ int hoc_raster_forward_ex(const float *faces, const float *textures, int B, int 
  *   use_alpha        1 when the forward produced alpha (return_alpha), else 0
  *   grad_faces       [B,F,3,3] out (fully overwritten) or NULL to skip the geometry gradient
  *   grad_textures    [B,F,ts,ts,ts,3] out (fully overwritten) or NULL to skip it
- *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes: line spans, counters, per-face depth sums,
- *                    the list of covered pixels (4 S^2 B) and the per-line queues of outward scans (2-byte records,
- *                    12 S^2 B worst case, of which only the used part is ever touched)
+ *   workspace        hoc_raster_backward_workspace_bytes(B,F,S) bytes: line spans, counters, per-face depth sums and
+ *                    the list of pixels with a texture / depth gradient (8 S^2 B, of which only the used part is
+ *                    ever touched)
  */
 /* tex_grad_mode: CUBE = grad_textures is [B,F,ts,ts,ts,3] (the reference's backward_textures);
  * VERTEX = the cubes were built by hoc_mesh_gather from three vertex values per face (ts == 2): grad_textures
