@@ -4,7 +4,8 @@
  * Serial host emulation of the ALGORITHM of csrc/raster_fwd.cu and csrc/raster_bwd.cu: same
  * per-face / per-pixel functions (it includes the product header raster_math.h), same work
  * decomposition (face-parallel z-buffer with a packed (depth, face) min key, pixel resolve,
- * face-owned gradient gather, clipped outward scans), with loops where the kernels have lanes.
+ * face-owned gradient gather, pixel-driven inward terms, per-line outward scans clipped to the span of the
+ * pixels that matter and summed with the line pass's arithmetic), with loops where the kernels have lanes.
  * It lets the CPU test-suite check the restructured algorithm against the oracle's literal
  * restatement of the reference without a GPU.  It is never loaded by the product.
  * Build: g++ -O2 -ffp-contract=off -shared -fPIC (tests/test_host_emulation.py).
@@ -171,6 +172,11 @@ static float delta_at(const Maps &M, int xi, int yi, const float *Iref)
     return d;
 }
 
+/* Outward scans whose pixels did NOT all have the sign of c * (d1 - cross) the line pass assumes for the whole scan
+ * (it adds the reference's +-eps as one constant per scan): must stay 0. */
+static long g_sign_violations = 0;
+extern "C" long emul_sign_violations() { return g_sign_violations; }
+
 extern "C" void emul_raster_backward(const float *faces, const int32_t *face_index_map, const float *rgb,
                                      const float *g_rgb, const float *g_alpha, const float *g_depth, int B, int F,
                                      int S, int ts, float near_, float far_, float eps, int layout, int use_alpha,
@@ -193,7 +199,8 @@ extern "C" void emul_raster_backward(const float *faces, const int32_t *face_ind
                         nz = nz || !(g_rgb[rgb_off(layout, S, b, yi, xi, c)] == 0.0f);
                 if (g_alpha && use_alpha)
                     nz = nz || !(g_alpha[plane_off(layout, S, b, yi, xi)] == 0.0f);
-                if (nz) {
+                /* the line pass looks at the covered pixels (they own the scans) and at those with a gradient */
+                if (nz || face_index_map[((long)b * S + yi) * S + xi] >= 0) {
                     e[0 * S + yi] = std::min(e[0 * S + yi], xi);
                     e[1 * S + yi] = std::max(e[1 * S + yi], xi);
                     e[2 * S + xi] = std::min(e[2 * S + xi], yi);
@@ -354,12 +361,36 @@ extern "C" void emul_raster_backward(const float *faces, const int32_t *face_ind
                         load_I(M, xin, yin, I_in);
                         const int d1_from = pos ? std::max(d1_out, lo) : lo;
                         const int d1_to = pos ? hi : std::min(d1_out, hi);
+                        /* the arithmetic of hoc_raster_bwd_line_kernel's chunk loop: per-scan constants, the reference's
+                         * +-eps as ONE constant per scan (sign of c * (d1_out - cross)), both distances by FMA, one
+                         * reciprocal of their product for both vertices */
+                        HocK4Col C;
+                        hoc_k4_col(&E, S, d0, d1_cross, &C);
+                        const float scale = 2.0f / (float)S, t_first = (float)d1_out - d1_cross;
+                        float cA = 0.0f, cB = 0.0f, eA = 1.0f, eB = 1.0f;
+                        if (C.hasA) {
+                            cA = C.cA * scale;
+                            eA = (0.0f < cA * t_first) ? eps : -eps;
+                        }
+                        if (C.hasB) {
+                            cB = C.cB * scale;
+                            eB = (0.0f < cB * t_first) ? eps : -eps;
+                        }
                         float gA = 0.0f, gB = 0.0f;
                         for (int d1 = d1_from; d1 <= d1_to; d1++) {
+                            const float u = (float)d1 - d1_cross;
+                            if ((C.hasA && ((0.0f < C.cA * (u * scale)) ? eps : -eps) != eA) ||
+                                (C.hasB && ((0.0f < C.cB * (u * scale)) ? eps : -eps) != eB))
+                                g_sign_violations++;
                             const float delta = delta_at(M, axis == 0 ? d0 : d1, axis == 0 ? d1 : d0, I_in);
                             if (delta <= 0.0f)
                                 continue;
-                            hoc_k4_accum(&E, S, d0, d1, d1_cross, eps, delta, &gA, &gB);
+                            const float dA = fmaf(cA, u, eA), dB = fmaf(cB, u, eB);
+                            const float t = delta * (1.0f / (dA * dB));
+                            if (C.hasA)
+                                gA -= t * dB;
+                            if (C.hasB)
+                                gB -= t * dA;
                         }
                         float *gf = grad_faces + ((long)b * F + fi) * 9;
                         gf[edge * 3 + (1 - axis)] += gA;

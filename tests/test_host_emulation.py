@@ -105,6 +105,11 @@ def test_backward_matches_oracle(dense, S):
     # fp64 re-evaluation flips a few floor/ceil / sign gates: norm-wise bound only
     assert np.linalg.norm(gf - gf64) / np.linalg.norm(gf64) < 2e-2
     assert np.linalg.norm(gt - gt64) / np.linalg.norm(gt64) < 2e-2
+    # the line pass adds the reference's +-eps as one constant per outward scan: every scanned pixel must have had
+    # the sign that constant assumes
+    L = _build()
+    L.emul_sign_violations.restype = ctypes.c_long
+    assert L.emul_sign_violations() == 0
 
 
 def test_backward_float_oracle_agrees_with_double():
