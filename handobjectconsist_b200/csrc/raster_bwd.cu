@@ -804,6 +804,7 @@ struct HocLineScan {
 };
 
 #define LN_THREADS 256
+#define LN_PAD 32 /* staged entries past the span that the unrolled chunk loop may read (never used): the longest chunk */
 #ifdef LN_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
 #define LN_BOUNDS __launch_bounds__(LN_THREADS, LN_MINB)
 #else
@@ -845,8 +846,8 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     /* dynamic shared memory, per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (see the
      * queued kernel), float4 (I_r, I_g, I_b, g_alpha), int owning face */
     extern __shared__ float4 s_line4[];
-    float4 *s_pg = s_line4, *s_ia = s_line4 + (S + 16);
-    int *s_fi = reinterpret_cast<int *>(s_line4 + 2 * (S + 16));
+    float4 *s_pg = s_line4, *s_ia = s_line4 + (S + LN_PAD);
+    int *s_fi = reinterpret_cast<int *>(s_line4 + 2 * (S + LN_PAD));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int T = blockDim.x; /* multiple of 32, <= LN_THREADS */
     const bool has_alpha = (use_alpha != 0) && (g_alpha != nullptr);
@@ -1082,13 +1083,13 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
 /* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
 static int g_cover_ctas = 296;
 static int g_tex_in_line = 1; /* the line pass's row CTAs also run the (vertex-value) texture gradient (HOC_TUNE_TEX_IN_LINE) */
-static int g_line_threads = 128, g_line_seg = 16;
+static int g_line_threads = 128, g_line_seg = 0; /* seg 0: by raster size (16 pixels up to 320, 32 above: 176 -> 163 us at 32 x 480^2) */
 
 extern "C" int hoc_set_tuning(int key, int value)
 {
     if (key == HOC_TUNE_LINE_THREADS && value >= 32 && value <= LN_THREADS && value % 32 == 0)
         g_line_threads = value;
-    else if (key == HOC_TUNE_LINE_SEGMENT && (value == 8 || value == 16))
+    else if (key == HOC_TUNE_LINE_SEGMENT && (value == 0 || value == 8 || value == 16 || value == 32))
         g_line_seg = value;
     else if (key == HOC_TUNE_DETERMINISTIC && (value == 0 || value == 1))
         g_hoc_deterministic = value;
@@ -1113,7 +1114,7 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
                                     int g_channels, cudaStream_t st)
 {
     /* two float4 and one int per staged pixel, + padding for the unrolled chunk loop: 9.8 KB at S = 256, 74 KB at 2048 */
-    const size_t smem = ((size_t)S + 16) * (2 * sizeof(float4) + sizeof(int));
+    const size_t smem = ((size_t)S + LN_PAD) * (2 * sizeof(float4) + sizeof(int));
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
@@ -1412,7 +1413,12 @@ static int hoc_raster_backward_impl(const float *faces, const float *textures, c
     }
     if (k4) {
         const int n_line = tex_in_line ? B : k4_samples; /* (texture gradient: row CTAs of every sample) */
-        if (g_line_seg >= 16)
+        const int seg = g_line_seg > 0 ? g_line_seg : (S > 320 ? 32 : 16);
+        if (seg >= 32)
+            e = hoc_launch_line<32>(faces, face_index_map, rgb, grad_rgb, g_alpha, n_line, k4_samples, F, S, eps, layout,
+                                    use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
+                                    tex_in_line ? gt : nullptr, g_channels, st);
+        else if (seg >= 16)
             e = hoc_launch_line<16>(faces, face_index_map, rgb, grad_rgb, g_alpha, n_line, k4_samples, F, S, eps, layout,
                                     use_alpha, w, grad_faces, tex_in_line ? weight_map : nullptr, depth,
                                     tex_in_line ? gt : nullptr, g_channels, st);

@@ -99,7 +99,7 @@ const char *hoc_last_error(void);
 
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
- *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan (8 or 16)
+ *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan (8, 16 or 32; 0 = by raster size, the default)
  *   HOC_TUNE_DETERMINISTIC 0 (default) / 1: reproducible mode.  The gradient sums that production accumulates with
  *                          float atomics (like the reference's backward_textures / backward_depth_map /
  *                          index_put(accumulate)) are accumulated in 128-bit fixed point with integer atomics

@@ -55,7 +55,7 @@ def test_argument_errors_are_codes_not_crashes():
     # the newer entry points: same contract (a code and a message, nothing launched)
     assert L.hoc_set_tuning(99, 1) == -1 and b"hoc_set_tuning" in L.hoc_last_error()
     assert L.hoc_set_tuning(1, 100) == -1            # threads per CTA must be a multiple of 32
-    assert L.hoc_set_tuning(1, 128) == 0 and L.hoc_set_tuning(2, 16) == 0
+    assert L.hoc_set_tuning(1, 128) == 0 and L.hoc_set_tuning(2, 16) == 0 and L.hoc_set_tuning(2, 0) == 0  # (0: by raster size)
     assert L.hoc_unpack_u8(None, None, 16, 255.0, 0.5, None) == -1 and b"hoc_unpack_u8" in L.hoc_last_error()
     assert L.hoc_unpack_u8(None, None, 0, 255.0, 0.5, None) == 0   # nothing to do
     assert L.hoc_cat_meshes(None, None, None, None, None, 0, None, 0, 778, 1502, 1552, 3000, None, None, None, None) == 0
