@@ -135,6 +135,41 @@ def test_backward_matches_oracle(dense, S, B):
     assert np.abs(t2.grad.cpu().numpy() - gt).max() <= 1e-3 * np.abs(gt).max()
 
 
+def test_backward_on_a_large_raster():
+    """S = 1400: the line pass stages (S + 32) x 36 bytes per CTA = 51.6 KB, above the 48 KB a kernel gets without
+    opting in (cudaFuncAttributeMaxDynamicSharedMemorySize), and cuts its scans into 32-pixel chunks (rasters above
+    320).  A handful of large triangles keeps the oracle fast."""
+    S, F = 1400, 10
+    rng = np.random.default_rng(5)
+    faces = np.zeros((1, F, 3, 3), np.float32)
+    for k in range(F):
+        c = rng.uniform(-0.6, 0.6, 2)
+        ang = np.sort(rng.uniform(0, 2 * np.pi, 3))  # counter-clockwise: front-facing
+        r = rng.uniform(0.15, 0.5, 3)
+        faces[0, k, :, 0] = c[0] + r * np.cos(ang)
+        faces[0, k, :, 1] = c[1] + r * np.sin(ang)
+        faces[0, k, :, 2] = rng.uniform(1.0, 3.0, 3)
+    tex = rng.uniform(0.1, 1.0, (1, F, 2, 2, 2, 3)).astype(np.float32)
+    ora = onmr.rasterize_forward(faces, tex, S, 0.1, 100.0, 1e-3, (0, 0, 0), True, True, True)
+    assert (ora["face_index_map"] >= 0).mean() > 0.05
+    g_rgb = rng.normal(size=ora["rgb_map"].shape).astype(np.float32)
+    g_rgb *= (ora["face_index_map"] >= 0).astype(np.float32)[..., None]
+    g_alpha = np.zeros_like(ora["alpha_map"])
+    g_depth = np.zeros_like(ora["depth_map"])
+    gf64, gt64 = onmr.rasterize_backward(ora, g_rgb, g_alpha, g_depth, dtype=np.float64)
+    gf32, gt32 = onmr.rasterize_backward(ora, g_rgb, g_alpha, g_depth)
+    f, t, (rgb, alpha, depth, idx, inv, wmap) = _run_function(faces, tex, S)
+    np.testing.assert_array_equal(idx.cpu().numpy(), ora["face_index_map"])
+    (rgb * _cuda(g_rgb)).sum().backward()
+    # triangles of ~10^5 pixels: every gradient is a sum of 10^4 .. 10^5 terms that cancel to 1e-3 of their size, and
+    # the fp32 summation orders differ (serial per face in the oracle, chunks and atomics here): the bar is relative
+    # to the gradient scale, as for every comparison of float-atomic sums, plus the norm-wise fp64 bound
+    for g, g32, g64 in ((t.grad.cpu().numpy(), gt32, gt64), (f.grad.cpu().numpy(), gf32, gf64)):
+        assert np.isfinite(g).all() and np.abs(g32).max() > 0
+        assert np.abs(g - g32).max() <= 1e-3 * np.abs(g32).max()
+        assert np.linalg.norm(g - g64) / np.linalg.norm(g64) < 2e-2
+
+
 @pytest.mark.parametrize("S,B", [(48, 2), (96, 2)])
 def test_backward_reproducible_mode(det_mode, S, B):
     """HOC_TUNE_DETERMINISTIC: same parity bar against the oracle, and two runs give the same bits."""
