@@ -449,18 +449,18 @@ def run_native(args, rank, world, local_rank):
         # source 12 + target 12 at the valid pixels
         "warp_photo_bwd": 2 * ncrop * 1 + npx2 * 12 + int(c * 2 * ncrop) * 36,
         # scan pass over both renders with the backward of pair_consist fused in (hoc_raster_bwd_scan_pair_kernel): idx4 +
-        # valid1 in, grad_rgb12 out per pixel; flow8 + mult4 + source 12 + target 12 at the valid pixels; list entries
-        # (8 B per covered pixel) out; zero-fill of grad_faces (one render) + grad of the vertex values (both) + the
-        # scatter's outputs
-        "raster_bwd_pixel": (npx2 * 16 + 2 * ncrop * 1 + int(c * 2 * ncrop) * 36 + int(c * npx2) * 8 + nf * 36 + nf2 * 36
+        # valid1 in, two gradient planes (8) out per pixel; flow8 + mult4 + source 12 + target 12 at the valid pixels;
+        # zero-fill of grad_faces (one render) + grad of the vertex values (both) + the scatter's outputs
+        "raster_bwd_pixel": (npx2 * 12 + 2 * ncrop * 1 + int(c * 2 * ncrop) * 36 + nf * 36 + nf2 * 36
                              + 2 * 2 * Bp * V * 12),
         # (cover pass: only in configurations whose texture gradient the line pass does not run; not in this workload)
         "raster_bwd_cover": int(c * npx2) * 36 + nf2 * 72,
         "raster_backward": nf * (36 + 12 + 36),                    # depth epilogue (only with dL/ddepth)
-        # line pass: rgb, grad_rgb, idx of the render with the pseudo-gradient once (both axes read the same maps), faces
-        # of its covered pixels, grad_faces update; texture gradient of both renders: grad_rgb12 (second render) +
-        # weights12 + depth4 at the valid pixels, 9 sums per face out
-        "raster_bwd_line": npx * (12 + 12 + 4) + nf * (36 + 36) + npx * 12 + int(c * npx2) * 16 + nf2 * 36,
+        # line pass: the two flow channels of rgb (8), the two gradient planes (8) and idx (4) of the render with the
+        # pseudo-gradient once (both axes read the same maps), faces of its covered pixels, grad_faces update; texture
+        # gradient of both renders: the second render's gradient planes (8) + weights12 + depth4 at the valid pixels, 9
+        # sums per face out
+        "raster_bwd_line": npx * (8 + 8 + 4) + nf * (36 + 36) + npx * 8 + int(c * npx2) * 16 + nf2 * 36,
         "mesh_scatter": nf * 36 + nf2 * 36 + 2 * Bp * Fm * 24 + 2 * 2 * Bp * V * 12,
         "pair_back": 2 * 2 * Bp * V * 12 + 2 * Bp * V * 12 + Bp * V * 12,
     }
