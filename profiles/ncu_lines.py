@@ -1,7 +1,15 @@
 """usage: ncu_lines.py <rep> <kernel regex> <cubin> [top]
 Executed warp instructions and stall samples of one kernel aggregated by SOURCE LINE: ncu's SASS page is aligned (by
 instruction order) with nvdisasm -g of the same build's cubin."""
-import csv, re, subprocess, sys, collections
+import collections
+import csv
+import glob
+import os
+import re
+import subprocess
+import sys
+
+CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "handobjectconsist_b200", "csrc")
 rep, kre, cubin = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre], capture_output=True, text=True).stdout
@@ -44,8 +52,7 @@ srcs = {}
 for (ln, (c, s)) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     text = ""
     if ln:
-        import glob
-        for cand in glob.glob("/root/repo/handobjectconsist_b200/csrc/" + ln[0]):
+        for cand in glob.glob(os.path.join(CSRC, ln[0])):
             if cand not in srcs: srcs[cand] = open(cand).read().splitlines()
             if ln[1] - 1 < len(srcs[cand]): text = srcs[cand][ln[1] - 1].strip()[:90]
     print(f"{c:9d} {100*c/tot:5.1f}%  smp {100*s/max(ts,1):5.1f}%  {ln[0] if ln else '?'}:{ln[1] if ln else 0}  {text}")
