@@ -172,9 +172,9 @@ __device__ __forceinline__ void hoc_k4_stage_b(const HocK4Stage &T, int axis, co
 
 /*
  * Scan pass.  Block (32, 8) covers a 32 x 32 pixel tile (4 rows per thread).  Pure streaming: reads
- * face_index_map and the incoming gradients once, writes the line spans, the list of covered pixels that have
- * work (all of them when the pseudo-gradient is wanted, else those with a texture / depth gradient).  One global
- * atomic per CTA reserves the tile's list slots.
+ * face_index_map and the incoming gradients once, writes the line spans and -- unless nobody reads it -- the list of
+ * the pixels with a texture / depth gradient (`list_all`: every covered pixel).  One global atomic per CTA reserves
+ * the tile's list slots.
  */
 __global__ void __launch_bounds__(256)
 hoc_raster_bwd_scan_kernel(const int32_t *__restrict__ face_index_map, const float *__restrict__ g_rgb_k4,
@@ -362,7 +362,7 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
             want |= 1u << j;
     __syncthreads(); /* s_clo / s_chi initialised */
     if (SPAN) {
-        /* span of non-zero incoming gradient of this row (the warp's) and of the tile's columns */
+        /* span of this row (the warp's) and of the tile's columns */
         /* (pixels the line pass has to look at: those with an incoming gradient -- the only ones a scan gets a term
          * from -- and the covered ones, which own the scans) */
         const unsigned spm = nzm | (K4 ? ((fis[0] >= 0 ? 1u : 0u) | (fis[1] >= 0 ? 2u : 0u) | (fis[2] >= 0 ? 4u : 0u) |
@@ -432,7 +432,7 @@ hoc_raster_bwd_scan4_kernel(const int32_t *__restrict__ face_index_map, const fl
  * else, so instead of one pass that writes it (12 B/px) and another that reads it back, this pass reads the valid mask
  * (1 B/px), computes the gradient of the valid pixels (phase B of the two-phase pattern: 12 bilinear taps each, one
  * pixel per thread) into a shared tile, and goes on as hoc_raster_bwd_scan4_kernel from there -- spans, covered-pixel
- * list, zero-fills -- writing the gradient planes once for the cover and line passes.  One launch and 12 B/px less.
+ * list, zero-fills -- writing the gradient planes once for the line pass.  One launch and 12 B/px less.
  * Stacked row b of the launch is render (b + row_offset) / pairs of pair (b + row_offset) % pairs; render 1's flow is
  * consumed by pair_consist's direction 1, render 2's by direction 0.
  */
@@ -537,7 +537,7 @@ hoc_raster_bwd_scan_pair_kernel(const int32_t *__restrict__ face_index_map, HocP
         }
     }
     __syncthreads();
-    /* phase C: the gradient planes (written once, for the cover and line passes) and the scan pass proper */
+    /* phase C: the gradient planes (written once, for the line pass) and the scan pass proper */
     unsigned nzm = 0;
     if (in) {
         const float4 gx = *reinterpret_cast<const float4 *>(s_gx + threadIdx.x * 4);
@@ -798,7 +798,7 @@ struct HocLineScan {
                        * (they all lie strictly on the outside of the crossing); 1 for a vertex without term */
     float cross;
     float I1, I2, I3; /* colour of the inside pixel */
-    int from, to;     /* range on the line, clipped to the span of non-zero gradient */
+    int from, to;     /* range on the line, clipped to the line's span */
     int gfA, gfB;     /* element of grad_faces, -1 for a vertex without term */
     int nchunk;
 };
@@ -844,7 +844,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
 {
     hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     /* dynamic shared memory, per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (see the
-     * queued kernel), float4 (I_r, I_g, I_b, g_alpha), int owning face */
+     * chunk loop below), float4 (I_r, I_g, I_b, g_alpha), int owning face */
     extern __shared__ float4 s_line4[];
     float4 *s_pg = s_line4, *s_ia = s_line4 + (S + LN_PAD);
     int *s_fi = reinterpret_cast<int *>(s_line4 + 2 * (S + LN_PAD));
@@ -1029,7 +1029,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 }
             }
         }
-        /* the warp's scans, cut into chunks of CH pixels, one chunk per lane (see the queued kernel) */
+        /* the warp's scans, cut into chunks of CH pixels, one chunk per lane */
         int incl = sc.nchunk;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1216,7 +1216,7 @@ extern "C" int hoc_raster_backward_ex(const float *faces, const float *textures,
 
 /* The backward of the frame-pair step from the loss to grad_faces / grad_textures in one call: the backward of
  * pair_consist (hoc_warp_photo_backward_pair) fused into the rasterizer backward's scan pass
- * (hoc_raster_bwd_scan_pair_kernel), then the cover and line passes.  grad_rgb [n,3,S,S] is scratch the call fills.
+ * (hoc_raster_bwd_scan_pair_kernel), then the line pass.  grad_rgb [n,3,S,S] is scratch of the call (two planes used).
  * The stacked batch holds rows [row_offset, row_offset + n) of (render 1 of every pair, render 2 of every pair). */
 extern "C" int hoc_pair_backward_raster(const float *image_ref, const float *image, const float *flow12,
                                         const float *flow21, const uint8_t *const *valid_mask, const double *sums,
