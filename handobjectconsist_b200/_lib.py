@@ -67,6 +67,7 @@ SIGNATURES = {
                                     _i, _i, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _vp]),
     "hoc_raster_backward_zero_bytes": (_sz, [_i, _i, _i]),
     "hoc_flow_finalize_warp": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 8),
+    "hoc_flow_finalize_warp_ex": (_i, [_vp] * 10 + [_i] * 4 + [_vp, _i, _f, _f] + [_vp] * 7 + [_i, _vp]),
     "hoc_pair_backward_zero_bytes": (_sz, [_i, _i, _i]),
     "hoc_pair_loss_mean": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _sz, _vp]),
     "hoc_pair_backward_raster": (_i, [_vp] * 10 + [_i] * 5 + [_vp] * 6 + [_i] * 3 + [_f] * 3 + [_i, _i, _vp, _sz, _vp, _vp,

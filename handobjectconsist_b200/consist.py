@@ -107,6 +107,7 @@ class _PairConsistFunction(Function):
         ignore = cfg["ignore"]
         n_ign = 0 if ignore is None else ignore.numel()
         visuals = bool(cfg["visuals"])
+        loss_only = bool(cfg.get("loss_only")) and not visuals
         bg = (ctypes.c_float * 3)(*[float(x) for x in r.background_color])
         near, far, eps = float(r.near), float(r.far), float(r.rasterizer_eps)
         with torch.cuda.device(dev):
@@ -141,16 +142,19 @@ class _PairConsistFunction(Function):
             flow12, flow21 = e(B, H, W, 2), e(B, H, W, 2)
             mult = e(2, B, H, W)
             valid = e(2, B, H, W, dtype=torch.bool)
-            flow_mask = e(2, B, H, W, 2, dtype=torch.bool)
+            flow_mask = None if loss_only else e(2, B, H, W, 2, dtype=torch.bool)
             pp = _lib.ptr_pair
             renders = (_lib.ptr(rgb[:B]), _lib.ptr(alpha[:B]), _lib.ptr(idx[:B]), _lib.ptr(rgb[B:]), _lib.ptr(alpha[B:]),
                        _lib.ptr(idx[B:]))
             vis = None
             if not visuals:
-                _lib.check(L.hoc_flow_finalize_warp(
+                # loss_only: flows / mult are written where the valid mask is set (all the backward reads) and left
+                # undefined elsewhere, no flow masks: 24 B/px of zero stores less
+                _lib.check(L.hoc_flow_finalize_warp_ex(
                     *renders, _lib.ptr(ir), _lib.ptr(im), _lib.ptr(jr), _lib.ptr(jm), B, S, H, W, _lib.ptr(ignore), n_ign,
                     0.03, float(cfg["thresh"]), _lib.ptr(flow12), _lib.ptr(flow21), _lib.ptr(mult[0]), _lib.ptr(mult[1]),
-                    pp(valid[0], valid[1]), pp(flow_mask[0], flow_mask[1]), _lib.ptr(sums), st), "hoc_flow_finalize_warp")
+                    pp(valid[0], valid[1]), None if loss_only else pp(flow_mask[0], flow_mask[1]), _lib.ptr(sums),
+                    int(loss_only), st), "hoc_flow_finalize_warp")
             else:
                 _lib.check(L.hoc_flow_finalize(*renders, B, S, H, W, _lib.ptr(ignore), n_ign, 1, 0.03, _lib.ptr(flow12),
                                                _lib.ptr(flow21), _lib.ptr(mult[0]), _lib.ptr(mult[1]), st),
@@ -180,10 +184,13 @@ class _PairConsistFunction(Function):
         ctx.cfg = dict(B=B, Vh=Vh, Vo=Vo, Fn=Fn, Fr=Fr, S=S, H=H, W=W, near=near, far=far, eps=eps, fill_back=fill_back,
                        orig_size=float(r.orig_size), detach_renders=bool(cfg["detach_renders"]),
                        use_backward=bool(cfg["use_backward"]), cam_flags=[a for a in cam_args[1::2]])
-        outs = (loss, mean, flow12, flow21, valid[0], valid[1], flow_mask[0], flow_mask[1])
+        if loss_only:  # (flows are undefined outside the valid pixels: not handed out)
+            outs = (loss, mean, None, None, valid[0], valid[1], None, None)
+        else:
+            outs = (loss, mean, flow12, flow21, valid[0], valid[1], flow_mask[0], flow_mask[1])
         if visuals:
             outs = outs + tuple(vis[k] for k in range(6))
-        ctx.mark_non_differentiable(*outs[2:])
+        ctx.mark_non_differentiable(*[o for o in outs[2:] if o is not None])
         ctx.set_materialize_grads(False)
         return outs
 
@@ -268,18 +275,20 @@ class _PairConsistFunction(Function):
 
 def pair_consist_step(hand1, obj1, hand2, obj2, hand_faces, obj_faces, K1, K2, image_ref, image, jitter_mask_ref,
                       jitter_mask, renderer, image_size, hand_ignore_faces=None, detach_renders=True, use_backward=True,
-                      return_visuals=True, thresh=0.99999):
+                      return_visuals=True, thresh=0.99999, loss_only=False):
     """Loss [B] of one frame pair and the reference's result structures.
 
     Returns ``((loss, mean), flows, masks, warps, diffs)``: ``loss`` [B] and its batch mean (scalar, computed by the
     same launch); ``flows = [flow12, flow21]`` ([B,H,W,2]); ``masks`` the two dicts
     of pair_consist (``warp_mask`` is None without visuals); ``warps`` / ``diffs`` lists of two tensors (None entries
-    without visuals).  Only ``loss`` / ``mean`` are differentiable -- w.r.t. the four vertex tensors."""
+    without visuals).  Only ``loss`` / ``mean`` are differentiable -- w.r.t. the four vertex tensors.
+    ``loss_only=True`` (with ``return_visuals=False``: what a captured training step asks for): the flows and flow
+    masks are not handed out either (None) -- the step then writes them only where the backward reads them."""
     S = int(renderer.image_size)
     wh = (min(int(image_size[0]), S), min(int(image_size[1]), S)) if image_size is not None else (S, S)
     ignore = None if hand_ignore_faces is None else _ignore_tensor(hand_ignore_faces, hand1.device)
     cfg = dict(renderer=renderer, wh=wh, ignore=ignore, detach_renders=detach_renders, use_backward=use_backward,
-               visuals=return_visuals, thresh=thresh)
+               visuals=return_visuals, thresh=thresh, loss_only=bool(loss_only) and not return_visuals)
     outs = _PairConsistFunction.apply(hand1, obj1, hand2, obj2, hand_faces, obj_faces, K1, K2, image_ref, image,
                                       jitter_mask_ref, jitter_mask, cfg)
     loss, mean, flow12, flow21, valid1, valid2, fmask1, fmask2 = outs[:8]

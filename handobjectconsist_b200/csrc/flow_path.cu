@@ -379,7 +379,7 @@ struct HocFinWarpDir {
 __global__ void FW_BOUNDS
 hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocFinWarpDir D1, int S, int H, int W,
                               const int *__restrict__ ignore, int n_ignore, float distance_thresh, float inv_w,
-                              float inv_h, float thresh)
+                              float inv_h, float thresh, int sparse_outputs)
 {
     hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     /* Two phases per CTA (4 pixels per thread).  A: every thread streams its four pixels -- 16-byte loads of alpha and the two
@@ -418,9 +418,11 @@ hoc_flow_finalize_warp_kernel(HocRender R1, HocRender R2, HocFinWarpDir D0, HocF
         const float al[4] = {a4.x, a4.y, a4.z, a4.w}, c0[4] = {r4.x, r4.y, r4.z, r4.w}, c1[4] = {g4.x, g4.y, g4.z, g4.w};
         const long o = (long)b * npix + (long)ry * W + x0;
         const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        *reinterpret_cast<float4 *>(D.flow + o * 2) = z4;
-        *reinterpret_cast<float4 *>(D.flow + o * 2 + 4) = z4;
-        *reinterpret_cast<float4 *>(D.mult + o) = z4;
+        if (!sparse_outputs) { /* (sparse: flow / mult are only defined where valid_mask is set -- all the backward reads) */
+            *reinterpret_cast<float4 *>(D.flow + o * 2) = z4;
+            *reinterpret_cast<float4 *>(D.flow + o * 2 + 4) = z4;
+            *reinterpret_cast<float4 *>(D.mult + o) = z4;
+        }
         *reinterpret_cast<unsigned *>(D.valid_mask + o) = 0u;
         if (D.flow_mask != nullptr)
             *reinterpret_cast<uint2 *>(D.flow_mask + o * 2) = make_uint2(0u, 0u);
@@ -1289,12 +1291,13 @@ extern "C" int hoc_pair_back(const float *hand1, const float *obj1, const float 
     return HOC_OK;
 }
 
-extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
-                                      const float *alpha2, const int32_t *idx2, const float *image_ref,
-                                      const float *image, const float *jitter_ref, const float *jitter, int B, int S,
-                                      int H, int W, const int *ignore_faces, int n_ignore, float distance_thresh,
-                                      float thresh, float *flow12, float *flow21, float *mult1, float *mult2,
-                                      uint8_t *const *valid_mask, uint8_t *const *flow_mask, double *sums, void *stream)
+extern "C" int hoc_flow_finalize_warp_ex(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
+                                         const float *alpha2, const int32_t *idx2, const float *image_ref,
+                                         const float *image, const float *jitter_ref, const float *jitter, int B, int S,
+                                         int H, int W, const int *ignore_faces, int n_ignore, float distance_thresh,
+                                         float thresh, float *flow12, float *flow21, float *mult1, float *mult2,
+                                         uint8_t *const *valid_mask, uint8_t *const *flow_mask, double *sums,
+                                         int sparse_outputs, void *stream)
 {
     HOC_CHECK_ARG(B >= 0 && S >= 4 && (S % 4) == 0 && H >= 1 && W >= 4 && (W % 4) == 0 && H <= S && W <= S,
                   "hoc_flow_finalize_warp: bad shape B=%d S=%d H=%d W=%d (S, W multiples of 4)", B, S, H, W);
@@ -1322,7 +1325,20 @@ extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, co
     HOC_LAUNCH(HOC_K_FLOW_FINALIZE, (cudaStream_t)stream,
                (hoc_launch_pdl((hoc_flow_finalize_warp_kernel), grid, FW_THREADS, 0, (cudaStream_t)stream, 
                    R1, R2, D0, D1, S, H, W, ignore_faces, n_ignore, distance_thresh,
-                   1.0f / (float)(W - 1 > 1 ? W - 1 : 1), 1.0f / (float)(H - 1 > 1 ? H - 1 : 1), thresh)));
+                   1.0f / (float)(W - 1 > 1 ? W - 1 : 1), 1.0f / (float)(H - 1 > 1 ? H - 1 : 1), thresh,
+                   sparse_outputs ? 1 : 0)));
     HOC_CHECK_LAUNCH("hoc_flow_finalize_warp_kernel");
     return HOC_OK;
+}
+
+extern "C" int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
+                                      const float *alpha2, const int32_t *idx2, const float *image_ref,
+                                      const float *image, const float *jitter_ref, const float *jitter, int B, int S,
+                                      int H, int W, const int *ignore_faces, int n_ignore, float distance_thresh,
+                                      float thresh, float *flow12, float *flow21, float *mult1, float *mult2,
+                                      uint8_t *const *valid_mask, uint8_t *const *flow_mask, double *sums, void *stream)
+{
+    return hoc_flow_finalize_warp_ex(rgb1, alpha1, idx1, rgb2, alpha2, idx2, image_ref, image, jitter_ref, jitter, B, S, H,
+                                     W, ignore_faces, n_ignore, distance_thresh, thresh, flow12, flow21, mult1, mult2,
+                                     valid_mask, flow_mask, sums, 0, stream);
 }

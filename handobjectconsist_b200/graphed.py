@@ -34,7 +34,8 @@ class GraphedConsistStep:
         # (warps / diffs / warp_mask) would be dead stores inside the graph (return_visuals=True keeps them, for
         # benchmarking the difference)
         self.kw = dict(gt_refs=gt_refs, first_only=first_only, hand_ignore_faces=hand_ignore_faces,
-                       use_backward=use_backward, detach_renders=detach_renders, return_visuals=return_visuals)
+                       use_backward=use_backward, detach_renders=detach_renders, return_visuals=return_visuals,
+                       loss_only=not return_visuals)  # (the captured step hands out the loss and its gradients only)
         self.hand_face = hand_face.to(dev)
         self._u8_stage = {}
         self._one = torch.ones((), dtype=torch.float32, device=dev)  # d loss / d loss, created once (not per replay)

@@ -37,7 +37,7 @@ def _base(sample, name):
 
 
 def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt_refs=True, first_only=True,
-            hand_ignore_faces=None, use_backward=True, detach_renders=True, return_visuals=True):
+            hand_ignore_faces=None, use_backward=True, detach_renders=True, return_visuals=True, loss_only=False):
     """
     Args:
         use_backward: also compare the warp from the first to the other frame (warpbranch.py:21-25)
@@ -45,6 +45,8 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
             NMR geometry gradient flow as well
         return_visuals: extension -- False skips the visualisation entries of ``pair_results`` (``warps``, ``diffs``
             and the masks' ``warp_mask`` are None): nothing the loss or its gradient depends on
+        loss_only: extension (frame-pair path, with return_visuals=False) -- ``recons_flows`` and the masks'
+            ``flow_mask`` are None as well: a step that only wants the loss and its gradient
     Returns (full_loss, pair_results) like the reference.
     """
     # Put inputs on GPU (stream-ordered copies when the host tensors are pinned)
@@ -64,13 +66,13 @@ def forward(samples, all_results, hand_face, renderer, image_size, criterion, gt
     if (len(samples) == 2 and _config.fused_pair and hand_face.dim() in (2, 3)
             and consist.pair_path_ok(renderer, criterion, images, jitter_masks, image_size)):
         # one frame pair, the renderer WarpRegNet builds, L1: the whole step behind one autograd node
-        # (consist.py: 6 launches forward, 5 backward, both renders stacked along the batch)
+        # (consist.py: 5 launches forward, 4 backward, both renders stacked along the batch)
         hand2, obj2 = (hand_verts[1].detach(), obj_verts[1].detach()) if first_only else (hand_verts[1], obj_verts[1])
         (warp_loss, warp_mean), flows, masks, warps, diffs = consist.pair_consist_step(
             hand_verts[0], obj_verts[0], hand2, obj2, hand_face.cuda(non_blocking=True), obj_faces[last], camintrs[0],
             camintrs[1], images[0], images[1], jitter_masks[0], jitter_masks[1], renderer, image_size,
             hand_ignore_faces=hand_ignore_faces, detach_renders=detach_renders, use_backward=use_backward,
-            return_visuals=return_visuals)
+            return_visuals=return_visuals, loss_only=loss_only)
         # the mean over the single pair's per-sample losses (warpbranch.py:88) comes out of the same launch
         pair_results = {"masks": [masks], "warps": [warps], "recons_flows": [flows], "diffs": [diffs],
                         "diff_losses": warp_loss.unsqueeze(0)}

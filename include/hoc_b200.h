@@ -284,6 +284,15 @@ int hoc_flow_finalize_warp(const float *rgb1, const float *alpha1, const int32_t
                            const int *ignore_faces, int n_ignore, float distance_thresh, float thresh, float *flow12,
                            float *flow21, float *mult1, float *mult2, uint8_t *const *valid_mask,
                            uint8_t *const *flow_mask, double *sums, void *stream);
+/* The same; sparse_outputs = 1: the step wants the loss and its gradient only -- flow12 / flow21 / mult1 / mult2 are
+ * written where valid_mask is set (all that hoc_pair_backward_raster reads) and left undefined elsewhere: 24 B/px of
+ * zero stores less (pass flow_mask = NULL as well). */
+int hoc_flow_finalize_warp_ex(const float *rgb1, const float *alpha1, const int32_t *idx1, const float *rgb2,
+                              const float *alpha2, const int32_t *idx2, const float *image_ref, const float *image,
+                              const float *jitter_ref, const float *jitter, int B, int S, int H, int W,
+                              const int *ignore_faces, int n_ignore, float distance_thresh, float thresh, float *flow12,
+                              float *flow21, float *mult1, float *mult2, uint8_t *const *valid_mask,
+                              uint8_t *const *flow_mask, double *sums, int sparse_outputs, void *stream);
 /* hoc_pair_loss plus the mean over the batch (warpbranch.py:88 for one pair), one launch.  zero: an optional buffer the
  * launch also zero-fills (the counters of the step's rasterizer backward, HOC_BWD_WORKSPACE_ZEROED). */
 int hoc_pair_loss_mean(const double *sums_fwd, const double *sums_bwd, int B, float *loss, float *mean, void *zero,

@@ -47,7 +47,7 @@ def rel_err(a, b):
 HAND_VERTS, HAND_FACES = 778, 1552
 
 
-def pair_step(sc, S, crop, dev, detach_renders, use_backward, return_visuals=True):
+def pair_step(sc, S, crop, dev, detach_renders, use_backward, return_visuals=True, loss_only=False):
     """The fused frame-pair path (handobjectconsist_b200.consist) on a synth scene: hand / object split like
     warpbranch.forward receives them.  Returns (mean loss, dict like warpbranch.consist_step's, leaf vertices)."""
     from handobjectconsist_b200 import consist
@@ -64,5 +64,5 @@ def pair_step(sc, S, crop, dev, detach_renders, use_backward, return_visuals=Tru
         v1[:, :hv], v1[:, hv:], g["verts2"][:, :hv], g["verts2"][:, hv:], hand_faces, obj_faces, g["K"], g["K"],
         g["image_ref"], g["image"], g["jitter_mask_ref"], g["jitter_mask"], r, crop,
         hand_ignore_faces=sc["hand_ignore_faces"], detach_renders=detach_renders, use_backward=use_backward,
-        return_visuals=return_visuals)
+        return_visuals=return_visuals, loss_only=loss_only)
     return mean, dict(flows=flows, loss=loss, masks=masks, warps=warps, diffs=diffs), v1

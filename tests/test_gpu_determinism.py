@@ -104,6 +104,12 @@ def test_tuning_switches_do_not_change_the_result():
                 _lib.check(L.hoc_set_tuning(key, back), "hoc_set_tuning")
             for a, b in zip(base, other):
                 assert torch.equal(a, b), (key, value)
+        # ... and neither does asking for the loss only (flows / flow masks not handed out: written sparsely)
+        loss, res, v1 = helpers.pair_step(sc, S, (S, 96), dev, False, True, False, loss_only=True)
+        loss.backward()
+        assert res["flows"] == [None, None] and res["masks"][0]["flow_mask"] is None
+        assert torch.equal(loss.detach(), base[0]) and torch.equal(res["loss"].detach(), base[1])
+        assert torch.equal(v1.grad, base[2])
     assert base[0].item() > 0 and base[2].abs().max().item() > 0
     assert L.hoc_set_tuning(4, 1) != 0 and b"hoc_set_tuning" in L.hoc_last_error()  # (a key of an earlier round: gone)
 
