@@ -311,6 +311,16 @@ def run_native(args, rank, world, local_rank):
         n_k = L.hoc_timer_peek(buf, ids, 8192)
         group_ms += [buf[j] for j in range(n_k) if buf[j] >= 0]
     L.hoc_timer_begin(0)
+    # what the one event pair costs, measured live: the step of the bracketed copy against the plain captured step on the
+    # same input set, alternating (the two event-record nodes sit at the bracket's ends, so their whole cost -- the extra
+    # step time -- is an UPPER bound of what they add to the bracketed interval; the CUPTI timeline shows the same ~4 us)
+    cal_plain, cal_inst = [], []
+    if world == 1:
+        probe_g.load(*dbatches[0])  # (gstep's own input set)
+        for _ in range(7):
+            cal_plain.append(timed(lambda i: gstep.replay(), 50) / 50)
+            cal_inst.append(timed(lambda i: probe_g.replay(), 50) / 50)
+    bracket_cost_ms = max(0.0, median(cal_inst) - median(cal_plain)) if cal_plain else None
     del probe_g
 
     # ---- end-to-end arm: pinned host buffers -> static device buffers -> graph -> host ----
@@ -558,6 +568,15 @@ def run_native(args, rank, world, local_rank):
             "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms,
             "share_of_step": bwd_ms / step_ms if bwd_ms else None,
             "launches_timed": len(group_ms), "sum_of_per_kernel_brackets_ms": bwd_ms_kernels,
+            "event_pair": ({"cost_ms_per_step": bracket_cost_ms, "plain_step_ms": median(cal_plain),
+                            "bracketed_step_ms": median(cal_inst),
+                            "frac_net": ((bwd_bytes / ((bwd_ms - bracket_cost_ms) * 1e-3) / 1e9 / peak)
+                                         if bwd_ms > bracket_cost_ms else None),
+                            "note": "cost of the bracket's two event-record nodes = step time of the bracketed copy of the "
+                                    "graph minus the plain captured step (same inputs, 7 alternating blocks of 50 replays, "
+                                    "medians); `frac` above is NOT corrected for it -- `frac_net` is the fraction if all of "
+                                    "that cost fell inside the bracket, so the kernels' own fraction lies between the two"}
+                           if (bracket_cost_ms is not None and group_ms) else None),
             "timing": "ONE pair of CUDA events (external event nodes of an instrumented copy of the captured graph) around the "
                       "two launches of hoc_pair_backward_raster; the pair adds ~4 us (profiles/timeline_r2.txt holds the "
                       "CUPTI durations of an un-instrumented replay)",

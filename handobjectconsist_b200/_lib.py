@@ -23,6 +23,8 @@ HOC_TUNE_LINE_SEGMENT = 2
 HOC_TUNE_DETERMINISTIC = 3
 HOC_TUNE_PDL = 5
 HOC_TUNE_COVER_CTAS = 6
+HOC_TUNE_LINE_LINES = 7
+HOC_TUNE_LINE_FOLD = 8
 HOC_TUNE_TEX_IN_LINE = 9
 HOC_BWD_WORKSPACE_ZEROED = 1
 

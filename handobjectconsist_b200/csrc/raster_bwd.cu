@@ -804,6 +804,7 @@ struct HocLineScan {
 };
 
 #define LN_THREADS 256
+#define LN_MAX_LINES 8 /* lines per CTA (HOC_TUNE_LINE_LINES) */
 #define LN_PAD 32 /* staged entries past the span that the unrolled chunk loop may read (never used): the longest chunk */
 #ifdef LN_MINB /* (occupancy experiments: minimum resident CTAs per SM) */
 #define LN_BOUNDS __launch_bounds__(LN_THREADS, LN_MINB)
@@ -814,7 +815,8 @@ struct HocLineScan {
 /*
  * Line pass: the pseudo-gradient (backward_pixel_map) of one image column / row of one sample per CTA -- grid ((sample,
  * axis), S), sample fastest and lines from the image centre outwards (the lines that carry the most work -- meshes are centred
- * by the crop -- are dispatched first, the empty border lines last; an empty line costs its CTA ~50 instructions).
+ * by the crop -- are dispatched first, the empty border lines last; an empty line costs its CTA ~50 instructions).  On
+ * rasters above 320 a CTA runs three lines one after the other (grid ((sample, axis), S / 3); see g_line_lines).
  * Every term of backward_pixel_map lives on one line: for (face f, edge, axis, d0) the inside pixel, the outside pixel, the inward scan and the outward scan all have
  * walk coordinate d0.  So the CTA of line (axis, d0) stages the line's span once -- owning face, colour, incoming
  * gradient of every pixel -- and then runs, from shared memory, one CANDIDATE per (covered pixel of the line, edge of its
@@ -840,12 +842,14 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                             const int *__restrict__ ext, float scale, float *__restrict__ grad_faces,
                             unsigned long long *__restrict__ det_gf, int k4_samples, int g_channels,
                             const float *__restrict__ weight_map, const float *__restrict__ depth_map,
-                            float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gt)
+                            float *__restrict__ grad_textures, unsigned long long *__restrict__ det_gt, int lines,
+                            int fold)
 {
     hoc_pdl_sync(); /* programmatic dependent launch: see hoc_common.cuh */
     /* dynamic shared memory, per staged pixel: float4 (P, g_r, g_g, g_b) with P = sum_ch I_ch g_ch - g_alpha (see the
      * chunk loop below), float4 (I_r, I_g, I_b, g_alpha), int owning face */
     extern __shared__ float4 s_line4[];
+    __shared__ int s_span[LN_MAX_LINES][3]; /* (lo, hi, d0) of the CTA's lines */
     float4 *s_pg = s_line4, *s_ia = s_line4 + (S + LN_PAD);
     int *s_fi = reinterpret_cast<int *>(s_line4 + 2 * (S + LN_PAD));
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -856,7 +860,6 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     const int bx = blockIdx.x;
     const int b = bx < 2 * k4_samples ? (bx >> 1) : bx - k4_samples;
     const int axis = bx < 2 * k4_samples ? (bx & 1) : 1;
-    const int d0 = hoc_centre_out(blockIdx.y, S);
     /* samples [0, k4_samples) get the pseudo-gradient; with grad_textures given the ROW CTAs of every sample also run
      * backward_textures for the pixels of their row (three vertex values per face, weights and depth saved by the
      * forward): they have staged each pixel's owning face and incoming gradient anyway */
@@ -864,14 +867,31 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     const bool TEX = grad_textures != nullptr && axis == 1 && has_rgb;
     if (!K4 && !TEX)
         return;
-    /* level 1: the span of the pixels that matter on this line (covered or with an incoming gradient: the scan pass) */
-    const int *e = ext + (long)b * 4 * S;
-    const int lo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
-    const int hi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0] - 1;
-    if (lo > hi)
-        return;
-    const int len = hi - lo + 1;
+    /* level 1: the spans of the pixels that matter on this CTA's lines (covered or with an incoming gradient: the scan
+     * pass), all fetched at once.  A CTA runs `lines` lines (HOC_TUNE_LINE_LINES; 1: grid.y = S): line k of CTA y has
+     * centre-out rank k * G + y (G = grid.y) -- or, folded, k * G + (G - 1 - y) for odd k, which pairs a heavy central
+     * line with a light outer one -- so that an empty border line costs a loop iteration instead of a CTA. */
+    if (tid < lines) {
+        const int G = gridDim.y;
+        const int li = tid * G + ((fold && (tid & 1)) ? G - 1 - (int)blockIdx.y : (int)blockIdx.y);
+        int lo_ = 1, hi_ = 0, d0_ = 0;
+        if (li < S) {
+            const int *e = ext + (long)b * 4 * S;
+            d0_ = hoc_centre_out(li, S);
+            lo_ = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0_];
+            hi_ = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0_] - 1;
+        }
+        s_span[tid][0] = lo_;
+        s_span[tid][1] = hi_;
+        s_span[tid][2] = d0_;
+    }
     const int32_t *idx = face_index_map + (long)b * S * S;
+    for (int ln = 0; ln < lines; ln++) {
+    __syncthreads(); /* the spans are written; every warp is done with the previous line's staged pixels */
+    const int lo = s_span[ln][0], hi = s_span[ln][1], d0 = s_span[ln][2];
+    if (lo > hi)
+        continue;
+    const int len = hi - lo + 1;
 
     /* level 2: the line */
     for (int i = tid; i < len; i += T) {
@@ -929,7 +949,7 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
             }
         }
         if (!K4)
-            return;
+            continue;
     }
 
     HocBwdMaps M; /* (for the outside pixel of an inward term that lies beyond the staged span) */
@@ -1078,11 +1098,16 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
                 hoc_accum(grad_faces, gfB, gB, det_gf);
         }
     }
+    } /* (the CTA's next line) */
 }
 
 /* Tuning knobs of the line pass (hoc_set_tuning): threads per CTA, chunk length in pixels (8 or 16). */
 static int g_cover_ctas = 296;
 static int g_tex_in_line = 1; /* the line pass's row CTAs also run the (vertex-value) texture gradient (HOC_TUNE_TEX_IN_LINE) */
+/* lines per CTA of the line pass and the way they are dealt (HOC_TUNE_LINE_LINES / _FOLD).  0: by raster size -- one line
+ * per CTA up to 320 (measured at 16 pairs of 256^2: 119.8 us per step with 1, 120.2 / 120.5 / 121.4 with 2 / 3 / 4 folded;
+ * unfolded 121.3 / 125.2 / 139.2 with 2 / 4 / 8), three folded lines above (32 pairs of 480 x 270: 494.4 -> 483.5 us) */
+static int g_line_lines = 0, g_line_fold = 1;
 static int g_line_threads = 128, g_line_seg = 0; /* seg 0: by raster size (16 pixels up to 320, 32 above: 176 -> 163 us at 32 x 480^2) */
 
 extern "C" int hoc_set_tuning(int key, int value)
@@ -1099,6 +1124,10 @@ extern "C" int hoc_set_tuning(int key, int value)
         g_cover_ctas = value;
     else if (key == HOC_TUNE_TEX_IN_LINE && (value == 0 || value == 1))
         g_tex_in_line = value;
+    else if (key == HOC_TUNE_LINE_LINES && value >= 0 && value <= LN_MAX_LINES)
+        g_line_lines = value;
+    else if (key == HOC_TUNE_LINE_FOLD && (value == 0 || value == 1))
+        g_line_fold = value;
     else {
         hoc_set_error("hoc_set_tuning: bad key %d / value %d", key, value);
         return HOC_ERR_INVALID_ARG;
@@ -1121,11 +1150,13 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
         if (e != cudaSuccess)
             return e;
     }
+    const int lines = g_line_lines > 0 ? g_line_lines : (S > 320 ? 3 : 1);
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B + k4_samples, S), g_line_threads, smem, st, faces,
+               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B + k4_samples, (S + lines - 1) / lines),
+                               g_line_threads, smem, st, faces,
                                face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
                                2.0f / (float)S, grad_faces, w.det_gf, k4_samples, g_channels, weight_map, depth_map,
-                               grad_textures, w.det_gt)));
+                               grad_textures, w.det_gt, lines, g_line_fold)));
     return cudaSuccess;
 }
 

@@ -100,6 +100,7 @@ const char *hoc_last_error(void);
 /* Tuning knobs (defaults are the measured optimum on B200; meant for benchmarking sweeps).
  *   HOC_TUNE_LINE_THREADS  threads per CTA of the rasterizer backward's line pass (multiple of 32, <= 256)
  *   HOC_TUNE_LINE_SEGMENT  pixels per work item of an outward scan (8, 16 or 32; 0 = by raster size, the default)
+ *   HOC_TUNE_LINE_LINES / HOC_TUNE_LINE_FOLD  image lines per CTA of the line pass and the way they are dealt (below)
  *   HOC_TUNE_DETERMINISTIC 0 (default) / 1: reproducible mode.  The gradient sums that production accumulates with
  *                          float atomics (like the reference's backward_textures / backward_depth_map /
  *                          index_put(accumulate)) are accumulated in 128-bit fixed point with integer atomics
@@ -116,6 +117,11 @@ const char *hoc_last_error(void);
 #define HOC_TUNE_TEX_IN_LINE 9 /* 1 (default) / 0: the line pass's row CTAs also run backward_textures (vertex-value
                                 * textures, saved weights: the frame-pair path); 0 = a cover pass does it */
 #define HOC_TUNE_COVER_CTAS 6 /* CTAs per sample of the rasterizer backward's cover pass (grid-stride over the listed pixels) */
+#define HOC_TUNE_LINE_LINES 7 /* lines (image columns / rows) per CTA of the line pass, 1 .. 8; 0 (default) = by raster
+                               * size: 1 up to 320, 3 above.  Line k of CTA y has centre-out rank k * G + y, G = CTAs per
+                               * (sample, axis) */
+#define HOC_TUNE_LINE_FOLD 8  /* 1 (default) / 0: odd k take rank k * G + (G - 1 - y) instead -- a heavy central line
+                               * shares its CTA with a light outer one */
 int hoc_set_tuning(int key, int value);
 
 /* Number of launches of one kernel (or of all kernels, kernel_id = -1) since the library was loaded. */

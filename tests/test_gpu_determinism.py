@@ -82,7 +82,8 @@ def test_tuning_switches_do_not_change_the_result():
     """hoc_set_tuning switches that only change HOW the frame-pair step is executed must not change its result, bit
     for bit in the reproducible mode: programmatic dependent launch of its kernels (HOC_TUNE_PDL), and the texture
     gradient through the cover pass instead of the line pass's row CTAs (HOC_TUNE_TEX_IN_LINE = 0: scan pass lists the
-    pixels, three gradient planes, hoc_raster_bwd_cover_kernel)."""
+    pixels, three gradient planes, hoc_raster_bwd_cover_kernel), and several image lines per CTA of the line pass
+    (HOC_TUNE_LINE_LINES / HOC_TUNE_LINE_FOLD)."""
     import helpers
     S, B = 128, 3
     dev = torch.device("cuda:0")
@@ -96,14 +97,21 @@ def test_tuning_switches_do_not_change_the_result():
 
     with _lib.deterministic(True):
         base = run()
-        for key, value, back in ((_lib.HOC_TUNE_PDL, 1, 0), (_lib.HOC_TUNE_TEX_IN_LINE, 0, 1)):
-            _lib.check(L.hoc_set_tuning(key, value), "hoc_set_tuning")
+        LINES, FOLD = _lib.HOC_TUNE_LINE_LINES, _lib.HOC_TUNE_LINE_FOLD
+        for settings in (((_lib.HOC_TUNE_PDL, 1, 0),), ((_lib.HOC_TUNE_TEX_IN_LINE, 0, 1),),
+                         # several image lines per CTA of the line pass (3 does not divide 128: ragged last CTA), folded
+                         # (the default) or not; 0 = by raster size (here: 1)
+                         ((LINES, 1, 0),), ((LINES, 2, 0), (FOLD, 0, 1)), ((LINES, 3, 0),), ((LINES, 4, 0),),
+                         ((LINES, 8, 0), (FOLD, 0, 1))):
+            for key, value, _ in settings:
+                _lib.check(L.hoc_set_tuning(key, value), "hoc_set_tuning")
             try:
                 other = run()
             finally:
-                _lib.check(L.hoc_set_tuning(key, back), "hoc_set_tuning")
+                for key, _, back in settings:
+                    _lib.check(L.hoc_set_tuning(key, back), "hoc_set_tuning")
             for a, b in zip(base, other):
-                assert torch.equal(a, b), (key, value)
+                assert torch.equal(a, b), settings
         # ... and neither does asking for the loss only (flows / flow masks not handed out: written sparsely)
         loss, res, v1 = helpers.pair_step(sc, S, (S, 96), dev, False, True, False, loss_only=True)
         loss.backward()
