@@ -474,16 +474,6 @@ def run_native(args, rank, world, local_rank):
         "mesh_scatter": nf * 36 + nf2 * 36 + 2 * Bp * Fm * 24 + 2 * 2 * Bp * V * 12,
         "pair_back": 2 * 2 * Bp * V * 12 + 2 * Bp * V * 12 + Bp * V * 12,
     }
-    table = []
-    step_ms = ms / args.steps
-    for name, v in per_kernel.items():
-        avg = sum(v) / len(v)
-        ab = algo.get(name)
-        table.append({"kernel": name, "launches_per_step": len(v) / probe_steps, "avg_ms": avg,
-                      "share_of_step": sum(v) / probe_steps / step_ms,
-                      "algorithmic_bytes_per_launch": ab,
-                      "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
-    table.sort(key=lambda r: -r["share_of_step"])
     kname = {"raster_zbuf": "hoc_raster_zbuf_kernel", "raster_resolve": "hoc_raster_resolve4_kernel",
              "raster_bwd_pixel": "hoc_raster_bwd_scan_pair_kernel",
              "raster_bwd_cover": "hoc_raster_bwd_cover_kernel", "raster_backward": "hoc_raster_bwd_depth_kernel",
@@ -491,6 +481,17 @@ def run_native(args, rank, world, local_rank):
              "flow_finalize": "hoc_flow_finalize_warp_kernel", "mesh_scatter": "hoc_mesh_scatter_kernel",
              "pair_front": "hoc_pair_front_kernel", "pair_back": "hoc_pair_back_kernel",
              "pair_loss": "hoc_pair_loss_mean_kernel"}
+    table = []
+    step_ms = ms / args.steps
+    for name, v in per_kernel.items():
+        avg = sum(v) / len(v)
+        ab = algo.get(name)
+        table.append({"kernel": name, "launches_per_step": len(v) / probe_steps, "avg_ms": avg,
+                      "cupti_ms": None,  # (filled in by the cross-check at the very end of the run)
+                      "share_of_step": sum(v) / probe_steps / step_ms,
+                      "algorithmic_bytes_per_launch": ab,
+                      "achieved_gbs": (ab / (avg * 1e-3) / 1e9) if ab else None})
+    table.sort(key=lambda r: -r["share_of_step"])
     traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "kernel_traffic_r2.json")
     if os.path.exists(tpath):
@@ -568,6 +569,7 @@ def run_native(args, rank, world, local_rank):
             "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms,
             "share_of_step": bwd_ms / step_ms if bwd_ms else None,
             "launches_timed": len(group_ms), "sum_of_per_kernel_brackets_ms": bwd_ms_kernels,
+            "cupti": None,  # (filled in by the cross-check at the very end of the run)
             "event_pair": ({"cost_ms_per_step": bracket_cost_ms, "plain_step_ms": median(cal_plain),
                             "bracketed_step_ms": median(cal_inst),
                             "frac_net": ((bwd_bytes / ((bwd_ms - bracket_cost_ms) * 1e-3) / 1e9 / peak)
@@ -587,6 +589,32 @@ def run_native(args, rank, world, local_rank):
         "roofline_dominant": roof(dom),
         "kernels": table,
     }
+    def cupti_crosscheck(out):
+        """Cross-check, NOT a bench value: CUPTI durations (torch.profiler) of the kernels in 20 plain replays of the
+        captured step -- what the kernels take without event nodes around them (profiles/timeline.py prints the same as a
+        timeline).  Runs after everything else has been measured: the profiler stays loaded in the process."""
+        durs = {}
+        with torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CUDA]) as prof:
+            for i in range(20):
+                graphed_step(i)
+            torch.cuda.synchronize()
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA and "hoc_" in ev.name:
+                nm = ev.name.split("(")[0].split("<")[0].replace("void ", "").strip()
+                durs.setdefault(nm, []).append((ev.time_range.end - ev.time_range.start) * 1e-3)
+        for r in out["kernels"]:
+            v = durs.get(kname.get(r["kernel"], r["kernel"]))
+            r["cupti_ms"] = (sum(v) / len(v)) if v else None
+        rows = [r for r in out["kernels"] if r["kernel"] in ("raster_bwd_pixel", "raster_bwd_cover", "raster_backward",
+                                                             "raster_bwd_line")]
+        if rows and all(r["cupti_ms"] for r in rows):
+            t = sum(r["cupti_ms"] * r["launches_per_step"] for r in rows)
+            out["roofline"]["cupti"] = {
+                "launch_ms": t, "frac": bwd_bytes / (t * 1e-3) / 1e9 / peak,
+                "note": "cross-check only (taken under torch.profiler after everything else was measured, so not a bench "
+                        "value): sum of the CUPTI durations of the same launches in plain replays of the captured step"}
+
+    out["_cupti_crosscheck"] = cupti_crosscheck  # (main() runs it last and removes the key)
     return out
 
 
@@ -1194,6 +1222,12 @@ def main():
                 out["head_graph"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
+        crosscheck = out.pop("_cupti_crosscheck", None)
+        if crosscheck is not None and world == 1:
+            try:
+                crosscheck(out)
+            except Exception as exc:  # a cross-check must never cost the bench line
+                out["roofline"]["cupti"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
         _emit(out)
     if world > 1:
         dist.destroy_process_group()
