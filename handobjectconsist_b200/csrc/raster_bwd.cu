@@ -834,7 +834,7 @@ struct HocLineScan {
  * per-pixel edge work and queueing the outward scans on their lines, a line pass draining the queues: six dependent
  * loads, a 25 MB queue workspace and 40 us against 31.)
  */
-template <int CH>
+template <int CH, bool MULTI>
 __global__ void LN_BOUNDS
 hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index_map,
                             const float *__restrict__ rgb, const float *__restrict__ g_rgb,
@@ -867,11 +867,13 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
     const bool TEX = grad_textures != nullptr && axis == 1 && has_rgb;
     if (!K4 && !TEX)
         return;
-    /* level 1: the spans of the pixels that matter on this CTA's lines (covered or with an incoming gradient: the scan
-     * pass), all fetched at once.  A CTA runs `lines` lines (HOC_TUNE_LINE_LINES; 1: grid.y = S): line k of CTA y has
-     * centre-out rank k * G + y (G = grid.y) -- or, folded, k * G + (G - 1 - y) for odd k, which pairs a heavy central
-     * line with a light outer one -- so that an empty border line costs a loop iteration instead of a CTA. */
-    if (tid < lines) {
+    /* level 1: the span of the pixels that matter on a line (covered or with an incoming gradient: the scan pass).
+     * MULTI: a CTA runs `lines` lines (HOC_TUNE_LINE_LINES), their spans fetched at once: line k of CTA y has centre-out
+     * rank k * G + y (G = grid.y) -- or, folded, k * G + (G - 1 - y) for odd k, which pairs a heavy central line with a
+     * light outer one -- so that an empty border line costs a loop iteration instead of a CTA.  (One line per CTA is its
+     * own instantiation: the shared-memory round trip of the spans and the barrier cost the 10 000 empty CTAs of a
+     * 256^2 step 2 us.) */
+    if (MULTI && tid < lines) {
         const int G = gridDim.y;
         const int li = tid * G + ((fold && (tid & 1)) ? G - 1 - (int)blockIdx.y : (int)blockIdx.y);
         int lo_ = 1, hi_ = 0, d0_ = 0;
@@ -886,11 +888,23 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
         s_span[tid][2] = d0_;
     }
     const int32_t *idx = face_index_map + (long)b * S * S;
-    for (int ln = 0; ln < lines; ln++) {
-    __syncthreads(); /* the spans are written; every warp is done with the previous line's staged pixels */
-    const int lo = s_span[ln][0], hi = s_span[ln][1], d0 = s_span[ln][2];
-    if (lo > hi)
-        continue;
+    for (int ln = 0; ln < (MULTI ? lines : 1); ln++) {
+    int lo, hi, d0;
+    if (MULTI) {
+        __syncthreads(); /* the spans are written; every warp is done with the previous line's staged pixels */
+        lo = s_span[ln][0];
+        hi = s_span[ln][1];
+        d0 = s_span[ln][2];
+        if (lo > hi)
+            continue;
+    } else {
+        const int *e = ext + (long)b * 4 * S;
+        d0 = hoc_centre_out(blockIdx.y, S);
+        lo = S - e[(axis == 0 ? EXT_COL_LO : EXT_ROW_LO) * S + d0];
+        hi = e[(axis == 0 ? EXT_COL_HI : EXT_ROW_HI) * S + d0] - 1;
+        if (lo > hi)
+            return;
+    }
     const int len = hi - lo + 1;
 
     /* level 2: the line */
@@ -1105,8 +1119,9 @@ hoc_raster_bwd_line_kernel(const float *__restrict__ faces, const int32_t *__res
 static int g_cover_ctas = 296;
 static int g_tex_in_line = 1; /* the line pass's row CTAs also run the (vertex-value) texture gradient (HOC_TUNE_TEX_IN_LINE) */
 /* lines per CTA of the line pass and the way they are dealt (HOC_TUNE_LINE_LINES / _FOLD).  0: by raster size -- one line
- * per CTA up to 320 (measured at 16 pairs of 256^2: 119.8 us per step with 1, 120.2 / 120.5 / 121.4 with 2 / 3 / 4 folded;
- * unfolded 121.3 / 125.2 / 139.2 with 2 / 4 / 8), three folded lines above (32 pairs of 480 x 270: 494.4 -> 483.5 us) */
+ * per CTA up to 320 (measured at 16 pairs of 256^2, all through the MULTI instantiation: 119.8 us per step with 1,
+ * 120.2 / 120.5 / 121.4 with 2 / 3 / 4 folded; unfolded 121.3 / 125.2 / 139.2 with 2 / 4 / 8; the MULTI = false
+ * instantiation is another 2 us faster), three folded lines above (32 pairs of 480 x 270: 494.4 -> 483.5 us) */
 static int g_line_lines = 0, g_line_fold = 1;
 static int g_line_threads = 128, g_line_seg = 0; /* seg 0: by raster size (16 pixels up to 320, 32 above: 176 -> 163 us at 32 x 480^2) */
 
@@ -1144,16 +1159,15 @@ static cudaError_t hoc_launch_line(const float *faces, const int32_t *face_index
 {
     /* two float4 and one int per staged pixel, + padding for the unrolled chunk loop: 9.8 KB at S = 256, 74 KB at 2048 */
     const size_t smem = ((size_t)S + LN_PAD) * (2 * sizeof(float4) + sizeof(int));
+    const int lines = g_line_lines > 0 ? g_line_lines : (S > 320 ? 3 : 1);
+    auto kernel = lines > 1 ? hoc_raster_bwd_line_kernel<CH, true> : hoc_raster_bwd_line_kernel<CH, false>;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(hoc_raster_bwd_line_kernel<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess)
             return e;
     }
-    const int lines = g_line_lines > 0 ? g_line_lines : (S > 320 ? 3 : 1);
     HOC_LAUNCH(HOC_K_RASTER_BWD_LINE, st,
-               (hoc_launch_pdl((hoc_raster_bwd_line_kernel<CH>), dim3(B + k4_samples, (S + lines - 1) / lines),
-                               g_line_threads, smem, st, faces,
+               (hoc_launch_pdl(kernel, dim3(B + k4_samples, (S + lines - 1) / lines), g_line_threads, smem, st, faces,
                                face_index_map, rgb, grad_rgb, g_alpha, F, S, eps, layout, use_alpha, w.ext,
                                2.0f / (float)S, grad_faces, w.det_gf, k4_samples, g_channels, weight_map, depth_map,
                                grad_textures, w.det_gt, lines, g_line_fold)));
