@@ -451,10 +451,11 @@ def run_native(args, rank, world, local_rank):
         "raster_zbuf": nf2 * 36 + npx2 * 8,                       # faces in, 8-byte depth/face key per pixel
         # key in; idx4 + alpha4 + rgb12 out; at the covered pixels face + vertex values in, depth4 + weights12 out
         "raster_resolve": npx2 * (8 + 20) + int(c * npx2) * (36 + 36 + 16),
-        # finalize + warp, both directions: alpha4 + rgb8 in, flow8 + mult4 + valid1 + flow_mask2 out per pixel; at
-        # covered pixels the ignore / occlusion look-ups (idx4 + 2 x (alpha4 + rgb8 + idx4)) and the warp's operands
-        # (source 12, target 12, jitter 4 + 4)
-        "flow_finalize": 2 * ncrop * (12 + 15) + int(c * 2 * ncrop) * (4 + 32 + 32),
+        # finalize + warp, both directions, in the captured step (loss_only: sparse outputs): alpha4 + rgb8 in, valid1 out
+        # per pixel; at covered pixels the ignore / occlusion look-ups (idx4 + 2 x (alpha4 + rgb8 + idx4)), the warp's
+        # operands (source 12, target 12, jitter 4 + 4) and flow8 + mult4 out (with every output dense, as the eager
+        # API hands them out: + flow8 + mult4 + flow_mask2 = 14 B per pixel more)
+        "flow_finalize": 2 * ncrop * (12 + 1) + int(c * 2 * ncrop) * (4 + 32 + 32 + 12),
         # warp backward fused with the finalize backward: valid1 in, grad_rgb 12 out per raster pixel; flow8 + mult4 +
         # source 12 + target 12 at the valid pixels
         "warp_photo_bwd": 2 * ncrop * 1 + npx2 * 12 + int(c * 2 * ncrop) * 36,
