@@ -93,3 +93,26 @@ def test_batch_masked_mean_loss_contract():
     assert batch_masked_mean_loss(d, full)[0].item() == pytest.approx(float((d[0] * full[0]).sum()) / 6)
     soft = torch.full((2, 3, 2, 2), 0.01)                                             # soft weights summing to 0.12 < 1
     assert batch_masked_mean_loss(d, soft)[0].item() == pytest.approx(float(d[0].mean()), rel=1e-5)
+
+
+def test_line_pass_deals_every_line_once():
+    """The line pass of the rasterizer backward (csrc/raster_bwd.cu, hoc_raster_bwd_line_kernel) hands image lines to
+    CTAs by centre-out rank: with `lines` lines per CTA (HOC_TUNE_LINE_LINES), line k of CTA y has rank k * G + y -- or,
+    folded (HOC_TUNE_LINE_FOLD), k * G + (G - 1 - y) for odd k -- with G = ceil(S / lines) CTAs; ranks >= S are skipped.
+    Restated here (same integer formulas, hoc_centre_out of csrc/hoc_common.cuh included): every line of the raster is
+    visited exactly once, whatever S (ragged last CTA), `lines` and the fold."""
+    def centre_out(k, n):  # hoc_centre_out: lines from the image centre outwards
+        return (n >> 1) + (-((k + 1) >> 1) if (k & 1) else (k >> 1))
+
+    for S in (4, 63, 64, 128, 255, 256, 480, 1400):
+        assert sorted(centre_out(k, S) for k in range(S)) == list(range(S))
+        for lines in range(1, 9):
+            G = (S + lines - 1) // lines
+            for fold in (0, 1):
+                seen = []
+                for y in range(G):
+                    for k in range(lines):
+                        li = k * G + ((G - 1 - y) if (fold and (k & 1)) else y)
+                        if li < S:
+                            seen.append(centre_out(li, S))
+                assert sorted(seen) == list(range(S)), (S, lines, fold)
