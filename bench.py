@@ -581,8 +581,9 @@ def run_native(args, rank, world, local_rank):
                                     "that cost fell inside the bracket, so the kernels' own fraction lies between the two"}
                            if (bracket_cost_ms is not None and group_ms) else None),
             "timing": "ONE pair of CUDA events (external event nodes of an instrumented copy of the captured graph) around the "
-                      "two launches of hoc_pair_backward_raster; the pair adds ~4 us (profiles/timeline_r2.txt holds the "
-                      "CUPTI durations of an un-instrumented replay)",
+                      "two launches of hoc_pair_backward_raster; the pair adds ~4 us inside the bracket (`cupti` below; "
+                      "profiles/timeline_r2.txt holds the CUPTI durations of an un-instrumented replay) and "
+                      "`event_pair.cost_ms_per_step` to the step",
             "note": "scan + line pass over the stacked batch of both renders (one launch each); bytes: the render "
                     "with the pseudo-gradient (H*W*28 + 2F*108 per sample) + the texture-only render (H*W*16 + 2F*72).  "
                     "The scan pass also computes the backward of pair_consist (fused in; its own operand bytes are NOT "
