@@ -517,7 +517,8 @@ def run_native(args, rank, world, local_rank):
         if r is None:
             return None
         return {"kernel": kname.get(r["kernel"], r["kernel"]), "bound": "hbm", "achieved": r["achieved_gbs"], "peak": peak,
-                "unit": "GB/s", "frac": r["achieved_gbs"] / peak, "traffic": traffic_tab.get(kname.get(r["kernel"])),
+                "unit": "GB/s", "frac": r["achieved_gbs"] / peak, "frac_of_nominal_8000": r["achieved_gbs"] / 8000.0,
+                "traffic": traffic_tab.get(kname.get(r["kernel"])),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": r["algorithmic_bytes_per_launch"],
                 "avg_launch_ms": r["avg_ms"], "launches_timed": int(r["launches_per_step"] * probe_steps),
                 "share_of_step": r["share_of_step"], "timing": timing_note}
@@ -566,7 +567,9 @@ def run_native(args, rank, world, local_rank):
         "roofline": {
             "kernel": "rasterizer backward: " + " + ".join(sorted({kname[r["kernel"]] for r in bwd})), "bound": "hbm",
             "achieved": (bwd_bytes / (bwd_ms * 1e-3) / 1e9) if bwd_ms > 0 else None, "peak": peak, "unit": "GB/s",
-            "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak) if bwd_ms > 0 else None, "traffic": bwd_traffic,
+            "frac": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / peak) if bwd_ms > 0 else None,
+            "frac_of_nominal_8000": (bwd_bytes / (bwd_ms * 1e-3) / 1e9 / 8000.0) if bwd_ms > 0 else None,  # 
+            "traffic": bwd_traffic,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": bwd_bytes, "avg_launch_ms": bwd_ms,
             "share_of_step": bwd_ms / step_ms if bwd_ms else None,
             "launches_timed": len(group_ms), "sum_of_per_kernel_brackets_ms": bwd_ms_kernels,
